@@ -1,0 +1,294 @@
+/* libmonte_gpu — C ABI of the B200-native CBCT engine (MC photon transport + FDK).
+ *
+ * The reference (Tomato27/Monte) has no plugin/FFI layer: every program is one
+ * main().  The seams this ABI replaces are
+ *   - FDK:  recon/bp3d20.cpp:29 (fread of the map) .. :171 (first writeRawFile);
+ *           same span in recon/bp3d20_325.cpp:30..:181 and recon/fbp2.cpp:28..:157
+ *   - MC:   monte_cu/CBCT_real325im.cu:232-248 (RandStateGenerator + projection
+ *           launch + the two D2H copies) and :258-288 (counts -> -log map);
+ *           CPU form monte_cpp/CBCT_real2.cpp:169-595 (the view/pixel/photon loops)
+ *   - tables: monte_cpp/CBCT_real2.cpp:633-668 (readcsv), CBCT_real325im.cu:299-355
+ * Plain pointers and sizes only.  All host buffers are caller-owned; outputs are
+ * overwritten; inputs are const.  Every call returns 0 on success or a negative
+ * MONTE_E_* code (never exit()), with text in monte_gpu_last_error().
+ * Calls are blocking and not re-entrant (reference: single host thread,
+ * cudaThreadSynchronize after each launch, CBCT_real325im.cu:236,244).
+ *
+ * Lengths are cm, energies keV, angles degrees — the reference's units.
+ */
+#ifndef MONTE_GPU_H
+#define MONTE_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MONTE_GPU_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------ */
+#define MONTE_OK            0
+#define MONTE_E_ARG        -1   /* bad argument / inconsistent geometry          */
+#define MONTE_E_CUDA       -2   /* CUDA runtime error (text in last_error)       */
+#define MONTE_E_NOINIT     -3   /* monte_gpu_init not called                     */
+#define MONTE_E_NODEV      -4   /* no usable sm_100 device                        */
+#define MONTE_E_NOMEM      -5
+#define MONTE_E_IO         -6   /* table / raw file problems (host helpers)      */
+
+/* ---- library lifetime --------------------------------------------------- */
+/* Selects the device of this process (one process per GPU).  ndev must be 1 in
+ * this ABI version; ids[0] is the CUDA ordinal (ids == NULL -> device 0).      */
+int  monte_gpu_init(int ndev, const int *ids);
+void monte_gpu_shutdown(void);
+const char *monte_gpu_last_error(void);
+int  monte_gpu_abi_version(void);
+/* number of SMs of the bound device (grid sizing is reported in stats) */
+int  monte_gpu_sm_count(void);
+
+/* ======================================================================== */
+/*  FDK reconstruction  (replaces bp3d20 / bp3d20_325 / fbp2)               */
+/* ======================================================================== */
+
+/* weight_mode */
+#define MONTE_FDK_REFERENCE 0  /* reproduces the shipped arithmetic incl. its quirks:
+                                  cosine weight and distance weight use weight_dist
+                                  (=Dod=60, bp3d20.cpp:40,159), tan() of the angle in
+                                  degrees taken as radians (bp3d20.cpp:137), fixed
+                                  filter_scale (bp3d20.cpp:68), out_scale fudge (:160) */
+#define MONTE_FDK_TEXTBOOK  1  /* Feldkamp 1984: weights with Dsd / Dso, ramp scaled by
+                                  the detector pitch, no fudge factors                 */
+
+/* coord_mode: association of the detector-coordinate expression (1-ulp effects) */
+#define MONTE_FDK_COORD_SCALE_AFTER  0  /* y = -inv_du*(u - half_u)   bp3d20.cpp:123-124     */
+#define MONTE_FDK_COORD_SCALE_BEFORE 1  /* y = -(u*inv_du - nu/2)     bp3d20_325.cpp:134-135 */
+
+typedef struct monte_fdk_geom {
+    /* projections: map[view][iu][iv], iu = transaxial (the filtered direction,
+       "zeta"/"c" in bp3d20.cpp:37,67), iv = axial ("p"/"d").  Filtered output is
+       written transposed, filtered[view][iv][iu] (bp3d20.cpp:70).                 */
+    int32_t n_views;
+    int32_t nu, nv;
+    double  du, dv;            /* detector pitch: 0.5 (bp3d20) or 0.1 (bp3d20_325)   */
+    double  half_u, half_v;    /* 16.25: detector half-extent (bp3d20.cpp:40,116)    */
+    double  dso, dsd;          /* 160, 220  (bp3d20.cpp:85,107)                      */
+    double  weight_dist;       /* 60 in REFERENCE mode (Q10); ignored in TEXTBOOK    */
+    double  filter_scale;      /* 0.5 (bp3d20.cpp:68)                                */
+    double  out_scale;         /* 2.7 (bp3d20.cpp:160)                               */
+    double  out_scale2;        /* 1, or 5 for bp3d20_325.cpp:170 ((o*2.7)*5)         */
+    double  angle0_deg;        /* first view angle                                   */
+    double  angle_step_deg;    /* "beta_span" = 1 (bp3d20.cpp:82)                    */
+    /* volume: vol_xy[z][t][s], X = x0 + vox*s, Y = y0 - vox*t, Z = z0 - vox*z
+       (bp3d20.cpp:96-98: -12.8+0.1s, 12.8-0.1t, 12.8-0.1z)                          */
+    int32_t nx, ny, nz;
+    double  vox;
+    double  x0, y0, z0;
+    /* region actually reconstructed (everything else stays 0); the shipped loops
+       run s in [125,130) only (bp3d20.cpp:93).                                      */
+    int32_t s_begin, s_end, t_begin, t_end, z_begin, z_end;
+    /* sphere mask (bp3d20.cpp:145): (z-cz)^2+(t-ct)^2+(s-cs)^2 <= r2 ; r2 < 0 = off  */
+    int32_t mask_cs, mask_ct, mask_cz;
+    int64_t mask_r2;
+    int32_t weight_mode;       /* MONTE_FDK_REFERENCE / MONTE_FDK_TEXTBOOK           */
+    int32_t coord_mode;        /* MONTE_FDK_COORD_*                                  */
+} monte_fdk_geom;
+
+typedef struct monte_fdk_stats {
+    double   ms_h2d, ms_filter, ms_backproject, ms_transpose, ms_d2h, ms_total;
+    uint64_t voxel_updates;    /* voxels in ROI x views                              */
+    uint64_t filter_macs;
+    int32_t  launches;         /* kernels launched by this call                      */
+    int32_t  sm_count;
+} monte_fdk_stats;
+
+/* Presets filling every field with the literals of the shipped programs. */
+void monte_fdk_geom_bp3d20(monte_fdk_geom *g);      /* recon/bp3d20.cpp        */
+void monte_fdk_geom_bp3d20_325(monte_fdk_geom *g);  /* recon/bp3d20_325.cpp    */
+
+/* Whole pipeline on host buffers (the drop-in for bp3d20.cpp:29-171).
+ * map      [n_views][nu][nv]  float32, in
+ * filtered [n_views][nv][nu]  float32, out, nullable   ("map_out", bp3d20.cpp:187)
+ * vol_xy   [nz][ny][nx]       float32, out             ("image_xy")
+ * vol_zy   [nx][ny][nz]       float32, out, nullable   ("image_zy", bp3d20.cpp:161)  */
+int monte_gpu_fdk(const monte_fdk_geom *g, const float *map, float *filtered,
+                  float *vol_xy, float *vol_zy, monte_fdk_stats *stats);
+
+/* Device-resident stages (pointers are CUDA device pointers on the bound device,
+ * stream is a cudaStream_t passed as void*; asynchronous w.r.t. the host).
+ * The filtered projections live in a padded row layout:
+ *   rows = n_views*nv + 2, row pitch = monte_gpu_fdk_filtered_pitch(g) floats,
+ *   element [r][nu] duplicates [r+1][0] and the two trailing rows are zero, so the
+ *   reference's inclusive bilinear bound (bp3d20.cpp:152-156, reads one past the
+ *   row / view) is reproduced by plain row addressing.                             */
+size_t monte_gpu_fdk_filtered_pitch(const monte_fdk_geom *g);           /* floats */
+size_t monte_gpu_fdk_filtered_elems(const monte_fdk_geom *g);           /* floats */
+int monte_gpu_fdk_filter_dev(const monte_fdk_geom *g, const float *d_map,
+                             int view_begin, int view_end,
+                             float *d_filtered_padded, void *stream);
+/* fix up the duplicated column / trailing rows after views were written or gathered */
+int monte_gpu_fdk_pad_dev(const monte_fdk_geom *g, float *d_filtered_padded, void *stream);
+/* Backproject all views into z-slices [z_lo, z_hi) of the volume;
+ * d_vol_slab points at slice z_lo, layout [z_hi-z_lo][ny][nx].  Overwrites.        */
+int monte_gpu_fdk_backproject_dev(const monte_fdk_geom *g, const float *d_filtered_padded,
+                                  int z_lo, int z_hi, float *d_vol_slab, void *stream);
+/* vol_zy[s][t][z] = vol_xy[z][t][s] */
+int monte_gpu_fdk_transpose_dev(const monte_fdk_geom *g, const float *d_vol_xy,
+                                float *d_vol_zy, void *stream);
+/* copy padded -> dense [n_views][nv][nu] (device to device) */
+int monte_gpu_fdk_unpad_dev(const monte_fdk_geom *g, const float *d_filtered_padded,
+                            float *d_filtered_dense, void *stream);
+
+/* 2-D fan-beam FBP (recon/fbp2.cpp): sino[n_views][nu] -> filtered[n_views][nu],
+ * image[ny][nx]; nearest-neighbour detector lookup (fbp2.cpp:126,147), views start
+ * at view_first (=1 in the shipped loop, fbp2.cpp:89), out_scale 1.7 (:148).
+ * Uses g->nu, du, half_u, dso, dsd, weight_dist, filter_scale, out_scale, angles,
+ * nx, ny, vox, x0, y0, s/t ROI.                                                    */
+void monte_fdk_geom_fbp2(monte_fdk_geom *g);
+int monte_gpu_fbp2(const monte_fdk_geom *g, int view_first, const float *sino,
+                   float *filtered, float *image, monte_fdk_stats *stats);
+
+/* ======================================================================== */
+/*  Monte-Carlo photon transport (replaces the `projection` kernel)         */
+/* ======================================================================== */
+
+#define MONTE_MC_MAX_MATERIALS 8
+#define MONTE_MC_TABLE_ROWS    201   /* index = keV, 0..200 (CBCT_real325im.cu:76-78) */
+
+/* cross-section tables per material, index (int)(E+0.5) (CBCT_real325im.cu:501,627-630).
+ * Values are mass coefficients cm^2/g; mu = value * density.                        */
+typedef struct monte_mc_xs {
+    int32_t n_materials;                 /* label m (1..n) uses entry m-1; label 0 = air;
+                                            labels > n use the last entry (the reference's
+                                            final else = PMMA, CBCT_real325im.cu:640-646) */
+    float   density[MONTE_MC_MAX_MATERIALS];                       /* g/cm^3 */
+    float   coh  [MONTE_MC_MAX_MATERIALS][MONTE_MC_TABLE_ROWS];    /* coherent           */
+    float   compt[MONTE_MC_MAX_MATERIALS][MONTE_MC_TABLE_ROWS];    /* incoherent         */
+    float   photo[MONTE_MC_MAX_MATERIALS][MONTE_MC_TABLE_ROWS];    /* photoelectric "ab" */
+    float   total[MONTE_MC_MAX_MATERIALS][MONTE_MC_TABLE_ROWS];    /* "mua"              */
+} monte_mc_xs;
+
+/* voxelised label volume, x fastest (make_image01.cpp:20: g[k*L*M + j*M + i]).
+ * Voxel index along an axis = (int)floor((p - origin)/pitch); the reference's two
+ * addressing forms map onto it: CBCT_real325im.cu:921 int((p+10)*10) -> origin -10;
+ * CBCT_real2.cpp:771 rint(p*10)+90 -> origin -(90+0.5)*0.1.
+ * Lookups happen only inside the clip box (CBCT_real2.cpp:770; the tight box around
+ * the phantom); outside it the photon flies straight (air).                          */
+typedef struct monte_mc_volume {
+    int32_t nx, ny, nz;
+    double  pitch;
+    double  origin[3];
+    double  clip_lo[3], clip_hi[3];
+} monte_mc_volume;
+
+#define MONTE_MC_SOURCE_PENCIL 0  /* one pencil per pixel centre, `per` photons each
+                                     (CBCT_real325im.cu:464-527; survey Q2)             */
+#define MONTE_MC_SOURCE_CONE   1  /* same stratification, aim point jittered uniformly
+                                     inside the pixel: a sampled cone beam              */
+
+typedef struct monte_mc_geom {
+    int32_t n_views;
+    double  angle0_deg, angle_step_deg;  /* view v at angle0 + v*step (1 deg, :462,508) */
+    int32_t ny, nx;          /* detector pixels: ny transaxial ("i"), nx axial ("j")    */
+    double  pixel;           /* 0.1 (GPU) / 0.5 (CPU)                                    */
+    double  half;            /* detector_height 16.25 (CBCT_real325im.cu:459)            */
+    double  dso, dod;        /* 160, 60                                                  */
+    int32_t source_mode;
+    int32_t max_scatter;     /* ScatterNUM = 5 (CBCT_real325im.cu:7)                     */
+} monte_mc_geom;
+
+/* spectrum: n_bins == 0 -> mono-energetic at mono_keV (as shipped: 140, survey Q3);
+ * else cdf[0..n_bins], cdf[0]=0, cdf[n_bins]=1, E = (k+1)*bin_keV for
+ * cdf[k] <= u <= cdf[k+1]  (CBCT_real325im.cu:493-497, bin 0.5 keV).                   */
+typedef struct monte_mc_spectrum {
+    int32_t n_bins;
+    double  bin_keV;
+    double  mono_keV;
+    const float *cdf;
+} monte_mc_spectrum;
+
+typedef struct monte_mc_stats {
+    uint64_t histories;
+    uint64_t primaries;        /* histories that reached the detector unscattered        */
+    uint64_t scatter_detected; /* tallied to image5 after >=1 interaction                */
+    uint64_t absorbed;         /* photoelectric                                          */
+    uint64_t interactions;     /* all accepted collisions                                */
+    uint64_t coherent, compton;
+    uint64_t woodcock_steps;   /* tentative collisions sampled (N-bar * histories)       */
+    double   sum_e_primary;    /* keV, for mean detected energy                          */
+    double   sum_e_scatter;
+    double   ms_h2d, ms_kernel, ms_d2h, ms_total;
+    int32_t  launches;
+    int32_t  sm_count;
+} monte_mc_stats;
+
+/* Whole simulation on host buffers.  photons_per_pixel is the reference's `per`
+ * (CBCT_real325im.cu:182): histories per view = per*ny*nx.  History id
+ * h = (view*ny*nx + pixel)*per + n draws from Philox4x32-10 stream (seed, h), so the
+ * result is independent of how histories are partitioned; [hist_begin, hist_end) of the
+ * per-view history range lets several processes split a view (0,0 = everything).
+ * image0 [n_views][ny][nx] int32: unscattered;  image5: unscattered + scattered
+ * (CBCT_real325im.cu:584-585,692,841).  labels: uint8 [nz][ny][nx].                    */
+int monte_gpu_simulate(const monte_mc_geom *g, const monte_mc_volume *vol,
+                       const uint8_t *labels, const monte_mc_xs *xs,
+                       const monte_mc_spectrum *spec, uint32_t photons_per_pixel,
+                       uint64_t seed, int view_begin, int view_end,
+                       int32_t *image0, int32_t *image5, monte_mc_stats *stats);
+
+/* Device-resident form: the scene is uploaded once, tallies accumulate into device
+ * int32 images [view_end-view_begin... indexed by absolute view][ny][nx].             */
+typedef struct monte_mc_scene monte_mc_scene;   /* opaque */
+int monte_gpu_scene_create(const monte_mc_geom *g, const monte_mc_volume *vol,
+                           const uint8_t *labels, const monte_mc_xs *xs,
+                           const monte_mc_spectrum *spec, monte_mc_scene **out);
+void monte_gpu_scene_destroy(monte_mc_scene *s);
+/* Run photons n in [n_begin, n_end) of every pixel of views [view_begin, view_end)
+ * and add into d_image0/d_image5 (device, [n_views][ny][nx], caller zeroes).
+ * d_stats: device uint64[16] accumulators (nullable), see monte_gpu_mc_stats_unpack. */
+int monte_gpu_simulate_dev(const monte_mc_scene *s, uint64_t seed,
+                           int view_begin, int view_end,
+                           uint32_t n_begin, uint32_t n_end, uint32_t photons_per_pixel,
+                           int32_t *d_image0, int32_t *d_image5,
+                           unsigned long long *d_stats, void *stream);
+#define MONTE_MC_STATS_WORDS 16
+void monte_gpu_mc_stats_unpack(const unsigned long long *h_words, monte_mc_stats *out);
+
+/* per-history fate records for history-coupled parity tests (debug; small runs).
+ * fate[h] = kind | bin<<8 | n_interactions<<28 ; kind: 1 primary, 2 scatter detected,
+ * 3 absorbed, 4 escaped undetected, 5 scatter budget exhausted.                        */
+int monte_gpu_simulate_fates(const monte_mc_scene *s, uint64_t seed, int view,
+                             uint32_t photons_per_pixel, uint32_t *fates /*host*/,
+                             float *energies /*host, nullable*/);
+
+/* counts -> line-integral map: c=min(c,per); c=max(c,1); map=-ln(c)+ln(per)
+ * (CBCT_real325im.cu:267-285; monte_cpp/map.cpp:19).                                   */
+int monte_gpu_counts_to_map(const int32_t *counts, size_t n, int32_t per, float *map);
+int monte_gpu_counts_to_map_dev(const int32_t *d_counts, size_t n, int32_t per,
+                                float *d_map, void *stream);
+
+/* Deterministic primary projection: map[view][iy][ix] = integral of mu along the ray
+ * from the source to the pixel centre at energy keV (the variance-free limit of
+ * -ln(image0/per)); exact voxel traversal.                                             */
+int monte_gpu_project_primary(const monte_mc_geom *g, const monte_mc_volume *vol,
+                              const uint8_t *labels, const monte_mc_xs *xs,
+                              double keV, int view_begin, int view_end, float *map);
+
+/* ---- host helpers shared by the C++ drivers (no GPU) ---------------------- */
+/* readcsv role (CBCT_real2.cpp:633-668): 200 rows "coh,compton,photo,total", UTF-8 BOM
+ * and CRLF tolerated, row r -> index r+1 (keV); index 0 is a copy of index 1.
+ * quirk_bom != 0 reproduces csvarray[0][1]=1.372 for every file (CBCT_real2.cpp:663).  */
+int monte_xs_load_csv(const char *path, int material, float density, int quirk_bom,
+                      monte_mc_xs *xs);
+/* make_fantom.cpp:10-19: n x n uint8 disc, (j-cy)^2+(k-cx)^2 <= r2 -> 1 */
+void monte_make_fantom(uint8_t *g, int n, int cy, int cx, int r2);
+/* make_image01.cpp:15-23: nx*ny*nz uint8 sphere */
+void monte_make_sphere(uint8_t *g, int nx, int ny, int nz, int cx, int cy, int cz, int r2);
+/* ctnum_to_mu role (ctnum_to_mu.cpp:55 computes mu_H2O and stops): HU -> mu(E) =
+ * mu_water(E)*(1+HU/1000) and a label segmentation by HU thresholds.                   */
+int monte_ctnum_to_mu(const float *hu, size_t n, const monte_mc_xs *xs, double keV,
+                      float hu_air_max, float hu_bone_min, float *mu, uint8_t *labels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MONTE_GPU_H */

@@ -1,0 +1,182 @@
+"""Thin ctypes layer over libmonte_gpu.so for tests, bench.py and the multi-GPU plumbing.
+
+There is no CPU fallback: if the library cannot be loaded, or no B200 is visible at init time,
+every entry point raises MonteError.  The oracle under oracle/ is never imported from here.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import (FdkGeom, FdkStats, McGeom, McSpectrum, McStats, McVolume, McXs)
+
+
+class MonteError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libmonte_gpu.so (no device needed) and declare the prototypes of include/monte_gpu.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_abi.LIB_PATH):
+        raise MonteError("libmonte_gpu.so not built (%s); run `python -m monte_b200.build` — "
+                         "there is no CPU fallback" % _abi.LIB_PATH)
+    lib = C.CDLL(_abi.LIB_PATH)
+    vp, i32, u32, u64, sz = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, C.c_size_t
+    fp = C.POINTER(C.c_float)
+    ip = C.POINTER(C.c_int32)
+    G = C.POINTER(FdkGeom)
+    proto = {
+        "monte_gpu_init": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+        "monte_gpu_shutdown": (None, []),
+        "monte_gpu_last_error": (C.c_char_p, []),
+        "monte_gpu_abi_version": (C.c_int, []),
+        "monte_gpu_sm_count": (C.c_int, []),
+        "monte_fdk_geom_bp3d20": (None, [G]),
+        "monte_fdk_geom_bp3d20_325": (None, [G]),
+        "monte_fdk_geom_fbp2": (None, [G]),
+        "monte_gpu_fdk": (C.c_int, [G, vp, vp, vp, vp, C.POINTER(FdkStats)]),
+        "monte_gpu_fdk_filtered_pitch": (sz, [G]),
+        "monte_gpu_fdk_filtered_elems": (sz, [G]),
+        "monte_gpu_fdk_filter_dev": (C.c_int, [G, vp, C.c_int, C.c_int, vp, vp]),
+        "monte_gpu_fdk_pad_dev": (C.c_int, [G, vp, vp]),
+        "monte_gpu_fdk_backproject_dev": (C.c_int, [G, vp, C.c_int, C.c_int, vp, vp]),
+        "monte_gpu_fdk_transpose_dev": (C.c_int, [G, vp, vp, vp]),
+        "monte_gpu_fdk_unpad_dev": (C.c_int, [G, vp, vp, vp]),
+        "monte_gpu_fbp2": (C.c_int, [G, C.c_int, vp, vp, vp, C.POINTER(FdkStats)]),
+        "monte_gpu_simulate": (C.c_int, [C.POINTER(McGeom), C.POINTER(McVolume), vp, C.POINTER(McXs),
+                                         C.POINTER(McSpectrum), u32, u64, C.c_int, C.c_int, vp, vp,
+                                         C.POINTER(McStats)]),
+        "monte_gpu_scene_create": (C.c_int, [C.POINTER(McGeom), C.POINTER(McVolume), vp, C.POINTER(McXs),
+                                             C.POINTER(McSpectrum), C.POINTER(vp)]),
+        "monte_gpu_scene_destroy": (None, [vp]),
+        "monte_gpu_simulate_dev": (C.c_int, [vp, u64, C.c_int, C.c_int, u32, u32, u32, vp, vp, vp, vp]),
+        "monte_gpu_mc_stats_unpack": (None, [vp, C.POINTER(McStats)]),
+        "monte_gpu_simulate_fates": (C.c_int, [vp, u64, C.c_int, u32, vp, vp]),
+        "monte_gpu_counts_to_map": (C.c_int, [vp, sz, i32, vp]),
+        "monte_gpu_counts_to_map_dev": (C.c_int, [vp, sz, i32, vp, vp]),
+        "monte_gpu_project_primary": (C.c_int, [C.POINTER(McGeom), C.POINTER(McVolume), vp, C.POINTER(McXs),
+                                                C.c_double, C.c_int, C.c_int, vp]),
+        "monte_xs_load_csv": (C.c_int, [C.c_char_p, C.c_int, C.c_float, C.c_int, C.POINTER(McXs)]),
+        "monte_make_fantom": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
+        "monte_make_sphere": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+        "monte_ctnum_to_mu": (C.c_int, [vp, sz, C.POINTER(McXs), C.c_double, C.c_float, C.c_float, vp, vp]),
+    }
+    missing = []
+    for name, (res, args) in proto.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:           # header/library mismatch: tests/test_abi.py fails on this
+            missing.append(name)
+            continue
+        fn.restype = res
+        fn.argtypes = args
+    lib._monte_symbols = sorted(proto)
+    lib._monte_missing = missing
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise MonteError("libmonte_gpu error %d: %s" % (rc, load().monte_gpu_last_error().decode()))
+
+
+_inited_dev = None
+
+
+def init(device=0):
+    """Bind this process to one B200 (one process per GPU)."""
+    global _inited_dev
+    lib = load()
+    ids = (C.c_int * 1)(device)
+    _check(lib.monte_gpu_init(1, ids))
+    _inited_dev = device
+    return lib
+
+
+def shutdown():
+    global _inited_dev
+    if _lib is not None:
+        _lib.monte_gpu_shutdown()
+    _inited_dev = None
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+# ------------------------------------------------------------------ FDK, host buffers
+def fdk(g, proj, want_filtered=True, want_zy=False, out=None):
+    """monte_gpu_fdk on numpy (or pinned torch .numpy()) buffers.
+    Returns (filtered|None, vol_xy, vol_zy|None, stats dict)."""
+    lib = load()
+    proj = np.ascontiguousarray(proj, dtype=np.float32)
+    if proj.shape != (g.n_views, g.nu, g.nv):
+        raise MonteError("proj shape %r != (%d,%d,%d)" % (proj.shape, g.n_views, g.nu, g.nv))
+    filt = np.empty((g.n_views, g.nv, g.nu), np.float32) if want_filtered else None
+    vol = out if out is not None else np.empty((g.nz, g.ny, g.nx), np.float32)
+    vzy = np.empty((g.nx, g.ny, g.nz), np.float32) if want_zy else None
+    st = FdkStats()
+    _check(lib.monte_gpu_fdk(C.byref(g), _ptr(proj), _ptr(filt), _ptr(vol), _ptr(vzy), C.byref(st)))
+    return filt, vol, vzy, _abi.stats_dict(st)
+
+
+def fbp2(g, sino, view_first=1):
+    lib = load()
+    sino = np.ascontiguousarray(sino, dtype=np.float32)
+    filt = np.empty((g.n_views, g.nu), np.float32)
+    img = np.empty((g.ny, g.nx), np.float32)
+    st = FdkStats()
+    _check(lib.monte_gpu_fbp2(C.byref(g), view_first, _ptr(sino), _ptr(filt), _ptr(img), C.byref(st)))
+    return filt, img, _abi.stats_dict(st)
+
+
+# ------------------------------------------------------------------ FDK, device buffers (torch)
+def _stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def fdk_filtered_shape(g):
+    lib = load()
+    pitch = lib.monte_gpu_fdk_filtered_pitch(C.byref(g))
+    return (g.n_views * g.nv + 2, pitch)
+
+
+def fdk_filter_dev(g, d_map, d_filt, view_begin=0, view_end=None, stream=None, pad=True):
+    """d_map: cuda float32 [views][nu][nv]; d_filt: cuda float32 of fdk_filtered_shape(g)."""
+    lib = load()
+    ve = g.n_views if view_end is None else view_end
+    _check(lib.monte_gpu_fdk_filter_dev(C.byref(g), C.c_void_p(d_map.data_ptr()), view_begin, ve,
+                                        C.c_void_p(d_filt.data_ptr()), _stream_ptr(stream)))
+    if pad:
+        _check(lib.monte_gpu_fdk_pad_dev(C.byref(g), C.c_void_p(d_filt.data_ptr()), _stream_ptr(stream)))
+
+
+def fdk_pad_dev(g, d_filt, stream=None):
+    _check(load().monte_gpu_fdk_pad_dev(C.byref(g), C.c_void_p(d_filt.data_ptr()), _stream_ptr(stream)))
+
+
+def fdk_backproject_dev(g, d_filt, d_slab, z_lo=0, z_hi=None, stream=None):
+    lib = load()
+    zh = g.nz if z_hi is None else z_hi
+    _check(lib.monte_gpu_fdk_backproject_dev(C.byref(g), C.c_void_p(d_filt.data_ptr()), z_lo, zh,
+                                             C.c_void_p(d_slab.data_ptr()), _stream_ptr(stream)))
+
+
+def fdk_unpad_dev(g, d_filt, d_dense, stream=None):
+    _check(load().monte_gpu_fdk_unpad_dev(C.byref(g), C.c_void_p(d_filt.data_ptr()),
+                                          C.c_void_p(d_dense.data_ptr()), _stream_ptr(stream)))
+
+
+def fdk_transpose_dev(g, d_xy, d_zy, stream=None):
+    _check(load().monte_gpu_fdk_transpose_dev(C.byref(g), C.c_void_p(d_xy.data_ptr()),
+                                              C.c_void_p(d_zy.data_ptr()), _stream_ptr(stream)))

@@ -1,0 +1,65 @@
+// common.cuh — process-wide context and error plumbing of libmonte_gpu (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/monte_gpu.h"
+
+namespace monte {
+
+struct Context {
+    bool      inited = false;
+    int       device = 0;
+    int       sm_count = 0;
+    cudaStream_t stream = nullptr;     // library-owned stream for the host-buffer entry points
+    cudaStream_t copy_stream = nullptr; // second stream: D2H of finished slabs overlaps compute
+    // grow-only device scratch shared by the host-buffer entry points
+    void  *scratch[8] = {nullptr};
+    size_t scratch_bytes[8] = {0};
+};
+
+Context &ctx();
+void set_error(const char *fmt, ...);
+int  cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+// returns device pointer of at least `bytes` in slot `slot` (contents undefined), or nullptr
+void *scratch(int slot, size_t bytes);
+
+#define MONTE_CUDA(call)                                                        \
+    do {                                                                        \
+        cudaError_t _e = (call);                                                \
+        if (_e != cudaSuccess) return ::monte::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define MONTE_REQUIRE_INIT()                                                    \
+    do {                                                                        \
+        if (!::monte::ctx().inited) {                                           \
+            ::monte::set_error("monte_gpu_init has not been called");           \
+            return MONTE_E_NOINIT;                                              \
+        }                                                                       \
+    } while (0)
+
+#define MONTE_ARG(cond, ...)                                                    \
+    do {                                                                        \
+        if (!(cond)) {                                                          \
+            ::monte::set_error(__VA_ARGS__);                                    \
+            return MONTE_E_ARG;                                                 \
+        }                                                                       \
+    } while (0)
+
+struct EventTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t s;
+    explicit EventTimer(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~EventTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    void start() { cudaEventRecord(a, s); }
+    void stop() { cudaEventRecord(b, s); }
+    double ms() { float m = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&m, a, b); return m; }
+};
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace monte

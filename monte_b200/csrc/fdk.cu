@@ -1,0 +1,562 @@
+// fdk.cu — FDK reconstruction kernels for sm_100a and their C-ABI entry points.
+//
+// Replaces recon/bp3d20.cpp:36-166 (and bp3d20_325.cpp, fbp2.cpp) of the reference:
+//   fdk_weight_filter_kernel  = step 1 + step 2 (bp3d20.cpp:36-43, 48-73): cosine weight fused into
+//                               the load of a shared-memory Ram-Lak convolution; writes transposed.
+//   fdk_pad_kernel            = materialises the reference's "one past the row/view" reads
+//                               (bp3d20.cpp:152-156) as a duplicated column + two zero rows.
+//   fdk_backproject_kernel    = step 3 (bp3d20.cpp:83-166): voxel-driven, one thread per (s,t)
+//                               column of ZT z-slices, all per-(s,t,view) terms hoisted, bilinear in
+//                               registers, fp32 accumulation over views in registers.
+//   fdk_transpose_kernel      = image_zy (bp3d20.cpp:161) as a tiled transpose of image_xy.
+//   fbp2_* kernels            = recon/fbp2.cpp in double (nearest-neighbour lookup is discontinuous,
+//                               fp32 coordinates would flip pixels).
+// Neither kernel is a contraction worth tensor cores: the filter is a 1-D convolution with
+// per-row taps, the backprojector a gather.  Bound: FP32 pipe + L1 gather.
+#include "common.cuh"
+#include <cmath>
+
+namespace monte {
+
+// ------------------------------------------------------------------------------------------
+// per-view constants (host computes them in double with the reference's own expressions)
+// ------------------------------------------------------------------------------------------
+struct ViewConst {
+    float  cb, sb;        // cos / sin of beta (radians from degrees)           bp3d20.cpp:87-88
+    float  ca, sa;        // 1/sqrt(1+tan^2(beta_deg)), tan(beta_deg)/sqrt(..)  bp3d20.cpp:137 (Q12)
+    double cbd, sbd;      // cos(M_PI*beta/180), sin(M_PI*beta/180)
+    double cnb, snb;      // cos(-1*M_PI*beta/180), sin(-1*M_PI*beta/180)       bp3d20.cpp:103-104
+    double pxd, pyd;      // primary_x, primary_y                               bp3d20.cpp:87-88
+};
+
+static void make_view_consts(const monte_fdk_geom &g, std::vector<ViewConst> &out) {
+    out.resize(g.n_views);
+    for (int v = 0; v < g.n_views; v++) {
+        double beta = g.angle0_deg + g.angle_step_deg * (double)v;
+        float start_x = (float)(-g.dso), start_y = 0;
+        ViewConst c;
+        c.cbd = cos(M_PI * beta / 180);
+        c.sbd = sin(M_PI * beta / 180);
+        c.cnb = cos(-1 * M_PI * beta / 180);
+        c.snb = sin(-1 * M_PI * beta / 180);
+        c.pxd = start_x * c.cbd - start_y * c.sbd;
+        c.pyd = start_x * c.sbd + start_y * c.cbd;
+        double T = tan(beta);                       // degrees taken as radians, as shipped
+        double inv = 1.0 / sqrt(1 + T * T);
+        c.cb = (float)c.cbd; c.sb = (float)c.sbd;
+        c.ca = (float)inv;   c.sa = (float)(T * inv);
+        out[v] = c;
+    }
+}
+
+static int check_geom(const monte_fdk_geom *g) {
+    MONTE_ARG(g != nullptr, "fdk: geom is NULL");
+    MONTE_ARG(g->n_views > 0 && g->nu > 0 && g->nv > 0, "fdk: n_views/nu/nv must be positive");
+    MONTE_ARG(g->du > 0 && g->dv > 0 && g->vox > 0, "fdk: du/dv/vox must be positive");
+    MONTE_ARG(g->nx > 0 && g->ny > 0 && g->nz > 0, "fdk: volume dims must be positive");
+    MONTE_ARG(0 <= g->s_begin && g->s_begin <= g->s_end && g->s_end <= g->nx, "fdk: bad s ROI");
+    MONTE_ARG(0 <= g->t_begin && g->t_begin <= g->t_end && g->t_end <= g->ny, "fdk: bad t ROI");
+    MONTE_ARG(0 <= g->z_begin && g->z_begin <= g->z_end && g->z_end <= g->nz, "fdk: bad z ROI");
+    MONTE_ARG(g->weight_mode == MONTE_FDK_REFERENCE || g->weight_mode == MONTE_FDK_TEXTBOOK,
+              "fdk: unknown weight_mode %d", g->weight_mode);
+    MONTE_ARG(g->dso > 0 && g->dsd > 0, "fdk: dso/dsd must be positive");
+    MONTE_ARG((size_t)g->n_views * g->nv + 2 < (size_t)1 << 31, "fdk: too many projection rows");
+    return MONTE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// weight + Ram-Lak filter
+// ------------------------------------------------------------------------------------------
+constexpr int FT_D = 8;          // axial rows (d) per CTA
+constexpr int FT_NB = 8;         // outputs of one parity per task
+constexpr int FT_THREADS = 256;
+
+struct FilterParams {
+    const float  *map;      // [views][nu][nv]
+    const double *wtab;     // [nu][nv] cosine weights (double, host-computed)
+    const float  *taps;     // odd-offset taps, index (n + noff) >> 1
+    float        *out;      // padded rows
+    int nu, nv, pitch;      // pitch of `out` rows in floats
+    int view_begin;
+    int nu_pad;             // zero-padded extent of a staged row (multiple of 16, >= nu+16)
+    int in_pitch;           // smem row pitch, == 2 (mod 32)
+    int noff, tap_len;
+    float center;           // filter_scale * 0.25
+};
+
+__global__ void __launch_bounds__(FT_THREADS)
+fdk_weight_filter_kernel(const FilterParams p) {
+    extern __shared__ float smem[];
+    float *s_in  = smem;                                  // [FT_D][in_pitch]
+    float *s_out = s_in + FT_D * p.in_pitch;              // [FT_D][in_pitch]
+    float *s_tap = s_out + FT_D * p.in_pitch;             // [tap_len]
+    const int tid = threadIdx.x;
+    const int v = p.view_begin + blockIdx.y;
+    const int d0 = blockIdx.x * FT_D;
+
+    for (int m = tid; m < p.tap_len; m += FT_THREADS) s_tap[m] = p.taps[m];
+    // step 1 fused into the load: map_w = float(double(map) * w)     (bp3d20.cpp:40)
+    const float *mv = p.map + (size_t)v * p.nu * p.nv;
+    for (int idx = tid; idx < FT_D * p.nu_pad; idx += FT_THREADS) {
+        const int c = idx / FT_D, dl = idx % FT_D, d = d0 + dl;
+        float val = 0.f;
+        if (c < p.nu && d < p.nv) {
+            const size_t i = (size_t)c * p.nv + d;
+            val = (float)((double)__ldg(mv + i) * __ldg(p.wtab + i));
+        }
+        s_in[dl * p.in_pitch + c] = val;
+    }
+    __syncthreads();
+
+    // step 2: out[b] = sum_c in[c]*tap(c-b); even offsets are zero, offset 0 is the centre tap.
+    // A task owns FT_NB outputs of one parity b_j = b0 + 2j and walks the inputs of the other
+    // parity in ascending c (the reference's order, bp3d20.cpp:67).
+    const int n_strips = (p.nu + 15) / 16;
+    const int n_tasks = FT_D * 2 * n_strips;
+    for (int task = tid; task < n_tasks; task += FT_THREADS) {
+        const int dl = task & 7, q = (task >> 3) & 1, strip = task >> 4;
+        const int b0 = strip * 16 + q;
+        const float *row = s_in + dl * p.in_pitch;
+        float acc[FT_NB];
+#pragma unroll
+        for (int j = 0; j < FT_NB; j++) acc[j] = row[b0 + 2 * j] * p.center;
+        for (int c = q ^ 1; c < p.nu; c += 16) {
+            const int mbase = (c - b0 - 14 + p.noff) >> 1;
+            float tp[15], x[8];
+#pragma unroll
+            for (int k = 0; k < 15; k++) tp[k] = s_tap[mbase + k];
+#pragma unroll
+            for (int u = 0; u < 8; u++) x[u] = row[c + 2 * u];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int j = 0; j < FT_NB; j++) acc[j] = fmaf(x[u], tp[u - j + 7], acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < FT_NB; j++) s_out[dl * p.in_pitch + b0 + 2 * j] = acc[j];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < FT_D * p.nu; idx += FT_THREADS) {
+        const int dl = idx / p.nu, b = idx - dl * p.nu, d = d0 + dl;
+        if (d < p.nv) p.out[((size_t)v * p.nv + d) * p.pitch + b] = s_out[dl * p.in_pitch + b];
+    }
+}
+
+// element [r][nu] = [r+1][0]; columns nu+1.. and the two trailing rows are zero.
+__global__ void fdk_pad_kernel(float *f, int rows, int nu, int pitch) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows + 2) return;
+    float *row = f + (size_t)r * pitch;
+    if (r >= rows) {
+        for (int c = 0; c < pitch; c++) row[c] = 0.f;
+        return;
+    }
+    row[nu] = (r + 1 < rows) ? f[(size_t)(r + 1) * pitch] : 0.f;
+    for (int c = nu + 1; c < pitch; c++) row[c] = 0.f;
+}
+
+__global__ void fdk_unpad_kernel(const float *f, float *dense, size_t rows, int nu, int pitch) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * nu) return;
+    const size_t r = i / nu;
+    const int c = (int)(i - r * nu);
+    dense[i] = f[r * pitch + c];
+}
+
+// ------------------------------------------------------------------------------------------
+// backprojection
+// ------------------------------------------------------------------------------------------
+constexpr int BP_TX = 32, BP_TY = 8;   // threads: 32 along s (x-fastest, coalesced), 8 along t
+
+struct BpParams {
+    const float *filt;          // padded rows [n_views*nv + 2][pitch]
+    const ViewConst *vc;
+    float *vol;                 // slab base: slice z_lo
+    int n_views, nu, nv, pitch;
+    int nx, ny;
+    int s_begin, s_end, t_begin, t_end, z_lo, z_hi;   // z range of this launch (absolute)
+    int roi_z_begin, roi_z_end;                        // geometry ROI in z (outside -> 0)
+    float x0, y0, z0, vox;
+    float dso, dsd, half_u, half_v, inv_du, inv_dv;
+    float wd, wd2;              // weight_dist and its square (REFERENCE)
+    float out_fac;              // beta_span*2*pi/360 * out_scale*out_scale2 (REFERENCE) or 0.5*dbeta
+    float eps_u, eps_v;         // half-widths of the bands re-evaluated in double
+    float eps_ts;               // |tmp_s| below this: its sign is re-evaluated in double
+    int textbook, coord_mode;
+    int mask_cs, mask_ct, mask_cz;
+    long long mask_r2;
+    // doubles for the exact edge path
+    double x0d, y0d, z0d, voxd, dsdd, half_ud, half_vd, inv_dud, inv_dvd, nu_half, nv_half;
+};
+
+// The reference decides in double whether a voxel's projection is on the detector
+// (bp3d20.cpp:116) and the decision is discontinuous, so fp32 values inside a narrow band
+// around the edge are re-evaluated with the reference's exact double expressions (no FMA
+// contraction).  Returns false if the reference skips this (voxel, view).
+__device__ __noinline__ bool bp_exact(const BpParams &p, const ViewConst &c, int s, int t, int z,
+                                      float &xf, float &yf) {
+    double X = __dadd_rn(p.x0d, __dmul_rn((double)s, p.voxd));
+    double Y = __dsub_rn(p.y0d, __dmul_rn((double)t, p.voxd));
+    double Z = __dsub_rn(p.z0d, __dmul_rn((double)z, p.voxd));
+    double pv0 = __dsub_rn(X, c.pxd), pv1 = __dsub_rn(Y, c.pyd);
+    double r0 = __dsub_rn(__dmul_rn(pv0, c.cnb), __dmul_rn(pv1, c.snb));
+    double r1 = __dadd_rn(__dmul_rn(pv0, c.snb), __dmul_rn(pv1, c.cnb));
+    double to_det = __ddiv_rn(p.dsdd, r0);
+    double u = __dmul_rn(r1, to_det), w = __dmul_rn(Z, to_det);
+    if (fabs(u) > p.half_ud || fabs(w) > p.half_vd) return false;
+    double y, x;
+    if (p.coord_mode == MONTE_FDK_COORD_SCALE_BEFORE) {
+        y = -__dsub_rn(__dmul_rn(u, p.inv_dud), p.nu_half);
+        x = -__dsub_rn(__dmul_rn(w, p.inv_dvd), p.nv_half);
+    } else {
+        y = __dmul_rn(-p.inv_dud, __dsub_rn(u, p.half_ud));
+        x = __dmul_rn(-p.inv_dvd, __dsub_rn(w, p.half_vd));
+    }
+    if (!(0 <= x && x <= p.nv && 0 <= y && y <= p.nu)) { xf = -1.f; yf = -1.f; return true; }
+    xf = (float)x; yf = (float)y;
+    return true;
+}
+
+// sign(tmp_s) flips the sign of d (bp3d20.cpp:140-142) and tmp_s crosses zero on a line through
+// the rotation centre; the reference's double rounding decides there, so reproduce it.
+__device__ __noinline__ bool bp_exact_ts_negative(const BpParams &p, const ViewConst &c, int s, int t) {
+    double X = __dadd_rn(p.x0d, __dmul_rn((double)s, p.voxd));
+    double Y = __dsub_rn(p.y0d, __dmul_rn((double)t, p.voxd));
+    return __dsub_rn(__dmul_rn(X, c.cbd), __dmul_rn(Y, c.sbd)) < 0;
+}
+
+__device__ __forceinline__ float bp_bilinear(const float *__restrict__ f, int pitch, float x, float y) {
+    const int xi = (int)x, yi = (int)y;
+    const float fx = x - (float)xi, fy = y - (float)yi;
+    const float *q = f + (size_t)xi * pitch + yi;
+    const float a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + pitch), d = __ldg(q + pitch + 1);
+    const float lo = fmaf(fx, c - a, a);      // (1-fx)*a + fx*c
+    const float hi = fmaf(fx, d - b, b);
+    return fmaf(fy, hi - lo, lo);
+}
+
+template <int ZT>
+__global__ void __launch_bounds__(BP_TX *BP_TY)
+fdk_backproject_kernel(const __grid_constant__ BpParams p) {
+    const int s = p.s_begin + blockIdx.x * BP_TX + threadIdx.x;
+    const int t = p.t_begin + blockIdx.y * BP_TY + threadIdx.y;
+    const int zb = p.z_lo + blockIdx.z * ZT;
+    if (s >= p.s_end || t >= p.t_end) return;
+
+    const float X = fmaf(p.vox, (float)s, p.x0);
+    const float Y = fmaf(-p.vox, (float)t, p.y0);
+    float Zc[ZT], acc[ZT];
+#pragma unroll
+    for (int i = 0; i < ZT; i++) {
+        Zc[i] = fmaf(-p.vox, (float)(zb + i), p.z0);
+        acc[i] = 0.f;
+    }
+    const float xoff = p.half_v * p.inv_dv;
+    const int nz_here = min(ZT, p.z_hi - zb);
+
+    for (int v = 0; v < p.n_views; v++) {
+        const ViewConst &c = p.vc[v];
+        const float cb = c.cb, sb = c.sb;
+        const float rx = fmaf(X, cb, fmaf(Y, sb, p.dso));       // distance from the source along the axis
+        const float ry = fmaf(Y, cb, -X * sb);
+        const float k = __fdividef(p.dsd, rx);
+        const float u = k * ry;
+        const float au = fabsf(u);
+        const bool u_band = fabsf(au - p.half_u) < p.eps_u;
+        if (au > p.half_u && !u_band) continue;                 // bp3d20.cpp:116
+        float y = (p.half_u - u) * p.inv_du;
+        float wgt;
+        if (!p.textbook) {
+            const float ts = fmaf(X, cb, -Y * sb);               // bp3d20.cpp:134-142
+            const float tt = fmaf(X, sb, Y * cb);
+            float d = fabsf(fmaf(ts, c.ca, -tt * c.sa));
+            bool neg = ts < 0.f;
+            if (fabsf(ts) < p.eps_ts) neg = bp_exact_ts_negative(p, c, s, t);
+            d = neg ? -d : d;
+            const float e = p.wd - d;
+            wgt = __fdividef(p.wd2, e * e) * p.out_fac;
+        } else {
+            wgt = __fdividef(p.dso * p.dso, rx * rx) * p.out_fac;
+        }
+        const float kz = k * p.inv_dv;
+        const float *fv = p.filt + (size_t)v * p.nv * p.pitch;
+#pragma unroll
+        for (int i = 0; i < ZT; i++) {
+            const float w = k * Zc[i];
+            const float aw = fabsf(w);
+            float x = fmaf(-kz, Zc[i], xoff);
+            float yy = y;
+            bool use = aw <= p.half_v && au <= p.half_u;
+            if (u_band || fabsf(aw - p.half_v) < p.eps_v) {
+                if (aw > p.half_v + p.eps_v) use = false;
+                else {
+                    float xe, ye;
+                    use = bp_exact(p, c, s, t, zb + i, xe, ye);
+                    if (use) {
+                        if (xe < 0.f) use = false;              // inside detector test but outside the fetch test
+                        else { x = xe; yy = ye; }
+                    }
+                }
+            }
+            if (use) {
+                x = fminf(fmaxf(x, 0.f), (float)p.nv);
+                yy = fminf(fmaxf(yy, 0.f), (float)p.nu);
+                acc[i] = fmaf(wgt, bp_bilinear(fv, p.pitch, x, yy), acc[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < ZT; i++) {
+        if (i < nz_here) {
+            const int z = zb + i;
+            float r = acc[i];
+            if (z < p.roi_z_begin || z >= p.roi_z_end) r = 0.f;
+            if (p.mask_r2 >= 0) {
+                const long long dz = z - p.mask_cz, dt = t - p.mask_ct, ds = s - p.mask_cs;
+                if (dz * dz + dt * dt + ds * ds > p.mask_r2) r = 0.f;
+            }
+            p.vol[((size_t)(z - p.z_lo) * p.ny + t) * p.nx + s] = r;
+        }
+    }
+}
+
+// vol_zy[s][t][z] = vol_xy[z][t][s]  (32x32 tiles of the (z,s) plane for every t)
+__global__ void fdk_transpose_kernel(const float *__restrict__ in, float *__restrict__ out, int nx, int ny, int nz) {
+    __shared__ float tile[32][33];
+    const int t = blockIdx.z;
+    int s = blockIdx.x * 32 + threadIdx.x, z = blockIdx.y * 32 + threadIdx.y;
+    for (int j = 0; j < 32; j += 8)
+        if (s < nx && z + j < nz) tile[threadIdx.y + j][threadIdx.x] = in[((size_t)(z + j) * ny + t) * nx + s];
+    __syncthreads();
+    z = blockIdx.y * 32 + threadIdx.x;
+    s = blockIdx.x * 32 + threadIdx.y;
+    for (int j = 0; j < 32; j += 8)
+        if (z < nz && s + j < nx) out[((size_t)(s + j) * ny + t) * nz + z] = tile[threadIdx.x][threadIdx.y + j];
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct FdkCache {           // per-geometry device constants, rebuilt only when the geometry changes
+    monte_fdk_geom g;
+    bool valid = false;
+    ViewConst *d_vc = nullptr;
+    double *d_wtab = nullptr;
+    float *d_taps = nullptr;
+    int noff = 0, tap_len = 0, nu_pad = 0, in_pitch = 0;
+    size_t vc_cap = 0, wtab_cap = 0, taps_cap = 0;
+};
+static FdkCache g_fdk;
+
+static int fdk_prepare(const monte_fdk_geom *g, cudaStream_t st) {
+    if (g_fdk.valid && memcmp(&g_fdk.g, g, sizeof(*g)) == 0) return MONTE_OK;
+    g_fdk.valid = false;
+    std::vector<ViewConst> vc;
+    make_view_consts(*g, vc);
+    // cosine weights, bp3d20.cpp:40 (REFERENCE: weight_dist=60; TEXTBOOK: Dsd)
+    const bool textbook = g->weight_mode == MONTE_FDK_TEXTBOOK;
+    const double wd = textbook ? g->dsd : g->weight_dist;
+    std::vector<double> wtab((size_t)g->nu * g->nv);
+    for (int zeta = 0; zeta < g->nu; zeta++)
+        for (int pp = 0; pp < g->nv; pp++) {
+            double a = -1 * (zeta * g->du) + g->half_u, b = (pp * g->dv) - g->half_v;
+            wtab[(size_t)zeta * g->nv + pp] = wd / sqrt(pow(wd, 2) + pow(a, 2) + pow(b, 2));
+        }
+    // Ram-Lak taps for odd offsets, bp3d20.cpp:57 (float) times the filter scale (double product)
+    const int nu_pad = ((g->nu + 15) / 16) * 16 + 16;
+    int noff = nu_pad + 17; if ((noff & 1) == 0) noff++;
+    const int tap_len = (nu_pad + 2 + noff) / 2 + 16;
+    const double scale = textbook ? g->dsd / (g->dso * g->du) : g->filter_scale;
+    std::vector<float> taps(tap_len, 0.f);
+    for (int m = 0; m < tap_len; m++) {
+        int n = 2 * m - noff, an = n < 0 ? -n : n;
+        if ((an & 1) && an <= g->nu - 1) {
+            float ramp = (float)(-1. / pow(an * M_PI, 2));
+            taps[m] = (float)(scale * (double)ramp);
+        }
+    }
+    int in_pitch = nu_pad;
+    while ((in_pitch & 31) != 2) in_pitch++;
+    if (vc.size() > g_fdk.vc_cap) { cudaFree(g_fdk.d_vc); MONTE_CUDA(cudaMalloc(&g_fdk.d_vc, vc.size() * sizeof(ViewConst))); g_fdk.vc_cap = vc.size(); }
+    if (wtab.size() > g_fdk.wtab_cap) { cudaFree(g_fdk.d_wtab); MONTE_CUDA(cudaMalloc(&g_fdk.d_wtab, wtab.size() * sizeof(double))); g_fdk.wtab_cap = wtab.size(); }
+    if (taps.size() > g_fdk.taps_cap) { cudaFree(g_fdk.d_taps); MONTE_CUDA(cudaMalloc(&g_fdk.d_taps, taps.size() * sizeof(float))); g_fdk.taps_cap = taps.size(); }
+    MONTE_CUDA(cudaMemcpyAsync(g_fdk.d_vc, vc.data(), vc.size() * sizeof(ViewConst), cudaMemcpyHostToDevice, st));
+    MONTE_CUDA(cudaMemcpyAsync(g_fdk.d_wtab, wtab.data(), wtab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    MONTE_CUDA(cudaMemcpyAsync(g_fdk.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    MONTE_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope
+    g_fdk.g = *g;
+    g_fdk.noff = noff; g_fdk.tap_len = tap_len; g_fdk.nu_pad = nu_pad; g_fdk.in_pitch = in_pitch;
+    g_fdk.valid = true;
+    return MONTE_OK;
+}
+
+static size_t filtered_pitch(const monte_fdk_geom *g) { return (size_t)((g->nu + 1 + 3) / 4) * 4; }
+
+}  // namespace monte
+
+using namespace monte;
+
+extern "C" {
+
+size_t monte_gpu_fdk_filtered_pitch(const monte_fdk_geom *g) { return g ? filtered_pitch(g) : 0; }
+size_t monte_gpu_fdk_filtered_elems(const monte_fdk_geom *g) {
+    return g ? ((size_t)g->n_views * g->nv + 2) * filtered_pitch(g) : 0;
+}
+
+int monte_gpu_fdk_filter_dev(const monte_fdk_geom *g, const float *d_map, int view_begin, int view_end,
+                             float *d_filtered_padded, void *stream) {
+    MONTE_REQUIRE_INIT();
+    if (int rc = check_geom(g)) return rc;
+    MONTE_ARG(d_map && d_filtered_padded, "fdk_filter: NULL device pointer");
+    MONTE_ARG(0 <= view_begin && view_begin <= view_end && view_end <= g->n_views, "fdk_filter: bad view range");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = fdk_prepare(g, st)) return rc;
+    if (view_begin == view_end) return MONTE_OK;
+    FilterParams p;
+    p.map = d_map; p.wtab = g_fdk.d_wtab; p.taps = g_fdk.d_taps; p.out = d_filtered_padded;
+    p.nu = g->nu; p.nv = g->nv; p.pitch = (int)filtered_pitch(g);
+    p.view_begin = view_begin; p.nu_pad = g_fdk.nu_pad; p.in_pitch = g_fdk.in_pitch;
+    p.noff = g_fdk.noff; p.tap_len = g_fdk.tap_len;
+    const bool textbook = g->weight_mode == MONTE_FDK_TEXTBOOK;
+    p.center = (float)((textbook ? g->dsd / (g->dso * g->du) : g->filter_scale) * 0.25);
+    const size_t smem = ((size_t)2 * FT_D * p.in_pitch + p.tap_len) * sizeof(float);
+    MONTE_ARG(smem <= 227 * 1024, "fdk_filter: nu=%d needs %zu B of shared memory (> 227 KB)", g->nu, smem);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        MONTE_CUDA(cudaFuncSetAttribute(fdk_weight_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    dim3 grid(ceil_div(g->nv, FT_D), view_end - view_begin);
+    fdk_weight_filter_kernel<<<grid, FT_THREADS, smem, st>>>(p);
+    MONTE_CUDA(cudaGetLastError());
+    return MONTE_OK;
+}
+
+int monte_gpu_fdk_pad_dev(const monte_fdk_geom *g, float *d_filtered_padded, void *stream) {
+    MONTE_REQUIRE_INIT();
+    if (int rc = check_geom(g)) return rc;
+    const int rows = g->n_views * g->nv;
+    fdk_pad_kernel<<<ceil_div(rows + 2, 256), 256, 0, (cudaStream_t)stream>>>(d_filtered_padded, rows, g->nu, (int)filtered_pitch(g));
+    MONTE_CUDA(cudaGetLastError());
+    return MONTE_OK;
+}
+
+int monte_gpu_fdk_unpad_dev(const monte_fdk_geom *g, const float *d_filtered_padded, float *d_dense, void *stream) {
+    MONTE_REQUIRE_INIT();
+    if (int rc = check_geom(g)) return rc;
+    const size_t rows = (size_t)g->n_views * g->nv, n = rows * g->nu;
+    fdk_unpad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_filtered_padded, d_dense, rows, g->nu, (int)filtered_pitch(g));
+    MONTE_CUDA(cudaGetLastError());
+    return MONTE_OK;
+}
+
+int monte_gpu_fdk_backproject_dev(const monte_fdk_geom *g, const float *d_filtered_padded, int z_lo, int z_hi,
+                                  float *d_vol_slab, void *stream) {
+    MONTE_REQUIRE_INIT();
+    if (int rc = check_geom(g)) return rc;
+    MONTE_ARG(d_filtered_padded && d_vol_slab, "fdk_backproject: NULL device pointer");
+    MONTE_ARG(0 <= z_lo && z_lo <= z_hi && z_hi <= g->nz, "fdk_backproject: bad z range [%d,%d)", z_lo, z_hi);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = fdk_prepare(g, st)) return rc;
+    if (z_lo == z_hi) return MONTE_OK;
+    // everything outside the ROI is zero (the reference callocs the volume, bp3d20.cpp:32)
+    MONTE_CUDA(cudaMemsetAsync(d_vol_slab, 0, (size_t)(z_hi - z_lo) * g->ny * g->nx * sizeof(float), st));
+    if (g->s_begin == g->s_end || g->t_begin == g->t_end) return MONTE_OK;
+    const bool textbook = g->weight_mode == MONTE_FDK_TEXTBOOK;
+    BpParams p;
+    p.filt = d_filtered_padded; p.vc = g_fdk.d_vc; p.vol = d_vol_slab;
+    p.n_views = g->n_views; p.nu = g->nu; p.nv = g->nv; p.pitch = (int)filtered_pitch(g);
+    p.nx = g->nx; p.ny = g->ny;
+    p.s_begin = g->s_begin; p.s_end = g->s_end; p.t_begin = g->t_begin; p.t_end = g->t_end;
+    p.z_lo = z_lo; p.z_hi = z_hi; p.roi_z_begin = g->z_begin; p.roi_z_end = g->z_end;
+    p.x0 = (float)g->x0; p.y0 = (float)g->y0; p.z0 = (float)g->z0; p.vox = (float)g->vox;
+    p.dso = (float)g->dso; p.dsd = (float)g->dsd;
+    p.half_u = (float)g->half_u; p.half_v = (float)g->half_v;
+    p.inv_du = (float)(1.0 / g->du); p.inv_dv = (float)(1.0 / g->dv);
+    p.wd = (float)g->weight_dist; p.wd2 = (float)(g->weight_dist * g->weight_dist);
+    const double dbeta = (double)(float)g->angle_step_deg * 2 * M_PI / 360;
+    p.out_fac = (float)(textbook ? 0.5 * dbeta : dbeta * g->out_scale * g->out_scale2);
+    p.eps_u = (float)(g->half_u * 2e-5); p.eps_v = (float)(g->half_v * 2e-5);
+    p.eps_ts = (float)(2e-5 * (fabs(g->x0) + fabs(g->y0) + g->vox * (g->nx + g->ny)));
+    p.textbook = textbook; p.coord_mode = g->coord_mode;
+    p.mask_cs = g->mask_cs; p.mask_ct = g->mask_ct; p.mask_cz = g->mask_cz; p.mask_r2 = g->mask_r2;
+    p.x0d = g->x0; p.y0d = g->y0; p.z0d = g->z0; p.voxd = g->vox; p.dsdd = g->dsd;
+    p.half_ud = g->half_u; p.half_vd = g->half_v; p.inv_dud = 1.0 / g->du; p.inv_dvd = 1.0 / g->dv;
+    p.nu_half = g->nu / 2.; p.nv_half = g->nv / 2.;
+    constexpr int ZT = 16;
+    dim3 block(BP_TX, BP_TY);
+    dim3 grid(ceil_div(g->s_end - g->s_begin, BP_TX), ceil_div(g->t_end - g->t_begin, BP_TY), ceil_div(z_hi - z_lo, ZT));
+    fdk_backproject_kernel<ZT><<<grid, block, 0, st>>>(p);
+    MONTE_CUDA(cudaGetLastError());
+    return MONTE_OK;
+}
+
+int monte_gpu_fdk_transpose_dev(const monte_fdk_geom *g, const float *d_vol_xy, float *d_vol_zy, void *stream) {
+    MONTE_REQUIRE_INIT();
+    if (int rc = check_geom(g)) return rc;
+    dim3 grid(ceil_div(g->nx, 32), ceil_div(g->nz, 32), g->ny);
+    fdk_transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(d_vol_xy, d_vol_zy, g->nx, g->ny, g->nz);
+    MONTE_CUDA(cudaGetLastError());
+    return MONTE_OK;
+}
+
+// Host-buffer pipeline: the drop-in for bp3d20.cpp:29-171.
+int monte_gpu_fdk(const monte_fdk_geom *g, const float *map, float *filtered, float *vol_xy, float *vol_zy,
+                  monte_fdk_stats *stats) {
+    MONTE_REQUIRE_INIT();
+    if (int rc = check_geom(g)) return rc;
+    MONTE_ARG(map && vol_xy, "fdk: map and vol_xy must not be NULL");
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    const size_t n_map = (size_t)g->n_views * g->nu * g->nv;
+    const size_t n_vol = (size_t)g->nx * g->ny * g->nz;
+    float *d_map = (float *)scratch(0, n_map * sizeof(float));
+    float *d_filt = (float *)scratch(1, monte_gpu_fdk_filtered_elems(g) * sizeof(float));
+    float *d_vol = (float *)scratch(2, n_vol * sizeof(float));
+    if (!d_map || !d_filt || !d_vol) return MONTE_E_NOMEM;
+    EventTimer t_all(st), t_h2d(st), t_f(st), t_b(st), t_t(st), t_d2h(st);
+    int launches = 0;
+    t_all.start();
+    t_h2d.start();
+    MONTE_CUDA(cudaMemcpyAsync(d_map, map, n_map * sizeof(float), cudaMemcpyHostToDevice, st));
+    t_h2d.stop();
+    t_f.start();
+    if (int rc = monte_gpu_fdk_filter_dev(g, d_map, 0, g->n_views, d_filt, st)) return rc;
+    if (int rc = monte_gpu_fdk_pad_dev(g, d_filt, st)) return rc;
+    launches += 2;
+    t_f.stop();
+    t_b.start();
+    if (int rc = monte_gpu_fdk_backproject_dev(g, d_filt, 0, g->nz, d_vol, st)) return rc;
+    launches += 1;
+    t_b.stop();
+    t_d2h.start();
+    MONTE_CUDA(cudaMemcpyAsync(vol_xy, d_vol, n_vol * sizeof(float), cudaMemcpyDeviceToHost, st));
+    t_d2h.stop();
+    t_t.start();
+    if (filtered) {   // d_map is free now: reuse it for the dense copy of the filtered projections
+        if (int rc = monte_gpu_fdk_unpad_dev(g, d_filt, d_map, st)) return rc;
+        launches += 1;
+        MONTE_CUDA(cudaMemcpyAsync(filtered, d_map, n_map * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    if (vol_zy) {
+        float *d_zy = (float *)scratch(3, n_vol * sizeof(float));
+        if (!d_zy) return MONTE_E_NOMEM;
+        if (int rc = monte_gpu_fdk_transpose_dev(g, d_vol, d_zy, st)) return rc;
+        launches += 1;
+        MONTE_CUDA(cudaMemcpyAsync(vol_zy, d_zy, n_vol * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    t_t.stop();
+    t_all.stop();
+    MONTE_CUDA(cudaStreamSynchronize(st));
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->ms_h2d = t_h2d.ms(); stats->ms_filter = t_f.ms(); stats->ms_backproject = t_b.ms();
+        stats->ms_transpose = t_t.ms(); stats->ms_d2h = t_d2h.ms(); stats->ms_total = t_all.ms();
+        stats->voxel_updates = (uint64_t)(g->s_end - g->s_begin) * (g->t_end - g->t_begin) * (g->z_end - g->z_begin) * g->n_views;
+        stats->filter_macs = (uint64_t)g->n_views * g->nv * g->nu * g->nu;
+        stats->launches = launches; stats->sm_count = c.sm_count;
+    }
+    return MONTE_OK;
+}
+
+}  // extern "C"

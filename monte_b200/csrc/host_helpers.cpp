@@ -1,0 +1,135 @@
+// host_helpers.cpp — GPU-free pieces of the reference's driver surface: cross-section tables,
+// phantom generators, CT-number conversion, geometry presets.  Linked into libmonte_gpu and used
+// by the C++ drivers under monte_b200/host/.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include "../../include/monte_gpu.h"
+
+namespace monte { void set_error(const char *fmt, ...); }
+
+extern "C" {
+
+// ---- presets: the literals of the shipped recon programs ------------------------------------
+static void fdk_common(monte_fdk_geom *g) {
+    memset(g, 0, sizeof(*g));
+    g->n_views = 360;                          // bp3d20.cpp:19
+    g->half_u = g->half_v = 16.25;             // bp3d20.cpp:40,116
+    g->dso = 160; g->dsd = 220;                // bp3d20.cpp:85,107
+    g->weight_dist = 60;                       // bp3d20.cpp:40,159
+    g->filter_scale = 0.5;                     // bp3d20.cpp:68
+    g->out_scale = 2.7; g->out_scale2 = 1;     // bp3d20.cpp:160
+    g->angle0_deg = 0; g->angle_step_deg = 1;  // bp3d20.cpp:82-83
+    g->nx = g->ny = g->nz = 256; g->vox = 0.1; // bp3d20.cpp:18,96
+    g->x0 = -12.8; g->y0 = 12.8; g->z0 = 12.8; // bp3d20.cpp:96-98
+    g->s_begin = 125; g->s_end = 130;          // bp3d20.cpp:93
+    g->t_begin = 0; g->t_end = 256; g->z_begin = 0; g->z_end = 256;
+    g->mask_r2 = -1;
+    g->weight_mode = MONTE_FDK_REFERENCE;
+}
+void monte_fdk_geom_bp3d20(monte_fdk_geom *g) {
+    fdk_common(g);
+    g->nu = g->nv = 65; g->du = g->dv = 0.5;               // bp3d20.cpp:17,40
+    g->mask_cs = g->mask_ct = g->mask_cz = 128; g->mask_r2 = 118 * 118;  // bp3d20.cpp:145
+    g->coord_mode = MONTE_FDK_COORD_SCALE_AFTER;
+}
+void monte_fdk_geom_bp3d20_325(monte_fdk_geom *g) {
+    fdk_common(g);
+    g->nu = g->nv = 325; g->du = g->dv = 0.1;              // bp3d20_325.cpp:17,43
+    g->out_scale2 = 5;                                     // bp3d20_325.cpp:170
+    g->coord_mode = MONTE_FDK_COORD_SCALE_BEFORE;          // bp3d20_325.cpp:134-135
+}
+void monte_fdk_geom_fbp2(monte_fdk_geom *g) {
+    fdk_common(g);
+    g->nu = 65; g->nv = 1; g->du = g->dv = 0.5;            // fbp2.cpp:17,38
+    g->nz = 1; g->z_end = 1; g->s_begin = 0; g->s_end = 256;
+    g->out_scale = 1.7;                                    // fbp2.cpp:148
+}
+
+// ---- cross-section tables ---------------------------------------------------------------------
+// readcsv role (CBCT_real2.cpp:633-668): rows are "coh,compton,photo,total" for 1..200 keV.
+int monte_xs_load_csv(const char *path, int material, float density, int quirk_bom, monte_mc_xs *xs) {
+    if (!path || !xs || material < 0 || material >= MONTE_MC_MAX_MATERIALS) {
+        monte::set_error("monte_xs_load_csv: bad argument");
+        return MONTE_E_ARG;
+    }
+    FILE *f = fopen(path, "rb");
+    if (!f) {
+        monte::set_error("monte_xs_load_csv: cannot open %s", path);
+        return MONTE_E_IO;
+    }
+    char line[512];
+    int row = 0;
+    while (row < MONTE_MC_TABLE_ROWS - 1 && fgets(line, sizeof(line), f)) {
+        char *p = line;
+        if (row == 0 && (unsigned char)p[0] == 0xEF && (unsigned char)p[1] == 0xBB && (unsigned char)p[2] == 0xBF) p += 3;
+        double a, b, c, d;
+        if (sscanf(p, "%lf,%lf,%lf,%lf", &a, &b, &c, &d) != 4) {
+            if (p[0] == '\r' || p[0] == '\n' || p[0] == 0) continue;
+            fclose(f);
+            monte::set_error("monte_xs_load_csv: %s line %d is not 4 comma-separated numbers", path, row + 1);
+            return MONTE_E_IO;
+        }
+        const int k = row + 1;            // index = keV (CBCT_real2.cpp:646)
+        xs->coh[material][k] = (float)a;
+        xs->compt[material][k] = (float)b;
+        xs->photo[material][k] = (float)c;
+        xs->total[material][k] = (float)d;
+        row++;
+    }
+    fclose(f);
+    if (row != MONTE_MC_TABLE_ROWS - 1) {
+        monte::set_error("monte_xs_load_csv: %s has %d rows, expected %d", path, row, MONTE_MC_TABLE_ROWS - 1);
+        return MONTE_E_IO;
+    }
+    if (quirk_bom) xs->coh[material][1] = 1.372f;   // CBCT_real2.cpp:663, applied to every file
+    xs->coh[material][0] = xs->coh[material][1];
+    xs->compt[material][0] = xs->compt[material][1];
+    xs->photo[material][0] = xs->photo[material][1];
+    xs->total[material][0] = xs->total[material][1];
+    xs->density[material] = density;
+    if (xs->n_materials < material + 1) xs->n_materials = material + 1;
+    return MONTE_OK;
+}
+
+// ---- phantoms ------------------------------------------------------------------------------------
+void monte_make_fantom(uint8_t *g, int n, int cy, int cx, int r2) {   // make_fantom.cpp:10-19
+    for (int j = 0; j < n; j++)
+        for (int k = 0; k < n; k++)
+            g[j * n + k] = ((j - cy) * (j - cy) + (k - cx) * (k - cx) <= r2) ? 1 : 0;
+}
+
+void monte_make_sphere(uint8_t *g, int nx, int ny, int nz, int cx, int cy, int cz, int r2) {  // make_image01.cpp:15-23
+    for (int k = 0; k < nz; k++)
+        for (int j = 0; j < ny; j++)
+            for (int i = 0; i < nx; i++)
+                g[((size_t)k * ny + j) * nx + i] =
+                    ((i - cx) * (i - cx) + (j - cy) * (j - cy) + (k - cz) * (k - cz) <= r2) ? 1 : 0;
+}
+
+// ---- CT number -> mu -----------------------------------------------------------------------------
+// The reference file only gets as far as mu_H2O = csv_H2O[3][(int)(E+0.5)]*dens (ctnum_to_mu.cpp:55);
+// the conversion it is named after is the standard mu = mu_water*(1+HU/1000).
+int monte_ctnum_to_mu(const float *hu, size_t n, const monte_mc_xs *xs, double keV,
+                      float hu_air_max, float hu_bone_min, float *mu, uint8_t *labels) {
+    if (!hu || !xs || xs->n_materials < 1) {
+        monte::set_error("monte_ctnum_to_mu: bad argument");
+        return MONTE_E_ARG;
+    }
+    int k = (int)(keV + 0.5);
+    if (k < 1) k = 1;
+    if (k > MONTE_MC_TABLE_ROWS - 1) k = MONTE_MC_TABLE_ROWS - 1;
+    const float mu_w = xs->total[0][k] * xs->density[0];
+    for (size_t i = 0; i < n; i++) {
+        if (mu) {
+            float m = mu_w * (1.0f + hu[i] / 1000.0f);
+            mu[i] = m > 0.f ? m : 0.f;
+        }
+        if (labels) labels[i] = hu[i] <= hu_air_max ? 0 : (hu[i] >= hu_bone_min && xs->n_materials > 1 ? 2 : 1);
+    }
+    return MONTE_OK;
+}
+
+}  // extern "C"

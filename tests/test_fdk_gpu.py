@@ -1,0 +1,141 @@
+"""GPU parity tests of the FDK path, called through the C ABI (libmonte_gpu.so).
+
+Tolerance (BASELINE.json north_star): the FDK volume and the filtered projections agree with the
+reference CPU path within 1e-4 relative, fp32.  "Relative" is to max|reference| of the compared
+array (the volume crosses zero), and it must hold for EVERY element:
+    max|gpu - ref| <= REL * max|ref|.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from monte_b200 import _abi
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+
+
+def rand(seed, shape):
+    return np.random.default_rng(seed).random(shape, dtype=np.float32)
+
+
+def assert_close(got, ref, what):
+    scale = float(np.abs(ref).max())
+    err = float(np.abs(got.astype(np.float64) - ref.astype(np.float64)).max())
+    assert err <= REL * scale, "%s: max err %.3e > %.1e * max|ref| (%.3e)" % (what, err, REL, scale)
+    return err / scale
+
+
+def test_bp3d20_against_reference_golden(monte):
+    """recon/bp3d20.cpp as shipped (65x65x360 -> 256^3, s in [125,130), sphere mask)."""
+    gold = np.load(os.path.join(GOLDEN, "fdk_bp3d20.npz"))
+    g = _abi.bp3d20_geom()
+    f, xy, zy, st = monte.fdk(g, rand(int(gold["seed"]), (360, 65, 65)), want_zy=True)
+    assert_close(f[gold["views_kept"]], gold["filtered_views"], "filtered")
+    assert_close(xy[:, :, 125:130][::4, ::4, :], gold["slab_sub"], "slab")
+    assert not xy[:, :, :125].any() and not xy[:, :, 130:].any()
+    assert np.array_equal(zy.transpose(2, 1, 0), xy)
+    assert st["launches"] >= 3 and st["voxel_updates"] == 256 * 256 * 5 * 360
+
+
+def test_bp3d20_325_against_reference_golden(monte):
+    gold = np.load(os.path.join(GOLDEN, "fdk_bp3d20_325.npz"))
+    g = _abi.bp3d20_325_geom()
+    f, xy, _, _ = monte.fdk(g, rand(int(gold["seed"]), (360, 325, 325)))
+    assert_close(f[gold["views_kept"]][:, ::4, :], gold["filtered_views"], "filtered")
+    assert_close(xy[:, :, 125:130][::4, ::4, :], gold["slab_sub"], "slab")
+
+
+def test_bp3d20_full_slab_against_oracle(monte, oracle):
+    """every voxel of the shipped slab, every filtered pixel, against the CPU restatement"""
+    g = _abi.bp3d20_geom()
+    proj = rand(5, (360, 65, 65))
+    f_o, xy_o, _ = oracle.fdk(g, proj)
+    f, xy, _, _ = monte.fdk(g, proj)
+    assert_close(f, f_o, "filtered")
+    assert_close(xy, xy_o, "volume")
+
+
+@pytest.mark.parametrize("nu,nv,n,views,textbook", [
+    (65, 65, 48, 90, False),       # reference-style square detector
+    (96, 40, 40, 60, False),       # ragged: nu != nv, neither a multiple of the tile sizes
+    (33, 17, 24, 45, True),        # tiny + textbook weights
+    (130, 70, 56, 120, True),
+])
+def test_generic_geometry_against_oracle(monte, oracle, nu, nv, n, views, textbook):
+    g = _abi.generic_fdk_geom(views, nu, nv, n, textbook=textbook)
+    proj = rand(nu * 1000 + nv, (views, nu, nv))
+    f_o, xy_o, zy_o = oracle.fdk(g, proj, want_zy=True)
+    f, xy, zy, _ = monte.fdk(g, proj, want_zy=True)
+    assert_close(f, f_o, "filtered")
+    assert_close(xy, xy_o, "volume")
+    assert np.array_equal(zy.transpose(2, 1, 0), xy)
+
+
+def test_partial_roi_and_mask(monte, oracle):
+    g = _abi.generic_fdk_geom(72, 65, 65, 64)
+    g.s_begin, g.s_end, g.t_begin, g.t_end, g.z_begin, g.z_end = 3, 50, 7, 64, 10, 33
+    g.mask_cs = g.mask_ct = g.mask_cz = 32
+    g.mask_r2 = 25 * 25
+    proj = rand(9, (72, 65, 65))
+    _, xy_o, _ = oracle.fdk(g, proj)
+    _, xy, _, _ = monte.fdk(g, proj, want_filtered=False)
+    assert_close(xy, xy_o, "volume")
+    assert np.array_equal(xy == 0, xy_o == 0)
+
+
+def test_empty_roi_gives_zero_volume(monte):
+    g = _abi.generic_fdk_geom(8, 33, 33, 16)
+    g.s_begin = g.s_end = 0
+    _, xy, _, _ = monte.fdk(g, rand(1, (8, 33, 33)), want_filtered=False)
+    assert not xy.any()
+
+
+def test_fbp2_against_reference_golden(monte):
+    gold = np.load(os.path.join(GOLDEN, "fdk_fbp2.npz"))
+    f, img, _ = monte.fbp2(_abi.fbp2_geom(), rand(int(gold["seed"]), (360, 65)), view_first=1)
+    assert_close(f[::8], gold["filtered"], "fbp2 filtered")
+    assert_close(img[::2, ::2], gold["image_sub"], "fbp2 image")
+
+
+def test_linearity_of_the_whole_pipeline(monte):
+    """size-independent property: FDK is linear in the projections"""
+    g = _abi.generic_fdk_geom(64, 80, 48, 48)
+    a, b = rand(3, (64, 80, 48)), rand(4, (64, 80, 48))
+    va = monte.fdk(g, a, want_filtered=False)[1]
+    vb = monte.fdk(g, b, want_filtered=False)[1]
+    vab = monte.fdk(g, a + 2 * b, want_filtered=False)[1]
+    assert_close(va + 2 * vb, vab, "linearity")
+
+
+def test_device_api_slabs_equal_whole(monte):
+    """z-slab sharding (the multi-GPU partition) reproduces the single launch bit for bit"""
+    import torch
+    g = _abi.generic_fdk_geom(60, 65, 65, 40)
+    proj = torch.from_numpy(rand(8, (60, 65, 65))).cuda()
+    filt = torch.empty(monte.fdk_filtered_shape(g), dtype=torch.float32, device="cuda")
+    monte.fdk_filter_dev(g, proj, filt)
+    whole = torch.empty((g.nz, g.ny, g.nx), dtype=torch.float32, device="cuda")
+    monte.fdk_backproject_dev(g, filt, whole)
+    parts = torch.empty_like(whole)
+    for lo, hi in ((0, 7), (7, 24), (24, 40)):
+        monte.fdk_backproject_dev(g, filt, parts[lo:hi], lo, hi)
+    # filter by view ranges too
+    filt2 = torch.zeros_like(filt)
+    monte.fdk_filter_dev(g, proj, filt2, 0, 25, pad=False)
+    monte.fdk_filter_dev(g, proj, filt2, 25, 60, pad=False)
+    monte.fdk_pad_dev(g, filt2)
+    torch.cuda.synchronize()
+    assert torch.equal(whole, parts)
+    assert torch.equal(filt, filt2)
+    ref = monte.fdk(g, proj.cpu().numpy(), want_filtered=False)[1]
+    assert np.array_equal(whole.cpu().numpy(), ref)
+
+
+def test_bad_arguments_are_reported_not_fatal(monte):
+    g = _abi.generic_fdk_geom(4, 16, 16, 8)
+    g.s_end = 99
+    with pytest.raises(monte.MonteError, match="ROI"):
+        monte.fdk(g, rand(0, (4, 16, 16)))
