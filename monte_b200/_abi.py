@@ -142,6 +142,7 @@ def bp3d20_325_geom():
     g.nu = g.nv = 325
     g.du = g.dv = 0.1
     g.out_scale2 = 5.0
+    g.mask_cs = g.mask_ct = g.mask_cz = 0
     g.mask_r2 = -1
     g.coord_mode = COORD_SCALE_BEFORE
     return g
@@ -154,7 +155,9 @@ def fbp2_geom():
     g.nz = 1
     g.z_begin, g.z_end = 0, 1
     g.s_begin, g.s_end = 0, 256
+    g.mask_cs = g.mask_ct = g.mask_cz = 0
     g.mask_r2 = -1
+    g.dv = 0.5
     g.out_scale = 1.7
     return g
 

@@ -180,3 +180,82 @@ def fdk_unpad_dev(g, d_filt, d_dense, stream=None):
 def fdk_transpose_dev(g, d_xy, d_zy, stream=None):
     _check(load().monte_gpu_fdk_transpose_dev(C.byref(g), C.c_void_p(d_xy.data_ptr()),
                                               C.c_void_p(d_zy.data_ptr()), _stream_ptr(stream)))
+
+
+# ------------------------------------------------------------------ Monte Carlo
+def simulate(g, vol, labels, xs, spec, per, seed=1, views=None):
+    """monte_gpu_simulate on host buffers.  Returns (image0, image5 [n_views][ny][nx] int32, stats dict)."""
+    lib = load()
+    labels = np.ascontiguousarray(labels, np.uint8)
+    vb, ve = views if views else (0, g.n_views)
+    im0 = np.zeros((g.n_views, g.ny, g.nx), np.int32)
+    im5 = np.zeros((g.n_views, g.ny, g.nx), np.int32)
+    st = McStats()
+    _check(lib.monte_gpu_simulate(C.byref(g), C.byref(vol), _ptr(labels), C.byref(xs),
+                                  C.byref(spec) if spec is not None else None, per, seed, vb, ve,
+                                  _ptr(im0), _ptr(im5), C.byref(st)))
+    return im0, im5, _abi.stats_dict(st)
+
+
+class Scene:
+    """Device-resident scene (labels, tables, spectrum) for repeated transport launches."""
+
+    def __init__(self, g, vol, labels, xs, spec):
+        lib = load()
+        self.g = g
+        self._keep = (vol, np.ascontiguousarray(labels, np.uint8), xs, spec)
+        self.handle = C.c_void_p()
+        _check(lib.monte_gpu_scene_create(C.byref(g), C.byref(vol), _ptr(self._keep[1]), C.byref(xs),
+                                          C.byref(spec) if spec is not None else None, C.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            load().monte_gpu_scene_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def simulate_dev(self, d_image0, d_image5, per, seed=1, views=None, n_range=None, d_stats=None, stream=None):
+        """Add photons n in n_range of every pixel of `views` into the cuda int32 tensors
+        d_image0/d_image5 [n_views][ny][nx]; d_stats: cuda int64[16] accumulators or None."""
+        vb, ve = views if views else (0, self.g.n_views)
+        nb, ne = n_range if n_range else (0, per)
+        _check(load().monte_gpu_simulate_dev(self.handle, seed, vb, ve, nb, ne, per,
+                                             C.c_void_p(d_image0.data_ptr()), C.c_void_p(d_image5.data_ptr()),
+                                             C.c_void_p(d_stats.data_ptr()) if d_stats is not None else None,
+                                             _stream_ptr(stream)))
+
+    def fates(self, view, per, seed=1):
+        """Per-history fate records of one view (see include/monte_gpu.h)."""
+        n = self.g.ny * self.g.nx * per
+        f = np.zeros(n, np.uint32)
+        e = np.zeros(n, np.float32)
+        _check(load().monte_gpu_simulate_fates(self.handle, seed, view, per, _ptr(f), _ptr(e)))
+        return f, e
+
+
+def unpack_stats(words):
+    """words: 16 uint64 (numpy) from the device accumulators -> dict"""
+    st = McStats()
+    w = np.ascontiguousarray(words, np.uint64)
+    load().monte_gpu_mc_stats_unpack(_ptr(w), C.byref(st))
+    return _abi.stats_dict(st)
+
+
+def counts_to_map(counts, per):
+    counts = np.ascontiguousarray(counts, np.int32)
+    out = np.empty(counts.shape, np.float32)
+    _check(load().monte_gpu_counts_to_map(_ptr(counts), counts.size, per, _ptr(out)))
+    return out
+
+
+def project_primary(g, vol, labels, xs, keV, views=None):
+    labels = np.ascontiguousarray(labels, np.uint8)
+    vb, ve = views if views else (0, g.n_views)
+    out = np.zeros((g.n_views, g.ny, g.nx), np.float32)
+    _check(load().monte_gpu_project_primary(C.byref(g), C.byref(vol), _ptr(labels), C.byref(xs), keV, vb, ve, _ptr(out)))
+    return out

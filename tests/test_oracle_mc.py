@@ -1,0 +1,148 @@
+"""CPU: the Monte-Carlo oracle against the reference's own outputs and analytic known answers.
+
+The strongest pin: with every quirk of the shipped monte_cpp/CBCT_real2.cpp switched on and the
+reference's MT19937 seeded as the binary is (oracle/shim/windows.h pins time() to 5489), the oracle
+reproduces the unmodified binary's 65x65 scatter image and its three printed counters bit for bit.
+The golden (tests/golden/mc_real2.npz) was produced by tests/golden/make_golden_mc.py.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from monte_b200 import _abi, scenes
+from conftest import GOLDEN
+
+
+def real2_scene():
+    """the as-shipped run: spher01.raw geometry (make_image01.cpp), lookup box of CBCT_real2.cpp:770"""
+    sphere = np.zeros((325, 185, 185), np.uint8)
+    kk, jj, ii = np.ogrid[:325, :185, :185]
+    sphere[((ii - 90) ** 2 + (jj - 90) ** 2 + (kk - 160) ** 2) <= 2500] = 1      # make_image01.cpp:19
+    vol = _abi.McVolume()
+    vol.nx, vol.ny, vol.nz, vol.pitch = 185, 185, 325, 0.1
+    vol.origin[0] = vol.origin[1] = -9.05
+    vol.origin[2] = -16.05
+    for a, (lo, hi) in enumerate(((-6, 10), (-6, 6), (-10, 10))):
+        vol.clip_lo[a], vol.clip_hi[a] = lo, hi
+    return scenes.mc_geom(65, 0.5), vol, sphere
+
+
+def test_philox2x32_known_answers(oracle):
+    """Random123 kat_vectors, philox2x32 10 rounds"""
+    assert oracle.philox2x32(0, 0, 0) == (0xff1dae59, 0x6cd10df2)
+    assert oracle.philox2x32(0xffffffff, 0xffffffff, 0xffffffff) == (0x2c3f628b, 0xab4fd7ad)
+    assert oracle.philox2x32(0x243f6a88, 0x85a308d3, 0x13198a2e) == (0xdd7ce038, 0xf62a4c12)
+
+
+def test_table_known_answers():
+    """SURVEY 8a-A1"""
+    h2o, ca = scenes.load_tables()
+    assert abs(h2o[3, 140] - 0.1538092) < 1e-9 and abs(ca[3, 140] - 0.17730) < 1e-9
+    assert abs(h2o[3, 60] - 0.20585) < 1e-5
+    hq, cq = scenes.load_tables(quirk_bom=True)
+    assert hq[0, 1] == 1.372 and cq[0, 1] == 1.372          # CBCT_real2.cpp:663
+
+
+def test_oracle_reproduces_unmodified_cbct_real2_bit_for_bit(oracle):
+    gold = np.load(os.path.join(GOLDEN, "mc_real2.npz"))
+    g, vol, sphere = real2_scene()
+    assert int(sphere.sum()) == int(gold["sphere_voxels"])
+    h2o, ca = scenes.load_tables(quirk_bom=True)
+    tb = oracle.tables_from_arrays([(h2o, 1.0), (ca, 1.55)])
+    o = oracle.mc_opts(rng_mode=oracle.RNG_MT, quirks=oracle.Q_REAL2, seed=int(gold["seed"]), n_threads=1)
+    im0, im5, res, _, _ = oracle.mc_run(g, vol, sphere, tb, scenes.mono_spectrum(140.0), o, int(gold["per"]),
+                                        views=(0, 1), pixels=(32, 33, 32, 33))
+    assert np.array_equal(im5[0], gold["image"])
+    assert res["num_scatter"] == int(gold["num_scatter"])
+    assert res["num_nd"] == int(gold["num_nd"])
+    assert res["scatter_detected"] == int(gold["count"])
+    assert not im0.any()                                   # CBCT_real2.cpp:290: primaries not tallied
+    # coarse known answers of SURVEY 8c(4): 75.07 % and 1.13 %
+    assert abs(res["num_scatter"] / 1e7 - 0.7507) < 5e-4
+
+
+@pytest.mark.slow
+def test_golden_is_what_the_binary_prints(oracle):
+    if not oracle.have_ref("CBCT_real2"):
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    gold = np.load(os.path.join(GOLDEN, "mc_real2.npz"))
+    img, c, _ = oracle.ref_cbct_real2()
+    assert np.array_equal(img, gold["image"]) and c["count"] == int(gold["count"])
+
+
+def small_scene(n=33, pitch=1.0, det=17, views=4, mode=_abi.SOURCE_PENCIL):
+    lab = scenes.cylinder_phantom(n, pitch)
+    g = scenes.mc_geom(det, 32.5 / det, n_views=views, source_mode=mode)
+    g.angle_step_deg = 90.0 / views * 4
+    return g, scenes.volume_for(lab, pitch), lab
+
+
+def test_primary_transmission_known_answer(oracle):
+    """exp(-mu*L): central pencil through 20 cm of water (SURVEY 8c(4) analytic KAT), both RNGs"""
+    lab = scenes.cylinder_phantom(41, 0.5, rods=False)
+    g = scenes.mc_geom(1, 0.5, n_views=1)
+    g.half = 0.25
+    vol = scenes.volume_for(lab, 0.5)
+    xs = scenes.make_xs()
+    tb = oracle.tables_from_xs(xs)
+    per = 400000
+    chord = 20.5                                             # 41 voxels of 0.5 cm across the diameter
+    p = math.exp(-float(xs.total[0][140]) * chord)
+    for mode in (oracle.RNG_MT, oracle.RNG_PHILOX):
+        im0, im5, res, _, _ = oracle.mc_run(g, vol, lab, tb, scenes.mono_spectrum(140.0),
+                                            oracle.mc_opts(rng_mode=mode, seed=3), per)
+        assert res["primaries"] == im0.sum()
+        assert abs(res["primaries"] / per - p) < 4 * math.sqrt(p * (1 - p) / per)
+        assert res["histories"] == per and im5.sum() == res["primaries"] + res["scatter_detected"]
+
+
+def test_mt_and_philox_modes_agree_statistically(oracle):
+    g, vol, lab = small_scene()
+    tb = oracle.tables_from_xs(scenes.make_xs())
+    per = 3000
+    a = oracle.mc_run(g, vol, lab, tb, scenes.mono_spectrum(140.0), oracle.mc_opts(oracle.RNG_MT, seed=5), per)
+    b = oracle.mc_run(g, vol, lab, tb, scenes.mono_spectrum(140.0), oracle.mc_opts(oracle.RNG_PHILOX, seed=5), per)
+    for k in ("primaries", "scatter_detected", "absorbed", "compton", "coherent"):
+        na, nb = a[2][k], b[2][k]
+        assert abs(na - nb) < 5 * math.sqrt(na + nb + 1), k
+    sa, sb = a[1].astype(np.int64) - a[0], b[1].astype(np.int64) - b[0]       # scatter-only images
+    chi2 = ((sa - sb) ** 2 / np.maximum(sa + sb, 1))[(sa + sb) > 0]
+    assert abs(chi2.sum() - chi2.size) < 5 * math.sqrt(2 * chi2.size)
+
+
+def test_philox_result_is_partition_independent(oracle):
+    g, vol, lab = small_scene(views=2)
+    tb = oracle.tables_from_xs(scenes.make_xs())
+    o = oracle.mc_opts(oracle.RNG_PHILOX, seed=9)
+    whole = oracle.mc_run(g, vol, lab, tb, scenes.mono_spectrum(), o, 40)
+    p1 = oracle.mc_run(g, vol, lab, tb, scenes.mono_spectrum(), o, 40, n_range=(0, 13))
+    p2 = oracle.mc_run(g, vol, lab, tb, scenes.mono_spectrum(), o, 40, n_range=(13, 40))
+    assert np.array_equal(whole[0], p1[0] + p2[0]) and np.array_equal(whole[1], p1[1] + p2[1])
+
+
+def test_project_primary_chord_lengths(oracle):
+    """line integral through the water cylinder = mu * chord (voxelisation error ~ one voxel)"""
+    lab = scenes.cylinder_phantom(81, 0.25, rods=False)
+    g = scenes.mc_geom(33, 32.5 / 33, n_views=3)
+    g.angle_step_deg = 37.0
+    vol = scenes.volume_for(lab, 0.25)
+    xs = scenes.make_xs()
+    m = oracle.project_primary(g, vol, lab, oracle.tables_from_xs(xs), 140.0)
+    mu = float(xs.total[0][140])
+    for v in range(3):
+        i = j = 16                                           # central pixel: chord = diameter 20 cm
+        assert abs(m[v, i, j] / mu - 20.0) < 0.5
+    assert m[:, 0, :].max() == 0                            # the edge rays miss the cylinder
+    assert (m >= 0).all()
+
+
+def test_counts_to_map_known_answers(oracle):
+    c = np.array([0, 1, 50, 2000, 5000], np.int32)
+    m = oracle.counts_to_map(c, 2000)                       # CBCT_real325im.cu:267-285
+    assert m[0] == m[1] and abs(m[0] - math.log(2000.0)) < 1e-6       # 0 counts are clamped to 1
+    assert abs(m[2] - math.log(40.0)) < 1e-6
+    # -log(int) is the double overload, log(float(per)) the float one: counts == per gives the
+    # float rounding of log(2000), not exactly 0; counts > per are clamped to per
+    assert m[3] == m[4] and abs(m[3]) < 2e-7
