@@ -225,8 +225,8 @@ typedef struct monte_mc_stats {
 /* Whole simulation on host buffers.  photons_per_pixel is the reference's `per`
  * (CBCT_real325im.cu:182): histories per view = per*ny*nx.  History id
  * h = (view*ny*nx + pixel)*per + n draws from Philox4x32-10 stream (seed, h), so the
- * result is independent of how histories are partitioned; [hist_begin, hist_end) of the
- * per-view history range lets several processes split a view (0,0 = everything).
+ * result is independent of how histories are partitioned.  view_begin == view_end == 0 means
+ * all views; only the requested views of image0/image5 are written.
  * image0 [n_views][ny][nx] int32: unscattered;  image5: unscattered + scattered
  * (CBCT_real325im.cu:584-585,692,841).  labels: uint8 [nz][ny][nx].                    */
 int monte_gpu_simulate(const monte_mc_geom *g, const monte_mc_volume *vol,
@@ -234,6 +234,15 @@ int monte_gpu_simulate(const monte_mc_geom *g, const monte_mc_volume *vol,
                        const monte_mc_spectrum *spec, uint32_t photons_per_pixel,
                        uint64_t seed, int view_begin, int view_end,
                        int32_t *image0, int32_t *image5, monte_mc_stats *stats);
+
+/* Same, restricted to photons n in [n_begin, n_end) of every pixel: several processes (one per
+ * GPU) split a view and sum their integer tallies; the union equals the undivided run.          */
+int monte_gpu_simulate_range(const monte_mc_geom *g, const monte_mc_volume *vol,
+                             const uint8_t *labels, const monte_mc_xs *xs,
+                             const monte_mc_spectrum *spec, uint32_t photons_per_pixel,
+                             uint32_t n_begin, uint32_t n_end,
+                             uint64_t seed, int view_begin, int view_end,
+                             int32_t *image0, int32_t *image5, monte_mc_stats *stats);
 
 /* Device-resident form: the scene is uploaded once, tallies accumulate into device
  * int32 images [view_end-view_begin... indexed by absolute view][ny][nx].             */

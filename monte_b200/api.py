@@ -53,6 +53,9 @@ def load():
         "monte_gpu_simulate": (C.c_int, [C.POINTER(McGeom), C.POINTER(McVolume), vp, C.POINTER(McXs),
                                          C.POINTER(McSpectrum), u32, u64, C.c_int, C.c_int, vp, vp,
                                          C.POINTER(McStats)]),
+        "monte_gpu_simulate_range": (C.c_int, [C.POINTER(McGeom), C.POINTER(McVolume), vp, C.POINTER(McXs),
+                                               C.POINTER(McSpectrum), u32, u32, u32, u64, C.c_int, C.c_int, vp, vp,
+                                               C.POINTER(McStats)]),
         "monte_gpu_scene_create": (C.c_int, [C.POINTER(McGeom), C.POINTER(McVolume), vp, C.POINTER(McXs),
                                              C.POINTER(McSpectrum), C.POINTER(vp)]),
         "monte_gpu_scene_destroy": (None, [vp]),
@@ -183,17 +186,22 @@ def fdk_transpose_dev(g, d_xy, d_zy, stream=None):
 
 
 # ------------------------------------------------------------------ Monte Carlo
-def simulate(g, vol, labels, xs, spec, per, seed=1, views=None):
-    """monte_gpu_simulate on host buffers.  Returns (image0, image5 [n_views][ny][nx] int32, stats dict)."""
+def simulate(g, vol, labels, xs, spec, per, seed=1, views=None, n_range=None, out=None):
+    """monte_gpu_simulate(_range) on host buffers.  Returns (image0, image5 [n_views][ny][nx] int32,
+    stats dict).  out=(image0, image5) reuses caller (e.g. pinned) buffers; only `views` are written."""
     lib = load()
     labels = np.ascontiguousarray(labels, np.uint8)
     vb, ve = views if views else (0, g.n_views)
-    im0 = np.zeros((g.n_views, g.ny, g.nx), np.int32)
-    im5 = np.zeros((g.n_views, g.ny, g.nx), np.int32)
+    nb, ne = n_range if n_range else (0, per)
+    if out is None:
+        im0 = np.zeros((g.n_views, g.ny, g.nx), np.int32)
+        im5 = np.zeros((g.n_views, g.ny, g.nx), np.int32)
+    else:
+        im0, im5 = out
     st = McStats()
-    _check(lib.monte_gpu_simulate(C.byref(g), C.byref(vol), _ptr(labels), C.byref(xs),
-                                  C.byref(spec) if spec is not None else None, per, seed, vb, ve,
-                                  _ptr(im0), _ptr(im5), C.byref(st)))
+    _check(lib.monte_gpu_simulate_range(C.byref(g), C.byref(vol), _ptr(labels), C.byref(xs),
+                                        C.byref(spec) if spec is not None else None, per, nb, ne, seed, vb, ve,
+                                        _ptr(im0), _ptr(im5), C.byref(st)))
     return im0, im5, _abi.stats_dict(st)
 
 

@@ -370,8 +370,10 @@ struct monte_mc_scene {
     McSceneDev dev;
     monte_mc_geom geom;
     void *d_labels = nullptr, *d_tab = nullptr, *d_inv = nullptr, *d_cdf = nullptr, *d_view = nullptr;
+    size_t cap_labels = 0, cap_tab = 0, cap_cdf = 0, cap_view = 0;     // grow-only capacities (bytes)
     unsigned long long *d_work = nullptr;
     size_t smem = 0;
+    size_t h2d_bytes = 0;
 };
 
 static int check_mc(const monte_mc_geom *g, const monte_mc_volume *vol, const monte_mc_xs *xs) {
@@ -388,18 +390,23 @@ static int check_mc(const monte_mc_geom *g, const monte_mc_volume *vol, const mo
 
 extern "C" {
 
-int monte_gpu_scene_create(const monte_mc_geom *g, const monte_mc_volume *vol, const uint8_t *labels,
-                           const monte_mc_xs *xs, const monte_mc_spectrum *spec, monte_mc_scene **out) {
-    MONTE_REQUIRE_INIT();
-    if (int rc = check_mc(g, vol, xs)) return rc;
-    MONTE_ARG(labels && out, "mc: NULL argument");
-    MONTE_ARG(!spec || spec->n_bins == 0 || (spec->cdf && spec->n_bins > 0 && spec->n_bins <= 4096), "mc: bad spectrum");
-    monte_mc_scene *s = new monte_mc_scene();
+static int grow(void **p, size_t *cap, size_t bytes) {
+    if (bytes <= *cap) return MONTE_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    MONTE_CUDA(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return MONTE_OK;
+}
+
+// (re)fill a scene: device buffers are reused when large enough; copies are issued on `st`
+static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_mc_volume *vol, const uint8_t *labels,
+                        const monte_mc_xs *xs, const monte_mc_spectrum *spec, cudaStream_t st) {
     s->geom = *g;
     McSceneDev &d = s->dev;
     const size_t nvox = (size_t)vol->nx * vol->ny * vol->nz;
-    MONTE_CUDA(cudaMalloc(&s->d_labels, nvox));
-    MONTE_CUDA(cudaMemcpy(s->d_labels, labels, nvox, cudaMemcpyHostToDevice));
+    if (int rc = grow(&s->d_labels, &s->cap_labels, nvox)) return rc;
+    MONTE_CUDA(cudaMemcpyAsync(s->d_labels, labels, nvox, cudaMemcpyHostToDevice, st));
     d.labels = (const uint8_t *)s->d_labels;
     d.nx = vol->nx; d.ny = vol->ny; d.nz = vol->nz;
     d.inv_pitch = (float)(1.0 / vol->pitch);
@@ -422,18 +429,21 @@ int monte_gpu_scene_create(const monte_mc_geom *g, const monte_mc_volume *vol, c
             tab[(size_t)m * TAB_ROWS + k] = t;
         }
     }
-    MONTE_CUDA(cudaMalloc(&s->d_tab, tab.size() * sizeof(float4)));
-    MONTE_CUDA(cudaMemcpy(s->d_tab, tab.data(), tab.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    MONTE_CUDA(cudaMalloc(&s->d_inv, inv.size() * sizeof(float)));
-    MONTE_CUDA(cudaMemcpy(s->d_inv, inv.data(), inv.size() * sizeof(float), cudaMemcpyHostToDevice));
+    const size_t tab_bytes = tab.size() * sizeof(float4), inv_bytes = inv.size() * sizeof(float);
+    if (int rc = grow(&s->d_tab, &s->cap_tab, tab_bytes + inv_bytes)) return rc;
+    s->d_inv = (char *)s->d_tab + tab_bytes;
+    MONTE_CUDA(cudaMemcpyAsync(s->d_tab, tab.data(), tab_bytes, cudaMemcpyHostToDevice, st));
+    MONTE_CUDA(cudaMemcpyAsync(s->d_inv, inv.data(), inv_bytes, cudaMemcpyHostToDevice, st));
     d.tab = (const float4 *)s->d_tab; d.inv_mumax = (const float *)s->d_inv; d.n_mat = nm;
     d.n_bins = 0; d.cdf = nullptr; d.bin_keV = 0.5f; d.mono_keV = 140.f;
+    size_t cdf_bytes = 0;
     if (spec) {
         d.mono_keV = (float)spec->mono_keV; d.bin_keV = (float)spec->bin_keV;
         if (spec->n_bins > 0) {
             d.n_bins = spec->n_bins;
-            MONTE_CUDA(cudaMalloc(&s->d_cdf, (spec->n_bins + 1) * sizeof(float)));
-            MONTE_CUDA(cudaMemcpy(s->d_cdf, spec->cdf, (spec->n_bins + 1) * sizeof(float), cudaMemcpyHostToDevice));
+            cdf_bytes = (spec->n_bins + 1) * sizeof(float);
+            if (int rc = grow(&s->d_cdf, &s->cap_cdf, cdf_bytes)) return rc;
+            MONTE_CUDA(cudaMemcpyAsync(s->d_cdf, spec->cdf, cdf_bytes, cudaMemcpyHostToDevice, st));
             d.cdf = (const float *)s->d_cdf;
         }
     }
@@ -442,22 +452,36 @@ int monte_gpu_scene_create(const monte_mc_geom *g, const monte_mc_volume *vol, c
         const double beta = M_PI * (g->angle0_deg + g->angle_step_deg * v) / 180;
         vcs[v] = make_float2((float)cos(beta), (float)sin(beta));
     }
-    MONTE_CUDA(cudaMalloc(&s->d_view, vcs.size() * sizeof(float2)));
-    MONTE_CUDA(cudaMemcpy(s->d_view, vcs.data(), vcs.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    if (int rc = grow(&s->d_view, &s->cap_view, vcs.size() * sizeof(float2))) return rc;
+    MONTE_CUDA(cudaMemcpyAsync(s->d_view, vcs.data(), vcs.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
     d.view_cs = (const float2 *)s->d_view;
     d.n_views = g->n_views; d.det_ny = g->ny; d.det_nx = g->nx;
     d.pixel = (float)g->pixel; d.inv_pixel = (float)(1.0 / g->pixel); d.half = (float)g->half;
     d.dso = (float)g->dso; d.dod = (float)g->dod; d.dsd = (float)(g->dso + g->dod);
     d.source_mode = g->source_mode; d.max_scatter = g->max_scatter;
-    MONTE_CUDA(cudaMalloc(&s->d_work, sizeof(unsigned long long)));
+    if (!s->d_work) MONTE_CUDA(cudaMalloc(&s->d_work, sizeof(unsigned long long)));
     s->smem = (size_t)nm * TAB_ROWS * sizeof(float4) + (TAB_ROWS + 3 + d.n_bins + 1) * sizeof(float);
+    s->h2d_bytes = nvox + tab_bytes + inv_bytes + cdf_bytes + vcs.size() * sizeof(float2);
+    // the host vectors above are pageable: the async copies have already staged them
+    MONTE_CUDA(cudaStreamSynchronize(st));
+    return MONTE_OK;
+}
+
+int monte_gpu_scene_create(const monte_mc_geom *g, const monte_mc_volume *vol, const uint8_t *labels,
+                           const monte_mc_xs *xs, const monte_mc_spectrum *spec, monte_mc_scene **out) {
+    MONTE_REQUIRE_INIT();
+    if (int rc = check_mc(g, vol, xs)) return rc;
+    MONTE_ARG(labels && out, "mc: NULL argument");
+    MONTE_ARG(!spec || spec->n_bins == 0 || (spec->cdf && spec->n_bins > 0 && spec->n_bins <= 4096), "mc: bad spectrum");
+    monte_mc_scene *s = new monte_mc_scene();
+    if (int rc = scene_upload(s, g, vol, labels, xs, spec, ctx().stream)) { monte_gpu_scene_destroy(s); return rc; }
     *out = s;
     return MONTE_OK;
 }
 
 void monte_gpu_scene_destroy(monte_mc_scene *s) {
     if (!s) return;
-    cudaFree(s->d_labels); cudaFree(s->d_tab); cudaFree(s->d_inv); cudaFree(s->d_cdf); cudaFree(s->d_view); cudaFree(s->d_work);
+    cudaFree(s->d_labels); cudaFree(s->d_tab); cudaFree(s->d_cdf); cudaFree(s->d_view); cudaFree(s->d_work);
     delete s;
 }
 
@@ -514,51 +538,62 @@ void monte_gpu_mc_stats_unpack(const unsigned long long *w, monte_mc_stats *out)
     out->sum_e_scatter = (double)w[ST_ESCAT] / 1024.0;
 }
 
+// scene kept between monte_gpu_simulate calls: device buffers are reused, contents re-uploaded
+static monte_mc_scene *g_host_scene = nullptr;
+
 int monte_gpu_simulate(const monte_mc_geom *g, const monte_mc_volume *vol, const uint8_t *labels, const monte_mc_xs *xs,
                        const monte_mc_spectrum *spec, uint32_t photons_per_pixel, uint64_t seed, int view_begin,
                        int view_end, int32_t *image0, int32_t *image5, monte_mc_stats *stats) {
+    return monte_gpu_simulate_range(g, vol, labels, xs, spec, photons_per_pixel, 0, photons_per_pixel, seed,
+                                    view_begin, view_end, image0, image5, stats);
+}
+
+int monte_gpu_simulate_range(const monte_mc_geom *g, const monte_mc_volume *vol, const uint8_t *labels,
+                             const monte_mc_xs *xs, const monte_mc_spectrum *spec, uint32_t photons_per_pixel,
+                             uint32_t n_begin, uint32_t n_end, uint64_t seed, int view_begin, int view_end,
+                             int32_t *image0, int32_t *image5, monte_mc_stats *stats) {
     MONTE_REQUIRE_INIT();
     if (int rc = check_mc(g, vol, xs)) return rc;
-    MONTE_ARG(image0 && image5, "mc: NULL image");
+    MONTE_ARG(labels && image0 && image5, "mc: NULL buffer");
+    MONTE_ARG(!spec || spec->n_bins == 0 || (spec->cdf && spec->n_bins > 0 && spec->n_bins <= 4096), "mc: bad spectrum");
     if (view_begin == 0 && view_end == 0) view_end = g->n_views;
+    MONTE_ARG(0 <= view_begin && view_begin <= view_end && view_end <= g->n_views, "mc: bad view range");
     Context &c = ctx();
     cudaStream_t st = c.stream;
     EventTimer t_all(st), t_h2d(st), t_k(st), t_d2h(st);
     t_all.start();
     t_h2d.start();
-    monte_mc_scene *s = nullptr;
-    if (int rc = monte_gpu_scene_create(g, vol, labels, xs, spec, &s)) return rc;
+    if (!g_host_scene) g_host_scene = new monte_mc_scene();
+    monte_mc_scene *s = g_host_scene;
+    if (int rc = scene_upload(s, g, vol, labels, xs, spec, st)) return rc;
     t_h2d.stop();
-    const size_t n_img = (size_t)g->n_views * g->ny * g->nx;
-    int32_t *d_im = (int32_t *)scratch(5, 2 * n_img * sizeof(int32_t) + MONTE_MC_STATS_WORDS * sizeof(unsigned long long));
-    if (!d_im) { monte_gpu_scene_destroy(s); return MONTE_E_NOMEM; }
-    unsigned long long *d_stats = (unsigned long long *)(d_im + 2 * n_img);
-    int rc = MONTE_OK;
-    do {
-        if (cudaMemsetAsync(d_im, 0, 2 * n_img * sizeof(int32_t) + MONTE_MC_STATS_WORDS * sizeof(unsigned long long), st) != cudaSuccess) { rc = MONTE_E_CUDA; break; }
-        t_k.start();
-        rc = launch_mc(s, seed, view_begin, view_end, 0, photons_per_pixel, photons_per_pixel, d_im, d_im + n_img, d_stats, nullptr, nullptr, st);
-        t_k.stop();
-        if (rc) break;
-        t_d2h.start();
-        unsigned long long w[MONTE_MC_STATS_WORDS];
-        if (cudaMemcpyAsync(image0, d_im, n_img * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-            cudaMemcpyAsync(image5, d_im + n_img, n_img * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-            cudaMemcpyAsync(w, d_stats, sizeof(w), cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = MONTE_E_CUDA; break; }
-        t_d2h.stop();
-        t_all.stop();
-        cudaError_t e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) { rc = cuda_fail(e, "mc_transport_kernel", __FILE__, __LINE__); break; }
-        if (stats) {
-            memset(stats, 0, sizeof(*stats));
-            monte_gpu_mc_stats_unpack(w, stats);
-            stats->ms_h2d = t_h2d.ms(); stats->ms_kernel = t_k.ms(); stats->ms_d2h = t_d2h.ms(); stats->ms_total = t_all.ms();
-            stats->launches = 1; stats->sm_count = c.sm_count;
-        }
-    } while (0);
-    if (rc == MONTE_E_CUDA && monte_gpu_last_error()[0] == 0) set_error("CUDA error in monte_gpu_simulate: %s", cudaGetErrorString(cudaGetLastError()));
-    monte_gpu_scene_destroy(s);
-    return rc;
+    // tallies of the requested views only; the kernel indexes by absolute view
+    const size_t npix = (size_t)g->ny * g->nx, n_img = (size_t)(view_end - view_begin) * npix;
+    const size_t bytes = 2 * n_img * sizeof(int32_t) + MONTE_MC_STATS_WORDS * sizeof(unsigned long long);
+    int32_t *d_im = (int32_t *)scratch(5, bytes + 16);
+    if (!d_im) return MONTE_E_NOMEM;
+    unsigned long long *d_stats = (unsigned long long *)(((uintptr_t)(d_im + 2 * n_img) + 7) & ~(uintptr_t)7);
+    MONTE_CUDA(cudaMemsetAsync(d_im, 0, bytes + 16, st));
+    t_k.start();
+    if (int rc = launch_mc(s, seed, view_begin, view_end, n_begin, n_end, photons_per_pixel,
+                           d_im - (size_t)view_begin * npix, d_im + n_img - (size_t)view_begin * npix, d_stats,
+                           nullptr, nullptr, st)) return rc;
+    t_k.stop();
+    t_d2h.start();
+    unsigned long long w[MONTE_MC_STATS_WORDS];
+    MONTE_CUDA(cudaMemcpyAsync(image0 + (size_t)view_begin * npix, d_im, n_img * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MONTE_CUDA(cudaMemcpyAsync(image5 + (size_t)view_begin * npix, d_im + n_img, n_img * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MONTE_CUDA(cudaMemcpyAsync(w, d_stats, sizeof(w), cudaMemcpyDeviceToHost, st));
+    t_d2h.stop();
+    t_all.stop();
+    MONTE_CUDA(cudaStreamSynchronize(st));
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        monte_gpu_mc_stats_unpack(w, stats);
+        stats->ms_h2d = t_h2d.ms(); stats->ms_kernel = t_k.ms(); stats->ms_d2h = t_d2h.ms(); stats->ms_total = t_all.ms();
+        stats->launches = 1; stats->sm_count = c.sm_count;
+    }
+    return MONTE_OK;
 }
 
 int monte_gpu_simulate_fates(const monte_mc_scene *s, uint64_t seed, int view, uint32_t photons_per_pixel,

@@ -1,0 +1,85 @@
+"""One-process-per-GPU sharding of the two hot paths (torch.distributed is plumbing only).
+
+MC  : histories are independent.  Every rank runs photons n in its slice of [0, per) for the same
+      views (history ids are global, so the union is identical to a single-GPU run) and the integer
+      tallies are summed with ONE reduce to rank 0 per batch of views.  No other data-path exchange.
+FDK : the volume is cut into z-slabs, the filter into view ranges.  One exchange step: every rank's
+      filtered views are gathered by all ranks (all_gather when views divide evenly, else one
+      broadcast per rank); after that each rank backprojects its own slab and nothing is exchanged.
+
+The compute callables are injected, so the same code is exercised on CPU with the gloo backend
+(tests/test_dist_cpu.py) and on B200s with NCCL (bench.py, tests/test_dist_gpu.py).
+"""
+import torch
+import torch.distributed as dist
+
+
+def split_range(n, world, rank):
+    """Contiguous balanced split of range(n): sizes differ by at most one, earlier ranks get the extra."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def is_dist():
+    return dist.is_available() and dist.is_initialized()
+
+
+def world():
+    return (dist.get_rank(), dist.get_world_size()) if is_dist() else (0, 1)
+
+
+# ----------------------------------------------------------------------------------- MC
+def mc_sharded_step(run_local, image0, image5, per, views, reduce=True):
+    """run_local(image0, image5, per, views, n_range) adds this rank's photons into the (zeroed)
+    image tensors [n_views][ny][nx] int32; then the view slices are summed onto rank 0."""
+    rank, ws = world()
+    n_range = split_range(per, ws, rank)
+    run_local(image0, image5, per, views, n_range)
+    if ws > 1 and reduce:
+        vb, ve = views
+        dist.reduce(image0[vb:ve], dst=0, op=dist.ReduceOp.SUM)
+        dist.reduce(image5[vb:ve], dst=0, op=dist.ReduceOp.SUM)
+    return n_range
+
+
+# ----------------------------------------------------------------------------------- FDK
+def fdk_gather_filtered(filt_rows, n_views, nv, ws):
+    """filt_rows: [n_views*nv + 2][pitch] tensor in which this rank has filled the rows of its own
+    view range (split_range(n_views, ws, rank)); afterwards every rank holds all views."""
+    if ws == 1:
+        return
+    pitch = filt_rows.shape[1]
+    body = filt_rows[: n_views * nv].view(-1)
+    if n_views % ws == 0:
+        chunk = (n_views // ws) * nv * pitch
+        rank = dist.get_rank()
+        dist.all_gather_into_tensor(body, body[rank * chunk:(rank + 1) * chunk])
+    else:
+        for r in range(ws):
+            lo, hi = split_range(n_views, ws, r)
+            if hi > lo:
+                dist.broadcast(body[lo * nv * pitch: hi * nv * pitch], src=r)
+
+
+def fdk_sharded(filter_views, pad, backproject_slab, filt_rows, n_views, nv, nz):
+    """filter_views(view_lo, view_hi) fills this rank's rows of filt_rows; pad() fixes the duplicated
+    column / trailing rows; backproject_slab(z_lo, z_hi) reconstructs this rank's slab.
+    Returns (view range, z range) of this rank."""
+    rank, ws = world()
+    v_lo, v_hi = split_range(n_views, ws, rank)
+    z_lo, z_hi = split_range(nz, ws, rank)
+    filter_views(v_lo, v_hi)
+    fdk_gather_filtered(filt_rows, n_views, nv, ws)
+    pad()
+    backproject_slab(z_lo, z_hi)
+    return (v_lo, v_hi), (z_lo, z_hi)
+
+
+def max_over_ranks(value, device):
+    """max of a python float over ranks (timing rule: a multi-GPU time is the slowest rank's)"""
+    if not is_dist() or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

@@ -258,6 +258,8 @@ static int delta_sampling(const scene_t *S, rng_t *R, photon_t *p, double E, dou
     return collided;
 }
 
+#define TALLY(x) __atomic_fetch_add(&(x), 1, __ATOMIC_RELAXED)
+
 /* detector bin: result = -1*(int(d*inv_pixel - n/2.))   CBCT_real325im.cu:574-575 / CBCT_real2.cpp:311 */
 static int det_bin(double d, double inv_pixel, int n) { return -1 * ((int)(d * inv_pixel - n / 2.)); }
 
@@ -367,8 +369,8 @@ static void history(const scene_t *S, rng_t *R, int view, int i, int j, uint64_t
         double d_y = ((y_r - 0) / (x_r - (-g->dso))) * g->dod + g->dso * y_r / (x_r + g->dso);
         int ry = det_bin(d_y, inv_pixel, g->ny), rx = det_bin(d_z, inv_pixel, g->nx);
         if (!(q & OQ_NO_PRIMARY_TALLY) && ry >= 0 && ry < g->ny && rx >= 0 && rx < g->nx) {
-            image0[ry * g->nx + rx]++;
-            image5[ry * g->nx + rx]++;
+            TALLY(image0[ry * g->nx + rx]);
+            TALLY(image5[ry * g->nx + rx]);
         }
         bin = (uint32_t)(ry * g->nx + rx);
     } else {
@@ -418,7 +420,7 @@ static void history(const scene_t *S, rng_t *R, int view, int i, int j, uint64_t
                     if (x_rot >= g->dod && fabs(d_z) <= g->half && fabs(d_y) <= g->half) {
                         int ry = det_bin(d_y, inv_pixel, g->ny), rx = det_bin(d_z, inv_pixel, g->nx);
                         if (ry >= 0 && ry < g->ny && rx >= 0 && rx < g->nx) {
-                            image5[ry * g->nx + rx]++;
+                            TALLY(image5[ry * g->nx + rx]);
                             res->scatter_detected++;
                             res->sum_e_scatter += E;
                             kind = 2; bin = (uint32_t)(ry * g->nx + rx);
@@ -475,7 +477,7 @@ static void history(const scene_t *S, rng_t *R, int view, int i, int j, uint64_t
                         int ry = det_bin(d_y, inv_pixel, g->ny), rx = det_bin(d_z, inv_pixel, g->nx);
                         res->scatter_detected++;
                         res->sum_e_scatter += E;
-                        image5[ry * g->nx + rx]++;
+                        TALLY(image5[ry * g->nx + rx]);
                         kind = 2; bin = (uint32_t)(ry * g->nx + rx);
                     } else if (P.x > g->dod || fabs(P.y) > g->half || fabs(P.z) > g->half) res->num_nd++;
                 } else {                                     /* CBCT_real325im.cu:823-843 */
@@ -486,7 +488,7 @@ static void history(const scene_t *S, rng_t *R, int view, int i, int j, uint64_t
                     if (x_rotate >= g->dod && fabs(d_z) <= g->half && fabs(d_y) <= g->half) {
                         int ry = det_bin(d_y, inv_pixel, g->ny), rx = det_bin(d_z, inv_pixel, g->nx);
                         if (ry >= 0 && ry < g->ny && rx >= 0 && rx < g->nx) {
-                            image5[ry * g->nx + rx]++;
+                            TALLY(image5[ry * g->nx + rx]);
                             res->scatter_detected++;
                             res->sum_e_scatter += E;
                             kind = 2; bin = (uint32_t)(ry * g->nx + rx);
@@ -508,7 +510,7 @@ static void history(const scene_t *S, rng_t *R, int view, int i, int j, uint64_t
 /* Run photons n in [n_begin, n_end) of pixels [i_begin,i_end) x [j_begin,j_end) of views
  * [view_begin, view_end).  image0/image5: [n_views][ny][nx] int32, accumulated into.
  * MT mode is sequential in the reference's loop order (view, i, j, photon) when n_threads == 1;
- * with more threads each view gets its own MT stream seeded seed+view (statistical use only).
+ * with more threads each (view, detector row) task gets its own MT stream (statistical use only).
  * fates (nullable): one record per history of a single view, index (i*nx + j)*per + n.          */
 int oracle_mc_run(const monte_mc_geom *g, const monte_mc_volume *vol, const uint8_t *labels,
                   const oracle_mc_tables *tb, const monte_mc_spectrum *spec, const oracle_mc_opts *o,
@@ -522,24 +524,26 @@ int oracle_mc_run(const monte_mc_geom *g, const monte_mc_volume *vol, const uint
     if (o->rng_mode == ORACLE_RNG_MT && nthreads != 1 && (o->quirks & OQ_EXTRA_DRAW)) nthreads = 1;
     mt_state shared_mt;
     mt_seed(&shared_mt, (uint32_t)o->seed);
+    const int nrows = i_end - i_begin;
+    const long n_tasks = (long)(view_end - view_begin) * nrows;     /* one task = one detector row of one view */
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads > 0 ? nthreads : omp_get_max_threads()) if (nthreads != 1)
-    for (int view = view_begin; view < view_end; view++) {
+    for (long task = 0; task < n_tasks; task++) {
+        const int view = view_begin + (int)(task / nrows), i = i_begin + (int)(task % nrows);
         oracle_mc_result local; memset(&local, 0, sizeof(local));
         mt_state my_mt;
         rng_t R; memset(&R, 0, sizeof(R));
         R.mode = o->rng_mode;
         if (nthreads == 1) R.mt = &shared_mt;
-        else { mt_seed(&my_mt, (uint32_t)(o->seed + 7919u * (uint32_t)view)); R.mt = &my_mt; }
+        else { mt_seed(&my_mt, (uint32_t)(o->seed + 7919u * (uint32_t)(view * g->ny + i))); R.mt = &my_mt; }
         int32_t *im0 = image0 + (size_t)view * npix, *im5 = image5 + (size_t)view * npix;
-        for (int i = i_begin; i < i_end; i++)
-            for (int j = j_begin; j < j_end; j++)
-                for (uint32_t n = n_begin; n < n_end; n++) {
-                    const size_t pix = (size_t)i * g->nx + j;
-                    const uint64_t hid = ((uint64_t)view * npix + pix) * per + n;
-                    uint32_t *f = fates ? fates + (pix * per + n) : NULL;
-                    float *fe = (fates && fate_e) ? fate_e + (pix * per + n) : NULL;
-                    history(&S, &R, view, i, j, hid, im0, im5, &local, f, fe);
-                }
+        for (int j = j_begin; j < j_end; j++)
+            for (uint32_t n = n_begin; n < n_end; n++) {
+                const size_t pix = (size_t)i * g->nx + j;
+                const uint64_t hid = ((uint64_t)view * npix + pix) * per + n;
+                uint32_t *f = fates ? fates + (pix * per + n) : NULL;
+                float *fe = (fates && fate_e) ? fate_e + (pix * per + n) : NULL;
+                history(&S, &R, view, i, j, hid, im0, im5, &local, f, fe);
+            }
 #pragma omp critical
         {
             result->histories += local.histories; result->primaries += local.primaries;
