@@ -1,0 +1,40 @@
+"""Summarise an .ncu-rep (read here, no GPU needed) into a small text file for profiles/."""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__occupancy_limit_registers", "sm__cycles_elapsed.avg.per_second",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_adu.avg.pct_of_peak_sustained_active", "l1tex__throughput.avg.pct_of_peak_sustained_active"]
+
+
+def main(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    r = list(csv.reader(io.StringIO(out)))
+    h, u = r[0], r[1]
+    for row in r[2:]:
+        name = row[h.index("Kernel Name")] if "Kernel Name" in h else "?"
+        print("kernel: %s" % name)
+        for k in KEYS:
+            if k in h:
+                print("  %-72s %s %s" % (k, row[h.index(k)], u[h.index(k)]))
+        st = []
+        for i, n in enumerate(h):
+            if "issue_stalled" in n and n.endswith("per_issue_active.ratio"):
+                try:
+                    st.append((float(row[i]), n.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")))
+                except ValueError:
+                    pass
+        st.sort(reverse=True)
+        print("  stall reasons (warps per issue): " + ", ".join("%s %.2f" % (n, v) for v, n in st[:8]))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
