@@ -1,0 +1,61 @@
+// cbct_mc — the role of the main() of monte_cu/CBCT_real325im.cu (:83-297): read the label volume and
+// the cross-section tables, run the photon transport, write the count images and the -log maps in
+// the reference's headerless layouts (proj*_0 / proj*_5 int32, map*_0 / map*_5 float32, [view][y][x]).
+//   cbct_mc labels.raw N pitch_cm xcom2.csv Ca.csv [det=325] [pixel=0.1] [views=360] [per=10000] [seed=0] [tag=out]
+// All compute is in libmonte_gpu (no CPU fallback: the call fails without a B200).
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <string>
+#include <vector>
+#include "monte_gpu.h"
+
+static int fail() { fprintf(stderr, "cbct_mc: %s\n", monte_gpu_last_error()); return 1; }
+static void write_raw(const std::string &fn, const void *p, size_t bytes) {
+    FILE *f = fopen(fn.c_str(), "wb");
+    if (!f || fwrite(p, 1, bytes, f) != bytes) { fprintf(stderr, "failed to write %s\n", fn.c_str()); exit(1); }
+    fclose(f);
+}
+
+int main(int argc, char **argv) {
+    if (argc < 6) { fprintf(stderr, "usage: cbct_mc labels.raw N pitch xcom2.csv Ca.csv [det] [pixel] [views] [per] [seed] [tag]\n"); return 2; }
+    const int n = atoi(argv[2]);
+    const double pitch = atof(argv[3]);
+    const int det = argc > 6 ? atoi(argv[6]) : 325;
+    const double pixel = argc > 7 ? atof(argv[7]) : 0.1;
+    const int views = argc > 8 ? atoi(argv[8]) : 360;
+    const uint32_t per = argc > 9 ? (uint32_t)atol(argv[9]) : 10000;     // num_photon, CBCT_real325im.cu:6
+    const uint64_t seed = argc > 10 ? strtoull(argv[10], nullptr, 10) : 0;
+    const std::string tag = argc > 11 ? argv[11] : "out";
+    std::vector<uint8_t> lab((size_t)n * n * n);
+    FILE *f = fopen(argv[1], "rb");
+    if (!f || fread(lab.data(), 1, lab.size(), f) != lab.size()) { fprintf(stderr, "failed to read %s\n", argv[1]); return 1; }
+    fclose(f);
+    std::unique_ptr<monte_mc_xs> xs(new monte_mc_xs());
+    if (monte_xs_load_csv(argv[4], 0, 1.0f, 1, xs.get()) || monte_xs_load_csv(argv[5], 1, 1.55f, 1, xs.get())) return fail();
+    monte_mc_geom g = {};
+    g.n_views = views; g.angle0_deg = 0; g.angle_step_deg = 360.0 / views;
+    g.ny = g.nx = det; g.pixel = pixel; g.half = 0.5 * det * pixel; g.dso = 160; g.dod = 60;   // :459
+    g.source_mode = MONTE_MC_SOURCE_PENCIL; g.max_scatter = 5;                                    // :7
+    monte_mc_volume v = {};
+    v.nx = v.ny = v.nz = n; v.pitch = pitch;
+    for (int a = 0; a < 3; a++) { v.origin[a] = -0.5 * n * pitch; v.clip_lo[a] = v.origin[a]; v.clip_hi[a] = -v.origin[a]; }
+    monte_mc_spectrum sp = {0, 0.5, 140.0, nullptr};                                              // as shipped: 140 keV
+    if (monte_gpu_init(1, nullptr)) return fail();
+    const size_t n_img = (size_t)views * det * det;
+    std::vector<int32_t> im0(n_img), im5(n_img);
+    std::vector<float> map(n_img);
+    monte_mc_stats st;
+    if (monte_gpu_simulate(&g, &v, lab.data(), xs.get(), &sp, per, seed, 0, views, im0.data(), im5.data(), &st)) return fail();
+    printf("count = %llu primaries + %llu scattered / %llu histories, %.1f ms on the GPU (%.3g histories/s)\n",
+           (unsigned long long)st.primaries, (unsigned long long)st.scatter_detected, (unsigned long long)st.histories,
+           st.ms_kernel, st.histories / (st.ms_kernel * 1e-3));
+    write_raw("proj_" + tag + "0.raw", im0.data(), n_img * 4);
+    write_raw("proj_" + tag + "5.raw", im5.data(), n_img * 4);
+    if (monte_gpu_counts_to_map(im0.data(), n_img, (int32_t)per, map.data())) return fail();
+    write_raw("map_" + tag + "0.raw", map.data(), n_img * 4);
+    if (monte_gpu_counts_to_map(im5.data(), n_img, (int32_t)per, map.data())) return fail();
+    write_raw("map_" + tag + "5.raw", map.data(), n_img * 4);
+    monte_gpu_shutdown();
+    return 0;
+}
