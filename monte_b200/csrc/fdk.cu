@@ -235,80 +235,110 @@ __device__ __forceinline__ float bp_bilinear(const float *__restrict__ f, int pi
     return fmaf(fy, hi - lo, lo);
 }
 
+// exact contribution of one band voxel (rare path, kept out of line and out of the hot loop)
+__device__ __noinline__ float bp_fix_one(const BpParams &p, const ViewConst &c, int s, int t, int z,
+                                         const float *__restrict__ fv, float wgt) {
+    float xe, ye;
+    if (!bp_exact(p, c, s, t, z, xe, ye) || xe < 0.f) return 0.f;
+    xe = fminf(fmaxf(xe, 0.f), (float)p.nv);
+    ye = fminf(fmaxf(ye, 0.f), (float)p.nu);
+    return wgt * bp_bilinear(fv, p.pitch, xe, ye);
+}
+
+// Hot loop structure per view: (1) everything that depends on (s,t,view) only; (2) for a batch of
+// ZB z-slices: coordinates, then all 4*ZB gathers issued back to back (unconditional, clamped
+// addresses, no branch or call in between so they overlap), then the bilinear FMAs with a select;
+// (3) voxels inside the narrow bands around the detector edge contribute nothing in (2) and are
+// added exactly afterwards.
 template <int ZT>
-__global__ void __launch_bounds__(BP_TX *BP_TY)
+__global__ void __launch_bounds__(BP_TX *BP_TY, 3)
 fdk_backproject_kernel(const __grid_constant__ BpParams p) {
+    constexpr int ZB = 8;
     const int s = p.s_begin + blockIdx.x * BP_TX + threadIdx.x;
     const int t = p.t_begin + blockIdx.y * BP_TY + threadIdx.y;
-    const int zb = p.z_lo + blockIdx.z * ZT;
+    // z blocks are aligned to absolute multiples of ZT so that the per-slice increments below round
+    // identically however the volume is cut into slabs (multi-GPU slabs == single launch, bit for bit)
+    const int zb = (p.z_lo / ZT) * ZT + blockIdx.z * ZT;
     if (s >= p.s_end || t >= p.t_end) return;
 
     const float X = fmaf(p.vox, (float)s, p.x0);
     const float Y = fmaf(-p.vox, (float)t, p.y0);
-    float Zc[ZT], acc[ZT];
+    const float Z0 = fmaf(-p.vox, (float)zb, p.z0);
+    float acc[ZT];
 #pragma unroll
-    for (int i = 0; i < ZT; i++) {
-        Zc[i] = fmaf(-p.vox, (float)(zb + i), p.z0);
-        acc[i] = 0.f;
-    }
+    for (int i = 0; i < ZT; i++) acc[i] = 0.f;
     const float xoff = p.half_v * p.inv_dv;
-    const int nz_here = min(ZT, p.z_hi - zb);
+    const float hv_in = p.half_v - p.eps_v, hu_in = p.half_u - p.eps_u;
+    const float nvf = (float)p.nv, nuf = (float)p.nu;
 
     for (int v = 0; v < p.n_views; v++) {
-        const ViewConst &c = p.vc[v];
-        const float cb = c.cb, sb = c.sb;
+        const float4 cv = __ldg(reinterpret_cast<const float4 *>(p.vc + v));     // cb, sb, ca, sa
+        const float cb = cv.x, sb = cv.y;
         const float rx = fmaf(X, cb, fmaf(Y, sb, p.dso));       // distance from the source along the axis
         const float ry = fmaf(Y, cb, -X * sb);
         const float k = __fdividef(p.dsd, rx);
         const float u = k * ry;
         const float au = fabsf(u);
-        const bool u_band = fabsf(au - p.half_u) < p.eps_u;
-        if (au > p.half_u && !u_band) continue;                 // bp3d20.cpp:116
-        float y = (p.half_u - u) * p.inv_du;
+        if (au > p.half_u + p.eps_u) continue;                  // bp3d20.cpp:116
+        const bool u_ok = au <= hu_in;                          // else: inside the u band -> exact path for the column
         float wgt;
         if (!p.textbook) {
             const float ts = fmaf(X, cb, -Y * sb);               // bp3d20.cpp:134-142
             const float tt = fmaf(X, sb, Y * cb);
-            float d = fabsf(fmaf(ts, c.ca, -tt * c.sa));
+            float d = fabsf(fmaf(ts, cv.z, -tt * cv.w));
             bool neg = ts < 0.f;
-            if (fabsf(ts) < p.eps_ts) neg = bp_exact_ts_negative(p, c, s, t);
+            if (fabsf(ts) < p.eps_ts) neg = bp_exact_ts_negative(p, p.vc[v], s, t);
             d = neg ? -d : d;
             const float e = p.wd - d;
             wgt = __fdividef(p.wd2, e * e) * p.out_fac;
         } else {
             wgt = __fdividef(p.dso * p.dso, rx * rx) * p.out_fac;
         }
+        const float y = fminf(fmaxf((p.half_u - u) * p.inv_du, 0.f), nuf);
+        const int yi = (int)y;
+        const float fy = y - (float)yi;
+        const float *__restrict__ fv = p.filt + (size_t)v * p.nv * p.pitch;
+        const float *__restrict__ q0 = fv + yi;
         const float kz = k * p.inv_dv;
-        const float *fv = p.filt + (size_t)v * p.nv * p.pitch;
+        const float kzv = kz * p.vox, kv = k * p.vox;            // per-slice increments of x and w
+        const float x0v = fmaf(-kz, Z0, xoff), w0v = k * Z0;
+        unsigned band = 0;
 #pragma unroll
-        for (int i = 0; i < ZT; i++) {
-            const float w = k * Zc[i];
-            const float aw = fabsf(w);
-            float x = fmaf(-kz, Zc[i], xoff);
-            float yy = y;
-            bool use = aw <= p.half_v && au <= p.half_u;
-            if (u_band || fabsf(aw - p.half_v) < p.eps_v) {
-                if (aw > p.half_v + p.eps_v) use = false;
-                else {
-                    float xe, ye;
-                    use = bp_exact(p, c, s, t, zb + i, xe, ye);
-                    if (use) {
-                        if (xe < 0.f) use = false;              // inside detector test but outside the fetch test
-                        else { x = xe; yy = ye; }
-                    }
-                }
+        for (int h = 0; h < ZT; h += ZB) {
+            float fx[ZB], va[ZB], vb[ZB], vc2[ZB], vd[ZB];
+            bool ok[ZB];
+#pragma unroll
+            for (int i = 0; i < ZB; i++) {
+                const float fi = (float)(h + i);
+                const float w = fmaf(-kv, fi, w0v);             // k*(Z0 - vox*i)
+                const float aw = fabsf(w);
+                float x = fmaf(kzv, fi, x0v);
+                ok[i] = u_ok && aw <= hv_in;
+                if (fabsf(aw - p.half_v) < p.eps_v || (!u_ok && aw < p.half_v + p.eps_v)) band |= 1u << (h + i);
+                x = fminf(fmaxf(x, 0.f), nvf);
+                const int xi = (int)x;
+                fx[i] = x - (float)xi;
+                const float *__restrict__ q = q0 + xi * p.pitch;
+                va[i] = __ldg(q); vb[i] = __ldg(q + 1); vc2[i] = __ldg(q + p.pitch); vd[i] = __ldg(q + p.pitch + 1);
             }
-            if (use) {
-                x = fminf(fmaxf(x, 0.f), (float)p.nv);
-                yy = fminf(fmaxf(yy, 0.f), (float)p.nu);
-                acc[i] = fmaf(wgt, bp_bilinear(fv, p.pitch, x, yy), acc[i]);
+#pragma unroll
+            for (int i = 0; i < ZB; i++) {
+                const float lo = fmaf(fx[i], vc2[i] - va[i], va[i]);      // (1-fx)*a + fx*c
+                const float hi = fmaf(fx[i], vd[i] - vb[i], vb[i]);
+                const float val = fmaf(fy, hi - lo, lo);
+                acc[h + i] = fmaf(ok[i] ? wgt : 0.f, val, acc[h + i]);
             }
+        }
+        if (band) {                                             // rare: exact double evaluation
+#pragma unroll
+            for (int i = 0; i < ZT; i++)
+                if (band & (1u << i)) acc[i] += bp_fix_one(p, p.vc[v], s, t, zb + i, fv, wgt);
         }
     }
 #pragma unroll
     for (int i = 0; i < ZT; i++) {
-        if (i < nz_here) {
-            const int z = zb + i;
+        const int z = zb + i;
+        if (z >= p.z_lo && z < p.z_hi) {
             float r = acc[i];
             if (z < p.roi_z_begin || z >= p.roi_z_end) r = 0.f;
             if (p.mask_r2 >= 0) {
@@ -485,7 +515,8 @@ int monte_gpu_fdk_backproject_dev(const monte_fdk_geom *g, const float *d_filter
     p.nu_half = g->nu / 2.; p.nv_half = g->nv / 2.;
     constexpr int ZT = 16;
     dim3 block(BP_TX, BP_TY);
-    dim3 grid(ceil_div(g->s_end - g->s_begin, BP_TX), ceil_div(g->t_end - g->t_begin, BP_TY), ceil_div(z_hi - z_lo, ZT));
+    dim3 grid(ceil_div(g->s_end - g->s_begin, BP_TX), ceil_div(g->t_end - g->t_begin, BP_TY),
+              ceil_div(z_hi - (z_lo / ZT) * ZT, ZT));
     fdk_backproject_kernel<ZT><<<grid, block, 0, st>>>(p);
     MONTE_CUDA(cudaGetLastError());
     return MONTE_OK;
