@@ -15,6 +15,7 @@
 // per-row taps, the backprojector a gather.  Bound: FP32 pipe + L1 gather.
 #include "common.cuh"
 #include <cmath>
+#include <cstdlib>
 
 namespace monte {
 
@@ -250,12 +251,14 @@ __device__ __noinline__ float bp_fix_one(const BpParams &p, const ViewConst &c, 
 // addresses, no branch or call in between so they overlap), then the bilinear FMAs with a select;
 // (3) voxels inside the narrow bands around the detector edge contribute nothing in (2) and are
 // added exactly afterwards.
-template <int ZT>
-__global__ void __launch_bounds__(BP_TX *BP_TY, 3)
+template <int ZT, int ZB, int MINB>
+__global__ void __launch_bounds__(BP_TX *BP_TY, MINB)
 fdk_backproject_kernel(const __grid_constant__ BpParams p) {
-    constexpr int ZB = 8;
-    const int s = p.s_begin + blockIdx.x * BP_TX + threadIdx.x;
-    const int t = p.t_begin + blockIdx.y * BP_TY + threadIdx.y;
+    // a warp covers an 8 (s) x 4 (t) patch of columns, not 32 x 1: its detector footprint per
+    // gather is ~2x narrower (fewer 128-byte lines per LDG), stores stay full 32-byte sectors
+    const int tid = threadIdx.y * BP_TX + threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int s = p.s_begin + blockIdx.x * BP_TX + (wid & 3) * 8 + (lane & 7);
+    const int t = p.t_begin + blockIdx.y * BP_TY + (wid >> 2) * 4 + (lane >> 3);
     // z blocks are aligned to absolute multiples of ZT so that the per-slice increments below round
     // identically however the volume is cut into slabs (multi-GPU slabs == single launch, bit for bit)
     const int zb = (p.z_lo / ZT) * ZT + blockIdx.z * ZT;
@@ -299,10 +302,35 @@ fdk_backproject_kernel(const __grid_constant__ BpParams p) {
         const float fy = y - (float)yi;
         const float *__restrict__ fv = p.filt + (size_t)v * p.nv * p.pitch;
         const float *__restrict__ q0 = fv + yi;
+        const float *__restrict__ q1 = q0 + p.pitch;
         const float kz = k * p.inv_dv;
         const float kzv = kz * p.vox, kv = k * p.vox;            // per-slice increments of x and w
         const float x0v = fmaf(-kz, Z0, xoff), w0v = k * Z0;
         unsigned band = 0;
+        // w is linear in the slice index: if both ends of the column are safely inside the detector
+        // every slice is, and the per-slice edge tests and clamps can be dropped altogether
+        const float w_last = fmaf(-kv, (float)(ZT - 1), w0v);
+        if (u_ok && fmaxf(fabsf(w0v), fabsf(w_last)) <= hv_in) {
+#pragma unroll
+            for (int h = 0; h < ZT; h += ZB) {
+                float fx[ZB], va[ZB], vb[ZB], vc2[ZB], vd[ZB];
+#pragma unroll
+                for (int i = 0; i < ZB; i++) {
+                    const float x = fmaxf(fmaf(kzv, (float)(h + i), x0v), 0.f);   // >= -ulp by construction
+                    const int xi = (int)x;
+                    fx[i] = x - (float)xi;
+                    const int off = xi * p.pitch;
+                    va[i] = __ldg(q0 + off); vb[i] = __ldg(q0 + off + 1); vc2[i] = __ldg(q1 + off); vd[i] = __ldg(q1 + off + 1);
+                }
+#pragma unroll
+                for (int i = 0; i < ZB; i++) {
+                    const float lo = fmaf(fx[i], vc2[i] - va[i], va[i]);      // (1-fx)*a + fx*c
+                    const float hi = fmaf(fx[i], vd[i] - vb[i], vb[i]);
+                    acc[h + i] = fmaf(wgt, fmaf(fy, hi - lo, lo), acc[h + i]);
+                }
+            }
+            continue;
+        }
 #pragma unroll
         for (int h = 0; h < ZT; h += ZB) {
             float fx[ZB], va[ZB], vb[ZB], vc2[ZB], vd[ZB];
@@ -318,12 +346,12 @@ fdk_backproject_kernel(const __grid_constant__ BpParams p) {
                 x = fminf(fmaxf(x, 0.f), nvf);
                 const int xi = (int)x;
                 fx[i] = x - (float)xi;
-                const float *__restrict__ q = q0 + xi * p.pitch;
-                va[i] = __ldg(q); vb[i] = __ldg(q + 1); vc2[i] = __ldg(q + p.pitch); vd[i] = __ldg(q + p.pitch + 1);
+                const int off = xi * p.pitch;
+                va[i] = __ldg(q0 + off); vb[i] = __ldg(q0 + off + 1); vc2[i] = __ldg(q1 + off); vd[i] = __ldg(q1 + off + 1);
             }
 #pragma unroll
             for (int i = 0; i < ZB; i++) {
-                const float lo = fmaf(fx[i], vc2[i] - va[i], va[i]);      // (1-fx)*a + fx*c
+                const float lo = fmaf(fx[i], vc2[i] - va[i], va[i]);
                 const float hi = fmaf(fx[i], vd[i] - vb[i], vb[i]);
                 const float val = fmaf(fy, hi - lo, lo);
                 acc[h + i] = fmaf(ok[i] ? wgt : 0.f, val, acc[h + i]);
@@ -513,11 +541,25 @@ int monte_gpu_fdk_backproject_dev(const monte_fdk_geom *g, const float *d_filter
     p.x0d = g->x0; p.y0d = g->y0; p.z0d = g->z0; p.voxd = g->vox; p.dsdd = g->dsd;
     p.half_ud = g->half_u; p.half_vd = g->half_v; p.inv_dud = 1.0 / g->du; p.inv_dvd = 1.0 / g->dv;
     p.nu_half = g->nu / 2.; p.nv_half = g->nv / 2.;
-    constexpr int ZT = 16;
     dim3 block(BP_TX, BP_TY);
-    dim3 grid(ceil_div(g->s_end - g->s_begin, BP_TX), ceil_div(g->t_end - g->t_begin, BP_TY),
-              ceil_div(z_hi - (z_lo / ZT) * ZT, ZT));
-    fdk_backproject_kernel<ZT><<<grid, block, 0, st>>>(p);
+    // tuning knob (default = the fastest measured variant, see profiles/): MONTE_BP_VARIANT=0..4
+    static int variant = -1;
+    if (variant < 0) { const char *e = getenv("MONTE_BP_VARIANT"); variant = e ? atoi(e) : 0; }
+#define BP_LAUNCH(ZT, ZB, MINB)                                                                          \
+    do {                                                                                                 \
+        dim3 grid(ceil_div(g->s_end - g->s_begin, BP_TX), ceil_div(g->t_end - g->t_begin, BP_TY),        \
+                  ceil_div(z_hi - (z_lo / ZT) * ZT, ZT));                                                \
+        fdk_backproject_kernel<ZT, ZB, MINB><<<grid, block, 0, st>>>(p);                                 \
+    } while (0)
+    switch (variant) {
+        case 1: BP_LAUNCH(16, 8, 2); break;
+        case 2: BP_LAUNCH(16, 16, 2); break;
+        case 3: BP_LAUNCH(8, 8, 4); break;
+        case 5: BP_LAUNCH(16, 8, 3); break;
+        case 6: BP_LAUNCH(32, 16, 2); break;
+        default: BP_LAUNCH(32, 8, 2); break;
+    }
+#undef BP_LAUNCH
     MONTE_CUDA(cudaGetLastError());
     return MONTE_OK;
 }
