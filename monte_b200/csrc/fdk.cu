@@ -174,6 +174,7 @@ struct BpParams {
     const ViewConst *vc;
     float *vol;                 // slab base: slice z_lo
     int n_views, nu, nv, pitch;
+    int accumulate;                   // start from the stored volume (view chunks after the first)
     int nx, ny;
     int s_begin, s_end, t_begin, t_end, z_lo, z_hi;   // z range of this launch (absolute)
     int roi_z_begin, roi_z_end;                        // geometry ROI in z (outside -> 0)
@@ -270,6 +271,13 @@ fdk_backproject_kernel(const __grid_constant__ BpParams p) {
     float acc[ZT];
 #pragma unroll
     for (int i = 0; i < ZT; i++) acc[i] = 0.f;
+    if (p.accumulate) {                              // later view chunks continue the stored fp32 partial sums
+#pragma unroll
+        for (int i = 0; i < ZT; i++) {
+            const int z = zb + i;
+            if (z >= p.z_lo && z < p.z_hi) acc[i] = p.vol[((size_t)(z - p.z_lo) * p.ny + t) * p.nx + s];
+        }
+    }
     const float xoff = p.half_v * p.inv_dv;
     const float hv_in = p.half_v - p.eps_v, hu_in = p.half_u - p.eps_u;
     const float nvf = (float)p.nv, nuf = (float)p.nu;
@@ -551,6 +559,26 @@ int monte_gpu_fdk_backproject_dev(const monte_fdk_geom *g, const float *d_filter
                   ceil_div(z_hi - (z_lo / ZT) * ZT, ZT));                                                \
         fdk_backproject_kernel<ZT, ZB, MINB><<<grid, block, 0, st>>>(p);                                 \
     } while (0)
+    // Views are streamed in chunks so that the detector rows a wave of CTAs touches stay L2-resident
+    // (all 720 views of one z-block are ~200 MB; CTAs drifting apart in view index thrash the L2).
+    // fp32 partial sums are stored and reloaded exactly, so chunking does not change the result.
+    int vchunk;
+    {
+        static int env_chunk = -2;
+        if (env_chunk == -2) { const char *e = getenv("MONTE_BP_VCHUNK"); env_chunk = e ? atoi(e) : -1; }
+        if (env_chunk >= 0) vchunk = env_chunk > 0 ? env_chunk : 1 << 30;
+        else {   // rows of one view that a 32-slice z-block projects onto, times the row size, against ~64 MB of L2
+            const double r = 0.5 * g->vox * sqrt((double)g->nx * g->nx + (double)g->ny * g->ny);
+            const double mag = g->dsd / fmax(g->dso - r, 0.1 * g->dso);
+            const double band_rows = 32.0 * g->vox / g->dv * mag + 8.0;
+            const double per_view = band_rows * (double)p.pitch * sizeof(float);
+            vchunk = (int)fmax(30.0, 64.0 * 1024 * 1024 / per_view);
+        }
+    }
+    for (int vb = 0; vb < g->n_views; vb += vchunk) {
+    // a chunk is presented to the kernel as a shorter scan: shifted view constants and rows
+    p.n_views = vb + vchunk < g->n_views ? vchunk : g->n_views - vb;
+    p.vc = g_fdk.d_vc + vb; p.filt = d_filtered_padded + (size_t)vb * g->nv * p.pitch; p.accumulate = vb > 0;
     switch (variant) {
         case 1: BP_LAUNCH(16, 8, 2); break;
         case 2: BP_LAUNCH(16, 16, 2); break;
@@ -558,6 +586,7 @@ int monte_gpu_fdk_backproject_dev(const monte_fdk_geom *g, const float *d_filter
         case 5: BP_LAUNCH(16, 8, 3); break;
         case 6: BP_LAUNCH(32, 16, 2); break;
         default: BP_LAUNCH(32, 8, 2); break;
+    }
     }
 #undef BP_LAUNCH
     MONTE_CUDA(cudaGetLastError());
