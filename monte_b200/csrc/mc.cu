@@ -17,6 +17,7 @@
 // order; tests compare the two history by history.
 #include "common.cuh"
 #include <cmath>
+#include <cstdlib>
 
 namespace monte {
 
@@ -381,6 +382,356 @@ mc_transport_kernel(const __grid_constant__ McLaunch P) {
     if (prim_cnt) { atomicAdd(P.image0 + cur_pv, (int)prim_cnt); atomicAdd(P.image5 + cur_pv, (int)prim_cnt); }
 }
 
+// ------------------------------------------------------------------------------------------------
+// v3: K histories per lane, parked in shared memory.
+// v2's vote still leaves ~half of the lanes idle in every executed phase, because each lane owns
+// exactly one history and it is often in a minority phase.  Here every lane owns K histories
+// ("slots"); their state lives in shared memory (struct-of-arrays, column = lane, so accesses are
+// conflict-free) and only a 4-bit one-hot phase per slot stays in a register.  Each iteration the
+// warp votes for the phase in which most LANES have at least one slot, every such lane loads that
+// slot, advances it by one phase and stores it back.  With K = 4 nearly every lane has work in the
+// winning phase.  Units are chained without draining the warp.  Per-history variates are unchanged
+// (counter-based), so results are bit-identical to v1/v2.
+// ------------------------------------------------------------------------------------------------
+enum : uint32_t { P_REFILL = 1u, P_STEP = 2u, P_COLLIDE = 4u, P_COMPTON = 8u };
+enum { F_X = 0, F_Y, F_Z, F_DX, F_DY, F_DZ, F_E, F_C0, F_META, F_CTR, F_PIXVIEW, F_UPHI, F_REC, F_COUNT };
+// META: bits 0-7 kE, 8-11 nint, 12-14 material, 15 pending-detect, 24-31 high byte of the history id
+// CTR : bits 0-19 flight-stream index, 20-31 event-stream index
+// PIXVIEW: bits 0-19 pixel, 20-31 view
+
+template <bool RECORD, int K>
+__global__ void __launch_bounds__(MC_THREADS, 3)
+mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
+    extern __shared__ float4 s_mem[];
+    const McSceneDev &sc = P.sc;
+    float4 *s_tab = s_mem;                                             // [n_mat*201]
+    float *s_inv = reinterpret_cast<float *>(s_tab + sc.n_mat * TAB_ROWS);   // [201]
+    float *s_cdf = s_inv + TAB_ROWS + 3;                               // [n_bins+1]
+    constexpr int NF = RECORD ? F_COUNT : F_COUNT - 1;
+    constexpr int FSTRIDE = K * 32;                                    // words per field per warp
+    uint32_t *s_slots = reinterpret_cast<uint32_t *>(s_cdf + ((sc.n_bins + 1 + 3) & ~3)) +
+                        (threadIdx.x >> 5) * (NF * FSTRIDE);
+    for (int i = threadIdx.x; i < sc.n_mat * TAB_ROWS; i += MC_THREADS) s_tab[i] = sc.tab[i];
+    for (int i = threadIdx.x; i < TAB_ROWS; i += MC_THREADS) s_inv[i] = sc.inv_mumax[i];
+    for (int i = threadIdx.x; i <= sc.n_bins && sc.n_bins > 0; i += MC_THREADS) s_cdf[i] = sc.cdf[i];
+    __syncthreads();
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t npix = (uint32_t)(sc.det_ny * sc.det_nx);
+    const float vox_off[3] = {-sc.org[0] * sc.inv_pitch - 0.5f, -sc.org[1] * sc.inv_pitch - 0.5f, -sc.org[2] * sc.inv_pitch - 0.5f};
+    constexpr uint32_t ALL = (K == 4) ? 0x1111u : (K == 3) ? 0x0111u : (K == 2) ? 0x0011u : 0x0001u;
+
+#define SLOT_F(f) (*reinterpret_cast<float *>(slot + (f) * FSTRIDE))
+#define SLOT_U(f) (slot[(f) * FSTRIDE])
+
+    uint32_t st = ALL * P_REFILL;                                      // one-hot phase per slot
+#pragma unroll
+    for (int j = 0; j < K; j++) s_slots[F_META * FSTRIDE + j * 32 + lane] = 0u;   // no pending detection in an empty slot
+    uint32_t cur_pv = 0xffffffffu, prim_cnt = 0;
+    uint32_t c_hist = 0, c_prim = 0, c_scat = 0, c_abs = 0, c_int = 0, c_coh = 0, c_comp = 0, c_steps = 0;
+    unsigned long long e_prim = 0, e_scat = 0;                         // fixed point, 1/1024 keV
+    // current unit (warp-uniform)
+    uint32_t unit_cnt = 0, next_off = 0, n0 = 0, v0 = 0, p0 = 0;
+    bool grid_done = false;
+
+    for (;;) {
+        // ---------------- vote: the phase in which most lanes have a slot waiting ---------------
+        uint32_t onehot = 0;
+        if (st & (ALL * P_REFILL)) onehot |= 1u;
+        if (st & (ALL * P_STEP)) onehot |= 1u << 8;
+        if (st & (ALL * P_COLLIDE)) onehot |= 1u << 16;
+        if (st & (ALL * P_COMPTON)) onehot |= 1u << 24;
+        const uint32_t cnts = __reduce_add_sync(0xffffffffu, onehot);
+        if (cnts == 0u) break;                                          // every slot of every lane is done
+        const int n_ref = cnts & 0xFF, n_step = (cnts >> 8) & 0xFF, n_col = (cnts >> 16) & 0xFF, n_kah = cnts >> 24;
+        uint32_t phase = P_STEP;
+        int best = n_step;
+        if (n_ref > best) { phase = P_REFILL; best = n_ref; }
+        if (n_col > best) { phase = P_COLLIDE; best = n_col; }
+        if (n_kah > best) { phase = P_COMPTON; best = n_kah; }
+        const uint32_t mine = st & (ALL * phase);
+        const bool active = mine != 0u;
+        const int j = active ? ((__ffs(mine) - 1) >> 2) : 0;            // my slot in that phase
+        uint32_t *slot = s_slots + j * 32 + lane;
+        const uint32_t clr = ~(0xFu << (4 * j));
+
+        if (phase == P_STEP) {
+            if (!active) continue;
+            // ---------------- one Woodcock step, CBCT_real325im.cu:886-968 ---------------
+            float x = SLOT_F(F_X), y = SLOT_F(F_Y), z = SLOT_F(F_Z);
+            const float dx = SLOT_F(F_DX), dy = SLOT_F(F_DY), dz = SLOT_F(F_DZ);
+            const uint32_t c0 = SLOT_U(F_C0), meta = SLOT_U(F_META), ctr = SLOT_U(F_CTR);
+            const int kE = meta & 0xFF;
+            const uint2 r = philox2x32_10(c0, (meta & 0xFF000000u) | (STREAM_FLIGHT << 22) | (ctr & 0xFFFFFu), P.key);
+            SLOT_U(F_CTR) = (ctr & 0xFFF00000u) | ((ctr + 1u) & 0xFFFFFu);
+            const float s = -__logf(u01(r.x)) * s_inv[kE];
+            x = fmaf(s, dx, x); y = fmaf(s, dy, y); z = fmaf(s, dz, z);
+            SLOT_F(F_X) = x; SLOT_F(F_Y) = y; SLOT_F(F_Z) = z;
+            c_steps++;
+            const bool inside = x >= sc.clip_lo[0] && x < sc.clip_hi[0] && y >= sc.clip_lo[1] && y < sc.clip_hi[1] &&
+                                z >= sc.clip_lo[2] && z < sc.clip_hi[2];
+            if (!inside) {                       // left the volume: only air ahead
+                if ((meta & 0xF00u) == 0u) {     // unscattered: lands in the pixel it was aimed at (:567-590)
+                    const uint32_t pvw = SLOT_U(F_PIXVIEW);
+                    const uint32_t pva = (pvw >> 20) * npix + (pvw & 0xFFFFFu);
+                    if (pva != cur_pv) {
+                        if (prim_cnt) { atomicAdd(P.image0 + cur_pv, (int)prim_cnt); atomicAdd(P.image5 + cur_pv, (int)prim_cnt); }
+                        cur_pv = pva; prim_cnt = 0;
+                    }
+                    prim_cnt++; c_prim++;
+                    const float E = SLOT_F(F_E);
+                    e_prim += (unsigned long long)(E * 1024.f + 0.5f);
+                    if (RECORD) { P.fates[SLOT_U(F_REC)] = 1u | ((pvw & 0xFFFFFu) << 8); P.fate_e[SLOT_U(F_REC)] = E; }
+                } else SLOT_U(F_META) = meta | 0x8000u;     // scatter detection runs with the refill phase
+                st = (st & clr) | (P_REFILL << (4 * j));
+                continue;
+            }
+            int ix = __float_as_int(fmaf(x, sc.inv_pitch, vox_off[0]) + 12582912.0f) - 0x4B400000;
+            int iy = __float_as_int(fmaf(y, sc.inv_pitch, vox_off[1]) + 12582912.0f) - 0x4B400000;
+            int iz = __float_as_int(fmaf(z, sc.inv_pitch, vox_off[2]) + 12582912.0f) - 0x4B400000;
+            ix = (int)min((unsigned)ix, (unsigned)(sc.nx - 1)); iy = (int)min((unsigned)iy, (unsigned)(sc.ny - 1));
+            iz = (int)min((unsigned)iz, (unsigned)(sc.nz - 1));     // safety only: the clip box lies inside the volume
+            const int lab = __ldg(sc.labels + ((size_t)iz * sc.ny + iy) * sc.nx + ix);
+            if (lab == 0) continue;                                   // air: virtual collision
+            const int mat = min(lab, sc.n_mat) - 1;
+            if (u01(r.y) > s_tab[mat * TAB_ROWS + kE].x) continue;    // virtual collision, :941-961
+            SLOT_U(F_META) = (meta & ~0x7000u) | ((uint32_t)mat << 12);
+            st = (st & clr) | (P_COLLIDE << (4 * j));
+            continue;
+        }
+
+        if (phase == P_COLLIDE) {
+            if (!active) continue;
+            // ---------------- real collision, CBCT_real325im.cu:599-656 ----------------------
+            uint32_t meta = SLOT_U(F_META);
+            const int nint = (meta >> 8) & 0xF, kE = meta & 0xFF, mat = (meta >> 12) & 0x7;
+            if (nint >= sc.max_scatter) {                             // scatter budget used up
+                if (RECORD) { P.fates[SLOT_U(F_REC)] = 5u | ((uint32_t)nint << 28); P.fate_e[SLOT_U(F_REC)] = SLOT_F(F_E); }
+                st = (st & clr) | (P_REFILL << (4 * j));
+                continue;
+            }
+            {
+                const float x = SLOT_F(F_X), y = SLOT_F(F_Y), z = SLOT_F(F_Z);
+                const float2 cs = __ldg(sc.view_cs + (SLOT_U(F_PIXVIEW) >> 20));
+                const float xr = x * cs.x + y * cs.y, yr = -x * cs.y + y * cs.x;
+                if (xr >= sc.dod || fabsf(yr) >= sc.half || fabsf(z) >= sc.half) {        // :613-619
+                    if (RECORD) { P.fates[SLOT_U(F_REC)] = 4u | ((uint32_t)nint << 28); P.fate_e[SLOT_U(F_REC)] = SLOT_F(F_E); }
+                    st = (st & clr) | (P_REFILL << (4 * j));
+                    continue;
+                }
+            }
+            meta += 0x100u;                                           // nint++
+            c_int++;
+            const uint32_t ctr = SLOT_U(F_CTR);
+            const uint2 re = philox2x32_10(SLOT_U(F_C0), (meta & 0xFF000000u) | (STREAM_EVENT << 22) | (ctr >> 20), P.key);
+            SLOT_U(F_CTR) = ctr + 0x100000u;
+            SLOT_U(F_META) = meta;
+            const float u_sel = u01(re.x);
+            const float4 tb = s_tab[mat * TAB_ROWS + kE];
+            if (u_sel <= tb.y) {                                      // photoelectric, :651-655
+                c_abs++;
+                if (RECORD) { P.fates[SLOT_U(F_REC)] = 3u | ((uint32_t)(nint + 1) << 28); P.fate_e[SLOT_U(F_REC)] = SLOT_F(F_E); }
+                st = (st & clr) | (P_REFILL << (4 * j));
+            } else if (u_sel <= tb.z) { c_coh++; st = (st & clr) | (P_STEP << (4 * j)); }    // coherent: no deflection
+            else { c_comp++; SLOT_F(F_UPHI) = u01(re.y); st = (st & clr) | (P_COMPTON << (4 * j)); }
+            continue;
+        }
+
+        if (phase == P_COMPTON) {
+            if (!active) continue;
+            // ---------------- one round of Kahn's method, :701-736 -----------------------------
+            const float E0 = SLOT_F(F_E);
+            const uint32_t meta = SLOT_U(F_META), ctr = SLOT_U(F_CTR), c0 = SLOT_U(F_C0);
+            const float lam = __fdividef(511.0f, E0);
+            const uint32_t ne = ctr >> 20;
+            const uint2 ra = philox2x32_10(c0, (meta & 0xFF000000u) | (STREAM_EVENT << 22) | ne, P.key);
+            const uint2 rb = philox2x32_10(c0, (meta & 0xFF000000u) | (STREAM_EVENT << 22) | ((ne + 1u) & 0xFFFu), P.key);
+            SLOT_U(F_CTR) = ctr + 0x200000u;
+            const float r1 = u01(ra.x), r2 = u01(ra.y), r3 = u01(rb.x);
+            const bool br1 = r1 * (9.0f * lam + 2.0f) < (lam + 2.0f);
+            const float ro1 = 1.0f + __fdividef(2.0f, lam) * r2;
+            const float ro2 = __fdividef(lam + 2.0f, lam + 2.0f * (1.0f - r2));
+            const float ro = br1 ? ro1 : ro2;
+            const float iro = __fdividef(1.0f, ro);
+            const float t = lam - ro * lam + 1.0f;
+            const float lim = br1 ? 4.0f * (iro - iro * iro) : 0.5f * (t * t + iro);
+            if (!(r3 <= lim)) continue;                               // rejected: next round next time
+            const float lam_d = ro * lam;
+            float cos_t = 1.0f - (lam_d - lam);
+            cos_t = fmaxf(cos_t, -1.0f);                              // :746-747
+            const float sin_t = sqrtf(fmaxf(0.f, 1.0f - cos_t * cos_t));
+            const float E = __fdividef(511.0f, lam_d);
+            const int kE = min(max((int)(E + 0.5f), 0), TAB_ROWS - 1);
+            SLOT_F(F_E) = E;
+            SLOT_U(F_META) = (meta & ~0xFFu) | (uint32_t)kE;
+            float sphi, cphi;
+            sincospif(2.0f * SLOT_F(F_UPHI), &sphi, &cphi);           // phi = 2 pi u, :764
+            const float dx = SLOT_F(F_DX), dy = SLOT_F(F_DY), dz = SLOT_F(F_DZ);
+            // direction update, :768-780, as a rotation of the unit vector (see v2 for the algebra)
+            const float st2 = dx * dx + dy * dy;
+            float e1x, e1y, e1z, e2x, e2y;
+            if (st2 > 1e-12f) {
+                const float ist = rsqrtf(st2), sta = st2 * ist;
+                e1x = dx * dz * ist; e1y = dy * dz * ist; e1z = -sta;
+                e2x = -dy * ist; e2y = dx * ist;
+            } else { e1x = dz; e1y = 0.f; e1z = 0.f; e2x = 0.f; e2y = 1.f; }
+            const float a = sin_t * cphi, b = sin_t * sphi;
+            const float nxd = cos_t * dx + a * e1x + b * e2x;
+            const float nyd = cos_t * dy + a * e1y + b * e2y;
+            const float nzd = cos_t * dz + a * e1z;
+            const float nn = rsqrtf(nxd * nxd + nyd * nyd + nzd * nzd);
+            SLOT_F(F_DX) = nxd * nn; SLOT_F(F_DY) = nyd * nn; SLOT_F(F_DZ) = nzd * nn;
+            st = (st & clr) | (P_STEP << (4 * j));
+            continue;
+        }
+
+        // ---------------- phase == P_REFILL: finish the ended history, start the next one ----------
+        // unit bookkeeping is warp-uniform: executed by every lane
+        if (next_off >= unit_cnt && !grid_done) {
+            unsigned long long unit = 0;
+            if (lane == 0) unit = atomicAdd(P.work, 1ull);
+            unit = __shfl_sync(0xffffffffu, unit, 0);
+            if (unit >= P.n_units) grid_done = true;
+            else {
+                const unsigned long long base = unit * (unsigned long long)MC_UNIT;
+                unit_cnt = (uint32_t)min((unsigned long long)MC_UNIT, P.total - base);
+                const uint32_t pv0 = (uint32_t)(base / P.cnt);
+                n0 = (uint32_t)(base - (unsigned long long)pv0 * P.cnt);
+                v0 = pv0 / npix; p0 = pv0 - v0 * npix;
+                next_off = 0;
+            }
+        }
+        const unsigned m_ref = __ballot_sync(0xffffffffu, active);
+        const uint32_t my_off = next_off + __popc(m_ref & lt_mask);
+        next_off = min(next_off + (uint32_t)__popc(m_ref), unit_cnt);
+        if (!active) continue;
+        {
+            const uint32_t meta = SLOT_U(F_META);
+            if (meta & 0x8000u) {                        // scatter detection, CBCT_real325im.cu:823-843
+                SLOT_U(F_META) = meta & ~0x8000u;
+                const int nint = (meta >> 8) & 0xF;
+                uint32_t fate = 4u | ((uint32_t)nint << 28);
+                const float x = SLOT_F(F_X), y = SLOT_F(F_Y), z = SLOT_F(F_Z);
+                const float dx = SLOT_F(F_DX), dy = SLOT_F(F_DY), dz = SLOT_F(F_DZ), E = SLOT_F(F_E);
+                const int view = (int)(SLOT_U(F_PIXVIEW) >> 20);
+                const float2 cs = __ldg(sc.view_cs + view);
+                const float xr = x * cs.x + y * cs.y, yr = -x * cs.y + y * cs.x;      // rotate by -beta
+                const float dxr = dx * cs.x + dy * cs.y, dyr = -dx * cs.y + dy * cs.x;
+                if (dxr > 0.f) {
+                    const float t = (sc.dod - xr) / dxr;
+                    const float yd = fmaf(t, dyr, yr), zd = fmaf(t, dz, z);
+                    if (fabsf(yd) <= sc.half && fabsf(zd) <= sc.half && fmaf(1000.f, dxr, xr) >= sc.dod) {
+                        const int by = (int)((sc.half - yd) * sc.inv_pixel), bx = (int)((sc.half - zd) * sc.inv_pixel);
+                        if (by >= 0 && by < sc.det_ny && bx >= 0 && bx < sc.det_nx) {
+                            const uint32_t bin = (uint32_t)(by * sc.det_nx + bx);
+                            atomicAdd(P.image5 + (size_t)view * npix + bin, 1);
+                            c_scat++;
+                            e_scat += (unsigned long long)(E * 1024.f + 0.5f);
+                            fate = 2u | (bin << 8) | ((uint32_t)nint << 28);
+                        }
+                    }
+                }
+                if (RECORD) { P.fates[SLOT_U(F_REC)] = fate; P.fate_e[SLOT_U(F_REC)] = E; }
+            }
+        }
+        if (my_off >= unit_cnt) {                        // no history left in this unit for me
+            if (grid_done) st &= clr;                    // ... nor anywhere: the slot is done
+            continue;                                    // else: stays REFILL, the next visit opens a new unit
+        }
+        {
+            uint32_t n = n0 + my_off;
+            const uint32_t dpv = n / P.cnt;
+            n -= dpv * P.cnt;
+            uint32_t pix = p0 + dpv, vrel = v0;
+            if (pix >= npix) { const uint32_t q = pix / npix; vrel += q; pix -= q * npix; }
+            const int view = P.view_begin + (int)vrel;
+            const uint32_t pva = (uint32_t)view * npix + pix;
+            n += P.n_begin;
+            const unsigned long long hid = (unsigned long long)pva * P.per + n;
+            const uint32_t c0 = (uint32_t)hid;
+            const uint32_t c1hi = ((uint32_t)(hid >> 32) & 0xFFu) << 24;
+            uint32_t rec_idx = 0;
+            if (RECORD) { rec_idx = pix * P.per + n; SLOT_U(F_COUNT - 1) = rec_idx; }
+            c_hist++;
+            // ---- source, CBCT_real325im.cu:464-540 (exact aim at the pixel) ----
+            const uint32_t pi = pix / (uint32_t)sc.det_nx, pj = pix - pi * (uint32_t)sc.det_nx;
+            float uy = 0.5f, uz = 0.5f;
+            if (sc.source_mode == MONTE_MC_SOURCE_CONE) {
+                const uint2 r = philox2x32_10(c0, c1hi | (STREAM_SOURCE << 22), P.key);
+                uy = u01(r.x); uz = u01(r.y);
+            }
+            float E = sc.mono_keV;
+            if (sc.n_bins > 0) {                              // CBCT_real325im.cu:492-498
+                const uint2 r = philox2x32_10(c0, c1hi | (STREAM_SOURCE << 22) | 1u, P.key);
+                const float ue = u01(r.x);
+                int lo = 0, hi = sc.n_bins;                  // first k with ue <= cdf[k+1]
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (ue <= s_cdf[mid + 1]) hi = mid; else lo = mid + 1; }
+                if (lo < sc.n_bins) E = (float)(lo + 1) * sc.bin_keV;
+            }
+            const int kE = min(max((int)(E + 0.5f), 0), TAB_ROWS - 1);
+            const float yl = sc.half - sc.pixel * ((float)pi + uy);
+            const float zl = sc.half - sc.pixel * ((float)pj + uz);
+            const float rn = rsqrtf(sc.dsd * sc.dsd + yl * yl + zl * zl);
+            const float2 cs = __ldg(sc.view_cs + view);
+            const float dxr = sc.dsd * rn, dyr = yl * rn;
+            const float dx = dxr * cs.x - dyr * cs.y;
+            const float dy = dxr * cs.y + dyr * cs.x;
+            const float dz = zl * rn;
+            const float sx = -sc.dso * cs.x, sy = -sc.dso * cs.y;
+            float t0 = 0.f, t1 = 1e30f;                       // analytic flight to the clip box (slab method)
+            {
+                const float o3[3] = {sx, sy, 0.f}, d3[3] = {dx, dy, dz};
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    if (d3[a] != 0.f) {
+                        const float inv = 1.0f / d3[a];
+                        float ta = (sc.clip_lo[a] - o3[a]) * inv, tb = (sc.clip_hi[a] - o3[a]) * inv;
+                        if (ta > tb) { const float t = ta; ta = tb; tb = t; }
+                        t0 = fmaxf(t0, ta); t1 = fminf(t1, tb);
+                    } else if (o3[a] < sc.clip_lo[a] || o3[a] >= sc.clip_hi[a]) t1 = -1.f;
+                }
+            }
+            if (t0 >= t1) {                                   // misses the phantom: unscattered
+                if (pva != cur_pv) {
+                    if (prim_cnt) { atomicAdd(P.image0 + cur_pv, (int)prim_cnt); atomicAdd(P.image5 + cur_pv, (int)prim_cnt); }
+                    cur_pv = pva; prim_cnt = 0;
+                }
+                prim_cnt++; c_prim++;
+                e_prim += (unsigned long long)(E * 1024.f + 0.5f);
+                if (RECORD) { P.fates[rec_idx] = 1u | (pix << 8); P.fate_e[rec_idx] = E; }
+                // the slot stays in REFILL and takes another history on the next visit
+            } else {
+                SLOT_F(F_X) = fmaf(t0, dx, sx); SLOT_F(F_Y) = fmaf(t0, dy, sy); SLOT_F(F_Z) = t0 * dz;
+                SLOT_F(F_DX) = dx; SLOT_F(F_DY) = dy; SLOT_F(F_DZ) = dz;
+                SLOT_F(F_E) = E; SLOT_U(F_C0) = c0;
+                SLOT_U(F_META) = c1hi | (uint32_t)kE;
+                SLOT_U(F_CTR) = 0u;
+                SLOT_U(F_PIXVIEW) = ((uint32_t)view << 20) | pix;
+                st = (st & clr) | (P_STEP << (4 * j));
+            }
+        }
+    }
+#undef SLOT_F
+#undef SLOT_U
+    if (prim_cnt) { atomicAdd(P.image0 + cur_pv, (int)prim_cnt); atomicAdd(P.image5 + cur_pv, (int)prim_cnt); }
+    if (P.stats) {
+        const uint32_t v[8] = {c_hist, c_prim, c_scat, c_abs, c_int, c_coh, c_comp, c_steps};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            // 32-bit per-lane counters, summed in 64 bits
+            unsigned long long s = v[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0 && s) atomicAdd(P.stats + i, s);
+        }
+        unsigned long long ep = e_prim, es = e_scat;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { ep += __shfl_xor_sync(0xffffffffu, ep, o); es += __shfl_xor_sync(0xffffffffu, es, o); }
+        if (lane == 0) { if (ep) atomicAdd(P.stats + ST_EPRIM, ep); if (es) atomicAdd(P.stats + ST_ESCAT, es); }
+    }
+}
+
 // counts -> -ln(I/I0), CBCT_real325im.cu:267-285
 // (-log(int) is the double overload there, log(float(per)) the float one: log_per is computed by
 // the host's logf so both terms round exactly as in the reference)
@@ -546,17 +897,46 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     MONTE_CUDA(cudaMemsetAsync(s->d_work, 0, sizeof(unsigned long long), st));
     const int sms = ctx().sm_count;
     const unsigned long long warps_needed = L.n_units;
-    static int occ[2] = {0, 0};                    // resident CTAs per SM: persistent grid = SMs x occupancy
-    int &oc = occ[d_fates ? 1 : 0];
-    if (oc == 0) {
-        if (d_fates) MONTE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, mc_transport_kernel<true>, MC_THREADS, s->smem));
-        else MONTE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, mc_transport_kernel<false>, MC_THREADS, s->smem));
+    // kernel selection: v3 (K parked histories per lane) is the default; MONTE_MC_KERNEL=2 runs v2, =31..34 v3 with K=1..4
+    static int which = -1;
+    if (which < 0) { const char *e = getenv("MONTE_MC_KERNEL"); which = e ? atoi(e) : 34; }
+    MONTE_ARG(s->geom.n_views < 4096, "mc: more than 4095 views");
+    const int rec = d_fates ? 1 : 0;
+    const int K = which >= 31 && which <= 34 ? which - 30 : 0;
+    const size_t slot_bytes = (size_t)K * 32 * (rec ? F_COUNT : F_COUNT - 1) * sizeof(uint32_t) * (MC_THREADS / 32);
+    const size_t smem = K ? (size_t)s->dev.n_mat * TAB_ROWS * sizeof(float4) +
+                                (TAB_ROWS + 3 + ((s->dev.n_bins + 1 + 3) & ~3)) * sizeof(float) + slot_bytes
+                          : s->smem;
+    const void *fn = nullptr;
+    switch (which * 2 + rec) {
+        case 62: fn = (const void *)mc_transport_kernel_v3<false, 1>; break;
+        case 63: fn = (const void *)mc_transport_kernel_v3<true, 1>; break;
+        case 64: fn = (const void *)mc_transport_kernel_v3<false, 2>; break;
+        case 65: fn = (const void *)mc_transport_kernel_v3<true, 2>; break;
+        case 66: fn = (const void *)mc_transport_kernel_v3<false, 3>; break;
+        case 67: fn = (const void *)mc_transport_kernel_v3<true, 3>; break;
+        case 68: fn = (const void *)mc_transport_kernel_v3<false, 4>; break;
+        case 69: fn = (const void *)mc_transport_kernel_v3<true, 4>; break;
+        default: fn = rec ? (const void *)mc_transport_kernel<true> : (const void *)mc_transport_kernel<false>; break;
+    }
+    static int occ[80] = {0};                      // resident CTAs per SM: persistent grid = SMs x occupancy
+    static size_t smem_set[80] = {0}, smem_occ[80] = {0};
+    const int slot_id = (which * 2 + rec) % 80;
+    int &oc = occ[slot_id];
+    MONTE_ARG(smem <= 227 * 1024, "mc: %zu bytes of shared memory needed (> 227 KB)", smem);
+    if (smem > smem_set[slot_id]) {
+        MONTE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[slot_id] = smem;
+    }
+    if (oc == 0 || smem != smem_occ[slot_id]) {
+        MONTE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, fn, MC_THREADS, smem));
         if (oc < 1) oc = 1;
+        smem_occ[slot_id] = smem;
     }
     int grid = sms * oc;
     if ((unsigned long long)grid * (MC_THREADS / 32) > warps_needed) grid = (int)((warps_needed + MC_THREADS / 32 - 1) / (MC_THREADS / 32));
-    if (d_fates) mc_transport_kernel<true><<<grid, MC_THREADS, s->smem, st>>>(L);
-    else mc_transport_kernel<false><<<grid, MC_THREADS, s->smem, st>>>(L);
+    void *args[] = {(void *)&L};
+    MONTE_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(MC_THREADS), args, smem, st));
     MONTE_CUDA(cudaGetLastError());
     return MONTE_OK;
 }
