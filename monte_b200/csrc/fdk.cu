@@ -144,9 +144,9 @@ fdk_weight_filter_kernel(const FilterParams p) {
 }
 
 // element [r][nu] = [r+1][0]; columns nu+1.. and the two trailing rows are zero.
-__global__ void fdk_pad_kernel(float *f, int rows, int nu, int pitch) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= rows + 2) return;
+__global__ void fdk_pad_kernel(float *f, int rows, int nu, int pitch, int r0, int r1) {
+    const int r = r0 + blockIdx.x * blockDim.x + threadIdx.x;      // rows [r0, r1) of the rows+2 in the buffer
+    if (r >= r1) return;
     float *row = f + (size_t)r * pitch;
     if (r >= rows) {
         for (int c = 0; c < pitch; c++) row[c] = 0.f;
@@ -502,7 +502,7 @@ int monte_gpu_fdk_pad_dev(const monte_fdk_geom *g, float *d_filtered_padded, voi
     MONTE_REQUIRE_INIT();
     if (int rc = check_geom(g)) return rc;
     const int rows = g->n_views * g->nv;
-    fdk_pad_kernel<<<ceil_div(rows + 2, 256), 256, 0, (cudaStream_t)stream>>>(d_filtered_padded, rows, g->nu, (int)filtered_pitch(g));
+    fdk_pad_kernel<<<ceil_div(rows + 2, 256), 256, 0, (cudaStream_t)stream>>>(d_filtered_padded, rows, g->nu, (int)filtered_pitch(g), 0, rows + 2);
     MONTE_CUDA(cudaGetLastError());
     return MONTE_OK;
 }
@@ -516,18 +516,15 @@ int monte_gpu_fdk_unpad_dev(const monte_fdk_geom *g, const float *d_filtered_pad
     return MONTE_OK;
 }
 
-int monte_gpu_fdk_backproject_dev(const monte_fdk_geom *g, const float *d_filtered_padded, int z_lo, int z_hi,
-                                  float *d_vol_slab, void *stream) {
-    MONTE_REQUIRE_INIT();
-    if (int rc = check_geom(g)) return rc;
-    MONTE_ARG(d_filtered_padded && d_vol_slab, "fdk_backproject: NULL device pointer");
-    MONTE_ARG(0 <= z_lo && z_lo <= z_hi && z_hi <= g->nz, "fdk_backproject: bad z range [%d,%d)", z_lo, z_hi);
-    cudaStream_t st = (cudaStream_t)stream;
+// Backproject views [view_lo, view_hi) into z-slices [z_lo, z_hi).  continue_sum: the slab already
+// holds the fp32 partial sums of the earlier views (they are reloaded exactly), else it is zeroed.
+static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_padded, int z_lo, int z_hi,
+                             float *d_vol_slab, cudaStream_t st, int view_lo, int view_hi, bool continue_sum) {
     if (int rc = fdk_prepare(g, st)) return rc;
     if (z_lo == z_hi) return MONTE_OK;
     // everything outside the ROI is zero (the reference callocs the volume, bp3d20.cpp:32)
-    MONTE_CUDA(cudaMemsetAsync(d_vol_slab, 0, (size_t)(z_hi - z_lo) * g->ny * g->nx * sizeof(float), st));
-    if (g->s_begin == g->s_end || g->t_begin == g->t_end) return MONTE_OK;
+    if (!continue_sum) MONTE_CUDA(cudaMemsetAsync(d_vol_slab, 0, (size_t)(z_hi - z_lo) * g->ny * g->nx * sizeof(float), st));
+    if (g->s_begin == g->s_end || g->t_begin == g->t_end || view_lo >= view_hi) return MONTE_OK;
     const bool textbook = g->weight_mode == MONTE_FDK_TEXTBOOK;
     BpParams p;
     p.filt = d_filtered_padded; p.vc = g_fdk.d_vc; p.vol = d_vol_slab;
@@ -575,10 +572,10 @@ int monte_gpu_fdk_backproject_dev(const monte_fdk_geom *g, const float *d_filter
             vchunk = (int)fmax(30.0, 64.0 * 1024 * 1024 / per_view);
         }
     }
-    for (int vb = 0; vb < g->n_views; vb += vchunk) {
+    for (int vb = view_lo; vb < view_hi; vb += vchunk) {
     // a chunk is presented to the kernel as a shorter scan: shifted view constants and rows
-    p.n_views = vb + vchunk < g->n_views ? vchunk : g->n_views - vb;
-    p.vc = g_fdk.d_vc + vb; p.filt = d_filtered_padded + (size_t)vb * g->nv * p.pitch; p.accumulate = vb > 0;
+    p.n_views = vb + vchunk < view_hi ? vchunk : view_hi - vb;
+    p.vc = g_fdk.d_vc + vb; p.filt = d_filtered_padded + (size_t)vb * g->nv * p.pitch; p.accumulate = continue_sum || vb > view_lo;
     switch (variant) {
         case 1: BP_LAUNCH(16, 8, 2); break;
         case 2: BP_LAUNCH(16, 16, 2); break;
@@ -591,6 +588,15 @@ int monte_gpu_fdk_backproject_dev(const monte_fdk_geom *g, const float *d_filter
 #undef BP_LAUNCH
     MONTE_CUDA(cudaGetLastError());
     return MONTE_OK;
+}
+
+int monte_gpu_fdk_backproject_dev(const monte_fdk_geom *g, const float *d_filtered_padded, int z_lo, int z_hi,
+                                  float *d_vol_slab, void *stream) {
+    MONTE_REQUIRE_INIT();
+    if (int rc = check_geom(g)) return rc;
+    MONTE_ARG(d_filtered_padded && d_vol_slab, "fdk_backproject: NULL device pointer");
+    MONTE_ARG(0 <= z_lo && z_lo <= z_hi && z_hi <= g->nz, "fdk_backproject: bad z range [%d,%d)", z_lo, z_hi);
+    return backproject_views(g, d_filtered_padded, z_lo, z_hi, d_vol_slab, (cudaStream_t)stream, 0, g->n_views, false);
 }
 
 int monte_gpu_fdk_transpose_dev(const monte_fdk_geom *g, const float *d_vol_xy, float *d_vol_zy, void *stream) {
@@ -609,32 +615,76 @@ int monte_gpu_fdk(const monte_fdk_geom *g, const float *map, float *filtered, fl
     if (int rc = check_geom(g)) return rc;
     MONTE_ARG(map && vol_xy, "fdk: map and vol_xy must not be NULL");
     Context &c = ctx();
-    cudaStream_t st = c.stream;
-    const size_t n_map = (size_t)g->n_views * g->nu * g->nv;
-    const size_t n_vol = (size_t)g->nx * g->ny * g->nz;
+    cudaStream_t st = c.stream, cp = c.copy_stream;
+    const size_t per_view = (size_t)g->nu * g->nv;
+    const size_t n_map = (size_t)g->n_views * per_view;
+    const size_t slice = (size_t)g->nx * g->ny, n_vol = slice * g->nz;
     float *d_map = (float *)scratch(0, n_map * sizeof(float));
     float *d_filt = (float *)scratch(1, monte_gpu_fdk_filtered_elems(g) * sizeof(float));
     float *d_vol = (float *)scratch(2, n_vol * sizeof(float));
     if (!d_map || !d_filt || !d_vol) return MONTE_E_NOMEM;
-    EventTimer t_all(st), t_h2d(st), t_f(st), t_b(st), t_t(st), t_d2h(st);
+    if (int rc = fdk_prepare(g, st)) return rc;
+    // Two streams: the copy stream uploads view chunks while the compute stream filters the previous
+    // chunk, and downloads finished z-slabs while the next slab is backprojected.  With pinned host
+    // buffers the copies are truly asynchronous; with pageable ones they still overlap the kernels.
+    constexpr int MAXC = 16;
+    static cudaEvent_t ev_up[MAXC] = {nullptr}, ev_slab[MAXC] = {nullptr}, ev_t[6] = {nullptr};
+    if (!ev_up[0]) {
+        for (int i = 0; i < MAXC; i++) {
+            MONTE_CUDA(cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming));
+            MONTE_CUDA(cudaEventCreateWithFlags(&ev_slab[i], cudaEventDisableTiming));
+        }
+        for (int i = 0; i < 6; i++) MONTE_CUDA(cudaEventCreate(&ev_t[i]));
+    }
     int launches = 0;
-    t_all.start();
-    t_h2d.start();
-    MONTE_CUDA(cudaMemcpyAsync(d_map, map, n_map * sizeof(float), cudaMemcpyHostToDevice, st));
-    t_h2d.stop();
-    t_f.start();
-    if (int rc = monte_gpu_fdk_filter_dev(g, d_map, 0, g->n_views, d_filt, st)) return rc;
-    if (int rc = monte_gpu_fdk_pad_dev(g, d_filt, st)) return rc;
-    launches += 2;
-    t_f.stop();
-    t_b.start();
-    if (int rc = monte_gpu_fdk_backproject_dev(g, d_filt, 0, g->nz, d_vol, st)) return rc;
-    launches += 1;
-    t_b.stop();
-    t_d2h.start();
-    MONTE_CUDA(cudaMemcpyAsync(vol_xy, d_vol, n_vol * sizeof(float), cudaMemcpyDeviceToHost, st));
-    t_d2h.stop();
-    t_t.start();
+    MONTE_CUDA(cudaEventRecord(ev_t[0], st));                       // start of everything
+    MONTE_CUDA(cudaStreamWaitEvent(cp, ev_t[0], 0));
+    // Views travel in chunks: upload k | filter k | (pad k-1, which needs the first row of chunk k) |
+    // backproject k-1 into the whole volume, continuing the stored partial sums.  The last chunk is
+    // backprojected slab by slab so that finished slabs go home while the next one is computed.
+    const int n_up = g->n_views >= 64 ? 8 : 1;
+    const int rows = g->n_views * g->nv, pitch = (int)filtered_pitch(g);
+    const int n_slab = g->nz >= 128 ? 4 : 1;
+    int prev0 = 0, prev1 = 0;
+    for (int k = 0; k <= n_up; k++) {
+        int v0 = 0, v1 = 0;
+        if (k < n_up) {
+            v0 = (int)((long long)g->n_views * k / n_up); v1 = (int)((long long)g->n_views * (k + 1) / n_up);
+            MONTE_CUDA(cudaMemcpyAsync(d_map + v0 * per_view, map + v0 * per_view, (size_t)(v1 - v0) * per_view * sizeof(float),
+                                       cudaMemcpyHostToDevice, cp));
+            MONTE_CUDA(cudaEventRecord(ev_up[k], cp));
+            MONTE_CUDA(cudaStreamWaitEvent(st, ev_up[k], 0));
+            if (int rc = monte_gpu_fdk_filter_dev(g, d_map, v0, v1, d_filt, st)) return rc;
+            launches++;
+        }
+        if (k > 0) {                                                // chunk k-1 = views [prev0, prev1)
+            const bool last = k == n_up;
+            // the last view of the chunk reads up to two rows into the next chunk (already filtered):
+            // their duplicated column must be valid too
+            const int r0 = prev0 * g->nv, r1 = last ? rows + 2 : min(prev1 * g->nv + 2, rows + 2);
+            fdk_pad_kernel<<<ceil_div(r1 - r0, 256), 256, 0, st>>>(d_filt, rows, g->nu, pitch, r0, r1);
+            MONTE_CUDA(cudaGetLastError());
+            launches++;
+            if (last) MONTE_CUDA(cudaEventRecord(ev_t[1], st));     // everything filtered
+            const int ns = last ? n_slab : 1;
+            for (int q = 0; q < ns; q++) {
+                int z0 = (int)((long long)g->nz * q / ns), z1 = (int)((long long)g->nz * (q + 1) / ns);
+                z0 = q == 0 ? 0 : (z0 / 32) * 32;                   // slabs on z-block boundaries
+                z1 = q == ns - 1 ? g->nz : (z1 / 32) * 32;
+                if (z1 <= z0) continue;
+                if (int rc = backproject_views(g, d_filt, z0, z1, d_vol + z0 * slice, st, prev0, prev1, prev0 > 0)) return rc;
+                launches++;
+                if (last) {
+                    MONTE_CUDA(cudaEventRecord(ev_slab[q], st));
+                    MONTE_CUDA(cudaStreamWaitEvent(cp, ev_slab[q], 0));
+                    MONTE_CUDA(cudaMemcpyAsync(vol_xy + z0 * slice, d_vol + z0 * slice, (size_t)(z1 - z0) * slice * sizeof(float),
+                                               cudaMemcpyDeviceToHost, cp));
+                }
+            }
+        }
+        prev0 = v0; prev1 = v1;
+    }
+    MONTE_CUDA(cudaEventRecord(ev_t[2], st));                       // backprojected
     if (filtered) {   // d_map is free now: reuse it for the dense copy of the filtered projections
         if (int rc = monte_gpu_fdk_unpad_dev(g, d_filt, d_map, st)) return rc;
         launches += 1;
@@ -647,13 +697,20 @@ int monte_gpu_fdk(const monte_fdk_geom *g, const float *map, float *filtered, fl
         launches += 1;
         MONTE_CUDA(cudaMemcpyAsync(vol_zy, d_zy, n_vol * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
-    t_t.stop();
-    t_all.stop();
+    MONTE_CUDA(cudaEventRecord(ev_t[3], st));
+    MONTE_CUDA(cudaEventRecord(ev_t[4], cp));                       // last slab downloaded
+    MONTE_CUDA(cudaStreamWaitEvent(st, ev_t[4], 0));
+    MONTE_CUDA(cudaEventRecord(ev_t[5], st));                       // end of everything
     MONTE_CUDA(cudaStreamSynchronize(st));
     if (stats) {
         memset(stats, 0, sizeof(*stats));
-        stats->ms_h2d = t_h2d.ms(); stats->ms_filter = t_f.ms(); stats->ms_backproject = t_b.ms();
-        stats->ms_transpose = t_t.ms(); stats->ms_d2h = t_d2h.ms(); stats->ms_total = t_all.ms();
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_t[0], ev_t[1]); stats->ms_filter = ms;        // incl. the overlapped uploads
+        cudaEventElapsedTime(&ms, ev_t[1], ev_t[2]); stats->ms_backproject = ms;
+        cudaEventElapsedTime(&ms, ev_t[2], ev_t[3]); stats->ms_transpose = ms;
+        cudaEventElapsedTime(&ms, ev_t[2], ev_t[5]); stats->ms_d2h = ms;           // download not hidden behind compute
+        cudaEventElapsedTime(&ms, ev_t[0], ev_t[5]); stats->ms_total = ms;
+        stats->ms_h2d = 0;                                                          // overlapped with the filter
         stats->voxel_updates = (uint64_t)(g->s_end - g->s_begin) * (g->t_end - g->t_begin) * (g->z_end - g->z_begin) * g->n_views;
         stats->filter_macs = (uint64_t)g->n_views * g->nv * g->nu * g->nu;
         stats->launches = launches; stats->sm_count = c.sm_count;

@@ -134,6 +134,26 @@ def test_device_api_slabs_equal_whole(monte):
     assert np.array_equal(whole.cpu().numpy(), ref)
 
 
+def test_host_pipeline_chunks_equal_single_launch(monte):
+    """the host-buffer call streams views in 8 chunks and downloads 4 z-slabs (>= 64 views, nz >= 128);
+    fp32 partial sums are reloaded exactly, so it equals the one-launch device path bit for bit"""
+    import torch
+    g = _abi.generic_fdk_geom(96, 48, 40, 128)
+    g.s_begin, g.s_end, g.t_begin, g.t_end = 40, 88, 30, 100          # keep it small: a 48 x 70 x 128 region
+    proj = rand(21, (96, 48, 40))
+    f, vol, _, st = monte.fdk(g, proj)
+    d_proj = torch.from_numpy(proj).cuda()
+    filt = torch.empty(monte.fdk_filtered_shape(g), dtype=torch.float32, device="cuda")
+    monte.fdk_filter_dev(g, d_proj, filt)
+    whole = torch.empty((g.nz, g.ny, g.nx), dtype=torch.float32, device="cuda")
+    monte.fdk_backproject_dev(g, filt, whole)
+    torch.cuda.synchronize()
+    assert np.array_equal(vol, whole.cpu().numpy())
+    pitch = filt.shape[1]
+    assert np.array_equal(f, filt[: 96 * 40].view(96, 40, pitch)[:, :, :48].cpu().numpy())
+    assert st["launches"] > 20
+
+
 def test_bad_arguments_are_reported_not_fatal(monte):
     g = _abi.generic_fdk_geom(4, 16, 16, 8)
     g.s_end = 99
