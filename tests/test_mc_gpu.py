@@ -210,3 +210,44 @@ def test_full_size_c2_shape_properties(monte):
     assert st["interactions"] == st["absorbed"] + st["coherent"] + st["compton"]
     # central pixel transmission ~ exp(-mu*20cm) = 0.046: far fewer than per
     assert im0[100, 150:175, 150:175].mean() < 0.2 * per
+
+
+def test_c2_full_shape_statistical_parity(monte, oracle):
+    """BASELINE config 2 at its full shape (325^3 labels, 325x325 detector), one view, 24 photons per
+    pixel = 2.5e6 histories: CUDA path (Philox) against the oracle on MT19937 (all host threads)."""
+    g, vol, lab = scenes.config_c2()
+    xs = scenes.make_xs()
+    per, view = 24, 37
+    im0, im5, st = monte.simulate(g, vol, lab, xs, scenes.mono_spectrum(140.0), per, seed=99, views=(view, view + 1))
+    o0, o5, res, _, _ = oracle.mc_run(g, vol, lab, oracle.tables_from_xs(xs), scenes.mono_spectrum(140.0),
+                                      oracle.mc_opts(oracle.RNG_MT, seed=5, n_threads=0), per, views=(view, view + 1))
+    assert st["histories"] == res["histories"] == 325 * 325 * per
+    c2, dof, frac3 = chi2_images(im0[view], o0[view], binomial_per=per)
+    assert abs(c2 - dof) < 5 * math.sqrt(2 * dof), ("image0 chi2", c2, dof)
+    assert frac3 < 0.006
+    c2, dof, frac3 = chi2_images((im5 - im0)[view], (o5 - o0)[view])
+    assert abs(c2 - dof) < 5 * math.sqrt(2 * dof), ("scatter chi2", c2, dof)
+    for k in ("primaries", "scatter_detected", "absorbed", "compton", "coherent", "woodcock_steps"):
+        assert abs(st[k] - res[k]) < 5 * math.sqrt(st[k] + res[k] + 1) * (3 if k == "woodcock_steps" else 1), (k, st[k], res[k])
+    eg, ec = st["sum_e_scatter"] / st["scatter_detected"], res["sum_e_scatter"] / res["scatter_detected"]
+    assert abs(eg - ec) < 5 * 15.0 / math.sqrt(res["scatter_detected"]), (eg, ec)
+
+
+def test_c4_polyenergetic_cone_statistical_parity(monte, oracle):
+    """BASELINE config 4 physics (120 kVp spectrum, sampled cone) on a reduced scene, against MT19937"""
+    g, vol, lab = scene(n=41, pitch=0.5, det=25, views=2, mode=_abi.SOURCE_CONE)
+    xs = scenes.make_xs()
+    spec, keep = scenes.kramers_spectrum(120.0)
+    per = 1500
+    im0, im5, st = monte.simulate(g, vol, lab, xs, spec, per, seed=31)
+    o0, o5, res, _, _ = oracle.mc_run(g, vol, lab, oracle.tables_from_xs(xs), spec, oracle.mc_opts(oracle.RNG_MT, seed=8), per)
+    c2, dof, frac3 = chi2_images(im0, o0, binomial_per=per)
+    assert abs(c2 - dof) < 5 * math.sqrt(2 * dof) and frac3 < 0.012, ("image0", c2, dof, frac3)
+    c2, dof, frac3 = chi2_images(im5 - im0, o5 - o0)
+    assert abs(c2 - dof) < 5 * math.sqrt(2 * dof) and frac3 < 0.012, ("scatter", c2, dof, frac3)
+    # mean energies of the detected primaries (beam hardening) and of the scattered photons
+    ep_g, ep_c = st["sum_e_primary"] / st["primaries"], res["sum_e_primary"] / res["primaries"]
+    es_g, es_c = st["sum_e_scatter"] / st["scatter_detected"], res["sum_e_scatter"] / res["scatter_detected"]
+    assert abs(ep_g - ep_c) < 5 * 25.0 / math.sqrt(res["primaries"]), (ep_g, ep_c)
+    assert abs(es_g - es_c) < 5 * 25.0 / math.sqrt(res["scatter_detected"]), (es_g, es_c)
+    assert 40.0 < ep_c < 90.0
