@@ -308,9 +308,11 @@ fdk_backproject_kernel(const __grid_constant__ BpParams p) {
         const float y = fminf(fmaxf((p.half_u - u) * p.inv_du, 0.f), nuf);
         const int yi = (int)y;
         const float fy = y - (float)yi;
+        // warp-uniform row pointers + one 32-bit element offset per voxel: one IMAD and two
+        // IMAD.WIDE per update instead of 64-bit add/shift chains on the ALU pipe
         const float *__restrict__ fv = p.filt + (size_t)v * p.nv * p.pitch;
-        const float *__restrict__ q0 = fv + yi;
-        const float *__restrict__ q1 = q0 + p.pitch;
+        const float *__restrict__ fv1 = fv + p.pitch;
+        const unsigned upitch = (unsigned)p.pitch, uyi = (unsigned)yi;
         const float kz = k * p.inv_dv;
         const float kzv = kz * p.vox, kv = k * p.vox;            // per-slice increments of x and w
         const float x0v = fmaf(-kz, Z0, xoff), w0v = k * Z0;
@@ -327,8 +329,9 @@ fdk_backproject_kernel(const __grid_constant__ BpParams p) {
                     const float x = fmaxf(fmaf(kzv, (float)(h + i), x0v), 0.f);   // >= -ulp by construction
                     const int xi = (int)x;
                     fx[i] = x - (float)xi;
-                    const int off = xi * p.pitch;
-                    va[i] = __ldg(q0 + off); vb[i] = __ldg(q0 + off + 1); vc2[i] = __ldg(q1 + off); vd[i] = __ldg(q1 + off + 1);
+                    const unsigned off = (unsigned)xi * upitch + uyi;
+                    const float *__restrict__ qa = fv + off, *__restrict__ qc = fv1 + off;
+                    va[i] = __ldg(qa); vb[i] = __ldg(qa + 1); vc2[i] = __ldg(qc); vd[i] = __ldg(qc + 1);
                 }
 #pragma unroll
                 for (int i = 0; i < ZB; i++) {
@@ -354,8 +357,9 @@ fdk_backproject_kernel(const __grid_constant__ BpParams p) {
                 x = fminf(fmaxf(x, 0.f), nvf);
                 const int xi = (int)x;
                 fx[i] = x - (float)xi;
-                const int off = xi * p.pitch;
-                va[i] = __ldg(q0 + off); vb[i] = __ldg(q0 + off + 1); vc2[i] = __ldg(q1 + off); vd[i] = __ldg(q1 + off + 1);
+                const unsigned off = (unsigned)xi * upitch + uyi;
+                const float *__restrict__ qa = fv + off, *__restrict__ qc = fv1 + off;
+                va[i] = __ldg(qa); vb[i] = __ldg(qa + 1); vc2[i] = __ldg(qc); vd[i] = __ldg(qc + 1);
             }
 #pragma unroll
             for (int i = 0; i < ZB; i++) {
