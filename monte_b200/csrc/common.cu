@@ -81,7 +81,7 @@ void monte_gpu_shutdown(void) {
     if (!c.inited) return;
     cudaSetDevice(c.device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < 12; i++) {
         if (c.scratch[i]) cudaFree(c.scratch[i]);
         c.scratch[i] = nullptr;
         c.scratch_bytes[i] = 0;

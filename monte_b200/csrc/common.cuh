@@ -18,8 +18,8 @@ struct Context {
     cudaStream_t stream = nullptr;     // library-owned stream for the host-buffer entry points
     cudaStream_t copy_stream = nullptr; // second stream: D2H of finished slabs overlaps compute
     // grow-only device scratch shared by the host-buffer entry points
-    void  *scratch[8] = {nullptr};
-    size_t scratch_bytes[8] = {0};
+    void  *scratch[12] = {nullptr};
+    size_t scratch_bytes[12] = {0};
 };
 
 Context &ctx();

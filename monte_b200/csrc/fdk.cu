@@ -156,6 +156,17 @@ __global__ void fdk_pad_kernel(float *f, int rows, int nu, int pitch, int r0, in
     for (int c = nu + 1; c < pitch; c++) row[c] = 0.f;
 }
 
+// pairs[r][c] = { f[r][c], f[r+1][c] }: the two rows a bilinear fetch needs sit in one aligned 8-byte
+// element, so a voxel update issues 2 x LDG.64 instead of 4 x LDG.32 (the gathers were LSU-issue bound)
+__global__ void fdk_pair_kernel(const float *__restrict__ f, float2 *__restrict__ pairs, int r0, int r1, int rows_total, int pitch) {
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    const int r = r0 + blockIdx.x;
+    if (c >= pitch || r >= r1) return;
+    const float a = f[(size_t)r * pitch + c];
+    const float b = r + 1 < rows_total ? f[(size_t)(r + 1) * pitch + c] : 0.f;
+    pairs[(size_t)r * pitch + c] = make_float2(a, b);
+}
+
 __global__ void fdk_unpad_kernel(const float *f, float *dense, size_t rows, int nu, int pitch) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * nu) return;
@@ -171,6 +182,7 @@ constexpr int BP_TX = 32, BP_TY = 8;   // threads: 32 along s (x-fastest, coales
 
 struct BpParams {
     const float *filt;          // padded rows [n_views*nv + 2][pitch]
+    const float2 *pairs;        // same rows as vertical pairs (fdk_pair_kernel)
     const ViewConst *vc;
     float *vol;                 // slab base: slice z_lo
     int n_views, nu, nv, pitch;
@@ -311,7 +323,7 @@ fdk_backproject_kernel(const __grid_constant__ BpParams p) {
         // warp-uniform row pointers + one 32-bit element offset per voxel: one IMAD and two
         // IMAD.WIDE per update instead of 64-bit add/shift chains on the ALU pipe
         const float *__restrict__ fv = p.filt + (size_t)v * p.nv * p.pitch;
-        const float *__restrict__ fv1 = fv + p.pitch;
+        const float2 *__restrict__ fp = p.pairs + (size_t)v * p.nv * p.pitch;
         const unsigned upitch = (unsigned)p.pitch, uyi = (unsigned)yi;
         const float kz = k * p.inv_dv;
         const float kzv = kz * p.vox, kv = k * p.vox;            // per-slice increments of x and w
@@ -329,9 +341,9 @@ fdk_backproject_kernel(const __grid_constant__ BpParams p) {
                     const float x = fmaxf(fmaf(kzv, (float)(h + i), x0v), 0.f);   // >= -ulp by construction
                     const int xi = (int)x;
                     fx[i] = x - (float)xi;
-                    const unsigned off = (unsigned)xi * upitch + uyi;
-                    const float *__restrict__ qa = fv + off, *__restrict__ qc = fv1 + off;
-                    va[i] = __ldg(qa); vb[i] = __ldg(qa + 1); vc2[i] = __ldg(qc); vd[i] = __ldg(qc + 1);
+                    const float2 *__restrict__ q = fp + ((unsigned)xi * upitch + uyi);
+                    const float2 p0 = __ldg(q), p1 = __ldg(q + 1);
+                    va[i] = p0.x; vc2[i] = p0.y; vb[i] = p1.x; vd[i] = p1.y;
                 }
 #pragma unroll
                 for (int i = 0; i < ZB; i++) {
@@ -357,9 +369,9 @@ fdk_backproject_kernel(const __grid_constant__ BpParams p) {
                 x = fminf(fmaxf(x, 0.f), nvf);
                 const int xi = (int)x;
                 fx[i] = x - (float)xi;
-                const unsigned off = (unsigned)xi * upitch + uyi;
-                const float *__restrict__ qa = fv + off, *__restrict__ qc = fv1 + off;
-                va[i] = __ldg(qa); vb[i] = __ldg(qa + 1); vc2[i] = __ldg(qc); vd[i] = __ldg(qc + 1);
+                const float2 *__restrict__ q = fp + ((unsigned)xi * upitch + uyi);
+                const float2 p0 = __ldg(q), p1 = __ldg(q + 1);
+                va[i] = p0.x; vc2[i] = p0.y; vb[i] = p1.x; vd[i] = p1.y;
             }
 #pragma unroll
             for (int i = 0; i < ZB; i++) {
@@ -576,17 +588,27 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
             vchunk = (int)fmax(30.0, 64.0 * 1024 * 1024 / per_view);
         }
     }
+    // vertical row pairs of the views of this call (+ the rows the last view reaches into)
+    const int rows_total = g->n_views * g->nv + 2;
+    float2 *d_pairs = (float2 *)scratch(8, (size_t)rows_total * p.pitch * sizeof(float2));
+    if (!d_pairs) return MONTE_E_NOMEM;
+    {
+        const int r0 = view_lo * g->nv, r1 = view_hi * g->nv + 2 < rows_total ? view_hi * g->nv + 2 : rows_total;
+        fdk_pair_kernel<<<dim3(r1 - r0, ceil_div(p.pitch, 128)), 128, 0, st>>>(d_filtered_padded, d_pairs, r0, r1, rows_total, p.pitch);
+        MONTE_CUDA(cudaGetLastError());
+    }
     for (int vb = view_lo; vb < view_hi; vb += vchunk) {
     // a chunk is presented to the kernel as a shorter scan: shifted view constants and rows
     p.n_views = vb + vchunk < view_hi ? vchunk : view_hi - vb;
-    p.vc = g_fdk.d_vc + vb; p.filt = d_filtered_padded + (size_t)vb * g->nv * p.pitch; p.accumulate = continue_sum || vb > view_lo;
+    p.vc = g_fdk.d_vc + vb; p.filt = d_filtered_padded + (size_t)vb * g->nv * p.pitch;
+    p.pairs = d_pairs + (size_t)vb * g->nv * p.pitch; p.accumulate = continue_sum || vb > view_lo;
     switch (variant) {
         case 1: BP_LAUNCH(16, 8, 2); break;
         case 2: BP_LAUNCH(16, 16, 2); break;
         case 3: BP_LAUNCH(8, 8, 4); break;
-        case 5: BP_LAUNCH(16, 8, 3); break;
+        case 5: BP_LAUNCH(32, 8, 2); break;
         case 6: BP_LAUNCH(32, 16, 2); break;
-        default: BP_LAUNCH(32, 8, 2); break;
+        default: BP_LAUNCH(16, 8, 3); break;
     }
     }
 #undef BP_LAUNCH
