@@ -8,6 +8,12 @@ static thread_local char g_err[1024] = "";
 
 Context &ctx() { return g_ctx; }
 
+static std::vector<void (*)()> g_cleanups;
+void at_shutdown(void (*fn)()) {
+    for (auto f : g_cleanups) if (f == fn) return;
+    g_cleanups.push_back(fn);
+}
+
 void set_error(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -81,6 +87,7 @@ void monte_gpu_shutdown(void) {
     if (!c.inited) return;
     cudaSetDevice(c.device);
     cudaDeviceSynchronize();
+    for (auto f : g_cleanups) f();
     for (int i = 0; i < 12; i++) {
         if (c.scratch[i]) cudaFree(c.scratch[i]);
         c.scratch[i] = nullptr;

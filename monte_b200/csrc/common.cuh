@@ -23,6 +23,8 @@ struct Context {
 };
 
 Context &ctx();
+// modules register a function that frees their cached device buffers (called by monte_gpu_shutdown)
+void at_shutdown(void (*fn)());
 void set_error(const char *fmt, ...);
 int  cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 // returns device pointer of at least `bytes` in slot `slot` (contents undefined), or nullptr

@@ -429,9 +429,14 @@ struct FdkCache {           // per-geometry device constants, rebuilt only when 
     size_t vc_cap = 0, wtab_cap = 0, taps_cap = 0;
 };
 static FdkCache g_fdk;
+static void fdk_cleanup() {
+    cudaFree(g_fdk.d_vc); cudaFree(g_fdk.d_wtab); cudaFree(g_fdk.d_taps);
+    g_fdk = FdkCache();
+}
 
 static int fdk_prepare(const monte_fdk_geom *g, cudaStream_t st) {
     if (g_fdk.valid && memcmp(&g_fdk.g, g, sizeof(*g)) == 0) return MONTE_OK;
+    at_shutdown(fdk_cleanup);
     g_fdk.valid = false;
     std::vector<ViewConst> vc;
     make_view_consts(*g, vc);

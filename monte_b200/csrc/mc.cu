@@ -54,6 +54,7 @@ struct McLaunch {
     unsigned long long *work;     // unit counter (zeroed by the host)
     uint32_t *fates;              // RECORD only
     float *fate_e;
+    uint32_t second_min;          // run the runner-up phase on the same vote if >= this many lanes wait for it
 };
 
 // stats word indices
@@ -420,7 +421,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t npix = (uint32_t)(sc.det_ny * sc.det_nx);
     const float vox_off[3] = {-sc.org[0] * sc.inv_pitch - 0.5f, -sc.org[1] * sc.inv_pitch - 0.5f, -sc.org[2] * sc.inv_pitch - 0.5f};
-    constexpr uint32_t ALL = (K == 4) ? 0x1111u : (K == 3) ? 0x0111u : (K == 2) ? 0x0011u : 0x0001u;
+    constexpr uint32_t ALL = (K == 6) ? 0x111111u : (K == 5) ? 0x11111u : (K == 4) ? 0x1111u : (K == 3) ? 0x0111u : (K == 2) ? 0x0011u : 0x0001u;
 
 #define SLOT_F(f) (*reinterpret_cast<float *>(slot + (f) * FSTRIDE))
 #define SLOT_U(f) (slot[(f) * FSTRIDE])
@@ -444,12 +445,16 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
         if (st & (ALL * P_COMPTON)) onehot |= 1u << 24;
         const uint32_t cnts = __reduce_add_sync(0xffffffffu, onehot);
         if (cnts == 0u) break;                                          // every slot of every lane is done
-        const int n_ref = cnts & 0xFF, n_step = (cnts >> 8) & 0xFF, n_col = (cnts >> 16) & 0xFF, n_kah = cnts >> 24;
-        uint32_t phase = P_STEP;
-        int best = n_step;
-        if (n_ref > best) { phase = P_REFILL; best = n_ref; }
-        if (n_col > best) { phase = P_COLLIDE; best = n_col; }
-        if (n_kah > best) { phase = P_COMPTON; best = n_kah; }
+        // keys = count << 4 | phase bit; the two best phases are run on one vote (the second one's
+        // count can only have grown meanwhile), which halves the voting overhead per phase visit
+        const uint32_t k_ref = ((cnts & 0xFFu) << 4) | P_REFILL, k_step = (((cnts >> 8) & 0xFFu) << 4) | P_STEP;
+        const uint32_t k_col = (((cnts >> 16) & 0xFFu) << 4) | P_COLLIDE, k_kah = ((cnts >> 24) << 4) | P_COMPTON;
+        const uint32_t ka = max(k_ref, k_step), kb = max(k_col, k_kah), kc = min(k_ref, k_step), kd = min(k_col, k_kah);
+        const uint32_t key1 = max(ka, kb), key2 = max(min(ka, kb), ka > kb ? kc : kd);
+      for (int pass = 0; pass < 2; pass++) {
+        const uint32_t key = pass ? key2 : key1;
+        if (pass && (key >> 4) < P.second_min) break;                   // second phase only if it is well filled
+        const uint32_t phase = key & 0xFu;
         const uint32_t mine = st & (ALL * phase);
         const bool active = mine != 0u;
         const int j = active ? ((__ffs(mine) - 1) >> 2) : 0;            // my slot in that phase
@@ -566,7 +571,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             SLOT_F(F_E) = E;
             SLOT_U(F_META) = (meta & ~0xFFu) | (uint32_t)kE;
             float sphi, cphi;
-            sincospif(2.0f * SLOT_F(F_UPHI), &sphi, &cphi);           // phi = 2 pi u, :764
+            __sincosf(6.2831853071795865f * SLOT_F(F_UPHI), &sphi, &cphi);   // phi = 2 pi u, :764 (MUFU, |err| ~1e-6)
             const float dx = SLOT_F(F_DX), dy = SLOT_F(F_DY), dz = SLOT_F(F_DZ);
             // direction update, :768-780, as a rotation of the unit vector (see v2 for the algebra)
             const float st2 = dx * dx + dy * dy;
@@ -711,6 +716,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 st = (st & clr) | (P_STEP << (4 * j));
             }
         }
+      }   // pass
     }
 #undef SLOT_F
 #undef SLOT_U
@@ -893,16 +899,18 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     L.n_units = (L.total + MC_UNIT - 1) / MC_UNIT;
     L.image0 = d_image0; L.image5 = d_image5; L.stats = d_stats; L.work = s->d_work;
     L.fates = d_fates; L.fate_e = d_fate_e;
+    { static int sm = -1; if (sm < 0) { const char *e = getenv("MONTE_MC_SECOND"); sm = e ? atoi(e) : 16; } L.second_min = (uint32_t)sm; }
     if (L.total == 0) return MONTE_OK;
     MONTE_CUDA(cudaMemsetAsync(s->d_work, 0, sizeof(unsigned long long), st));
     const int sms = ctx().sm_count;
     const unsigned long long warps_needed = L.n_units;
-    // kernel selection: v3 (K parked histories per lane) is the default; MONTE_MC_KERNEL=2 runs v2, =31..34 v3 with K=1..4
+    // kernel selection: v3 with K=5 parked histories per lane is the default (measured best: K=4 9.83 ms,
+    // K=5 9.45 ms, K=6 11.2 ms per 1e8 C2 histories); MONTE_MC_KERNEL=2 runs v2, =31..36 v3 with K=1..6
     static int which = -1;
-    if (which < 0) { const char *e = getenv("MONTE_MC_KERNEL"); which = e ? atoi(e) : 34; }
+    if (which < 0) { const char *e = getenv("MONTE_MC_KERNEL"); which = e ? atoi(e) : 35; }
     MONTE_ARG(s->geom.n_views < 4096, "mc: more than 4095 views");
     const int rec = d_fates ? 1 : 0;
-    const int K = which >= 31 && which <= 34 ? which - 30 : 0;
+    const int K = which >= 31 && which <= 36 ? which - 30 : 0;
     const size_t slot_bytes = (size_t)K * 32 * (rec ? F_COUNT : F_COUNT - 1) * sizeof(uint32_t) * (MC_THREADS / 32);
     const size_t smem = K ? (size_t)s->dev.n_mat * TAB_ROWS * sizeof(float4) +
                                 (TAB_ROWS + 3 + ((s->dev.n_bins + 1 + 3) & ~3)) * sizeof(float) + slot_bytes
@@ -917,6 +925,10 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
         case 67: fn = (const void *)mc_transport_kernel_v3<true, 3>; break;
         case 68: fn = (const void *)mc_transport_kernel_v3<false, 4>; break;
         case 69: fn = (const void *)mc_transport_kernel_v3<true, 4>; break;
+        case 70: fn = (const void *)mc_transport_kernel_v3<false, 5>; break;
+        case 71: fn = (const void *)mc_transport_kernel_v3<true, 5>; break;
+        case 72: fn = (const void *)mc_transport_kernel_v3<false, 6>; break;
+        case 73: fn = (const void *)mc_transport_kernel_v3<true, 6>; break;
         default: fn = rec ? (const void *)mc_transport_kernel<true> : (const void *)mc_transport_kernel<false>; break;
     }
     static int occ[80] = {0};                      // resident CTAs per SM: persistent grid = SMs x occupancy
@@ -960,6 +972,10 @@ void monte_gpu_mc_stats_unpack(const unsigned long long *w, monte_mc_stats *out)
 
 // scene kept between monte_gpu_simulate calls: device buffers are reused, contents re-uploaded
 static monte_mc_scene *g_host_scene = nullptr;
+static void mc_cleanup() {
+    if (g_host_scene) monte_gpu_scene_destroy(g_host_scene);
+    g_host_scene = nullptr;
+}
 
 int monte_gpu_simulate(const monte_mc_geom *g, const monte_mc_volume *vol, const uint8_t *labels, const monte_mc_xs *xs,
                        const monte_mc_spectrum *spec, uint32_t photons_per_pixel, uint64_t seed, int view_begin,
@@ -983,7 +999,7 @@ int monte_gpu_simulate_range(const monte_mc_geom *g, const monte_mc_volume *vol,
     EventTimer t_all(st), t_h2d(st), t_k(st), t_d2h(st);
     t_all.start();
     t_h2d.start();
-    if (!g_host_scene) g_host_scene = new monte_mc_scene();
+    if (!g_host_scene) { g_host_scene = new monte_mc_scene(); at_shutdown(mc_cleanup); }
     monte_mc_scene *s = g_host_scene;
     if (int rc = scene_upload(s, g, vol, labels, xs, spec, st)) return rc;
     t_h2d.stop();
