@@ -260,7 +260,7 @@ def main():
     achieved = (hist_rank / (ms_mc * 1e-3)) * instr_per_hist / 1e12            # per GPU, T lane-instr/s
     mc_roof = {"bound": "fp32-issue", "achieved": achieved, "peak": pk["fp32_tlane_instr"], "unit": "Tlane-instr/s",
                "frac": achieved / pk["fp32_tlane_instr"], "traffic": profile_traffic("mc_transport_kernel"),
-               "kernel": "mc_transport_kernel", "kernel_ms_per_launch": ms_mc / K,
+               "kernel": "mc_transport_kernel_v3<false,5>", "kernel_ms_per_launch": ms_mc / K,
                "model": "%d instr/Woodcock step x %.3f steps/history + %d instr/interaction x %.3f (SURVEY 8d); "
                         "peak = 148 SM x 128 lanes x %.0f MHz (%s)" % (MC_INSTR_PER_STEP, steps_per_hist,
                                                                       MC_INSTR_PER_INTERACTION, int_per_hist,
@@ -279,8 +279,9 @@ def main():
         if ws == 1:
             api.simulate(g, vol, lab_pin.numpy(), xs, spec, per_total, seed=20261017, views=(v, v + 1),
                          out=(h0.numpy(), h5.numpy()))
-        else:                                     # H2D scene, kernel, NCCL reduce, D2H on rank 0
-            sc = api.Scene(g, vol, lab_pin.numpy(), xs, spec)
+        else:                                     # H2D labels, kernel, NCCL reduce, D2H on rank 0
+            sc = scene
+            sc.update_labels(lab_pin.numpy())
             im0[v].zero_(); im5[v].zero_()
             sc.simulate_dev(im0, im5, per_total, seed=20261017, views=(v, v + 1), n_range=nr)
             dist.reduce(im0[v:v + 1], dst=0)
@@ -289,7 +290,6 @@ def main():
                 h0[v].copy_(im0[v], non_blocking=True)
                 h5[v].copy_(im5[v], non_blocking=True)
             torch.cuda.synchronize()
-            sc.close()
 
     for k in range(2):
         mc_e2e_step(k)

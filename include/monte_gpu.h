@@ -251,6 +251,8 @@ int monte_gpu_scene_create(const monte_mc_geom *g, const monte_mc_volume *vol,
                            const uint8_t *labels, const monte_mc_xs *xs,
                            const monte_mc_spectrum *spec, monte_mc_scene **out);
 void monte_gpu_scene_destroy(monte_mc_scene *s);
+/* re-upload the label volume of an existing scene (same dimensions) from a host buffer, on `stream` */
+int monte_gpu_scene_update_labels(monte_mc_scene *s, const uint8_t *labels, void *stream);
 /* Run photons n in [n_begin, n_end) of every pixel of views [view_begin, view_end)
  * and add into d_image0/d_image5 (device, [n_views][ny][nx], caller zeroes).
  * d_stats: device uint64[16] accumulators (nullable), see monte_gpu_mc_stats_unpack. */

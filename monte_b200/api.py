@@ -59,6 +59,7 @@ def load():
         "monte_gpu_scene_create": (C.c_int, [C.POINTER(McGeom), C.POINTER(McVolume), vp, C.POINTER(McXs),
                                              C.POINTER(McSpectrum), C.POINTER(vp)]),
         "monte_gpu_scene_destroy": (None, [vp]),
+        "monte_gpu_scene_update_labels": (C.c_int, [vp, vp, vp]),
         "monte_gpu_simulate_dev": (C.c_int, [vp, u64, C.c_int, C.c_int, u32, u32, u32, vp, vp, vp, vp]),
         "monte_gpu_mc_stats_unpack": (None, [vp, C.POINTER(McStats)]),
         "monte_gpu_simulate_fates": (C.c_int, [vp, u64, C.c_int, u32, vp, vp]),
@@ -215,6 +216,11 @@ class Scene:
         self.handle = C.c_void_p()
         _check(lib.monte_gpu_scene_create(C.byref(g), C.byref(vol), _ptr(self._keep[1]), C.byref(xs),
                                           C.byref(spec) if spec is not None else None, C.byref(self.handle)))
+
+    def update_labels(self, labels, stream=None):
+        """H2D of a new label volume (same shape) into the resident scene"""
+        labels = np.ascontiguousarray(labels, np.uint8)
+        _check(load().monte_gpu_scene_update_labels(self.handle, _ptr(labels), _stream_ptr(stream)))
 
     def close(self):
         if self.handle:

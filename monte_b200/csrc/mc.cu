@@ -876,6 +876,14 @@ int monte_gpu_scene_create(const monte_mc_geom *g, const monte_mc_volume *vol, c
     return MONTE_OK;
 }
 
+int monte_gpu_scene_update_labels(monte_mc_scene *s, const uint8_t *labels, void *stream) {
+    MONTE_REQUIRE_INIT();
+    MONTE_ARG(s && labels, "scene_update_labels: NULL argument");
+    const size_t nvox = (size_t)s->dev.nx * s->dev.ny * s->dev.nz;
+    MONTE_CUDA(cudaMemcpyAsync(s->d_labels, labels, nvox, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return MONTE_OK;
+}
+
 void monte_gpu_scene_destroy(monte_mc_scene *s) {
     if (!s) return;
     cudaFree(s->d_labels); cudaFree(s->d_tab); cudaFree(s->d_cdf); cudaFree(s->d_view); cudaFree(s->d_work);
