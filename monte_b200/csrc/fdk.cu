@@ -69,7 +69,7 @@ static int check_geom(const monte_fdk_geom *g) {
 // weight + Ram-Lak filter
 // ------------------------------------------------------------------------------------------
 constexpr int FT_D = 8;          // axial rows (d) per CTA
-constexpr int FT_NB = 8;         // outputs of one parity per task
+constexpr int FT_NB = 16;        // outputs of one parity per task
 constexpr int FT_THREADS = 256;
 
 struct FilterParams {
@@ -111,27 +111,30 @@ fdk_weight_filter_kernel(const FilterParams p) {
 
     // step 2: out[b] = sum_c in[c]*tap(c-b); even offsets are zero, offset 0 is the centre tap.
     // A task owns FT_NB outputs of one parity b_j = b0 + 2j and walks the inputs of the other
-    // parity in ascending c (the reference's order, bp3d20.cpp:67).
-    const int n_strips = (p.nu + 15) / 16;
+    // parity in ascending c (the reference's order, bp3d20.cpp:67), 8 inputs per trip:
+    // 8 + (8 + FT_NB - 1) shared-memory loads feed 8*FT_NB FMAs.
+    constexpr int SW = 2 * FT_NB;                       // outputs covered by a strip (both parities)
+    constexpr int NT = 8 + FT_NB - 1;                   // taps needed per trip
+    const int n_strips = (p.nu + SW - 1) / SW;
     const int n_tasks = FT_D * 2 * n_strips;
     for (int task = tid; task < n_tasks; task += FT_THREADS) {
         const int dl = task & 7, q = (task >> 3) & 1, strip = task >> 4;
-        const int b0 = strip * 16 + q;
+        const int b0 = strip * SW + q;
         const float *row = s_in + dl * p.in_pitch;
         float acc[FT_NB];
 #pragma unroll
         for (int j = 0; j < FT_NB; j++) acc[j] = row[b0 + 2 * j] * p.center;
         for (int c = q ^ 1; c < p.nu; c += 16) {
-            const int mbase = (c - b0 - 14 + p.noff) >> 1;
-            float tp[15], x[8];
+            const int mbase = (c - b0 - 2 * (FT_NB - 1) + p.noff) >> 1;
+            float tp[NT], x[8];
 #pragma unroll
-            for (int k = 0; k < 15; k++) tp[k] = s_tap[mbase + k];
+            for (int k = 0; k < NT; k++) tp[k] = s_tap[mbase + k];
 #pragma unroll
             for (int u = 0; u < 8; u++) x[u] = row[c + 2 * u];
 #pragma unroll
             for (int u = 0; u < 8; u++)
 #pragma unroll
-                for (int j = 0; j < FT_NB; j++) acc[j] = fmaf(x[u], tp[u - j + 7], acc[j]);
+                for (int j = 0; j < FT_NB; j++) acc[j] = fmaf(x[u], tp[u - j + FT_NB - 1], acc[j]);
         }
 #pragma unroll
         for (int j = 0; j < FT_NB; j++) s_out[dl * p.in_pitch + b0 + 2 * j] = acc[j];
@@ -450,9 +453,9 @@ static int fdk_prepare(const monte_fdk_geom *g, cudaStream_t st) {
             wtab[(size_t)zeta * g->nv + pp] = wd / sqrt(pow(wd, 2) + pow(a, 2) + pow(b, 2));
         }
     // Ram-Lak taps for odd offsets, bp3d20.cpp:57 (float) times the filter scale (double product)
-    const int nu_pad = ((g->nu + 15) / 16) * 16 + 16;
-    int noff = nu_pad + 17; if ((noff & 1) == 0) noff++;
-    const int tap_len = (nu_pad + 2 + noff) / 2 + 16;
+    const int nu_pad = ((g->nu + 2 * FT_NB - 1) / (2 * FT_NB)) * (2 * FT_NB) + 16;   // strips of 2*FT_NB outputs + 16 inputs of slack
+    int noff = nu_pad + 2 * FT_NB + 1; if ((noff & 1) == 0) noff++;
+    const int tap_len = (nu_pad + 2 + noff) / 2 + FT_NB + 8;
     const double scale = textbook ? g->dsd / (g->dso * g->du) : g->filter_scale;
     std::vector<float> taps(tap_len, 0.f);
     for (int m = 0; m < tap_len; m++) {
