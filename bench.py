@@ -67,6 +67,11 @@ class ClockSampler:
 
     def __init__(self, device):
         self.device, self.proc, self.path = device, None, None
+        try:                                   # CUDA_VISIBLE_DEVICES may renumber: address the GPU by UUID
+            import torch
+            self.device = "GPU-" + str(torch.cuda.get_device_properties(int(device)).uuid)
+        except Exception:
+            pass
 
     def start(self):
         try:

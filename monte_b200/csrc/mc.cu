@@ -400,8 +400,8 @@ enum { F_X = 0, F_Y, F_Z, F_DX, F_DY, F_DZ, F_E, F_C0, F_META, F_CTR, F_PIXVIEW,
 // CTR : bits 0-19 flight-stream index, 20-31 event-stream index
 // PIXVIEW: bits 0-19 pixel, 20-31 view
 
-template <bool RECORD, int K>
-__global__ void __launch_bounds__(MC_THREADS, 3)
+template <bool RECORD, int K, int MINB = 3>
+__global__ void __launch_bounds__(MC_THREADS, MINB)
 mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
     extern __shared__ float4 s_mem[];
     const McSceneDev &sc = P.sc;
@@ -918,7 +918,7 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     if (which < 0) { const char *e = getenv("MONTE_MC_KERNEL"); which = e ? atoi(e) : 35; }
     MONTE_ARG(s->geom.n_views < 4096, "mc: more than 4095 views");
     const int rec = d_fates ? 1 : 0;
-    const int K = which >= 31 && which <= 36 ? which - 30 : 0;
+    const int K = which >= 31 && which <= 36 ? which - 30 : (which == 44 ? 4 : (which == 43 ? 3 : 0));
     const size_t slot_bytes = (size_t)K * 32 * (rec ? F_COUNT : F_COUNT - 1) * sizeof(uint32_t) * (MC_THREADS / 32);
     const size_t smem = K ? (size_t)s->dev.n_mat * TAB_ROWS * sizeof(float4) +
                                 (TAB_ROWS + 3 + ((s->dev.n_bins + 1 + 3) & ~3)) * sizeof(float) + slot_bytes
@@ -936,12 +936,14 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
         case 70: fn = (const void *)mc_transport_kernel_v3<false, 5>; break;
         case 71: fn = (const void *)mc_transport_kernel_v3<true, 5>; break;
         case 72: fn = (const void *)mc_transport_kernel_v3<false, 6>; break;
+        case 88: fn = (const void *)mc_transport_kernel_v3<false, 4, 4>; break;    // which=44: K=4, 4 CTAs/SM (64 regs)
+        case 86: fn = (const void *)mc_transport_kernel_v3<false, 3, 4>; break;    // which=43
         case 73: fn = (const void *)mc_transport_kernel_v3<true, 6>; break;
         default: fn = rec ? (const void *)mc_transport_kernel<true> : (const void *)mc_transport_kernel<false>; break;
     }
-    static int occ[80] = {0};                      // resident CTAs per SM: persistent grid = SMs x occupancy
-    static size_t smem_set[80] = {0}, smem_occ[80] = {0};
-    const int slot_id = (which * 2 + rec) % 80;
+    static int occ[96] = {0};                      // resident CTAs per SM: persistent grid = SMs x occupancy
+    static size_t smem_set[96] = {0}, smem_occ[96] = {0};
+    const int slot_id = (which * 2 + rec) % 96;
     int &oc = occ[slot_id];
     MONTE_ARG(smem <= 227 * 1024, "mc: %zu bytes of shared memory needed (> 227 KB)", smem);
     if (smem > smem_set[slot_id]) {
