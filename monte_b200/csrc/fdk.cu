@@ -161,10 +161,13 @@ __global__ void fdk_pad_kernel(float *f, int rows, int nu, int pitch, int r0, in
 
 // pairs[r][c] = { f[r][c], f[r+1][c] }: the two rows a bilinear fetch needs sit in one aligned 8-byte
 // element, so a voxel update issues 2 x LDG.64 instead of 4 x LDG.32 (the gathers were LSU-issue bound)
-__global__ void fdk_pair_kernel(const float *__restrict__ f, float2 *__restrict__ pairs, int r0, int r1, int rows_total, int pitch) {
+// Only rows [b_lo, b_hi) of every view are paired: the band a z-slab projects onto (all rows for a
+// whole-volume call, ~1/N of them for one of N multi-GPU slabs).
+__global__ void fdk_pair_kernel(const float *__restrict__ f, float2 *__restrict__ pairs, int view_lo, int nv, int b_lo, int b_hi,
+                                int rows_total, int pitch) {
     const int c = blockIdx.y * blockDim.x + threadIdx.x;
-    const int r = r0 + blockIdx.x;
-    if (c >= pitch || r >= r1) return;
+    const int r = (view_lo + (int)blockIdx.z) * nv + b_lo + (int)blockIdx.x;
+    if (c >= pitch || (int)blockIdx.x >= b_hi - b_lo || r >= rows_total) return;
     const float a = f[(size_t)r * pitch + c];
     const float b = r + 1 < rows_total ? f[(size_t)(r + 1) * pitch + c] : 0.f;
     pairs[(size_t)r * pitch + c] = make_float2(a, b);
@@ -601,9 +604,35 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
     float2 *d_pairs = (float2 *)scratch(8, (size_t)rows_total * p.pitch * sizeof(float2));
     if (!d_pairs) return MONTE_E_NOMEM;
     {
-        const int r0 = view_lo * g->nv, r1 = view_hi * g->nv + 2 < rows_total ? view_hi * g->nv + 2 : rows_total;
-        fdk_pair_kernel<<<dim3(r1 - r0, ceil_div(p.pitch, 128)), 128, 0, st>>>(d_filtered_padded, d_pairs, r0, r1, rows_total, p.pitch);
+        // axial detector rows the slab [z_lo, z_hi) can reach: x = nv/2-ish - k*Z/dv with k between the
+        // magnifications of the nearest and the farthest voxel; +-2 rows of slack, +1 for the pair's partner
+        const double r = 0.5 * g->vox * sqrt((double)g->nx * g->nx + (double)g->ny * g->ny) +
+                         fmax(fabs(g->x0 + 0.5 * g->vox * g->nx), fabs(g->y0 - 0.5 * g->vox * g->ny));
+        const double kmin = g->dsd / (g->dso + r), kmax = g->dsd / fmax(g->dso - r, 0.05 * g->dso);
+        const double Za = g->z0 - g->vox * z_lo, Zb = g->z0 - g->vox * (z_hi - 1);
+        double xmin = 1e30, xmax = -1e30;
+        for (int i = 0; i < 4; i++) {
+            const double x = (g->half_v - ((i & 1) ? kmax : kmin) * ((i & 2) ? Zb : Za)) / g->dv;
+            xmin = fmin(xmin, x); xmax = fmax(xmax, x);
+        }
+        int b_lo = (int)floor(xmin) - 2, b_hi = (int)ceil(xmax) + 4;
+        if (b_lo < 0) b_lo = 0;
+        if (b_hi > g->nv) b_hi = g->nv;       // rows nv, nv+1 of a view are rows 0, 1 of the next one
+        if (b_hi <= b_lo) { b_lo = 0; b_hi = g->nv; }
+        // rows 0..3 of every view are always paired too: they are what the previous view reaches past its end
+        const int n_v = view_hi - view_lo + (view_hi < g->n_views ? 1 : 0);
+        if (b_lo > 0) {
+            fdk_pair_kernel<<<dim3(b_lo < 4 ? b_lo : 4, ceil_div(p.pitch, 128), n_v), 128, 0, st>>>(d_filtered_padded, d_pairs, view_lo, g->nv, 0,
+                                                                                                   b_lo < 4 ? b_lo : 4, rows_total, p.pitch);
+            MONTE_CUDA(cudaGetLastError());
+        }
+        fdk_pair_kernel<<<dim3(b_hi - b_lo, ceil_div(p.pitch, 128), n_v), 128, 0, st>>>(d_filtered_padded, d_pairs, view_lo, g->nv, b_lo, b_hi,
+                                                                                       rows_total, p.pitch);
         MONTE_CUDA(cudaGetLastError());
+        if (view_hi == g->n_views) {          // the two zero rows after the last view
+            fdk_pair_kernel<<<dim3(2, ceil_div(p.pitch, 128), 1), 128, 0, st>>>(d_filtered_padded, d_pairs, g->n_views, g->nv, 0, 2, rows_total, p.pitch);
+            MONTE_CUDA(cudaGetLastError());
+        }
     }
     for (int vb = view_lo; vb < view_hi; vb += vchunk) {
     // a chunk is presented to the kernel as a shorter scan: shifted view constants and rows
