@@ -132,6 +132,16 @@ int monte_gpu_fdk_pad_dev(const monte_fdk_geom *g, float *d_filtered_padded, voi
  * d_vol_slab points at slice z_lo, layout [z_hi-z_lo][ny][nx].  Overwrites.        */
 int monte_gpu_fdk_backproject_dev(const monte_fdk_geom *g, const float *d_filtered_padded,
                                   int z_lo, int z_hi, float *d_vol_slab, void *stream);
+/* Same for views [view_lo, view_hi) only.  continue_sum != 0: the slab already holds the fp32 partial
+ * sums of the earlier views (they are continued exactly, so feeding the views in ascending pieces
+ * gives the bits of the single call); 0: the slab is overwritten.  This is what lets a multi-GPU
+ * host overlap the exchange of later views with the backprojection of earlier ones.              */
+int monte_gpu_fdk_backproject_views_dev(const monte_fdk_geom *g, const float *d_filtered_padded,
+                                        int z_lo, int z_hi, float *d_vol_slab,
+                                        int view_lo, int view_hi, int continue_sum, void *stream);
+/* pad fix-up restricted to the rows of views [view_lo, view_hi) (+ the two rows they reach into) */
+int monte_gpu_fdk_pad_views_dev(const monte_fdk_geom *g, float *d_filtered_padded,
+                                int view_lo, int view_hi, void *stream);
 /* vol_zy[s][t][z] = vol_xy[z][t][s] */
 int monte_gpu_fdk_transpose_dev(const monte_fdk_geom *g, const float *d_vol_xy,
                                 float *d_vol_zy, void *stream);

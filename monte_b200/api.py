@@ -48,6 +48,8 @@ def load():
         "monte_gpu_fdk_pad_dev": (C.c_int, [G, vp, vp]),
         "monte_gpu_fdk_backproject_dev": (C.c_int, [G, vp, C.c_int, C.c_int, vp, vp]),
         "monte_gpu_fdk_transpose_dev": (C.c_int, [G, vp, vp, vp]),
+        "monte_gpu_fdk_backproject_views_dev": (C.c_int, [G, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
+        "monte_gpu_fdk_pad_views_dev": (C.c_int, [G, vp, C.c_int, C.c_int, vp]),
         "monte_gpu_fdk_unpad_dev": (C.c_int, [G, vp, vp, vp]),
         "monte_gpu_fbp2": (C.c_int, [G, C.c_int, vp, vp, vp, C.POINTER(FdkStats)]),
         "monte_gpu_simulate": (C.c_int, [C.POINTER(McGeom), C.POINTER(McVolume), vp, C.POINTER(McXs),
@@ -174,6 +176,16 @@ def fdk_backproject_dev(g, d_filt, d_slab, z_lo=0, z_hi=None, stream=None):
     zh = g.nz if z_hi is None else z_hi
     _check(lib.monte_gpu_fdk_backproject_dev(C.byref(g), C.c_void_p(d_filt.data_ptr()), z_lo, zh,
                                              C.c_void_p(d_slab.data_ptr()), _stream_ptr(stream)))
+
+
+def fdk_backproject_views_dev(g, d_filt, d_slab, z_lo, z_hi, view_lo, view_hi, continue_sum, stream=None):
+    _check(load().monte_gpu_fdk_backproject_views_dev(C.byref(g), C.c_void_p(d_filt.data_ptr()), z_lo, z_hi,
+                                                      C.c_void_p(d_slab.data_ptr()), view_lo, view_hi,
+                                                      1 if continue_sum else 0, _stream_ptr(stream)))
+
+
+def fdk_pad_views_dev(g, d_filt, view_lo, view_hi, stream=None):
+    _check(load().monte_gpu_fdk_pad_views_dev(C.byref(g), C.c_void_p(d_filt.data_ptr()), view_lo, view_hi, _stream_ptr(stream)))
 
 
 def fdk_unpad_dev(g, d_filt, d_dense, stream=None):

@@ -534,6 +534,18 @@ int monte_gpu_fdk_pad_dev(const monte_fdk_geom *g, float *d_filtered_padded, voi
     return MONTE_OK;
 }
 
+int monte_gpu_fdk_pad_views_dev(const monte_fdk_geom *g, float *d_filtered_padded, int view_lo, int view_hi, void *stream) {
+    MONTE_REQUIRE_INIT();
+    if (int rc = check_geom(g)) return rc;
+    MONTE_ARG(0 <= view_lo && view_lo <= view_hi && view_hi <= g->n_views, "fdk_pad_views: bad view range");
+    if (view_lo == view_hi) return MONTE_OK;
+    const int rows = g->n_views * g->nv;
+    const int r0 = view_lo * g->nv, r1 = view_hi == g->n_views ? rows + 2 : min(view_hi * g->nv + 2, rows + 2);
+    fdk_pad_kernel<<<ceil_div(r1 - r0, 256), 256, 0, (cudaStream_t)stream>>>(d_filtered_padded, rows, g->nu, (int)filtered_pitch(g), r0, r1);
+    MONTE_CUDA(cudaGetLastError());
+    return MONTE_OK;
+}
+
 int monte_gpu_fdk_unpad_dev(const monte_fdk_geom *g, const float *d_filtered_padded, float *d_dense, void *stream) {
     MONTE_REQUIRE_INIT();
     if (int rc = check_geom(g)) return rc;
@@ -660,6 +672,16 @@ int monte_gpu_fdk_backproject_dev(const monte_fdk_geom *g, const float *d_filter
     MONTE_ARG(d_filtered_padded && d_vol_slab, "fdk_backproject: NULL device pointer");
     MONTE_ARG(0 <= z_lo && z_lo <= z_hi && z_hi <= g->nz, "fdk_backproject: bad z range [%d,%d)", z_lo, z_hi);
     return backproject_views(g, d_filtered_padded, z_lo, z_hi, d_vol_slab, (cudaStream_t)stream, 0, g->n_views, false);
+}
+
+int monte_gpu_fdk_backproject_views_dev(const monte_fdk_geom *g, const float *d_filtered_padded, int z_lo, int z_hi,
+                                        float *d_vol_slab, int view_lo, int view_hi, int continue_sum, void *stream) {
+    MONTE_REQUIRE_INIT();
+    if (int rc = check_geom(g)) return rc;
+    MONTE_ARG(d_filtered_padded && d_vol_slab, "fdk_backproject_views: NULL device pointer");
+    MONTE_ARG(0 <= z_lo && z_lo <= z_hi && z_hi <= g->nz, "fdk_backproject_views: bad z range [%d,%d)", z_lo, z_hi);
+    MONTE_ARG(0 <= view_lo && view_lo <= view_hi && view_hi <= g->n_views, "fdk_backproject_views: bad view range");
+    return backproject_views(g, d_filtered_padded, z_lo, z_hi, d_vol_slab, (cudaStream_t)stream, view_lo, view_hi, continue_sum != 0);
 }
 
 int monte_gpu_fdk_transpose_dev(const monte_fdk_geom *g, const float *d_vol_xy, float *d_vol_zy, void *stream) {

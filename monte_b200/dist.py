@@ -76,6 +76,39 @@ def fdk_sharded(filter_views, pad, backproject_slab, filt_rows, n_views, nv, nz)
     return (v_lo, v_hi), (z_lo, z_hi)
 
 
+def fdk_sharded_pipelined(filter_views, pad_views, backproject_views, filt_rows, n_views, nv, nz):
+    """Same result as fdk_sharded, bit for bit, with the exchange hidden behind the backprojection:
+    every rank filters its own views, then the view pieces are broadcast in ascending order (all
+    broadcasts are queued at once on NCCL's stream) and piece r is backprojected — continuing the
+    fp32 partial sums — as soon as pieces r and r+1 have landed (piece r's pad fix-up needs the first
+    rows of piece r+1).  Views are consumed in ascending order, exactly as on one GPU.
+    filter_views(lo, hi); pad_views(lo, hi); backproject_views(z_lo, z_hi, v_lo, v_hi, continue_sum)."""
+    rank, ws = world()
+    z_lo, z_hi = split_range(nz, ws, rank)
+    pieces = [split_range(n_views, ws, r) for r in range(ws)]
+    v_lo, v_hi = pieces[rank]
+    filter_views(v_lo, v_hi)
+    works = [None] * ws
+    if ws > 1:
+        pitch = filt_rows.shape[1]
+        body = filt_rows[: n_views * nv].view(-1)
+        for r, (lo, hi) in enumerate(pieces):
+            if hi > lo:
+                works[r] = dist.broadcast(body[lo * nv * pitch: hi * nv * pitch], src=r, async_op=True)
+    started = False
+    for r, (lo, hi) in enumerate(pieces):
+        if hi <= lo:
+            continue
+        for q in (r, r + 1):                       # this piece and the one its last view reaches into
+            if q < ws and works[q] is not None:
+                works[q].wait()
+                works[q] = None
+        pad_views(lo, hi)
+        backproject_views(z_lo, z_hi, lo, hi, started)
+        started = True
+    return (v_lo, v_hi), (z_lo, z_hi)
+
+
 def max_over_ranks(value, device):
     """max of a python float over ranks (timing rule: a multi-GPU time is the slowest rank's)"""
     if not is_dist() or dist.get_world_size() == 1:

@@ -99,3 +99,71 @@ def test_sharded_equals_unsharded(tmp_path, oracle, ws):
         z = p["z"][1]
     assert z == fg.nz
     assert sum(int(p["v"][1] - p["v"][0]) for p in parts) == fg.n_views
+
+
+# ---------------------------------------------------------------- pipelined exchange (async broadcasts)
+def _fake_rows(v, nv, pitch, nu):
+    rng = np.random.default_rng(1000 + v)
+    r = np.zeros((nv, pitch), np.float32)
+    r[:, :nu] = rng.random((nv, nu), dtype=np.float32)
+    return r
+
+
+def _pipe_worker(rank, ws, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    n_views, nv, nu, pitch, nz = 11, 5, 6, 8, 7
+    rows = torch.full((n_views * nv + 2, pitch), float("nan"))        # NaN = "not received yet"
+    rows[n_views * nv:] = 0
+    slab = {}
+    log = []
+
+    def filter_views(lo, hi):
+        for v in range(lo, hi):
+            rows[v * nv:(v + 1) * nv] = torch.from_numpy(_fake_rows(v, nv, pitch, nu))
+
+    def pad_views(lo, hi):                      # the dup column needs the NEXT row, i.e. the next piece's first row
+        r1 = min(hi * nv + 2, n_views * nv + 2) if hi < n_views else n_views * nv + 2
+        for r in range(lo * nv, r1):
+            if r < n_views * nv:
+                rows[r, nu] = rows[r + 1, 0] if r + 1 < n_views * nv else 0.0
+                rows[r, nu + 1:] = 0
+
+    def backproject_views(z_lo, z_hi, v_lo, v_hi, cont):
+        acc = slab["v"] if cont else torch.zeros(z_hi - z_lo, dtype=torch.float32)
+        for v in range(v_lo, v_hi):             # order-sensitive fp32 accumulation; reads one row past the view
+            blk = rows[v * nv:(v + 1) * nv + 1, : nu + 1]
+            assert not torch.isnan(blk).any(), "view %d used before it (or its successor) arrived" % v
+            acc = acc * np.float32(1.0001) + blk.sum() * torch.arange(z_lo, z_hi, dtype=torch.float32)
+        slab["v"] = acc
+        log.append((v_lo, v_hi, cont))
+
+    vr, zr = mdist.fdk_sharded_pipelined(filter_views, pad_views, backproject_views, rows, n_views, nv, nz)
+    np.savez(os.path.join(out_dir, "p%d.npz" % rank), slab=slab["v"].numpy(), z=np.array(zr), log=np.array(log))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ws", [1, 2, 3])
+def test_pipelined_exchange_equals_sequential(tmp_path, ws):
+    port = 29800 + os.getpid() % 1500 + ws
+    mp.spawn(_pipe_worker, args=(ws, port, str(tmp_path)), nprocs=ws, join=True)
+    n_views, nv, nu, pitch, nz = 11, 5, 6, 8, 7
+    rows = np.zeros((n_views * nv + 2, pitch), np.float32)
+    for v in range(n_views):
+        rows[v * nv:(v + 1) * nv] = _fake_rows(v, nv, pitch, nu)
+    for r in range(n_views * nv):
+        rows[r, nu] = rows[r + 1, 0] if r + 1 < n_views * nv else 0.0
+    acc = np.zeros(nz, np.float32)
+    for v in range(n_views):
+        acc = (torch.from_numpy(acc) * np.float32(1.0001) + torch.from_numpy(rows[v * nv:(v + 1) * nv + 1, : nu + 1]).sum()
+               * torch.arange(0, nz, dtype=torch.float32)).numpy()
+    z = 0
+    for r in range(ws):
+        p = np.load(os.path.join(str(tmp_path), "p%d.npz" % r))
+        assert p["z"][0] == z
+        assert np.array_equal(p["slab"], acc[p["z"][0]:p["z"][1]]), r
+        assert [int(x) for x in p["log"][:, 0]] == [mdist.split_range(n_views, ws, q)[0] for q in range(ws)]
+        z = p["z"][1]
+    assert z == nz

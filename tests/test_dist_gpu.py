@@ -38,8 +38,15 @@ z_lo, z_hi = mdist.split_range(fg.nz, ws, rank)
 slab = torch.empty((z_hi - z_lo, fg.ny, fg.nx), device=dev)
 mdist.fdk_sharded(lambda a, b: api.fdk_filter_dev(fg, proj, filt, a, b, pad=False), lambda: api.fdk_pad_dev(fg, filt),
                   lambda a, b: api.fdk_backproject_dev(fg, filt, slab, a, b), filt, fg.n_views, fg.nv, fg.nz)
+slab2 = torch.empty_like(slab)
+filt.zero_()
+mdist.fdk_sharded_pipelined(lambda a, b: api.fdk_filter_dev(fg, proj, filt, a, b, pad=False),
+                            lambda a, b: api.fdk_pad_views_dev(fg, filt, a, b),
+                            lambda z0, z1, a, b, cont: api.fdk_backproject_views_dev(fg, filt, slab2, z0, z1, a, b, cont),
+                            filt, fg.n_views, fg.nv, fg.nz)
 torch.cuda.synchronize()
-np.savez(os.path.join(out, "r%%d.npz" %% rank), im0=im0.cpu().numpy(), im5=im5.cpu().numpy(), slab=slab.cpu().numpy(), z=np.array([z_lo, z_hi]))
+assert torch.equal(slab, slab2), "pipelined exchange differs from gather-then-backproject"
+np.savez(os.path.join(out, "r%%d.npz" %% rank), im0=im0.cpu().numpy(), im5=im5.cpu().numpy(), slab=slab2.cpu().numpy(), z=np.array([z_lo, z_hi]))
 dist.barrier(); dist.destroy_process_group()
 '''
 
