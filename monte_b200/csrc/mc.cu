@@ -22,7 +22,10 @@
 namespace monte {
 
 constexpr int MC_THREADS = 256;
-constexpr int MC_UNIT = 2048;            // histories per work unit (one warp)
+#ifndef MONTE_MC_UNIT
+#define MONTE_MC_UNIT 1024
+#endif
+constexpr int MC_UNIT = MONTE_MC_UNIT;   // histories per work unit (one warp)
 constexpr int TAB_ROWS = MONTE_MC_TABLE_ROWS;
 
 struct McSceneDev {
