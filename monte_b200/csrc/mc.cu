@@ -398,10 +398,15 @@ mc_transport_kernel(const __grid_constant__ McLaunch P) {
 // (counter-based), so results are bit-identical to v1/v2.
 // ------------------------------------------------------------------------------------------------
 enum : uint32_t { P_REFILL = 1u, P_STEP = 2u, P_COLLIDE = 4u, P_COMPTON = 8u };
-enum { F_X = 0, F_Y, F_Z, F_DX, F_DY, F_DZ, F_E, F_C0, F_META, F_CTR, F_PIXVIEW, F_UPHI, F_REC, F_COUNT };
+// Slot state = three (RECORD: four) 16-byte groups per slot and lane, laid out [group][slot][lane]
+// so that a warp's LDS.128 / STS.128 touches 512 contiguous bytes (conflict-free):
+//   G_POS : x, y, z, E            G_DIR : dx, dy, dz, u_phi
+//   G_ID  : c0, META, CTR, PIXVIEW            G_REC : record index (fate dump only)
 // META: bits 0-7 kE, 8-11 nint, 12-14 material, 15 pending-detect, 24-31 high byte of the history id
 // CTR : bits 0-19 flight-stream index, 20-31 event-stream index
 // PIXVIEW: bits 0-19 pixel, 20-31 view
+enum { G_POS = 0, G_DIR = 1, G_ID = 2, G_REC = 3 };
+constexpr int mc_slot_groups(bool record) { return record ? 4 : 3; }
 
 template <bool RECORD, int K, int MINB = 3>
 __global__ void __launch_bounds__(MC_THREADS, MINB)
@@ -411,10 +416,9 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
     float4 *s_tab = s_mem;                                             // [n_mat*201]
     float *s_inv = reinterpret_cast<float *>(s_tab + sc.n_mat * TAB_ROWS);   // [201]
     float *s_cdf = s_inv + TAB_ROWS + 3;                               // [n_bins+1]
-    constexpr int NF = RECORD ? F_COUNT : F_COUNT - 1;
-    constexpr int FSTRIDE = K * 32;                                    // words per field per warp
-    uint32_t *s_slots = reinterpret_cast<uint32_t *>(s_cdf + ((sc.n_bins + 1 + 3) & ~3)) +
-                        (threadIdx.x >> 5) * (NF * FSTRIDE);
+    constexpr int NG = mc_slot_groups(RECORD);
+    constexpr int GSTRIDE = K * 32;                                    // uint4 per group per warp
+    uint4 *s_slots = reinterpret_cast<uint4 *>(s_cdf + ((sc.n_bins + 1 + 3) & ~3)) + (threadIdx.x >> 5) * (NG * GSTRIDE);
     for (int i = threadIdx.x; i < sc.n_mat * TAB_ROWS; i += MC_THREADS) s_tab[i] = sc.tab[i];
     for (int i = threadIdx.x; i < TAB_ROWS; i += MC_THREADS) s_inv[i] = sc.inv_mumax[i];
     for (int i = threadIdx.x; i <= sc.n_bins && sc.n_bins > 0; i += MC_THREADS) s_cdf[i] = sc.cdf[i];
@@ -426,12 +430,13 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
     const float vox_off[3] = {-sc.org[0] * sc.inv_pitch - 0.5f, -sc.org[1] * sc.inv_pitch - 0.5f, -sc.org[2] * sc.inv_pitch - 0.5f};
     constexpr uint32_t ALL = (K == 6) ? 0x111111u : (K == 5) ? 0x11111u : (K == 4) ? 0x1111u : (K == 3) ? 0x0111u : (K == 2) ? 0x0011u : 0x0001u;
 
-#define SLOT_F(f) (*reinterpret_cast<float *>(slot + (f) * FSTRIDE))
-#define SLOT_U(f) (slot[(f) * FSTRIDE])
+#define GRP(g) (slot[(g) * GSTRIDE])
+#define WORD(g, w) (reinterpret_cast<uint32_t *>(slot + (g) * GSTRIDE)[w])
+#define WORDF(g, w) (reinterpret_cast<float *>(slot + (g) * GSTRIDE)[w])
 
     uint32_t st = ALL * P_REFILL;                                      // one-hot phase per slot
 #pragma unroll
-    for (int j = 0; j < K; j++) s_slots[F_META * FSTRIDE + j * 32 + lane] = 0u;   // no pending detection in an empty slot
+    for (int j = 0; j < K; j++) s_slots[G_ID * GSTRIDE + j * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);   // no pending detection
     uint32_t cur_pv = 0xffffffffu, prim_cnt = 0;
     uint32_t c_hist = 0, c_prim = 0, c_scat = 0, c_abs = 0, c_int = 0, c_coh = 0, c_comp = 0, c_steps = 0;
     unsigned long long e_prim = 0, e_scat = 0;                         // fixed point, 1/1024 keV
@@ -461,50 +466,50 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
         const uint32_t mine = st & (ALL * phase);
         const bool active = mine != 0u;
         const int j = active ? ((__ffs(mine) - 1) >> 2) : 0;            // my slot in that phase
-        uint32_t *slot = s_slots + j * 32 + lane;
+        uint4 *slot = s_slots + j * 32 + lane;
         const uint32_t clr = ~(0xFu << (4 * j));
 
         if (phase == P_STEP) {
             if (!active) continue;
             // ---------------- one Woodcock step, CBCT_real325im.cu:886-968 ---------------
-            float x = SLOT_F(F_X), y = SLOT_F(F_Y), z = SLOT_F(F_Z);
-            const float dx = SLOT_F(F_DX), dy = SLOT_F(F_DY), dz = SLOT_F(F_DZ);
-            const uint32_t c0 = SLOT_U(F_C0), meta = SLOT_U(F_META), ctr = SLOT_U(F_CTR);
+            const uint4 id = GRP(G_ID);
+            float4 pos = *reinterpret_cast<float4 *>(&GRP(G_POS));
+            const float4 dir = *reinterpret_cast<float4 *>(&GRP(G_DIR));
+            const uint32_t c0 = id.x, meta = id.y, ctr = id.z;
             const int kE = meta & 0xFF;
             const uint2 r = philox2x32_10(c0, (meta & 0xFF000000u) | (STREAM_FLIGHT << 22) | (ctr & 0xFFFFFu), P.key);
-            SLOT_U(F_CTR) = (ctr & 0xFFF00000u) | ((ctr + 1u) & 0xFFFFFu);
+            WORD(G_ID, 2) = (ctr & 0xFFF00000u) | ((ctr + 1u) & 0xFFFFFu);
             const float s = -__logf(u01(r.x)) * s_inv[kE];
-            x = fmaf(s, dx, x); y = fmaf(s, dy, y); z = fmaf(s, dz, z);
-            SLOT_F(F_X) = x; SLOT_F(F_Y) = y; SLOT_F(F_Z) = z;
+            pos.x = fmaf(s, dir.x, pos.x); pos.y = fmaf(s, dir.y, pos.y); pos.z = fmaf(s, dir.z, pos.z);
+            *reinterpret_cast<float4 *>(&GRP(G_POS)) = pos;
             c_steps++;
-            const bool inside = x >= sc.clip_lo[0] && x < sc.clip_hi[0] && y >= sc.clip_lo[1] && y < sc.clip_hi[1] &&
-                                z >= sc.clip_lo[2] && z < sc.clip_hi[2];
+            const bool inside = pos.x >= sc.clip_lo[0] && pos.x < sc.clip_hi[0] && pos.y >= sc.clip_lo[1] && pos.y < sc.clip_hi[1] &&
+                                pos.z >= sc.clip_lo[2] && pos.z < sc.clip_hi[2];
             if (!inside) {                       // left the volume: only air ahead
                 if ((meta & 0xF00u) == 0u) {     // unscattered: lands in the pixel it was aimed at (:567-590)
-                    const uint32_t pvw = SLOT_U(F_PIXVIEW);
+                    const uint32_t pvw = id.w;
                     const uint32_t pva = (pvw >> 20) * npix + (pvw & 0xFFFFFu);
                     if (pva != cur_pv) {
                         if (prim_cnt) { atomicAdd(P.image0 + cur_pv, (int)prim_cnt); atomicAdd(P.image5 + cur_pv, (int)prim_cnt); }
                         cur_pv = pva; prim_cnt = 0;
                     }
                     prim_cnt++; c_prim++;
-                    const float E = SLOT_F(F_E);
-                    e_prim += (unsigned long long)(E * 1024.f + 0.5f);
-                    if (RECORD) { P.fates[SLOT_U(F_REC)] = 1u | ((pvw & 0xFFFFFu) << 8); P.fate_e[SLOT_U(F_REC)] = E; }
-                } else SLOT_U(F_META) = meta | 0x8000u;     // scatter detection runs with the refill phase
+                    e_prim += (unsigned long long)(pos.w * 1024.f + 0.5f);
+                    if (RECORD) { P.fates[WORD(G_REC, 0)] = 1u | ((pvw & 0xFFFFFu) << 8); P.fate_e[WORD(G_REC, 0)] = pos.w; }
+                } else WORD(G_ID, 1) = meta | 0x8000u;     // scatter detection runs with the refill phase
                 st = (st & clr) | (P_REFILL << (4 * j));
                 continue;
             }
-            int ix = __float_as_int(fmaf(x, sc.inv_pitch, vox_off[0]) + 12582912.0f) - 0x4B400000;
-            int iy = __float_as_int(fmaf(y, sc.inv_pitch, vox_off[1]) + 12582912.0f) - 0x4B400000;
-            int iz = __float_as_int(fmaf(z, sc.inv_pitch, vox_off[2]) + 12582912.0f) - 0x4B400000;
+            int ix = __float_as_int(fmaf(pos.x, sc.inv_pitch, vox_off[0]) + 12582912.0f) - 0x4B400000;
+            int iy = __float_as_int(fmaf(pos.y, sc.inv_pitch, vox_off[1]) + 12582912.0f) - 0x4B400000;
+            int iz = __float_as_int(fmaf(pos.z, sc.inv_pitch, vox_off[2]) + 12582912.0f) - 0x4B400000;
             ix = (int)min((unsigned)ix, (unsigned)(sc.nx - 1)); iy = (int)min((unsigned)iy, (unsigned)(sc.ny - 1));
             iz = (int)min((unsigned)iz, (unsigned)(sc.nz - 1));     // safety only: the clip box lies inside the volume
-            const int lab = __ldg(sc.labels + ((size_t)iz * sc.ny + iy) * sc.nx + ix);
+            const int lab = __ldg(sc.labels + ((unsigned)(iz * sc.ny + iy) * (unsigned)sc.nx + (unsigned)ix));
             if (lab == 0) continue;                                   // air: virtual collision
             const int mat = min(lab, sc.n_mat) - 1;
             if (u01(r.y) > s_tab[mat * TAB_ROWS + kE].x) continue;    // virtual collision, :941-961
-            SLOT_U(F_META) = (meta & ~0x7000u) | ((uint32_t)mat << 12);
+            WORD(G_ID, 1) = (meta & ~0x7000u) | ((uint32_t)mat << 12);
             st = (st & clr) | (P_COLLIDE << (4 * j));
             continue;
         }
@@ -512,50 +517,50 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
         if (phase == P_COLLIDE) {
             if (!active) continue;
             // ---------------- real collision, CBCT_real325im.cu:599-656 ----------------------
-            uint32_t meta = SLOT_U(F_META);
+            uint4 id = GRP(G_ID);
+            const float4 pos = *reinterpret_cast<float4 *>(&GRP(G_POS));
+            uint32_t meta = id.y;
             const int nint = (meta >> 8) & 0xF, kE = meta & 0xFF, mat = (meta >> 12) & 0x7;
             if (nint >= sc.max_scatter) {                             // scatter budget used up
-                if (RECORD) { P.fates[SLOT_U(F_REC)] = 5u | ((uint32_t)nint << 28); P.fate_e[SLOT_U(F_REC)] = SLOT_F(F_E); }
+                if (RECORD) { P.fates[WORD(G_REC, 0)] = 5u | ((uint32_t)nint << 28); P.fate_e[WORD(G_REC, 0)] = pos.w; }
                 st = (st & clr) | (P_REFILL << (4 * j));
                 continue;
             }
             {
-                const float x = SLOT_F(F_X), y = SLOT_F(F_Y), z = SLOT_F(F_Z);
-                const float2 cs = __ldg(sc.view_cs + (SLOT_U(F_PIXVIEW) >> 20));
-                const float xr = x * cs.x + y * cs.y, yr = -x * cs.y + y * cs.x;
-                if (xr >= sc.dod || fabsf(yr) >= sc.half || fabsf(z) >= sc.half) {        // :613-619
-                    if (RECORD) { P.fates[SLOT_U(F_REC)] = 4u | ((uint32_t)nint << 28); P.fate_e[SLOT_U(F_REC)] = SLOT_F(F_E); }
+                const float2 cs = __ldg(sc.view_cs + (id.w >> 20));
+                const float xr = pos.x * cs.x + pos.y * cs.y, yr = -pos.x * cs.y + pos.y * cs.x;
+                if (xr >= sc.dod || fabsf(yr) >= sc.half || fabsf(pos.z) >= sc.half) {        // :613-619
+                    if (RECORD) { P.fates[WORD(G_REC, 0)] = 4u | ((uint32_t)nint << 28); P.fate_e[WORD(G_REC, 0)] = pos.w; }
                     st = (st & clr) | (P_REFILL << (4 * j));
                     continue;
                 }
             }
             meta += 0x100u;                                           // nint++
             c_int++;
-            const uint32_t ctr = SLOT_U(F_CTR);
-            const uint2 re = philox2x32_10(SLOT_U(F_C0), (meta & 0xFF000000u) | (STREAM_EVENT << 22) | (ctr >> 20), P.key);
-            SLOT_U(F_CTR) = ctr + 0x100000u;
-            SLOT_U(F_META) = meta;
+            const uint2 re = philox2x32_10(id.x, (meta & 0xFF000000u) | (STREAM_EVENT << 22) | (id.z >> 20), P.key);
+            id.y = meta; id.z += 0x100000u;
+            GRP(G_ID) = id;
             const float u_sel = u01(re.x);
             const float4 tb = s_tab[mat * TAB_ROWS + kE];
             if (u_sel <= tb.y) {                                      // photoelectric, :651-655
                 c_abs++;
-                if (RECORD) { P.fates[SLOT_U(F_REC)] = 3u | ((uint32_t)(nint + 1) << 28); P.fate_e[SLOT_U(F_REC)] = SLOT_F(F_E); }
+                if (RECORD) { P.fates[WORD(G_REC, 0)] = 3u | ((uint32_t)(nint + 1) << 28); P.fate_e[WORD(G_REC, 0)] = pos.w; }
                 st = (st & clr) | (P_REFILL << (4 * j));
             } else if (u_sel <= tb.z) { c_coh++; st = (st & clr) | (P_STEP << (4 * j)); }    // coherent: no deflection
-            else { c_comp++; SLOT_F(F_UPHI) = u01(re.y); st = (st & clr) | (P_COMPTON << (4 * j)); }
+            else { c_comp++; WORDF(G_DIR, 3) = u01(re.y); st = (st & clr) | (P_COMPTON << (4 * j)); }
             continue;
         }
 
         if (phase == P_COMPTON) {
             if (!active) continue;
             // ---------------- one round of Kahn's method, :701-736 -----------------------------
-            const float E0 = SLOT_F(F_E);
-            const uint32_t meta = SLOT_U(F_META), ctr = SLOT_U(F_CTR), c0 = SLOT_U(F_C0);
+            uint4 id = GRP(G_ID);
+            const float E0 = WORDF(G_POS, 3);
             const float lam = __fdividef(511.0f, E0);
-            const uint32_t ne = ctr >> 20;
-            const uint2 ra = philox2x32_10(c0, (meta & 0xFF000000u) | (STREAM_EVENT << 22) | ne, P.key);
-            const uint2 rb = philox2x32_10(c0, (meta & 0xFF000000u) | (STREAM_EVENT << 22) | ((ne + 1u) & 0xFFFu), P.key);
-            SLOT_U(F_CTR) = ctr + 0x200000u;
+            const uint32_t ne = id.z >> 20;
+            const uint2 ra = philox2x32_10(id.x, (id.y & 0xFF000000u) | (STREAM_EVENT << 22) | ne, P.key);
+            const uint2 rb = philox2x32_10(id.x, (id.y & 0xFF000000u) | (STREAM_EVENT << 22) | ((ne + 1u) & 0xFFFu), P.key);
+            id.z += 0x200000u;
             const float r1 = u01(ra.x), r2 = u01(ra.y), r3 = u01(rb.x);
             const bool br1 = r1 * (9.0f * lam + 2.0f) < (lam + 2.0f);
             const float ro1 = 1.0f + __fdividef(2.0f, lam) * r2;
@@ -564,18 +569,20 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             const float iro = __fdividef(1.0f, ro);
             const float t = lam - ro * lam + 1.0f;
             const float lim = br1 ? 4.0f * (iro - iro * iro) : 0.5f * (t * t + iro);
-            if (!(r3 <= lim)) continue;                               // rejected: next round next time
+            if (!(r3 <= lim)) { WORD(G_ID, 2) = id.z; continue; }     // rejected: next round next time
             const float lam_d = ro * lam;
             float cos_t = 1.0f - (lam_d - lam);
             cos_t = fmaxf(cos_t, -1.0f);                              // :746-747
             const float sin_t = sqrtf(fmaxf(0.f, 1.0f - cos_t * cos_t));
             const float E = __fdividef(511.0f, lam_d);
             const int kE = min(max((int)(E + 0.5f), 0), TAB_ROWS - 1);
-            SLOT_F(F_E) = E;
-            SLOT_U(F_META) = (meta & ~0xFFu) | (uint32_t)kE;
+            WORDF(G_POS, 3) = E;
+            id.y = (id.y & ~0xFFu) | (uint32_t)kE;
+            GRP(G_ID) = id;
+            float4 dir = *reinterpret_cast<float4 *>(&GRP(G_DIR));
             float sphi, cphi;
-            __sincosf(6.2831853071795865f * SLOT_F(F_UPHI), &sphi, &cphi);   // phi = 2 pi u, :764 (MUFU, |err| ~1e-6)
-            const float dx = SLOT_F(F_DX), dy = SLOT_F(F_DY), dz = SLOT_F(F_DZ);
+            __sincosf(6.2831853071795865f * dir.w, &sphi, &cphi);     // phi = 2 pi u, :764 (MUFU, |err| ~1e-6)
+            const float dx = dir.x, dy = dir.y, dz = dir.z;
             // direction update, :768-780, as a rotation of the unit vector (see v2 for the algebra)
             const float st2 = dx * dx + dy * dy;
             float e1x, e1y, e1z, e2x, e2y;
@@ -589,7 +596,8 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             const float nyd = cos_t * dy + a * e1y + b * e2y;
             const float nzd = cos_t * dz + a * e1z;
             const float nn = rsqrtf(nxd * nxd + nyd * nyd + nzd * nzd);
-            SLOT_F(F_DX) = nxd * nn; SLOT_F(F_DY) = nyd * nn; SLOT_F(F_DZ) = nzd * nn;
+            dir.x = nxd * nn; dir.y = nyd * nn; dir.z = nzd * nn;
+            *reinterpret_cast<float4 *>(&GRP(G_DIR)) = dir;
             st = (st & clr) | (P_STEP << (4 * j));
             continue;
         }
@@ -615,32 +623,32 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
         next_off = min(next_off + (uint32_t)__popc(m_ref), unit_cnt);
         if (!active) continue;
         {
-            const uint32_t meta = SLOT_U(F_META);
-            if (meta & 0x8000u) {                        // scatter detection, CBCT_real325im.cu:823-843
-                SLOT_U(F_META) = meta & ~0x8000u;
-                const int nint = (meta >> 8) & 0xF;
+            const uint4 id = GRP(G_ID);
+            if (id.y & 0x8000u) {                        // scatter detection, CBCT_real325im.cu:823-843
+                WORD(G_ID, 1) = id.y & ~0x8000u;
+                const int nint = (id.y >> 8) & 0xF;
                 uint32_t fate = 4u | ((uint32_t)nint << 28);
-                const float x = SLOT_F(F_X), y = SLOT_F(F_Y), z = SLOT_F(F_Z);
-                const float dx = SLOT_F(F_DX), dy = SLOT_F(F_DY), dz = SLOT_F(F_DZ), E = SLOT_F(F_E);
-                const int view = (int)(SLOT_U(F_PIXVIEW) >> 20);
+                const float4 pos = *reinterpret_cast<float4 *>(&GRP(G_POS));
+                const float4 dir = *reinterpret_cast<float4 *>(&GRP(G_DIR));
+                const int view = (int)(id.w >> 20);
                 const float2 cs = __ldg(sc.view_cs + view);
-                const float xr = x * cs.x + y * cs.y, yr = -x * cs.y + y * cs.x;      // rotate by -beta
-                const float dxr = dx * cs.x + dy * cs.y, dyr = -dx * cs.y + dy * cs.x;
+                const float xr = pos.x * cs.x + pos.y * cs.y, yr = -pos.x * cs.y + pos.y * cs.x;      // rotate by -beta
+                const float dxr = dir.x * cs.x + dir.y * cs.y, dyr = -dir.x * cs.y + dir.y * cs.x;
                 if (dxr > 0.f) {
                     const float t = (sc.dod - xr) / dxr;
-                    const float yd = fmaf(t, dyr, yr), zd = fmaf(t, dz, z);
+                    const float yd = fmaf(t, dyr, yr), zd = fmaf(t, dir.z, pos.z);
                     if (fabsf(yd) <= sc.half && fabsf(zd) <= sc.half && fmaf(1000.f, dxr, xr) >= sc.dod) {
                         const int by = (int)((sc.half - yd) * sc.inv_pixel), bx = (int)((sc.half - zd) * sc.inv_pixel);
                         if (by >= 0 && by < sc.det_ny && bx >= 0 && bx < sc.det_nx) {
                             const uint32_t bin = (uint32_t)(by * sc.det_nx + bx);
                             atomicAdd(P.image5 + (size_t)view * npix + bin, 1);
                             c_scat++;
-                            e_scat += (unsigned long long)(E * 1024.f + 0.5f);
+                            e_scat += (unsigned long long)(pos.w * 1024.f + 0.5f);
                             fate = 2u | (bin << 8) | ((uint32_t)nint << 28);
                         }
                     }
                 }
-                if (RECORD) { P.fates[SLOT_U(F_REC)] = fate; P.fate_e[SLOT_U(F_REC)] = E; }
+                if (RECORD) { P.fates[WORD(G_REC, 0)] = fate; P.fate_e[WORD(G_REC, 0)] = pos.w; }
             }
         }
         if (my_off >= unit_cnt) {                        // no history left in this unit for me
@@ -660,7 +668,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             const uint32_t c0 = (uint32_t)hid;
             const uint32_t c1hi = ((uint32_t)(hid >> 32) & 0xFFu) << 24;
             uint32_t rec_idx = 0;
-            if (RECORD) { rec_idx = pix * P.per + n; SLOT_U(F_COUNT - 1) = rec_idx; }
+            if (RECORD) { rec_idx = pix * P.per + n; WORD(G_REC, 0) = rec_idx; }
             c_hist++;
             // ---- source, CBCT_real325im.cu:464-540 (exact aim at the pixel) ----
             const uint32_t pi = pix / (uint32_t)sc.det_nx, pj = pix - pi * (uint32_t)sc.det_nx;
@@ -693,7 +701,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
                     if (d3[a] != 0.f) {
-                        const float inv = 1.0f / d3[a];
+                        const float inv = __fdividef(1.0f, d3[a]);
                         float ta = (sc.clip_lo[a] - o3[a]) * inv, tb = (sc.clip_hi[a] - o3[a]) * inv;
                         if (ta > tb) { const float t = ta; ta = tb; tb = t; }
                         t0 = fmaxf(t0, ta); t1 = fminf(t1, tb);
@@ -710,19 +718,17 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 if (RECORD) { P.fates[rec_idx] = 1u | (pix << 8); P.fate_e[rec_idx] = E; }
                 // the slot stays in REFILL and takes another history on the next visit
             } else {
-                SLOT_F(F_X) = fmaf(t0, dx, sx); SLOT_F(F_Y) = fmaf(t0, dy, sy); SLOT_F(F_Z) = t0 * dz;
-                SLOT_F(F_DX) = dx; SLOT_F(F_DY) = dy; SLOT_F(F_DZ) = dz;
-                SLOT_F(F_E) = E; SLOT_U(F_C0) = c0;
-                SLOT_U(F_META) = c1hi | (uint32_t)kE;
-                SLOT_U(F_CTR) = 0u;
-                SLOT_U(F_PIXVIEW) = ((uint32_t)view << 20) | pix;
+                *reinterpret_cast<float4 *>(&GRP(G_POS)) = make_float4(fmaf(t0, dx, sx), fmaf(t0, dy, sy), t0 * dz, E);
+                *reinterpret_cast<float4 *>(&GRP(G_DIR)) = make_float4(dx, dy, dz, 0.f);
+                GRP(G_ID) = make_uint4(c0, c1hi | (uint32_t)kE, 0u, ((uint32_t)view << 20) | pix);
                 st = (st & clr) | (P_STEP << (4 * j));
             }
         }
       }   // pass
     }
-#undef SLOT_F
-#undef SLOT_U
+#undef GRP
+#undef WORD
+#undef WORDF
     if (prim_cnt) { atomicAdd(P.image0 + cur_pv, (int)prim_cnt); atomicAdd(P.image5 + cur_pv, (int)prim_cnt); }
     if (P.stats) {
         const uint32_t v[8] = {c_hist, c_prim, c_scat, c_abs, c_int, c_coh, c_comp, c_steps};
@@ -777,6 +783,7 @@ static int check_mc(const monte_mc_geom *g, const monte_mc_volume *vol, const mo
     MONTE_ARG((size_t)g->ny * g->nx < (1u << 20), "mc: detector has more than 2^20 pixels");
     MONTE_ARG(g->max_scatter >= 0 && g->max_scatter <= 15, "mc: max_scatter must be 0..15");
     MONTE_ARG(vol->nx > 0 && vol->ny > 0 && vol->nz > 0 && vol->pitch > 0, "mc: bad volume");
+    MONTE_ARG((uint64_t)vol->nx * vol->ny * vol->nz < (1ull << 32), "mc: label volume has 2^32 voxels or more");
     MONTE_ARG(xs->n_materials >= 1 && xs->n_materials <= MONTE_MC_MAX_MATERIALS, "mc: n_materials must be 1..%d", MONTE_MC_MAX_MATERIALS);
     const int dims[3] = {vol->nx, vol->ny, vol->nz};
     for (int a = 0; a < 3; a++) {
@@ -922,7 +929,7 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     MONTE_ARG(s->geom.n_views < 4096, "mc: more than 4095 views");
     const int rec = d_fates ? 1 : 0;
     const int K = which >= 31 && which <= 36 ? which - 30 : (which == 44 ? 4 : (which == 43 ? 3 : 0));
-    const size_t slot_bytes = (size_t)K * 32 * (rec ? F_COUNT : F_COUNT - 1) * sizeof(uint32_t) * (MC_THREADS / 32);
+    const size_t slot_bytes = (size_t)K * 32 * mc_slot_groups(rec != 0) * sizeof(uint4) * (MC_THREADS / 32);
     const size_t smem = K ? (size_t)s->dev.n_mat * TAB_ROWS * sizeof(float4) +
                                 (TAB_ROWS + 3 + ((s->dev.n_bins + 1 + 3) & ~3)) * sizeof(float) + slot_bytes
                           : s->smem;
