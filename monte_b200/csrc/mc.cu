@@ -441,8 +441,9 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
     uint32_t c_hist = 0, c_prim = 0, c_scat = 0, c_abs = 0, c_int = 0, c_coh = 0, c_comp = 0, c_steps = 0;
     unsigned long long e_prim = 0, e_scat = 0;                         // fixed point, 1/1024 keV
     // current unit (warp-uniform)
-    uint32_t unit_cnt = 0, next_off = 0, n0 = 0, v0 = 0, p0 = 0;
+    uint32_t unit_cnt = 0, next_off = 0, n0 = 0, v0 = 0, p0 = 0, pi0 = 0, pj0 = 0;
     bool grid_done = false;
+    const bool few_pixels_per_unit = P.cnt >= (uint32_t)MC_UNIT / 4u;  // a unit then spans at most six pixels
 
     for (;;) {
         // ---------------- vote: the phase in which most lanes have a slot waiting ---------------
@@ -615,6 +616,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 const uint32_t pv0 = (uint32_t)(base / P.cnt);
                 n0 = (uint32_t)(base - (unsigned long long)pv0 * P.cnt);
                 v0 = pv0 / npix; p0 = pv0 - v0 * npix;
+                pi0 = p0 / (uint32_t)sc.det_nx; pj0 = p0 - pi0 * (uint32_t)sc.det_nx;
                 next_off = 0;
             }
         }
@@ -635,7 +637,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 const float xr = pos.x * cs.x + pos.y * cs.y, yr = -pos.x * cs.y + pos.y * cs.x;      // rotate by -beta
                 const float dxr = dir.x * cs.x + dir.y * cs.y, dyr = -dir.x * cs.y + dir.y * cs.x;
                 if (dxr > 0.f) {
-                    const float t = (sc.dod - xr) / dxr;
+                    const float t = __fdividef(sc.dod - xr, dxr);
                     const float yd = fmaf(t, dyr, yr), zd = fmaf(t, dir.z, pos.z);
                     if (fabsf(yd) <= sc.half && fabsf(zd) <= sc.half && fmaf(1000.f, dxr, xr) >= sc.dod) {
                         const int by = (int)((sc.half - yd) * sc.inv_pixel), bx = (int)((sc.half - zd) * sc.inv_pixel);
@@ -656,11 +658,15 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             continue;                                    // else: stays REFILL, the next visit opens a new unit
         }
         {
-            uint32_t n = n0 + my_off;
-            const uint32_t dpv = n / P.cnt;
-            n -= dpv * P.cnt;
-            uint32_t pix = p0 + dpv, vrel = v0;
-            if (pix >= npix) { const uint32_t q = pix / npix; vrel += q; pix -= q * npix; }
+            // history index -> (pixel, photon): divisions only in the rare general case
+            uint32_t n = n0 + my_off, dpv;
+            if (few_pixels_per_unit) { dpv = 0u; while (n >= P.cnt) { n -= P.cnt; dpv++; } }
+            else { dpv = n / P.cnt; n -= dpv * P.cnt; }
+            uint32_t pix = p0 + dpv, vrel = v0, pi = pi0, pj = pj0 + dpv;
+            if (pix >= npix || pj >= (uint32_t)sc.det_nx) {
+                if (pix >= npix) { const uint32_t q = pix / npix; vrel += q; pix -= q * npix; }
+                pi = pix / (uint32_t)sc.det_nx; pj = pix - pi * (uint32_t)sc.det_nx;
+            }
             const int view = P.view_begin + (int)vrel;
             const uint32_t pva = (uint32_t)view * npix + pix;
             n += P.n_begin;
@@ -671,7 +677,6 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             if (RECORD) { rec_idx = pix * P.per + n; WORD(G_REC, 0) = rec_idx; }
             c_hist++;
             // ---- source, CBCT_real325im.cu:464-540 (exact aim at the pixel) ----
-            const uint32_t pi = pix / (uint32_t)sc.det_nx, pj = pix - pi * (uint32_t)sc.det_nx;
             float uy = 0.5f, uz = 0.5f;
             if (sc.source_mode == MONTE_MC_SOURCE_CONE) {
                 const uint2 r = philox2x32_10(c0, c1hi | (STREAM_SOURCE << 22), P.key);
@@ -695,17 +700,16 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             const float dy = dxr * cs.y + dyr * cs.x;
             const float dz = zl * rn;
             const float sx = -sc.dso * cs.x, sy = -sc.dso * cs.y;
-            float t0 = 0.f, t1 = 1e30f;                       // analytic flight to the clip box (slab method)
+            // analytic flight to the clip box: branch-free slab method (a zero direction component gives
+            // +-inf bounds, which fminf/fmaxf handle; CUDA's fminf/fmaxf drop a NaN operand)
+            float t0 = 0.f, t1 = 1e30f;
             {
                 const float o3[3] = {sx, sy, 0.f}, d3[3] = {dx, dy, dz};
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
-                    if (d3[a] != 0.f) {
-                        const float inv = __fdividef(1.0f, d3[a]);
-                        float ta = (sc.clip_lo[a] - o3[a]) * inv, tb = (sc.clip_hi[a] - o3[a]) * inv;
-                        if (ta > tb) { const float t = ta; ta = tb; tb = t; }
-                        t0 = fmaxf(t0, ta); t1 = fminf(t1, tb);
-                    } else if (o3[a] < sc.clip_lo[a] || o3[a] >= sc.clip_hi[a]) t1 = -1.f;
+                    const float inv = __fdividef(1.0f, d3[a]);
+                    const float ta = (sc.clip_lo[a] - o3[a]) * inv, tb = (sc.clip_hi[a] - o3[a]) * inv;
+                    t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
                 }
             }
             if (t0 >= t1) {                                   // misses the phantom: unscattered
