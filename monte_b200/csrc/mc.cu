@@ -221,9 +221,9 @@ mc_transport_kernel(const __grid_constant__ McLaunch P) {
                 // ---------------- one round of Kahn's method, :701-736 -----------------------------
                 const float lam = __fdividef(511.0f, E);
                 const uint2 ra = philox2x32_10(c0, c1hi | (STREAM_EVENT << 22) | (n_ev & 0x3FFFFFu), P.key);
-                const uint2 rb = philox2x32_10(c0, c1hi | (STREAM_EVENT << 22) | ((n_ev + 1) & 0x3FFFFFu), P.key);
-                n_ev += 2;
-                const float r1 = u01(ra.x), r2 = u01(ra.y), r3 = u01(rb.x);
+                n_ev += 1;
+                const float r2 = u01(ra.x), r3 = u01(ra.y);
+                const float r1 = ((float)(((ra.x & 0x1FFu) << 9) | (ra.y & 0x1FFu)) + 0.5f) * (1.0f / 262144.0f);
                 // both branches evaluated branch-free (the lanes of a Kahn round split ~1:5 between them)
                 const bool br1 = r1 * (9.0f * lam + 2.0f) < (lam + 2.0f);
                 const float ro1 = 1.0f + __fdividef(2.0f, lam) * r2;
@@ -559,10 +559,12 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             const float E0 = WORDF(G_POS, 3);
             const float lam = __fdividef(511.0f, E0);
             const uint32_t ne = id.z >> 20;
+            // one Philox block per round: r2, r3 from the high 23 bits of the two words, r1 (which only
+            // picks the branch) from their 2 x 9 low bits -- disjoint bits, hence independent variates
             const uint2 ra = philox2x32_10(id.x, (id.y & 0xFF000000u) | (STREAM_EVENT << 22) | ne, P.key);
-            const uint2 rb = philox2x32_10(id.x, (id.y & 0xFF000000u) | (STREAM_EVENT << 22) | ((ne + 1u) & 0xFFFu), P.key);
-            id.z += 0x200000u;
-            const float r1 = u01(ra.x), r2 = u01(ra.y), r3 = u01(rb.x);
+            id.z += 0x100000u;
+            const float r2 = u01(ra.x), r3 = u01(ra.y);
+            const float r1 = ((float)(((ra.x & 0x1FFu) << 9) | (ra.y & 0x1FFu)) + 0.5f) * (1.0f / 262144.0f);
             const bool br1 = r1 * (9.0f * lam + 2.0f) < (lam + 2.0f);
             const float ro1 = 1.0f + __fdividef(2.0f, lam) * r2;
             const float ro2 = __fdividef(lam + 2.0f, lam + 2.0f * (1.0f - r2));

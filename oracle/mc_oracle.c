@@ -437,7 +437,13 @@ static void history(const scene_t *S, rng_t *R, int view, int i, int j, uint64_t
                 for (;;) {                                   /* Kahn, CBCT_real2.cpp:410-434 */
                     double r1, r2, r3, unused;
                     if (R->mode == ORACLE_RNG_MT) { r1 = mt_real3(R->mt); r2 = mt_real3(R->mt); r3 = mt_real3(R->mt); }
-                    else { rng_pair(R, STREAM_EVENT, R->n_event++, &r1, &r2); rng_pair(R, STREAM_EVENT, R->n_event++, &r3, &unused); }
+                    else {   /* one Philox block per round: r2, r3 = high 23 bits of the two words, r1 = their 2 x 9 low bits */
+                        uint32_t o2[2];
+                        philox2x32(R->c0, R->c1hi | (STREAM_EVENT << 22) | (R->n_event++ & 0x3FFFFFu), R->key, o2);
+                        r2 = u01_23(o2[0]); r3 = u01_23(o2[1]);
+                        r1 = ((double)(((o2[0] & 0x1FFu) << 9) | (o2[1] & 0x1FFu)) + 0.5) * (1.0 / 262144.0);
+                        unused = 0; (void)unused;
+                    }
                     kahn_round++;
                     if (r1 < (lambda + 2.0) / (9.0 * lambda + 2.0)) {
                         double ro = 1.0 + (2.0 / lambda) * r2;
