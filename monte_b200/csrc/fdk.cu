@@ -338,6 +338,8 @@ fdk_backproject_kernel(const __grid_constant__ BpParams p) {
         // w is linear in the slice index: if both ends of the column are safely inside the detector
         // every slice is, and the per-slice edge tests and clamps can be dropped altogether
         const float w_last = fmaf(-kv, (float)(ZT - 1), w0v);
+        // whole column above or below the detector for this view (bp3d20.cpp:116 skips every slice)
+        if (w0v * w_last > 0.f && fminf(fabsf(w0v), fabsf(w_last)) > p.half_v + p.eps_v) continue;
         if (u_ok && fmaxf(fabsf(w0v), fabsf(w_last)) <= hv_in) {
 #pragma unroll
             for (int h = 0; h < ZT; h += ZB) {
