@@ -28,7 +28,9 @@ def make_xs(materials=("h2o", "ca"), quirk_bom=False):
     """monte_mc_xs with water (label 1, rho 1.0) and calcium (label 2, rho 1.55)
     (CBCT_real325im.cu:115-117)."""
     h2o, ca = load_tables(quirk_bom)
-    tabs = {"h2o": (h2o, 1.0), "ca": (ca, 1.55)}
+    # "pmma": the reference's third material (CBCT_real325im.cu:117, density 1.18); its PMMA.txt is not in
+    # the repository, so the water table stands in for the mass coefficients
+    tabs = {"h2o": (h2o, 1.0), "ca": (ca, 1.55), "pmma": (h2o, 1.18)}
     xs = McXs()
     xs.n_materials = len(materials)
     for m, name in enumerate(materials):

@@ -251,3 +251,33 @@ def test_c4_polyenergetic_cone_statistical_parity(monte, oracle):
     assert abs(ep_g - ep_c) < 5 * 25.0 / math.sqrt(res["primaries"]), (ep_g, ep_c)
     assert abs(es_g - es_c) < 5 * 25.0 / math.sqrt(res["scatter_detected"]), (es_g, es_c)
     assert 40.0 < ep_c < 90.0
+
+
+def test_three_materials_im_variant_coupled(monte, oracle):
+    """CBCT_real325im.cu semantics: labels 1 = H2O, 2 = Ca, anything else = the last material (PMMA,
+    :640-646); a PMMA cylinder with a water core and calcium inserts, history-coupled with the oracle"""
+    n, pitch = 41, 0.5
+    c = (np.arange(n) + 0.5) * pitch - 0.5 * n * pitch
+    x, y, z = c[None, None, :], c[None, :, None], c[:, None, None]
+    lab = np.zeros((n, n, n), np.uint8)
+    body = (x * x + y * y <= 81.0) & (np.abs(z) <= 9.0)           # r = 9 cylinder along z (:904)
+    lab[np.broadcast_to(body, lab.shape)] = 3                      # PMMA
+    lab[np.broadcast_to(body & (x * x + y * y <= 9.0), lab.shape)] = 1
+    lab[np.broadcast_to(body & ((x - 5) ** 2 + y * y <= 2.25), lab.shape)] = 2
+    lab[np.broadcast_to(body & ((x + 5) ** 2 + y * y <= 2.25), lab.shape)] = 7     # unknown label -> last material
+    g = scenes.mc_geom(21, 32.5 / 21, n_views=2)
+    g.angle_step_deg = 90.0
+    vol = scenes.volume_for(lab, pitch)
+    xs = scenes.make_xs(("h2o", "ca", "pmma"))
+    per, seed = 30, 12
+    sc = monte.Scene(g, vol, lab, xs, scenes.mono_spectrum(140.0))
+    f_gpu, _ = sc.fates(0, per, seed)
+    sc.close()
+    _, _, res, f_cpu, _ = oracle.mc_run(g, vol, lab, oracle.tables_from_xs(xs), scenes.mono_spectrum(140.0),
+                                        oracle.mc_opts(oracle.RNG_PHILOX, seed=seed), per, views=(0, 1), want_fates=True)
+    assert (f_gpu == f_cpu).mean() > 0.997
+    im0, im5, st = monte.simulate(g, vol, lab, xs, scenes.mono_spectrum(140.0), per, seed)
+    o0, o5, res, _, _ = oracle.mc_run(g, vol, lab, oracle.tables_from_xs(xs), scenes.mono_spectrum(140.0),
+                                      oracle.mc_opts(oracle.RNG_PHILOX, seed=seed), per)
+    assert np.abs(im5.astype(int) - o5).sum() <= 0.004 * st["histories"]
+    assert abs(st["compton"] - res["compton"]) <= 0.004 * res["compton"] + 5
