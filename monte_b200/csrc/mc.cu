@@ -85,311 +85,13 @@ __device__ __forceinline__ float u01(uint32_t x) {
 #define STREAM_EVENT  1u
 #define STREAM_SOURCE 2u
 
-// lane states of the warp-level scheduler
-enum : int { S_DONE = 0, S_REFILL = 1, S_STEP = 2, S_COLLIDE = 3, S_COMPTON = 4 };
-
+// ------------------------------------------------------------------------------------------------
 // The transport loop of one history is a sequence of phases of very different cost and frequency
 // (Woodcock step / collision bookkeeping / one Kahn round / end-of-history tally + source set-up).
-// Lanes of a warp are in different phases at any time, so instead of letting every lane run its own
-// control flow (v1: 8.9 of 32 lanes active per issued instruction, profiles/r01_v1_mc_ncu_full.txt),
-// each iteration the warp votes and executes ONLY the phase that most lanes are waiting for; the
-// other lanes keep their state and wait.  Results are unchanged: every history consumes its own
-// counter-based variates in the same order regardless of when its phases are scheduled.
-template <bool RECORD>
-__global__ void __launch_bounds__(MC_THREADS, 3)
-mc_transport_kernel(const __grid_constant__ McLaunch P) {
-    extern __shared__ float4 s_mem[];
-    const McSceneDev &sc = P.sc;
-    float4 *s_tab = s_mem;                                             // [n_mat*201]
-    float *s_inv = reinterpret_cast<float *>(s_tab + sc.n_mat * TAB_ROWS);   // [201]
-    float *s_cdf = s_inv + TAB_ROWS + 3;                               // [n_bins+1]
-    for (int i = threadIdx.x; i < sc.n_mat * TAB_ROWS; i += MC_THREADS) s_tab[i] = sc.tab[i];
-    for (int i = threadIdx.x; i < TAB_ROWS; i += MC_THREADS) s_inv[i] = sc.inv_mumax[i];
-    for (int i = threadIdx.x; i <= sc.n_bins && sc.n_bins > 0; i += MC_THREADS) s_cdf[i] = sc.cdf[i];
-    __syncthreads();
-
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const uint32_t npix = (uint32_t)(sc.det_ny * sc.det_nx);
-    // voxel index = round-to-nearest of (p - org)/pitch - 0.5 through the 1.5*2^23 trick (no F2I)
-    const float vox_off[3] = {-sc.org[0] * sc.inv_pitch - 0.5f, -sc.org[1] * sc.inv_pitch - 0.5f, -sc.org[2] * sc.inv_pitch - 0.5f};
-
-    // tally of unscattered photons of the pixel this lane is currently working on
-    uint32_t cur_pv = 0xffffffffu, prim_cnt = 0;
-
-    for (;;) {
-        unsigned long long unit = 0;
-        if (lane == 0) unit = atomicAdd(P.work, 1ull);
-        unit = __shfl_sync(0xffffffffu, unit, 0);
-        if (unit >= P.n_units) break;
-        const unsigned long long base = unit * (unsigned long long)MC_UNIT;
-        const uint32_t unit_cnt = (uint32_t)min((unsigned long long)MC_UNIT, P.total - base);
-        const uint32_t pv0 = (uint32_t)(base / P.cnt);
-        const uint32_t n0 = (uint32_t)(base - (unsigned long long)pv0 * P.cnt);
-        const uint32_t v0 = pv0 / npix, p0 = pv0 - v0 * npix;
-        uint32_t next_off = 0;
-
-        uint32_t c_hist = 0, c_prim = 0, c_scat = 0, c_abs = 0, c_int = 0, c_coh = 0, c_comp = 0, c_steps = 0;
-        unsigned long long e_prim = 0, e_scat = 0;      // fixed point, 1/1024 keV
-
-        // per-history state
-        int state = S_REFILL;
-        bool pending_detect = false;                     // the history that just ended escaped after >=1 interaction
-        float x = 0, y = 0, z = 0, dx = 0, dy = 0, dz = 0, E = 0, inv_mumax = 0, u_phi = 0;
-        int kE = 0, nint = 0, mat = 0;
-        uint32_t c0 = 0, c1hi = 0, n_fl = 0, n_ev = 0, pv_abs = 0, rec_idx = 0;
-        int cur_view = 0;
-
-        for (;;) {
-            // ---------------- vote: run the phase most lanes wait for -------------------------
-            // one REDUX over a packed one-hot (8 bits per phase, counts <= 32) replaces four ballots
-            const uint32_t onehot = state == S_DONE ? 0u : (1u << ((state - 1) * 8));
-            const uint32_t cnts = __reduce_add_sync(0xffffffffu, onehot);   // REFILL | STEP<<8 | COLLIDE<<16 | COMPTON<<24
-            if (cnts == 0u) break;                                          // every lane is S_DONE
-            const int n_ref = cnts & 0xFF, n_step = (cnts >> 8) & 0xFF, n_col = (cnts >> 16) & 0xFF, n_kah = cnts >> 24;
-            int phase = S_STEP, best = n_step;
-            if (n_ref > best) { phase = S_REFILL; best = n_ref; }
-            if (n_col > best) { phase = S_COLLIDE; best = n_col; }
-            if (n_kah > best) { phase = S_COMPTON; best = n_kah; }
-
-            if (phase == S_STEP) {
-                if (state != S_STEP) continue;
-                // ---------------- one Woodcock step, CBCT_real325im.cu:886-968 ---------------
-                const uint2 r = philox2x32_10(c0, c1hi | (STREAM_FLIGHT << 22) | (n_fl & 0x3FFFFFu), P.key);
-                n_fl++;
-                const float s = -__logf(u01(r.x)) * inv_mumax;
-                x = fmaf(s, dx, x); y = fmaf(s, dy, y); z = fmaf(s, dz, z);
-                c_steps++;
-                const bool inside = x >= sc.clip_lo[0] && x < sc.clip_hi[0] && y >= sc.clip_lo[1] && y < sc.clip_hi[1] &&
-                                    z >= sc.clip_lo[2] && z < sc.clip_hi[2];
-                if (!inside) {                       // left the volume: only air ahead
-                    if (nint == 0) {                 // unscattered: lands in the pixel it was aimed at (:567-590)
-                        prim_cnt++; c_prim++;
-                        e_prim += (unsigned long long)(E * 1024.f + 0.5f);
-                        if (RECORD) { P.fates[rec_idx] = 1u | ((pv_abs - (uint32_t)cur_view * npix) << 8); P.fate_e[rec_idx] = E; }
-                    } else pending_detect = true;    // scatter detection runs with the refill phase
-                    state = S_REFILL;
-                    continue;
-                }
-                int ix = __float_as_int(fmaf(x, sc.inv_pitch, vox_off[0]) + 12582912.0f) - 0x4B400000;
-                int iy = __float_as_int(fmaf(y, sc.inv_pitch, vox_off[1]) + 12582912.0f) - 0x4B400000;
-                int iz = __float_as_int(fmaf(z, sc.inv_pitch, vox_off[2]) + 12582912.0f) - 0x4B400000;
-                ix = (int)min((unsigned)ix, (unsigned)(sc.nx - 1)); iy = (int)min((unsigned)iy, (unsigned)(sc.ny - 1));
-                iz = (int)min((unsigned)iz, (unsigned)(sc.nz - 1));     // safety only: the clip box lies inside the volume
-                const int lab = __ldg(sc.labels + ((size_t)iz * sc.ny + iy) * sc.nx + ix);
-                if (lab == 0) continue;                                   // air: virtual collision
-                mat = min(lab, sc.n_mat) - 1;
-                if (u01(r.y) > s_tab[mat * TAB_ROWS + kE].x) continue;    // virtual collision, :941-961
-                state = S_COLLIDE;
-                continue;
-            }
-
-            if (phase == S_COLLIDE) {
-                if (state != S_COLLIDE) continue;
-                // ---------------- real collision, CBCT_real325im.cu:599-656 ----------------------
-                if (nint >= sc.max_scatter) {                             // scatter budget used up
-                    if (RECORD) { P.fates[rec_idx] = 5u | ((uint32_t)nint << 28); P.fate_e[rec_idx] = E; }
-                    state = S_REFILL;
-                    continue;
-                }
-                {
-                    const float2 cs = __ldg(sc.view_cs + cur_view);
-                    const float xr = x * cs.x + y * cs.y, yr = -x * cs.y + y * cs.x;
-                    if (xr >= sc.dod || fabsf(yr) >= sc.half || fabsf(z) >= sc.half) {        // :613-619
-                        if (RECORD) { P.fates[rec_idx] = 4u | ((uint32_t)nint << 28); P.fate_e[rec_idx] = E; }
-                        state = S_REFILL;
-                        continue;
-                    }
-                }
-                nint++; c_int++;
-                const uint2 re = philox2x32_10(c0, c1hi | (STREAM_EVENT << 22) | (n_ev & 0x3FFFFFu), P.key);
-                n_ev++;
-                const float u_sel = u01(re.x);
-                u_phi = u01(re.y);
-                const float4 tb = s_tab[mat * TAB_ROWS + kE];
-                if (u_sel <= tb.y) {                                      // photoelectric, :651-655
-                    c_abs++;
-                    if (RECORD) { P.fates[rec_idx] = 3u | ((uint32_t)nint << 28); P.fate_e[rec_idx] = E; }
-                    state = S_REFILL;
-                } else if (u_sel <= tb.z) { c_coh++; state = S_STEP; }    // coherent: no deflection, :656-670
-                else { c_comp++; state = S_COMPTON; }
-                continue;
-            }
-
-            if (phase == S_COMPTON) {
-                if (state != S_COMPTON) continue;
-                // ---------------- one round of Kahn's method, :701-736 -----------------------------
-                const float lam = __fdividef(511.0f, E);
-                const uint2 ra = philox2x32_10(c0, c1hi | (STREAM_EVENT << 22) | (n_ev & 0x3FFFFFu), P.key);
-                n_ev += 1;
-                const float r2 = u01(ra.x), r3 = u01(ra.y);
-                const float r1 = ((float)(((ra.x & 0x1FFu) << 9) | (ra.y & 0x1FFu)) + 0.5f) * (1.0f / 262144.0f);
-                // both branches evaluated branch-free (the lanes of a Kahn round split ~1:5 between them)
-                const bool br1 = r1 * (9.0f * lam + 2.0f) < (lam + 2.0f);
-                const float ro1 = 1.0f + __fdividef(2.0f, lam) * r2;
-                const float ro2 = __fdividef(lam + 2.0f, lam + 2.0f * (1.0f - r2));
-                const float ro = br1 ? ro1 : ro2;
-                const float iro = __fdividef(1.0f, ro);
-                const float t = lam - ro * lam + 1.0f;
-                const float lim = br1 ? 4.0f * (iro - iro * iro) : 0.5f * (t * t + iro);
-                const bool acc = r3 <= lim;
-                if (!acc) continue;                                       // rejected: next round next time
-                const float lam_d = ro * lam;
-                float cos_t = 1.0f - (lam_d - lam);
-                cos_t = fmaxf(cos_t, -1.0f);                              // :746-747
-                const float sin_t = sqrtf(fmaxf(0.f, 1.0f - cos_t * cos_t));
-                E = __fdividef(511.0f, lam_d);
-                kE = min(max((int)(E + 0.5f), 0), TAB_ROWS - 1);
-                inv_mumax = s_inv[kE];
-                float sphi, cphi;
-                sincospif(2.0f * u_phi, &sphi, &cphi);                    // phi = 2 pi u, :764
-                // ---- direction update, :768-780, as a rotation of the unit vector.  With
-                //      (sin th_a cos ph_a, sin th_a sin ph_a, cos th_a) = d the reference's formulas are
-                //      d' = cos_t d + sin_t (cos phi e1 + sin phi e2),
-                //      e1 = (cos th_a cos ph_a, cos th_a sin ph_a, -sin th_a), e2 = (-sin ph_a, cos ph_a, 0).
-                const float st2 = dx * dx + dy * dy;
-                float e1x, e1y, e1z, e2x, e2y;
-                if (st2 > 1e-12f) {
-                    const float ist = rsqrtf(st2), sta = st2 * ist;
-                    e1x = dx * dz * ist; e1y = dy * dz * ist; e1z = -sta;
-                    e2x = -dy * ist; e2y = dx * ist;
-                } else {                                                  // along +-z: azimuth undefined, pick phi_a = 0
-                    e1x = dz; e1y = 0.f; e1z = 0.f; e2x = 0.f; e2y = 1.f;
-                }
-                const float a = sin_t * cphi, b = sin_t * sphi;
-                const float nxd = cos_t * dx + a * e1x + b * e2x;
-                const float nyd = cos_t * dy + a * e1y + b * e2y;
-                const float nzd = cos_t * dz + a * e1z;
-                const float nn = rsqrtf(nxd * nxd + nyd * nyd + nzd * nzd);
-                dx = nxd * nn; dy = nyd * nn; dz = nzd * nn;
-                state = S_STEP;
-                continue;
-            }
-
-            // ---------------- phase == S_REFILL: finish the ended history, start the next one ----------
-            const unsigned m_ref = __ballot_sync(0xffffffffu, state == S_REFILL);
-            const uint32_t my_off = next_off + __popc(m_ref & lt_mask);
-            next_off += (uint32_t)n_ref;                 // uniform: every lane advances the unit cursor
-            if (state != S_REFILL) continue;
-            if (pending_detect) {                        // scatter detection, CBCT_real325im.cu:823-843
-                pending_detect = false;
-                uint32_t fate = 4u | ((uint32_t)nint << 28);
-                const int view = cur_view;
-                const float2 cs = __ldg(sc.view_cs + view);
-                const float xr = x * cs.x + y * cs.y, yr = -x * cs.y + y * cs.x;      // rotate by -beta
-                const float dxr = dx * cs.x + dy * cs.y, dyr = -dx * cs.y + dy * cs.x;
-                if (dxr > 0.f) {
-                    const float t = (sc.dod - xr) / dxr;
-                    const float yd = fmaf(t, dyr, yr), zd = fmaf(t, dz, z);
-                    if (fabsf(yd) <= sc.half && fabsf(zd) <= sc.half && fmaf(1000.f, dxr, xr) >= sc.dod) {
-                        const int by = (int)((sc.half - yd) * sc.inv_pixel), bx = (int)((sc.half - zd) * sc.inv_pixel);
-                        if (by >= 0 && by < sc.det_ny && bx >= 0 && bx < sc.det_nx) {
-                            const uint32_t bin = (uint32_t)(by * sc.det_nx + bx);
-                            atomicAdd(P.image5 + (size_t)view * npix + bin, 1);
-                            c_scat++;
-                            e_scat += (unsigned long long)(E * 1024.f + 0.5f);
-                            fate = 2u | (bin << 8) | ((uint32_t)nint << 28);
-                        }
-                    }
-                }
-                if (RECORD) { P.fates[rec_idx] = fate; P.fate_e[rec_idx] = E; }
-            }
-            {
-                const uint32_t off = my_off;
-                if (off >= unit_cnt) { state = S_DONE; continue; }
-                uint32_t n = n0 + off;
-                const uint32_t dpv = n / P.cnt;
-                n -= dpv * P.cnt;
-                uint32_t pix = p0 + dpv, vrel = v0;
-                if (pix >= npix) { const uint32_t q = pix / npix; vrel += q; pix -= q * npix; }
-                const int view = P.view_begin + (int)vrel;
-                const uint32_t pva = (uint32_t)view * npix + pix;
-                if (pva != cur_pv) {
-                    if (prim_cnt) { atomicAdd(P.image0 + cur_pv, (int)prim_cnt); atomicAdd(P.image5 + cur_pv, (int)prim_cnt); }
-                    cur_pv = pva; prim_cnt = 0;
-                }
-                pv_abs = pva;
-                cur_view = view;
-                n += P.n_begin;
-                const unsigned long long hid = (unsigned long long)pva * P.per + n;
-                c0 = (uint32_t)hid;
-                c1hi = ((uint32_t)(hid >> 32) & 0xFFu) << 24;
-                n_fl = 0; n_ev = 0; nint = 0;
-                if (RECORD) rec_idx = pix * P.per + n;
-                c_hist++;
-                // ---- source, CBCT_real325im.cu:464-540 (exact aim at the pixel) ----
-                const uint32_t pi = pix / (uint32_t)sc.det_nx, pj = pix - pi * (uint32_t)sc.det_nx;
-                float uy = 0.5f, uz = 0.5f;
-                if (sc.source_mode == MONTE_MC_SOURCE_CONE) {
-                    const uint2 r = philox2x32_10(c0, c1hi | (STREAM_SOURCE << 22), P.key);
-                    uy = u01(r.x); uz = u01(r.y);
-                }
-                E = sc.mono_keV;
-                if (sc.n_bins > 0) {                              // CBCT_real325im.cu:492-498
-                    const uint2 r = philox2x32_10(c0, c1hi | (STREAM_SOURCE << 22) | 1u, P.key);
-                    const float ue = u01(r.x);
-                    int lo = 0, hi = sc.n_bins;                  // first k with ue <= cdf[k+1]
-                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ue <= s_cdf[mid + 1]) hi = mid; else lo = mid + 1; }
-                    if (lo < sc.n_bins) E = (float)(lo + 1) * sc.bin_keV;
-                }
-                kE = min(max((int)(E + 0.5f), 0), TAB_ROWS - 1);
-                inv_mumax = s_inv[kE];
-                const float yl = sc.half - sc.pixel * ((float)pi + uy);
-                const float zl = sc.half - sc.pixel * ((float)pj + uz);
-                const float rn = rsqrtf(sc.dsd * sc.dsd + yl * yl + zl * zl);
-                const float2 cs = __ldg(sc.view_cs + view);
-                const float dxr = sc.dsd * rn, dyr = yl * rn;
-                dx = dxr * cs.x - dyr * cs.y;
-                dy = dxr * cs.y + dyr * cs.x;
-                dz = zl * rn;
-                const float sx = -sc.dso * cs.x, sy = -sc.dso * cs.y;
-                // analytic flight to the clip box (slab method)
-                float t0 = 0.f, t1 = 1e30f;
-                {
-                    const float o3[3] = {sx, sy, 0.f}, d3[3] = {dx, dy, dz};
-#pragma unroll
-                    for (int a = 0; a < 3; a++) {
-                        if (d3[a] != 0.f) {
-                            const float inv = 1.0f / d3[a];
-                            float ta = (sc.clip_lo[a] - o3[a]) * inv, tb = (sc.clip_hi[a] - o3[a]) * inv;
-                            if (ta > tb) { const float t = ta; ta = tb; tb = t; }
-                            t0 = fmaxf(t0, ta); t1 = fminf(t1, tb);
-                        } else if (o3[a] < sc.clip_lo[a] || o3[a] >= sc.clip_hi[a]) t1 = -1.f;
-                    }
-                }
-                if (t0 >= t1) {                                   // misses the phantom: unscattered
-                    prim_cnt++; c_prim++;
-                    e_prim += (unsigned long long)(E * 1024.f + 0.5f);
-                    if (RECORD) { P.fates[rec_idx] = 1u | (pix << 8); P.fate_e[rec_idx] = E; }
-                    // state stays S_REFILL: the next vote fetches another history for this lane
-                } else {
-                    x = fmaf(t0, dx, sx); y = fmaf(t0, dy, sy); z = t0 * dz;
-                    state = S_STEP;
-                }
-            }
-        }
-
-        // ---------------- per-unit statistics ------------------------------------------------
-        if (P.stats) {
-            const uint32_t v[8] = {c_hist, c_prim, c_scat, c_abs, c_int, c_coh, c_comp, c_steps};
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const uint32_t s = __reduce_add_sync(0xffffffffu, v[i]);
-                if (lane == 0 && s) atomicAdd(P.stats + i, (unsigned long long)s);
-            }
-            unsigned long long ep = e_prim, es = e_scat;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { ep += __shfl_xor_sync(0xffffffffu, ep, o); es += __shfl_xor_sync(0xffffffffu, es, o); }
-            if (lane == 0) { if (ep) atomicAdd(P.stats + ST_EPRIM, ep); if (es) atomicAdd(P.stats + ST_ESCAT, es); }
-        }
-    }
-    if (prim_cnt) { atomicAdd(P.image0 + cur_pv, (int)prim_cnt); atomicAdd(P.image5 + cur_pv, (int)prim_cnt); }
-}
-
-// ------------------------------------------------------------------------------------------------
-// v3: K histories per lane, parked in shared memory.
-// v2's vote still leaves ~half of the lanes idle in every executed phase, because each lane owns
-// exactly one history and it is often in a minority phase.  Here every lane owns K histories
+// Lanes of a warp are in different phases at any time.  v1 let every lane run its own control flow
+// (8.9 of 32 lanes active per issued instruction); v2 let the warp vote and execute only the phase
+// most lanes wait for (16.9 lanes), but a lane that owns exactly one history is often in a minority
+// phase.  This kernel (v3) parks K histories per lane in shared memory: every lane owns K histories
 // ("slots"); their state lives in shared memory (struct-of-arrays, column = lane, so accesses are
 // conflict-free) and only a 4-bit one-hot phase per slot stays in a register.  Each iteration the
 // warp votes for the phase in which most LANES have at least one slot, every such lane loads that
@@ -586,7 +288,10 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             float sphi, cphi;
             __sincosf(6.2831853071795865f * dir.w, &sphi, &cphi);     // phi = 2 pi u, :764 (MUFU, |err| ~1e-6)
             const float dx = dir.x, dy = dir.y, dz = dir.z;
-            // direction update, :768-780, as a rotation of the unit vector (see v2 for the algebra)
+            // direction update, :768-780, as a rotation of the unit vector.  With
+            // (sin th_a cos ph_a, sin th_a sin ph_a, cos th_a) = d the reference's formulas are
+            //   d' = cos_t d + sin_t (cos phi e1 + sin phi e2),
+            //   e1 = (cos th_a cos ph_a, cos th_a sin ph_a, -sin th_a), e2 = (-sin ph_a, cos ph_a, 0).
             const float st2 = dx * dx + dy * dy;
             float e1x, e1y, e1z, e2x, e2y;
             if (st2 > 1e-12f) {
@@ -928,17 +633,16 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     MONTE_CUDA(cudaMemsetAsync(s->d_work, 0, sizeof(unsigned long long), st));
     const int sms = ctx().sm_count;
     const unsigned long long warps_needed = L.n_units;
-    // kernel selection: v3 with K=5 parked histories per lane is the default (measured best: K=4 9.83 ms,
-    // K=5 9.45 ms, K=6 11.2 ms per 1e8 C2 histories); MONTE_MC_KERNEL=2 runs v2, =31..36 v3 with K=1..6
+    // K = 5 parked histories per lane is the default (measured: K=4 9.83 ms, K=5 9.45 ms, K=6 11.2 ms per
+    // 1e8 C2 histories before the later trims); MONTE_MC_KERNEL=31..36 selects K=1..6 for A/B runs
     static int which = -1;
     if (which < 0) { const char *e = getenv("MONTE_MC_KERNEL"); which = e ? atoi(e) : 35; }
     MONTE_ARG(s->geom.n_views < 4096, "mc: more than 4095 views");
     const int rec = d_fates ? 1 : 0;
-    const int K = which >= 31 && which <= 36 ? which - 30 : (which == 44 ? 4 : (which == 43 ? 3 : 0));
+    const int K = which >= 31 && which <= 36 ? which - 30 : (which == 44 ? 4 : (which == 43 ? 3 : 5));
     const size_t slot_bytes = (size_t)K * 32 * mc_slot_groups(rec != 0) * sizeof(uint4) * (MC_THREADS / 32);
-    const size_t smem = K ? (size_t)s->dev.n_mat * TAB_ROWS * sizeof(float4) +
-                                (TAB_ROWS + 3 + ((s->dev.n_bins + 1 + 3) & ~3)) * sizeof(float) + slot_bytes
-                          : s->smem;
+    const size_t smem = (size_t)s->dev.n_mat * TAB_ROWS * sizeof(float4) +
+                        (TAB_ROWS + 3 + ((s->dev.n_bins + 1 + 3) & ~3)) * sizeof(float) + slot_bytes;
     const void *fn = nullptr;
     switch (which * 2 + rec) {
         case 62: fn = (const void *)mc_transport_kernel_v3<false, 1>; break;
@@ -955,7 +659,7 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
         case 88: fn = (const void *)mc_transport_kernel_v3<false, 4, 4>; break;    // which=44: K=4, 4 CTAs/SM (64 regs)
         case 86: fn = (const void *)mc_transport_kernel_v3<false, 3, 4>; break;    // which=43
         case 73: fn = (const void *)mc_transport_kernel_v3<true, 6>; break;
-        default: fn = rec ? (const void *)mc_transport_kernel<true> : (const void *)mc_transport_kernel<false>; break;
+        default: fn = rec ? (const void *)mc_transport_kernel_v3<true, 5> : (const void *)mc_transport_kernel_v3<false, 5>; break;
     }
     static int occ[96] = {0};                      // resident CTAs per SM: persistent grid = SMs x occupancy
     static size_t smem_set[96] = {0}, smem_occ[96] = {0};
