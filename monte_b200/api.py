@@ -279,9 +279,10 @@ def counts_to_map(counts, per):
     return out
 
 
-def project_primary(g, vol, labels, xs, keV, views=None):
+def project_primary(g, vol, labels, xs, keV, views=None, out=None):
     labels = np.ascontiguousarray(labels, np.uint8)
     vb, ve = views if views else (0, g.n_views)
-    out = np.zeros((g.n_views, g.ny, g.nx), np.float32)
+    if out is None:
+        out = np.zeros((g.n_views, g.ny, g.nx), np.float32)
     _check(load().monte_gpu_project_primary(C.byref(g), C.byref(vol), _ptr(labels), C.byref(xs), keV, vb, ve, _ptr(out)))
     return out

@@ -12,7 +12,8 @@
 namespace monte {
 
 struct ProjParams {
-    const uint8_t *labels;
+    const uint8_t *labels;       // [z][y][x]
+    const uint8_t *labels_t;     // [z][x][y]: the copy walked by views whose rays run mostly along x
     int nx, ny, nz;
     float pitch, inv_pitch;
     float org[3], clip_lo[3], clip_hi[3];
@@ -23,60 +24,101 @@ struct ProjParams {
     float *map;                  // [n_views_total][ny][nx], written at absolute view index
 };
 
+// Raw labels [z][y][x] -> two copies with a one-voxel guard ring of air (label 0): `out` [z][y][x]
+// and `out_t` [z][x][y].  32x32 byte tiles go through shared memory for the transposed one.  The
+// guard ring makes the walk below safe without per-step bounds tests: a plane crossing that rounding
+// puts a hair before the exit face steps into air, never out of the allocation.
+__global__ void __launch_bounds__(256)
+labels_pad_transpose_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, uint8_t *__restrict__ out_t,
+                            int nx, int ny) {
+    __shared__ uint8_t tile[32][33];
+    const int px = nx + 2, py = ny + 2;
+    const size_t slice = (size_t)blockIdx.z * nx * ny;
+    const size_t pslice = (size_t)(blockIdx.z + 1) * px * py;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int x = x0 + threadIdx.x, y = y0 + r;
+        if (x < nx && y < ny) {
+            const uint8_t v = in[slice + (size_t)y * nx + x];
+            tile[r][threadIdx.x] = v;
+            out[pslice + (size_t)(y + 1) * px + x + 1] = v;
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int y = y0 + threadIdx.x, x = x0 + r;
+        if (x < nx && y < ny) out_t[pslice + (size_t)(x + 1) * py + y + 1] = tile[threadIdx.x][r];
+    }
+}
+
+// One thread per ray.  A warp holds 32 transaxially adjacent pixels of one detector row: at any
+// step its rays sit in neighbouring voxels ACROSS the dominant direction of travel, so with the
+// label copy whose fastest axis is that transverse axis a warp-wide fetch touches one or two
+// 128-byte lines instead of 32.
 __global__ void __launch_bounds__(128)
 project_primary_kernel(const __grid_constant__ ProjParams p) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;      // axial pixel (fastest)
-    const int i = blockIdx.y;
+    __shared__ float s_mu[256];                               // per-label attenuation (a divergent index into
+    for (int l = threadIdx.x; l < 256; l += 128) s_mu[l] = p.mu[l];   // the kernel-parameter bank would serialise)
+    __syncthreads();
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31);       // transaxial pixel: lanes of a warp
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 5);        // axial pixel (fastest in the map)
     const int view = p.view_begin + blockIdx.z;
-    if (j >= p.det_nx) return;
+    if (i >= p.det_ny || j >= p.det_nx) return;
     double sb_d, cb_d;
     sincospi((p.angle0 + p.angle_step * view) / 180.0, &sb_d, &cb_d);
     const float cb = (float)cb_d, sb = (float)sb_d;
+    const bool along_x = fabsf(cb) >= fabsf(sb);              // uniform per block
+    const uint8_t *__restrict__ lab_base = along_x ? p.labels_t : p.labels;
     const float yl = p.half - p.pixel * ((float)i + 0.5f), zl = p.half - p.pixel * ((float)j + 0.5f);
     const float rn = rsqrtf(p.dsd * p.dsd + yl * yl + zl * zl);
     const float d[3] = {(p.dsd * cb - yl * sb) * rn, (p.dsd * sb + yl * cb) * rn, zl * rn};
     const float src[3] = {-p.dso * cb, -p.dso * sb, 0.f};
     float t0 = 0.f, t1 = 1e30f;
 #pragma unroll
-    for (int a = 0; a < 3; a++) {
-        if (d[a] != 0.f) {
-            const float inv = 1.0f / d[a];
-            float ta = (p.clip_lo[a] - src[a]) * inv, tb = (p.clip_hi[a] - src[a]) * inv;
-            if (ta > tb) { const float t = ta; ta = tb; tb = t; }
-            t0 = fmaxf(t0, ta); t1 = fminf(t1, tb);
-        } else if (src[a] < p.clip_lo[a] || src[a] >= p.clip_hi[a]) t1 = -1.f;
+    for (int a = 0; a < 3; a++) {                             // branch-free slab clip (inf bounds for d == 0)
+        const float inv = 1.0f / d[a];
+        const float ta = (p.clip_lo[a] - src[a]) * inv, tb = (p.clip_hi[a] - src[a]) * inv;
+        t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
     }
     float acc = 0.f;
     if (t0 < t1) {
-        // traverse with the parameter measured from the entry point (keeps fp32 resolution ~1e-6 cm)
+        // Amanatides-Woo with the ray parameter measured from the entry point (keeps fp32 resolution
+        // ~1e-6 cm), a linear voxel index advanced by the stride of the crossed axis, and the next
+        // label fetched while the current segment is accumulated.
         const float len = t1 - t0;
-        float e[3], tnext[3], dt[3];
-        int idx[3], step[3];
+        float tn[3], dt[3];
+        int idx[3], stp[3];
         const int dims[3] = {p.nx, p.ny, p.nz};
+        const int px = p.nx + 2, py = p.ny + 2;
+        const int strides[3] = {along_x ? py : 1, along_x ? 1 : px, px * py};
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-            e[a] = fmaf(t0, d[a], src[a]);
-            const float q = fmaf(1e-4f * p.pitch, d[a], e[a]);
-            idx[a] = (int)floorf((q - p.org[a]) * p.inv_pitch);
-            step[a] = d[a] > 0.f ? 1 : -1;
+            const float e = fmaf(t0, d[a], src[a]);
+            const float q = fmaf(1e-4f * p.pitch, d[a], e);
+            idx[a] = min(max((int)floorf((q - p.org[a]) * p.inv_pitch), 0), dims[a] - 1);
             if (d[a] != 0.f) {
                 const float edge = p.org[a] + (float)(idx[a] + (d[a] > 0.f ? 1 : 0)) * p.pitch;
-                tnext[a] = (edge - e[a]) / d[a];
+                tn[a] = fmaxf((edge - e) / d[a], 0.f);       // >= 0, so the crossings below never decrease
                 dt[a] = p.pitch / fabsf(d[a]);
-            } else { tnext[a] = 1e30f; dt[a] = 1e30f; }
+            } else { tn[a] = 1e30f; dt[a] = 1e30f; }
+            stp[a] = d[a] > 0.f ? strides[a] : -strides[a];
         }
+        unsigned lin = (unsigned)((idx[2] + 1) * strides[2] + (idx[1] + 1) * strides[1] + (idx[0] + 1) * strides[0]);
+        int lab = __ldg(lab_base + lin);
         float t = 0.f;
         while (t < len) {
-            const int a = tnext[0] <= tnext[1] ? (tnext[0] <= tnext[2] ? 0 : 2) : (tnext[1] <= tnext[2] ? 1 : 2);
-            const float te = fminf(tnext[a], len);
-            if (idx[0] >= 0 && idx[1] >= 0 && idx[2] >= 0 && idx[0] < dims[0] && idx[1] < dims[1] && idx[2] < dims[2]) {
-                const int l = __ldg(p.labels + ((size_t)idx[2] * p.ny + idx[1]) * p.nx + idx[0]);
-                if (te > t) acc = fmaf(p.mu[l], te - t, acc);
-            }
+            const float m12 = fminf(tn[1], tn[2]);
+            const bool ax = tn[0] <= m12;
+            const bool ay = !ax && tn[1] <= tn[2];
+            const float te = fminf(fminf(tn[0], m12), len);
+            acc = fmaf(s_mu[lab], te - t, acc);
             t = te;
-            if (a == 0) { idx[0] += step[0]; tnext[0] += dt[0]; }
-            else if (a == 1) { idx[1] += step[1]; tnext[1] += dt[1]; }
-            else { idx[2] += step[2]; tnext[2] += dt[2]; }
+            lin += (unsigned)(ax ? stp[0] : (ay ? stp[1] : stp[2]));
+            lab = __ldg(lab_base + lin);                      // at most one voxel past the box: the guard ring
+            const bool az = !ax && !ay;
+            if (ax) tn[0] += dt[0];
+            if (ay) tn[1] += dt[1];
+            if (az) tn[2] += dt[2];
         }
     }
     p.map[((size_t)view * p.det_ny + i) * p.det_nx + j] = acc;
@@ -99,13 +141,21 @@ extern "C" int monte_gpu_project_primary(const monte_mc_geom *g, const monte_mc_
     cudaStream_t st = ctx().stream;
     const size_t nvox = (size_t)vol->nx * vol->ny * vol->nz;
     const size_t n_map = (size_t)g->n_views * g->ny * g->nx;
-    char *base = (char *)scratch(6, nvox + 256 + n_map * sizeof(float));
+    const size_t nvox_al = (nvox + 255) / 256 * 256;
+    const size_t npad = (size_t)(vol->nx + 2) * (vol->ny + 2) * (vol->nz + 2);
+    const size_t npad_al = (npad + 255) / 256 * 256;
+    MONTE_ARG(npad < ((size_t)1 << 32), "project_primary: volume too large for 32-bit voxel offsets");
+    char *base = (char *)scratch(6, nvox_al + 2 * npad_al + n_map * sizeof(float));
     if (!base) return MONTE_E_NOMEM;
-    uint8_t *d_lab = (uint8_t *)base;
-    float *d_map = (float *)(base + (nvox + 255) / 256 * 256);
-    MONTE_CUDA(cudaMemcpyAsync(d_lab, labels, nvox, cudaMemcpyHostToDevice, st));
+    uint8_t *d_raw = (uint8_t *)base, *d_lab = d_raw + nvox_al, *d_lab_t = d_lab + npad_al;
+    float *d_map = (float *)(base + nvox_al + 2 * npad_al);
+    MONTE_CUDA(cudaMemcpyAsync(d_raw, labels, nvox, cudaMemcpyHostToDevice, st));
+    MONTE_CUDA(cudaMemsetAsync(d_lab, 0, 2 * npad_al, st));
+    labels_pad_transpose_kernel<<<dim3(ceil_div(vol->nx, 32), ceil_div(vol->ny, 32), vol->nz), dim3(32, 8), 0, st>>>(
+        d_raw, d_lab, d_lab_t, vol->nx, vol->ny);
+    MONTE_CUDA(cudaGetLastError());
     ProjParams p;
-    p.labels = d_lab; p.nx = vol->nx; p.ny = vol->ny; p.nz = vol->nz;
+    p.labels = d_lab; p.labels_t = d_lab_t; p.nx = vol->nx; p.ny = vol->ny; p.nz = vol->nz;
     p.pitch = (float)vol->pitch; p.inv_pitch = (float)(1.0 / vol->pitch);
     for (int a = 0; a < 3; a++) { p.org[a] = (float)vol->origin[a]; p.clip_lo[a] = (float)vol->clip_lo[a]; p.clip_hi[a] = (float)vol->clip_hi[a]; }
     int k = (int)(keV + 0.5);
@@ -118,12 +168,29 @@ extern "C" int monte_gpu_project_primary(const monte_mc_geom *g, const monte_mc_
     p.pixel = (float)g->pixel; p.half = (float)g->half; p.dso = (float)g->dso; p.dsd = (float)(g->dso + g->dod);
     p.angle0 = g->angle0_deg; p.angle_step = g->angle_step_deg;
     p.map = d_map;
-    dim3 grid(ceil_div(g->nx, 128), g->ny, view_end - view_begin);
-    project_primary_kernel<<<grid, 128, 0, st>>>(p);
-    MONTE_CUDA(cudaGetLastError());
+    // views in chunks: chunk k is downloaded on the copy stream while chunk k+1 is traced
+    constexpr int MAXC = 8;
+    static cudaEvent_t ev[MAXC] = {nullptr};
+    if (!ev[0]) {
+        for (int i = 0; i < MAXC; i++) MONTE_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        at_shutdown([] { for (int i = 0; i < MAXC; i++) if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = nullptr; } });
+    }
+    cudaStream_t cp = ctx().copy_stream;
     const size_t per_view = (size_t)g->ny * g->nx;
-    MONTE_CUDA(cudaMemcpyAsync(map + view_begin * per_view, d_map + view_begin * per_view,
-                               (size_t)(view_end - view_begin) * per_view * sizeof(float), cudaMemcpyDeviceToHost, st));
+    const int n_run = view_end - view_begin;
+    const int chunk = ceil_div(n_run, MAXC);
+    for (int k = 0, v0 = view_begin; v0 < view_end; k++, v0 += chunk) {
+        const int v1 = v0 + chunk < view_end ? v0 + chunk : view_end;
+        p.view_begin = v0; p.n_views_run = v1 - v0;
+        dim3 grid(ceil_div(g->ny, 32), ceil_div(g->nx, 4), v1 - v0);
+        project_primary_kernel<<<grid, 128, 0, st>>>(p);
+        MONTE_CUDA(cudaGetLastError());
+        MONTE_CUDA(cudaEventRecord(ev[k], st));
+        MONTE_CUDA(cudaStreamWaitEvent(cp, ev[k], 0));
+        MONTE_CUDA(cudaMemcpyAsync(map + v0 * per_view, d_map + v0 * per_view, (size_t)(v1 - v0) * per_view * sizeof(float),
+                                   cudaMemcpyDeviceToHost, cp));
+    }
     MONTE_CUDA(cudaStreamSynchronize(st));
+    MONTE_CUDA(cudaStreamSynchronize(cp));
     return MONTE_OK;
 }
