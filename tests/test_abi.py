@@ -125,3 +125,17 @@ def test_host_helpers(lib):
                                  C.c_void_p(mu.ctypes.data), C.c_void_p(lab.ctypes.data)) == 0
     assert mu[0] == 0 and abs(mu[1] - 0.1538092) < 1e-6 and abs(mu[2] - 2 * 0.1538092) < 1e-6
     assert list(lab) == [0, 1, 2, 2]
+
+
+def test_fft_core_on_the_host(tmp_path):
+    """monte_b200/csrc/fft_core.cuh is plain C++: its per-thread FFT phases, driven by a sequential loop
+    over the threads, reproduce the direct Ram-Lak convolution of recon/bp3d20.cpp:63-73 (all three
+    transform lengths, full and partial rows)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "fft_core_host")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(root, "monte_b200", "csrc"),
+                    os.path.join(root, "tests", "fft_core_host.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stdout
+    assert r.stdout.count("rel_err") == 6

@@ -154,6 +154,25 @@ def test_host_pipeline_chunks_equal_single_launch(monte):
     assert st["launches"] > 20
 
 
+@pytest.mark.parametrize("nu,nv", [(300, 37), (640, 21), (1100, 10), (2048, 3)])
+def test_fft_and_direct_filter_against_oracle(monte, oracle, nu, nv, monkeypatch):
+    """Wide detectors take the FFT filter (transform length 1024 / 2048 / 4096, odd nv leaves a lone
+    column in the last pair); both it and the direct convolution must match the oracle's filter."""
+    import torch
+    g = _abi.generic_fdk_geom(3, nu, nv, 16)
+    p = rand(nu + nv, (3, nu, nv)) - 0.25
+    ref = oracle.fdk_filter(g, p)
+    d = torch.from_numpy(p).cuda()
+    got = {}
+    for mode in ("direct", "fft"):
+        monkeypatch.setenv("MONTE_FDK_FILTER", mode)
+        f = torch.full(monte.fdk_filtered_shape(g), 7.0, dtype=torch.float32, device="cuda")
+        monte.fdk_filter_dev(g, d, f)
+        got[mode] = f[: 3 * nv].view(3, nv, f.shape[1])[:, :, :nu].cpu().numpy()
+        assert_close(got[mode], ref, "filter (%s)" % mode)
+    assert float(np.abs(got["fft"] - got["direct"]).max()) <= 1e-5 * float(np.abs(ref).max())
+
+
 def test_c3_full_size(monte, oracle):
     """BASELINE config 3 at full size: 512^3 from 720 views of a 1024x768 detector.
     (a) the filter of two full-size views against the oracle; (b) the whole reconstruction on the GPU,
