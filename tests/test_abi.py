@@ -139,3 +139,25 @@ def test_fft_core_on_the_host(tmp_path):
     r = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
     assert r.returncode == 0, r.stdout
     assert r.stdout.count("rel_err") == 6
+
+
+@pytest.mark.parametrize("L", [1024, 2048, 4096])
+def test_fft_exchange_swizzle_is_bank_conflict_free(L):
+    """fft_pad (csrc/fft_core.cuh) must be a bijection and put the 16 eight-byte elements a half-warp
+    touches in one access on 16 distinct bank pairs, for the loads and the stores of every pass."""
+    def pad(i):
+        m = i >> 4
+        return i ^ ((m & 7) | ((m & 4) << 1))
+    assert sorted(pad(i) for i in range(L)) == list(range(L))
+    T, r_last = L // 8, L // 512
+    patterns = [lambda j, r: j + r * T,                                     # loads of the radix-8 passes
+                lambda j, q: 8 * j + q,                                     # stores, Ns = 1
+                lambda j, q: (j // 8) * 64 + j % 8 + 8 * q,                 # stores, Ns = 8
+                lambda j, q: (j // 64) * 512 + j % 64 + 64 * q,             # stores, Ns = 64
+                lambda j, q: j + (q % r_last) * (L // r_last),              # loads of the last pass
+                lambda j, q: j + (q % r_last) * 512]                        # stores of the last pass
+    for f in patterns:
+        for hw in range(T // 16):
+            for q in range(8):
+                banks = {pad(f(16 * hw + lane, q)) % 16 for lane in range(16)}
+                assert len(banks) == 16
