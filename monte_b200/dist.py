@@ -21,6 +21,55 @@ def split_range(n, world, rank):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def balanced_split(cost, world, align=1):
+    """Contiguous split of range(len(cost)) into `world` pieces of nearly equal total cost: piece r ends
+    where the running sum first reaches (r+1)/world of the total.  Every piece gets at least one item
+    when len(cost) >= world.  With align > 1 a cut is moved to the nearest multiple of `align` when that
+    keeps the pieces non-empty (the backprojector works in z-blocks of 16 slices at absolute multiples
+    of 16, so aligned slabs waste no partial block).  Returns the list of (lo, hi)."""
+    n = len(cost)
+    acc, total = [0.0], 0.0
+    for c in cost:
+        total += float(c)
+        acc.append(total)
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r / world
+        lo = cuts[-1] + 1 if n >= world else cuts[-1]          # leave at least one item to the previous piece
+        hi = n - (world - r) if n >= world else n              # ... and to each of the following ones
+        k = lo
+        while k < hi and acc[k] < target:
+            k += 1
+        if k > lo and target - acc[k - 1] < acc[k] - target:   # the nearer of the two candidate cuts
+            k -= 1
+        k = min(max(k, lo), hi)
+        if align > 1:
+            ka = (k + align // 2) // align * align
+            if lo <= ka <= hi:
+                k = ka
+        cuts.append(k)
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def fdk_slice_cost(g, overhead=0.1, stride=8):
+    """Relative backprojection cost of every z-slice of the volume: the fraction of its (voxel, view)
+    pairs that project onto the detector (the others are skipped, recon/bp3d20.cpp:116) plus a constant
+    for the per-column work that is done regardless.  Sampled on a coarse (s, t, view) grid with the
+    reference's projection formulas (bp3d20.cpp:99-113); used to cut z-slabs of equal work, because at
+    wide cone angles the end slices see the detector in few views or none."""
+    import numpy as np
+    X = (g.x0 + g.vox * np.arange(0, g.nx, stride))[None, :, None]
+    Y = (g.y0 - g.vox * np.arange(0, g.ny, stride))[:, None, None]
+    beta = np.deg2rad(g.angle0_deg + g.angle_step_deg * np.arange(0, g.n_views, stride))[None, None, :]
+    k = g.dsd / (X * np.cos(beta) + Y * np.sin(beta) + g.dso)
+    u_ok = np.abs(k * (-X * np.sin(beta) + Y * np.cos(beta))) <= g.half_u
+    ks = np.sort(k[u_ok])                                      # |k Z| <= half_v  <=>  k <= half_v / |Z|
+    Z = np.abs(g.z0 - g.vox * np.arange(g.nz))
+    frac = np.searchsorted(ks, g.half_v / np.maximum(Z, 1e-12), side="right") / float(k.size)
+    return frac + overhead
+
+
 def is_dist():
     return dist.is_available() and dist.is_initialized()
 
@@ -76,15 +125,17 @@ def fdk_sharded(filter_views, pad, backproject_slab, filt_rows, n_views, nv, nz)
     return (v_lo, v_hi), (z_lo, z_hi)
 
 
-def fdk_sharded_pipelined(filter_views, pad_views, backproject_views, filt_rows, n_views, nv, nz):
+def fdk_sharded_pipelined(filter_views, pad_views, backproject_views, filt_rows, n_views, nv, nz, z_ranges=None):
     """Same result as fdk_sharded, bit for bit, with the exchange hidden behind the backprojection:
     every rank filters its own views, then the view pieces are broadcast in ascending order (all
     broadcasts are queued at once on NCCL's stream) and piece r is backprojected — continuing the
     fp32 partial sums — as soon as pieces r and r+1 have landed (piece r's pad fix-up needs the first
     rows of piece r+1).  Views are consumed in ascending order, exactly as on one GPU.
-    filter_views(lo, hi); pad_views(lo, hi); backproject_views(z_lo, z_hi, v_lo, v_hi, continue_sum)."""
+    filter_views(lo, hi); pad_views(lo, hi); backproject_views(z_lo, z_hi, v_lo, v_hi, continue_sum).
+    z_ranges: one (z_lo, z_hi) per rank (e.g. balanced_split(fdk_slice_cost(g), world)); default: equal
+    thickness.  Any contiguous partition gives the same voxels bit for bit."""
     rank, ws = world()
-    z_lo, z_hi = split_range(nz, ws, rank)
+    z_lo, z_hi = z_ranges[rank] if z_ranges is not None else split_range(nz, ws, rank)
     pieces = [split_range(n_views, ws, r) for r in range(ws)]
     v_lo, v_hi = pieces[rank]
     filter_views(v_lo, v_hi)

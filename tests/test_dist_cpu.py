@@ -139,15 +139,19 @@ def _pipe_worker(rank, ws, port, out_dir):
         slab["v"] = acc
         log.append((v_lo, v_hi, cont))
 
-    vr, zr = mdist.fdk_sharded_pipelined(filter_views, pad_views, backproject_views, rows, n_views, nv, nz)
+    z_ranges = mdist.balanced_split([5, 1, 1, 1, 1, 1, 5], ws) if out_dir.endswith("uneven") else None
+    vr, zr = mdist.fdk_sharded_pipelined(filter_views, pad_views, backproject_views, rows, n_views, nv, nz, z_ranges=z_ranges)
     np.savez(os.path.join(out_dir, "p%d.npz" % rank), slab=slab["v"].numpy(), z=np.array(zr), log=np.array(log))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("ws", [1, 2, 3])
-def test_pipelined_exchange_equals_sequential(tmp_path, ws):
-    port = 29800 + os.getpid() % 1500 + ws
+@pytest.mark.parametrize("ws,uneven", [(1, False), (2, False), (3, False), (3, True)])
+def test_pipelined_exchange_equals_sequential(tmp_path, ws, uneven):
+    port = 29800 + os.getpid() % 1500 + ws + (7 if uneven else 0)
+    if uneven:                                   # z-slabs of equal work instead of equal thickness
+        tmp_path = tmp_path / "uneven"
+        tmp_path.mkdir()
     mp.spawn(_pipe_worker, args=(ws, port, str(tmp_path)), nprocs=ws, join=True)
     n_views, nv, nu, pitch, nz = 11, 5, 6, 8, 7
     rows = np.zeros((n_views * nv + 2, pitch), np.float32)
@@ -167,3 +171,39 @@ def test_pipelined_exchange_equals_sequential(tmp_path, ws):
         assert [int(x) for x in p["log"][:, 0]] == [mdist.split_range(n_views, ws, q)[0] for q in range(ws)]
         z = p["z"][1]
     assert z == nz
+
+
+def test_balanced_split():
+    """z-slabs of equal work: contiguous, complete, non-empty, and better balanced than equal thickness."""
+    cost = [0.1] * 100 + [1.0] * 300 + [0.1] * 112                 # end slices nearly free, as at wide cone angles
+    for ws in (1, 2, 3, 4, 8):
+        parts = mdist.balanced_split(cost, ws)
+        assert parts[0][0] == 0 and parts[-1][1] == len(cost)
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:])) and all(hi > lo for lo, hi in parts)
+        load = [sum(cost[lo:hi]) for lo, hi in parts]
+        even = [sum(cost[slice(*mdist.split_range(len(cost), ws, r))]) for r in range(ws)]
+        assert max(load) <= max(even) + 1e-9
+        assert max(load) <= 1.05 * sum(cost) / ws + 1.0
+        aligned = mdist.balanced_split(cost, ws, align=16)
+        assert aligned[0][0] == 0 and aligned[-1][1] == len(cost) and all(hi > lo for lo, hi in aligned)
+        assert all(lo % 16 == 0 for lo, _ in aligned)
+    assert mdist.balanced_split([1, 1, 1], 5)[-1][1] == 3          # fewer items than ranks: some pieces are empty
+    assert [hi - lo for lo, hi in mdist.balanced_split([0, 0, 0, 0], 2)] == [1, 3]
+    assert mdist.balanced_split([5, 0, 0, 0, 0, 0, 0, 5], 4) == [(0, 1), (1, 2), (2, 7), (7, 8)]
+
+
+def test_fdk_slice_cost_matches_the_oracle_geometry():
+    """the sampled on-detector fraction per slice agrees with a direct count using the projection
+    formulas of recon/bp3d20.cpp:99-116"""
+    from monte_b200 import _abi
+    g = _abi.generic_fdk_geom(90, 96, 40, 48)
+    c = mdist.fdk_slice_cost(g, overhead=0.0, stride=1)
+    X = (g.x0 + g.vox * np.arange(g.nx))[None, :, None]
+    Y = (g.y0 - g.vox * np.arange(g.ny))[:, None, None]
+    b = np.deg2rad(g.angle0_deg + g.angle_step_deg * np.arange(g.n_views))[None, None, :]
+    k = g.dsd / (X * np.cos(b) + Y * np.sin(b) + g.dso)
+    u_ok = np.abs(k * (-X * np.sin(b) + Y * np.cos(b))) <= g.half_u
+    for z in (0, 5, 24, 47):
+        Z = g.z0 - g.vox * z
+        assert abs(c[z] - np.mean(u_ok & (np.abs(k * Z) <= g.half_v))) < 1e-12
+    assert c[24] > c[0]                                            # central slices see the detector more often

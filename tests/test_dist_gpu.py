@@ -46,6 +46,16 @@ mdist.fdk_sharded_pipelined(lambda a, b: api.fdk_filter_dev(fg, proj, filt, a, b
                             filt, fg.n_views, fg.nv, fg.nz)
 torch.cuda.synchronize()
 assert torch.equal(slab, slab2), "pipelined exchange differs from gather-then-backproject"
+# z-slabs of equal work (uneven thickness): same voxels
+zr = mdist.balanced_split(mdist.fdk_slice_cost(fg), ws, 8)
+slab3 = torch.empty((zr[rank][1] - zr[rank][0], fg.ny, fg.nx), device=dev)
+filt.zero_()
+mdist.fdk_sharded_pipelined(lambda a, b: api.fdk_filter_dev(fg, proj, filt, a, b, pad=False),
+                            lambda a, b: api.fdk_pad_views_dev(fg, filt, a, b),
+                            lambda z0, z1, a, b, cont: api.fdk_backproject_views_dev(fg, filt, slab3, z0, z1, a, b, cont),
+                            filt, fg.n_views, fg.nv, fg.nz, z_ranges=zr)
+torch.cuda.synchronize()
+np.savez(os.path.join(out, "u%%d.npz" %% rank), slab=slab3.cpu().numpy(), z=np.array(zr[rank]))
 np.savez(os.path.join(out, "r%%d.npz" %% rank), im0=im0.cpu().numpy(), im5=im5.cpu().numpy(), slab=slab2.cpu().numpy(), z=np.array([z_lo, z_hi]))
 dist.barrier(); dist.destroy_process_group()
 '''
@@ -72,3 +82,6 @@ def test_two_gpus_equal_one(monte, tmp_path):
     _, vol, _, _ = monte.fdk(fg, proj, want_filtered=False)
     for p in parts:
         assert np.array_equal(p["slab"], vol[p["z"][0]:p["z"][1]])
+    for r in range(2):                           # the equal-work partition reconstructs the same voxels
+        u = np.load(os.path.join(str(tmp_path), "u%d.npz" % r))
+        assert np.array_equal(u["slab"], vol[u["z"][0]:u["z"][1]])
