@@ -145,6 +145,33 @@ def cpu_fdk_sample(ob, z_slices=2, seed=0):
     return g.nx * g.ny * z_slices * g.n_views, dt
 
 
+def as_shipped_reference(ob):
+    """The UNMODIFIED reference programs (oracle/_ref, compiled from /root/reference's own sources by
+    oracle/Makefile) timed as whole programs on one core, where they can express a workload at all:
+    CBCT_real2 = 1e7 histories of one pencil through the 65^3-scale sphere phantom (scatter tally only),
+    bp3d20 = 65x65x360 projections -> 5 columns of a 256^3 volume.  SURVEY 8(d) item (1)."""
+    out = {}
+    try:
+        if ob.have_ref("CBCT_real2") and ob.have_ref("make_image01"):
+            t = time.perf_counter()
+            _, c, _ = ob.ref_cbct_real2()
+            dt = time.perf_counter() - t
+            out["mc"] = {"value": 1e7 / dt, "unit": "histories/s", "cores": 1, "kind": "reference",
+                         "sample": "unmodified monte_cpp/CBCT_real2.cpp binary, as shipped: 1e7 histories, one pixel, one view, "
+                                   "whole program in %.1f s (count = %d detected scatters)" % (dt, c["count"])}
+        if ob.have_ref("bp3d20"):
+            p = np.random.default_rng(0).random((360, 65, 65), dtype=np.float32)
+            t = time.perf_counter()
+            ob.ref_bp3d20(p)
+            dt = time.perf_counter() - t
+            out["fdk"] = {"value": 256 * 256 * 5 * 360 / dt / 1e9, "unit": "GUPS", "cores": 1, "kind": "reference",
+                          "sample": "unmodified recon/bp3d20.cpp binary, as shipped: 65x65x360 -> 256x256x5 voxel columns, "
+                                    "whole program incl. filter and raw-file I/O in %.1f s" % dt}
+    except Exception as ex:                                  # the binaries are optional evidence, never a reason to fail the bench
+        out["error"] = repr(ex)[:200]
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -174,6 +201,9 @@ def run_reference(args):
                                  "sample": "C3 geometry, backprojection of 2 central z-slices from 720 views (%.3g updates)" % upd},
                 "e2e": {"value": upd / dtf / 1e9, "unit": "GUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
     }
+    shipped = as_shipped_reference(ob)
+    if shipped:
+        line["as_shipped"] = shipped
     print(json.dumps(line))
 
 
@@ -320,6 +350,9 @@ def main():
         n, dt, _ = cpu_mc_sample(ob, 400)
         mc_cpu = {"value": n / dt, "unit": "histories/s", "cores": os.cpu_count(), "kind": "port",
                   "sample": "C2 scene, view 0, 400 photons/pixel = %d histories in %.1f s (oracle: double, MT19937, OpenMP over detector rows)" % (n, dt)}
+        shipped = as_shipped_reference(ob)                   # the unmodified reference programs, one core, as shipped
+        if "mc" in shipped:
+            mc_cpu["as_shipped"] = shipped["mc"]
 
     # ------------------------------------------------------------------ FDK, config 3
     fdk = None
@@ -348,6 +381,8 @@ def main():
             "wall_s_timed_region": t_wall,
             "fdk": fdk,
         }
+        if mc_cpu is not None and fdk and fdk.get("cpu_baseline") and "fdk" in shipped:
+            fdk["cpu_baseline"]["as_shipped"] = shipped["fdk"]
         if args.path == "fdk" and fdk and "value" in fdk:      # FDK as the top-level line, MC nested
             top = dict(fdk)
             mc = {k: line[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "roofline", "cpu_baseline", "config", "gpu_launches")}

@@ -252,8 +252,17 @@ def ref_cbct_real2(timeout=600):
     tmp = tempfile.mkdtemp(prefix="monte_refmc_")
     try:
         subprocess.check_call([os.path.join(REF_DIR, "make_image01")], cwd=tmp)
-        for fn in ("xcom2.csv", "Ca.csv"):
-            shutil.copy(os.path.join(REFERENCE_ROOT, "monte_cpp", fn), os.path.join(tmp, fn))
+        for fn, key in (("xcom2.csv", "h2o"), ("Ca.csv", "ca")):
+            src = os.path.join(REFERENCE_ROOT, "monte_cpp", fn)
+            if os.path.exists(src):
+                shutil.copy(src, os.path.join(tmp, fn))
+            else:
+                # no reference tree (GPU box): rewrite the CSV from the packed copy of the same tables
+                # (scripts/make_xs_tables.py); %.17g round-trips every double, and the reader overwrites
+                # the first field of row 1 anyway (CBCT_real2.cpp:663), so the binary computes the same
+                t = np.load(os.path.join(os.path.dirname(HERE), "monte_b200", "data", "xs_tables.npz"))[key]
+                with open(os.path.join(tmp, fn), "w") as f:
+                    f.write("\n".join("%.17g,%.17g,%.17g,%.17g" % tuple(t[:, k]) for k in range(1, 201)))
         rows = "\n".join("%g,%g,%g,%g" % (1.0, 1.0, 1.0, (i + 1) / 250.0) for i in range(250))
         for fn in ("125kv_al2mm.csv", "125kv_al10mm.csv"):
             with open(os.path.join(tmp, fn), "w") as f:
