@@ -230,8 +230,10 @@ __global__ void fdk_pad_kernel(float *f, int rows, int nu, int pitch, int r0, in
     for (int c = nu + 1; c < pitch; c++) row[c] = 0.f;
 }
 
-// pairs[r][c] = { f[r][c], f[r+1][c] }: the two rows a bilinear fetch needs sit in one aligned 8-byte
-// element, so a voxel update issues 2 x LDG.64 instead of 4 x LDG.32 (the gathers were LSU-issue bound)
+// pairs[r][c] = { f[r][c], f[r+1][c] - f[r][c] }: the two rows a bilinear fetch needs sit in one aligned
+// 8-byte element, so a voxel update issues 2 x LDG.64 instead of 4 x LDG.32 (the gathers were LSU-issue
+// bound), and the row difference the interpolation starts with (same fp32 subtraction, same rounding as
+// in the hot loop before) is taken once per texel here instead of once per voxel update there
 // Only rows [b_lo, b_hi) of every view are paired: the band a z-slab projects onto (all rows for a
 // whole-volume call, ~1/N of them for one of N multi-GPU slabs).
 __global__ void fdk_pair_kernel(const float *__restrict__ f, float2 *__restrict__ pairs, int view_lo, int nv, int b_lo, int b_hi,
@@ -241,7 +243,7 @@ __global__ void fdk_pair_kernel(const float *__restrict__ f, float2 *__restrict_
     if (c >= pitch || (int)blockIdx.x >= b_hi - b_lo || r >= rows_total) return;
     const float a = f[(size_t)r * pitch + c];
     const float b = r + 1 < rows_total ? f[(size_t)(r + 1) * pitch + c] : 0.f;
-    pairs[(size_t)r * pitch + c] = make_float2(a, b);
+    pairs[(size_t)r * pitch + c] = make_float2(a, b - a);
 }
 
 __global__ void fdk_unpad_kernel(const float *f, float *dense, size_t rows, int nu, int pitch) {
@@ -401,7 +403,11 @@ fdk_backproject_kernel(const __grid_constant__ BpParams p) {
         // IMAD.WIDE per update instead of 64-bit add/shift chains on the ALU pipe
         const float *__restrict__ fv = p.filt + (size_t)v * p.nv * p.pitch;
         const float2 *__restrict__ fp = p.pairs + (size_t)v * p.nv * p.pitch;
-        const unsigned upitch = (unsigned)p.pitch, uyi = (unsigned)yi;
+        // column yi of this view's rows as one opaque 64-bit value: otherwise the compiler keeps the
+        // warp-uniform view base apart and re-adds it for every slice (IADD3 + IADD3.X per update)
+        unsigned long long fcol = reinterpret_cast<unsigned long long>(fp + yi);
+        asm volatile("" : "+l"(fcol));
+        const unsigned pitch_bytes = (unsigned)p.pitch * (unsigned)sizeof(float2);
         const float kz = k * p.inv_dv;
         const float kzv = kz * p.vox, kv = k * p.vox;            // per-slice increments of x and w
         const float x0v = fmaf(-kz, Z0, xoff), w0v = k * Z0;
@@ -417,17 +423,19 @@ fdk_backproject_kernel(const __grid_constant__ BpParams p) {
                 float fx[ZB], va[ZB], vb[ZB], vc2[ZB], vd[ZB];
 #pragma unroll
                 for (int i = 0; i < ZB; i++) {
-                    const float x = fmaxf(fmaf(kzv, (float)(h + i), x0v), 0.f);   // >= -ulp by construction
+                    // x >= -ulp by construction; truncation maps that to row 0 with fx = -ulp
+                    const float x = fmaf(kzv, (float)(h + i), x0v);
                     const int xi = (int)x;
                     fx[i] = x - (float)xi;
-                    const float2 *__restrict__ q = fp + ((unsigned)xi * upitch + uyi);
+                    // one IMAD.WIDE: 64-bit (warp-uniform row base + column) + xi * row pitch in bytes
+                    const float2 *__restrict__ q = reinterpret_cast<const float2 *>(fcol + (unsigned long long)(unsigned)xi * pitch_bytes);
                     const float2 p0 = __ldg(q), p1 = __ldg(q + 1);
                     va[i] = p0.x; vc2[i] = p0.y; vb[i] = p1.x; vd[i] = p1.y;
                 }
 #pragma unroll
                 for (int i = 0; i < ZB; i++) {
-                    const float lo = fmaf(fx[i], vc2[i] - va[i], va[i]);      // (1-fx)*a + fx*c
-                    const float hi = fmaf(fx[i], vd[i] - vb[i], vb[i]);
+                    const float lo = fmaf(fx[i], vc2[i], va[i]);              // a + fx*(c-a)
+                    const float hi = fmaf(fx[i], vd[i], vb[i]);
                     acc[h + i] = fmaf(wgt, fmaf(fy, hi - lo, lo), acc[h + i]);
                 }
             }
@@ -448,14 +456,14 @@ fdk_backproject_kernel(const __grid_constant__ BpParams p) {
                 x = fminf(fmaxf(x, 0.f), nvf);
                 const int xi = (int)x;
                 fx[i] = x - (float)xi;
-                const float2 *__restrict__ q = fp + ((unsigned)xi * upitch + uyi);
+                const float2 *__restrict__ q = reinterpret_cast<const float2 *>(fcol + (unsigned long long)(unsigned)xi * pitch_bytes);
                 const float2 p0 = __ldg(q), p1 = __ldg(q + 1);
                 va[i] = p0.x; vc2[i] = p0.y; vb[i] = p1.x; vd[i] = p1.y;
             }
 #pragma unroll
             for (int i = 0; i < ZB; i++) {
-                const float lo = fmaf(fx[i], vc2[i] - va[i], va[i]);
-                const float hi = fmaf(fx[i], vd[i] - vb[i], vb[i]);
+                const float lo = fmaf(fx[i], vc2[i], va[i]);
+                const float hi = fmaf(fx[i], vd[i], vb[i]);
                 const float val = fmaf(fy, hi - lo, lo);
                 acc[h + i] = fmaf(ok[i] ? wgt : 0.f, val, acc[h + i]);
             }
