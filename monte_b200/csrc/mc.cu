@@ -110,7 +110,7 @@ enum : uint32_t { P_REFILL = 1u, P_STEP = 2u, P_COLLIDE = 4u, P_COMPTON = 8u };
 enum { G_POS = 0, G_DIR = 1, G_ID = 2, G_REC = 3 };
 constexpr int mc_slot_groups(bool record) { return record ? 4 : 3; }
 
-template <bool RECORD, int K, int MINB = 3>
+template <bool RECORD, int K, int MINB = 3, int NSTEP = 2>
 __global__ void __launch_bounds__(MC_THREADS, MINB)
 mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
     extern __shared__ float4 s_mem[];
@@ -174,46 +174,78 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
 
         if (phase == P_STEP) {
             if (!active) continue;
-            // ---------------- one Woodcock step, CBCT_real325im.cu:886-968 ---------------
-            const uint4 id = GRP(G_ID);
-            float4 pos = *reinterpret_cast<float4 *>(&GRP(G_POS));
-            const float4 dir = *reinterpret_cast<float4 *>(&GRP(G_DIR));
-            const uint32_t c0 = id.x, meta = id.y, ctr = id.z;
-            const int kE = meta & 0xFF;
-            const uint2 r = philox2x32_10(c0, (meta & 0xFF000000u) | (STREAM_FLIGHT << 22) | (ctr & 0xFFFFFu), P.key);
-            WORD(G_ID, 2) = (ctr & 0xFFF00000u) | ((ctr + 1u) & 0xFFFFFu);
-            const float s = -__logf(u01(r.x)) * s_inv[kE];
-            pos.x = fmaf(s, dir.x, pos.x); pos.y = fmaf(s, dir.y, pos.y); pos.z = fmaf(s, dir.z, pos.z);
-            *reinterpret_cast<float4 *>(&GRP(G_POS)) = pos;
-            c_steps++;
-            const bool inside = pos.x >= sc.clip_lo[0] && pos.x < sc.clip_hi[0] && pos.y >= sc.clip_lo[1] && pos.y < sc.clip_hi[1] &&
-                                pos.z >= sc.clip_lo[2] && pos.z < sc.clip_hi[2];
-            if (!inside) {                       // left the volume: only air ahead
-                if ((meta & 0xF00u) == 0u) {     // unscattered: lands in the pixel it was aimed at (:567-590)
-                    const uint32_t pvw = id.w;
-                    const uint32_t pva = (pvw >> 20) * npix + (pvw & 0xFFFFFu);
-                    if (pva != cur_pv) {
-                        if (prim_cnt) { atomicAdd(P.image0 + cur_pv, (int)prim_cnt); atomicAdd(P.image5 + cur_pv, (int)prim_cnt); }
-                        cur_pv = pva; prim_cnt = 0;
-                    }
-                    prim_cnt++; c_prim++;
-                    e_prim += (unsigned long long)(pos.w * 1024.f + 0.5f);
-                    if (RECORD) { P.fates[WORD(G_REC, 0)] = 1u | ((pvw & 0xFFFFFu) << 8); P.fate_e[WORD(G_REC, 0)] = pos.w; }
-                } else WORD(G_ID, 1) = meta | 0x8000u;     // scatter detection runs with the refill phase
-                st = (st & clr) | (P_REFILL << (4 * j));
-                continue;
+            // ---------------- Woodcock steps, CBCT_real325im.cu:886-968 ---------------
+            // Two slots of the lane are advanced per visit when it has two waiting (the second one is
+            // predicated off otherwise): the two Philox chains and the two label fetches are independent,
+            // so they overlap instead of each stalling the warp on its own fixed-latency chain ("wait" was
+            // the top stall reason), and the vote / dispatch overhead per step drops.  Measured at C2:
+            // one slot 8.52 ms, two 8.25 ms, three 9.05 ms per 1e8 histories.
+            constexpr int NS = NSTEP;                              // slots advanced per visit
+            bool en2[NS]; int jj[NS]; uint4 *sl[NS];
+            {
+                uint32_t rest = mine;
+#pragma unroll
+                for (int q = 0; q < NS; q++) {
+                    en2[q] = rest != 0u;
+                    jj[q] = rest ? ((__ffs(rest) - 1) >> 2) : j;
+                    sl[q] = s_slots + jj[q] * 32 + lane;
+                    rest &= rest - 1u;
+                }
             }
-            int ix = __float_as_int(fmaf(pos.x, sc.inv_pitch, vox_off[0]) + 12582912.0f) - 0x4B400000;
-            int iy = __float_as_int(fmaf(pos.y, sc.inv_pitch, vox_off[1]) + 12582912.0f) - 0x4B400000;
-            int iz = __float_as_int(fmaf(pos.z, sc.inv_pitch, vox_off[2]) + 12582912.0f) - 0x4B400000;
-            ix = (int)min((unsigned)ix, (unsigned)(sc.nx - 1)); iy = (int)min((unsigned)iy, (unsigned)(sc.ny - 1));
-            iz = (int)min((unsigned)iz, (unsigned)(sc.nz - 1));     // safety only: the clip box lies inside the volume
-            const int lab = __ldg(sc.labels + ((unsigned)(iz * sc.ny + iy) * (unsigned)sc.nx + (unsigned)ix));
-            if (lab == 0) continue;                                   // air: virtual collision
-            const int mat = min(lab, sc.n_mat) - 1;
-            if (u01(r.y) > s_tab[mat * TAB_ROWS + kE].x) continue;    // virtual collision, :941-961
-            WORD(G_ID, 1) = (meta & ~0x7000u) | ((uint32_t)mat << 12);
-            st = (st & clr) | (P_COLLIDE << (4 * j));
+            uint4 id2[NS]; float4 pos2[NS]; uint2 r2[NS]; bool inside2[NS]; int lab2[NS];
+#pragma unroll
+            for (int q = 0; q < NS; q++) {
+                id2[q] = sl[q][G_ID * GSTRIDE];
+                pos2[q] = *reinterpret_cast<float4 *>(&sl[q][G_POS * GSTRIDE]);
+            }
+#pragma unroll
+            for (int q = 0; q < NS; q++)
+                r2[q] = philox2x32_10(id2[q].x, (id2[q].y & 0xFF000000u) | (STREAM_FLIGHT << 22) | (id2[q].z & 0xFFFFFu), P.key);
+#pragma unroll
+            for (int q = 0; q < NS; q++) {
+                const float4 dir = *reinterpret_cast<float4 *>(&sl[q][G_DIR * GSTRIDE]);
+                const float sp = -__logf(u01(r2[q].x)) * s_inv[id2[q].y & 0xFF];
+                pos2[q].x = fmaf(sp, dir.x, pos2[q].x); pos2[q].y = fmaf(sp, dir.y, pos2[q].y); pos2[q].z = fmaf(sp, dir.z, pos2[q].z);
+                inside2[q] = pos2[q].x >= sc.clip_lo[0] && pos2[q].x < sc.clip_hi[0] && pos2[q].y >= sc.clip_lo[1] && pos2[q].y < sc.clip_hi[1] &&
+                             pos2[q].z >= sc.clip_lo[2] && pos2[q].z < sc.clip_hi[2];
+                int ix = __float_as_int(fmaf(pos2[q].x, sc.inv_pitch, vox_off[0]) + 12582912.0f) - 0x4B400000;
+                int iy = __float_as_int(fmaf(pos2[q].y, sc.inv_pitch, vox_off[1]) + 12582912.0f) - 0x4B400000;
+                int iz = __float_as_int(fmaf(pos2[q].z, sc.inv_pitch, vox_off[2]) + 12582912.0f) - 0x4B400000;
+                ix = (int)min((unsigned)ix, (unsigned)(sc.nx - 1)); iy = (int)min((unsigned)iy, (unsigned)(sc.ny - 1));
+                iz = (int)min((unsigned)iz, (unsigned)(sc.nz - 1));     // safety only: the clip box lies inside the volume
+                lab2[q] = (en2[q] && inside2[q]) ? __ldg(sc.labels + ((unsigned)(iz * sc.ny + iy) * (unsigned)sc.nx + (unsigned)ix)) : 0;
+            }
+#pragma unroll
+            for (int q = 0; q < NS; q++) {
+                if (!en2[q]) continue;
+                uint4 *slot = sl[q];                               // GRP/WORD below refer to this slot
+                const uint32_t meta = id2[q].y, ctr = id2[q].z;
+                const uint32_t clrq = ~(0xFu << (4 * jj[q]));
+                const int kE = meta & 0xFF;
+                WORD(G_ID, 2) = (ctr & 0xFFF00000u) | ((ctr + 1u) & 0xFFFFFu);
+                *reinterpret_cast<float4 *>(&GRP(G_POS)) = pos2[q];
+                c_steps++;
+                if (!inside2[q]) {                   // left the volume: only air ahead
+                    if ((meta & 0xF00u) == 0u) {     // unscattered: lands in the pixel it was aimed at (:567-590)
+                        const uint32_t pvw = id2[q].w;
+                        const uint32_t pva = (pvw >> 20) * npix + (pvw & 0xFFFFFu);
+                        if (pva != cur_pv) {
+                            if (prim_cnt) { atomicAdd(P.image0 + cur_pv, (int)prim_cnt); atomicAdd(P.image5 + cur_pv, (int)prim_cnt); }
+                            cur_pv = pva; prim_cnt = 0;
+                        }
+                        prim_cnt++; c_prim++;
+                        e_prim += (unsigned long long)(pos2[q].w * 1024.f + 0.5f);
+                        if (RECORD) { P.fates[WORD(G_REC, 0)] = 1u | ((pvw & 0xFFFFFu) << 8); P.fate_e[WORD(G_REC, 0)] = pos2[q].w; }
+                    } else WORD(G_ID, 1) = meta | 0x8000u;     // scatter detection runs with the refill phase
+                    st = (st & clrq) | (P_REFILL << (4 * jj[q]));
+                    continue;
+                }
+                if (lab2[q] == 0) continue;                               // air: virtual collision
+                const int mat = min(lab2[q], sc.n_mat) - 1;
+                if (u01(r2[q].y) > s_tab[mat * TAB_ROWS + kE].x) continue;    // virtual collision, :941-961
+                WORD(G_ID, 1) = (meta & ~0x7000u) | ((uint32_t)mat << 12);
+                st = (st & clrq) | (P_COLLIDE << (4 * jj[q]));
+            }
             continue;
         }
 
@@ -659,6 +691,8 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
         case 88: fn = (const void *)mc_transport_kernel_v3<false, 4, 4>; break;    // which=44: K=4, 4 CTAs/SM (64 regs)
         case 86: fn = (const void *)mc_transport_kernel_v3<false, 3, 4>; break;    // which=43
         case 73: fn = (const void *)mc_transport_kernel_v3<true, 6>; break;
+        case 90: fn = (const void *)mc_transport_kernel_v3<false, 5, 3, 1>; break;   // which=45: one slot per STEP visit
+        case 92: fn = (const void *)mc_transport_kernel_v3<false, 5, 3, 3>; break;   // which=46: three slots per STEP visit
         default: fn = rec ? (const void *)mc_transport_kernel_v3<true, 5> : (const void *)mc_transport_kernel_v3<false, 5>; break;
     }
     static int occ[96] = {0};                      // resident CTAs per SM: persistent grid = SMs x occupancy
