@@ -308,6 +308,9 @@ void monte_make_sphere(uint8_t *g, int nx, int ny, int nz, int cx, int cy, int c
  * mu_water(E)*(1+HU/1000) and a label segmentation by HU thresholds.                   */
 int monte_ctnum_to_mu(const float *hu, size_t n, const monte_mc_xs *xs, double keV,
                       float hu_air_max, float hu_bone_min, float *mu, uint8_t *labels);
+/* per-keV Woodcock majorant (1/cm) over the materials that occur in `labels` (NULL: all materials):
+ * the max of CBCT_real325im.cu:866 restricted to what the volume contains; mu_max[201].               */
+int monte_xs_majorant(const monte_mc_xs *xs, const uint8_t *labels, size_t n, float *mu_max);
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,7 @@ def load():
         "monte_make_fantom": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
         "monte_make_sphere": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
         "monte_ctnum_to_mu": (C.c_int, [vp, sz, C.POINTER(McXs), C.c_double, C.c_float, C.c_float, vp, vp]),
+        "monte_xs_majorant": (C.c_int, [C.POINTER(McXs), vp, sz, vp]),
     }
     missing = []
     for name, (res, args) in proto.items():

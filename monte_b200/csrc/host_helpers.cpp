@@ -132,4 +132,30 @@ int monte_ctnum_to_mu(const float *hu, size_t n, const monte_mc_xs *xs, double k
     return MONTE_OK;
 }
 
+/* Woodcock majorant per keV: max over the materials (labels 1..n_materials) that occur in `labels`
+ * (all materials if labels is NULL) of total[m][k]*density[m] -- CBCT_real325im.cu:866 takes the max over
+ * every table it loaded; restricting it to the materials present is what makes a calcium-free volume
+ * cheap to track.  mu_max[k], k = 0..200, in 1/cm.                                                     */
+int monte_xs_majorant(const monte_mc_xs *xs, const uint8_t *labels, size_t n, float *mu_max) {
+    if (!xs || !mu_max || xs->n_materials < 1 || xs->n_materials > MONTE_MC_MAX_MATERIALS) {
+        monte::set_error("monte_xs_majorant: bad argument");
+        return MONTE_E_ARG;
+    }
+    bool present[MONTE_MC_MAX_MATERIALS];
+    for (int m = 0; m < MONTE_MC_MAX_MATERIALS; m++) present[m] = labels == nullptr;
+    for (size_t i = 0; labels && i < n; i++) {
+        int l = labels[i];
+        if (l == 0) continue;
+        if (l > xs->n_materials) l = xs->n_materials;          // same clamp as the transport kernel
+        present[l - 1] = true;
+    }
+    for (int k = 0; k < MONTE_MC_TABLE_ROWS; k++) {
+        float mx = 0.f;
+        for (int m = 0; m < xs->n_materials; m++)
+            if (present[m]) { const float v = xs->total[m][k] * xs->density[m]; if (v > mx) mx = v; }
+        mu_max[k] = mx;
+    }
+    return MONTE_OK;
+}
+
 }  // extern "C"

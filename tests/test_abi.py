@@ -125,6 +125,15 @@ def test_host_helpers(lib):
                                  C.c_void_p(mu.ctypes.data), C.c_void_p(lab.ctypes.data)) == 0
     assert mu[0] == 0 and abs(mu[1] - 0.1538092) < 1e-6 and abs(mu[2] - 2 * 0.1538092) < 1e-6
     assert list(lab) == [0, 1, 2, 2]
+    # per-keV majorant over the materials present (CBCT_real325im.cu:866 restricted to the volume's labels)
+    mm = np.zeros(201, np.float32)
+    assert lib.monte_xs_majorant(C.byref(xs2), lab.ctypes.data, 4, mm.ctypes.data) == 0
+    assert abs(mm[140] - 0.17730 * 1.55) < 1e-4                    # calcium sets it
+    water_only = np.array([0, 1, 1, 0], np.uint8)
+    assert lib.monte_xs_majorant(C.byref(xs2), water_only.ctypes.data, 4, mm.ctypes.data) == 0
+    assert abs(mm[140] - 0.1538092) < 1e-6
+    assert lib.monte_xs_majorant(C.byref(xs2), None, 0, mm.ctypes.data) == 0 and abs(mm[60] - max(0.20585, xs2.total[1][60] * 1.55)) < 1e-4
+    assert lib.monte_xs_majorant(None, None, 0, mm.ctypes.data) == -1
 
 
 def test_fft_core_on_the_host(tmp_path):
