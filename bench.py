@@ -398,20 +398,26 @@ def bench_fdk(args, api, mdist, torch, dist, dev, ws, rank, pk, flush, barrier):
     Kf, Wf = max(args.fdk_steps, 1), 3
     v_lo, v_hi = split_range(g.n_views, ws, rank)
     # z-slabs of equal WORK, not equal thickness: at this cone angle the end slices see the detector in
-    # few views or none (cuts snapped to the backprojector's 16-slice blocks)
-    z_ranges = mdist.balanced_split(mdist.fdk_slice_cost(g), ws, 16)
-    z_lo, z_hi = z_ranges[rank]
+    # few views or none (cuts on the backprojector's 16-slice blocks; a rank may own several ranges)
+    z_ranges = mdist.fdk_z_partition(g, ws)
+    my_z = z_ranges[rank]
+    n_my = sum(b - a for a, b in my_z)
     gen = torch.Generator(device=dev).manual_seed(1234)
     proj = torch.rand((g.n_views, g.nu, g.nv), device=dev, generator=gen)     # same on every rank
     filt = torch.zeros(api.fdk_filtered_shape(g), device=dev)
-    slab = torch.empty((z_hi - z_lo, g.ny, g.nx), device=dev)
+    slab = torch.empty((n_my, g.ny, g.nx), device=dev)      # this rank's ranges, stacked in ascending z
+    z_off, o = {}, 0
+    for a, b in my_z:
+        z_off[a] = o
+        o += b - a
 
     def sharded(src):
         # filter own views | broadcast the view pieces in ascending order (async, NCCL stream) |
         # backproject piece r as soon as pieces r and r+1 have landed, continuing the partial sums
         mdist.fdk_sharded_pipelined(lambda a, b: api.fdk_filter_dev(g, src, filt, a, b, pad=False),
                                     lambda a, b: api.fdk_pad_views_dev(g, filt, a, b),
-                                    lambda z0, z1, a, b, cont: api.fdk_backproject_views_dev(g, filt, slab, z0, z1, a, b, cont),
+                                    lambda z0, z1, a, b, cont: api.fdk_backproject_views_dev(
+                                        g, filt, slab[z_off[z0]:z_off[z0] + z1 - z0], z0, z1, a, b, cont),
                                     filt, g.n_views, g.nv, g.nz, z_ranges=z_ranges)
 
     def fdk_step():
@@ -436,7 +442,8 @@ def bench_fdk(args, api, mdist, torch, dist, dev, ws, rank, pk, flush, barrier):
     e[0].record()
     api.fdk_filter_dev(g, proj, filt, v_lo, v_hi, pad=False)
     e[1].record()
-    api.fdk_backproject_dev(g, filt, slab, z_lo, z_hi)
+    for a, b in my_z:
+        api.fdk_backproject_dev(g, filt, slab[z_off[a]:z_off[a] + b - a], a, b)
     e[2].record()
     torch.cuda.synchronize()
     t_filter, t_bp = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
@@ -445,14 +452,15 @@ def bench_fdk(args, api, mdist, torch, dist, dev, ws, rank, pk, flush, barrier):
     tot = mdist.max_over_ranks(tot, dev)
     updates = g.nx * g.ny * g.nz * g.n_views
     gups = updates * Kf / (tot * 1e-3) / 1e9
-    upd_rank = g.nx * g.ny * (z_hi - z_lo) * g.n_views
+    upd_rank = g.nx * g.ny * n_my * g.n_views
     # (voxel, view) pairs that project onto the detector (the others are skipped, as in bp3d20.cpp:116):
     # Monte-Carlo estimate with the reference's projection formulas, 2e6 samples of this rank's slab
     rs = np.random.default_rng(7)
     ns = 2_000_000
     sx = g.x0 + g.vox * rs.integers(0, g.nx, ns)
     sy = g.y0 - g.vox * rs.integers(0, g.ny, ns)
-    sz = g.z0 - g.vox * rs.integers(z_lo, z_hi, ns)
+    my_slices = np.concatenate([np.arange(a, b) for a, b in my_z])
+    sz = g.z0 - g.vox * rs.choice(my_slices, ns)
     beta = np.deg2rad(g.angle0_deg + g.angle_step_deg * rs.integers(0, g.n_views, ns))
     kk = g.dsd / (sx * np.cos(beta) + sy * np.sin(beta) + g.dso)
     inside = float(np.mean((np.abs(kk * (-sx * np.sin(beta) + sy * np.cos(beta))) <= g.half_u) & (np.abs(kk * sz) <= g.half_v)))
@@ -463,13 +471,13 @@ def bench_fdk(args, api, mdist, torch, dist, dev, ws, rank, pk, flush, barrier):
             "model": "%d lane-instr per voxel-update (SURVEY 8d) x %.4g updates per launch x %.3f of them on the detector "
                      "(off-detector pairs are skipped per column, as the reference skips them per voxel)" % (FDK_INSTR_PER_UPDATE, upd_rank, inside),
             "on_detector_fraction": inside,
-            "hbm": {"algorithmic_bytes": 4 * g.nx * g.ny * (z_hi - z_lo) + 4 * g.n_views * g.nu * g.nv,
-                    "achieved_gbs": (4 * g.nx * g.ny * (z_hi - z_lo) + 4 * g.n_views * g.nu * g.nv) / (t_bp * 1e-3) / 1e9,
+            "hbm": {"algorithmic_bytes": 4 * g.nx * g.ny * n_my + 4 * g.n_views * g.nu * g.nv,
+                    "achieved_gbs": (4 * g.nx * g.ny * n_my + 4 * g.n_views * g.nu * g.nv) / (t_bp * 1e-3) / 1e9,
                     "peak_gbs": pk["hbm_gbs"], "note": "projections are read once from HBM and re-read from L1/L2; not HBM-bound"}}
 
     # e2e through the C ABI with pinned host buffers (N=1), or H2D views + sharded pipeline + D2H slab (N>1)
     host_proj = torch.rand((g.n_views, g.nu, g.nv)).pin_memory() if ws == 1 else torch.rand((v_hi - v_lo, g.nu, g.nv)).pin_memory()
-    host_vol = torch.empty((z_hi - z_lo, g.ny, g.nx)).pin_memory()
+    host_vol = torch.empty((n_my, g.ny, g.nx)).pin_memory()
     del proj
     if ws > 1:
         proj_part = torch.empty((g.n_views, g.nu, g.nv), device=dev)
@@ -505,7 +513,7 @@ def bench_fdk(args, api, mdist, torch, dist, dev, ws, rank, pk, flush, barrier):
             "ms_per_step": tot / Kf, "scaling": "strong", "dtype": "f32",
             "config": {"workload": "C3 (BASELINE configs[2]): 512^3 volume from 720 views of a 1024x768 detector, REFERENCE weights, "
                                    "weight+ramp filter + backprojection per step",
-                       "parallelism": "z-slabs of equal work x%d %s, filter by views, view pieces broadcast in order and overlapped with the backprojection" % (ws, [list(z) for z in z_ranges]) if ws > 1 else "single GPU",
+                       "parallelism": "z-ranges of equal work x%d %s, filter by views, view pieces broadcast in order and overlapped with the backprojection" % (ws, [[list(z) for z in zr] for zr in z_ranges]) if ws > 1 else "single GPU",
                        "l2": "256 MiB fill between steps; projections (2.26 GB) exceed L2"},
             "e2e": e2e, "gpu_launches": 3 * Kf, "roofline": roof, "cpu_baseline": cpu,
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},

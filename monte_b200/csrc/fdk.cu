@@ -274,6 +274,7 @@ struct BpParams {
     float wd, wd2;              // weight_dist and its square (REFERENCE)
     float out_fac;              // beta_span*2*pi/360 * out_scale*out_scale2 (REFERENCE) or 0.5*dbeta
     float eps_u, eps_v;         // half-widths of the bands re-evaluated in double
+    float kmin;                 // smallest magnification dsd / r_x any column of the ROI can have (0.99 x, for the z-block early-out)
     float eps_ts;               // |tmp_s| below this: its sign is re-evaluated in double
     int textbook, coord_mode;
     int mask_cs, mask_ct, mask_cz;
@@ -355,6 +356,12 @@ fdk_backproject_kernel(const __grid_constant__ BpParams p) {
     // identically however the volume is cut into slabs (multi-GPU slabs == single launch, bit for bit)
     const int zb = (p.z_lo / ZT) * ZT + blockIdx.z * ZT;
     if (s >= p.s_end || t >= p.t_end) return;
+    {
+        // z-block entirely above or below the detector even at the smallest magnification any column can
+        // have: no view contributes (bp3d20.cpp:116), the stored zeros / partial sums stay as they are
+        const float Za = fmaf(-p.vox, (float)zb, p.z0), Zb = fmaf(-p.vox, (float)(zb + ZT - 1), p.z0);
+        if (Za * Zb > 0.f && fminf(fabsf(Za), fabsf(Zb)) * p.kmin > p.half_v + 2.f * p.eps_v) return;
+    }
 
     const float X = fmaf(p.vox, (float)s, p.x0);
     const float Y = fmaf(-p.vox, (float)t, p.y0);
@@ -725,6 +732,10 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
     p.out_fac = (float)(textbook ? 0.5 * dbeta : dbeta * g->out_scale * g->out_scale2);
     p.eps_u = (float)(g->half_u * 2e-5); p.eps_v = (float)(g->half_v * 2e-5);
     p.eps_ts = (float)(2e-5 * (fabs(g->x0) + fabs(g->y0) + g->vox * (g->nx + g->ny)));
+    {   // farthest a voxel column can be from the rotation axis -> smallest magnification
+        const double ax = fmax(fabs(g->x0), fabs(g->x0 + g->vox * (g->nx - 1))), ay = fmax(fabs(g->y0), fabs(g->y0 - g->vox * (g->ny - 1)));
+        p.kmin = (float)(0.99 * g->dsd / (g->dso + sqrt(ax * ax + ay * ay)));
+    }
     p.textbook = textbook; p.coord_mode = g->coord_mode;
     p.mask_cs = g->mask_cs; p.mask_ct = g->mask_ct; p.mask_cz = g->mask_cz; p.mask_r2 = g->mask_r2;
     p.x0d = g->x0; p.y0d = g->y0; p.z0d = g->z0; p.voxd = g->vox; p.dsdd = g->dsd;
@@ -775,7 +786,9 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
         int b_lo = (int)floor(xmin) - 2, b_hi = (int)ceil(xmax) + 4;
         if (b_lo < 0) b_lo = 0;
         if (b_hi > g->nv) b_hi = g->nv;       // rows nv, nv+1 of a view are rows 0, 1 of the next one
-        if (b_hi <= b_lo) { b_lo = 0; b_hi = g->nv; }
+        // the whole slab projects above or below the detector in every view (bp3d20.cpp:116 skips every
+        // voxel of it): its voxels keep the zeros / partial sums they have
+        if (b_hi <= b_lo) return MONTE_OK;
         // rows 0..3 of every view are always paired too: they are what the previous view reaches past its end
         const int n_v = view_hi - view_lo + (view_hi < g->n_views ? 1 : 0);
         if (b_lo > 0) {

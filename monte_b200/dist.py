@@ -52,12 +52,65 @@ def balanced_split(cost, world, align=1):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
-def fdk_slice_cost(g, overhead=0.1, stride=8):
-    """Relative backprojection cost of every z-slice of the volume: the fraction of its (voxel, view)
-    pairs that project onto the detector (the others are skipped, recon/bp3d20.cpp:116) plus a constant
-    for the per-column work that is done regardless.  Sampled on a coarse (s, t, view) grid with the
-    reference's projection formulas (bp3d20.cpp:99-113); used to cut z-slabs of equal work, because at
-    wide cone angles the end slices see the detector in few views or none."""
+def balanced_blocks(cost, world, block=16):
+    """Partition range(len(cost)) into per-rank lists of ranges whose cuts all lie on multiples of `block`
+    (the backprojector's z-block: an unaligned cut makes both neighbours compute the straddled block).
+    With whole blocks as the unit a contiguous split cannot balance a volume whose end blocks are cheap
+    (off the detector) and whose middle blocks are expensive: the expensive zone is therefore split
+    contiguously and evenly, and the cheap blocks outside it are then handed, cheapest-loaded rank
+    first, to the ranks as a second range.  Returns [[(lo, hi), ...] per rank]; every slice is covered
+    exactly once."""
+    n = len(cost)
+    nb = (n + block - 1) // block
+    bc = [float(sum(cost[b * block:min((b + 1) * block, n)])) for b in range(nb)]
+    if nb <= world or max(bc) <= 0:
+        return [[r] if r[1] > r[0] else [] for r in balanced_split(cost, world, block)]
+    heavy = [b for b in range(nb) if bc[b] > 0.25 * max(bc)]
+    h0, h1 = heavy[0], heavy[-1] + 1                            # the expensive zone (contiguous by construction of the cost)
+    if h1 - h0 < world:
+        return [[r] if r[1] > r[0] else [] for r in balanced_split(cost, world, block)]
+    mid = balanced_split(bc[h0:h1], world)
+    parts = [[(h0 + a, h0 + b)] for a, b in mid]
+    load = [sum(bc[h0 + a:h0 + b]) for a, b in mid]
+    for b in sorted(list(range(0, h0)) + list(range(h1, nb)), key=lambda q: -bc[q]):
+        r = min(range(world), key=lambda q: load[q])
+        parts[r].append((b, b + 1))
+        load[r] += bc[b]
+    out = []
+    for pr in parts:
+        pr.sort()
+        merged = []
+        for a, b in pr:
+            if merged and merged[-1][1] == a:
+                merged[-1] = (merged[-1][0], b)
+            else:
+                merged.append((a, b))
+        out.append([(a * block, min(b * block, n)) for a, b in merged])
+    return out
+
+
+def fdk_z_partition(g, world_size, block=16, min_gain=0.03):
+    """z-ranges per rank for the sharded backprojection: the contiguous equal-work split, unless handing
+    the cheap end blocks out separately (balanced_blocks) lowers the slowest rank's load by > min_gain."""
+    cost = fdk_slice_cost(g)
+    contiguous = [[r] for r in balanced_split(cost, world_size, block)]
+    blocks = balanced_blocks(cost, world_size, block)
+
+    def worst(parts):
+        return max(sum(float(cost[a:b].sum()) for a, b in pr) for pr in parts)
+    return blocks if worst(blocks) < (1.0 - min_gain) * worst(contiguous) else contiguous
+
+
+def fdk_slice_cost(g, overhead=0.32, partial_penalty=0.45, stride=8):
+    """Relative backprojection cost of every z-slice of the volume, used to cut z-slabs of equal work: at
+    wide cone angles the end slices see the detector in few views or none.  Model, calibrated on one
+    B200 at C3 by timing slabs (scripts/fdk_slab_cost.py): cost = overhead + f * (1 + partial_penalty * [f
+    below its maximum]) where f is the fraction of the slice's (voxel, view) pairs that project onto the
+    detector (the others are skipped, recon/bp3d20.cpp:116), `overhead` the per-column work done
+    regardless of f while any view sees the slice (0.042 ms per slice against 0.131 ms per fully visible
+    slice; z-blocks that no view sees return at once), and the penalty the
+    slower general path that columns near the detector edge take.  f is sampled on a coarse (s, t, view)
+    grid with the reference's projection formulas (bp3d20.cpp:99-113)."""
     import numpy as np
     X = (g.x0 + g.vox * np.arange(0, g.nx, stride))[None, :, None]
     Y = (g.y0 - g.vox * np.arange(0, g.ny, stride))[:, None, None]
@@ -67,7 +120,9 @@ def fdk_slice_cost(g, overhead=0.1, stride=8):
     ks = np.sort(k[u_ok])                                      # |k Z| <= half_v  <=>  k <= half_v / |Z|
     Z = np.abs(g.z0 - g.vox * np.arange(g.nz))
     frac = np.searchsorted(ks, g.half_v / np.maximum(Z, 1e-12), side="right") / float(k.size)
-    return frac + overhead
+    partial = (frac > 0) & (frac < 0.97 * frac.max())
+    # slices no view can see cost (almost) nothing: their z-blocks return at once
+    return np.where(frac > 0, overhead, min(overhead, 0.02)) + frac * (1.0 + partial_penalty * partial)
 
 
 def is_dist():
@@ -132,10 +187,12 @@ def fdk_sharded_pipelined(filter_views, pad_views, backproject_views, filt_rows,
     fp32 partial sums — as soon as pieces r and r+1 have landed (piece r's pad fix-up needs the first
     rows of piece r+1).  Views are consumed in ascending order, exactly as on one GPU.
     filter_views(lo, hi); pad_views(lo, hi); backproject_views(z_lo, z_hi, v_lo, v_hi, continue_sum).
-    z_ranges: one (z_lo, z_hi) per rank (e.g. balanced_split(fdk_slice_cost(g), world)); default: equal
-    thickness.  Any contiguous partition gives the same voxels bit for bit."""
+    z_ranges: per rank one (z_lo, z_hi) or a list of them (balanced_split / balanced_blocks of
+    fdk_slice_cost(g)); default: equal thickness.  Any partition gives the same voxels bit for bit."""
     rank, ws = world()
-    z_lo, z_hi = z_ranges[rank] if z_ranges is not None else split_range(nz, ws, rank)
+    mine = z_ranges[rank] if z_ranges is not None else split_range(nz, ws, rank)
+    if len(mine) == 2 and not isinstance(mine[0], (tuple, list)):
+        mine = [tuple(mine)]                                    # one (z_lo, z_hi)
     pieces = [split_range(n_views, ws, r) for r in range(ws)]
     v_lo, v_hi = pieces[rank]
     filter_views(v_lo, v_hi)
@@ -155,9 +212,11 @@ def fdk_sharded_pipelined(filter_views, pad_views, backproject_views, filt_rows,
                 works[q].wait()
                 works[q] = None
         pad_views(lo, hi)
-        backproject_views(z_lo, z_hi, lo, hi, started)
+        for (z_lo, z_hi) in mine:                  # several ranges per rank: see balanced_blocks
+            if z_hi > z_lo:
+                backproject_views(z_lo, z_hi, lo, hi, started)
         started = True
-    return (v_lo, v_hi), (z_lo, z_hi)
+    return (v_lo, v_hi), (mine[0] if len(mine) == 1 else list(mine))
 
 
 def max_over_ranks(value, device):

@@ -142,6 +142,17 @@ def _pipe_worker(rank, ws, port, out_dir):
     z_ranges = mdist.balanced_split([5, 1, 1, 1, 1, 1, 5], ws) if out_dir.endswith("uneven") else None
     vr, zr = mdist.fdk_sharded_pipelined(filter_views, pad_views, backproject_views, rows, n_views, nv, nz, z_ranges=z_ranges)
     np.savez(os.path.join(out_dir, "p%d.npz" % rank), slab=slab["v"].numpy(), z=np.array(zr), log=np.array(log))
+    if out_dir.endswith("uneven"):               # several ranges per rank (balanced_blocks): each is its own slab
+        multi = [[(0, 1), (5, 7)], [(1, 3)], [(3, 5)]]
+        slabs = {}
+
+        def bp_multi(z_lo, z_hi, v_lo, v_hi, cont):
+            slab["v"] = slabs.get(z_lo)
+            backproject_views(z_lo, z_hi, v_lo, v_hi, cont)
+            slabs[z_lo] = slab["v"]
+        rows[: n_views * nv] = float("nan")
+        mdist.fdk_sharded_pipelined(filter_views, pad_views, bp_multi, rows, n_views, nv, nz, z_ranges=multi)
+        np.savez(os.path.join(out_dir, "m%d.npz" % rank), **{"z%d_%d" % (a, b): slabs[a].numpy() for a, b in multi[rank]})
     dist.barrier()
     dist.destroy_process_group()
 
@@ -171,6 +182,15 @@ def test_pipelined_exchange_equals_sequential(tmp_path, ws, uneven):
         assert [int(x) for x in p["log"][:, 0]] == [mdist.split_range(n_views, ws, q)[0] for q in range(ws)]
         z = p["z"][1]
     assert z == nz
+    if uneven:
+        seen = []
+        for r in range(ws):
+            m = np.load(os.path.join(str(tmp_path), "m%d.npz" % r))
+            for k in m.files:
+                a, b = (int(x) for x in k[1:].split("_"))
+                assert np.array_equal(m[k], acc[a:b]), (r, k)
+                seen += list(range(a, b))
+        assert sorted(seen) == list(range(nz))
 
 
 def test_balanced_split():
@@ -197,7 +217,7 @@ def test_fdk_slice_cost_matches_the_oracle_geometry():
     formulas of recon/bp3d20.cpp:99-116"""
     from monte_b200 import _abi
     g = _abi.generic_fdk_geom(90, 96, 40, 48)
-    c = mdist.fdk_slice_cost(g, overhead=0.0, stride=1)
+    c = mdist.fdk_slice_cost(g, overhead=0.0, partial_penalty=0.0, stride=1)
     X = (g.x0 + g.vox * np.arange(g.nx))[None, :, None]
     Y = (g.y0 - g.vox * np.arange(g.ny))[:, None, None]
     b = np.deg2rad(g.angle0_deg + g.angle_step_deg * np.arange(g.n_views))[None, None, :]
@@ -207,3 +227,23 @@ def test_fdk_slice_cost_matches_the_oracle_geometry():
         Z = g.z0 - g.vox * z
         assert abs(c[z] - np.mean(u_ok & (np.abs(k * Z) <= g.half_v))) < 1e-12
     assert c[24] > c[0]                                            # central slices see the detector more often
+
+
+def test_balanced_blocks_cover_every_slice_once_and_beat_the_contiguous_split():
+    """cheap end blocks + expensive middle blocks (C3's shape): whole-block contiguous slabs cannot be
+    balanced over 8 ranks, handing the cheap blocks out separately can"""
+    cost = np.array([0.3] * 64 + [1.5] * 384 + [0.3] * 64)
+    for ws in (2, 3, 4, 8):
+        parts = mdist.balanced_blocks(cost, ws, 16)
+        covered = sorted(z for pr in parts for a, b in pr for z in range(a, b))
+        assert covered == list(range(512))
+        assert all(a % 16 == 0 for pr in parts for a, _ in pr)
+    load = lambda parts: max(sum(cost[a:b].sum() for a, b in pr) for pr in parts)
+    contiguous = [[r] for r in mdist.balanced_split(cost, 8, 16)]
+    assert load(mdist.balanced_blocks(cost, 8, 16)) < 0.9 * load(contiguous)
+    assert mdist.balanced_blocks([1.0] * 40, 3, 16) == [[(0, 16)], [(16, 32)], [(32, 40)]]
+    from monte_b200 import _abi
+    g = _abi.generic_fdk_geom(720, 1024, 768, 512)
+    for ws in (1, 2, 4, 8):
+        parts = mdist.fdk_z_partition(g, ws)
+        assert sorted(z for pr in parts for a, b in pr for z in range(a, b)) == list(range(512))
