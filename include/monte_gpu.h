@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MONTE_GPU_ABI_VERSION 1
+#define MONTE_GPU_ABI_VERSION 2   /* 2: monte_mc_geom.detector_mode */
 
 /* ---- status codes ------------------------------------------------------ */
 #define MONTE_OK            0
@@ -196,6 +196,11 @@ typedef struct monte_mc_volume {
 #define MONTE_MC_SOURCE_CONE   1  /* same stratification, aim point jittered uniformly
                                      inside the pixel: a sampled cone beam              */
 
+/* detector response (anything but COUNTING changes results against the reference) */
+#define MONTE_MC_DETECTOR_COUNTING 0  /* image[...]++ per detected photon (CBCT_real325im.cu:589-590)   */
+#define MONTE_MC_DETECTOR_ENERGY   1  /* energy integrating: += (int)(E_keV * MONTE_MC_EID_SCALE + 0.5) */
+#define MONTE_MC_EID_SCALE 16         /* tally unit = 1/16 keV; per * 200 keV * 16 must stay < 2^31     */
+
 typedef struct monte_mc_geom {
     int32_t n_views;
     double  angle0_deg, angle_step_deg;  /* view v at angle0 + v*step (1 deg, :462,508) */
@@ -205,6 +210,8 @@ typedef struct monte_mc_geom {
     double  dso, dod;        /* 160, 60                                                  */
     int32_t source_mode;
     int32_t max_scatter;     /* ScatterNUM = 5 (CBCT_real325im.cu:7)                     */
+    int32_t detector_mode;   /* MONTE_MC_DETECTOR_*; 0 = the reference's photon counting  */
+    int32_t reserved;        /* must be 0                                                 */
 } monte_mc_geom;
 
 /* spectrum: n_bins == 0 -> mono-energetic at mono_keV (as shipped: 140, survey Q3);

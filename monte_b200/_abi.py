@@ -87,6 +87,7 @@ class McGeom(C.Structure):
         ("pixel", C.c_double), ("half", C.c_double),
         ("dso", C.c_double), ("dod", C.c_double),
         ("source_mode", C.c_int32), ("max_scatter", C.c_int32),
+        ("detector_mode", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

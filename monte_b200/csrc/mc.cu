@@ -43,6 +43,7 @@ struct McSceneDev {
     int n_views, det_ny, det_nx;
     float pixel, inv_pixel, half, dso, dod, dsd;
     int source_mode, max_scatter;
+    int eid;                    // energy-integrating detector: tally (int)(E*16+0.5) instead of 1
 };
 
 struct McLaunch {
@@ -233,7 +234,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                             if (prim_cnt) { atomicAdd(P.image0 + cur_pv, (int)prim_cnt); atomicAdd(P.image5 + cur_pv, (int)prim_cnt); }
                             cur_pv = pva; prim_cnt = 0;
                         }
-                        prim_cnt++; c_prim++;
+                        prim_cnt += sc.eid ? (uint32_t)(pos2[q].w * (float)MONTE_MC_EID_SCALE + 0.5f) : 1u; c_prim++;
                         e_prim += (unsigned long long)(pos2[q].w * 1024.f + 0.5f);
                         if (RECORD) { P.fates[WORD(G_REC, 0)] = 1u | ((pvw & 0xFFFFFu) << 8); P.fate_e[WORD(G_REC, 0)] = pos2[q].w; }
                     } else WORD(G_ID, 1) = meta | 0x8000u;     // scatter detection runs with the refill phase
@@ -382,7 +383,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                         const int by = (int)((sc.half - yd) * sc.inv_pixel), bx = (int)((sc.half - zd) * sc.inv_pixel);
                         if (by >= 0 && by < sc.det_ny && bx >= 0 && bx < sc.det_nx) {
                             const uint32_t bin = (uint32_t)(by * sc.det_nx + bx);
-                            atomicAdd(P.image5 + (size_t)view * npix + bin, 1);
+                            atomicAdd(P.image5 + (size_t)view * npix + bin, sc.eid ? (int)(pos.w * (float)MONTE_MC_EID_SCALE + 0.5f) : 1);
                             c_scat++;
                             e_scat += (unsigned long long)(pos.w * 1024.f + 0.5f);
                             fate = 2u | (bin << 8) | ((uint32_t)nint << 28);
@@ -456,7 +457,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                     if (prim_cnt) { atomicAdd(P.image0 + cur_pv, (int)prim_cnt); atomicAdd(P.image5 + cur_pv, (int)prim_cnt); }
                     cur_pv = pva; prim_cnt = 0;
                 }
-                prim_cnt++; c_prim++;
+                prim_cnt += sc.eid ? (uint32_t)(E * (float)MONTE_MC_EID_SCALE + 0.5f) : 1u; c_prim++;
                 e_prim += (unsigned long long)(E * 1024.f + 0.5f);
                 if (RECORD) { P.fates[rec_idx] = 1u | (pix << 8); P.fate_e[rec_idx] = E; }
                 // the slot stays in REFILL and takes another history on the next visit
@@ -525,6 +526,8 @@ static int check_mc(const monte_mc_geom *g, const monte_mc_volume *vol, const mo
     MONTE_ARG((uint64_t)g->n_views * g->ny * g->nx < (1ull << 32), "mc: views*pixels must fit 32 bits");
     MONTE_ARG((size_t)g->ny * g->nx < (1u << 20), "mc: detector has more than 2^20 pixels");
     MONTE_ARG(g->max_scatter >= 0 && g->max_scatter <= 15, "mc: max_scatter must be 0..15");
+    MONTE_ARG(g->detector_mode == MONTE_MC_DETECTOR_COUNTING || g->detector_mode == MONTE_MC_DETECTOR_ENERGY,
+              "mc: unknown detector_mode %d", g->detector_mode);
     MONTE_ARG(vol->nx > 0 && vol->ny > 0 && vol->nz > 0 && vol->pitch > 0, "mc: bad volume");
     MONTE_ARG((uint64_t)vol->nx * vol->ny * vol->nz < (1ull << 32), "mc: label volume has 2^32 voxels or more");
     MONTE_ARG(xs->n_materials >= 1 && xs->n_materials <= MONTE_MC_MAX_MATERIALS, "mc: n_materials must be 1..%d", MONTE_MC_MAX_MATERIALS);
@@ -609,6 +612,7 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
     d.pixel = (float)g->pixel; d.inv_pixel = (float)(1.0 / g->pixel); d.half = (float)g->half;
     d.dso = (float)g->dso; d.dod = (float)g->dod; d.dsd = (float)(g->dso + g->dod);
     d.source_mode = g->source_mode; d.max_scatter = g->max_scatter;
+    d.eid = g->detector_mode == MONTE_MC_DETECTOR_ENERGY ? 1 : 0;
     if (!s->d_work) MONTE_CUDA(cudaMalloc(&s->d_work, sizeof(unsigned long long)));
     s->smem = (size_t)nm * TAB_ROWS * sizeof(float4) + (TAB_ROWS + 3 + d.n_bins + 1) * sizeof(float);
     s->h2d_bytes = nvox + tab_bytes + inv_bytes + cdf_bytes + vcs.size() * sizeof(float2);
@@ -652,6 +656,8 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     MONTE_ARG(d_image0 && d_image5, "mc: NULL image");
     const uint64_t npix = (uint64_t)s->geom.ny * s->geom.nx;
     MONTE_ARG((uint64_t)s->geom.n_views * npix * per < (1ull << 40), "mc: more than 2^40 history ids");
+    MONTE_ARG(!s->dev.eid || (uint64_t)per * (MONTE_MC_TABLE_ROWS - 1) * MONTE_MC_EID_SCALE < (1ull << 31),
+              "mc: %u photons per pixel overflow an int32 energy tally", per);
     McLaunch L;
     L.sc = s->dev;
     L.key = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u);

@@ -258,7 +258,8 @@ static int delta_sampling(const scene_t *S, rng_t *R, photon_t *p, double E, dou
     return collided;
 }
 
-#define TALLY(x) __atomic_fetch_add(&(x), 1, __ATOMIC_RELAXED)
+/* photon counting (the reference) or energy-integrating response in units of 1/16 keV (monte_gpu.h) */
+#define TALLY(x) __atomic_fetch_add(&(x), (g->detector_mode == MONTE_MC_DETECTOR_ENERGY ? (int)(E * MONTE_MC_EID_SCALE + 0.5) : 1), __ATOMIC_RELAXED)
 
 /* detector bin: result = -1*(int(d*inv_pixel - n/2.))   CBCT_real325im.cu:574-575 / CBCT_real2.cpp:311 */
 static int det_bin(double d, double inv_pixel, int n) { return -1 * ((int)(d * inv_pixel - n / 2.)); }

@@ -79,6 +79,29 @@ def test_images_and_counters_match_coupled_oracle(monte, oracle):
     assert im0.sum() == st["primaries"] and im5.sum() == st["primaries"] + st["scatter_detected"]
 
 
+def test_energy_integrating_detector_matches_coupled_oracle(monte, oracle):
+    """SURVEY 8f-3 flag (off in parity mode): energy-integrating tallies in 1/16 keV, against the oracle
+    run on the same Philox variates, and against the photon-counting run of the same histories"""
+    g, vol, lab = scene(n=33, pitch=1.0, det=17, views=2)
+    xs = scenes.make_xs()
+    per, seed = 60, 5
+    c0, c5, stc = monte.simulate(g, vol, lab, xs, scenes.mono_spectrum(140.0), per, seed)
+    g.detector_mode = 1
+    e0, e5, ste = monte.simulate(g, vol, lab, xs, scenes.mono_spectrum(140.0), per, seed)
+    assert ste["primaries"] == stc["primaries"] and ste["scatter_detected"] == stc["scatter_detected"]
+    assert np.array_equal(e0, c0 * (16 * 140))                 # primaries arrive with the source energy
+    scat = (e5.astype(np.int64) - e0).sum()
+    assert abs(scat / 16.0 - ste["sum_e_scatter"]) <= (0.5 / 16 + 1 / 1024) * ste["scatter_detected"] + 1e-3
+    o0, o5, res, _, _ = oracle.mc_run(g, vol, lab, oracle.tables_from_xs(xs), scenes.mono_spectrum(140.0),
+                                      oracle.mc_opts(oracle.RNG_PHILOX, seed=seed), per)
+    n = ste["histories"]
+    assert np.abs(e0.astype(np.int64) - o0).sum() <= 0.003 * n * 16 * 140
+    assert np.abs(e5.astype(np.int64) - o5).sum() <= 0.003 * n * 16 * 140
+    g.detector_mode = 7
+    with pytest.raises(Exception, match="detector_mode"):
+        monte.simulate(g, vol, lab, xs, scenes.mono_spectrum(140.0), per, seed)
+
+
 def test_statistical_parity_with_reference_generator(monte, oracle):
     """north_star: per pixel within 3 sigma, chi-square over the image, mean detected energy —
     oracle on MT19937 (the reference's generator), CUDA path on Philox."""

@@ -146,3 +146,22 @@ def test_counts_to_map_known_answers(oracle):
     # -log(int) is the double overload, log(float(per)) the float one: counts == per gives the
     # float rounding of log(2000), not exactly 0; counts > per are clamped to per
     assert m[3] == m[4] and abs(m[3]) < 2e-7
+
+
+def test_energy_integrating_detector_mode(oracle):
+    """SURVEY 8f-3, off by default: with detector_mode = ENERGY every detected photon adds
+    (int)(16 E + 0.5) instead of 1 (CBCT_real325im.cu:589-590 counts photons).  Same histories, so the
+    primary image is the count image times 16*140 and the scatter part sums to the detected scatter energy."""
+    lab = scenes.cylinder_phantom(33, 1.0)
+    g = scenes.mc_geom(9, 32.5 / 9, n_views=1)
+    vol = scenes.volume_for(lab, 1.0)
+    tb = oracle.tables_from_xs(scenes.make_xs())
+    opts = oracle.mc_opts(oracle.RNG_PHILOX, seed=4)
+    c0, c5, rc, _, _ = oracle.mc_run(g, vol, lab, tb, scenes.mono_spectrum(140.0), opts, 300)
+    g.detector_mode = 1
+    e0, e5, re, _, _ = oracle.mc_run(g, vol, lab, tb, scenes.mono_spectrum(140.0), opts, 300)
+    assert rc["primaries"] == re["primaries"] and rc["scatter_detected"] == re["scatter_detected"] > 0
+    assert np.array_equal(e0, c0 * (16 * 140))
+    scat = (e5.astype(np.int64) - e0).sum()
+    assert abs(scat / 16.0 - re["sum_e_scatter"]) <= 0.5 / 16 * re["scatter_detected"] + 1e-6
+    assert scat < 16 * 140 * re["scatter_detected"]            # Compton-scattered photons arrive with less than 140 keV
