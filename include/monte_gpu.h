@@ -123,6 +123,10 @@ int monte_gpu_fdk(const monte_fdk_geom *g, const float *map, float *filtered,
  *   row / view) is reproduced by plain row addressing.                             */
 size_t monte_gpu_fdk_filtered_pitch(const monte_fdk_geom *g);           /* floats */
 size_t monte_gpu_fdk_filtered_elems(const monte_fdk_geom *g);           /* floats */
+/* Steps 1+2 of bp3d20.cpp (:36-43 cosine weight, :48-73 Ram-Lak convolution, written transposed) for
+ * views [view_begin, view_end).  nu <= 256: direct shared-memory convolution in the reference's
+ * summation order; wider detectors (up to nu = 2048): the same linear convolution by FFT (length >= 2 nu,
+ * fp32, ~3e-7 of the row maximum from the direct sum).  MONTE_FDK_FILTER=direct|fft overrides.        */
 int monte_gpu_fdk_filter_dev(const monte_fdk_geom *g, const float *d_map,
                              int view_begin, int view_end,
                              float *d_filtered_padded, void *stream);
