@@ -220,3 +220,18 @@ def test_bad_arguments_are_reported_not_fatal(monte):
     g.s_end = 99
     with pytest.raises(monte.MonteError, match="ROI"):
         monte.fdk(g, rand(0, (4, 16, 16)))
+    # detectors wider than the FFT filter's longest transform fall back to the direct convolution;
+    # forcing the FFT there is an error, not a crash
+    import torch
+    gw = _abi.generic_fdk_geom(1, 2100, 2, 8)
+    d = torch.rand((1, 2100, 2), device="cuda")
+    f = torch.zeros(monte.fdk_filtered_shape(gw), dtype=torch.float32, device="cuda")
+    monte.fdk_filter_dev(gw, d, f)
+    torch.cuda.synchronize()
+    assert float(f[:2, :2100].abs().max()) > 0
+    os.environ["MONTE_FDK_FILTER"] = "fft"
+    try:
+        with pytest.raises(monte.MonteError, match="too wide"):
+            monte.fdk_filter_dev(gw, d, f)
+    finally:
+        del os.environ["MONTE_FDK_FILTER"]
