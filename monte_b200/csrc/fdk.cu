@@ -742,7 +742,7 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
     p.half_ud = g->half_u; p.half_vd = g->half_v; p.inv_dud = 1.0 / g->du; p.inv_dvd = 1.0 / g->dv;
     p.nu_half = g->nu / 2.; p.nv_half = g->nv / 2.;
     dim3 block(BP_TX, BP_TY);
-    // tuning knob (default = the fastest measured variant): MONTE_BP_VARIANT=0|1
+    // tuning knob (default = the fastest measured variant): MONTE_BP_VARIANT=0..3
     static int variant = -1;
     if (variant < 0) { const char *e = getenv("MONTE_BP_VARIANT"); variant = e ? atoi(e) : 0; }
 #define BP_LAUNCH(ZT, ZB, MINB)                                                                          \
@@ -810,8 +810,11 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
     p.vc = g_fdk.d_vc + vb; p.filt = d_filtered_padded + (size_t)vb * g->nv * p.pitch;
     p.pairs = d_pairs + (size_t)vb * g->nv * p.pitch; p.accumulate = continue_sum || vb > view_lo;
     switch (variant) {
-        case 1: BP_LAUNCH(32, 8, 2); break;     // 32 slices per thread, 2 CTAs/SM: 74.8 ms at C3
-        default: BP_LAUNCH(16, 8, 3); break;    // 16 slices per thread, 3 CTAs/SM: 67.4 ms at C3
+        case 1: BP_LAUNCH(32, 8, 2); break;     // 32 slices per thread, 2 CTAs/SM: 74.8 ms at C3 (before the 12-instruction update)
+        case 2: BP_LAUNCH(16, 8, 3); break;     // 80 registers, 3 CTAs/SM: 61.9 ms
+        case 3: BP_LAUNCH(16, 16, 3); break;    // gather batches of 16: 58.6 ms
+        default: BP_LAUNCH(16, 8, 4); break;    // 64 registers (4 bytes spilled), 4 CTAs/SM = 32 warps: 56.2 ms -- the gathers'
+                                                // latency (long scoreboard, the top stall) is hidden by more resident warps
     }
     }
 #undef BP_LAUNCH
