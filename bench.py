@@ -468,6 +468,8 @@ def bench_fdk(args, api, mdist, torch, dist, dev, ws, rank, pk, flush, barrier):
     roof = {"bound": "fp32-issue", "achieved": achieved, "peak": pk["fp32_tlane_instr"], "unit": "Tlane-instr/s",
             "frac": achieved / pk["fp32_tlane_instr"], "traffic": profile_traffic("fdk_backproject_kernel"),
             "kernel": "fdk_backproject_kernel", "kernel_ms_per_launch": t_bp, "filter_ms_per_launch": t_filter,
+            "traffic_note": "achieved and kernel_ms_per_launch cover one whole backprojection (the library splits it into L2-sized "
+                            "view-chunk launches, 4 at C3 on one GPU); traffic is the ncu DRAM figure of ONE such chunk launch",
             "model": "%d lane-instr per voxel-update (SURVEY 8d) x %.4g updates per launch x %.3f of them on the detector "
                      "(off-detector pairs are skipped per column, as the reference skips them per voxel); the kernel's fast path needs 12 SASS "
                      "instructions per update, fewer than the model's %d, so frac can exceed 1" % (FDK_INSTR_PER_UPDATE, upd_rank, inside, FDK_INSTR_PER_UPDATE),
