@@ -411,14 +411,23 @@ def bench_fdk(args, api, mdist, torch, dist, dev, ws, rank, pk, flush, barrier):
         z_off[a] = o
         o += b - a
 
+    exchange = os.environ.get("MONTE_BENCH_FDK_EXCHANGE", "band")
+
     def sharded(src):
-        # filter own views | broadcast the view pieces in ascending order (async, NCCL stream) |
-        # backproject piece r as soon as pieces r and r+1 have landed, continuing the partial sums
-        mdist.fdk_sharded_pipelined(lambda a, b: api.fdk_filter_dev(g, src, filt, a, b, pad=False),
-                                    lambda a, b: api.fdk_pad_views_dev(g, filt, a, b),
-                                    lambda z0, z1, a, b, cont: api.fdk_backproject_views_dev(
-                                        g, filt, slab[z_off[z0]:z_off[z0] + z1 - z0], z0, z1, a, b, cont),
-                                    filt, g.n_views, g.nv, g.nz, z_ranges=z_ranges)
+        if exchange == "pipelined":
+            # filter own views | broadcast the view pieces in ascending order (async, NCCL stream) |
+            # backproject piece r as soon as pieces r and r+1 have landed, continuing the partial sums
+            mdist.fdk_sharded_pipelined(lambda a, b: api.fdk_filter_dev(g, src, filt, a, b, pad=False),
+                                        lambda a, b: api.fdk_pad_views_dev(g, filt, a, b),
+                                        lambda z0, z1, a, b, cont: api.fdk_backproject_views_dev(
+                                            g, filt, slab[z_off[z0]:z_off[z0] + z1 - z0], z0, z1, a, b, cont),
+                                        filt, g.n_views, g.nv, g.nz, z_ranges=z_ranges)
+        else:
+            # filter own views | ONE all_to_all of the detector-row bands the peers' slabs read | backproject
+            mdist.fdk_sharded_band(lambda a, b: api.fdk_filter_dev(g, src, filt, a, b, pad=False),
+                                   lambda: api.fdk_pad_dev(g, filt),
+                                   lambda z0, z1: api.fdk_backproject_dev(g, filt, slab[z_off[z0]:z_off[z0] + z1 - z0], z0, z1),
+                                   lambda z0, z1: api.fdk_slab_rows(g, z0, z1), filt, g.n_views, g.nv, z_ranges)
 
     def fdk_step():
         sharded(proj)
@@ -516,7 +525,10 @@ def bench_fdk(args, api, mdist, torch, dist, dev, ws, rank, pk, flush, barrier):
             "ms_per_step": tot / Kf, "scaling": "strong", "dtype": "f32",
             "config": {"workload": "C3 (BASELINE configs[2]): 512^3 volume from 720 views of a 1024x768 detector, REFERENCE weights, "
                                    "weight+ramp filter + backprojection per step",
-                       "parallelism": "z-ranges of equal work x%d %s, filter by views, view pieces broadcast in order and overlapped with the backprojection" % (ws, [[list(z) for z in zr] for zr in z_ranges]) if ws > 1 else "single GPU",
+                       "parallelism": "z-ranges of equal work x%d %s, filter by views, %s" % (
+                           ws, [[list(z) for z in zr] for zr in z_ranges],
+                           "view pieces broadcast in order and overlapped with the backprojection" if exchange == "pipelined"
+                           else "one all_to_all of the detector-row bands each slab reads") if ws > 1 else "single GPU",
                        "l2": "256 MiB fill between steps; projections (2.26 GB) exceed L2"},
             "e2e": e2e, "gpu_launches": 3 * Kf, "roofline": roof, "cpu_baseline": cpu,
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},

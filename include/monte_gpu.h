@@ -132,6 +132,11 @@ int monte_gpu_fdk_filter_dev(const monte_fdk_geom *g, const float *d_map,
                              float *d_filtered_padded, void *stream);
 /* fix up the duplicated column / trailing rows after views were written or gathered */
 int monte_gpu_fdk_pad_dev(const monte_fdk_geom *g, float *d_filtered_padded, void *stream);
+/* Axial detector rows [row_lo, row_hi) of every view that backprojecting slices [z_lo, z_hi) reads, beside
+ * rows 0..3 of every view (what the previous view's last row reaches into, bp3d20.cpp:152-156).  A rank that
+ * owns a z-slab needs only these rows of the other ranks' filtered views (multi-GPU exchange).
+ * row_lo == row_hi: no view sees the slab.                                                               */
+int monte_gpu_fdk_slab_rows(const monte_fdk_geom *g, int z_lo, int z_hi, int *row_lo, int *row_hi);
 /* Backproject all views into z-slices [z_lo, z_hi) of the volume;
  * d_vol_slab points at slice z_lo, layout [z_hi-z_lo][ny][nx].  Overwrites.        */
 int monte_gpu_fdk_backproject_dev(const monte_fdk_geom *g, const float *d_filtered_padded,

@@ -74,6 +74,7 @@ def load():
         "monte_make_sphere": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
         "monte_ctnum_to_mu": (C.c_int, [vp, sz, C.POINTER(McXs), C.c_double, C.c_float, C.c_float, vp, vp]),
         "monte_xs_majorant": (C.c_int, [C.POINTER(McXs), vp, sz, vp]),
+        "monte_gpu_fdk_slab_rows": (C.c_int, [C.POINTER(FdkGeom), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     }
     missing = []
     for name, (res, args) in proto.items():
@@ -183,6 +184,13 @@ def fdk_backproject_views_dev(g, d_filt, d_slab, z_lo, z_hi, view_lo, view_hi, c
     _check(load().monte_gpu_fdk_backproject_views_dev(C.byref(g), C.c_void_p(d_filt.data_ptr()), z_lo, z_hi,
                                                       C.c_void_p(d_slab.data_ptr()), view_lo, view_hi,
                                                       1 if continue_sum else 0, _stream_ptr(stream)))
+
+
+def fdk_slab_rows(g, z_lo, z_hi):
+    """(row_lo, row_hi): the axial detector rows of every view that slices [z_lo, z_hi) read (beside rows 0..3)"""
+    a, b = C.c_int(0), C.c_int(0)
+    _check(load().monte_gpu_fdk_slab_rows(C.byref(g), z_lo, z_hi, C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def fdk_pad_views_dev(g, d_filt, view_lo, view_hi, stream=None):

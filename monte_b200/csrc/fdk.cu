@@ -709,6 +709,24 @@ int monte_gpu_fdk_unpad_dev(const monte_fdk_geom *g, const float *d_filtered_pad
 
 // Backproject views [view_lo, view_hi) into z-slices [z_lo, z_hi).  continue_sum: the slab already
 // holds the fp32 partial sums of the earlier views (they are reloaded exactly), else it is zeroed.
+// axial detector rows [b_lo, b_hi) of every view that the slab [z_lo, z_hi) can reach: x = (half_v - k Z) / dv
+// with k between the magnifications of the farthest and the nearest voxel; +-2 rows of slack, +1 for the
+// pair's partner.  b_hi <= b_lo: the slab projects above or below the detector in every view.
+static void slab_band(const monte_fdk_geom *g, int z_lo, int z_hi, int &b_lo, int &b_hi) {
+    const double r = 0.5 * g->vox * sqrt((double)g->nx * g->nx + (double)g->ny * g->ny) +
+                     fmax(fabs(g->x0 + 0.5 * g->vox * g->nx), fabs(g->y0 - 0.5 * g->vox * g->ny));
+    const double kmin = g->dsd / (g->dso + r), kmax = g->dsd / fmax(g->dso - r, 0.05 * g->dso);
+    const double Za = g->z0 - g->vox * z_lo, Zb = g->z0 - g->vox * (z_hi - 1);
+    double xmin = 1e30, xmax = -1e30;
+    for (int i = 0; i < 4; i++) {
+        const double x = (g->half_v - ((i & 1) ? kmax : kmin) * ((i & 2) ? Zb : Za)) / g->dv;
+        xmin = fmin(xmin, x); xmax = fmax(xmax, x);
+    }
+    b_lo = (int)floor(xmin) - 2; b_hi = (int)ceil(xmax) + 4;
+    if (b_lo < 0) b_lo = 0;
+    if (b_hi > g->nv) b_hi = g->nv;       // rows nv, nv+1 of a view are rows 0, 1 of the next one
+}
+
 static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_padded, int z_lo, int z_hi,
                              float *d_vol_slab, cudaStream_t st, int view_lo, int view_hi, bool continue_sum) {
     if (int rc = fdk_prepare(g, st)) return rc;
@@ -772,20 +790,8 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
     float2 *d_pairs = (float2 *)scratch(8, (size_t)rows_total * p.pitch * sizeof(float2));
     if (!d_pairs) return MONTE_E_NOMEM;
     {
-        // axial detector rows the slab [z_lo, z_hi) can reach: x = nv/2-ish - k*Z/dv with k between the
-        // magnifications of the nearest and the farthest voxel; +-2 rows of slack, +1 for the pair's partner
-        const double r = 0.5 * g->vox * sqrt((double)g->nx * g->nx + (double)g->ny * g->ny) +
-                         fmax(fabs(g->x0 + 0.5 * g->vox * g->nx), fabs(g->y0 - 0.5 * g->vox * g->ny));
-        const double kmin = g->dsd / (g->dso + r), kmax = g->dsd / fmax(g->dso - r, 0.05 * g->dso);
-        const double Za = g->z0 - g->vox * z_lo, Zb = g->z0 - g->vox * (z_hi - 1);
-        double xmin = 1e30, xmax = -1e30;
-        for (int i = 0; i < 4; i++) {
-            const double x = (g->half_v - ((i & 1) ? kmax : kmin) * ((i & 2) ? Zb : Za)) / g->dv;
-            xmin = fmin(xmin, x); xmax = fmax(xmax, x);
-        }
-        int b_lo = (int)floor(xmin) - 2, b_hi = (int)ceil(xmax) + 4;
-        if (b_lo < 0) b_lo = 0;
-        if (b_hi > g->nv) b_hi = g->nv;       // rows nv, nv+1 of a view are rows 0, 1 of the next one
+        int b_lo, b_hi;
+        slab_band(g, z_lo, z_hi, b_lo, b_hi);
         // the whole slab projects above or below the detector in every view (bp3d20.cpp:116 skips every
         // voxel of it): its voxels keep the zeros / partial sums they have
         if (b_hi <= b_lo) return MONTE_OK;
@@ -819,6 +825,16 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
     }
 #undef BP_LAUNCH
     MONTE_CUDA(cudaGetLastError());
+    return MONTE_OK;
+}
+
+int monte_gpu_fdk_slab_rows(const monte_fdk_geom *g, int z_lo, int z_hi, int *row_lo, int *row_hi) {
+    if (int rc = check_geom(g)) return rc;
+    MONTE_ARG(row_lo && row_hi && 0 <= z_lo && z_lo <= z_hi && z_hi <= g->nz, "fdk_slab_rows: bad argument");
+    int a = 0, b = 0;
+    if (z_hi > z_lo) slab_band(g, z_lo, z_hi, a, b);
+    if (b < a) b = a;
+    *row_lo = a; *row_hi = b;
     return MONTE_OK;
 }
 

@@ -247,3 +247,75 @@ def test_balanced_blocks_cover_every_slice_once_and_beat_the_contiguous_split():
     for ws in (1, 2, 4, 8):
         parts = mdist.fdk_z_partition(g, ws)
         assert sorted(z for pr in parts for a, b in pr for z in range(a, b)) == list(range(512))
+
+
+# ---------------------------------------------------------------- band-limited exchange (one all_to_all)
+def _band_rows(z_lo, z_hi):
+    return (z_lo + 1, z_hi + 2)                  # a made-up "slab -> detector rows" map for the CPU test
+
+
+def _band_slab_value(rows3, z_lo, z_hi, n_views, nv, nu):
+    """order-sensitive fp32 sum over views of what the slab reads: the rows of its band with their duplicated
+    column (= first element of the following row, hence the extra exchanged row) and rows 0..2 of the next
+    view with theirs (zeros after the last view)"""
+    a, b = _band_rows(z_lo, z_hi)
+    acc = torch.zeros(z_hi - z_lo, dtype=torch.float32)
+    for v in range(n_views):
+        blk = rows3[v, a:b, : nu + 1]
+        nxt = rows3[v + 1, 0:3, : nu + 1] if v + 1 < n_views else torch.zeros(3, nu + 1)
+        assert not torch.isnan(blk).any() and not torch.isnan(nxt).any(), "view %d: a row the slab reads never arrived" % v
+        acc = acc * np.float32(1.0001) + (blk.sum() + 2 * nxt.sum()) * torch.arange(z_lo, z_hi, dtype=torch.float32)
+    return acc
+
+
+def _band_worker(rank, ws, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    n_views, nv, nu, pitch = 11, 12, 6, 8
+    rows = torch.full((n_views * nv + 2, pitch), float("nan"))
+    rows[n_views * nv:] = 0
+    z_ranges = [[(0, 2), (8, 9)], [(2, 5)], [(5, 8)]][:ws] if ws == 3 else [(0, 4), (4, 9)]
+    out = {}
+
+    def filter_views(lo, hi):
+        for v in range(lo, hi):
+            rows[v * nv:(v + 1) * nv] = torch.from_numpy(_fake_rows(v, nv, pitch, nu))
+
+    def pad():                                   # NaN-tolerant: rows that never arrived stay NaN
+        f = rows[: n_views * nv]
+        f[:-1, nu] = f[1:, 0]
+        f[-1, nu] = 0
+
+    def backproject_slab(z_lo, z_hi):
+        out[(z_lo, z_hi)] = _band_slab_value(rows[: n_views * nv].view(n_views, nv, pitch), z_lo, z_hi, n_views, nv, nu)
+
+    mdist.fdk_sharded_band(filter_views, pad, backproject_slab, _band_rows, rows, n_views, nv, z_ranges)
+    n_nan = int(torch.isnan(rows).sum())
+    np.savez(os.path.join(out_dir, "b%d.npz" % rank), nan=n_nan, **{"z%d_%d" % k: v.numpy() for k, v in out.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ws", [2, 3])
+def test_band_exchange_equals_full_exchange(tmp_path, ws):
+    port = 29300 + os.getpid() % 1500 + ws
+    mp.spawn(_band_worker, args=(ws, port, str(tmp_path)), nprocs=ws, join=True)
+    n_views, nv, nu, pitch = 11, 12, 6, 8
+    rows = np.zeros((n_views * nv, pitch), np.float32)
+    for v in range(n_views):
+        rows[v * nv:(v + 1) * nv] = _fake_rows(v, nv, pitch, nu)
+    rows[:-1, nu] = rows[1:, 0]
+    full = torch.from_numpy(rows).view(n_views, nv, pitch)
+    seen, some_rows_skipped = [], False
+    for r in range(ws):
+        b = np.load(os.path.join(str(tmp_path), "b%d.npz" % r))
+        some_rows_skipped |= int(b["nan"]) > 0
+        for k in b.files:
+            if k == "nan":
+                continue
+            z_lo, z_hi = (int(x) for x in k[1:].split("_"))
+            assert np.array_equal(b[k], _band_slab_value(full, z_lo, z_hi, n_views, nv, nu).numpy()), (r, k)
+            seen += list(range(z_lo, z_hi))
+    assert sorted(seen) == list(range(9))
+    assert some_rows_skipped                     # the point of the exercise: not every row travels

@@ -56,6 +56,15 @@ mdist.fdk_sharded_pipelined(lambda a, b: api.fdk_filter_dev(fg, proj, filt, a, b
                             filt, fg.n_views, fg.nv, fg.nz, z_ranges=zr)
 torch.cuda.synchronize()
 np.savez(os.path.join(out, "u%%d.npz" %% rank), slab=slab3.cpu().numpy(), z=np.array(zr[rank]))
+# band-limited exchange: one all_to_all of the detector rows each slab reads, rows nobody needs stay NaN
+filt.fill_(float("nan"))
+slab4 = torch.empty_like(slab)
+mdist.fdk_sharded_band(lambda a, b: api.fdk_filter_dev(fg, proj, filt, a, b, pad=False), lambda: api.fdk_pad_dev(fg, filt),
+                       lambda a, b: api.fdk_backproject_dev(fg, filt, slab4, a, b), lambda a, b: api.fdk_slab_rows(fg, a, b),
+                       filt, fg.n_views, fg.nv, [mdist.split_range(fg.nz, ws, r) for r in range(ws)])
+torch.cuda.synchronize()
+assert torch.equal(slab, slab4), "band-limited exchange differs from gather-then-backproject"
+assert bool(torch.isnan(filt[: fg.n_views * fg.nv]).any()), "every row travelled: the band is not limiting anything"
 np.savez(os.path.join(out, "r%%d.npz" %% rank), im0=im0.cpu().numpy(), im5=im5.cpu().numpy(), slab=slab2.cpu().numpy(), z=np.array([z_lo, z_hi]))
 dist.barrier(); dist.destroy_process_group()
 '''
