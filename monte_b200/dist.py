@@ -3,9 +3,11 @@
 MC  : histories are independent.  Every rank runs photons n in its slice of [0, per) for the same
       views (history ids are global, so the union is identical to a single-GPU run) and the integer
       tallies are summed with ONE reduce to rank 0 per batch of views.  No other data-path exchange.
-FDK : the volume is cut into z-slabs, the filter into view ranges.  One exchange step: every rank's
-      filtered views are gathered by all ranks (all_gather when views divide evenly, else one
-      broadcast per rank); after that each rank backprojects its own slab and nothing is exchanged.
+FDK : the volume is cut into z-slabs of equal work (fdk_slice_cost, balanced_split), the filter into view
+      ranges.  One exchange step, three forms with identical results: fdk_sharded (every rank gathers all
+      filtered views), fdk_sharded_pipelined (view pieces broadcast in order, overlapped with the
+      backprojection) and fdk_sharded_band (one all_to_all of just the detector rows each slab reads --
+      the one bench.py uses).  After that each rank backprojects its own slab; nothing else is exchanged.
 
 The compute callables are injected, so the same code is exercised on CPU with the gloo backend
 (tests/test_dist_cpu.py) and on B200s with NCCL (bench.py, tests/test_dist_gpu.py).
