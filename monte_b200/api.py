@@ -27,7 +27,14 @@ def load():
     if not os.path.exists(_abi.LIB_PATH):
         raise MonteError("libmonte_gpu.so not built (%s); run `python -m monte_b200.build` — "
                          "there is no CPU fallback" % _abi.LIB_PATH)
-    lib = C.CDLL(_abi.LIB_PATH)
+    _lib = _bind(_abi.LIB_PATH)
+    return _lib
+
+
+def _bind(path):
+    """Open the shared library at `path` and declare the prototypes of include/monte_gpu.h on it.  load() binds the CUDA
+    library; the only other caller is tests/emu/build.py (CPU emulation of the same sources, tests only)."""
+    lib = C.CDLL(path)
     vp, i32, u32, u64, sz = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, C.c_size_t
     fp = C.POINTER(C.c_float)
     ip = C.POINTER(C.c_int32)
@@ -87,7 +94,6 @@ def load():
         fn.argtypes = args
     lib._monte_symbols = sorted(proto)
     lib._monte_missing = missing
-    _lib = lib
     return lib
 
 

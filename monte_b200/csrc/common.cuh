@@ -9,6 +9,19 @@
 #include <vector>
 #include "../../include/monte_gpu.h"
 
+// Kernel launches and dynamic shared memory are spelled through these two macros so that the same
+// sources also compile as plain C++ against tests/emu/cuda_runtime.h, a SIMT emulation the CPU test-suite
+// uses to drive the kernels and this host code without a GPU.  MONTE_EMU is never defined in the product
+// build (monte_b200/build.py, nvcc only); there is no CPU fallback.
+#ifdef MONTE_EMU
+#define MONTE_CFG(grid, block, smem, stream) \
+    *::monte_emu::CfgCall{::monte_emu::Cfg{dim3(grid), dim3(block), (size_t)(smem)}}
+#define MONTE_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(::monte_emu::dyn_smem())
+#else
+#define MONTE_CFG(grid, block, smem, stream) <<<(grid), (block), (smem), (stream)>>>
+#define MONTE_DYN_SMEM(type, name) extern __shared__ type name[]
+#endif
+
 namespace monte {
 
 struct Context {

@@ -111,7 +111,7 @@ extern "C" int monte_gpu_fbp2(const monte_fdk_geom *g, int view_first, const flo
     MONTE_CUDA(cudaMemcpyAsync(d_r, ramp.data(), ramp.size() * 8, cudaMemcpyHostToDevice, st));
     MONTE_CUDA(cudaMemcpyAsync(d_vc, vc.data(), vc.size() * sizeof(Fbp2View), cudaMemcpyHostToDevice, st));
     MONTE_CUDA(cudaMemsetAsync(d_img, 0, n_img * 4, st));
-    fbp2_filter_kernel<<<dim3(ceil_div(nu, 64), nviews), 64, 0, st>>>(d_sino, d_w, d_r, d_filt, nu, nviews, g->filter_scale);
+    fbp2_filter_kernel MONTE_CFG(dim3(ceil_div(nu, 64), nviews), 64, 0, st)(d_sino, d_w, d_r, d_filt, nu, nviews, g->filter_scale);
     MONTE_CUDA(cudaGetLastError());
     Fbp2Params p;
     p.filt = d_filt; p.vc = d_vc; p.img = d_img;
@@ -121,7 +121,7 @@ extern "C" int monte_gpu_fbp2(const monte_fdk_geom *g, int view_first, const flo
     p.wd = wd; p.beta_span = (double)(float)g->angle_step_deg; p.out_scale = g->out_scale;
     if (g->s_end > g->s_begin && g->t_end > g->t_begin) {
         dim3 grid(ceil_div(g->s_end - g->s_begin, 32), ceil_div(g->t_end - g->t_begin, 4));
-        fbp2_backproject_kernel<<<grid, dim3(32, 4), 0, st>>>(p);
+        fbp2_backproject_kernel MONTE_CFG(grid, dim3(32, 4), 0, st)(p);
         MONTE_CUDA(cudaGetLastError());
     }
     if (filtered) MONTE_CUDA(cudaMemcpyAsync(filtered, d_filt, n_s * 4, cudaMemcpyDeviceToHost, st));

@@ -88,7 +88,7 @@ struct FilterParams {
 
 __global__ void __launch_bounds__(FT_THREADS)
 fdk_weight_filter_kernel(const FilterParams p) {
-    extern __shared__ float smem[];
+    MONTE_DYN_SMEM(float, smem);
     float *s_in  = smem;                                  // [FT_D][in_pitch]
     float *s_out = s_in + FT_D * p.in_pitch;              // [FT_D][in_pitch]
     float *s_tap = s_out + FT_D * p.in_pitch;             // [tap_len]
@@ -171,7 +171,7 @@ constexpr size_t fft_filter_smem(int L) { return ((size_t)2 * fft_padded_len(L) 
 template <int L>
 __global__ void __launch_bounds__(L / 8, 8192 / L)
 fdk_weight_filter_fft_kernel(const FftFilterParams p) {
-    extern __shared__ cpx s_fft[];
+    MONTE_DYN_SMEM(cpx, s_fft);
     constexpr int T = FftPlan<L>::THREADS, PL = fft_padded_len(L), TP = fft_tile_pitch(L);
     cpx *bufA = s_fft, *bufB = s_fft + PL, *tile = s_fft + 2 * PL;
     const int j = threadIdx.x;
@@ -651,9 +651,9 @@ int monte_gpu_fdk_filter_dev(const monte_fdk_geom *g, const float *d_map, int vi
             MONTE_CUDA(cudaFuncSetAttribute(fdk_weight_filter_fft_kernel<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_filter_smem(4096)));
             attr_set = true;
         }
-        if (L == 1024) fdk_weight_filter_fft_kernel<1024><<<grid, 128, smem, st>>>(q);
-        else if (L == 2048) fdk_weight_filter_fft_kernel<2048><<<grid, 256, smem, st>>>(q);
-        else fdk_weight_filter_fft_kernel<4096><<<grid, 512, smem, st>>>(q);
+        if (L == 1024) fdk_weight_filter_fft_kernel<1024> MONTE_CFG(grid, 128, smem, st)(q);
+        else if (L == 2048) fdk_weight_filter_fft_kernel<2048> MONTE_CFG(grid, 256, smem, st)(q);
+        else fdk_weight_filter_fft_kernel<4096> MONTE_CFG(grid, 512, smem, st)(q);
         MONTE_CUDA(cudaGetLastError());
         return MONTE_OK;
     }
@@ -672,7 +672,7 @@ int monte_gpu_fdk_filter_dev(const monte_fdk_geom *g, const float *d_map, int vi
         smem_set = smem;
     }
     dim3 grid(ceil_div(g->nv, FT_D), view_end - view_begin);
-    fdk_weight_filter_kernel<<<grid, FT_THREADS, smem, st>>>(p);
+    fdk_weight_filter_kernel MONTE_CFG(grid, FT_THREADS, smem, st)(p);
     MONTE_CUDA(cudaGetLastError());
     return MONTE_OK;
 }
@@ -681,7 +681,7 @@ int monte_gpu_fdk_pad_dev(const monte_fdk_geom *g, float *d_filtered_padded, voi
     MONTE_REQUIRE_INIT();
     if (int rc = check_geom(g)) return rc;
     const int rows = g->n_views * g->nv;
-    fdk_pad_kernel<<<ceil_div(rows + 2, 256), 256, 0, (cudaStream_t)stream>>>(d_filtered_padded, rows, g->nu, (int)filtered_pitch(g), 0, rows + 2);
+    fdk_pad_kernel MONTE_CFG(ceil_div(rows + 2, 256), 256, 0, (cudaStream_t)stream)(d_filtered_padded, rows, g->nu, (int)filtered_pitch(g), 0, rows + 2);
     MONTE_CUDA(cudaGetLastError());
     return MONTE_OK;
 }
@@ -693,7 +693,7 @@ int monte_gpu_fdk_pad_views_dev(const monte_fdk_geom *g, float *d_filtered_padde
     if (view_lo == view_hi) return MONTE_OK;
     const int rows = g->n_views * g->nv;
     const int r0 = view_lo * g->nv, r1 = view_hi == g->n_views ? rows + 2 : min(view_hi * g->nv + 2, rows + 2);
-    fdk_pad_kernel<<<ceil_div(r1 - r0, 256), 256, 0, (cudaStream_t)stream>>>(d_filtered_padded, rows, g->nu, (int)filtered_pitch(g), r0, r1);
+    fdk_pad_kernel MONTE_CFG(ceil_div(r1 - r0, 256), 256, 0, (cudaStream_t)stream)(d_filtered_padded, rows, g->nu, (int)filtered_pitch(g), r0, r1);
     MONTE_CUDA(cudaGetLastError());
     return MONTE_OK;
 }
@@ -702,7 +702,7 @@ int monte_gpu_fdk_unpad_dev(const monte_fdk_geom *g, const float *d_filtered_pad
     MONTE_REQUIRE_INIT();
     if (int rc = check_geom(g)) return rc;
     const size_t rows = (size_t)g->n_views * g->nv, n = rows * g->nu;
-    fdk_unpad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_filtered_padded, d_dense, rows, g->nu, (int)filtered_pitch(g));
+    fdk_unpad_kernel MONTE_CFG((unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream)(d_filtered_padded, d_dense, rows, g->nu, (int)filtered_pitch(g));
     MONTE_CUDA(cudaGetLastError());
     return MONTE_OK;
 }
@@ -767,7 +767,7 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
     do {                                                                                                 \
         dim3 grid(ceil_div(g->s_end - g->s_begin, BP_TX), ceil_div(g->t_end - g->t_begin, BP_TY),        \
                   ceil_div(z_hi - (z_lo / ZT) * ZT, ZT));                                                \
-        fdk_backproject_kernel<ZT, ZB, MINB><<<grid, block, 0, st>>>(p);                                 \
+        fdk_backproject_kernel<ZT, ZB, MINB> MONTE_CFG(grid, block, 0, st)(p);                                 \
     } while (0)
     // Views are streamed in chunks so that the detector rows a wave of CTAs touches stay L2-resident
     // (all 720 views of one z-block are ~200 MB; CTAs drifting apart in view index thrash the L2).
@@ -798,15 +798,15 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
         // rows 0..3 of every view are always paired too: they are what the previous view reaches past its end
         const int n_v = view_hi - view_lo + (view_hi < g->n_views ? 1 : 0);
         if (b_lo > 0) {
-            fdk_pair_kernel<<<dim3(b_lo < 4 ? b_lo : 4, ceil_div(p.pitch, 128), n_v), 128, 0, st>>>(d_filtered_padded, d_pairs, view_lo, g->nv, 0,
+            fdk_pair_kernel MONTE_CFG(dim3(b_lo < 4 ? b_lo : 4, ceil_div(p.pitch, 128), n_v), 128, 0, st)(d_filtered_padded, d_pairs, view_lo, g->nv, 0,
                                                                                                    b_lo < 4 ? b_lo : 4, rows_total, p.pitch);
             MONTE_CUDA(cudaGetLastError());
         }
-        fdk_pair_kernel<<<dim3(b_hi - b_lo, ceil_div(p.pitch, 128), n_v), 128, 0, st>>>(d_filtered_padded, d_pairs, view_lo, g->nv, b_lo, b_hi,
+        fdk_pair_kernel MONTE_CFG(dim3(b_hi - b_lo, ceil_div(p.pitch, 128), n_v), 128, 0, st)(d_filtered_padded, d_pairs, view_lo, g->nv, b_lo, b_hi,
                                                                                        rows_total, p.pitch);
         MONTE_CUDA(cudaGetLastError());
         if (view_hi == g->n_views) {          // the two zero rows after the last view
-            fdk_pair_kernel<<<dim3(2, ceil_div(p.pitch, 128), 1), 128, 0, st>>>(d_filtered_padded, d_pairs, g->n_views, g->nv, 0, 2, rows_total, p.pitch);
+            fdk_pair_kernel MONTE_CFG(dim3(2, ceil_div(p.pitch, 128), 1), 128, 0, st)(d_filtered_padded, d_pairs, g->n_views, g->nv, 0, 2, rows_total, p.pitch);
             MONTE_CUDA(cudaGetLastError());
         }
     }
@@ -861,7 +861,7 @@ int monte_gpu_fdk_transpose_dev(const monte_fdk_geom *g, const float *d_vol_xy, 
     MONTE_REQUIRE_INIT();
     if (int rc = check_geom(g)) return rc;
     dim3 grid(ceil_div(g->nx, 32), ceil_div(g->nz, 32), g->ny);
-    fdk_transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(d_vol_xy, d_vol_zy, g->nx, g->ny, g->nz);
+    fdk_transpose_kernel MONTE_CFG(grid, dim3(32, 8), 0, (cudaStream_t)stream)(d_vol_xy, d_vol_zy, g->nx, g->ny, g->nz);
     MONTE_CUDA(cudaGetLastError());
     return MONTE_OK;
 }
@@ -920,7 +920,7 @@ int monte_gpu_fdk(const monte_fdk_geom *g, const float *map, float *filtered, fl
             // the last view of the chunk reads up to two rows into the next chunk (already filtered):
             // their duplicated column must be valid too
             const int r0 = prev0 * g->nv, r1 = last ? rows + 2 : min(prev1 * g->nv + 2, rows + 2);
-            fdk_pad_kernel<<<ceil_div(r1 - r0, 256), 256, 0, st>>>(d_filt, rows, g->nu, pitch, r0, r1);
+            fdk_pad_kernel MONTE_CFG(ceil_div(r1 - r0, 256), 256, 0, st)(d_filt, rows, g->nu, pitch, r0, r1);
             MONTE_CUDA(cudaGetLastError());
             launches++;
             if (last) MONTE_CUDA(cudaEventRecord(ev_t[1], st));     // everything filtered

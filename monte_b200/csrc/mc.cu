@@ -114,7 +114,7 @@ constexpr int mc_slot_groups(bool record) { return record ? 4 : 3; }
 template <bool RECORD, int K, int MINB = 3, int NSTEP = 2>
 __global__ void __launch_bounds__(MC_THREADS, MINB)
 mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
-    extern __shared__ float4 s_mem[];
+    MONTE_DYN_SMEM(float4, s_mem);
     const McSceneDev &sc = P.sc;
     float4 *s_tab = s_mem;                                             // [n_mat*201]
     float *s_inv = reinterpret_cast<float *>(s_tab + sc.n_mat * TAB_ROWS);   // [201]
@@ -717,8 +717,12 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     }
     int grid = sms * oc;
     if ((unsigned long long)grid * (MC_THREADS / 32) > warps_needed) grid = (int)((warps_needed + MC_THREADS / 32 - 1) / (MC_THREADS / 32));
+#ifdef MONTE_EMU   // CPU test build (tests/emu): the emulation calls the kernel function through its real type
+    reinterpret_cast<void (*)(const McLaunch)>(const_cast<void *>(fn)) MONTE_CFG(grid, MC_THREADS, smem, st)(L);
+#else
     void *args[] = {(void *)&L};
     MONTE_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(MC_THREADS), args, smem, st));
+#endif
     MONTE_CUDA(cudaGetLastError());
     return MONTE_OK;
 }
@@ -828,7 +832,7 @@ int monte_gpu_counts_to_map_dev(const int32_t *d_counts, size_t n, int32_t per, 
     MONTE_REQUIRE_INIT();
     MONTE_ARG(d_counts && d_map && per > 0, "counts_to_map: bad argument");
     if (n == 0) return MONTE_OK;
-    counts_to_map_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_counts, n, per, logf((float)per), d_map);
+    counts_to_map_kernel MONTE_CFG((unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream)(d_counts, n, per, logf((float)per), d_map);
     MONTE_CUDA(cudaGetLastError());
     return MONTE_OK;
 }

@@ -151,7 +151,7 @@ extern "C" int monte_gpu_project_primary(const monte_mc_geom *g, const monte_mc_
     float *d_map = (float *)(base + nvox_al + 2 * npad_al);
     MONTE_CUDA(cudaMemcpyAsync(d_raw, labels, nvox, cudaMemcpyHostToDevice, st));
     MONTE_CUDA(cudaMemsetAsync(d_lab, 0, 2 * npad_al, st));
-    labels_pad_transpose_kernel<<<dim3(ceil_div(vol->nx, 32), ceil_div(vol->ny, 32), vol->nz), dim3(32, 8), 0, st>>>(
+    labels_pad_transpose_kernel MONTE_CFG(dim3(ceil_div(vol->nx, 32), ceil_div(vol->ny, 32), vol->nz), dim3(32, 8), 0, st)(
         d_raw, d_lab, d_lab_t, vol->nx, vol->ny);
     MONTE_CUDA(cudaGetLastError());
     ProjParams p;
@@ -183,7 +183,7 @@ extern "C" int monte_gpu_project_primary(const monte_mc_geom *g, const monte_mc_
         const int v1 = v0 + chunk < view_end ? v0 + chunk : view_end;
         p.view_begin = v0; p.n_views_run = v1 - v0;
         dim3 grid(ceil_div(g->ny, 32), ceil_div(g->nx, 4), v1 - v0);
-        project_primary_kernel<<<grid, 128, 0, st>>>(p);
+        project_primary_kernel MONTE_CFG(grid, 128, 0, st)(p);
         MONTE_CUDA(cudaGetLastError());
         MONTE_CUDA(cudaEventRecord(ev[k], st));
         MONTE_CUDA(cudaStreamWaitEvent(cp, ev[k], 0));

@@ -31,4 +31,19 @@ def monte():
     api.shutdown()
 
 
+@pytest.fixture(scope="session")
+def monte_emu():
+    """The monte_b200.api surface bound to tests/emu/_build/libmonte_gpu_emu.so: the library's own .cu
+    sources compiled by g++ against a SIMT emulation (tests/emu/cuda_runtime.h).  Test infrastructure
+    only -- it lets the CPU suite run kernel and host logic; it is not a fallback of the product."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("monte_emu_build", os.path.join(ROOT, "tests", "emu", "build.py"))
+    eb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(eb)
+    api = eb.api()
+    api.init(0)
+    yield api
+    api.shutdown()
+
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")

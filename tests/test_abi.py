@@ -83,6 +83,21 @@ def test_product_never_imports_the_oracle():
                 assert "liboracle" not in text and "dlopen" not in text, fn
 
 
+def test_product_never_contains_or_loads_the_emulation():
+    """tests/emu (the SIMT emulation the CPU suite uses) is test infrastructure: libmonte_gpu.so is built by nvcc
+    without MONTE_EMU, exports nothing of it, and nothing under monte_b200/ points at the emulation library"""
+    import subprocess
+    syms = subprocess.run(["nm", "-D", "--defined-only", _abi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "monte_emu" not in syms
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "monte_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cpp")):
+                text = open(os.path.join(dirpath, fn), errors="replace").read()
+                assert "libmonte_gpu_emu" not in text and "MONTE_EMU" not in text, fn
+    build_py = open(os.path.join(ROOT, "monte_b200", "build.py")).read()
+    assert "tests" not in build_py.replace("tests/emu/build.py", "")
+
+
 def test_no_cpu_fallback_without_a_device(lib):
     import torch
     if torch.cuda.is_available():

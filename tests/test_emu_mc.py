@@ -1,0 +1,105 @@
+"""CPU tests of the Monte-Carlo transport kernel, the projector and their host code under SIMT emulation.
+
+monte_b200/csrc/mc.cu and project.cu are compiled by g++ against tests/emu/cuda_runtime.h: the transport
+kernel's warps run as 32 fibers each, so its warp votes (__reduce_add_sync / __ballot_sync / __shfl_sync), the
+parked-history slots in "shared memory", the unit chaining and the tally flushes are executed exactly as
+written.  The bodies of the GPU parity tests are reused (same assertions, same oracle), including the
+history-by-history comparison on shared Philox variates.  Test infrastructure only: the product has no CPU
+path, speed is not assessed here, and libm replaces the MUFU approximations (fewer fp threshold flips than on
+the GPU, never more logic).
+"""
+import numpy as np
+import pytest
+
+import test_mc_gpu as G
+from monte_b200 import _abi, scenes
+
+
+@pytest.mark.parametrize("mode,poly", [(_abi.SOURCE_PENCIL, False), (_abi.SOURCE_CONE, True)])
+def test_emu_history_coupled_fates_match_oracle(monte_emu, oracle, mode, poly):
+    G.test_history_coupled_fates_match_oracle(monte_emu, oracle, mode, poly)
+
+
+def test_emu_images_and_counters_match_coupled_oracle(monte_emu, oracle):
+    G.test_images_and_counters_match_coupled_oracle(monte_emu, oracle)
+
+
+def test_emu_energy_integrating_detector_matches_coupled_oracle(monte_emu, oracle):
+    G.test_energy_integrating_detector_matches_coupled_oracle(monte_emu, oracle)
+
+
+def test_emu_three_materials_im_variant_coupled(monte_emu, oracle):
+    G.test_three_materials_im_variant_coupled(monte_emu, oracle)
+
+
+def test_emu_edge_cases(monte_emu):
+    G.test_edge_cases(monte_emu)
+
+
+def test_emu_counts_to_map_matches_oracle(monte_emu, oracle):
+    G.test_counts_to_map_matches_oracle(monte_emu, oracle)
+
+
+def test_emu_project_primary_matches_oracle(monte_emu, oracle):
+    G.test_project_primary_matches_oracle(monte_emu, oracle)
+
+
+def test_emu_partition_independence(monte_emu):
+    """photon ranges (the multi-GPU split), view ranges and the resident-scene entry point give the tallies and
+    counters of the undivided host-buffer call, exactly"""
+    m = monte_emu
+    g, vol, lab = G.scene(n=33, pitch=1.0, det=17, views=3)
+    xs = scenes.make_xs()
+    per, seed = 30, 3
+    ref0, ref5, st = m.simulate(g, vol, lab, xs, scenes.mono_spectrum(), per, seed)
+    sc = m.Scene(g, vol, lab, xs, scenes.mono_spectrum())
+    a0, a5 = np.zeros((3, 17, 17), np.int32), np.zeros((3, 17, 17), np.int32)
+    stats = np.zeros(16, np.uint64)
+    for nr in ((0, 7), (7, 19), (19, 30)):
+        sc.simulate_dev(m.Dev(a0), m.Dev(a5), per, seed, views=(0, 2), n_range=nr, d_stats=m.Dev(stats))
+    sc.simulate_dev(m.Dev(a0), m.Dev(a5), per, seed, views=(2, 3), d_stats=m.Dev(stats))
+    sc.close()
+    assert np.array_equal(a0, ref0) and np.array_equal(a5, ref5)
+    st2 = m.unpack_stats(stats)
+    for k in ("histories", "primaries", "scatter_detected", "absorbed", "interactions", "woodcock_steps"):
+        assert st2[k] == st[k], k
+    assert st2["sum_e_scatter"] == st["sum_e_scatter"]
+    d0, _, _ = m.simulate(g, vol, lab, xs, scenes.mono_spectrum(), per, seed + 1)
+    assert not np.array_equal(d0, ref0)
+
+
+@pytest.mark.parametrize("which", ["31", "33", "36", "44", "45", "46"])
+def test_emu_kernel_variants_give_identical_tallies(which, oracle):
+    """MONTE_MC_KERNEL selects K = 1..6 parked histories per lane and the one- / three-slot step visits: every
+    history consumes its own counter-based variates, so all variants must produce the default kernel's tallies
+    bit for bit.  The variant is latched at the first launch of a process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import os, sys, importlib.util
+import numpy as np
+root = sys.argv[1]
+sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
+spec = importlib.util.spec_from_file_location("monte_emu_build", os.path.join(root, "tests", "emu", "build.py"))
+eb = importlib.util.module_from_spec(spec); spec.loader.exec_module(eb)
+m = eb.api(); m.init(0)
+import test_mc_gpu as G
+from monte_b200 import scenes
+g, vol, lab = G.scene(n=33, pitch=1.0, det=17, views=2)
+im0, im5, st = m.simulate(g, vol, lab, scenes.make_xs(), scenes.mono_spectrum(140.0), 25, 9)
+np.save(sys.argv[2], np.stack([im0, im5]))
+print(st["histories"], st["woodcock_steps"], st["interactions"])
+'''
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    with tempfile.TemporaryDirectory() as td:
+        for w in ("35", which):
+            env = dict(os.environ, MONTE_MC_KERNEL=w)
+            path = os.path.join(td, "im_%s.npy" % w)
+            r = subprocess.run([sys.executable, "-c", code, root, path], env=env, capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs[w] = (np.load(path), r.stdout.strip())
+    assert np.array_equal(outs["35"][0], outs[which][0])
+    assert outs["35"][1] == outs[which][1]
