@@ -26,7 +26,8 @@
 extern "C" {
 #endif
 
-#define MONTE_GPU_ABI_VERSION 2   /* 2: monte_mc_geom.detector_mode */
+#define MONTE_GPU_ABI_VERSION 3   /* 2: monte_mc_geom.detector_mode; 3: monte_mc_geom.coherent_mode (was
+                                     `reserved`, 0 = unchanged behaviour) + form-factor tables appended to monte_mc_xs */
 
 /* ---- status codes ------------------------------------------------------ */
 #define MONTE_OK            0
@@ -173,6 +174,7 @@ int monte_gpu_fbp2(const monte_fdk_geom *g, int view_first, const float *sino,
 
 #define MONTE_MC_MAX_MATERIALS 8
 #define MONTE_MC_TABLE_ROWS    201   /* index = keV, 0..200 (CBCT_real325im.cu:76-78) */
+#define MONTE_MC_FF_POINTS     128   /* grid points of a Rayleigh form-factor table */
 
 /* cross-section tables per material, index (int)(E+0.5) (CBCT_real325im.cu:501,627-630).
  * Values are mass coefficients cm^2/g; mu = value * density.                        */
@@ -185,6 +187,14 @@ typedef struct monte_mc_xs {
     float   compt[MONTE_MC_MAX_MATERIALS][MONTE_MC_TABLE_ROWS];    /* incoherent         */
     float   photo[MONTE_MC_MAX_MATERIALS][MONTE_MC_TABLE_ROWS];    /* photoelectric "ab" */
     float   total[MONTE_MC_MAX_MATERIALS][MONTE_MC_TABLE_ROWS];    /* "mua"              */
+    /* Rayleigh form-factor tables, read only when monte_mc_geom.coherent_mode == MONTE_MC_COHERENT_FORMFACTOR
+     * (the reference has none: its coherent event keeps the direction, CBCT_real325im.cu:656-695).
+     * Per material: ff_x2[i] = x^2 grid, x = sin(theta/2)/lambda in 1/Angstrom, ascending from ff_x2[0] = 0 and
+     * reaching at least (E_max/12.398 keV A)^2; ff_cum[i] = integral_0^{x2_i} F(x)^2 d(x^2), any normalisation.
+     * monte_xs_formfactor_hydrogenic() fills them with an analytic stand-in.                                   */
+    int32_t ff_points;                                             /* 0 = no tables; else 2..MONTE_MC_FF_POINTS */
+    float   ff_x2 [MONTE_MC_MAX_MATERIALS][MONTE_MC_FF_POINTS];
+    float   ff_cum[MONTE_MC_MAX_MATERIALS][MONTE_MC_FF_POINTS];
 } monte_mc_xs;
 
 /* voxelised label volume, x fastest (make_image01.cpp:20: g[k*L*M + j*M + i]).
@@ -210,6 +220,13 @@ typedef struct monte_mc_volume {
 #define MONTE_MC_DETECTOR_ENERGY   1  /* energy integrating: += (int)(E_keV * MONTE_MC_EID_SCALE + 0.5) */
 #define MONTE_MC_EID_SCALE 16         /* tally unit = 1/16 keV; per * 200 keV * 16 must stay < 2^31     */
 
+/* coherent (Rayleigh) events (anything but FORWARD changes results against the reference) */
+#define MONTE_MC_COHERENT_FORWARD    0  /* no deflection: the photon flies on (CBCT_real325im.cu:656-695)       */
+#define MONTE_MC_COHERENT_FORMFACTOR 1  /* theta from (1+cos^2 theta)/2 * F(x)^2 with the tables in monte_mc_xs:
+                                           x^2 drawn from F^2 up to x^2_max = (E/12.398)^2, accepted with
+                                           probability (1+cos^2 theta)/2, cos theta = 1 - 2 x^2/x^2_max; phi
+                                           uniform; energy unchanged                                             */
+
 typedef struct monte_mc_geom {
     int32_t n_views;
     double  angle0_deg, angle_step_deg;  /* view v at angle0 + v*step (1 deg, :462,508) */
@@ -220,7 +237,7 @@ typedef struct monte_mc_geom {
     int32_t source_mode;
     int32_t max_scatter;     /* ScatterNUM = 5 (CBCT_real325im.cu:7)                     */
     int32_t detector_mode;   /* MONTE_MC_DETECTOR_*; 0 = the reference's photon counting  */
-    int32_t reserved;        /* must be 0                                                 */
+    int32_t coherent_mode;   /* MONTE_MC_COHERENT_*; 0 = the reference's undeflected coherent event */
 } monte_mc_geom;
 
 /* spectrum: n_bins == 0 -> mono-energetic at mono_keV (as shipped: 140, survey Q3);
@@ -250,7 +267,7 @@ typedef struct monte_mc_stats {
 
 /* Whole simulation on host buffers.  photons_per_pixel is the reference's `per`
  * (CBCT_real325im.cu:182): histories per view = per*ny*nx.  History id
- * h = (view*ny*nx + pixel)*per + n draws from Philox4x32-10 stream (seed, h), so the
+ * h = (view*ny*nx + pixel)*per + n keys a Philox2x32-10 counter (seed, h), so the
  * result is independent of how histories are partitioned.  view_begin == view_end == 0 means
  * all views; only the requested views of image0/image5 are written.
  * image0 [n_views][ny][nx] int32: unscattered;  image5: unscattered + scattered
@@ -324,6 +341,10 @@ void monte_make_sphere(uint8_t *g, int nx, int ny, int nz, int cx, int cy, int c
  * mu_water(E)*(1+HU/1000) and a label segmentation by HU thresholds.                   */
 int monte_ctnum_to_mu(const float *hu, size_t n, const monte_mc_xs *xs, double keV,
                       float hu_air_max, float hu_bone_min, float *mu, uint8_t *labels);
+/* Analytic stand-in for a measured form factor (the reference ships none): F(x)^2 ~ (1 + x^2/x0^2)^-4, the
+ * hydrogen-like 1s charge cloud, x0 in 1/Angstrom (0.30 * Z_eff).  Fills ff_x2 / ff_cum of `material` on a
+ * logarithmic grid of MONTE_MC_FF_POINTS points up to x^2 = 270 (200 keV back-scatter) and sets ff_points.  */
+int monte_xs_formfactor_hydrogenic(monte_mc_xs *xs, int material, double x0);
 /* per-keV Woodcock majorant (1/cm) over the materials that occur in `labels` (NULL: all materials):
  * the max of CBCT_real325im.cu:866 restricted to what the volume contains; mu_max[201].               */
 int monte_xs_majorant(const monte_mc_xs *xs, const uint8_t *labels, size_t n, float *mu_max);

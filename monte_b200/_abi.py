@@ -12,11 +12,13 @@ LIB_PATH = os.path.join(HERE, "lib", "libmonte_gpu.so")
 
 MAX_MATERIALS = 8
 TABLE_ROWS = 201
+FF_POINTS = 128
 STATS_WORDS = 16
 
 FDK_REFERENCE, FDK_TEXTBOOK = 0, 1
 COORD_SCALE_AFTER, COORD_SCALE_BEFORE = 0, 1
 SOURCE_PENCIL, SOURCE_CONE = 0, 1
+COHERENT_FORWARD, COHERENT_FORMFACTOR = 0, 1
 
 
 class FdkGeom(C.Structure):
@@ -67,6 +69,9 @@ class McXs(C.Structure):
         ("compt", (C.c_float * TABLE_ROWS) * MAX_MATERIALS),
         ("photo", (C.c_float * TABLE_ROWS) * MAX_MATERIALS),
         ("total", (C.c_float * TABLE_ROWS) * MAX_MATERIALS),
+        ("ff_points", C.c_int32),
+        ("ff_x2", (C.c_float * FF_POINTS) * MAX_MATERIALS),
+        ("ff_cum", (C.c_float * FF_POINTS) * MAX_MATERIALS),
     ]
 
 
@@ -87,7 +92,7 @@ class McGeom(C.Structure):
         ("pixel", C.c_double), ("half", C.c_double),
         ("dso", C.c_double), ("dod", C.c_double),
         ("source_mode", C.c_int32), ("max_scatter", C.c_int32),
-        ("detector_mode", C.c_int32), ("reserved", C.c_int32),
+        ("detector_mode", C.c_int32), ("coherent_mode", C.c_int32),
     ]
 
 

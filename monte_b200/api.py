@@ -81,6 +81,7 @@ def _bind(path):
         "monte_make_sphere": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
         "monte_ctnum_to_mu": (C.c_int, [vp, sz, C.POINTER(McXs), C.c_double, C.c_float, C.c_float, vp, vp]),
         "monte_xs_majorant": (C.c_int, [C.POINTER(McXs), vp, sz, vp]),
+        "monte_xs_formfactor_hydrogenic": (C.c_int, [C.POINTER(McXs), C.c_int, C.c_double]),
         "monte_gpu_fdk_slab_rows": (C.c_int, [C.POINTER(FdkGeom), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     }
     missing = []

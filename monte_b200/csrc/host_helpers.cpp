@@ -158,4 +158,24 @@ int monte_xs_majorant(const monte_mc_xs *xs, const uint8_t *labels, size_t n, fl
     return MONTE_OK;
 }
 
+/* Analytic stand-in for a measured Rayleigh form factor (the reference ships none, and has no deflection at
+ * all: CBCT_real325im.cu:656-695): F(x)^2 ~ (1 + x^2/x0^2)^-4, the hydrogen-like 1s charge cloud, so that
+ * integral_0^{x2} F^2 d(x^2) = x0^2/3 * (1 - (1 + x2/x0^2)^-3).  Grid: x2[0] = 0, then logarithmic from 1e-4
+ * to 270 1/A^2 ((200 keV / 12.398 keV A)^2 = 260 is the largest x^2 a table row can ask for).               */
+int monte_xs_formfactor_hydrogenic(monte_mc_xs *xs, int material, double x0) {
+    if (!xs || material < 0 || material >= MONTE_MC_MAX_MATERIALS || !(x0 > 0)) {
+        monte::set_error("monte_xs_formfactor_hydrogenic: bad argument");
+        return MONTE_E_ARG;
+    }
+    const int n = MONTE_MC_FF_POINTS;
+    const double lo = 1e-4, hi = 270.0, ratio = pow(hi / lo, 1.0 / (n - 2));
+    for (int i = 0; i < n; i++) {
+        const double x2 = i == 0 ? 0.0 : (i == n - 1 ? hi : lo * pow(ratio, i - 1));
+        xs->ff_x2[material][i] = (float)x2;
+        xs->ff_cum[material][i] = (float)(x0 * x0 / 3.0 * (1.0 - pow(1.0 + (double)(float)x2 / (x0 * x0), -3.0)));
+    }
+    xs->ff_points = n;
+    return MONTE_OK;
+}
+
 }  // extern "C"

@@ -59,6 +59,9 @@ struct McLaunch {
     uint32_t *fates;              // RECORD only
     float *fate_e;
     uint32_t second_min;          // run the runner-up phase on the same vote if >= this many lanes wait for it
+    // RAYLEIGH instantiations only (appended: the parameter offsets of everything above do not move)
+    const float *ray;             // [n_mat][2][ray_n]: x^2 grid, then cumulative F^2 (monte_mc_xs.ff_x2 / ff_cum)
+    int ray_n;
 };
 
 // stats word indices
@@ -105,13 +108,25 @@ enum : uint32_t { P_REFILL = 1u, P_STEP = 2u, P_COLLIDE = 4u, P_COMPTON = 8u };
 // so that a warp's LDS.128 / STS.128 touches 512 contiguous bytes (conflict-free):
 //   G_POS : x, y, z, E            G_DIR : dx, dy, dz, u_phi
 //   G_ID  : c0, META, CTR, PIXVIEW            G_REC : record index (fate dump only)
-// META: bits 0-7 kE, 8-11 nint, 12-14 material, 15 pending-detect, 24-31 high byte of the history id
+// META: bits 0-7 kE, 8-11 nint, 12-14 material, 15 pending-detect, 16 coherent event waiting for its angle
+//       (RAYLEIGH kernels), 24-31 high byte of the history id
 // CTR : bits 0-19 flight-stream index, 20-31 event-stream index
 // PIXVIEW: bits 0-19 pixel, 20-31 view
 enum { G_POS = 0, G_DIR = 1, G_ID = 2, G_REC = 3 };
 constexpr int mc_slot_groups(bool record) { return record ? 4 : 3; }
 
-template <bool RECORD, int K, int MINB = 3, int NSTEP = 2>
+// y(v) by linear interpolation in a table (xs ascending, n >= 2), v clamped to the table's range
+__device__ __forceinline__ float ray_interp(const float *xs, const float *ys, int n, float v) {
+    int lo = 0, hi = n - 2;                      // largest i <= n-2 with xs[i] <= v
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (xs[mid] <= v) lo = mid; else hi = mid - 1; }
+    const float x0 = xs[lo], w = xs[lo + 1] - x0;
+    const float t = w > 0.f ? fminf(fmaxf(__fdividef(v - x0, w), 0.f), 1.f) : 0.f;
+    return fmaf(t, ys[lo + 1] - ys[lo], ys[lo]);
+}
+
+// RAYLEIGH = true: monte_mc_geom.coherent_mode == MONTE_MC_COHERENT_FORMFACTOR (off in parity mode).
+// A coherent event then waits in the COMPTON phase for its angle: one rejection round per visit, like Kahn's.
+template <bool RECORD, int K, int MINB = 3, int NSTEP = 2, bool RAYLEIGH = false>
 __global__ void __launch_bounds__(MC_THREADS, MINB)
 mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
     MONTE_DYN_SMEM(float4, s_mem);
@@ -121,10 +136,15 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
     float *s_cdf = s_inv + TAB_ROWS + 3;                               // [n_bins+1]
     constexpr int NG = mc_slot_groups(RECORD);
     constexpr int GSTRIDE = K * 32;                                    // uint4 per group per warp
-    uint4 *s_slots = reinterpret_cast<uint4 *>(s_cdf + ((sc.n_bins + 1 + 3) & ~3)) + (threadIdx.x >> 5) * (NG * GSTRIDE);
+    float *s_ray = s_cdf + ((sc.n_bins + 1 + 3) & ~3);                 // RAYLEIGH: [n_mat][2][ray_n], ray_n padded to 4
+    const int ray_stride = RAYLEIGH ? ((P.ray_n + 3) & ~3) : 0;
+    uint4 *s_slots = reinterpret_cast<uint4 *>(s_ray + sc.n_mat * 2 * ray_stride) + (threadIdx.x >> 5) * (NG * GSTRIDE);
     for (int i = threadIdx.x; i < sc.n_mat * TAB_ROWS; i += MC_THREADS) s_tab[i] = sc.tab[i];
     for (int i = threadIdx.x; i < TAB_ROWS; i += MC_THREADS) s_inv[i] = sc.inv_mumax[i];
     for (int i = threadIdx.x; i <= sc.n_bins && sc.n_bins > 0; i += MC_THREADS) s_cdf[i] = sc.cdf[i];
+    if (RAYLEIGH)
+        for (int i = threadIdx.x; i < sc.n_mat * 2 * P.ray_n; i += MC_THREADS)
+            s_ray[(i / P.ray_n) * ray_stride + i % P.ray_n] = P.ray[i];
     __syncthreads();
 
     const unsigned lane = threadIdx.x & 31u;
@@ -282,7 +302,13 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 c_abs++;
                 if (RECORD) { P.fates[WORD(G_REC, 0)] = 3u | ((uint32_t)(nint + 1) << 28); P.fate_e[WORD(G_REC, 0)] = pos.w; }
                 st = (st & clr) | (P_REFILL << (4 * j));
-            } else if (u_sel <= tb.z) { c_coh++; st = (st & clr) | (P_STEP << (4 * j)); }    // coherent: no deflection
+            } else if (u_sel <= tb.z) {                               // coherent: no deflection (:656-695) ...
+                c_coh++;
+                if (RAYLEIGH) {                                       // ... or an angle from the form factor
+                    WORD(G_ID, 1) = meta | 0x10000u; WORDF(G_DIR, 3) = u01(re.y);
+                    st = (st & clr) | (P_COMPTON << (4 * j));
+                } else st = (st & clr) | (P_STEP << (4 * j));
+            }
             else { c_comp++; WORDF(G_DIR, 3) = u01(re.y); st = (st & clr) | (P_COMPTON << (4 * j)); }
             continue;
         }
@@ -299,6 +325,19 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             const uint2 ra = philox2x32_10(id.x, (id.y & 0xFF000000u) | (STREAM_EVENT << 22) | ne, P.key);
             id.z += 0x100000u;
             const float r2 = u01(ra.x), r3 = u01(ra.y);
+            float cos_t, E;
+            if (RAYLEIGH && (id.y & 0x10000u)) {
+                // one round of form-factor sampling: x^2 from F^2 on [0, x^2_max], accepted with (1 + cos^2)/2
+                const int rn = P.ray_n;
+                const float *gx = s_ray + ((id.y >> 12) & 0x7u) * 2 * ray_stride, *gc = gx + ray_stride;
+                const float xm = E0 * (1.0f / 12.3984193f), x2max = xm * xm;
+                const float amax = ray_interp(gx, gc, rn, x2max);
+                const float x2 = fminf(ray_interp(gc, gx, rn, r2 * amax), x2max);
+                cos_t = fmaxf(1.0f - 2.0f * __fdividef(x2, x2max), -1.0f);
+                if (!(r3 <= 0.5f * (1.0f + cos_t * cos_t))) { WORD(G_ID, 2) = id.z; continue; }
+                id.y &= ~0x10000u;
+                E = E0;
+            } else {
             const float r1 = ((float)(((ra.x & 0x1FFu) << 9) | (ra.y & 0x1FFu)) + 0.5f) * (1.0f / 262144.0f);
             const bool br1 = r1 * (9.0f * lam + 2.0f) < (lam + 2.0f);
             const float ro1 = 1.0f + __fdividef(2.0f, lam) * r2;
@@ -309,10 +348,11 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             const float lim = br1 ? 4.0f * (iro - iro * iro) : 0.5f * (t * t + iro);
             if (!(r3 <= lim)) { WORD(G_ID, 2) = id.z; continue; }     // rejected: next round next time
             const float lam_d = ro * lam;
-            float cos_t = 1.0f - (lam_d - lam);
+            cos_t = 1.0f - (lam_d - lam);
             cos_t = fmaxf(cos_t, -1.0f);                              // :746-747
+            E = __fdividef(511.0f, lam_d);
+            }
             const float sin_t = sqrtf(fmaxf(0.f, 1.0f - cos_t * cos_t));
-            const float E = __fdividef(511.0f, lam_d);
             const int kE = min(max((int)(E + 0.5f), 0), TAB_ROWS - 1);
             WORDF(G_POS, 3) = E;
             id.y = (id.y & ~0xFFu) | (uint32_t)kE;
@@ -513,8 +553,9 @@ using namespace monte;
 struct monte_mc_scene {
     McSceneDev dev;
     monte_mc_geom geom;
-    void *d_labels = nullptr, *d_tab = nullptr, *d_inv = nullptr, *d_cdf = nullptr, *d_view = nullptr;
-    size_t cap_labels = 0, cap_tab = 0, cap_cdf = 0, cap_view = 0;     // grow-only capacities (bytes)
+    void *d_labels = nullptr, *d_tab = nullptr, *d_inv = nullptr, *d_cdf = nullptr, *d_view = nullptr, *d_ray = nullptr;
+    size_t cap_labels = 0, cap_tab = 0, cap_cdf = 0, cap_view = 0, cap_ray = 0;     // grow-only capacities (bytes)
+    int ray_n = 0;                                                     // > 0: form-factor tables uploaded (coherent_mode 1)
     unsigned long long *d_work = nullptr;
     size_t smem = 0;
     size_t h2d_bytes = 0;
@@ -531,6 +572,19 @@ static int check_mc(const monte_mc_geom *g, const monte_mc_volume *vol, const mo
     MONTE_ARG(vol->nx > 0 && vol->ny > 0 && vol->nz > 0 && vol->pitch > 0, "mc: bad volume");
     MONTE_ARG((uint64_t)vol->nx * vol->ny * vol->nz < (1ull << 32), "mc: label volume has 2^32 voxels or more");
     MONTE_ARG(xs->n_materials >= 1 && xs->n_materials <= MONTE_MC_MAX_MATERIALS, "mc: n_materials must be 1..%d", MONTE_MC_MAX_MATERIALS);
+    MONTE_ARG(g->coherent_mode == MONTE_MC_COHERENT_FORWARD || g->coherent_mode == MONTE_MC_COHERENT_FORMFACTOR,
+              "mc: unknown coherent_mode %d", g->coherent_mode);
+    if (g->coherent_mode == MONTE_MC_COHERENT_FORMFACTOR) {
+        MONTE_ARG(xs->ff_points >= 2 && xs->ff_points <= MONTE_MC_FF_POINTS,
+                  "mc: coherent_mode FORMFACTOR needs form-factor tables (ff_points = %d, must be 2..%d)", xs->ff_points, MONTE_MC_FF_POINTS);
+        for (int m = 0; m < xs->n_materials; m++) {
+            MONTE_ARG(xs->ff_x2[m][0] == 0.f && xs->ff_cum[m][0] == 0.f, "mc: form-factor table of material %d must start at (0, 0)", m);
+            for (int i = 1; i < xs->ff_points; i++)
+                MONTE_ARG(xs->ff_x2[m][i] > xs->ff_x2[m][i - 1] && xs->ff_cum[m][i] >= xs->ff_cum[m][i - 1],
+                          "mc: form-factor table of material %d is not ascending at point %d", m, i);
+            MONTE_ARG(xs->ff_cum[m][xs->ff_points - 1] > 0.f, "mc: form-factor table of material %d is all zero", m);
+        }
+    }
     const int dims[3] = {vol->nx, vol->ny, vol->nz};
     for (int a = 0; a < 3; a++) {
         MONTE_ARG(vol->clip_lo[a] < vol->clip_hi[a], "mc: empty clip box");
@@ -600,6 +654,19 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
             d.cdf = (const float *)s->d_cdf;
         }
     }
+    s->ray_n = 0;
+    size_t ray_bytes = 0;
+    if (g->coherent_mode == MONTE_MC_COHERENT_FORMFACTOR) {           // [material][x^2 grid | cumulative F^2][ff_points]
+        const int rn = xs->ff_points;
+        std::vector<float> ray((size_t)nm * 2 * rn);
+        for (int m = 0; m < nm; m++)
+            for (int i = 0; i < rn; i++) { ray[((size_t)m * 2) * rn + i] = xs->ff_x2[m][i]; ray[((size_t)m * 2 + 1) * rn + i] = xs->ff_cum[m][i]; }
+        ray_bytes = ray.size() * sizeof(float);
+        if (int rc = grow(&s->d_ray, &s->cap_ray, ray_bytes)) return rc;
+        MONTE_CUDA(cudaMemcpyAsync(s->d_ray, ray.data(), ray_bytes, cudaMemcpyHostToDevice, st));
+        MONTE_CUDA(cudaStreamSynchronize(st));                         // `ray` is pageable and goes out of scope
+        s->ray_n = rn;
+    }
     std::vector<float2> vcs(g->n_views);
     for (int v = 0; v < g->n_views; v++) {
         const double beta = M_PI * (g->angle0_deg + g->angle_step_deg * v) / 180;
@@ -615,7 +682,7 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
     d.eid = g->detector_mode == MONTE_MC_DETECTOR_ENERGY ? 1 : 0;
     if (!s->d_work) MONTE_CUDA(cudaMalloc(&s->d_work, sizeof(unsigned long long)));
     s->smem = (size_t)nm * TAB_ROWS * sizeof(float4) + (TAB_ROWS + 3 + d.n_bins + 1) * sizeof(float);
-    s->h2d_bytes = nvox + tab_bytes + inv_bytes + cdf_bytes + vcs.size() * sizeof(float2);
+    s->h2d_bytes = nvox + tab_bytes + inv_bytes + cdf_bytes + ray_bytes + vcs.size() * sizeof(float2);
     // the host vectors above are pageable: the async copies have already staged them
     MONTE_CUDA(cudaStreamSynchronize(st));
     return MONTE_OK;
@@ -643,7 +710,7 @@ int monte_gpu_scene_update_labels(monte_mc_scene *s, const uint8_t *labels, void
 
 void monte_gpu_scene_destroy(monte_mc_scene *s) {
     if (!s) return;
-    cudaFree(s->d_labels); cudaFree(s->d_tab); cudaFree(s->d_cdf); cudaFree(s->d_view); cudaFree(s->d_work);
+    cudaFree(s->d_labels); cudaFree(s->d_tab); cudaFree(s->d_cdf); cudaFree(s->d_view); cudaFree(s->d_work); cudaFree(s->d_ray);
     delete s;
 }
 
@@ -666,6 +733,7 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     L.n_units = (L.total + MC_UNIT - 1) / MC_UNIT;
     L.image0 = d_image0; L.image5 = d_image5; L.stats = d_stats; L.work = s->d_work;
     L.fates = d_fates; L.fate_e = d_fate_e;
+    L.ray = (const float *)s->d_ray; L.ray_n = s->ray_n;
     { static int sm = -1; if (sm < 0) { const char *e = getenv("MONTE_MC_SECOND"); sm = e ? atoi(e) : 16; } L.second_min = (uint32_t)sm; }
     if (L.total == 0) return MONTE_OK;
     MONTE_CUDA(cudaMemsetAsync(s->d_work, 0, sizeof(unsigned long long), st));
@@ -673,16 +741,21 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     const unsigned long long warps_needed = L.n_units;
     // K = 5 parked histories per lane is the default (measured: K=4 9.83 ms, K=5 9.45 ms, K=6 11.2 ms per
     // 1e8 C2 histories before the later trims); MONTE_MC_KERNEL=31..36 selects K=1..6 for A/B runs
-    static int which = -1;
-    if (which < 0) { const char *e = getenv("MONTE_MC_KERNEL"); which = e ? atoi(e) : 35; }
+    static int which_env = -1;
+    if (which_env < 0) { const char *e = getenv("MONTE_MC_KERNEL"); which_env = e ? atoi(e) : 35; }
     MONTE_ARG(s->geom.n_views < 4096, "mc: more than 4095 views");
     const int rec = d_fates ? 1 : 0;
+    const bool rayleigh = s->ray_n > 0;      // form-factor deflection of coherent events: its own instantiation (K = 5)
+    const int which = rayleigh ? 35 : which_env;
     const int K = which >= 31 && which <= 36 ? which - 30 : (which == 44 ? 4 : (which == 43 ? 3 : 5));
     const size_t slot_bytes = (size_t)K * 32 * mc_slot_groups(rec != 0) * sizeof(uint4) * (MC_THREADS / 32);
     const size_t smem = (size_t)s->dev.n_mat * TAB_ROWS * sizeof(float4) +
-                        (TAB_ROWS + 3 + ((s->dev.n_bins + 1 + 3) & ~3)) * sizeof(float) + slot_bytes;
+                        (TAB_ROWS + 3 + ((s->dev.n_bins + 1 + 3) & ~3)) * sizeof(float) + slot_bytes +
+                        (rayleigh ? (size_t)s->dev.n_mat * 2 * ((s->ray_n + 3) & ~3) * sizeof(float) : 0);
     const void *fn = nullptr;
-    switch (which * 2 + rec) {
+    switch (rayleigh ? 200 + rec : which * 2 + rec) {
+        case 200: fn = (const void *)mc_transport_kernel_v3<false, 5, 3, 2, true>; break;
+        case 201: fn = (const void *)mc_transport_kernel_v3<true, 5, 3, 2, true>; break;
         case 62: fn = (const void *)mc_transport_kernel_v3<false, 1>; break;
         case 63: fn = (const void *)mc_transport_kernel_v3<true, 1>; break;
         case 64: fn = (const void *)mc_transport_kernel_v3<false, 2>; break;
@@ -703,7 +776,7 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     }
     static int occ[96] = {0};                      // resident CTAs per SM: persistent grid = SMs x occupancy
     static size_t smem_set[96] = {0}, smem_occ[96] = {0};
-    const int slot_id = (which * 2 + rec) % 96;
+    const int slot_id = rayleigh ? 94 + rec : (which * 2 + rec) % 96;     // 94, 95: no `which` maps there (31..46 -> 62..93)
     int &oc = occ[slot_id];
     MONTE_ARG(smem <= 227 * 1024, "mc: %zu bytes of shared memory needed (> 227 KB)", smem);
     if (smem > smem_set[slot_id]) {

@@ -41,6 +41,23 @@ def make_xs(materials=("h2o", "ca"), quirk_bom=False):
     return xs
 
 
+# x0 (1/Angstrom) of the analytic hydrogen-like form factor F^2 ~ (1 + x^2/x0^2)^-4 used where Rayleigh deflection
+# is switched on (monte_xs_formfactor_hydrogenic; the reference ships no form-factor data): 0.30 * Z_eff
+FF_X0 = {"h2o": 1.0, "ca": 2.2, "pmma": 0.9}
+
+
+def add_formfactors(xs, materials=("h2o", "ca")):
+    """fill the Rayleigh form-factor tables of `xs` (needed for McGeom.coherent_mode = COHERENT_FORMFACTOR);
+    a host helper of libmonte_gpu, no device needed"""
+    from . import api
+    lib = api.load()
+    for m, name in enumerate(materials):
+        rc = lib.monte_xs_formfactor_hydrogenic(C.byref(xs), m, FF_X0[name])
+        if rc != 0:
+            raise api.MonteError(lib.monte_gpu_last_error().decode())
+    return xs
+
+
 def cylinder_phantom(n, pitch, radius=10.0, half_len=10.0, rods=True, rod_r=1.5, rod_ring=5.0):
     """Water cylinder (axis z) with 8 calcium rods every 45 degrees — the analytic phantom of
     CBCT_real325.cu:916-921 re-oriented as in CBCT_real325im.cu:903-904, voxelised to uint8 labels

@@ -142,7 +142,10 @@ class OracleTables(C.Structure):
                 ("coh", (C.c_double * _abi.TABLE_ROWS) * _abi.MAX_MATERIALS),
                 ("compt", (C.c_double * _abi.TABLE_ROWS) * _abi.MAX_MATERIALS),
                 ("photo", (C.c_double * _abi.TABLE_ROWS) * _abi.MAX_MATERIALS),
-                ("total", (C.c_double * _abi.TABLE_ROWS) * _abi.MAX_MATERIALS)]
+                ("total", (C.c_double * _abi.TABLE_ROWS) * _abi.MAX_MATERIALS),
+                ("ff_points", C.c_int32),
+                ("ff_x2", (C.c_double * _abi.FF_POINTS) * _abi.MAX_MATERIALS),
+                ("ff_cum", (C.c_double * _abi.FF_POINTS) * _abi.MAX_MATERIALS)]
 
 
 class OracleOpts(C.Structure):
@@ -180,6 +183,9 @@ def tables_from_xs(xs):
         for k in range(_abi.TABLE_ROWS):
             t.coh[m][k], t.compt[m][k] = xs.coh[m][k], xs.compt[m][k]
             t.photo[m][k], t.total[m][k] = xs.photo[m][k], xs.total[m][k]
+        for i in range(xs.ff_points):
+            t.ff_x2[m][i], t.ff_cum[m][i] = xs.ff_x2[m][i], xs.ff_cum[m][i]
+    t.ff_points = xs.ff_points
     return t
 
 
@@ -279,3 +285,12 @@ def ref_cbct_real2(timeout=600):
         return img, c, sphere
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+def rayleigh_round(tables, material, keV, r_a, r_acc):
+    """one rejection round of the form-factor sampler: (accepted, cos_theta)"""
+    c = C.c_double(0.0)
+    fn = lib().oracle_rayleigh_round
+    fn.restype = C.c_int
+    ok = fn(C.byref(tables), C.c_int(material), C.c_double(keV), C.c_double(r_a), C.c_double(r_acc), C.byref(c))
+    return bool(ok), c.value

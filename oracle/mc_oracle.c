@@ -67,6 +67,11 @@ typedef struct oracle_mc_tables {       /* double tables, index = keV 0..200, [m
     double compt[MONTE_MC_MAX_MATERIALS][MONTE_MC_TABLE_ROWS];
     double photo[MONTE_MC_MAX_MATERIALS][MONTE_MC_TABLE_ROWS];
     double total[MONTE_MC_MAX_MATERIALS][MONTE_MC_TABLE_ROWS];
+    /* Rayleigh form-factor tables (monte_mc_xs.ff_*; used only with coherent_mode FORMFACTOR, which the
+     * reference does not have: its coherent event keeps the direction, CBCT_real325im.cu:656-695) */
+    int32_t ff_points;
+    double ff_x2[MONTE_MC_MAX_MATERIALS][MONTE_MC_FF_POINTS];
+    double ff_cum[MONTE_MC_MAX_MATERIALS][MONTE_MC_FF_POINTS];
 } oracle_mc_tables;
 
 typedef struct oracle_mc_opts {
@@ -262,6 +267,33 @@ static int delta_sampling(const scene_t *S, rng_t *R, photon_t *p, double E, dou
 #define TALLY(x) __atomic_fetch_add(&(x), (g->detector_mode == MONTE_MC_DETECTOR_ENERGY ? (int)(E * MONTE_MC_EID_SCALE + 0.5) : 1), __ATOMIC_RELAXED)
 
 /* detector bin: result = -1*(int(d*inv_pixel - n/2.))   CBCT_real325im.cu:574-575 / CBCT_real2.cpp:311 */
+/* ---- Rayleigh angle from a tabulated form factor (not in the reference): x = sin(theta/2)/lambda,
+ * x^2 drawn from F(x)^2 on [0, x^2_max = (E/12.398)^2] by inverting the cumulative table, accepted with
+ * probability (1 + cos^2 theta)/2, cos theta = 1 - 2 x^2/x^2_max.  Same arithmetic as the CUDA kernel's
+ * ray_interp (monte_b200/csrc/mc.cu), in double. */
+static double ff_interp(const double *xs, const double *ys, int n, double v) {
+    int lo = 0, hi = n - 2;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (xs[mid] <= v) lo = mid; else hi = mid - 1; }
+    double w = xs[lo + 1] - xs[lo], t = 0;
+    if (w > 0) { t = (v - xs[lo]) / w; if (t < 0) t = 0; if (t > 1) t = 1; }
+    return ys[lo] + t * (ys[lo + 1] - ys[lo]);
+}
+/* one rejection round; returns 1 if accepted */
+static int rayleigh_round(const oracle_mc_tables *tb, int m, double E, double r_a, double r_acc, double *cos_theta) {
+    const int n = tb->ff_points;
+    const double xm = E * (double)(1.0f / 12.3984193f), x2max = xm * xm;
+    const double amax = ff_interp(tb->ff_x2[m], tb->ff_cum[m], n, x2max);
+    double x2 = ff_interp(tb->ff_cum[m], tb->ff_x2[m], n, r_a * amax);
+    if (x2 > x2max) x2 = x2max;
+    double c = 1.0 - 2.0 * x2 / x2max;
+    if (c < -1) c = -1;
+    *cos_theta = c;
+    return r_acc <= 0.5 * (1.0 + c * c);
+}
+int oracle_rayleigh_round(const oracle_mc_tables *tb, int m, double E, double r_a, double r_acc, double *cos_theta) {
+    return rayleigh_round(tb, m, E, r_a, r_acc, cos_theta);
+}
+
 static int det_bin(double d, double inv_pixel, int n) { return -1 * ((int)(d * inv_pixel - n / 2.)); }
 
 static double sample_energy(const scene_t *S, double u) {
@@ -411,6 +443,34 @@ static void history(const scene_t *S, rng_t *R, int view, int i, int j, uint64_t
             } else if (ab / mu < sc_rand && sc_rand <= (ab + coh) / mu) {   /* coherent, :656-695: no deflection */
                 res->coherent++;
                 res->num_scatter--;                         /* CBCT_real2.cpp:377 */
+                if (g->coherent_mode == MONTE_MC_COHERENT_FORMFACTOR) {
+                    /* not in the reference: deflect by an angle drawn from the form factor, then carry on exactly
+                     * like the reference's coherent event.  Philox mode: one block per rejection round, phi from the
+                     * second word of the interaction's own block (as for Compton). */
+                    double cos_theta = 1.0;
+                    for (;;) {
+                        double r_a, r_acc;
+                        if (R->mode == ORACLE_RNG_MT) { r_a = mt_real3(R->mt); r_acc = mt_real3(R->mt); }
+                        else rng_pair(R, STREAM_EVENT, R->n_event++, &r_a, &r_acc);
+                        if (rayleigh_round(S->tb, m, E, r_a, r_acc, &cos_theta)) break;
+                    }
+                    double sin_theta = sqrt(1. - cos_theta * cos_theta);
+                    if (R->mode == ORACLE_RNG_MT) u_phi = mt_real3(R->mt);
+                    double phi = u_phi * 2. * M_PI;
+                    if (com_flag) {                         /* same update as Compton's, CBCT_real325im.cu:768-780 */
+                        sin_theta_a = sin_theta_a_new; cos_theta_a = cos_theta_a_new;
+                        sin_phi_a = sin_phi_a_new; cos_phi_a = cos_phi_a_new;
+                    }
+                    cos_theta_a_new = cos_theta_a * cos_theta - sin_theta_a * sin_theta * cos(phi);
+                    if (cos_theta_a_new < -1) cos_theta_a_new = -1;
+                    if (cos_theta_a_new > 1) cos_theta_a_new = 1;
+                    sin_theta_a_new = sqrt(1. - pow(cos_theta_a_new, 2));
+                    if (sin_theta_a_new > 1e-9) {
+                        cos_phi_a_new = (cos_theta_a * cos_phi_a * sin_theta * cos(phi) + sin_theta_a * cos_phi_a * cos_theta - sin_phi_a * sin_theta * sin(phi)) / sin_theta_a_new;
+                        sin_phi_a_new = (cos_theta_a * sin_phi_a * sin_theta * cos(phi) + sin_theta_a * sin_phi_a * cos_theta + cos_phi_a * sin_theta * sin(phi)) / sin_theta_a_new;
+                    } else { cos_phi_a_new = cos_phi_a; sin_phi_a_new = sin_phi_a; }     /* along +-z: azimuth is immaterial */
+                    com_flag = 1;
+                }
                 if (!com_flag) collided = delta_sampling(S, R, &P, E, sin_theta_a0, cos_theta_a0, sin_phi_a0, cos_phi_a0, &steps);
                 else collided = delta_sampling(S, R, &P, E, sin_theta_a_new, cos_theta_a_new, sin_phi_a_new, cos_phi_a_new, &steps);
                 if (!(q & OQ_DETECT_UNROT)) {               /* GPU form tallies here, CBCT_real325im.cu:672-694 */

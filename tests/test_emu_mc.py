@@ -103,3 +103,21 @@ print(st["histories"], st["woodcock_steps"], st["interactions"])
             outs[w] = (np.load(path), r.stdout.strip())
     assert np.array_equal(outs["35"][0], outs[which][0])
     assert outs["35"][1] == outs[which][1]
+
+
+# ---- Rayleigh form-factor deflection (coherent_mode = FORMFACTOR): the GPU test bodies of
+# tests/test_zz_rayleigh_gpu.py on the emulated kernel
+import test_zz_rayleigh_gpu as R   # noqa: E402
+
+
+@pytest.mark.parametrize("keV,poly", [(60.0, False), (30.0, False), (0.0, True)])
+def test_emu_formfactor_history_coupled_fates_match_oracle(monte_emu, oracle, keV, poly):
+    R.test_formfactor_history_coupled_fates_match_oracle(monte_emu, oracle, keV, poly)
+
+
+def test_emu_formfactor_images_counters_and_difference_from_forward_mode(monte_emu, oracle):
+    R.test_formfactor_images_counters_and_difference_from_forward_mode(monte_emu, oracle)
+
+
+def test_emu_formfactor_mode_needs_tables(monte_emu):
+    R.test_formfactor_mode_needs_tables(monte_emu)

@@ -165,3 +165,57 @@ def test_energy_integrating_detector_mode(oracle):
     scat = (e5.astype(np.int64) - e0).sum()
     assert abs(scat / 16.0 - re["sum_e_scatter"]) <= 0.5 / 16 * re["scatter_detected"] + 1e-6
     assert scat < 16 * 140 * re["scatter_detected"]            # Compton-scattered photons arrive with less than 140 keV
+
+
+@pytest.mark.parametrize("keV,x0", [(30.0, 1.0), (80.0, 2.2), (140.0, 0.9)])
+def test_rayleigh_formfactor_sampler_against_closed_form(oracle, keV, x0):
+    """SURVEY 8f-3 (coherent_mode FORMFACTOR; not in the reference): the accepted cos(theta) of the table sampler
+    follow p(c) ~ (1 + c^2) F(x)^2, x^2 = x2max (1 - c)/2, for the analytic F^2 = (1 + x^2/x0^2)^-4 the tables were
+    built from (monte_xs_formfactor_hydrogenic)."""
+    from monte_b200 import api
+    xs = scenes.make_xs()
+    assert api.load().monte_xs_formfactor_hydrogenic(xs, 0, x0) == 0
+    api.load().monte_xs_formfactor_hydrogenic(xs, 1, 1.0)
+    assert xs.ff_points == 128 and xs.ff_x2[0][0] == 0.0 and xs.ff_x2[0][127] >= (200 / 12.3984) ** 2
+    tb = oracle.tables_from_xs(xs)
+    rng = np.random.default_rng(int(keV))
+    n = 60000
+    u = rng.random((n, 2))
+    cs = np.array([c for ok, c in (oracle.rayleigh_round(tb, 0, keV, a, b) for a, b in u) if ok])
+    assert 0.5 * n <= cs.size <= n                                     # acceptance (1 + c^2)/2 >= 1/2
+    x2max = (keV / 12.3984193) ** 2
+    edges = np.linspace(-1.0, 1.0, 21)
+    fine = np.linspace(-1.0, 1.0, 200001)
+    pdf = (1 + fine ** 2) * (1 + x2max * (1 - fine) / 2 / x0 ** 2) ** -4.0
+    cdf = np.concatenate([[0.0], np.cumsum(0.5 * (pdf[1:] + pdf[:-1]) * np.diff(fine))])
+    expect = np.diff(np.interp(edges, fine, cdf)) / cdf[-1] * cs.size
+    got = np.histogram(cs, edges)[0]
+    big = expect > 20
+    chi2 = ((got[big] - expect[big]) ** 2 / expect[big]).sum()
+    dof = int(big.sum()) - 1
+    assert chi2 < dof + 6 * math.sqrt(2 * dof) + 10, (chi2, dof, got, expect)   # + table-interpolation bias (128 points)
+    # forward peaked, and the more so the higher the energy / the more diffuse the charge cloud
+    assert cs.mean() > 0.2
+
+
+def test_rayleigh_mode_changes_only_coherent_histories(oracle):
+    """with the form factor on, every history without a coherent event keeps its fate; energy is unchanged by
+    coherent events (elastic): detected single-coherent photons still carry the source energy"""
+    lab = scenes.cylinder_phantom(33, 1.0)
+    g = scenes.mc_geom(9, 32.5 / 9, n_views=1)
+    vol = scenes.volume_for(lab, 1.0)
+    xs = scenes.add_formfactors(scenes.make_xs())
+    tb = oracle.tables_from_xs(xs)
+    opts = oracle.mc_opts(oracle.RNG_PHILOX, seed=4)
+    a0, a5, ra, fa, ea = oracle.mc_run(g, vol, lab, tb, scenes.mono_spectrum(40.0), opts, 400, want_fates=True)
+    g.coherent_mode = 1
+    b0, b5, rb, fb, eb = oracle.mc_run(g, vol, lab, tb, scenes.mono_spectrum(40.0), opts, 400, want_fates=True)
+    assert np.array_equal(a0, b0) and ra["primaries"] == rb["primaries"]
+    changed = fa != fb
+    assert 0.01 < changed.mean() < 0.3
+    assert rb["coherent"] > 0 and rb["scatter_detected"] < ra["scatter_detected"]    # deflected photons mostly miss
+    # MT19937 mode runs too and agrees statistically on the totals
+    g.coherent_mode = 1
+    c0, c5, rc, _, _ = oracle.mc_run(g, vol, lab, tb, scenes.mono_spectrum(40.0), oracle.mc_opts(oracle.RNG_MT, seed=3), 400)
+    for k in ("absorbed", "coherent", "compton"):
+        assert abs(rc[k] - rb[k]) < 6 * math.sqrt(rc[k] + rb[k] + 1), (k, rc[k], rb[k])
