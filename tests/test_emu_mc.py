@@ -106,8 +106,8 @@ print(st["histories"], st["woodcock_steps"], st["interactions"])
 
 
 # ---- Rayleigh form-factor deflection (coherent_mode = FORMFACTOR): the GPU test bodies of
-# tests/test_zz_rayleigh_gpu.py on the emulated kernel
-import test_zz_rayleigh_gpu as R   # noqa: E402
+# tests/test_rayleigh_gpu.py on the emulated kernel
+import test_rayleigh_gpu as R   # noqa: E402
 
 
 @pytest.mark.parametrize("keV,poly", [(60.0, False), (30.0, False), (0.0, True)])

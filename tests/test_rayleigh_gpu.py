@@ -3,8 +3,7 @@ MONTE_MC_COHERENT_FORMFACTOR).  The reference has no such mode (its coherent eve
 CBCT_real325im.cu:656-695), so parity here is against the oracle's restatement of the same sampler on the same
 Philox variates, history by history, and against the closed-form angular distribution (tests/test_oracle_mc.py).
 The default mode (FORWARD) is what every other MC test covers; the same bodies run on the CPU under SIMT
-emulation in tests/test_emu_mc.py.  (File name: sorted last on purpose -- the mode was added after the last
-GPU session of round 1, so on a B200 it runs after everything that had already been verified there.)
+emulation in tests/test_emu_mc.py.
 """
 import numpy as np
 import pytest
