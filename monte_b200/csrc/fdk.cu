@@ -526,9 +526,23 @@ struct FdkCache {           // per-geometry device constants, rebuilt only when 
     size_t vc_cap = 0, wtab_cap = 0, taps_cap = 0, fft_cap = 0;
 };
 static FdkCache g_fdk;
+// per-context state that must not survive monte_gpu_shutdown (a later monte_gpu_init may bind another device):
+// function attributes already raised, and the events of the host-buffer pipeline
+static bool g_fft_attr_set = false;
+static size_t g_filter_smem_set = 0;
+constexpr int FDK_MAXC = 16;
+static cudaEvent_t g_ev_up[FDK_MAXC] = {nullptr}, g_ev_slab[FDK_MAXC] = {nullptr}, g_ev_t[6] = {nullptr};
 static void fdk_cleanup() {
     cudaFree(g_fdk.d_vc); cudaFree(g_fdk.d_wtab); cudaFree(g_fdk.d_taps); cudaFree(g_fdk.d_tw); cudaFree(g_fdk.d_spec);
     g_fdk = FdkCache();
+    g_fft_attr_set = false;
+    g_filter_smem_set = 0;
+    for (int i = 0; i < FDK_MAXC; i++) {
+        if (g_ev_up[i]) cudaEventDestroy(g_ev_up[i]);
+        if (g_ev_slab[i]) cudaEventDestroy(g_ev_slab[i]);
+        g_ev_up[i] = g_ev_slab[i] = nullptr;
+    }
+    for (int i = 0; i < 6; i++) { if (g_ev_t[i]) cudaEventDestroy(g_ev_t[i]); g_ev_t[i] = nullptr; }
 }
 
 static int fdk_prepare(const monte_fdk_geom *g, cudaStream_t st) {
@@ -644,12 +658,11 @@ int monte_gpu_fdk_filter_dev(const monte_fdk_geom *g, const float *d_map, int vi
         const int L = g_fdk.fft_len;
         const size_t smem = fft_filter_smem(L);
         dim3 grid(ceil_div(g->nv, 2 * FFT_PAIRS), view_end - view_begin);
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (!g_fft_attr_set) {
             MONTE_CUDA(cudaFuncSetAttribute(fdk_weight_filter_fft_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_filter_smem(1024)));
             MONTE_CUDA(cudaFuncSetAttribute(fdk_weight_filter_fft_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_filter_smem(2048)));
             MONTE_CUDA(cudaFuncSetAttribute(fdk_weight_filter_fft_kernel<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_filter_smem(4096)));
-            attr_set = true;
+            g_fft_attr_set = true;
         }
         if (L == 1024) fdk_weight_filter_fft_kernel<1024> MONTE_CFG(grid, 128, smem, st)(q);
         else if (L == 2048) fdk_weight_filter_fft_kernel<2048> MONTE_CFG(grid, 256, smem, st)(q);
@@ -666,10 +679,9 @@ int monte_gpu_fdk_filter_dev(const monte_fdk_geom *g, const float *d_map, int vi
     p.center = (float)((textbook ? g->dsd / (g->dso * g->du) : g->filter_scale) * 0.25);
     const size_t smem = ((size_t)2 * FT_D * p.in_pitch + p.tap_len) * sizeof(float);
     MONTE_ARG(smem <= 227 * 1024, "fdk_filter: nu=%d needs %zu B of shared memory (> 227 KB)", g->nu, smem);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
+    if (smem > g_filter_smem_set) {
         MONTE_CUDA(cudaFuncSetAttribute(fdk_weight_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+        g_filter_smem_set = smem;
     }
     dim3 grid(ceil_div(g->nv, FT_D), view_end - view_begin);
     fdk_weight_filter_kernel MONTE_CFG(grid, FT_THREADS, smem, st)(p);
@@ -885,8 +897,8 @@ int monte_gpu_fdk(const monte_fdk_geom *g, const float *map, float *filtered, fl
     // Two streams: the copy stream uploads view chunks while the compute stream filters the previous
     // chunk, and downloads finished z-slabs while the next slab is backprojected.  With pinned host
     // buffers the copies are truly asynchronous; with pageable ones they still overlap the kernels.
-    constexpr int MAXC = 16;
-    static cudaEvent_t ev_up[MAXC] = {nullptr}, ev_slab[MAXC] = {nullptr}, ev_t[6] = {nullptr};
+    constexpr int MAXC = FDK_MAXC;
+    cudaEvent_t *ev_up = g_ev_up, *ev_slab = g_ev_slab, *ev_t = g_ev_t;     // destroyed by fdk_cleanup at shutdown
     if (!ev_up[0]) {
         for (int i = 0; i < MAXC; i++) {
             MONTE_CUDA(cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming));

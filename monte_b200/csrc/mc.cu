@@ -774,8 +774,11 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
         case 92: fn = (const void *)mc_transport_kernel_v3<false, 5, 3, 3>; break;   // which=46: three slots per STEP visit
         default: fn = rec ? (const void *)mc_transport_kernel_v3<true, 5> : (const void *)mc_transport_kernel_v3<false, 5>; break;
     }
-    static int occ[96] = {0};                      // resident CTAs per SM: persistent grid = SMs x occupancy
+    // resident CTAs per SM (persistent grid = SMs x occupancy) and the shared-memory attribute already raised, per
+    // kernel variant; per-context state: forgotten at monte_gpu_shutdown (a later init may bind another device)
+    static int occ[96] = {0};
     static size_t smem_set[96] = {0}, smem_occ[96] = {0};
+    at_shutdown([] { memset(occ, 0, sizeof(occ)); memset(smem_set, 0, sizeof(smem_set)); memset(smem_occ, 0, sizeof(smem_occ)); });
     const int slot_id = rayleigh ? 94 + rec : (which * 2 + rec) % 96;     // 94, 95: no `which` maps there (31..46 -> 62..93)
     int &oc = occ[slot_id];
     MONTE_ARG(smem <= 227 * 1024, "mc: %zu bytes of shared memory needed (> 227 KB)", smem);

@@ -167,3 +167,25 @@ def test_emu_bad_arguments_are_reported_not_fatal(monte_emu, monkeypatch):
     monkeypatch.setenv("MONTE_FDK_FILTER", "fft")
     with pytest.raises(m.MonteError, match="too wide"):
         m.fdk_filter_dev(gw, _Dev(d), _Dev(f))
+
+
+def test_emu_shutdown_and_reinit_rebuild_every_cache(monte_emu, oracle):
+    """monte_gpu_shutdown frees the cached device buffers, events and per-context attributes; a new
+    monte_gpu_init starts from scratch (host-buffer FDK with the 8-chunk pipeline, then MC) and gives the same bits"""
+    from monte_b200 import scenes
+    m = monte_emu
+    g = _abi.generic_fdk_geom(64, 40, 24, 128)
+    g.s_begin, g.s_end, g.t_begin, g.t_end = 60, 68, 60, 68
+    proj = rand(2, (64, 40, 24))
+    lab = scenes.cylinder_phantom(17, 2.0)
+    mg = scenes.mc_geom(9, 32.5 / 9, n_views=1)
+    args = (mg, scenes.volume_for(lab, 2.0), lab, scenes.make_xs(), scenes.mono_spectrum(), 20, 3)
+    f1, v1, _, _ = m.fdk(g, proj)
+    a0, a5, _ = m.simulate(*args)
+    m.shutdown()
+    with pytest.raises(m.MonteError, match="monte_gpu_init"):
+        m.fdk(g, proj)
+    m.init(0)
+    f2, v2, _, _ = m.fdk(g, proj)
+    b0, b5, _ = m.simulate(*args)
+    assert np.array_equal(f1, f2) and np.array_equal(v1, v2) and np.array_equal(a0, b0) and np.array_equal(a5, b5)
