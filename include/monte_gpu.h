@@ -27,7 +27,8 @@ extern "C" {
 #endif
 
 #define MONTE_GPU_ABI_VERSION 3   /* 2: monte_mc_geom.detector_mode; 3: monte_mc_geom.coherent_mode (was
-                                     `reserved`, 0 = unchanged behaviour) + form-factor tables appended to monte_mc_xs */
+                                     `reserved`, 0 = unchanged behaviour), form-factor tables appended to monte_mc_xs,
+                                     tracking_mode / clearance_cell_log2 appended to monte_mc_volume (0 = unchanged) */
 
 /* ---- status codes ------------------------------------------------------ */
 #define MONTE_OK            0
@@ -203,11 +204,24 @@ typedef struct monte_mc_xs {
  * CBCT_real2.cpp:771 rint(p*10)+90 -> origin -(90+0.5)*0.1.
  * Lookups happen only inside the clip box (CBCT_real2.cpp:770; the tight box around
  * the phantom); outside it the photon flies straight (air).                          */
+/* tracking_mode: how tentative collisions are sampled.  Both are exact (same physics, same expected tallies);
+ * they consume different variates, so a run is reproducible bit for bit only within one mode.               */
+#define MONTE_MC_TRACK_GLOBAL    0  /* the reference's Woodcock loop: one majorant, the maximum over all materials
+                                       at the photon's energy (CBCT_real325im.cu:866-868, :886-968)                 */
+#define MONTE_MC_TRACK_CLEARANCE 1  /* two-level majorant: a coarse clearance grid (monte_mc_clearance_grid) gives
+                                       every cell a radius D inside which the heaviest material does not occur; a
+                                       flight that starts there is sampled with the majorant of the other materials
+                                       and, if it would go farther than D, stops at D without a collision (Woodcock
+                                       steps are memoryless).  Pays when a dense insert sets the global majorant far
+                                       above the bulk: polyenergetic spectra, calcium / bone in water               */
+
 typedef struct monte_mc_volume {
     int32_t nx, ny, nz;
     double  pitch;
     double  origin[3];
     double  clip_lo[3], clip_hi[3];
+    int32_t tracking_mode;        /* MONTE_MC_TRACK_*; 0 = the reference's single majorant                      */
+    int32_t clearance_cell_log2;  /* CLEARANCE: cells of 2^n voxels per side (0..8); 3 is a good start         */
 } monte_mc_volume;
 
 #define MONTE_MC_SOURCE_PENCIL 0  /* one pencil per pixel centre, `per` photons each
@@ -345,6 +359,17 @@ int monte_ctnum_to_mu(const float *hu, size_t n, const monte_mc_xs *xs, double k
  * hydrogen-like 1s charge cloud, x0 in 1/Angstrom (0.30 * Z_eff).  Fills ff_x2 / ff_cum of `material` on a
  * logarithmic grid of MONTE_MC_FF_POINTS points up to x^2 = 270 (200 keV back-scatter) and sets ff_points.  */
 int monte_xs_formfactor_hydrogenic(monte_mc_xs *xs, int material, double x0);
+/* Clearance grid of MONTE_MC_TRACK_CLEARANCE (host only; the library builds it itself at scene upload, the call is
+ * exported for hosts that want to inspect it and for the CPU oracle): dims[] = ceil(n / 2^cell_log2) per axis;
+ * grid[(cz*dims[1] + cy)*dims[0] + cx] = floor(2 d) clipped to 127, d = smallest distance in cell sides between the
+ * cell's box and the box of any cell holding a voxel of `heavy_material` (index into monte_mc_xs, labels above
+ * n_materials clamp to the last material as in the transport).  A flight of at most grid * 2^cell_log2 * pitch / 2
+ * from anywhere in the cell cannot reach that material.                                                           */
+int monte_mc_clearance_dims(const monte_mc_volume *vol, int cell_log2, int32_t dims[3]);
+int monte_mc_clearance_grid(const monte_mc_volume *vol, const uint8_t *labels, int n_materials, int heavy_material,
+                            int cell_log2, uint8_t *grid);
+/* the material the clearance grid is built for: argmax of total*density at 60 keV; -1 with fewer than 2 materials */
+int monte_xs_heavy_material(const monte_mc_xs *xs);
 /* per-keV Woodcock majorant (1/cm) over the materials that occur in `labels` (NULL: all materials):
  * the max of CBCT_real325im.cu:866 restricted to what the volume contains; mu_max[201].               */
 int monte_xs_majorant(const monte_mc_xs *xs, const uint8_t *labels, size_t n, float *mu_max);

@@ -19,6 +19,7 @@ FDK_REFERENCE, FDK_TEXTBOOK = 0, 1
 COORD_SCALE_AFTER, COORD_SCALE_BEFORE = 0, 1
 SOURCE_PENCIL, SOURCE_CONE = 0, 1
 COHERENT_FORWARD, COHERENT_FORMFACTOR = 0, 1
+TRACK_GLOBAL, TRACK_CLEARANCE = 0, 1
 
 
 class FdkGeom(C.Structure):
@@ -81,6 +82,7 @@ class McVolume(C.Structure):
         ("pitch", C.c_double),
         ("origin", C.c_double * 3),
         ("clip_lo", C.c_double * 3), ("clip_hi", C.c_double * 3),
+        ("tracking_mode", C.c_int32), ("clearance_cell_log2", C.c_int32),
     ]
 
 

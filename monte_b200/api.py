@@ -82,6 +82,9 @@ def _bind(path):
         "monte_ctnum_to_mu": (C.c_int, [vp, sz, C.POINTER(McXs), C.c_double, C.c_float, C.c_float, vp, vp]),
         "monte_xs_majorant": (C.c_int, [C.POINTER(McXs), vp, sz, vp]),
         "monte_xs_formfactor_hydrogenic": (C.c_int, [C.POINTER(McXs), C.c_int, C.c_double]),
+        "monte_mc_clearance_dims": (C.c_int, [C.POINTER(McVolume), C.c_int, C.POINTER(C.c_int32)]),
+        "monte_mc_clearance_grid": (C.c_int, [C.POINTER(McVolume), vp, C.c_int, C.c_int, C.c_int, vp]),
+        "monte_xs_heavy_material": (C.c_int, [C.POINTER(McXs)]),
         "monte_gpu_fdk_slab_rows": (C.c_int, [C.POINTER(FdkGeom), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     }
     missing = []
@@ -293,6 +296,20 @@ def counts_to_map(counts, per):
     out = np.empty(counts.shape, np.float32)
     _check(load().monte_gpu_counts_to_map(_ptr(counts), counts.size, per, _ptr(out)))
     return out
+
+
+def clearance_grid(vol, labels, xs, cell_log2=None):
+    """(grid uint8 [gz][gy][gx], heavy material index) of MONTE_MC_TRACK_CLEARANCE -- host helper, no device needed"""
+    lib = load()
+    labels = np.ascontiguousarray(labels, np.uint8)
+    cl = vol.clearance_cell_log2 if cell_log2 is None else cell_log2
+    dims = (C.c_int32 * 3)()
+    _check(lib.monte_mc_clearance_dims(C.byref(vol), cl, dims))
+    heavy = lib.monte_xs_heavy_material(C.byref(xs))
+    grid = np.full((dims[2], dims[1], dims[0]), 127, np.uint8)
+    if heavy >= 0:
+        _check(lib.monte_mc_clearance_grid(C.byref(vol), _ptr(labels), xs.n_materials, heavy, cl, _ptr(grid)))
+    return grid, heavy
 
 
 def project_primary(g, vol, labels, xs, keV, views=None, out=None):

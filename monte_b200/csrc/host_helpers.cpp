@@ -1,6 +1,7 @@
 // host_helpers.cpp — GPU-free pieces of the reference's driver surface: cross-section tables,
 // phantom generators, CT-number conversion, geometry presets.  Linked into libmonte_gpu and used
 // by the C++ drivers under monte_b200/host/.
+#include <vector>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -176,6 +177,83 @@ int monte_xs_formfactor_hydrogenic(monte_mc_xs *xs, int material, double x0) {
     }
     xs->ff_points = n;
     return MONTE_OK;
+}
+
+/* ---- clearance grid for the two-level Woodcock majorant (monte_mc_volume.tracking_mode = CLEARANCE) -------
+ * The reference tracks with one majorant, the maximum over every table it loaded (CBCT_real325im.cu:866-868).  At
+ * diagnostic energies a dense insert (calcium) sets that maximum far above the attenuation of the water that
+ * fills most of the volume, and most tentative collisions are virtual.  The clearance grid lets the tracker use
+ * the majorant of the OTHER materials wherever the dense one is provably out of reach: cells of 2^cell_log2
+ * voxels per side; grid[cell] = floor(2 * d) clipped to 127 (7 bits of slot state in the transport kernel), d = smallest distance, in cell sides, between the
+ * cell's box and the box of any cell that contains a voxel of the heavy material (0 for those cells and their
+ * neighbours).  A flight of at most grid[cell] * half a cell side that starts anywhere in the cell cannot reach
+ * the heavy material.  Exact separable transform (the squared box distance is a sum over the axes).          */
+int monte_mc_clearance_dims(const monte_mc_volume *vol, int cell_log2, int32_t dims[3]) {
+    if (!vol || !dims || cell_log2 < 0 || cell_log2 > 8) { monte::set_error("monte_mc_clearance_dims: bad argument"); return MONTE_E_ARG; }
+    const int c = 1 << cell_log2;
+    dims[0] = (vol->nx + c - 1) >> cell_log2; dims[1] = (vol->ny + c - 1) >> cell_log2; dims[2] = (vol->nz + c - 1) >> cell_log2;
+    return MONTE_OK;
+}
+
+int monte_mc_clearance_grid(const monte_mc_volume *vol, const uint8_t *labels, int n_materials, int heavy_material,
+                            int cell_log2, uint8_t *grid) {
+    int32_t d[3];
+    if (int rc = monte_mc_clearance_dims(vol, cell_log2, d)) return rc;
+    if (!labels || !grid || n_materials < 1 || heavy_material < 0 || heavy_material >= n_materials) {
+        monte::set_error("monte_mc_clearance_grid: bad argument");
+        return MONTE_E_ARG;
+    }
+    const int gx = d[0], gy = d[1], gz = d[2];
+    const size_t ncell = (size_t)gx * gy * gz;
+    const float INF = 1e30f;
+    std::vector<float> f(ncell, INF), t(ncell);
+    for (int z = 0; z < vol->nz; z++)
+        for (int y = 0; y < vol->ny; y++) {
+            const uint8_t *row = labels + ((size_t)z * vol->ny + y) * vol->nx;
+            float *frow = f.data() + ((size_t)(z >> cell_log2) * gy + (y >> cell_log2)) * gx;
+            for (int x = 0; x < vol->nx; x++) {
+                int l = row[x];
+                if (l == 0) continue;
+                if (l > n_materials) l = n_materials;              // same clamp as the transport kernel
+                if (l - 1 == heavy_material) frow[x >> cell_log2] = 0.f;
+            }
+        }
+    // f <- min over the other cells of the line of f + max(0, |i - j| - 1)^2, one axis after the other
+    const int dims[3] = {gx, gy, gz};
+    const size_t stride[3] = {1, (size_t)gx, (size_t)gx * gy};
+    for (int a = 0; a < 3; a++) {
+        const int n = dims[a];
+        const int b = (a + 1) % 3, c = (a + 2) % 3;
+        for (int jb = 0; jb < dims[b]; jb++)
+            for (int jc = 0; jc < dims[c]; jc++) {
+                const size_t base = jb * stride[b] + jc * stride[c];
+                for (int i = 0; i < n; i++) {
+                    float best = f[base + i * stride[a]];
+                    for (int k = 1; k < n; k++) {                      // outwards from i; farther cells cannot beat `best`
+                        const float gap2 = (float)(k - 1) * (float)(k - 1);
+                        if (gap2 >= best) break;
+                        if (i - k >= 0) { const float w = f[base + (i - k) * stride[a]] + gap2; if (w < best) best = w; }
+                        if (i + k < n) { const float w = f[base + (i + k) * stride[a]] + gap2; if (w < best) best = w; }
+                    }
+                    t[base + i * stride[a]] = best;
+                }
+            }
+        f.swap(t);
+    }
+    for (size_t i = 0; i < ncell; i++) {
+        const double q = f[i] >= INF ? 127.0 : floor(2.0 * sqrt((double)f[i]));
+        grid[i] = (uint8_t)(q > 127.0 ? 127.0 : q);
+    }
+    return MONTE_OK;
+}
+
+/* the material whose attenuation sets the majorant: argmax of total*density at 60 keV (-1: fewer than 2 materials) */
+int monte_xs_heavy_material(const monte_mc_xs *xs) {
+    if (!xs || xs->n_materials < 2 || xs->n_materials > MONTE_MC_MAX_MATERIALS) return -1;
+    int best = 0;
+    for (int m = 1; m < xs->n_materials; m++)
+        if (xs->total[m][60] * xs->density[m] > xs->total[best][60] * xs->density[best]) best = m;
+    return best;
 }
 
 }  // extern "C"

@@ -62,6 +62,11 @@ struct McLaunch {
     // RAYLEIGH instantiations only (appended: the parameter offsets of everything above do not move)
     const float *ray;             // [n_mat][2][ray_n]: x^2 grid, then cumulative F^2 (monte_mc_xs.ff_x2 / ff_cum)
     int ray_n;
+    // CLEAR instantiations only (monte_mc_volume.tracking_mode == MONTE_MC_TRACK_CLEARANCE)
+    const uint8_t *clear;         // clearance grid [cgz][cgy][cgx] (monte_mc_clearance_grid, clipped to 127)
+    const float *inv_mulo;        // [201] 1 / majorant of every material but the heavy one
+    int cgx, cgy, cshift;         // grid dims and log2 of the cell side in voxels
+    float cunit;                  // cm per grid unit (half a cell side)
 };
 
 // stats word indices
@@ -109,7 +114,8 @@ enum : uint32_t { P_REFILL = 1u, P_STEP = 2u, P_COLLIDE = 4u, P_COMPTON = 8u };
 //   G_POS : x, y, z, E            G_DIR : dx, dy, dz, u_phi
 //   G_ID  : c0, META, CTR, PIXVIEW            G_REC : record index (fate dump only)
 // META: bits 0-7 kE, 8-11 nint, 12-14 material, 15 pending-detect, 16 coherent event waiting for its angle
-//       (RAYLEIGH kernels), 24-31 high byte of the history id
+//       (RAYLEIGH kernels), 17-23 clearance of the cell the photon is in, in grid units (CLEAR kernels),
+//       24-31 high byte of the history id
 // CTR : bits 0-19 flight-stream index, 20-31 event-stream index
 // PIXVIEW: bits 0-19 pixel, 20-31 view
 enum { G_POS = 0, G_DIR = 1, G_ID = 2, G_REC = 3 };
@@ -126,7 +132,12 @@ __device__ __forceinline__ float ray_interp(const float *xs, const float *ys, in
 
 // RAYLEIGH = true: monte_mc_geom.coherent_mode == MONTE_MC_COHERENT_FORMFACTOR (off in parity mode).
 // A coherent event then waits in the COMPTON phase for its angle: one rejection round per visit, like Kahn's.
-template <bool RECORD, int K, int MINB = 3, int NSTEP = 2, bool RAYLEIGH = false>
+// CLEAR = true: monte_mc_volume.tracking_mode == MONTE_MC_TRACK_CLEARANCE, the two-level majorant.  Every slot
+// carries the clearance of its current cell (META bits 17-23, fetched together with the label at the end of a
+// step); a step that starts with clearance > 0 is sampled with the majorant of the lighter materials and cut
+// at the clearance radius.  Same collision-site distribution as the reference's loop, far fewer virtual
+// collisions when a dense insert sets the global majorant (C4: 23 -> ~5 steps per history).
+template <bool RECORD, int K, int MINB = 3, int NSTEP = 2, bool RAYLEIGH = false, bool CLEAR = false>
 __global__ void __launch_bounds__(MC_THREADS, MINB)
 mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
     MONTE_DYN_SMEM(float4, s_mem);
@@ -138,13 +149,16 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
     constexpr int GSTRIDE = K * 32;                                    // uint4 per group per warp
     float *s_ray = s_cdf + ((sc.n_bins + 1 + 3) & ~3);                 // RAYLEIGH: [n_mat][2][ray_n], ray_n padded to 4
     const int ray_stride = RAYLEIGH ? ((P.ray_n + 3) & ~3) : 0;
-    uint4 *s_slots = reinterpret_cast<uint4 *>(s_ray + sc.n_mat * 2 * ray_stride) + (threadIdx.x >> 5) * (NG * GSTRIDE);
+    float *s_invlo = s_ray + sc.n_mat * 2 * ray_stride;                // CLEAR: [201 (+3)]
+    uint4 *s_slots = reinterpret_cast<uint4 *>(s_invlo + (CLEAR ? TAB_ROWS + 3 : 0)) + (threadIdx.x >> 5) * (NG * GSTRIDE);
     for (int i = threadIdx.x; i < sc.n_mat * TAB_ROWS; i += MC_THREADS) s_tab[i] = sc.tab[i];
     for (int i = threadIdx.x; i < TAB_ROWS; i += MC_THREADS) s_inv[i] = sc.inv_mumax[i];
     for (int i = threadIdx.x; i <= sc.n_bins && sc.n_bins > 0; i += MC_THREADS) s_cdf[i] = sc.cdf[i];
     if (RAYLEIGH)
         for (int i = threadIdx.x; i < sc.n_mat * 2 * P.ray_n; i += MC_THREADS)
             s_ray[(i / P.ray_n) * ray_stride + i % P.ray_n] = P.ray[i];
+    if (CLEAR)
+        for (int i = threadIdx.x; i < TAB_ROWS; i += MC_THREADS) s_invlo[i] = P.inv_mulo[i];
     __syncthreads();
 
     const unsigned lane = threadIdx.x & 31u;
@@ -214,6 +228,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 }
             }
             uint4 id2[NS]; float4 pos2[NS]; uint2 r2[NS]; bool inside2[NS]; int lab2[NS];
+            bool lo2[NS]; uint32_t qn2[NS];                        // CLEAR: sampled with the light majorant; clearance at the new site
 #pragma unroll
             for (int q = 0; q < NS; q++) {
                 id2[q] = sl[q][G_ID * GSTRIDE];
@@ -225,7 +240,17 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
 #pragma unroll
             for (int q = 0; q < NS; q++) {
                 const float4 dir = *reinterpret_cast<float4 *>(&sl[q][G_DIR * GSTRIDE]);
-                const float sp = -__logf(u01(r2[q].x)) * s_inv[id2[q].y & 0xFF];
+                float sp;
+                bool cut = false;
+                lo2[q] = false; qn2[q] = 0u;
+                if (CLEAR) {
+                    const uint32_t qc = (id2[q].y >> 17) & 0x7Fu;  // clearance of the cell the step starts in
+                    lo2[q] = qc != 0u;
+                    sp = -__logf(u01(r2[q].x)) * (lo2[q] ? s_invlo[id2[q].y & 0xFF] : s_inv[id2[q].y & 0xFF]);
+                    const float dcl = (float)qc * P.cunit;
+                    cut = lo2[q] && sp > dcl;                      // would leave the cleared ball: stop at its surface, no collision
+                    sp = cut ? dcl : sp;
+                } else sp = -__logf(u01(r2[q].x)) * s_inv[id2[q].y & 0xFF];
                 pos2[q].x = fmaf(sp, dir.x, pos2[q].x); pos2[q].y = fmaf(sp, dir.y, pos2[q].y); pos2[q].z = fmaf(sp, dir.z, pos2[q].z);
                 inside2[q] = pos2[q].x >= sc.clip_lo[0] && pos2[q].x < sc.clip_hi[0] && pos2[q].y >= sc.clip_lo[1] && pos2[q].y < sc.clip_hi[1] &&
                              pos2[q].z >= sc.clip_lo[2] && pos2[q].z < sc.clip_hi[2];
@@ -234,13 +259,17 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 int iz = __float_as_int(fmaf(pos2[q].z, sc.inv_pitch, vox_off[2]) + 12582912.0f) - 0x4B400000;
                 ix = (int)min((unsigned)ix, (unsigned)(sc.nx - 1)); iy = (int)min((unsigned)iy, (unsigned)(sc.ny - 1));
                 iz = (int)min((unsigned)iz, (unsigned)(sc.nz - 1));     // safety only: the clip box lies inside the volume
-                lab2[q] = (en2[q] && inside2[q]) ? __ldg(sc.labels + ((unsigned)(iz * sc.ny + iy) * (unsigned)sc.nx + (unsigned)ix)) : 0;
+                lab2[q] = (en2[q] && inside2[q] && !cut) ? __ldg(sc.labels + ((unsigned)(iz * sc.ny + iy) * (unsigned)sc.nx + (unsigned)ix)) : 0;
+                if (CLEAR && en2[q] && inside2[q])
+                    qn2[q] = __ldg(P.clear + ((unsigned)((iz >> P.cshift) * P.cgy + (iy >> P.cshift)) * (unsigned)P.cgx + (unsigned)(ix >> P.cshift)));
             }
 #pragma unroll
             for (int q = 0; q < NS; q++) {
                 if (!en2[q]) continue;
                 uint4 *slot = sl[q];                               // GRP/WORD below refer to this slot
-                const uint32_t meta = id2[q].y, ctr = id2[q].z;
+                uint32_t meta = id2[q].y;
+                const uint32_t ctr = id2[q].z;
+                if (CLEAR) { meta = (meta & ~0xFE0000u) | (qn2[q] << 17); WORD(G_ID, 1) = meta; }
                 const uint32_t clrq = ~(0xFu << (4 * jj[q]));
                 const int kE = meta & 0xFF;
                 WORD(G_ID, 2) = (ctr & 0xFFF00000u) | ((ctr + 1u) & 0xFFFFFu);
@@ -263,7 +292,10 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 }
                 if (lab2[q] == 0) continue;                               // air: virtual collision
                 const int mat = min(lab2[q], sc.n_mat) - 1;
-                if (u01(r2[q].y) > s_tab[mat * TAB_ROWS + kE].x) continue;    // virtual collision, :941-961
+                if (CLEAR) {                                              // acceptance against the majorant the step was sampled with
+                    const float ratio = lo2[q] ? s_tab[mat * TAB_ROWS + kE].w : s_tab[mat * TAB_ROWS + kE].x;
+                    if (u01(r2[q].y) > ratio) continue;
+                } else if (u01(r2[q].y) > s_tab[mat * TAB_ROWS + kE].x) continue;    // virtual collision, :941-961
                 WORD(G_ID, 1) = (meta & ~0x7000u) | ((uint32_t)mat << 12);
                 st = (st & clrq) | (P_COLLIDE << (4 * jj[q]));
             }
@@ -502,9 +534,18 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 if (RECORD) { P.fates[rec_idx] = 1u | (pix << 8); P.fate_e[rec_idx] = E; }
                 // the slot stays in REFILL and takes another history on the next visit
             } else {
-                *reinterpret_cast<float4 *>(&GRP(G_POS)) = make_float4(fmaf(t0, dx, sx), fmaf(t0, dy, sy), t0 * dz, E);
+                const float ex = fmaf(t0, dx, sx), ey = fmaf(t0, dy, sy), ez = t0 * dz;
+                uint32_t qe = 0u;
+                if (CLEAR) {                                  // clearance of the cell the photon enters through
+                    int ix = __float_as_int(fmaf(ex, sc.inv_pitch, vox_off[0]) + 12582912.0f) - 0x4B400000;
+                    int iy = __float_as_int(fmaf(ey, sc.inv_pitch, vox_off[1]) + 12582912.0f) - 0x4B400000;
+                    int iz = __float_as_int(fmaf(ez, sc.inv_pitch, vox_off[2]) + 12582912.0f) - 0x4B400000;
+                    ix = min(max(ix, 0), sc.nx - 1); iy = min(max(iy, 0), sc.ny - 1); iz = min(max(iz, 0), sc.nz - 1);
+                    qe = __ldg(P.clear + ((unsigned)((iz >> P.cshift) * P.cgy + (iy >> P.cshift)) * (unsigned)P.cgx + (unsigned)(ix >> P.cshift)));
+                }
+                *reinterpret_cast<float4 *>(&GRP(G_POS)) = make_float4(ex, ey, ez, E);
                 *reinterpret_cast<float4 *>(&GRP(G_DIR)) = make_float4(dx, dy, dz, 0.f);
-                GRP(G_ID) = make_uint4(c0, c1hi | (uint32_t)kE, 0u, ((uint32_t)view << 20) | pix);
+                GRP(G_ID) = make_uint4(c0, c1hi | (qe << 17) | (uint32_t)kE, 0u, ((uint32_t)view << 20) | pix);
                 st = (st & clr) | (P_STEP << (4 * j));
             }
         }
@@ -556,6 +597,13 @@ struct monte_mc_scene {
     void *d_labels = nullptr, *d_tab = nullptr, *d_inv = nullptr, *d_cdf = nullptr, *d_view = nullptr, *d_ray = nullptr;
     size_t cap_labels = 0, cap_tab = 0, cap_cdf = 0, cap_view = 0, cap_ray = 0;     // grow-only capacities (bytes)
     int ray_n = 0;                                                     // > 0: form-factor tables uploaded (coherent_mode 1)
+    // two-level majorant (tracking_mode CLEARANCE): clearance grid, light-majorant table, the material it excludes
+    void *d_clear = nullptr, *d_invlo = nullptr;
+    size_t cap_clear = 0;
+    int heavy = -1, cshift = 0, cg[3] = {0, 0, 0};
+    float cunit = 0.f;
+    monte_mc_volume vol;                                               // kept for scene_update_labels
+    int n_mat_host = 0;
     unsigned long long *d_work = nullptr;
     size_t smem = 0;
     size_t h2d_bytes = 0;
@@ -571,6 +619,10 @@ static int check_mc(const monte_mc_geom *g, const monte_mc_volume *vol, const mo
               "mc: unknown detector_mode %d", g->detector_mode);
     MONTE_ARG(vol->nx > 0 && vol->ny > 0 && vol->nz > 0 && vol->pitch > 0, "mc: bad volume");
     MONTE_ARG((uint64_t)vol->nx * vol->ny * vol->nz < (1ull << 32), "mc: label volume has 2^32 voxels or more");
+    MONTE_ARG(vol->tracking_mode == MONTE_MC_TRACK_GLOBAL || vol->tracking_mode == MONTE_MC_TRACK_CLEARANCE,
+              "mc: unknown tracking_mode %d", vol->tracking_mode);
+    MONTE_ARG(vol->tracking_mode != MONTE_MC_TRACK_CLEARANCE || (vol->clearance_cell_log2 >= 0 && vol->clearance_cell_log2 <= 8),
+              "mc: clearance_cell_log2 must be 0..8 (got %d)", vol->clearance_cell_log2);
     MONTE_ARG(xs->n_materials >= 1 && xs->n_materials <= MONTE_MC_MAX_MATERIALS, "mc: n_materials must be 1..%d", MONTE_MC_MAX_MATERIALS);
     MONTE_ARG(g->coherent_mode == MONTE_MC_COHERENT_FORWARD || g->coherent_mode == MONTE_MC_COHERENT_FORMFACTOR,
               "mc: unknown coherent_mode %d", g->coherent_mode);
@@ -606,6 +658,22 @@ static int grow(void **p, size_t *cap, size_t bytes) {
     return MONTE_OK;
 }
 
+// clearance grid of the current labels (host transform, ~10 ms per 1e7 voxels) -> device
+static int upload_clearance(monte_mc_scene *s, const uint8_t *labels, cudaStream_t st) {
+    const monte_mc_volume &v = s->vol;
+    int32_t d[3];
+    if (int rc = monte_mc_clearance_dims(&v, v.clearance_cell_log2, d)) return rc;
+    std::vector<uint8_t> grid((size_t)d[0] * d[1] * d[2]);
+    if (int rc = monte_mc_clearance_grid(&v, labels, s->n_mat_host, s->heavy, v.clearance_cell_log2, grid.data())) return rc;
+    if (int rc = grow(&s->d_clear, &s->cap_clear, grid.size())) return rc;
+    MONTE_CUDA(cudaMemcpyAsync(s->d_clear, grid.data(), grid.size(), cudaMemcpyHostToDevice, st));
+    MONTE_CUDA(cudaStreamSynchronize(st));                             // `grid` is pageable and goes out of scope
+    s->cg[0] = d[0]; s->cg[1] = d[1]; s->cg[2] = d[2];
+    s->cshift = v.clearance_cell_log2;
+    s->cunit = (float)(0.5 * (double)(1 << v.clearance_cell_log2) * v.pitch);
+    return MONTE_OK;
+}
+
 // (re)fill a scene: device buffers are reused when large enough; copies are issued on `st`
 static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_mc_volume *vol, const uint8_t *labels,
                         const monte_mc_xs *xs, const monte_mc_spectrum *spec, cudaStream_t st) {
@@ -621,18 +689,24 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
     // per-keV tables: majorant over materials (CBCT_real325im.cu:867-868) and branching ratios (:651,656)
     const int nm = xs->n_materials;
     std::vector<float4> tab((size_t)nm * TAB_ROWS);
-    std::vector<float> inv(TAB_ROWS);
+    std::vector<float> inv(TAB_ROWS), invlo(TAB_ROWS, 0.f);
+    // tracking_mode CLEARANCE needs a material to exclude; with a single material it is the reference's loop
+    s->heavy = vol->tracking_mode == MONTE_MC_TRACK_CLEARANCE ? monte_xs_heavy_material(xs) : -1;
     for (int k = 0; k < TAB_ROWS; k++) {
-        double mumax = 0;
-        for (int m = 0; m < nm; m++) mumax = fmax(mumax, (double)xs->total[m][k] * (double)xs->density[m]);
+        double mumax = 0, mulo = 0;
+        for (int m = 0; m < nm; m++) {
+            mumax = fmax(mumax, (double)xs->total[m][k] * (double)xs->density[m]);
+            if (m != s->heavy) mulo = fmax(mulo, (double)xs->total[m][k] * (double)xs->density[m]);
+        }
         inv[k] = mumax > 0 ? (float)(1.0 / mumax) : 0.f;
+        invlo[k] = mulo > 0 ? (float)(1.0 / mulo) : inv[k];
         for (int m = 0; m < nm; m++) {
             const double mu = (double)xs->total[m][k];
             float4 t;
             t.x = mumax > 0 ? (float)((mu * (double)xs->density[m]) / mumax) : 0.f;
             t.y = mu > 0 ? (float)((double)xs->photo[m][k] / mu) : 1.f;
             t.z = mu > 0 ? (float)(((double)xs->photo[m][k] + (double)xs->coh[m][k]) / mu) : 1.f;
-            t.w = 0.f;
+            t.w = mulo > 0 ? (float)fmin(1.0, (mu * (double)xs->density[m]) / mulo) : t.x;   // acceptance against the light majorant
             tab[(size_t)m * TAB_ROWS + k] = t;
         }
     }
@@ -653,6 +727,15 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
             MONTE_CUDA(cudaMemcpyAsync(s->d_cdf, spec->cdf, cdf_bytes, cudaMemcpyHostToDevice, st));
             d.cdf = (const float *)s->d_cdf;
         }
+    }
+    size_t clear_bytes = 0;
+    s->vol = *vol; s->n_mat_host = nm;
+    if (s->heavy >= 0) {
+        if (!s->d_invlo) MONTE_CUDA(cudaMalloc(&s->d_invlo, TAB_ROWS * sizeof(float)));
+        MONTE_CUDA(cudaMemcpyAsync(s->d_invlo, invlo.data(), TAB_ROWS * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (int rc = upload_clearance(s, labels, st)) return rc;
+        clear_bytes = (size_t)s->cg[0] * s->cg[1] * s->cg[2] + TAB_ROWS * sizeof(float);
+        MONTE_CUDA(cudaStreamSynchronize(st));                         // `invlo` is pageable and goes out of scope
     }
     s->ray_n = 0;
     size_t ray_bytes = 0;
@@ -682,7 +765,7 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
     d.eid = g->detector_mode == MONTE_MC_DETECTOR_ENERGY ? 1 : 0;
     if (!s->d_work) MONTE_CUDA(cudaMalloc(&s->d_work, sizeof(unsigned long long)));
     s->smem = (size_t)nm * TAB_ROWS * sizeof(float4) + (TAB_ROWS + 3 + d.n_bins + 1) * sizeof(float);
-    s->h2d_bytes = nvox + tab_bytes + inv_bytes + cdf_bytes + ray_bytes + vcs.size() * sizeof(float2);
+    s->h2d_bytes = nvox + tab_bytes + inv_bytes + cdf_bytes + ray_bytes + clear_bytes + vcs.size() * sizeof(float2);
     // the host vectors above are pageable: the async copies have already staged them
     MONTE_CUDA(cudaStreamSynchronize(st));
     return MONTE_OK;
@@ -705,12 +788,13 @@ int monte_gpu_scene_update_labels(monte_mc_scene *s, const uint8_t *labels, void
     MONTE_ARG(s && labels, "scene_update_labels: NULL argument");
     const size_t nvox = (size_t)s->dev.nx * s->dev.ny * s->dev.nz;
     MONTE_CUDA(cudaMemcpyAsync(s->d_labels, labels, nvox, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    if (s->heavy >= 0) return upload_clearance(s, labels, (cudaStream_t)stream);   // the grid follows the labels
     return MONTE_OK;
 }
 
 void monte_gpu_scene_destroy(monte_mc_scene *s) {
     if (!s) return;
-    cudaFree(s->d_labels); cudaFree(s->d_tab); cudaFree(s->d_cdf); cudaFree(s->d_view); cudaFree(s->d_work); cudaFree(s->d_ray);
+    cudaFree(s->d_labels); cudaFree(s->d_tab); cudaFree(s->d_cdf); cudaFree(s->d_view); cudaFree(s->d_work); cudaFree(s->d_ray); cudaFree(s->d_clear); cudaFree(s->d_invlo);
     delete s;
 }
 
@@ -734,6 +818,8 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     L.image0 = d_image0; L.image5 = d_image5; L.stats = d_stats; L.work = s->d_work;
     L.fates = d_fates; L.fate_e = d_fate_e;
     L.ray = (const float *)s->d_ray; L.ray_n = s->ray_n;
+    L.clear = (const uint8_t *)s->d_clear; L.inv_mulo = (const float *)s->d_invlo;
+    L.cgx = s->cg[0]; L.cgy = s->cg[1]; L.cshift = s->cshift; L.cunit = s->cunit;
     { static int sm = -1; if (sm < 0) { const char *e = getenv("MONTE_MC_SECOND"); sm = e ? atoi(e) : 16; } L.second_min = (uint32_t)sm; }
     if (L.total == 0) return MONTE_OK;
     MONTE_CUDA(cudaMemsetAsync(s->d_work, 0, sizeof(unsigned long long), st));
@@ -746,16 +832,22 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     MONTE_ARG(s->geom.n_views < 4096, "mc: more than 4095 views");
     const int rec = d_fates ? 1 : 0;
     const bool rayleigh = s->ray_n > 0;      // form-factor deflection of coherent events: its own instantiation (K = 5)
-    const int which = rayleigh ? 35 : which_env;
+    const bool clear = s->heavy >= 0;        // two-level majorant: its own instantiations too
+    const int which = rayleigh || clear ? 35 : which_env;
     const int K = which >= 31 && which <= 36 ? which - 30 : (which == 44 ? 4 : (which == 43 ? 3 : 5));
     const size_t slot_bytes = (size_t)K * 32 * mc_slot_groups(rec != 0) * sizeof(uint4) * (MC_THREADS / 32);
     const size_t smem = (size_t)s->dev.n_mat * TAB_ROWS * sizeof(float4) +
                         (TAB_ROWS + 3 + ((s->dev.n_bins + 1 + 3) & ~3)) * sizeof(float) + slot_bytes +
-                        (rayleigh ? (size_t)s->dev.n_mat * 2 * ((s->ray_n + 3) & ~3) * sizeof(float) : 0);
+                        (rayleigh ? (size_t)s->dev.n_mat * 2 * ((s->ray_n + 3) & ~3) * sizeof(float) : 0) +
+                        (clear ? (TAB_ROWS + 3) * sizeof(float) : 0);
     const void *fn = nullptr;
-    switch (rayleigh ? 200 + rec : which * 2 + rec) {
+    switch (rayleigh || clear ? 200 + rec + (clear ? 2 : 0) + (rayleigh && clear ? 2 : 0) : which * 2 + rec) {
         case 200: fn = (const void *)mc_transport_kernel_v3<false, 5, 3, 2, true>; break;
         case 201: fn = (const void *)mc_transport_kernel_v3<true, 5, 3, 2, true>; break;
+        case 202: fn = (const void *)mc_transport_kernel_v3<false, 5, 3, 2, false, true>; break;
+        case 203: fn = (const void *)mc_transport_kernel_v3<true, 5, 3, 2, false, true>; break;
+        case 204: fn = (const void *)mc_transport_kernel_v3<false, 5, 3, 2, true, true>; break;
+        case 205: fn = (const void *)mc_transport_kernel_v3<true, 5, 3, 2, true, true>; break;
         case 62: fn = (const void *)mc_transport_kernel_v3<false, 1>; break;
         case 63: fn = (const void *)mc_transport_kernel_v3<true, 1>; break;
         case 64: fn = (const void *)mc_transport_kernel_v3<false, 2>; break;
@@ -779,7 +871,8 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     static int occ[96] = {0};
     static size_t smem_set[96] = {0}, smem_occ[96] = {0};
     at_shutdown([] { memset(occ, 0, sizeof(occ)); memset(smem_set, 0, sizeof(smem_set)); memset(smem_occ, 0, sizeof(smem_occ)); });
-    const int slot_id = rayleigh ? 94 + rec : (which * 2 + rec) % 96;     // 94, 95: no `which` maps there (31..46 -> 62..93)
+    // 94, 95 (Rayleigh), 0..3 (clearance, clearance + Rayleigh): no `which` maps there (31..46 -> 62..93)
+    const int slot_id = clear ? rec + (rayleigh ? 2 : 0) : rayleigh ? 94 + rec : (which * 2 + rec) % 96;
     int &oc = occ[slot_id];
     MONTE_ARG(smem <= 227 * 1024, "mc: %zu bytes of shared memory needed (> 227 KB)", smem);
     if (smem > smem_set[slot_id]) {

@@ -151,7 +151,8 @@ class OracleTables(C.Structure):
 class OracleOpts(C.Structure):
     _fields_ = [("rng_mode", C.c_int32), ("quirks", C.c_int32), ("seed", C.c_uint64),
                 ("preadvance_start", C.c_double), ("track_box", C.c_double * 3),
-                ("n_threads", C.c_int32), ("label_center", C.c_double * 3)]
+                ("n_threads", C.c_int32), ("label_center", C.c_double * 3),
+                ("clear_grid", C.c_void_p), ("clear_dims", C.c_int32 * 3), ("heavy", C.c_int32)]
 
 
 class OracleResult(C.Structure):
@@ -223,6 +224,16 @@ def mc_run(g, vol, labels, tables, spec, opts, per, views=None, n_range=None, pi
             fe.ctypes.data_as(C.c_void_p) if want_fates else None)
     assert rc == 0
     return im0, im5, {k: getattr(res, k) for k, _ in res._fields_}, fates, fe
+
+
+def with_clearance(opts, grid, heavy):
+    """attach the clearance grid of monte_mc_clearance_grid (uint8 [gz][gy][gx]) to oracle options; the volume's
+    tracking_mode switches the two-level majorant on.  Returns (opts, array to keep alive)."""
+    grid = np.ascontiguousarray(grid, np.uint8)
+    opts.clear_grid = grid.ctypes.data
+    opts.clear_dims[0], opts.clear_dims[1], opts.clear_dims[2] = grid.shape[2], grid.shape[1], grid.shape[0]
+    opts.heavy = heavy
+    return opts, grid
 
 
 def project_primary(g, vol, labels, tables, keV, views=None):

@@ -82,6 +82,11 @@ typedef struct oracle_mc_opts {
     double   track_box[3];       /* 62, 62, 17 */
     int32_t  n_threads;          /* 0 = all (MT mode with >1 thread is not the reference's stream) */
     double   label_center[3];    /* OQ_LABEL_RINT: 90, 90, 160 (CBCT_real2.cpp:771) */
+    /* monte_mc_volume.tracking_mode == MONTE_MC_TRACK_CLEARANCE (not in the reference): the grid of
+     * monte_mc_clearance_grid (include/monte_gpu.h) and the material it was built for */
+    const uint8_t *clear_grid;
+    int32_t  clear_dims[3];
+    int32_t  heavy;
 } oracle_mc_opts;
 
 typedef struct oracle_mc_result {
@@ -195,6 +200,28 @@ static double mu_max_at(const scene_t *S, int k) {
     return m;
 }
 
+/* majorant over every material but the heavy one (tracking_mode CLEARANCE) */
+static double mu_lo_at(const scene_t *S, int k) {
+    double m = 0;
+    for (int i = 0; i < S->tb->n_materials; i++) {
+        if (i == S->o->heavy) continue;
+        double v = S->tb->total[i][k] * S->tb->density[i];
+        if (v > m) m = v;
+    }
+    return m;
+}
+/* clearance (cm) of the cell holding (x,y,z): no voxel of the heavy material within this distance */
+static double clearance_at(const scene_t *S, double x, double y, double z) {
+    const monte_mc_volume *v = S->vol;
+    const double inv = 1.0 / v->pitch;
+    int ix = (int)floor((x - v->origin[0]) * inv), iy = (int)floor((y - v->origin[1]) * inv), iz = (int)floor((z - v->origin[2]) * inv);
+    if (ix < 0) ix = 0; if (iy < 0) iy = 0; if (iz < 0) iz = 0;
+    if (ix > v->nx - 1) ix = v->nx - 1; if (iy > v->ny - 1) iy = v->ny - 1; if (iz > v->nz - 1) iz = v->nz - 1;
+    const int s = v->clearance_cell_log2;
+    const int q = S->o->clear_grid[((size_t)(iz >> s) * S->o->clear_dims[1] + (iy >> s)) * S->o->clear_dims[0] + (ix >> s)];
+    return q * (0.5 * (double)(1 << s) * v->pitch);
+}
+
 /* voxel label at (x,y,z), 0 outside the clip box */
 static int lookup(const scene_t *S, double x, double y, double z) {
     const monte_mc_volume *v = S->vol;
@@ -230,9 +257,36 @@ static int delta_sampling(const scene_t *S, rng_t *R, photon_t *p, double E, dou
     const int q = S->o->quirks;
     const monte_mc_volume *v = S->vol;
     int collided = 0;
+    const int clearance = v->tracking_mode == MONTE_MC_TRACK_CLEARANCE && S->o->clear_grid && !q;
+    const double mu_lo = clearance ? mu_lo_at(S, k) : 0;
     for (;;) {
         double beta, nu;
         draw_step(R, &beta, &nu);
+        if (clearance && mu_lo > 0) {
+            /* two-level majorant (not in the reference; same distribution of collision sites): inside the
+             * clearance radius D of the current cell only the lighter materials occur, so the flight is sampled
+             * with their majorant; a flight longer than D stops at D without a collision (memoryless) */
+            const double D = clearance_at(S, x, y, z);
+            if (D > 0) {
+                double r = -log(beta) / mu_lo;
+                const int cut = r > D;
+                if (cut) r = D;
+                x += r * sin_theta_a * cos_phi_a; y += r * sin_theta_a * sin_phi_a; z += r * cos_theta_a;
+                length += r;
+                (*steps)++;
+                const int in_box = v->clip_lo[0] <= x && x < v->clip_hi[0] && v->clip_lo[1] <= y && y < v->clip_hi[1] &&
+                                   v->clip_lo[2] <= z && z < v->clip_hi[2];
+                if (!in_box) {
+                    const double far = 1000.0;
+                    x += far * sin_theta_a * cos_phi_a; y += far * sin_theta_a * sin_phi_a; z += far * cos_theta_a;
+                    break;
+                }
+                if (cut) continue;
+                int m = label_material(S, lookup(S, x, y, z));
+                if (m >= 0 && nu <= (S->tb->total[m][k] * S->tb->density[m]) / mu_lo) { collided = 1; break; }
+                continue;
+            }
+        }
         double r = -log(beta) / mu_max;
         x += r * sin_theta_a * cos_phi_a;
         y += r * sin_theta_a * sin_phi_a;

@@ -121,3 +121,33 @@ def test_emu_formfactor_images_counters_and_difference_from_forward_mode(monte_e
 
 def test_emu_formfactor_mode_needs_tables(monte_emu):
     R.test_formfactor_mode_needs_tables(monte_emu)
+
+
+# ---- two-level Woodcock majorant (tracking_mode = CLEARANCE): the GPU test bodies of tests/test_clearance_gpu.py
+import test_clearance_gpu as CL   # noqa: E402
+
+
+@pytest.mark.parametrize("cell_log2,poly,rayleigh", [(0, True, False), (1, True, False), (2, False, False), (1, True, True)])
+def test_emu_clearance_history_coupled_fates_match_oracle(monte_emu, oracle, cell_log2, poly, rayleigh):
+    CL.test_clearance_history_coupled_fates_match_oracle(monte_emu, oracle, cell_log2, poly, rayleigh)
+
+
+def test_emu_clearance_counters_and_fewer_steps_than_the_reference_loop(monte_emu, oracle):
+    CL.test_clearance_counters_and_fewer_steps_than_the_reference_loop(monte_emu, oracle)
+
+
+def test_emu_clearance_partition_and_label_update(monte_emu):
+    CL.test_clearance_partition_and_label_update(monte_emu)
+    # resident scene: new labels through monte_gpu_scene_update_labels rebuild the clearance grid
+    m = monte_emu
+    g, vol, lab = G.scene(n=33, pitch=1.0, det=9, views=1)
+    vol.tracking_mode, vol.clearance_cell_log2 = _abi.TRACK_CLEARANCE, 1
+    xs, spec = scenes.make_xs(), scenes.mono_spectrum(50.0)
+    lab2 = np.ascontiguousarray(lab[:, :, ::-1])                    # mirrored phantom: rods elsewhere
+    ref0, ref5, _ = m.simulate(g, vol, lab2, xs, spec, 30, 8)
+    sc = m.Scene(g, vol, lab, xs, spec)
+    sc.update_labels(lab2)
+    a0, a5 = np.zeros((1, 9, 9), np.int32), np.zeros((1, 9, 9), np.int32)
+    sc.simulate_dev(m.Dev(a0), m.Dev(a5), 30, 8)
+    sc.close()
+    assert np.array_equal(a0, ref0) and np.array_equal(a5, ref5)
