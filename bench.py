@@ -221,6 +221,7 @@ def main():
     ap.add_argument("--path", default="mc", choices=["mc", "fdk"],
                     help="which hot path provides the top-level keys (default: MC, BASELINE configs[1]); the other is nested")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-c4", action="store_true", help="skip the nested polyenergetic MC block (BASELINE configs[3])")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -362,6 +363,14 @@ def main():
         except Exception as e:                      # the headline line is still printed
             fdk = {"error": "%s: %s" % (type(e).__name__, e)}
 
+    # ------------------------------------------------------------------ MC, config 4 (polyenergetic), nested
+    c4 = None
+    if not args.skip_c4:
+        try:
+            c4 = bench_mc_c4(args, api, mdist, torch, dist, dev, ws, rank, flush, barrier, (g, vol, lab, xs))
+        except Exception as e:                      # the headline line is still printed
+            c4 = {"error": "%s: %s" % (type(e).__name__, e)}
+
     if rank == 0:
         line = {
             "metric": "photon_histories_per_s", "value": mc_value, "unit": "histories/s",
@@ -380,6 +389,7 @@ def main():
             "roofline": mc_roof, "cpu_baseline": mc_cpu,
             "wall_s_timed_region": t_wall,
             "fdk": fdk,
+            "mc_c4": c4,
         }
         if mc_cpu is not None and fdk and fdk.get("cpu_baseline") and "fdk" in shipped:
             fdk["cpu_baseline"]["as_shipped"] = shipped["fdk"]
@@ -391,6 +401,58 @@ def main():
         print(json.dumps(line))
     if ws > 1:
         dist.destroy_process_group()
+
+
+def bench_mc_c4(args, api, mdist, torch, dist, dev, ws, rank, flush, barrier, scene_parts):
+    """BASELINE configs[3]: full-scatter MC over a 120 kVp polyenergetic spectrum, photon ranges split across the
+    GPUs, one NCCL reduce per view.  Same C2 scene and per-view history count as the headline; timed for the
+    reference's single-majorant Woodcock loop and for the two-level majorant (tracking_mode CLEARANCE)."""
+    g, vol, lab, xs = scene_parts
+    spec, keep = scenes.kramers_spectrum()
+    npix = g.ny * g.nx
+    per_total = PER * ws
+    K, W = 6, 3
+    im0 = torch.zeros((g.n_views, g.ny, g.nx), dtype=torch.int32, device=dev)
+    im5 = torch.zeros_like(im0)
+    stats = torch.zeros(16, dtype=torch.int64, device=dev)
+    out = {"metric": "photon_histories_per_s", "unit": "histories/s", "scaling": "weak", "dtype": "f32", "steps": K, "warmup": W,
+           "config": {"workload": "C4 (BASELINE configs[3]) physics on the C2 scene: 120 kVp Kramers spectrum hardened by 2.5 cm of "
+                                  "water (0.5 keV bins), pencil-per-pixel source, <=5 scatters, %d histories per view per GPU" % (npix * PER),
+                      "parallelism": "photon-range x%d + 1 NCCL reduce/view" % ws if ws > 1 else "single GPU",
+                      "l2": "256 MiB fill between steps"}}
+    old_mode, old_cell = vol.tracking_mode, vol.clearance_cell_log2
+    try:
+        for name, mode in (("reference_loop", _abi.TRACK_GLOBAL), ("clearance", _abi.TRACK_CLEARANCE)):
+            vol.tracking_mode, vol.clearance_cell_log2 = mode, 2
+            scene = api.Scene(g, vol, lab, xs, spec)
+
+            def run_local(a0, a5, per, views, n_range):
+                scene.simulate_dev(a0, a5, per, seed=20261017, views=views, n_range=n_range, d_stats=stats)
+
+            for k in range(W):
+                mdist.mc_sharded_step(run_local, im0, im5, per_total, (k, k + 1))
+            stats.zero_()
+            barrier()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+            for k in range(K):
+                flush.fill_(k & 0xFF)
+                ev[k][0].record()
+                mdist.mc_sharded_step(run_local, im0, im5, per_total, (W + k, W + k + 1))
+                ev[k][1].record()
+            barrier()
+            ms = mdist.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), dev)
+            st = api.unpack_stats(stats.cpu().numpy().astype(np.uint64))
+            scene.close()
+            hist = npix * PER * ws * K
+            out[name] = {"value": hist / (ms * 1e-3), "ms_per_step": ms / K, "steps_per_history": st["woodcock_steps"] / st["histories"],
+                         "scatter_detected_fraction": st["scatter_detected"] / st["histories"],
+                         "seconds_for_1e11_histories": 1e11 / (hist / (ms * 1e-3))}
+    finally:
+        vol.tracking_mode, vol.clearance_cell_log2 = old_mode, old_cell
+    out["value"] = out["clearance"]["value"]
+    out["ms_per_step"] = out["clearance"]["ms_per_step"]
+    out["tracking"] = "two-level majorant, 4-voxel clearance cells (tracking_mode CLEARANCE); reference_loop = single majorant"
+    return out
 
 
 def bench_fdk(args, api, mdist, torch, dist, dev, ws, rank, pk, flush, barrier):
