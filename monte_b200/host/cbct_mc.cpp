@@ -1,9 +1,11 @@
 // cbct_mc — the role of the main() of monte_cu/CBCT_real325im.cu (:83-297): read the label volume and
 // the cross-section tables, run the photon transport, write the count images and the -log maps in
 // the reference's headerless layouts (proj*_0 / proj*_5 int32, map*_0 / map*_5 float32, [view][y][x]).
-//   cbct_mc labels.raw N pitch_cm xcom2.csv Ca.csv [det=325] [pixel=0.1] [views=360] [per=10000] [seed=0] [tag=out] [rayleigh=0]
+//   cbct_mc labels.raw N pitch_cm xcom2.csv Ca.csv [det=325] [pixel=0.1] [views=360] [per=10000] [seed=0] [tag=out] [rayleigh=0] [clearance=0]
 // rayleigh=1 (not in the reference): coherent events are deflected by the analytic form factor of
 // monte_xs_formfactor_hydrogenic (x0 = 1.0 for water, 2.2 for calcium) instead of flying straight on.
+// clearance=n > 0 (not in the reference): two-level Woodcock majorant with clearance cells of 2^n voxels
+// (monte_mc_volume.tracking_mode = MONTE_MC_TRACK_CLEARANCE): same physics, faster when calcium sets the majorant.
 // All compute is in libmonte_gpu (no CPU fallback: the call fails without a B200).
 #include <cstdio>
 #include <cstdlib>
@@ -20,7 +22,7 @@ static void write_raw(const std::string &fn, const void *p, size_t bytes) {
 }
 
 int main(int argc, char **argv) {
-    if (argc < 6) { fprintf(stderr, "usage: cbct_mc labels.raw N pitch xcom2.csv Ca.csv [det] [pixel] [views] [per] [seed] [tag] [rayleigh]\n"); return 2; }
+    if (argc < 6) { fprintf(stderr, "usage: cbct_mc labels.raw N pitch xcom2.csv Ca.csv [det] [pixel] [views] [per] [seed] [tag] [rayleigh] [clearance]\n"); return 2; }
     const int n = atoi(argv[2]);
     const double pitch = atof(argv[3]);
     const int det = argc > 6 ? atoi(argv[6]) : 325;
@@ -30,6 +32,7 @@ int main(int argc, char **argv) {
     const uint64_t seed = argc > 10 ? strtoull(argv[10], nullptr, 10) : 0;
     const std::string tag = argc > 11 ? argv[11] : "out";
     const bool rayleigh = argc > 12 && atoi(argv[12]) != 0;
+    const int clearance = argc > 13 ? atoi(argv[13]) : 0;
     std::vector<uint8_t> lab((size_t)n * n * n);
     FILE *f = fopen(argv[1], "rb");
     if (!f || fread(lab.data(), 1, lab.size(), f) != lab.size()) { fprintf(stderr, "failed to read %s\n", argv[1]); return 1; }
@@ -47,6 +50,7 @@ int main(int argc, char **argv) {
     monte_mc_volume v = {};
     v.nx = v.ny = v.nz = n; v.pitch = pitch;
     for (int a = 0; a < 3; a++) { v.origin[a] = -0.5 * n * pitch; v.clip_lo[a] = v.origin[a]; v.clip_hi[a] = -v.origin[a]; }
+    if (clearance > 0) { v.tracking_mode = MONTE_MC_TRACK_CLEARANCE; v.clearance_cell_log2 = clearance; }
     monte_mc_spectrum sp = {0, 0.5, 140.0, nullptr};                                              // as shipped: 140 keV
     if (monte_gpu_init(1, nullptr)) return fail();
     const size_t n_img = (size_t)views * det * det;

@@ -219,3 +219,70 @@ def test_rayleigh_mode_changes_only_coherent_histories(oracle):
     c0, c5, rc, _, _ = oracle.mc_run(g, vol, lab, tb, scenes.mono_spectrum(40.0), oracle.mc_opts(oracle.RNG_MT, seed=3), 400)
     for k in ("absorbed", "coherent", "compton"):
         assert abs(rc[k] - rb[k]) < 6 * math.sqrt(rc[k] + rb[k] + 1), (k, rc[k], rb[k])
+
+
+def test_clearance_grid_is_a_safe_lower_bound():
+    """monte_mc_clearance_grid (host helper): for every cell, no voxel of the heavy material lies closer to any
+    point of the cell than grid * half a cell side -- brute force on a small volume -- and the bound is tight to
+    within one grid unit somewhere"""
+    from monte_b200 import api
+    rng = np.random.default_rng(5)
+    lab = np.zeros((20, 24, 28), np.uint8)
+    lab[2:18, 3:20, 4:25] = 1
+    for _ in range(6):                                   # a few heavy blobs
+        z, y, x = rng.integers(2, 18), rng.integers(3, 20), rng.integers(4, 25)
+        lab[z:z + 2, y:y + 1, x:x + 3] = 2
+    lab[10, 11, 12] = 7                                  # label above n_materials clamps to the last (= heavy) material
+    vol = scenes.volume_for(lab, 0.5, tight=False)
+    xs = scenes.make_xs()
+    for cl in (0, 1, 2):
+        grid, heavy = api.clearance_grid(vol, lab, xs, cell_log2=cl)
+        assert heavy == 1
+        c = 1 << cl
+        hz, hy, hx = np.nonzero(lab >= 2)
+        gz, gy, gx = grid.shape
+        assert (gz, gy, gx) == (-(-20 // c), -(-24 // c), -(-28 // c))
+        slack = []
+        for cz in range(gz):
+            for cy in range(gy):
+                for cx in range(gx):
+                    # smallest distance (voxel units) between the cell's box and any heavy VOXEL's box
+                    dz = np.maximum(0, np.maximum(cz * c - (hz + 1), hz - (cz + 1) * c))
+                    dy = np.maximum(0, np.maximum(cy * c - (hy + 1), hy - (cy + 1) * c))
+                    dx = np.maximum(0, np.maximum(cx * c - (hx + 1), hx - (cx + 1) * c))
+                    true = np.sqrt(dz * dz + dy * dy + dx * dx).min()
+                    reach = grid[cz, cy, cx] * 0.5 * c
+                    assert reach <= true + 1e-9, (cl, cz, cy, cx, reach, true)
+                    slack.append(true - reach)
+        assert min(slack) < 0.5 * c + 1e-9 and np.mean(slack) < 1.5 * c      # conservative by at most about a cell
+
+
+def test_clearance_tracking_is_the_same_physics(oracle):
+    """tracking_mode CLEARANCE against the reference's single-majorant loop, both on MT19937: images agree by
+    chi-square, totals within 5 sigma, with a fraction of the tentative collisions"""
+    from monte_b200 import api
+    lab = scenes.cylinder_phantom(41, 0.5)
+    g = scenes.mc_geom(13, 32.5 / 13, n_views=2)
+    g.angle_step_deg = 22.5
+    vol = scenes.volume_for(lab, 0.5)
+    xs = scenes.make_xs()
+    tb = oracle.tables_from_xs(xs)
+    spec, keep = scenes.kramers_spectrum()
+    per = 3000
+    a0, a5, ra, _, _ = oracle.mc_run(g, vol, lab, tb, spec, oracle.mc_opts(oracle.RNG_MT, seed=1), per)
+    vol.tracking_mode, vol.clearance_cell_log2 = 1, 1
+    grid, heavy = api.clearance_grid(vol, lab, xs)
+    o, keepg = oracle.with_clearance(oracle.mc_opts(oracle.RNG_MT, seed=2), grid, heavy)
+    b0, b5, rb, _, _ = oracle.mc_run(g, vol, lab, tb, spec, o, per)
+    assert rb["woodcock_steps"] < 0.45 * ra["woodcock_steps"]
+    for k in ("primaries", "scatter_detected", "absorbed", "compton", "coherent", "interactions"):
+        assert abs(ra[k] - rb[k]) < 5 * math.sqrt(ra[k] + rb[k] + 1), (k, ra[k], rb[k])
+    for x, y, binom in ((a0, b0, per), (a5 - a0, b5 - b0, None)):
+        d = x.astype(np.float64) - y
+        var = (x + y).astype(np.float64)
+        if binom:
+            var = var * (1.0 - (x + y) / (2.0 * binom))
+        m = var > 0.5
+        c2, dof = (d[m] ** 2 / var[m]).sum(), int(m.sum())
+        assert abs(c2 - dof) < 5 * math.sqrt(2 * dof), (c2, dof)
+    assert abs(ra["sum_e_scatter"] / ra["scatter_detected"] - rb["sum_e_scatter"] / rb["scatter_detected"]) < 3.0
