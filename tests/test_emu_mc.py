@@ -151,3 +151,24 @@ def test_emu_clearance_partition_and_label_update(monte_emu):
     sc.simulate_dev(m.Dev(a0), m.Dev(a5), 30, 8)
     sc.close()
     assert np.array_equal(a0, ref0) and np.array_equal(a5, ref5)
+
+
+def test_emu_clearance_grid_cache_follows_the_label_content(monte_emu):
+    """the host-buffer call keeps the clearance grid of the last labels (keyed by a content hash): the same buffer
+    with new content must rebuild it"""
+    m = monte_emu
+    g, vol, lab = G.scene(n=33, pitch=1.0, det=9, views=1)
+    vol.tracking_mode, vol.clearance_cell_log2 = _abi.TRACK_CLEARANCE, 0
+    xs, spec = scenes.make_xs(), scenes.mono_spectrum(50.0)
+    buf = lab.copy()
+    a0, a5, _ = m.simulate(g, vol, buf, xs, spec, 30, 8)
+    b0, b5, _ = m.simulate(g, vol, buf, xs, spec, 30, 8)                 # cached grid
+    assert np.array_equal(a0, b0) and np.array_equal(a5, b5)
+    buf[:] = np.roll(lab, 5, axis=2)                                     # same buffer, the rods moved
+    c0, c5, _ = m.simulate(g, vol, buf, xs, spec, 30, 8)
+    sc = m.Scene(g, vol, buf.copy(), xs, spec)                           # a fresh scene builds its own grid
+    d0, d5 = np.zeros((1, 9, 9), np.int32), np.zeros((1, 9, 9), np.int32)
+    sc.simulate_dev(m.Dev(d0), m.Dev(d5), 30, 8)
+    sc.close()
+    assert np.array_equal(c0, d0) and np.array_equal(c5, d5)
+    assert not np.array_equal(c5, a5)
