@@ -537,9 +537,11 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 const float ex = fmaf(t0, dx, sx), ey = fmaf(t0, dy, sy), ez = t0 * dz;
                 uint32_t qe = 0u;
                 if (CLEAR) {                                  // clearance of the cell the photon enters through
-                    int ix = __float_as_int(fmaf(ex, sc.inv_pitch, vox_off[0]) + 12582912.0f) - 0x4B400000;
-                    int iy = __float_as_int(fmaf(ey, sc.inv_pitch, vox_off[1]) + 12582912.0f) - 0x4B400000;
-                    int iz = __float_as_int(fmaf(ez, sc.inv_pitch, vox_off[2]) + 12582912.0f) - 0x4B400000;
+                    // the entry point lies exactly on a voxel face of the clip box: take the voxel 1e-3 of a voxel
+                    // side further along the ray, so that the choice does not hang on rounding (the oracle does the same)
+                    int ix = __float_as_int(fmaf(ex, sc.inv_pitch, vox_off[0]) + 1e-3f * dx + 12582912.0f) - 0x4B400000;
+                    int iy = __float_as_int(fmaf(ey, sc.inv_pitch, vox_off[1]) + 1e-3f * dy + 12582912.0f) - 0x4B400000;
+                    int iz = __float_as_int(fmaf(ez, sc.inv_pitch, vox_off[2]) + 1e-3f * dz + 12582912.0f) - 0x4B400000;
                     ix = min(max(ix, 0), sc.nx - 1); iy = min(max(iy, 0), sc.ny - 1); iz = min(max(iz, 0), sc.nz - 1);
                     qe = __ldg(P.clear + ((unsigned)((iz >> P.cshift) * P.cgy + (iy >> P.cshift)) * (unsigned)P.cgx + (unsigned)(ix >> P.cshift)));
                 }

@@ -177,6 +177,7 @@ typedef struct {
 
 typedef struct {                 /* class photon, CBCT_real2.cpp:38-49 (fields that matter) */
     double x, y, z, x_p, y_p, z_p, length;
+    int at_entry;                /* tracking_mode CLEARANCE: the photon sits on the face of the clip box it entered through */
 } photon_t;
 
 static int table_index(double E) {
@@ -266,7 +267,10 @@ static int delta_sampling(const scene_t *S, rng_t *R, photon_t *p, double E, dou
             /* two-level majorant (not in the reference; same distribution of collision sites): inside the
              * clearance radius D of the current cell only the lighter materials occur, so the flight is sampled
              * with their majorant; a flight longer than D stops at D without a collision (memoryless) */
-            const double D = clearance_at(S, x, y, z);
+            /* on the entry face the cell is taken 1e-3 of a voxel side further along the ray (as in the kernel) */
+            const double nud = p->at_entry ? 1e-3 * v->pitch : 0.0;
+            p->at_entry = 0;
+            const double D = clearance_at(S, x + nud * sin_theta_a * cos_phi_a, y + nud * sin_theta_a * sin_phi_a, z + nud * cos_theta_a);
             if (D > 0) {
                 double r = -log(beta) / mu_lo;
                 const int cut = r > D;
@@ -435,7 +439,9 @@ static void history(const scene_t *S, rng_t *R, int view, int i, int j, uint64_t
 
     double cos_theta_a_new = 1., cos_phi_a_new = 0., sin_theta_a_new = 0., sin_phi_a_new = 1.;   /* :193 */
     int collided = 0;
+    P.at_entry = 1;
     if (!missed) collided = delta_sampling(S, R, &P, E, sin_theta_a, cos_theta_a, sin_phi_a, cos_phi_a, &steps);
+    P.at_entry = 0;
 
     const double cr = cos(M_PI * -num_p / 180), sr = sin(M_PI * -num_p / 180);   /* rotate back by -beta */
     uint32_t kind = 0, bin = 0, nint = 0;

@@ -189,3 +189,11 @@ def test_emu_shutdown_and_reinit_rebuild_every_cache(monte_emu, oracle):
     f2, v2, _, _ = m.fdk(g, proj)
     b0, b5, _ = m.simulate(*args)
     assert np.array_equal(f1, f2) and np.array_equal(v1, v2) and np.array_equal(a0, b0) and np.array_equal(a5, b5)
+
+
+def test_emu_smoke_path(monte_emu):
+    """__graft_entry__.smoke()'s own checks (FDK, FFT filter, MC coupled with the oracle, projector, the optional
+    transport modes), run on the emulated library; leaves the binding initialised for the tests that follow"""
+    import __graft_entry__ as ge
+    ge._smoke(monte_emu)
+    monte_emu.init(0)
