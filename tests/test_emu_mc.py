@@ -123,8 +123,8 @@ def test_emu_formfactor_mode_needs_tables(monte_emu):
     R.test_formfactor_mode_needs_tables(monte_emu)
 
 
-# ---- two-level Woodcock majorant (tracking_mode = CLEARANCE): the GPU test bodies of tests/test_clearance_gpu.py
-import test_clearance_gpu as CL   # noqa: E402
+# ---- two-level Woodcock majorant (tracking_mode = CLEARANCE): the GPU test bodies of tests/test_tracking_gpu.py
+import test_tracking_gpu as CL   # noqa: E402
 
 
 @pytest.mark.parametrize("cell_log2,poly,rayleigh", [(0, True, False), (1, True, False), (2, False, False), (1, True, True)])
