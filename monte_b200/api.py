@@ -85,6 +85,7 @@ def _bind(path):
         "monte_mc_clearance_dims": (C.c_int, [C.POINTER(McVolume), C.c_int, C.POINTER(C.c_int32)]),
         "monte_mc_clearance_grid": (C.c_int, [C.POINTER(McVolume), vp, C.c_int, C.c_int, C.c_int, vp]),
         "monte_xs_heavy_material": (C.c_int, [C.POINTER(McXs)]),
+        "monte_mc_resolve_tracking": (C.c_int, [C.POINTER(McXs), C.POINTER(McSpectrum), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
         "monte_gpu_fdk_slab_rows": (C.c_int, [C.POINTER(FdkGeom), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     }
     missing = []
@@ -310,6 +311,13 @@ def clearance_grid(vol, labels, xs, cell_log2=None):
     if heavy >= 0:
         _check(lib.monte_mc_clearance_grid(C.byref(vol), _ptr(labels), xs.n_materials, heavy, cl, _ptr(grid)))
     return grid, heavy
+
+
+def resolve_tracking(xs, spec):
+    """what MONTE_MC_TRACK_AUTO picks for these tables and this spectrum: (mode, cell_log2, mean majorant ratio)"""
+    cl, ratio = C.c_int32(0), C.c_double(0.0)
+    mode = load().monte_mc_resolve_tracking(C.byref(xs), C.byref(spec) if spec is not None else None, C.byref(cl), C.byref(ratio))
+    return mode, cl.value, ratio.value
 
 
 def project_primary(g, vol, labels, xs, keV, views=None, out=None):

@@ -256,4 +256,36 @@ int monte_xs_heavy_material(const monte_mc_xs *xs) {
     return best;
 }
 
+int monte_mc_resolve_tracking(const monte_mc_xs *xs, const monte_mc_spectrum *spec, int32_t *cell_log2, double *ratio) {
+    if (cell_log2) *cell_log2 = 2;
+    if (ratio) *ratio = 1.0;
+    const int heavy = monte_xs_heavy_material(xs);
+    if (heavy < 0) return MONTE_MC_TRACK_GLOBAL;
+    auto r_at = [&](double keV) {
+        int k = (int)(keV + 0.5);
+        if (k < 1) k = 1;
+        if (k > MONTE_MC_TABLE_ROWS - 1) k = MONTE_MC_TABLE_ROWS - 1;
+        double mx = 0, lo = 0;
+        for (int m = 0; m < xs->n_materials; m++) {
+            const double v = (double)xs->total[m][k] * (double)xs->density[m];
+            if (v > mx) mx = v;
+            if (m != heavy && v > lo) lo = v;
+        }
+        return lo > 0 ? mx / lo : 1.0;
+    };
+    double mean = 1.0;
+    if (spec && spec->n_bins > 0 && spec->cdf) {             // weights = the bin probabilities of the CDF
+        double acc = 0, wsum = 0;
+        for (int b = 0; b < spec->n_bins; b++) {
+            const double w = (double)spec->cdf[b + 1] - (double)spec->cdf[b];
+            if (w <= 0) continue;
+            acc += w * r_at((b + 1) * spec->bin_keV);
+            wsum += w;
+        }
+        if (wsum > 0) mean = acc / wsum;
+    } else mean = r_at(spec ? spec->mono_keV : 140.0);
+    if (ratio) *ratio = mean;
+    return mean > 3.0 ? MONTE_MC_TRACK_CLEARANCE : MONTE_MC_TRACK_GLOBAL;
+}
+
 }  // extern "C"

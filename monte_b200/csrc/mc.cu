@@ -623,8 +623,8 @@ static int check_mc(const monte_mc_geom *g, const monte_mc_volume *vol, const mo
               "mc: unknown detector_mode %d", g->detector_mode);
     MONTE_ARG(vol->nx > 0 && vol->ny > 0 && vol->nz > 0 && vol->pitch > 0, "mc: bad volume");
     MONTE_ARG((uint64_t)vol->nx * vol->ny * vol->nz < (1ull << 32), "mc: label volume has 2^32 voxels or more");
-    MONTE_ARG(vol->tracking_mode == MONTE_MC_TRACK_GLOBAL || vol->tracking_mode == MONTE_MC_TRACK_CLEARANCE,
-              "mc: unknown tracking_mode %d", vol->tracking_mode);
+    MONTE_ARG(vol->tracking_mode == MONTE_MC_TRACK_GLOBAL || vol->tracking_mode == MONTE_MC_TRACK_CLEARANCE ||
+              vol->tracking_mode == MONTE_MC_TRACK_AUTO, "mc: unknown tracking_mode %d", vol->tracking_mode);
     MONTE_ARG(vol->tracking_mode != MONTE_MC_TRACK_CLEARANCE || (vol->clearance_cell_log2 >= 0 && vol->clearance_cell_log2 <= 8),
               "mc: clearance_cell_log2 must be 0..8 (got %d)", vol->clearance_cell_log2);
     MONTE_ARG(xs->n_materials >= 1 && xs->n_materials <= MONTE_MC_MAX_MATERIALS, "mc: n_materials must be 1..%d", MONTE_MC_MAX_MATERIALS);
@@ -722,7 +722,10 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
     std::vector<float4> tab((size_t)nm * TAB_ROWS);
     std::vector<float> inv(TAB_ROWS), invlo(TAB_ROWS, 0.f);
     // tracking_mode CLEARANCE needs a material to exclude; with a single material it is the reference's loop
-    s->heavy = vol->tracking_mode == MONTE_MC_TRACK_CLEARANCE ? monte_xs_heavy_material(xs) : -1;
+    monte_mc_volume vres = *vol;                                   // AUTO resolved (same rule on every rank: inputs only)
+    if (vol->tracking_mode == MONTE_MC_TRACK_AUTO)
+        vres.tracking_mode = monte_mc_resolve_tracking(xs, spec, &vres.clearance_cell_log2, nullptr);
+    s->heavy = vres.tracking_mode == MONTE_MC_TRACK_CLEARANCE ? monte_xs_heavy_material(xs) : -1;
     for (int k = 0; k < TAB_ROWS; k++) {
         double mumax = 0, mulo = 0;
         for (int m = 0; m < nm; m++) {
@@ -760,7 +763,7 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
         }
     }
     size_t clear_bytes = 0;
-    s->vol = *vol; s->n_mat_host = nm;
+    s->vol = vres; s->n_mat_host = nm;
     if (s->heavy >= 0) {
         if (!s->d_invlo) MONTE_CUDA(cudaMalloc(&s->d_invlo, TAB_ROWS * sizeof(float)));
         MONTE_CUDA(cudaMemcpyAsync(s->d_invlo, invlo.data(), TAB_ROWS * sizeof(float), cudaMemcpyHostToDevice, st));

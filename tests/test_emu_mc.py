@@ -172,3 +172,18 @@ def test_emu_clearance_grid_cache_follows_the_label_content(monte_emu):
     sc.close()
     assert np.array_equal(c0, d0) and np.array_equal(c5, d5)
     assert not np.array_equal(c5, a5)
+
+
+def test_emu_auto_tracking_equals_the_mode_it_resolves_to(monte_emu):
+    m = monte_emu
+    g, vol, lab = G.scene(n=33, pitch=1.0, det=9, views=1)
+    xs = scenes.make_xs()
+    for spec in (scenes.mono_spectrum(140.0), scenes.mono_spectrum(50.0)):
+        mode, cl, ratio = m.resolve_tracking(xs, spec)
+        vol.tracking_mode, vol.clearance_cell_log2 = _abi.TRACK_AUTO, 0
+        a0, a5, sa = m.simulate(g, vol, lab, xs, spec, 30, 4)
+        vol.tracking_mode, vol.clearance_cell_log2 = mode, cl
+        b0, b5, sb = m.simulate(g, vol, lab, xs, spec, 30, 4)
+        assert np.array_equal(a0, b0) and np.array_equal(a5, b5) and sa["woodcock_steps"] == sb["woodcock_steps"]
+    assert m.resolve_tracking(xs, scenes.mono_spectrum(140.0))[0] == _abi.TRACK_GLOBAL
+    assert m.resolve_tracking(xs, scenes.mono_spectrum(50.0))[0] == _abi.TRACK_CLEARANCE
