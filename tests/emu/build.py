@@ -25,26 +25,32 @@ def _newer(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False):
-    os.makedirs(OUT, exist_ok=True)
+def build(force=False, asan=False):
+    """asan=True: a second copy under _build_asan/ compiled with -fsanitize=address (device buffers are heap
+    blocks there, so an out-of-bounds access of a kernel or of the host code is reported like by compute-sanitizer
+    memcheck); load it in a process started with LD_PRELOAD=libasan (tests/emu/asan_check.py)."""
+    out_dir = OUT + "_asan" if asan else OUT
+    lib_path = os.path.join(out_dir, "libmonte_gpu_emu.so")
+    flags = CXXFLAGS + (["-fsanitize=address", "-fno-omit-frame-pointer", "-O1"] if asan else [])
+    os.makedirs(out_dir, exist_ok=True)
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     hdrs += [os.path.join(ROOT, "include", "monte_gpu.h"), os.path.join(HERE, "cuda_runtime.h")]
     jobs, objs = [], []
     for src, lang in [(os.path.join(CSRC, f), ["-x", "c++"]) for f in CU] + \
                      [(os.path.join(CSRC, "host_helpers.cpp"), []), (os.path.join(HERE, "emu_runtime.cpp"), [])]:
-        obj = os.path.join(OUT, os.path.basename(src) + ".o")
+        obj = os.path.join(out_dir, os.path.basename(src) + ".o")
         objs.append(obj)
         if force or _newer(obj, [src] + hdrs):
-            jobs.append((src, subprocess.Popen(["g++"] + CXXFLAGS + lang + ["-c", src, "-o", obj],
+            jobs.append((src, subprocess.Popen(["g++"] + flags + lang + ["-c", src, "-o", obj],
                                                stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in jobs:
         out = p.communicate()[0]
         if p.returncode != 0:
             sys.stderr.write(out)
             raise RuntimeError("g++ (emulation build) failed on %s" % src)
-    if force or _newer(LIB, objs):
-        subprocess.check_call(["g++", "-shared", "-o", LIB] + objs)
-    return LIB
+    if force or _newer(lib_path, objs):
+        subprocess.check_call(["g++", "-shared"] + (["-fsanitize=address"] if asan else []) + ["-o", lib_path] + objs)
+    return lib_path
 
 
 class Dev:
@@ -65,11 +71,11 @@ class Dev:
 _api = None
 
 
-def api():
+def api(asan=False):
     """A private copy of the monte_b200.api module whose entry points call the emulation library."""
     global _api
     if _api is None:
-        lib_path = build()
+        lib_path = build(asan=asan)
         spec = importlib.util.spec_from_file_location("monte_b200._api_emu", os.path.join(ROOT, "monte_b200", "api.py"),
                                                       submodule_search_locations=None)
         mod = importlib.util.module_from_spec(spec)

@@ -197,3 +197,21 @@ def test_emu_smoke_path(monte_emu):
     import __graft_entry__ as ge
     ge._smoke(monte_emu)
     monte_emu.init(0)
+
+
+@pytest.mark.slow
+def test_emu_address_sanitizer_clean():
+    """tests/emu/asan_check.py: kernels and host code on the ASan build of the emulated library -- no out-of-bounds
+    access of any "device" buffer (the CPU counterpart of compute-sanitizer memcheck)"""
+    import subprocess
+    import sys
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan not installed")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "emu", "asan_check.py")], env=env,
+                       capture_output=True, text=True, timeout=900)
+    out = r.stdout + r.stderr
+    assert "ERROR: AddressSanitizer" not in out, out[-4000:]
+    assert r.returncode == 0 and "ASAN RUN COMPLETE" in out, out[-4000:]
