@@ -20,7 +20,8 @@ def main():
     spec = importlib.util.spec_from_file_location("monte_emu_build", os.path.join(HERE, "build.py"))
     eb = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(eb)
-    m = eb.api(asan=True)
+    ubsan = "--ubsan" in sys.argv      # LD_PRELOAD=$(gcc -print-file-name=libubsan.so) python tests/emu/asan_check.py --ubsan
+    m = eb.api(asan=not ubsan, ubsan=ubsan)
     import __graft_entry__ as ge
     ge._smoke(m)
     m.init(0)

@@ -25,13 +25,14 @@ def _newer(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, asan=False):
+def build(force=False, asan=False, ubsan=False):
     """asan=True: a second copy under _build_asan/ compiled with -fsanitize=address (device buffers are heap
     blocks there, so an out-of-bounds access of a kernel or of the host code is reported like by compute-sanitizer
     memcheck); load it in a process started with LD_PRELOAD=libasan (tests/emu/asan_check.py)."""
-    out_dir = OUT + "_asan" if asan else OUT
+    out_dir = OUT + "_asan" if asan else OUT + "_ubsan" if ubsan else OUT
     lib_path = os.path.join(out_dir, "libmonte_gpu_emu.so")
-    flags = CXXFLAGS + (["-fsanitize=address", "-fno-omit-frame-pointer", "-O1"] if asan else [])
+    san = "address" if asan else "undefined" if ubsan else None       # ubsan=True: same idea with -fsanitize=undefined
+    flags = CXXFLAGS + (["-fsanitize=" + san, "-fno-omit-frame-pointer", "-O1"] if san else [])
     os.makedirs(out_dir, exist_ok=True)
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     hdrs += [os.path.join(ROOT, "include", "monte_gpu.h"), os.path.join(HERE, "cuda_runtime.h")]
@@ -49,7 +50,7 @@ def build(force=False, asan=False):
             sys.stderr.write(out)
             raise RuntimeError("g++ (emulation build) failed on %s" % src)
     if force or _newer(lib_path, objs):
-        subprocess.check_call(["g++", "-shared"] + (["-fsanitize=address"] if asan else []) + ["-o", lib_path] + objs)
+        subprocess.check_call(["g++", "-shared"] + (["-fsanitize=" + san] if san else []) + ["-o", lib_path] + objs)
     return lib_path
 
 
@@ -71,11 +72,11 @@ class Dev:
 _api = None
 
 
-def api(asan=False):
+def api(asan=False, ubsan=False):
     """A private copy of the monte_b200.api module whose entry points call the emulation library."""
     global _api
     if _api is None:
-        lib_path = build(asan=asan)
+        lib_path = build(asan=asan, ubsan=ubsan)
         spec = importlib.util.spec_from_file_location("monte_b200._api_emu", os.path.join(ROOT, "monte_b200", "api.py"),
                                                       submodule_search_locations=None)
         mod = importlib.util.module_from_spec(spec)
