@@ -3,8 +3,9 @@ built with AddressSanitizer.  Device buffers are heap blocks in the emulation, s
 of a kernel (labels, filtered rows, volumes, tallies, tables, clearance grid) or of the C-ABI host code aborts with
 an ASan report -- the CPU counterpart of `compute-sanitizer --tool memcheck` (profiles/README.md).  Start with
     LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 python tests/emu/asan_check.py
-(tests/test_emu_fdk.py::test_emu_address_sanitizer_clean does).  Shared memory is one static block here, so
-overruns inside it are not seen; racecheck has no counterpart (fibers run one at a time).
+(tests/test_emu_fdk.py::test_emu_address_sanitizer_clean does).  Dynamic shared memory is a heap block of exactly
+the size the launch asked for, static __shared__ arrays are instrumented statics, so overruns of either are
+reported too; racecheck has no counterpart (fibers run one at a time).
 """
 import importlib.util
 import os

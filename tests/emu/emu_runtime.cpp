@@ -11,7 +11,7 @@ namespace monte_emu {
 namespace {
 
 constexpr size_t STACK_BYTES = 256 * 1024;
-constexpr size_t SMEM_BYTES = 256 * 1024;
+constexpr size_t SMEM_BYTES = 227 * 1024;       // the opt-in maximum of dynamic shared memory per CTA on sm_100
 
 struct Barrier {
     int arrived = 0;
@@ -40,7 +40,8 @@ struct Machine {
     Fiber *running = nullptr;
     const std::function<void()> *body = nullptr;
     bool progress = false;
-    alignas(128) char smem[SMEM_BYTES];
+    char *smem = nullptr;                 // dynamic shared memory of the running launch: a heap block of exactly the
+    size_t smem_bytes = 0;                // requested size, so the ASan build reports overruns of it as well
 };
 Machine *g_m = nullptr;
 ThreadCtx g_host_ctx;                     // cur() outside a launch
@@ -116,6 +117,9 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
     const size_t nthr = (size_t)block.x * block.y * block.z;
     if (nthr == 0 || nthr > 1024) { fprintf(stderr, "monte_emu: bad block size %zu\n", nthr); abort(); }
     m.body = &body;
+    free(m.smem);
+    m.smem = nullptr; m.smem_bytes = smem;
+    if (smem && posix_memalign((void **)&m.smem, 128, smem) != 0) { fprintf(stderr, "monte_emu: out of memory\n"); abort(); }
     for (unsigned bz = 0; bz < grid.z; bz++)
         for (unsigned by = 0; by < grid.y; by++)
             for (unsigned bx = 0; bx < grid.x; bx++) {
@@ -123,7 +127,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
                 m.warps.assign((nthr + 31) / 32, Warp());
                 m.cta = Barrier();
                 m.cta.live = (int)nthr;
-                memset(m.smem, 0xFF, smem);                  // uninitialised shared memory is garbage on the GPU too: NaNs here
+                if (smem) memset(m.smem, 0xFF, smem);        // uninitialised shared memory is garbage on the GPU too: NaNs here
                 size_t i = 0;
                 for (unsigned tz = 0; tz < block.z; tz++)
                     for (unsigned ty = 0; ty < block.y; ty++)
