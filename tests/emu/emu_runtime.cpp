@@ -145,10 +145,23 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
                             f.uc.uc_link = &m.sched;
                             makecontext(&f.uc, (void (*)())fiber_main, 0);
                         }
+                // MONTE_EMU_SCHED=reverse | random: the order in which runnable fibers are resumed.  A kernel whose
+                // barriers are complete gives the same result for every order; a missing barrier does not.
+                static const int sched = [] { const char *e = getenv("MONTE_EMU_SCHED");
+                                              return !e ? 0 : !strcmp(e, "reverse") ? 1 : !strcmp(e, "random") ? 2 : 0; }();
+                static uint64_t rng = 0x2545F4914F6CDD1Dull;
+                std::vector<size_t> order(nthr);
+                for (size_t k = 0; k < nthr; k++) order[k] = sched == 1 ? nthr - 1 - k : k;
                 size_t left = nthr;
                 while (left) {
                     m.progress = false;
-                    for (size_t k = 0; k < nthr; k++) {
+                    if (sched == 2)
+                        for (size_t k = nthr - 1; k > 0; k--) {         // Fisher-Yates with xorshift64*
+                            rng ^= rng >> 12; rng ^= rng << 25; rng ^= rng >> 27;
+                            std::swap(order[k], order[(size_t)((rng * 0x2545F4914F6CDD1Dull) >> 33) % (k + 1)]);
+                        }
+                    for (size_t kk = 0; kk < nthr; kk++) {
+                        const size_t k = order[kk];
                         Fiber &f = m.fibers[k];
                         if (f.done) continue;
                         m.running = &f;

@@ -187,3 +187,45 @@ def test_emu_auto_tracking_equals_the_mode_it_resolves_to(monte_emu):
         assert np.array_equal(a0, b0) and np.array_equal(a5, b5) and sa["woodcock_steps"] == sb["woodcock_steps"]
     assert m.resolve_tracking(xs, scenes.mono_spectrum(140.0))[0] == _abi.TRACK_GLOBAL
     assert m.resolve_tracking(xs, scenes.mono_spectrum(50.0))[0] == _abi.TRACK_CLEARANCE
+
+
+@pytest.mark.parametrize("sched", ["reverse", "random"])
+def test_emu_results_do_not_depend_on_the_thread_schedule(sched, tmp_path):
+    """racecheck-lite: the emulator resumes runnable threads in reverse or random order (MONTE_EMU_SCHED) -- every
+    kernel with complete barriers must give bit-identical results; MC tallies (integer atomics), the direct and FFT
+    filters (shared-memory tiles and exchange buffers), backprojection, transpose, projector"""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import os, sys, importlib.util
+import numpy as np
+root = sys.argv[1]
+sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
+spec = importlib.util.spec_from_file_location("monte_emu_build", os.path.join(root, "tests", "emu", "build.py"))
+eb = importlib.util.module_from_spec(spec); spec.loader.exec_module(eb)
+m = eb.api(); m.init(0)
+import test_mc_gpu as G
+from monte_b200 import _abi, scenes
+g, vol, lab = G.scene(n=33, pitch=1.0, det=17, views=2)
+vol.tracking_mode, vol.clearance_cell_log2 = 1, 1
+g.coherent_mode = 1
+xs = scenes.add_formfactors(scenes.make_xs())
+im0, im5, st = m.simulate(g, vol, lab, xs, scenes.mono_spectrum(60.0), 25, 9)
+fg = _abi.generic_fdk_geom(24, 65, 33, 32)
+f, v, zy, _ = m.fdk(fg, np.random.default_rng(1).random((24, 65, 33), dtype=np.float32), want_zy=True)
+gw = _abi.generic_fdk_geom(2, 300, 5, 8)
+fw = m.fdk(gw, np.random.default_rng(2).random((2, 300, 5), dtype=np.float32))[0]
+pm = m.project_primary(g, vol, lab, xs, 60.0)
+np.savez(sys.argv[2], im0=im0, im5=im5, f=f, v=v, zy=zy, fw=fw, pm=pm, steps=st["woodcock_steps"])
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for mode in ("forward", sched):
+        path = os.path.join(str(tmp_path), mode + ".npz")
+        r = subprocess.run([sys.executable, "-c", code, root, path], env=dict(os.environ, MONTE_EMU_SCHED=mode),
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.load(path))
+    for k in outs[0].files:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
