@@ -250,7 +250,9 @@ typedef struct monte_mc_geom {
     double  angle0_deg, angle_step_deg;  /* view v at angle0 + v*step (1 deg, :462,508) */
     int32_t ny, nx;          /* detector pixels: ny transaxial ("i"), nx axial ("j")    */
     double  pixel;           /* 0.1 (GPU) / 0.5 (CPU)                                    */
-    double  half;            /* detector_height 16.25 (CBCT_real325im.cu:459)            */
+    double  half;            /* detector_height 16.25 (CBCT_real325im.cu:459).  Pixel i covers [half - pixel*(i+1),
+                                half - pixel*i] on both axes; the reference's detector is square and centred,
+                                n * pixel = 2 * half (its bin formula :574-575 assumes that)              */
     double  dso, dod;        /* 160, 60                                                  */
     int32_t source_mode;
     int32_t max_scatter;     /* ScatterNUM = 5 (CBCT_real325im.cu:7)                     */

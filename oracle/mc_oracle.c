@@ -628,6 +628,7 @@ static void history(const scene_t *S, rng_t *R, int view, int i, int j, uint64_t
             if (a == g->max_scatter - 1 && kind == 4 && collided) kind = 5;   /* budget exhausted at a collision */
         }
         (void)escaped;
+        if (g->max_scatter == 0 && collided) kind = 5;    /* no interaction allowed at all: the budget ends at the first collision */
     }
     res->woodcock_steps += steps;
     if (fate) { *fate = kind | (bin << 8) | (nint << 28); if (fate_e) *fate_e = (float)E; }

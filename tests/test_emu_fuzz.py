@@ -1,0 +1,121 @@
+"""Seeded random sweeps of the C ABI against the oracle on the emulated library (tests/emu): ragged and degenerate
+FDK geometries (non-cubic volumes, partial ROIs, masks, both weight and coordinate modes, off-centre volumes, short
+scans) and MC scenes (odd detector sizes, view / photon sub-ranges, every source / detector / coherent / tracking
+mode, 1..3 materials).  The same parity bars as the GPU tests: FDK 1e-4 of max|reference| on every element, MC
+fates history by history.  Test infrastructure only: this is the CPU way to cover many edge cases per second of
+GPU time saved; the fixed-size GPU tests remain the parity proof on hardware.
+"""
+import numpy as np
+import pytest
+
+from monte_b200 import _abi, scenes
+
+REL = 1e-4
+
+
+def _fdk_case(rng):
+    nu, nv = int(rng.integers(9, 90)), int(rng.integers(3, 60))
+    views = int(rng.integers(3, 40))
+    g = _abi.generic_fdk_geom(views, nu, nv, 8, textbook=bool(rng.integers(0, 2)))
+    g.nx, g.ny, g.nz = int(rng.integers(3, 40)), int(rng.integers(3, 40)), int(rng.integers(1, 40))
+    g.vox = float(rng.uniform(0.3, 1.2))
+    g.x0 = -0.5 * g.nx * g.vox + float(rng.uniform(-2, 2))          # off-centre volumes too
+    g.y0 = 0.5 * g.ny * g.vox + float(rng.uniform(-2, 2))
+    g.z0 = 0.5 * g.nz * g.vox + float(rng.uniform(-3, 3))
+    g.full_roi()
+    if rng.integers(0, 2):
+        a, b = sorted(rng.integers(0, g.nx + 1, 2)); g.s_begin, g.s_end = int(a), int(b)
+        a, b = sorted(rng.integers(0, g.ny + 1, 2)); g.t_begin, g.t_end = int(a), int(b)
+        a, b = sorted(rng.integers(0, g.nz + 1, 2)); g.z_begin, g.z_end = int(a), int(b)
+    if rng.integers(0, 3) == 0:
+        g.mask_cs, g.mask_ct, g.mask_cz = g.nx // 2, g.ny // 2, g.nz // 2
+        g.mask_r2 = int(rng.integers(1, 400))
+    g.coord_mode = int(rng.integers(0, 2))
+    g.angle0_deg = float(rng.uniform(-30, 30))
+    if rng.integers(0, 3) == 0:
+        g.angle_step_deg = float(rng.uniform(0.5, 3.0))               # short scan
+    return g
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_emu_fuzz_fdk_against_oracle(monte_emu, oracle, seed):
+    rng = np.random.default_rng(1000 + seed)
+    g = _fdk_case(rng)
+    proj = rng.random((g.n_views, g.nu, g.nv), dtype=np.float32) - 0.3
+    want_zy = bool(rng.integers(0, 2))
+    f_o, xy_o, zy_o = oracle.fdk(g, proj, want_zy=want_zy)
+    f, xy, zy, _ = monte_emu.fdk(g, proj, want_zy=want_zy)
+    for got, ref, what in ((f, f_o, "filtered"), (xy, xy_o, "volume")):
+        scale = float(np.abs(ref).max())
+        err = float(np.abs(got.astype(np.float64) - ref).max())
+        assert err <= REL * scale + 1e-30, (what, err, scale, [getattr(g, k) for k, _ in g._fields_])
+    assert np.array_equal(xy == 0, xy_o == 0) or np.abs(xy[(xy == 0) != (xy_o == 0)]).max() <= REL * np.abs(xy_o).max()
+    if want_zy:
+        assert np.array_equal(zy.transpose(2, 1, 0), xy)
+
+
+def _mc_case(rng):
+    n = int(rng.choice([17, 25, 33]))
+    pitch = 33.0 / n * float(rng.uniform(0.6, 1.0))
+    mats = [("h2o",), ("h2o", "ca"), ("h2o", "ca", "pmma")][int(rng.integers(0, 3))]
+    lab = scenes.cylinder_phantom(n, pitch, radius=0.3 * n * pitch, half_len=0.35 * n * pitch,
+                                  rods=len(mats) > 1, rod_r=0.05 * n * pitch, rod_ring=0.15 * n * pitch)
+    if len(mats) == 3:
+        lab[lab == 1] = np.where(rng.random((lab == 1).sum()) < 0.5, 1, 3).astype(np.uint8)   # salt-and-pepper third material
+    # square detectors: monte_mc_geom has one pixel size and one half-extent like the reference (detector_height
+    # 16.25 on both axes, CBCT_real325im.cu:459), and its bin formula (:574-575) is centred, n * pixel = 2 * half
+    ny = nx = int(rng.integers(3, 14))
+    g = scenes.mc_geom(0, 32.5 / nx, n_views=int(rng.integers(1, 5)), ny=ny, nx=nx,
+                       source_mode=int(rng.integers(0, 2)), max_scatter=int(rng.integers(0, 7)))
+    g.angle0_deg, g.angle_step_deg = float(rng.uniform(0, 360)), float(rng.uniform(5, 120))
+    g.detector_mode = int(rng.integers(0, 2))
+    xs = scenes.make_xs(mats)
+    if rng.integers(0, 2):
+        g.coherent_mode = _abi.COHERENT_FORMFACTOR
+        scenes.add_formfactors(xs, mats)
+    vol = scenes.volume_for(lab, pitch, tight=bool(rng.integers(0, 2)))
+    vol.tracking_mode = int(rng.integers(0, 3))
+    vol.clearance_cell_log2 = int(rng.integers(0, 4))
+    if rng.integers(0, 2):
+        spec, keep = scenes.kramers_spectrum(kvp=float(rng.choice([80.0, 120.0])))
+    else:
+        spec, keep = scenes.mono_spectrum(float(rng.uniform(25, 150))), None
+    return g, vol, lab, xs, spec, keep
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_emu_fuzz_mc_fates_against_oracle(monte_emu, oracle, seed):
+    m = monte_emu
+    rng = np.random.default_rng(2000 + seed)
+    g, vol, lab, xs, spec, keep = _mc_case(rng)
+    per, sd = int(rng.integers(1, 40)), int(rng.integers(0, 2 ** 40))
+    view = int(rng.integers(0, g.n_views))
+    # what the kernel will do for AUTO, told to the oracle explicitly
+    mode, cl = vol.tracking_mode, vol.clearance_cell_log2
+    if mode == _abi.TRACK_AUTO:
+        mode, cl, _ = m.resolve_tracking(xs, spec)
+    ovol = _abi.McVolume.from_buffer_copy(vol)
+    ovol.tracking_mode, ovol.clearance_cell_log2 = mode, cl
+    opts = oracle.mc_opts(oracle.RNG_PHILOX, seed=sd)
+    if mode == _abi.TRACK_CLEARANCE and xs.n_materials > 1:
+        grid, heavy = m.clearance_grid(ovol, lab, xs)
+        opts, keepg = oracle.with_clearance(opts, grid, heavy)
+    sc = m.Scene(g, vol, lab, xs, spec)
+    f_k, e_k = sc.fates(view, per, sd)
+    sc.close()
+    i0, i5, res, f_o, e_o = oracle.mc_run(g, ovol, lab, oracle.tables_from_xs(xs), spec, opts, per,
+                                          views=(view, view + 1), want_fates=True)
+    same = f_k == f_o
+    assert same.mean() >= 0.995, (same.mean(), same.size)
+    assert np.allclose(e_k[same], e_o[same], rtol=2e-5)
+    # tallies of the same view through the host-buffer call, photons split in two ranges
+    cut = int(rng.integers(0, per + 1))
+    a0, a5, sa = m.simulate(g, vol, lab, xs, spec, per, sd, views=(view, view + 1), n_range=(0, cut))
+    b0, b5, sb = m.simulate(g, vol, lab, xs, spec, per, sd, views=(view, view + 1), n_range=(cut, per))
+    n = g.ny * g.nx * per
+    assert sa["histories"] + sb["histories"] == n == res["histories"]
+    scale = 16 * 200 if g.detector_mode else 1
+    assert np.abs((a0 + b0)[view].astype(np.int64) - i0[view]).sum() <= 0.005 * n * scale + 2 * scale * (~same).sum()
+    assert np.abs((a5 + b5)[view].astype(np.int64) - i5[view]).sum() <= 0.005 * n * scale + 2 * scale * (~same).sum()
+    other = [v for v in range(g.n_views) if v != view]
+    assert not (a0 + b0)[other].any() and not (a5 + b5)[other].any()
