@@ -119,3 +119,29 @@ def test_emu_fuzz_mc_fates_against_oracle(monte_emu, oracle, seed):
     assert np.abs((a5 + b5)[view].astype(np.int64) - i5[view]).sum() <= 0.005 * n * scale + 2 * scale * (~same).sum()
     other = [v for v in range(g.n_views) if v != view]
     assert not (a0 + b0)[other].any() and not (a5 + b5)[other].any()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_emu_fuzz_projector_against_oracle(monte_emu, oracle, seed):
+    """deterministic primary projection (1e-4 of the maximum, north_star) for random phantoms, detector sizes,
+    view ranges, angles (incl. axis-aligned ones, where whole rays run along voxel faces of even-sized volumes only)
+    and energies"""
+    rng = np.random.default_rng(3000 + seed)
+    n = int(rng.choice([9, 17, 25, 33]))
+    pitch = float(rng.uniform(0.4, 1.5))
+    mats = [("h2o",), ("h2o", "ca"), ("h2o", "ca", "pmma")][int(rng.integers(0, 3))]
+    lab = rng.integers(0, len(mats) + 2, size=(n, n, n)).astype(np.uint8)          # voxel noise incl. a label above n_materials
+    lab[rng.random(lab.shape) < 0.5] = 0
+    nd = int(rng.integers(2, 40))
+    g = scenes.mc_geom(nd, 32.5 / nd, n_views=int(rng.integers(1, 7)))
+    g.angle0_deg = float(rng.choice([0.0, 90.0, 45.0, rng.uniform(0, 360)]))
+    g.angle_step_deg = float(rng.choice([90.0, rng.uniform(1, 100)]))
+    vol = scenes.volume_for(lab, pitch, tight=bool(rng.integers(0, 2)))
+    xs = scenes.make_xs(mats)
+    keV = float(rng.uniform(15, 190))
+    a, b = sorted(rng.integers(0, g.n_views + 1, 2))
+    views = (int(a), int(b)) if b > a else None
+    got = monte_emu.project_primary(g, vol, lab, xs, keV, views=views)
+    ref = oracle.project_primary(g, vol, lab, oracle.tables_from_xs(xs), keV, views=views)
+    scale = float(np.abs(ref).max())
+    assert float(np.abs(got.astype(np.float64) - ref).max()) <= REL * scale + 1e-12, (scale, n, pitch, nd)
