@@ -22,7 +22,34 @@ struct ProjParams {
     float pixel, half, dso, dsd;
     double angle0, angle_step;
     float *map;                  // [n_views_total][ny][nx], written at absolute view index
+    // MACRO kernels: macro-cells of 2^mshift voxels per side; mcell[(cz*mgy + cy)*mgx + cx] = the label all voxels of
+    // the cell share, or 255 if they differ
+    const uint8_t *mcell;
+    int mshift, mgx, mgy;
 };
+
+// label shared by all voxels of a macro-cell (from the padded [z][y][x] copy), 255 = mixed (or the label 255 itself)
+__global__ void __launch_bounds__(128)
+macro_cell_kernel(const uint8_t *__restrict__ lab, uint8_t *__restrict__ mcell, int nx, int ny, int nz, int mshift,
+                  int mgx, int mgy, int mgz) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= mgx * mgy * mgz) return;
+    const int cx = c % mgx, cy = (c / mgx) % mgy, cz = c / (mgx * mgy);
+    const int C = 1 << mshift, px = nx + 2, py = ny + 2;
+    const int x1 = min((cx + 1) * C, nx), y1 = min((cy + 1) * C, ny), z1 = min((cz + 1) * C, nz);
+    int first = -1;
+    bool mixed = false;
+    for (int z = cz * C; z < z1 && !mixed; z++)
+        for (int y = cy * C; y < y1 && !mixed; y++) {
+            const uint8_t *row = lab + ((size_t)(z + 1) * py + (y + 1)) * px + 1;
+            for (int x = cx * C; x < x1; x++) {
+                const int l = row[x];
+                if (first < 0) first = l;
+                else if (l != first) { mixed = true; break; }
+            }
+        }
+    mcell[c] = (mixed || first < 0 || first == 255) ? 255 : (uint8_t)first;
+}
 
 // Raw labels [z][y][x] -> two copies with a one-voxel guard ring of air (label 0): `out` [z][y][x]
 // and `out_t` [z][x][y].  32x32 byte tiles go through shared memory for the transposed one.  The
@@ -55,6 +82,11 @@ labels_pad_transpose_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict_
 // step its rays sit in neighbouring voxels ACROSS the dominant direction of travel, so with the
 // label copy whose fastest axis is that transverse axis a warp-wide fetch touches one or two
 // 128-byte lines instead of 32.
+// MACRO = true (MONTE_PROJ_MACRO=n, macro-cells of 2^n voxels): whenever the walk enters a macro-cell whose voxels
+// all carry one label, the whole cell is crossed in one segment -- the DDA state of the three axes is advanced by the
+// number of voxel faces passed -- instead of voxel by voxel.  Same line integral (the segments still tile the ray),
+// far fewer steps through homogeneous regions.
+template <bool MACRO>
 __global__ void __launch_bounds__(128)
 project_primary_kernel(const __grid_constant__ ProjParams p) {
     __shared__ float s_mu[256];                               // per-label attenuation (a divergent index into
@@ -106,7 +138,46 @@ project_primary_kernel(const __grid_constant__ ProjParams p) {
         unsigned lin = (unsigned)((idx[2] + 1) * strides[2] + (idx[1] + 1) * strides[1] + (idx[0] + 1) * strides[0]);
         int lab = __ldg(lab_base + lin);
         float t = 0.f;
+        bool check = true;                                    // MACRO: a macro-cell was entered since the last look-up
+        const int cmask = (1 << p.mshift) - 1;
         while (t < len) {
+            if (MACRO && check) {
+                check = false;
+                if ((unsigned)idx[0] < (unsigned)p.nx && (unsigned)idx[1] < (unsigned)p.ny && (unsigned)idx[2] < (unsigned)p.nz) {
+                    const int cl = __ldg(p.mcell + ((idx[2] >> p.mshift) * p.mgy + (idx[1] >> p.mshift)) * p.mgx + (idx[0] >> p.mshift));
+                    if (cl != 255) {
+                        // faces left to the far side of the cell along each axis, and where the ray leaves the cell
+                        int k[3];
+                        float tx[3];
+#pragma unroll
+                        for (int a = 0; a < 3; a++) {
+                            const int in_cell = idx[a] & cmask;
+                            const int last = min(cmask, dims[a] - 1 - (idx[a] - in_cell));      // cells at the far edge are smaller
+                            k[a] = d[a] > 0.f ? last - in_cell : in_cell;
+                            tx[a] = fmaf(dt[a], (float)k[a], tn[a]);                            // 1e30 stays huge for d == 0
+                        }
+                        const float tex = fminf(tx[0], fminf(tx[1], tx[2]));
+                        const float te = fminf(tex, len);
+                        acc = fmaf(s_mu[cl], te - t, acc);
+                        t = te;
+                        if (tex >= len) break;
+                        // advance every axis by the faces it passed up to tex (the exit axis: all its k + 1)
+                        const int ea = tx[0] <= fminf(tx[1], tx[2]) ? 0 : (tx[1] <= tx[2] ? 1 : 2);
+#pragma unroll
+                        for (int a = 0; a < 3; a++) {
+                            int n = 0;
+                            if (a == ea) n = k[a] + 1;
+                            else if (tn[a] <= tex) n = min((int)((tex - tn[a]) / dt[a]) + 1, k[a]);
+                            tn[a] = fmaf(dt[a], (float)n, tn[a]);
+                            idx[a] += d[a] > 0.f ? n : -n;
+                            lin += (unsigned)(stp[a] * n);
+                        }
+                        lab = __ldg(lab_base + lin);
+                        check = true;
+                        continue;
+                    }
+                }
+            }
             const float m12 = fminf(tn[1], tn[2]);
             const bool ax = tn[0] <= m12;
             const bool ay = !ax && tn[1] <= tn[2];
@@ -119,6 +190,11 @@ project_primary_kernel(const __grid_constant__ ProjParams p) {
             if (ax) tn[0] += dt[0];
             if (ay) tn[1] += dt[1];
             if (az) tn[2] += dt[2];
+            if (MACRO) {                                      // keep the voxel index; a new macro-cell is worth a look-up
+                if (ax) { idx[0] += d[0] > 0.f ? 1 : -1; check = (idx[0] & cmask) == (d[0] > 0.f ? 0 : cmask); }
+                if (ay) { idx[1] += d[1] > 0.f ? 1 : -1; check = (idx[1] & cmask) == (d[1] > 0.f ? 0 : cmask); }
+                if (az) { idx[2] += d[2] > 0.f ? 1 : -1; check = (idx[2] & cmask) == (d[2] > 0.f ? 0 : cmask); }
+            }
         }
     }
     p.map[((size_t)view * p.det_ny + i) * p.det_nx + j] = acc;
@@ -145,16 +221,27 @@ extern "C" int monte_gpu_project_primary(const monte_mc_geom *g, const monte_mc_
     const size_t npad = (size_t)(vol->nx + 2) * (vol->ny + 2) * (vol->nz + 2);
     const size_t npad_al = (npad + 255) / 256 * 256;
     MONTE_ARG(npad < ((size_t)1 << 32), "project_primary: volume too large for 32-bit voxel offsets");
-    char *base = (char *)scratch(6, nvox_al + 2 * npad_al + n_map * sizeof(float));
+    // tuning knob: MONTE_PROJ_MACRO=n (1..6) crosses homogeneous macro-cells of 2^n voxels in one segment (0 = off)
+    static int macro = -1;
+    if (macro < 0) { const char *e = getenv("MONTE_PROJ_MACRO"); macro = e ? atoi(e) : 0; if (macro < 0 || macro > 6) macro = 0; }
+    const int mgx = macro ? ceil_div(vol->nx, 1 << macro) : 0, mgy = macro ? ceil_div(vol->ny, 1 << macro) : 0,
+              mgz = macro ? ceil_div(vol->nz, 1 << macro) : 0;
+    const size_t ncell_al = ((size_t)mgx * mgy * mgz + 255) / 256 * 256;
+    char *base = (char *)scratch(6, nvox_al + 2 * npad_al + ncell_al + n_map * sizeof(float));
     if (!base) return MONTE_E_NOMEM;
-    uint8_t *d_raw = (uint8_t *)base, *d_lab = d_raw + nvox_al, *d_lab_t = d_lab + npad_al;
-    float *d_map = (float *)(base + nvox_al + 2 * npad_al);
+    uint8_t *d_raw = (uint8_t *)base, *d_lab = d_raw + nvox_al, *d_lab_t = d_lab + npad_al, *d_cell = d_lab_t + npad_al;
+    float *d_map = (float *)(base + nvox_al + 2 * npad_al + ncell_al);
     MONTE_CUDA(cudaMemcpyAsync(d_raw, labels, nvox, cudaMemcpyHostToDevice, st));
     MONTE_CUDA(cudaMemsetAsync(d_lab, 0, 2 * npad_al, st));
     labels_pad_transpose_kernel MONTE_CFG(dim3(ceil_div(vol->nx, 32), ceil_div(vol->ny, 32), vol->nz), dim3(32, 8), 0, st)(
         d_raw, d_lab, d_lab_t, vol->nx, vol->ny);
     MONTE_CUDA(cudaGetLastError());
+    if (macro) {
+        macro_cell_kernel MONTE_CFG(ceil_div(mgx * mgy * mgz, 128), 128, 0, st)(d_lab, d_cell, vol->nx, vol->ny, vol->nz, macro, mgx, mgy, mgz);
+        MONTE_CUDA(cudaGetLastError());
+    }
     ProjParams p;
+    p.mcell = d_cell; p.mshift = macro; p.mgx = mgx; p.mgy = mgy;
     p.labels = d_lab; p.labels_t = d_lab_t; p.nx = vol->nx; p.ny = vol->ny; p.nz = vol->nz;
     p.pitch = (float)vol->pitch; p.inv_pitch = (float)(1.0 / vol->pitch);
     for (int a = 0; a < 3; a++) { p.org[a] = (float)vol->origin[a]; p.clip_lo[a] = (float)vol->clip_lo[a]; p.clip_hi[a] = (float)vol->clip_hi[a]; }
@@ -183,7 +270,8 @@ extern "C" int monte_gpu_project_primary(const monte_mc_geom *g, const monte_mc_
         const int v1 = v0 + chunk < view_end ? v0 + chunk : view_end;
         p.view_begin = v0; p.n_views_run = v1 - v0;
         dim3 grid(ceil_div(g->ny, 32), ceil_div(g->nx, 4), v1 - v0);
-        project_primary_kernel MONTE_CFG(grid, 128, 0, st)(p);
+        if (macro) project_primary_kernel<true> MONTE_CFG(grid, 128, 0, st)(p);
+        else project_primary_kernel<false> MONTE_CFG(grid, 128, 0, st)(p);
         MONTE_CUDA(cudaGetLastError());
         MONTE_CUDA(cudaEventRecord(ev[k], st));
         MONTE_CUDA(cudaStreamWaitEvent(cp, ev[k], 0));

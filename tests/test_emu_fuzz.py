@@ -130,8 +130,13 @@ def test_emu_fuzz_projector_against_oracle(monte_emu, oracle, seed):
     n = int(rng.choice([9, 17, 25, 33]))
     pitch = float(rng.uniform(0.4, 1.5))
     mats = [("h2o",), ("h2o", "ca"), ("h2o", "ca", "pmma")][int(rng.integers(0, 3))]
-    lab = rng.integers(0, len(mats) + 2, size=(n, n, n)).astype(np.uint8)          # voxel noise incl. a label above n_materials
-    lab[rng.random(lab.shape) < 0.5] = 0
+    if seed % 2:                                                                    # voxel noise incl. a label above n_materials
+        lab = rng.integers(0, len(mats) + 2, size=(n, n, n)).astype(np.uint8)
+        lab[rng.random(lab.shape) < 0.5] = 0
+    else:                                                                           # large homogeneous regions
+        lab = scenes.cylinder_phantom(n, pitch, radius=0.4 * n * pitch, half_len=0.3 * n * pitch, rods=len(mats) > 1,
+                                      rod_r=0.08 * n * pitch, rod_ring=0.2 * n * pitch)
+        lab[: n // 3, : n // 2, :] = np.where(lab[: n // 3, : n // 2, :] > 0, len(mats), 0)   # a block of the last material
     nd = int(rng.integers(2, 40))
     g = scenes.mc_geom(nd, 32.5 / nd, n_views=int(rng.integers(1, 7)))
     g.angle0_deg = float(rng.choice([0.0, 90.0, 45.0, rng.uniform(0, 360)]))
@@ -145,3 +150,18 @@ def test_emu_fuzz_projector_against_oracle(monte_emu, oracle, seed):
     ref = oracle.project_primary(g, vol, lab, oracle.tables_from_xs(xs), keV, views=views)
     scale = float(np.abs(ref).max())
     assert float(np.abs(got.astype(np.float64) - ref).max()) <= REL * scale + 1e-12, (scale, n, pitch, nd)
+
+
+@pytest.mark.parametrize("macro", ["1", "2", "3"])
+def test_emu_fuzz_projector_macro_cells(macro, oracle):
+    """MONTE_PROJ_MACRO=n (homogeneous macro-cells of 2^n voxels crossed in one segment; latched per process, hence
+    the subprocess): the same sweep and the fixed projector test must hold at the same 1e-4 bar"""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider",
+                        os.path.join(here, "test_emu_fuzz.py"), os.path.join(here, "test_emu_mc.py"),
+                        "-k", "fuzz_projector_against_oracle or emu_project_primary"],
+                       env=dict(os.environ, MONTE_PROJ_MACRO=macro), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and " passed" in r.stdout, (r.stdout[-3000:], r.stderr[-2000:])
