@@ -347,6 +347,17 @@ int monte_gpu_project_primary(const monte_mc_geom *g, const monte_mc_volume *vol
                               const uint8_t *labels, const monte_mc_xs *xs,
                               double keV, int view_begin, int view_end, float *map);
 
+/* Device-resident form of the same projector: the label copies are built once, the line integrals are written to
+ * a DEVICE buffer d_map [n_views][ny][nx] at the absolute view index -- the layout monte_gpu_fdk_filter_dev reads
+ * (iu = iy, iv = ix) -- so projection -> FDK needs no host round trip, and a multi-GPU host projects exactly the
+ * views it filters (BASELINE config 3: primary-only projection + FDK, sharded by views then z-slabs).
+ * Asynchronous on `stream` (a cudaStream_t passed as void*).                                                   */
+typedef struct monte_projector monte_projector;   /* opaque */
+int  monte_gpu_projector_create(const monte_mc_volume *vol, const uint8_t *labels /*host*/, monte_projector **out);
+void monte_gpu_projector_destroy(monte_projector *p);
+int  monte_gpu_project_primary_dev(const monte_projector *p, const monte_mc_geom *g, const monte_mc_xs *xs,
+                                   double keV, int view_begin, int view_end, float *d_map, void *stream);
+
 /* ---- host helpers shared by the C++ drivers (no GPU) ---------------------- */
 /* readcsv role (CBCT_real2.cpp:633-668): 200 rows "coh,compton,photo,total", UTF-8 BOM
  * and CRLF tolerated, row r -> index r+1 (keV); index 0 is a copy of index 1.

@@ -76,6 +76,9 @@ def _bind(path):
         "monte_gpu_counts_to_map_dev": (C.c_int, [vp, sz, i32, vp, vp]),
         "monte_gpu_project_primary": (C.c_int, [C.POINTER(McGeom), C.POINTER(McVolume), vp, C.POINTER(McXs),
                                                 C.c_double, C.c_int, C.c_int, vp]),
+        "monte_gpu_projector_create": (C.c_int, [C.POINTER(McVolume), vp, C.POINTER(vp)]),
+        "monte_gpu_projector_destroy": (None, [vp]),
+        "monte_gpu_project_primary_dev": (C.c_int, [vp, C.POINTER(McGeom), C.POINTER(McXs), C.c_double, C.c_int, C.c_int, vp, vp]),
         "monte_xs_load_csv": (C.c_int, [C.c_char_p, C.c_int, C.c_float, C.c_int, C.POINTER(McXs)]),
         "monte_make_fantom": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
         "monte_make_sphere": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -311,6 +314,32 @@ def clearance_grid(vol, labels, xs, cell_log2=None):
     if heavy >= 0:
         _check(lib.monte_mc_clearance_grid(C.byref(vol), _ptr(labels), xs.n_materials, heavy, cl, _ptr(grid)))
     return grid, heavy
+
+
+class Projector:
+    """Device-resident deterministic projector (label copies built once); project() writes line integrals into a
+    device tensor [n_views][ny][nx] -- the input layout of fdk_filter_dev."""
+
+    def __init__(self, vol, labels):
+        self._labels = np.ascontiguousarray(labels, np.uint8)
+        self.handle = C.c_void_p()
+        _check(load().monte_gpu_projector_create(C.byref(vol), _ptr(self._labels), C.byref(self.handle)))
+
+    def project(self, g, xs, keV, d_map, views=None, stream=None):
+        vb, ve = views if views else (0, g.n_views)
+        _check(load().monte_gpu_project_primary_dev(self.handle, C.byref(g), C.byref(xs), keV, vb, ve,
+                                                    C.c_void_p(d_map.data_ptr()), _stream_ptr(stream)))
+
+    def close(self):
+        if self.handle:
+            load().monte_gpu_projector_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def resolve_tracking(xs, spec):

@@ -282,3 +282,101 @@ extern "C" int monte_gpu_project_primary(const monte_mc_geom *g, const monte_mc_
     MONTE_CUDA(cudaStreamSynchronize(cp));
     return MONTE_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident projector: the label copies are built once, line integrals land in a device buffer
+// (the layout monte_gpu_fdk_filter_dev reads), so projection -> FDK runs without a host round trip and
+// a multi-GPU host projects exactly the views it filters (no exchange before the filter).
+// ------------------------------------------------------------------------------------------------
+struct monte_projector {
+    monte_mc_volume vol;
+    uint8_t *d_raw = nullptr, *d_lab = nullptr, *d_lab_t = nullptr, *d_cell = nullptr;
+    int macro = 0, mgx = 0, mgy = 0, mgz = 0;
+};
+
+static int macro_knob() {
+    const char *e = getenv("MONTE_PROJ_MACRO");
+    const int m = e ? atoi(e) : 0;
+    return m < 0 || m > 6 ? 0 : m;
+}
+
+extern "C" void monte_gpu_projector_destroy(monte_projector *s) {
+    if (!s) return;
+    cudaFree(s->d_raw);                        // one allocation holds all four buffers
+    delete s;
+}
+
+extern "C" int monte_gpu_projector_create(const monte_mc_volume *vol, const uint8_t *labels, monte_projector **out) {
+    MONTE_REQUIRE_INIT();
+    MONTE_ARG(vol && labels && out, "projector_create: NULL argument");
+    MONTE_ARG(vol->nx > 0 && vol->ny > 0 && vol->nz > 0 && vol->pitch > 0, "projector_create: bad volume");
+    const size_t nvox = (size_t)vol->nx * vol->ny * vol->nz;
+    const size_t nvox_al = (nvox + 255) / 256 * 256;
+    const size_t npad = (size_t)(vol->nx + 2) * (vol->ny + 2) * (vol->nz + 2);
+    const size_t npad_al = (npad + 255) / 256 * 256;
+    MONTE_ARG(npad < ((size_t)1 << 32), "projector_create: volume too large for 32-bit voxel offsets");
+    for (int a = 0; a < 3; a++) MONTE_ARG(vol->clip_lo[a] < vol->clip_hi[a], "projector_create: empty clip box");
+    monte_projector *s = new monte_projector();
+    s->vol = *vol;
+    s->macro = macro_knob();
+    if (s->macro) {
+        s->mgx = ceil_div(vol->nx, 1 << s->macro); s->mgy = ceil_div(vol->ny, 1 << s->macro); s->mgz = ceil_div(vol->nz, 1 << s->macro);
+    }
+    const size_t ncell_al = ((size_t)s->mgx * s->mgy * s->mgz + 255) / 256 * 256;
+    cudaStream_t st = ctx().stream;
+    cudaError_t e = cudaMalloc(&s->d_raw, nvox_al + 2 * npad_al + ncell_al + 256);
+    if (e != cudaSuccess) { delete s; return cuda_fail(e, "cudaMalloc(projector)", __FILE__, __LINE__); }
+    s->d_lab = s->d_raw + nvox_al; s->d_lab_t = s->d_lab + npad_al; s->d_cell = s->d_lab_t + npad_al;
+    int rc = MONTE_OK;
+    do {
+        if ((e = cudaMemcpyAsync(s->d_raw, labels, nvox, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(s->d_lab, 0, 2 * npad_al, st)) != cudaSuccess) break;
+        labels_pad_transpose_kernel MONTE_CFG(dim3(ceil_div(vol->nx, 32), ceil_div(vol->ny, 32), vol->nz), dim3(32, 8), 0, st)(
+            s->d_raw, s->d_lab, s->d_lab_t, vol->nx, vol->ny);
+        if (s->macro)
+            macro_cell_kernel MONTE_CFG(ceil_div(s->mgx * s->mgy * s->mgz, 128), 128, 0, st)(s->d_lab, s->d_cell, vol->nx, vol->ny, vol->nz,
+                                                                                       s->macro, s->mgx, s->mgy, s->mgz);
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        e = cudaStreamSynchronize(st);             // `labels` may be pageable; the scene is ready when this returns
+    } while (0);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "projector_create", __FILE__, __LINE__); monte_gpu_projector_destroy(s); return rc; }
+    *out = s;
+    return MONTE_OK;
+}
+
+extern "C" int monte_gpu_project_primary_dev(const monte_projector *s, const monte_mc_geom *g, const monte_mc_xs *xs, double keV,
+                                             int view_begin, int view_end, float *d_map, void *stream) {
+    MONTE_REQUIRE_INIT();
+    MONTE_ARG(s && g && xs && d_map, "project_primary_dev: NULL argument");
+    MONTE_ARG(g->n_views > 0 && g->ny > 0 && g->nx > 0 && g->pixel > 0, "project_primary_dev: bad detector");
+    MONTE_ARG(xs->n_materials >= 1 && xs->n_materials <= MONTE_MC_MAX_MATERIALS, "project_primary_dev: bad materials");
+    MONTE_ARG(0 <= view_begin && view_begin <= view_end && view_end <= g->n_views, "project_primary_dev: bad view range");
+    if (view_begin == view_end) return MONTE_OK;
+    const monte_mc_volume *vol = &s->vol;
+    ProjParams p;
+    p.labels = s->d_lab; p.labels_t = s->d_lab_t; p.nx = vol->nx; p.ny = vol->ny; p.nz = vol->nz;
+    p.pitch = (float)vol->pitch; p.inv_pitch = (float)(1.0 / vol->pitch);
+    for (int a = 0; a < 3; a++) { p.org[a] = (float)vol->origin[a]; p.clip_lo[a] = (float)vol->clip_lo[a]; p.clip_hi[a] = (float)vol->clip_hi[a]; }
+    int k = (int)(keV + 0.5);
+    k = k < 0 ? 0 : (k > MONTE_MC_TABLE_ROWS - 1 ? MONTE_MC_TABLE_ROWS - 1 : k);
+    for (int l = 0; l < 256; l++) {
+        const int m = l == 0 ? -1 : (l <= xs->n_materials ? l - 1 : xs->n_materials - 1);
+        p.mu[l] = m < 0 ? 0.f : (float)((double)xs->total[m][k] * (double)xs->density[m]);
+    }
+    p.view_begin = view_begin; p.n_views_run = view_end - view_begin; p.det_ny = g->ny; p.det_nx = g->nx;
+    p.pixel = (float)g->pixel; p.half = (float)g->half; p.dso = (float)g->dso; p.dsd = (float)(g->dso + g->dod);
+    p.angle0 = g->angle0_deg; p.angle_step = g->angle_step_deg;
+    p.map = d_map;
+    p.mcell = s->d_cell; p.mshift = s->macro; p.mgx = s->mgx; p.mgy = s->mgy;
+    cudaStream_t st = (cudaStream_t)stream;
+    // grid.z carries the views: at most 65535 per launch
+    for (int v0 = view_begin; v0 < view_end; v0 += 32768) {
+        const int v1 = v0 + 32768 < view_end ? v0 + 32768 : view_end;
+        p.view_begin = v0; p.n_views_run = v1 - v0;
+        dim3 grid(ceil_div(g->ny, 32), ceil_div(g->nx, 4), v1 - v0);
+        if (s->macro) project_primary_kernel<true> MONTE_CFG(grid, 128, 0, st)(p);
+        else project_primary_kernel<false> MONTE_CFG(grid, 128, 0, st)(p);
+        MONTE_CUDA(cudaGetLastError());
+    }
+    return MONTE_OK;
+}

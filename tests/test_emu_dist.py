@@ -70,3 +70,73 @@ def test_emu_ranks_equal_one_process(monte_emu, tmp_path, ws):
     for r in range(ws):                           # the equal-work partition reconstructs the same voxels
         u = np.load(os.path.join(str(tmp_path), "u%d.npz" % r))
         assert np.array_equal(u["slab"], vol[u["z"][0]:u["z"][1]])
+
+
+PIPE_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+''' + EMU_API + r'''
+from monte_b200 import dist as mdist
+rank, ws = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+api.init(0)
+out = sys.argv[1]
+# BASELINE config 3 in small: deterministic projection of the phantom, sharded by views (each rank projects exactly the
+# views it filters), one band-limited all_to_all of filtered rows, z-slabs of equal work
+lab = scenes.cylinder_phantom(33, 0.8)
+vol = scenes.volume_for(lab, 0.8)
+xs = scenes.make_xs()
+n_views, nu, nv = 30, 40, 24
+g = scenes.mc_geom(0, 32.5 / nu, n_views=n_views, ny=nu, nx=nv)
+fg = _abi.generic_fdk_geom(n_views, nu, nv, 40, textbook=True)
+d_map = torch.full((n_views, nu, nv), float("nan"))
+filt = torch.full(api.fdk_filtered_shape(fg), float("nan"))
+zr = mdist.fdk_z_partition(fg, ws, block=8)
+norm = [[tuple(q)] if not isinstance(q[0], (tuple, list)) else [tuple(x) for x in q] for q in zr]
+slabs = {}
+pr = api.Projector(vol, lab)
+
+def project_and_filter(a, b):
+    pr.project(g, xs, 70.0, d_map, views=(a, b))
+    api.fdk_filter_dev(fg, d_map, filt, a, b, pad=False)
+
+def backproject(a, b):
+    slabs[(a, b)] = torch.empty((b - a, fg.ny, fg.nx))
+    api.fdk_backproject_dev(fg, filt, slabs[(a, b)], a, b)
+
+mdist.fdk_sharded_band(project_and_filter, lambda: api.fdk_pad_dev(fg, filt), backproject, lambda a, b: api.fdk_slab_rows(fg, a, b),
+                       filt, fg.n_views, fg.nv, zr)
+pr.close()
+np.savez(os.path.join(out, "p%%d.npz" %% rank), **{"%%d_%%d" %% k: v.numpy() for k, v in slabs.items()})
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("ws", [2, 3])
+def test_emu_config3_pipeline_sharded_equals_one_process(monte_emu, tmp_path, ws):
+    """projection -> filter -> band exchange -> backprojection, every stage on the "device", sharded over ws ranks:
+    the slabs tile the volume and equal the single-process host-buffer chain bit for bit"""
+    script = os.path.join(str(tmp_path), "pw.py")
+    with open(script, "w") as f:
+        f.write(PIPE_WORKER % ROOT)
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % ws,
+                           "--master-addr", "127.0.0.1", "--master-port", str(29900 + os.getpid() % 90 + ws), script, str(tmp_path)],
+                          timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    m = monte_emu
+    lab = scenes.cylinder_phantom(33, 0.8)
+    vol = scenes.volume_for(lab, 0.8)
+    xs = scenes.make_xs()
+    n_views, nu, nv = 30, 40, 24
+    g = scenes.mc_geom(0, 32.5 / nu, n_views=n_views, ny=nu, nx=nv)
+    fg = _abi.generic_fdk_geom(n_views, nu, nv, 40, textbook=True)
+    _, ref, _, _ = m.fdk(fg, m.project_primary(g, vol, lab, xs, 70.0), want_filtered=False)
+    assert np.abs(ref).max() > 0
+    covered = np.zeros(fg.nz, int)
+    for r in range(ws):
+        z = np.load(os.path.join(str(tmp_path), "p%d.npz" % r))
+        for key in z.files:
+            a, b = (int(x) for x in key.split("_"))
+            assert np.array_equal(z[key], ref[a:b]), (r, a, b)
+            covered[a:b] += 1
+    assert (covered == 1).all()

@@ -229,3 +229,7 @@ np.savez(sys.argv[2], im0=im0, im5=im5, f=f, v=v, zy=zy, fw=fw, pm=pm, steps=st[
         outs.append(np.load(path))
     for k in outs[0].files:
         assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+def test_emu_resident_projector_feeds_fdk_like_the_host_path(monte_emu, oracle):
+    CL.test_resident_projector_feeds_fdk_like_the_host_path(monte_emu, oracle)

@@ -87,3 +87,46 @@ def test_clearance_partition_and_label_update(monte):
     vol.tracking_mode, vol.clearance_cell_log2 = _abi.TRACK_CLEARANCE, 11
     with pytest.raises(monte.MonteError, match="clearance_cell_log2"):
         monte.simulate(g, vol, lab, xs, spec, 2, 1)
+
+
+# ---- device-resident projector (monte_gpu_project_primary_dev): BASELINE config 3 without the host round trip
+def _dev_buffers(monte, shapes):
+    """device float32 buffers for the *_dev entry points: CUDA tensors on the GPU, host arrays under emulation"""
+    if hasattr(monte, "Dev"):
+        arrs = [np.full(s, np.nan, np.float32) for s in shapes]
+        return [monte.Dev(a) for a in arrs], (lambda d: d.a), (lambda: None)
+    import torch
+    ts = [torch.full(tuple(int(x) for x in s), float("nan"), dtype=torch.float32, device="cuda") for s in shapes]
+    return ts, (lambda t: t.cpu().numpy()), torch.cuda.synchronize
+
+
+def test_resident_projector_feeds_fdk_like_the_host_path(monte, oracle):
+    """projection on the device -> filter -> backprojection equals project_primary (host buffers) -> fdk, bit for
+    bit; the projection itself equals the oracle's within 1e-4 (north_star)"""
+    lab = scenes.cylinder_phantom(33, 0.8)
+    vol = scenes.volume_for(lab, 0.8)
+    xs = scenes.make_xs()
+    n_views, nu, nv = 24, 40, 24
+    g = scenes.mc_geom(0, 32.5 / nu, n_views=n_views, ny=nu, nx=nv)              # ny = transaxial = FDK's iu
+    fg = _abi.generic_fdk_geom(n_views, nu, nv, 32, textbook=True)
+    fg.angle0_deg, fg.angle_step_deg = g.angle0_deg, g.angle_step_deg
+    host_map = monte.project_primary(g, vol, lab, xs, 70.0)
+    ref = oracle.project_primary(g, vol, lab, oracle.tables_from_xs(xs), 70.0)
+    assert np.abs(host_map - ref).max() <= 1e-4 * np.abs(ref).max()
+    _, vol_host, _, _ = monte.fdk(fg, host_map, want_filtered=False)
+    (d_map, d_filt, d_vol), to_np, sync = _dev_buffers(monte, [(n_views, nu, nv), monte.fdk_filtered_shape(fg), (fg.nz, fg.ny, fg.nx)])
+    pr = monte.Projector(vol, lab)
+    pr.project(g, xs, 70.0, d_map, views=(0, 9))                                  # in two view ranges, as a sharded host would
+    pr.project(g, xs, 70.0, d_map, views=(9, n_views))
+    monte.fdk_filter_dev(fg, d_map, d_filt)
+    monte.fdk_backproject_dev(fg, d_filt, d_vol)
+    sync()
+    pr.close()
+    assert np.array_equal(to_np(d_map), host_map)
+    assert np.array_equal(to_np(d_vol), vol_host)
+    with pytest.raises(monte.MonteError, match="view range"):
+        pr2 = monte.Projector(vol, lab)
+        try:
+            pr2.project(g, xs, 70.0, d_map, views=(3, 99))
+        finally:
+            pr2.close()
