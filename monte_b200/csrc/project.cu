@@ -26,7 +26,35 @@ struct ProjParams {
     // the cell share, or 255 if they differ
     const uint8_t *mcell;
     int mshift, mgx, mgy;
+    // leaping: mrad[cell] = n means the (2n-1)^3 block of macro-cells centred on the cell shares the cell's label
+    // (0 for mixed cells); a ray inside the cell can advance (n-1) cell sides without leaving that block
+    const uint8_t *mrad;
+    float leap_unit;             // one cell side in cm, minus a safety margin
 };
+
+// one erosion pass of the block radius: a cell of radius `pass` whose 26 neighbours carry its label with radius >= pass
+// has radius pass + 1 (cells outside the grid count as different)
+__global__ void __launch_bounds__(128)
+macro_radius_kernel(const uint8_t *__restrict__ mcell, const uint8_t *__restrict__ rin, uint8_t *__restrict__ rout,
+                    int mgx, int mgy, int mgz, int pass) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= mgx * mgy * mgz) return;
+    int r = pass == 0 ? (mcell[c] != 255 ? 1 : 0) : rin[c];
+    if (pass > 0 && r == pass) {
+        const int cx = c % mgx, cy = (c / mgx) % mgy, cz = c / (mgx * mgy);
+        bool grow = cx > 0 && cy > 0 && cz > 0 && cx < mgx - 1 && cy < mgy - 1 && cz < mgz - 1;
+        const int l = mcell[c];
+        for (int dz = -1; dz <= 1 && grow; dz++)
+            for (int dy = -1; dy <= 1 && grow; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    const int nb = ((cz + dz) * mgy + cy + dy) * mgx + cx + dx;
+                    if (mcell[nb] != l || rin[nb] < pass) { grow = false; break; }
+                }
+        if (grow) r = pass + 1;
+    }
+    rout[c] = (uint8_t)r;
+}
+constexpr int PROJ_LEAP_PASSES = 24;     // block radius up to 25 cells
 
 // label shared by all voxels of a macro-cell (from the padded [z][y][x] copy), 255 = mixed (or the label 255 itself)
 __global__ void __launch_bounds__(128)
@@ -146,6 +174,29 @@ project_primary_kernel(const __grid_constant__ ProjParams p) {
                 if ((unsigned)idx[0] < (unsigned)p.nx && (unsigned)idx[1] < (unsigned)p.ny && (unsigned)idx[2] < (unsigned)p.nz) {
                     const int cl = __ldg(p.mcell + ((idx[2] >> p.mshift) * p.mgy + (idx[1] >> p.mshift)) * p.mgx + (idx[0] >> p.mshift));
                     if (cl != 255) {
+                        const int nr = __ldg(p.mrad + ((idx[2] >> p.mshift) * p.mgy + (idx[1] >> p.mshift)) * p.mgx + (idx[0] >> p.mshift));
+                        if (nr >= 2) {
+                            // deep inside a homogeneous block: leap (nr - 1) cell sides in one segment, then set the
+                            // voxel walk up again at the landing point (as at the entry point above)
+                            const float te = fminf(fmaf((float)(nr - 1), p.leap_unit, t), len);
+                            acc = fmaf(s_mu[cl], te - t, acc);
+                            t = te;
+                            if (te >= len) break;
+#pragma unroll
+                            for (int a = 0; a < 3; a++) {
+                                const float e = fmaf(t0 + t, d[a], src[a]);
+                                const float q = fmaf(1e-4f * p.pitch, d[a], e);
+                                idx[a] = min(max((int)floorf((q - p.org[a]) * p.inv_pitch), 0), dims[a] - 1);
+                                if (d[a] != 0.f) {
+                                    const float edge = p.org[a] + (float)(idx[a] + (d[a] > 0.f ? 1 : 0)) * p.pitch;
+                                    tn[a] = t + fmaxf((edge - e) / d[a], 0.f);
+                                }
+                            }
+                            lin = (unsigned)((idx[2] + 1) * strides[2] + (idx[1] + 1) * strides[1] + (idx[0] + 1) * strides[0]);
+                            lab = __ldg(lab_base + lin);
+                            check = true;
+                            continue;
+                        }
                         // faces left to the far side of the cell along each axis, and where the ray leaves the cell
                         int k[3];
                         float tx[3];
@@ -204,6 +255,19 @@ project_primary_kernel(const __grid_constant__ ProjParams p) {
 
 using namespace monte;
 
+// block radius of every macro-cell by PROJ_LEAP_PASSES ping-pong erosion passes; *out = the buffer holding the result
+static int macro_radius(const uint8_t *d_cell, uint8_t *a, uint8_t *b, int mgx, int mgy, int mgz, cudaStream_t st, const uint8_t **out) {
+    const int n = mgx * mgy * mgz;
+    uint8_t *src = b, *dst = a;
+    for (int pass = 0; pass <= PROJ_LEAP_PASSES; pass++) {
+        macro_radius_kernel MONTE_CFG(ceil_div(n, 128), 128, 0, st)(d_cell, src, dst, mgx, mgy, mgz, pass);
+        MONTE_CUDA(cudaGetLastError());
+        uint8_t *t = src; src = dst; dst = t;
+    }
+    *out = src;
+    return MONTE_OK;
+}
+
 extern "C" int monte_gpu_project_primary(const monte_mc_geom *g, const monte_mc_volume *vol, const uint8_t *labels,
                                          const monte_mc_xs *xs, double keV, int view_begin, int view_end, float *map) {
     MONTE_REQUIRE_INIT();
@@ -227,21 +291,24 @@ extern "C" int monte_gpu_project_primary(const monte_mc_geom *g, const monte_mc_
     const int mgx = macro ? ceil_div(vol->nx, 1 << macro) : 0, mgy = macro ? ceil_div(vol->ny, 1 << macro) : 0,
               mgz = macro ? ceil_div(vol->nz, 1 << macro) : 0;
     const size_t ncell_al = ((size_t)mgx * mgy * mgz + 255) / 256 * 256;
-    char *base = (char *)scratch(6, nvox_al + 2 * npad_al + ncell_al + n_map * sizeof(float));
+    char *base = (char *)scratch(6, nvox_al + 2 * npad_al + 3 * ncell_al + n_map * sizeof(float));
     if (!base) return MONTE_E_NOMEM;
     uint8_t *d_raw = (uint8_t *)base, *d_lab = d_raw + nvox_al, *d_lab_t = d_lab + npad_al, *d_cell = d_lab_t + npad_al;
-    float *d_map = (float *)(base + nvox_al + 2 * npad_al + ncell_al);
+    float *d_map = (float *)(base + nvox_al + 2 * npad_al + 3 * ncell_al);
     MONTE_CUDA(cudaMemcpyAsync(d_raw, labels, nvox, cudaMemcpyHostToDevice, st));
     MONTE_CUDA(cudaMemsetAsync(d_lab, 0, 2 * npad_al, st));
     labels_pad_transpose_kernel MONTE_CFG(dim3(ceil_div(vol->nx, 32), ceil_div(vol->ny, 32), vol->nz), dim3(32, 8), 0, st)(
         d_raw, d_lab, d_lab_t, vol->nx, vol->ny);
     MONTE_CUDA(cudaGetLastError());
+    const uint8_t *d_rad = nullptr;
     if (macro) {
         macro_cell_kernel MONTE_CFG(ceil_div(mgx * mgy * mgz, 128), 128, 0, st)(d_lab, d_cell, vol->nx, vol->ny, vol->nz, macro, mgx, mgy, mgz);
         MONTE_CUDA(cudaGetLastError());
+        if (int rc = macro_radius(d_cell, d_cell + ncell_al, d_cell + 2 * ncell_al, mgx, mgy, mgz, st, &d_rad)) return rc;
     }
     ProjParams p;
     p.mcell = d_cell; p.mshift = macro; p.mgx = mgx; p.mgy = mgy;
+    p.mrad = d_rad; p.leap_unit = (float)((double)(1 << macro) * vol->pitch * 0.999);
     p.labels = d_lab; p.labels_t = d_lab_t; p.nx = vol->nx; p.ny = vol->ny; p.nz = vol->nz;
     p.pitch = (float)vol->pitch; p.inv_pitch = (float)(1.0 / vol->pitch);
     for (int a = 0; a < 3; a++) { p.org[a] = (float)vol->origin[a]; p.clip_lo[a] = (float)vol->clip_lo[a]; p.clip_hi[a] = (float)vol->clip_hi[a]; }
@@ -291,6 +358,7 @@ extern "C" int monte_gpu_project_primary(const monte_mc_geom *g, const monte_mc_
 struct monte_projector {
     monte_mc_volume vol;
     uint8_t *d_raw = nullptr, *d_lab = nullptr, *d_lab_t = nullptr, *d_cell = nullptr;
+    const uint8_t *d_rad = nullptr;
     int macro = 0, mgx = 0, mgy = 0, mgz = 0;
 };
 
@@ -324,7 +392,7 @@ extern "C" int monte_gpu_projector_create(const monte_mc_volume *vol, const uint
     }
     const size_t ncell_al = ((size_t)s->mgx * s->mgy * s->mgz + 255) / 256 * 256;
     cudaStream_t st = ctx().stream;
-    cudaError_t e = cudaMalloc(&s->d_raw, nvox_al + 2 * npad_al + ncell_al + 256);
+    cudaError_t e = cudaMalloc(&s->d_raw, nvox_al + 2 * npad_al + 3 * ncell_al + 256);
     if (e != cudaSuccess) { delete s; return cuda_fail(e, "cudaMalloc(projector)", __FILE__, __LINE__); }
     s->d_lab = s->d_raw + nvox_al; s->d_lab_t = s->d_lab + npad_al; s->d_cell = s->d_lab_t + npad_al;
     int rc = MONTE_OK;
@@ -337,6 +405,10 @@ extern "C" int monte_gpu_projector_create(const monte_mc_volume *vol, const uint
             macro_cell_kernel MONTE_CFG(ceil_div(s->mgx * s->mgy * s->mgz, 128), 128, 0, st)(s->d_lab, s->d_cell, vol->nx, vol->ny, vol->nz,
                                                                                        s->macro, s->mgx, s->mgy, s->mgz);
         if ((e = cudaGetLastError()) != cudaSuccess) break;
+        if (s->macro && macro_radius(s->d_cell, s->d_cell + ncell_al, s->d_cell + 2 * ncell_al, s->mgx, s->mgy, s->mgz, st, &s->d_rad)) {
+            e = cudaErrorInvalidValue;             // (the message of the failed launch is already set)
+            break;
+        }
         e = cudaStreamSynchronize(st);             // `labels` may be pageable; the scene is ready when this returns
     } while (0);
     if (e != cudaSuccess) { rc = cuda_fail(e, "projector_create", __FILE__, __LINE__); monte_gpu_projector_destroy(s); return rc; }
@@ -368,6 +440,7 @@ extern "C" int monte_gpu_project_primary_dev(const monte_projector *s, const mon
     p.angle0 = g->angle0_deg; p.angle_step = g->angle_step_deg;
     p.map = d_map;
     p.mcell = s->d_cell; p.mshift = s->macro; p.mgx = s->mgx; p.mgy = s->mgy;
+    p.mrad = s->d_rad; p.leap_unit = (float)((double)(1 << s->macro) * vol->pitch * 0.999);
     cudaStream_t st = (cudaStream_t)stream;
     // grid.z carries the views: at most 65535 per launch
     for (int v0 = view_begin; v0 < view_end; v0 += 32768) {
