@@ -215,6 +215,11 @@ typedef struct monte_mc_xs {
                                        steps are memoryless).  Pays when a dense insert sets the global majorant far
                                        above the bulk: polyenergetic spectra, calcium / bone in water               */
 
+#define MONTE_MC_TRACK_ADAPTIVE  3  /* CLEARANCE with a per-step test: the light majorant is used only where the clearance
+                                       D exceeds -ln(1 - mu_light/mu_max)/mu_light at the photon's energy, i.e. where
+                                       stopping at D is less likely than a virtual collision would be; elsewhere the
+                                       step is the reference's.  Never more tentative collisions than GLOBAL (oracle:
+                                       4.32 vs 4.47 per history at 140 keV, 4.93 vs 22.4 at 120 kVp)                */
 #define MONTE_MC_TRACK_AUTO      2  /* the library picks one of the two from the tables and the spectrum
                                        (monte_mc_resolve_tracking): CLEARANCE with 4-voxel cells if the global
                                        majorant is on average more than 3x the majorant of the lighter materials  */
@@ -225,7 +230,7 @@ typedef struct monte_mc_volume {
     double  origin[3];
     double  clip_lo[3], clip_hi[3];
     int32_t tracking_mode;        /* MONTE_MC_TRACK_*; 0 = the reference's single majorant                      */
-    int32_t clearance_cell_log2;  /* CLEARANCE: cells of 2^n voxels per side (0..8); 3 is a good start         */
+    int32_t clearance_cell_log2;  /* CLEARANCE / ADAPTIVE: cells of 2^n voxels per side (0..8); 2 or 3         */
 } monte_mc_volume;
 
 #define MONTE_MC_SOURCE_PENCIL 0  /* one pencil per pixel centre, `per` photons each

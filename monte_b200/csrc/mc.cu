@@ -67,6 +67,8 @@ struct McLaunch {
     const float *inv_mulo;        // [201] 1 / majorant of every material but the heavy one
     int cgx, cgy, cshift;         // grid dims and log2 of the cell side in voxels
     float cunit;                  // cm per grid unit (half a cell side)
+    const float *clear_thr;       // [201] clearance (cm) above which the light majorant is used: 0 (CLEARANCE) or the
+                                  // break-even distance -ln(1 - mu_light/mu_max)/mu_light (ADAPTIVE)
 };
 
 // stats word indices
@@ -149,8 +151,9 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
     constexpr int GSTRIDE = K * 32;                                    // uint4 per group per warp
     float *s_ray = s_cdf + ((sc.n_bins + 1 + 3) & ~3);                 // RAYLEIGH: [n_mat][2][ray_n], ray_n padded to 4
     const int ray_stride = RAYLEIGH ? ((P.ray_n + 3) & ~3) : 0;
-    float *s_invlo = s_ray + sc.n_mat * 2 * ray_stride;                // CLEAR: [201 (+3)]
-    uint4 *s_slots = reinterpret_cast<uint4 *>(s_invlo + (CLEAR ? TAB_ROWS + 3 : 0)) + (threadIdx.x >> 5) * (NG * GSTRIDE);
+    float *s_invlo = s_ray + sc.n_mat * 2 * ray_stride;                // CLEAR: [201 (+3)], then the thresholds [201 (+3)]
+    float *s_thr = s_invlo + TAB_ROWS + 3;
+    uint4 *s_slots = reinterpret_cast<uint4 *>(s_invlo + (CLEAR ? 2 * (TAB_ROWS + 3) : 0)) + (threadIdx.x >> 5) * (NG * GSTRIDE);
     for (int i = threadIdx.x; i < sc.n_mat * TAB_ROWS; i += MC_THREADS) s_tab[i] = sc.tab[i];
     for (int i = threadIdx.x; i < TAB_ROWS; i += MC_THREADS) s_inv[i] = sc.inv_mumax[i];
     for (int i = threadIdx.x; i <= sc.n_bins && sc.n_bins > 0; i += MC_THREADS) s_cdf[i] = sc.cdf[i];
@@ -158,7 +161,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
         for (int i = threadIdx.x; i < sc.n_mat * 2 * P.ray_n; i += MC_THREADS)
             s_ray[(i / P.ray_n) * ray_stride + i % P.ray_n] = P.ray[i];
     if (CLEAR)
-        for (int i = threadIdx.x; i < TAB_ROWS; i += MC_THREADS) s_invlo[i] = P.inv_mulo[i];
+        for (int i = threadIdx.x; i < TAB_ROWS; i += MC_THREADS) { s_invlo[i] = P.inv_mulo[i]; s_thr[i] = P.clear_thr[i]; }
     __syncthreads();
 
     const unsigned lane = threadIdx.x & 31u;
@@ -245,9 +248,9 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 lo2[q] = false; qn2[q] = 0u;
                 if (CLEAR) {
                     const uint32_t qc = (id2[q].y >> 17) & 0x7Fu;  // clearance of the cell the step starts in
-                    lo2[q] = qc != 0u;
-                    sp = -__logf(u01(r2[q].x)) * (lo2[q] ? s_invlo[id2[q].y & 0xFF] : s_inv[id2[q].y & 0xFF]);
                     const float dcl = (float)qc * P.cunit;
+                    lo2[q] = dcl > s_thr[id2[q].y & 0xFF];         // CLEARANCE: threshold 0, i.e. wherever there is clearance
+                    sp = -__logf(u01(r2[q].x)) * (lo2[q] ? s_invlo[id2[q].y & 0xFF] : s_inv[id2[q].y & 0xFF]);
                     cut = lo2[q] && sp > dcl;                      // would leave the cleared ball: stop at its surface, no collision
                     sp = cut ? dcl : sp;
                 } else sp = -__logf(u01(r2[q].x)) * s_inv[id2[q].y & 0xFF];
@@ -624,8 +627,10 @@ static int check_mc(const monte_mc_geom *g, const monte_mc_volume *vol, const mo
     MONTE_ARG(vol->nx > 0 && vol->ny > 0 && vol->nz > 0 && vol->pitch > 0, "mc: bad volume");
     MONTE_ARG((uint64_t)vol->nx * vol->ny * vol->nz < (1ull << 32), "mc: label volume has 2^32 voxels or more");
     MONTE_ARG(vol->tracking_mode == MONTE_MC_TRACK_GLOBAL || vol->tracking_mode == MONTE_MC_TRACK_CLEARANCE ||
-              vol->tracking_mode == MONTE_MC_TRACK_AUTO, "mc: unknown tracking_mode %d", vol->tracking_mode);
-    MONTE_ARG(vol->tracking_mode != MONTE_MC_TRACK_CLEARANCE || (vol->clearance_cell_log2 >= 0 && vol->clearance_cell_log2 <= 8),
+              vol->tracking_mode == MONTE_MC_TRACK_AUTO || vol->tracking_mode == MONTE_MC_TRACK_ADAPTIVE,
+              "mc: unknown tracking_mode %d", vol->tracking_mode);
+    MONTE_ARG((vol->tracking_mode != MONTE_MC_TRACK_CLEARANCE && vol->tracking_mode != MONTE_MC_TRACK_ADAPTIVE) ||
+              (vol->clearance_cell_log2 >= 0 && vol->clearance_cell_log2 <= 8),
               "mc: clearance_cell_log2 must be 0..8 (got %d)", vol->clearance_cell_log2);
     MONTE_ARG(xs->n_materials >= 1 && xs->n_materials <= MONTE_MC_MAX_MATERIALS, "mc: n_materials must be 1..%d", MONTE_MC_MAX_MATERIALS);
     MONTE_ARG(g->coherent_mode == MONTE_MC_COHERENT_FORWARD || g->coherent_mode == MONTE_MC_COHERENT_FORMFACTOR,
@@ -720,12 +725,13 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
     // per-keV tables: majorant over materials (CBCT_real325im.cu:867-868) and branching ratios (:651,656)
     const int nm = xs->n_materials;
     std::vector<float4> tab((size_t)nm * TAB_ROWS);
-    std::vector<float> inv(TAB_ROWS), invlo(TAB_ROWS, 0.f);
+    std::vector<float> inv(TAB_ROWS), invlo(2 * TAB_ROWS, 0.f);        // invlo: 1/mu_light, then the clearance thresholds
     // tracking_mode CLEARANCE needs a material to exclude; with a single material it is the reference's loop
     monte_mc_volume vres = *vol;                                   // AUTO resolved (same rule on every rank: inputs only)
     if (vol->tracking_mode == MONTE_MC_TRACK_AUTO)
         vres.tracking_mode = monte_mc_resolve_tracking(xs, spec, &vres.clearance_cell_log2, nullptr);
-    s->heavy = vres.tracking_mode == MONTE_MC_TRACK_CLEARANCE ? monte_xs_heavy_material(xs) : -1;
+    const bool adaptive = vres.tracking_mode == MONTE_MC_TRACK_ADAPTIVE;
+    s->heavy = vres.tracking_mode == MONTE_MC_TRACK_CLEARANCE || adaptive ? monte_xs_heavy_material(xs) : -1;
     for (int k = 0; k < TAB_ROWS; k++) {
         double mumax = 0, mulo = 0;
         for (int m = 0; m < nm; m++) {
@@ -734,6 +740,8 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
         }
         inv[k] = mumax > 0 ? (float)(1.0 / mumax) : 0.f;
         invlo[k] = mulo > 0 ? (float)(1.0 / mulo) : inv[k];
+        // ADAPTIVE: light majorant only where a cut at D is less likely than a virtual collision, exp(-mu_light D) < 1 - mu_light/mu_max
+        invlo[TAB_ROWS + k] = !adaptive ? 0.f : (mulo > 0 && mulo < mumax ? (float)(-log(1.0 - mulo / mumax) / mulo) : 1e30f);
         for (int m = 0; m < nm; m++) {
             const double mu = (double)xs->total[m][k];
             float4 t;
@@ -765,10 +773,10 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
     size_t clear_bytes = 0;
     s->vol = vres; s->n_mat_host = nm;
     if (s->heavy >= 0) {
-        if (!s->d_invlo) MONTE_CUDA(cudaMalloc(&s->d_invlo, TAB_ROWS * sizeof(float)));
-        MONTE_CUDA(cudaMemcpyAsync(s->d_invlo, invlo.data(), TAB_ROWS * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (!s->d_invlo) MONTE_CUDA(cudaMalloc(&s->d_invlo, 2 * TAB_ROWS * sizeof(float)));
+        MONTE_CUDA(cudaMemcpyAsync(s->d_invlo, invlo.data(), 2 * TAB_ROWS * sizeof(float), cudaMemcpyHostToDevice, st));
         if (int rc = upload_clearance(s, labels, st)) return rc;
-        clear_bytes = (size_t)s->cg[0] * s->cg[1] * s->cg[2] + TAB_ROWS * sizeof(float);
+        clear_bytes = (size_t)s->cg[0] * s->cg[1] * s->cg[2] + 2 * TAB_ROWS * sizeof(float);
         MONTE_CUDA(cudaStreamSynchronize(st));                         // `invlo` is pageable and goes out of scope
     }
     s->ray_n = 0;
@@ -854,6 +862,7 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     L.ray = (const float *)s->d_ray; L.ray_n = s->ray_n;
     L.clear = (const uint8_t *)s->d_clear; L.inv_mulo = (const float *)s->d_invlo;
     L.cgx = s->cg[0]; L.cgy = s->cg[1]; L.cshift = s->cshift; L.cunit = s->cunit;
+    L.clear_thr = L.inv_mulo ? L.inv_mulo + TAB_ROWS : nullptr;
     { static int sm = -1; if (sm < 0) { const char *e = getenv("MONTE_MC_SECOND"); sm = e ? atoi(e) : 16; } L.second_min = (uint32_t)sm; }
     if (L.total == 0) return MONTE_OK;
     MONTE_CUDA(cudaMemsetAsync(s->d_work, 0, sizeof(unsigned long long), st));
@@ -873,7 +882,7 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     const size_t smem = (size_t)s->dev.n_mat * TAB_ROWS * sizeof(float4) +
                         (TAB_ROWS + 3 + ((s->dev.n_bins + 1 + 3) & ~3)) * sizeof(float) + slot_bytes +
                         (rayleigh ? (size_t)s->dev.n_mat * 2 * ((s->ray_n + 3) & ~3) * sizeof(float) : 0) +
-                        (clear ? (TAB_ROWS + 3) * sizeof(float) : 0);
+                        (clear ? 2 * (TAB_ROWS + 3) * sizeof(float) : 0);
     const void *fn = nullptr;
     switch (rayleigh || clear ? 200 + rec + (clear ? 2 : 0) + (rayleigh && clear ? 2 : 0) : which * 2 + rec) {
         case 200: fn = (const void *)mc_transport_kernel_v3<false, 5, 3, 2, true>; break;

@@ -258,7 +258,7 @@ static int delta_sampling(const scene_t *S, rng_t *R, photon_t *p, double E, dou
     const int q = S->o->quirks;
     const monte_mc_volume *v = S->vol;
     int collided = 0;
-    const int clearance = v->tracking_mode == MONTE_MC_TRACK_CLEARANCE && S->o->clear_grid && !q;
+    const int clearance = (v->tracking_mode == MONTE_MC_TRACK_CLEARANCE || v->tracking_mode == MONTE_MC_TRACK_ADAPTIVE) && S->o->clear_grid && !q;
     const double mu_lo = clearance ? mu_lo_at(S, k) : 0;
     for (;;) {
         double beta, nu;
@@ -271,7 +271,10 @@ static int delta_sampling(const scene_t *S, rng_t *R, photon_t *p, double E, dou
             const double nud = p->at_entry ? 1e-3 * v->pitch : 0.0;
             p->at_entry = 0;
             const double D = clearance_at(S, x + nud * sin_theta_a * cos_phi_a, y + nud * sin_theta_a * sin_phi_a, z + nud * cos_theta_a);
-            if (D > 0) {
+            /* ADAPTIVE: only where stopping at D is less likely than a virtual collision would be */
+            double thr = 0;
+            if (v->tracking_mode == MONTE_MC_TRACK_ADAPTIVE) thr = mu_lo < mu_max ? (double)(float)(-log(1.0 - mu_lo / mu_max) / mu_lo) : 1e30;
+            if (D > thr) {
                 double r = -log(beta) / mu_lo;
                 const int cut = r > D;
                 if (cut) r = D;

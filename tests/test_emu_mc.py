@@ -233,3 +233,12 @@ np.savez(sys.argv[2], im0=im0, im5=im5, f=f, v=v, zy=zy, fw=fw, pm=pm, steps=st[
 
 def test_emu_resident_projector_feeds_fdk_like_the_host_path(monte_emu, oracle):
     CL.test_resident_projector_feeds_fdk_like_the_host_path(monte_emu, oracle)
+
+
+@pytest.mark.parametrize("cell_log2,poly", [(0, True), (1, False)])
+def test_emu_adaptive_history_coupled_fates_match_oracle(monte_emu, oracle, cell_log2, poly):
+    CL.test_adaptive_history_coupled_fates_match_oracle(monte_emu, oracle, cell_log2, poly)
+
+
+def test_emu_adaptive_never_needs_more_steps_than_the_reference_loop(monte_emu):
+    CL.test_adaptive_never_needs_more_steps_than_the_reference_loop(monte_emu)

@@ -22,9 +22,9 @@ def _oracle_opts(monte, oracle, vol, lab, xs, seed, rng=None):
 
 
 @pytest.mark.parametrize("cell_log2,poly,rayleigh", [(0, True, False), (1, True, False), (2, False, False), (1, True, True)])
-def test_clearance_history_coupled_fates_match_oracle(monte, oracle, cell_log2, poly, rayleigh):
+def test_clearance_history_coupled_fates_match_oracle(monte, oracle, cell_log2, poly, rayleigh, mode=_abi.TRACK_CLEARANCE):
     g, vol, lab = G.scene(n=41, pitch=0.5, det=17, views=3, mode=_abi.SOURCE_CONE)
-    vol.tracking_mode, vol.clearance_cell_log2 = _abi.TRACK_CLEARANCE, cell_log2
+    vol.tracking_mode, vol.clearance_cell_log2 = mode, cell_log2
     xs = scenes.make_xs()
     if rayleigh:
         g.coherent_mode = _abi.COHERENT_FORMFACTOR
@@ -43,6 +43,26 @@ def test_clearance_history_coupled_fates_match_oracle(monte, oracle, cell_log2, 
     assert np.allclose(e_gpu[same], e_cpu[same], rtol=2e-5)
     for k in (1, 2, 3, 4):
         assert ((f_cpu & 0xFF) == k).any(), k
+
+
+@pytest.mark.parametrize("cell_log2,poly", [(0, True), (1, False)])
+def test_adaptive_history_coupled_fates_match_oracle(monte, oracle, cell_log2, poly):
+    """tracking_mode ADAPTIVE: the light majorant only where the clearance exceeds the break-even distance"""
+    test_clearance_history_coupled_fates_match_oracle(monte, oracle, cell_log2, poly, False, mode=_abi.TRACK_ADAPTIVE)
+
+
+def test_adaptive_never_needs_more_steps_than_the_reference_loop(monte):
+    g, vol, lab = G.scene(n=41, pitch=0.5, det=17, views=2)
+    xs = scenes.make_xs()
+    kr, keep = scenes.kramers_spectrum()
+    for spec in (scenes.mono_spectrum(140.0), scenes.mono_spectrum(60.0), kr):
+        steps = {}
+        for mode in (_abi.TRACK_GLOBAL, _abi.TRACK_CLEARANCE, _abi.TRACK_ADAPTIVE):
+            vol.tracking_mode, vol.clearance_cell_log2 = mode, 0
+            _, _, st = monte.simulate(g, vol, lab, xs, spec, 300, 17)
+            steps[mode] = st["woodcock_steps"] / st["histories"]
+        assert steps[_abi.TRACK_ADAPTIVE] <= 1.03 * steps[_abi.TRACK_GLOBAL], steps
+        assert steps[_abi.TRACK_ADAPTIVE] <= 1.03 * steps[_abi.TRACK_CLEARANCE], steps
 
 
 def test_clearance_counters_and_fewer_steps_than_the_reference_loop(monte, oracle):
