@@ -242,3 +242,44 @@ def test_emu_adaptive_history_coupled_fates_match_oracle(monte_emu, oracle, cell
 
 def test_emu_adaptive_never_needs_more_steps_than_the_reference_loop(monte_emu):
     CL.test_adaptive_never_needs_more_steps_than_the_reference_loop(monte_emu)
+
+
+def test_emu_cbct_mc_driver_end_to_end(monte_emu, tmp_path):
+    """the C++ driver main() of monte_b200/host/cbct_mc.cpp linked against the emulated library: argument parsing,
+    CSV tables with BOM/CRLF, raw label input, the reference's four output files -- with and without the optional
+    transport modes; the count images equal the same run through the Python binding"""
+    import os
+    import subprocess
+    import test_drivers as D
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    emu_dir = os.path.join(root, "tests", "emu", "_build")
+    exe = os.path.join(str(tmp_path), "cbct_mc_emu")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "monte_b200", "host", "cbct_mc.cpp"), "-o", exe,
+                           "-L" + emu_dir, "-lmonte_gpu_emu", "-Wl,-rpath," + emu_dir])
+    d = str(tmp_path)
+    h2o, ca = scenes.load_tables()
+    D._write_csv(os.path.join(d, "xcom2.csv"), h2o)
+    D._write_csv(os.path.join(d, "Ca.csv"), ca)
+    lab = scenes.cylinder_phantom(33, 1.0)
+    lab.tofile(os.path.join(d, "cyl.raw"))
+    for tag, extra in (("a", []), ("b", ["1", "1"])):                 # b: rayleigh = 1, clearance cells of 2 voxels
+        out = subprocess.run([exe, "cyl.raw", "33", "1.0", "xcom2.csv", "Ca.csv", "9", str(32.5 / 9), "2", "40", "3", tag] + extra,
+                             cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout.decode()
+        assert "histories" in out
+        p0 = np.fromfile(os.path.join(d, "proj_%s0.raw" % tag), np.int32).reshape(2, 9, 9)
+        p5 = np.fromfile(os.path.join(d, "proj_%s5.raw" % tag), np.int32).reshape(2, 9, 9)
+        m0 = np.fromfile(os.path.join(d, "map_%s0.raw" % tag), np.float32).reshape(2, 9, 9)
+        assert (p5 >= p0).all() and p0.max() <= 40
+        assert np.abs(m0 - (-np.log(np.clip(p0, 1, 40).astype(np.float64)) + np.log(40.0))).max() < 1e-5
+        # the same run through the Python binding (the driver's geometry: 180 degrees apart, untight clip box, BOM-quirk tables)
+        g = scenes.mc_geom(9, 32.5 / 9, n_views=2)
+        g.angle_step_deg = 180.0
+        vol = scenes.volume_for(lab, 1.0, tight=False)
+        xs = scenes.make_xs(quirk_bom=True)
+        if extra:
+            g.coherent_mode = _abi.COHERENT_FORMFACTOR
+            scenes.add_formfactors(xs)
+            vol.tracking_mode, vol.clearance_cell_log2 = _abi.TRACK_CLEARANCE, 1
+        r0, r5, _ = monte_emu.simulate(g, vol, lab, xs, scenes.mono_spectrum(140.0), 40, 3)
+        assert np.array_equal(r0, p0) and np.array_equal(r5, p5), tag
