@@ -215,3 +215,29 @@ def test_emu_address_sanitizer_clean():
     out = r.stdout + r.stderr
     assert "ERROR: AddressSanitizer" not in out, out[-4000:]
     assert r.returncode == 0 and "ASAN RUN COMPLETE" in out, out[-4000:]
+
+
+def test_emu_cbct_fdk_driver_fbp2_end_to_end(monte_emu, tmp_path):
+    """the recon main() replacement (monte_b200/host/cbct_fdk.cpp) linked against the emulated library, in its fbp2
+    role: reads the reference's input file, writes its output files; against the golden of the unmodified
+    recon/fbp2.cpp binary"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    emu_dir = os.path.join(root, "tests", "emu", "_build")
+    exe = os.path.join(str(tmp_path), "cbct_fdk_emu")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "monte_b200", "host", "cbct_fdk.cpp"), "-o", exe,
+                           "-L" + emu_dir, "-lmonte_gpu_emu", "-Wl,-rpath," + emu_dir])
+    gold = np.load(os.path.join(G.GOLDEN, "fdk_fbp2.npz"))
+    d = str(tmp_path)
+    rand(int(gold["seed"]), (360, 65)).tofile(os.path.join(d, "map5_20_2e5.raw"))          # fbp2.cpp:27
+    out = subprocess.run([exe, "fbp2", "map5_20_2e5.raw", "t"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                         check=True).stdout.decode()
+    assert "filtered" in out
+    img = np.fromfile(os.path.join(d, "xy_t.raw"), np.float32).reshape(256, 256)
+    f = np.fromfile(os.path.join(d, "map_t.raw"), np.float32).reshape(360, 65)
+    assert_close(f[::8], gold["filtered"], "fbp2 filtered")
+    assert_close(img[::2, ::2], gold["image_sub"], "fbp2 image")
+    # a missing input file is reported, not fatal in any other way
+    r = subprocess.run([exe, "fbp2", "nope.raw"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 1 and "failed to read" in r.stderr
