@@ -165,3 +165,30 @@ def test_emu_fuzz_projector_macro_cells(macro, oracle):
                         "-k", "fuzz_projector_against_oracle or emu_project_primary"],
                        env=dict(os.environ, MONTE_PROJ_MACRO=macro), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and " passed" in r.stdout, (r.stdout[-3000:], r.stderr[-2000:])
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_emu_fuzz_fbp2_against_oracle(monte_emu, oracle, seed):
+    """2-D fan-beam FBP (recon/fbp2.cpp: truncated detector index, views from view_first) for random sinogram widths,
+    image sizes, ROIs and first views"""
+    rng = np.random.default_rng(4000 + seed)
+    g = _abi.fbp2_geom()
+    g.nu = int(rng.integers(5, 120))
+    g.n_views = int(rng.integers(3, 90))
+    g.du = 32.5 / g.nu
+    g.half_u = 0.5 * g.nu * g.du
+    g.angle_step_deg = float(rng.choice([1.0, 360.0 / g.n_views]))
+    g.nx, g.ny = int(rng.integers(4, 70)), int(rng.integers(4, 70))
+    g.vox = float(rng.uniform(0.15, 0.6))
+    g.x0, g.y0 = -0.5 * g.nx * g.vox, 0.5 * g.ny * g.vox
+    g.s_begin, g.s_end, g.t_begin, g.t_end = 0, g.nx, 0, g.ny
+    if rng.integers(0, 2):
+        a, b = sorted(rng.integers(0, g.nx + 1, 2)); g.s_begin, g.s_end = int(a), int(b)
+        a, b = sorted(rng.integers(0, g.ny + 1, 2)); g.t_begin, g.t_end = int(a), int(b)
+    view_first = int(rng.integers(0, min(3, g.n_views)))
+    sino = rng.random((g.n_views, g.nu), dtype=np.float32) - 0.2
+    f_o, img_o = oracle.fbp2(g, sino, view_first=view_first)
+    f, img, _ = monte_emu.fbp2(g, sino, view_first=view_first)
+    for got, ref, what in ((f, f_o, "filtered"), (img, img_o, "image")):
+        scale = float(np.abs(ref).max())
+        assert float(np.abs(got.astype(np.float64) - ref).max()) <= REL * scale + 1e-30, (what, seed)
