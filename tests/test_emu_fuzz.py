@@ -192,3 +192,46 @@ def test_emu_fuzz_fbp2_against_oracle(monte_emu, oracle, seed):
     for got, ref, what in ((f, f_o, "filtered"), (img, img_o, "image")):
         scale = float(np.abs(ref).max())
         assert float(np.abs(got.astype(np.float64) - ref).max()) <= REL * scale + 1e-30, (what, seed)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_emu_fuzz_partition_invariants(monte_emu, seed):
+    """the invariants the multi-GPU plumbing relies on, for random geometries and random cuts: z-slabs, view pieces
+    (continuing the stored partial sums) and view-range filtering reproduce the single launch bit for bit; rows
+    outside monte_gpu_fdk_slab_rows (set to NaN) are never read by a slab"""
+    m = monte_emu
+    rng = np.random.default_rng(5000 + seed)
+    g = _fdk_case(rng)
+    g.full_roi()
+    g.mask_r2 = -1
+    proj = rng.random((g.n_views, g.nu, g.nv), dtype=np.float32)
+    filt = np.full(m.fdk_filtered_shape(g), np.nan, np.float32)
+    m.fdk_filter_dev(g, m.Dev(proj), m.Dev(filt))
+    whole = np.full((g.nz, g.ny, g.nx), np.nan, np.float32)
+    m.fdk_backproject_dev(g, m.Dev(filt), m.Dev(whole))
+    assert not np.isnan(whole).any()
+    # filter by view ranges
+    cuts = sorted(set([0, g.n_views] + [int(x) for x in rng.integers(0, g.n_views + 1, 2)]))
+    filt2 = np.full_like(filt, np.nan)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        m.fdk_filter_dev(g, m.Dev(proj), m.Dev(filt2), a, b, pad=False)
+    m.fdk_pad_dev(g, m.Dev(filt2))
+    assert np.array_equal(filt, filt2)
+    # z-slabs (+ the rows each slab may read)
+    zc = sorted(set([0, g.nz] + [int(x) for x in rng.integers(0, g.nz + 1, 3)]))
+    for a, b in zip(zc[:-1], zc[1:]):
+        r0, r1 = m.fdk_slab_rows(g, a, b)
+        holed = filt.copy()
+        rows = holed[: g.n_views * g.nv].reshape(g.n_views, g.nv, -1)
+        keep = np.zeros(g.nv, bool)
+        keep[r0:r1] = True
+        keep[:4] = True
+        rows[:, ~keep, :] = np.nan
+        slab = np.full((b - a, g.ny, g.nx), np.nan, np.float32)
+        m.fdk_backproject_dev(g, m.Dev(holed), m.Dev(slab), a, b)
+        assert np.array_equal(slab, whole[a:b]), (a, b, r0, r1)
+    # view pieces in ascending order continue the partial sums exactly
+    piece = np.full_like(whole, np.nan)
+    for i, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+        m.fdk_backproject_views_dev(g, m.Dev(filt), m.Dev(piece), 0, g.nz, a, b, i > 0)
+    assert np.array_equal(piece, whole)
