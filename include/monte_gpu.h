@@ -203,7 +203,10 @@ typedef struct monte_mc_xs {
  * addressing forms map onto it: CBCT_real325im.cu:921 int((p+10)*10) -> origin -10;
  * CBCT_real2.cpp:771 rint(p*10)+90 -> origin -(90+0.5)*0.1.
  * Lookups happen only inside the clip box (CBCT_real2.cpp:770; the tight box around
- * the phantom); outside it the photon flies straight (air).                          */
+ * the phantom); outside it the photon flies straight (air).  A position exactly on a voxel
+ * face may be assigned to either neighbour (the kernel rounds to even, the CPU restatement
+ * floors): a null set, except for pencil rays that run along a face of an even-sized volume
+ * centred on the axis -- use odd sizes, as the reference's 325^3 / 185x185x325 volumes are.  */
 /* tracking_mode: how tentative collisions are sampled.  Both are exact (same physics, same expected tallies);
  * they consume different variates, so a run is reproducible bit for bit only within one mode.               */
 #define MONTE_MC_TRACK_GLOBAL    0  /* the reference's Woodcock loop: one majorant, the maximum over all materials
