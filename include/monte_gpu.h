@@ -223,6 +223,10 @@ typedef struct monte_mc_xs {
                                        stopping at D is less likely than a virtual collision would be; elsewhere the
                                        step is the reference's.  Never more tentative collisions than GLOBAL (oracle:
                                        4.32 vs 4.47 per history at 140 keV, 4.93 vs 22.4 at 120 kVp)                */
+#define MONTE_MC_TRACK_DIRECTIONAL 4 /* ADAPTIVE with one clearance per octant of the flight direction
+                                       (monte_mc_clearance_grid_octants): only the heavy material a ray with that direction
+                                       can still reach counts, so a photon flying away from the insert is never cut short.
+                                       Oracle, steps per history: 3.6 at 140 keV (reference loop 4.5), 3.6 at 120 kVp (22.4) */
 #define MONTE_MC_TRACK_AUTO      2  /* the library picks one of the two from the tables and the spectrum
                                        (monte_mc_resolve_tracking): CLEARANCE with 4-voxel cells if the global
                                        majorant is on average more than 3x the majorant of the lighter materials  */
@@ -393,6 +397,10 @@ int monte_xs_formfactor_hydrogenic(monte_mc_xs *xs, int material, double x0);
 int monte_mc_clearance_dims(const monte_mc_volume *vol, int cell_log2, int32_t dims[3]);
 int monte_mc_clearance_grid(const monte_mc_volume *vol, const uint8_t *labels, int n_materials, int heavy_material,
                             int cell_log2, uint8_t *grid);
+/* eight grids [octant][cz][cy][cx], octant = (dx > 0) | (dy > 0) << 1 | (dz > 0) << 2 of the flight direction: the same
+ * bound restricted to the cells a ray with that direction can still reach (MONTE_MC_TRACK_DIRECTIONAL)            */
+int monte_mc_clearance_grid_octants(const monte_mc_volume *vol, const uint8_t *labels, int n_materials,
+                                    int heavy_material, int cell_log2, uint8_t *grid8);
 /* the material the clearance grid is built for: argmax of total*density at 60 keV; -1 with fewer than 2 materials */
 int monte_xs_heavy_material(const monte_mc_xs *xs);
 /* What MONTE_MC_TRACK_AUTO resolves to (host only, deterministic in its inputs, so every rank of a sharded run

@@ -19,7 +19,7 @@ FDK_REFERENCE, FDK_TEXTBOOK = 0, 1
 COORD_SCALE_AFTER, COORD_SCALE_BEFORE = 0, 1
 SOURCE_PENCIL, SOURCE_CONE = 0, 1
 COHERENT_FORWARD, COHERENT_FORMFACTOR = 0, 1
-TRACK_GLOBAL, TRACK_CLEARANCE, TRACK_AUTO, TRACK_ADAPTIVE = 0, 1, 2, 3
+TRACK_GLOBAL, TRACK_CLEARANCE, TRACK_AUTO, TRACK_ADAPTIVE, TRACK_DIRECTIONAL = 0, 1, 2, 3, 4
 
 
 class FdkGeom(C.Structure):

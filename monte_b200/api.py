@@ -88,6 +88,7 @@ def _bind(path):
         "monte_mc_clearance_dims": (C.c_int, [C.POINTER(McVolume), C.c_int, C.POINTER(C.c_int32)]),
         "monte_mc_clearance_grid": (C.c_int, [C.POINTER(McVolume), vp, C.c_int, C.c_int, C.c_int, vp]),
         "monte_xs_heavy_material": (C.c_int, [C.POINTER(McXs)]),
+        "monte_mc_clearance_grid_octants": (C.c_int, [C.POINTER(McVolume), vp, C.c_int, C.c_int, C.c_int, vp]),
         "monte_mc_resolve_tracking": (C.c_int, [C.POINTER(McXs), C.POINTER(McSpectrum), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
         "monte_gpu_fdk_slab_rows": (C.c_int, [C.POINTER(FdkGeom), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     }
@@ -310,6 +311,11 @@ def clearance_grid(vol, labels, xs, cell_log2=None):
     dims = (C.c_int32 * 3)()
     _check(lib.monte_mc_clearance_dims(C.byref(vol), cl, dims))
     heavy = lib.monte_xs_heavy_material(C.byref(xs))
+    if vol.tracking_mode == _abi.TRACK_DIRECTIONAL:          # eight grids, one per octant of the flight direction
+        grid = np.full((8, dims[2], dims[1], dims[0]), 127, np.uint8)
+        if heavy >= 0:
+            _check(lib.monte_mc_clearance_grid_octants(C.byref(vol), _ptr(labels), xs.n_materials, heavy, cl, _ptr(grid)))
+        return grid, heavy
     grid = np.full((dims[2], dims[1], dims[0]), 127, np.uint8)
     if heavy >= 0:
         _check(lib.monte_mc_clearance_grid(C.byref(vol), _ptr(labels), xs.n_materials, heavy, cl, _ptr(grid)))

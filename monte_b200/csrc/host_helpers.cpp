@@ -2,6 +2,8 @@
 // phantom generators, CT-number conversion, geometry presets.  Linked into libmonte_gpu and used
 // by the C++ drivers under monte_b200/host/.
 #include <vector>
+#include <thread>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -195,18 +197,11 @@ int monte_mc_clearance_dims(const monte_mc_volume *vol, int cell_log2, int32_t d
     return MONTE_OK;
 }
 
-int monte_mc_clearance_grid(const monte_mc_volume *vol, const uint8_t *labels, int n_materials, int heavy_material,
-                            int cell_log2, uint8_t *grid) {
-    int32_t d[3];
-    if (int rc = monte_mc_clearance_dims(vol, cell_log2, d)) return rc;
-    if (!labels || !grid || n_materials < 1 || heavy_material < 0 || heavy_material >= n_materials) {
-        monte::set_error("monte_mc_clearance_grid: bad argument");
-        return MONTE_E_ARG;
-    }
-    const int gx = d[0], gy = d[1], gz = d[2];
-    const size_t ncell = (size_t)gx * gy * gz;
+// cells that hold the heavy material: 0, others INF
+static void clearance_seed(const monte_mc_volume *vol, const uint8_t *labels, int n_materials, int heavy_material, int cell_log2,
+                           int gx, int gy, std::vector<float> &f) {
     const float INF = 1e30f;
-    std::vector<float> f(ncell, INF), t(ncell);
+    std::fill(f.begin(), f.end(), INF);
     for (int z = 0; z < vol->nz; z++)
         for (int y = 0; y < vol->ny; y++) {
             const uint8_t *row = labels + ((size_t)z * vol->ny + y) * vol->nx;
@@ -218,7 +213,14 @@ int monte_mc_clearance_grid(const monte_mc_volume *vol, const uint8_t *labels, i
                 if (l - 1 == heavy_material) frow[x >> cell_log2] = 0.f;
             }
         }
-    // f <- min over the other cells of the line of f + max(0, |i - j| - 1)^2, one axis after the other
+}
+
+// f <- min over the cells j of the line of f[j] + max(0, |i - j| - 1)^2, one axis after the other; sign[a] = 0: every j,
+// +1: only j >= i, -1: only j <= i (the cells a ray travelling in that direction along the axis can still reach)
+static void clearance_transform(std::vector<float> &f, int gx, int gy, int gz, const int sign[3], uint8_t *grid) {
+    const float INF = 1e30f;
+    const size_t ncell = (size_t)gx * gy * gz;
+    std::vector<float> t(ncell);
     const int dims[3] = {gx, gy, gz};
     const size_t stride[3] = {1, (size_t)gx, (size_t)gx * gy};
     for (int a = 0; a < 3; a++) {
@@ -232,8 +234,8 @@ int monte_mc_clearance_grid(const monte_mc_volume *vol, const uint8_t *labels, i
                     for (int k = 1; k < n; k++) {                      // outwards from i; farther cells cannot beat `best`
                         const float gap2 = (float)(k - 1) * (float)(k - 1);
                         if (gap2 >= best) break;
-                        if (i - k >= 0) { const float w = f[base + (i - k) * stride[a]] + gap2; if (w < best) best = w; }
-                        if (i + k < n) { const float w = f[base + (i + k) * stride[a]] + gap2; if (w < best) best = w; }
+                        if (sign[a] <= 0 && i - k >= 0) { const float w = f[base + (i - k) * stride[a]] + gap2; if (w < best) best = w; }
+                        if (sign[a] >= 0 && i + k < n) { const float w = f[base + (i + k) * stride[a]] + gap2; if (w < best) best = w; }
                     }
                     t[base + i * stride[a]] = best;
                 }
@@ -244,6 +246,46 @@ int monte_mc_clearance_grid(const monte_mc_volume *vol, const uint8_t *labels, i
         const double q = f[i] >= INF ? 127.0 : floor(2.0 * sqrt((double)f[i]));
         grid[i] = (uint8_t)(q > 127.0 ? 127.0 : q);
     }
+}
+
+int monte_mc_clearance_grid(const monte_mc_volume *vol, const uint8_t *labels, int n_materials, int heavy_material,
+                            int cell_log2, uint8_t *grid) {
+    int32_t d[3];
+    if (int rc = monte_mc_clearance_dims(vol, cell_log2, d)) return rc;
+    if (!labels || !grid || n_materials < 1 || heavy_material < 0 || heavy_material >= n_materials) {
+        monte::set_error("monte_mc_clearance_grid: bad argument");
+        return MONTE_E_ARG;
+    }
+    std::vector<float> f((size_t)d[0] * d[1] * d[2]);
+    clearance_seed(vol, labels, n_materials, heavy_material, cell_log2, d[0], d[1], f);
+    const int sign[3] = {0, 0, 0};
+    clearance_transform(f, d[0], d[1], d[2], sign, grid);
+    return MONTE_OK;
+}
+
+/* Directional form (MONTE_MC_TRACK_DIRECTIONAL): eight grids, one per octant of the flight direction, index
+ * o = (dx > 0) | (dy > 0) << 1 | (dz > 0) << 2, laid out [o][cz][cy][cx].  grid[o][cell] bounds the distance to the
+ * heavy material in the cells a ray with that direction can still reach (componentwise at or beyond the cell), so a
+ * photon flying away from the dense insert has an unbounded clearance.  Octants are transformed concurrently.     */
+int monte_mc_clearance_grid_octants(const monte_mc_volume *vol, const uint8_t *labels, int n_materials, int heavy_material,
+                                    int cell_log2, uint8_t *grid8) {
+    int32_t d[3];
+    if (int rc = monte_mc_clearance_dims(vol, cell_log2, d)) return rc;
+    if (!labels || !grid8 || n_materials < 1 || heavy_material < 0 || heavy_material >= n_materials) {
+        monte::set_error("monte_mc_clearance_grid_octants: bad argument");
+        return MONTE_E_ARG;
+    }
+    const size_t ncell = (size_t)d[0] * d[1] * d[2];
+    std::vector<float> seed(ncell);
+    clearance_seed(vol, labels, n_materials, heavy_material, cell_log2, d[0], d[1], seed);
+    std::vector<std::thread> th;
+    for (int o = 0; o < 8; o++)
+        th.emplace_back([&, o] {
+            std::vector<float> f(seed);
+            const int sign[3] = {(o & 1) ? 1 : -1, (o & 2) ? 1 : -1, (o & 4) ? 1 : -1};
+            clearance_transform(f, d[0], d[1], d[2], sign, grid8 + (size_t)o * ncell);
+        });
+    for (auto &t : th) t.join();
     return MONTE_OK;
 }
 

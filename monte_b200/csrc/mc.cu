@@ -69,6 +69,7 @@ struct McLaunch {
     float cunit;                  // cm per grid unit (half a cell side)
     const float *clear_thr;       // [201] clearance (cm) above which the light majorant is used: 0 (CLEARANCE) or the
                                   // break-even distance -ln(1 - mu_light/mu_max)/mu_light (ADAPTIVE)
+    unsigned coct;                // DIRECTIONAL: cells per grid (eight grids, one per direction octant); 0: one grid
 };
 
 // stats word indices
@@ -263,8 +264,10 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 ix = (int)min((unsigned)ix, (unsigned)(sc.nx - 1)); iy = (int)min((unsigned)iy, (unsigned)(sc.ny - 1));
                 iz = (int)min((unsigned)iz, (unsigned)(sc.nz - 1));     // safety only: the clip box lies inside the volume
                 lab2[q] = (en2[q] && inside2[q] && !cut) ? __ldg(sc.labels + ((unsigned)(iz * sc.ny + iy) * (unsigned)sc.nx + (unsigned)ix)) : 0;
-                if (CLEAR && en2[q] && inside2[q])
-                    qn2[q] = __ldg(P.clear + ((unsigned)((iz >> P.cshift) * P.cgy + (iy >> P.cshift)) * (unsigned)P.cgx + (unsigned)(ix >> P.cshift)));
+                if (CLEAR && en2[q] && inside2[q]) {
+                    const unsigned oc = (dir.x > 0.f ? 1u : 0u) | (dir.y > 0.f ? 2u : 0u) | (dir.z > 0.f ? 4u : 0u);   // coct == 0: one grid
+                    qn2[q] = __ldg(P.clear + oc * P.coct + ((unsigned)((iz >> P.cshift) * P.cgy + (iy >> P.cshift)) * (unsigned)P.cgx + (unsigned)(ix >> P.cshift)));
+                }
             }
 #pragma unroll
             for (int q = 0; q < NS; q++) {
@@ -414,6 +417,16 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             const float nn = rsqrtf(nxd * nxd + nyd * nyd + nzd * nzd);
             dir.x = nxd * nn; dir.y = nyd * nn; dir.z = nzd * nn;
             *reinterpret_cast<float4 *>(&GRP(G_DIR)) = dir;
+            if (CLEAR && P.coct) {                                    // DIRECTIONAL: the clearance depends on the new direction
+                const float4 pc = *reinterpret_cast<float4 *>(&GRP(G_POS));
+                int ix = __float_as_int(fmaf(pc.x, sc.inv_pitch, vox_off[0]) + 12582912.0f) - 0x4B400000;
+                int iy = __float_as_int(fmaf(pc.y, sc.inv_pitch, vox_off[1]) + 12582912.0f) - 0x4B400000;
+                int iz = __float_as_int(fmaf(pc.z, sc.inv_pitch, vox_off[2]) + 12582912.0f) - 0x4B400000;
+                ix = min(max(ix, 0), sc.nx - 1); iy = min(max(iy, 0), sc.ny - 1); iz = min(max(iz, 0), sc.nz - 1);
+                const unsigned oc = (dir.x > 0.f ? 1u : 0u) | (dir.y > 0.f ? 2u : 0u) | (dir.z > 0.f ? 4u : 0u);
+                const uint32_t qd = __ldg(P.clear + oc * P.coct + ((unsigned)((iz >> P.cshift) * P.cgy + (iy >> P.cshift)) * (unsigned)P.cgx + (unsigned)(ix >> P.cshift)));
+                WORD(G_ID, 1) = (id.y & ~0xFE0000u) | (qd << 17);
+            }
             st = (st & clr) | (P_STEP << (4 * j));
             continue;
         }
@@ -546,7 +559,8 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                     int iy = __float_as_int(fmaf(ey, sc.inv_pitch, vox_off[1]) + 1e-3f * dy + 12582912.0f) - 0x4B400000;
                     int iz = __float_as_int(fmaf(ez, sc.inv_pitch, vox_off[2]) + 1e-3f * dz + 12582912.0f) - 0x4B400000;
                     ix = min(max(ix, 0), sc.nx - 1); iy = min(max(iy, 0), sc.ny - 1); iz = min(max(iz, 0), sc.nz - 1);
-                    qe = __ldg(P.clear + ((unsigned)((iz >> P.cshift) * P.cgy + (iy >> P.cshift)) * (unsigned)P.cgx + (unsigned)(ix >> P.cshift)));
+                    const unsigned oc = (dx > 0.f ? 1u : 0u) | (dy > 0.f ? 2u : 0u) | (dz > 0.f ? 4u : 0u);
+                    qe = __ldg(P.clear + oc * P.coct + ((unsigned)((iz >> P.cshift) * P.cgy + (iy >> P.cshift)) * (unsigned)P.cgx + (unsigned)(ix >> P.cshift)));
                 }
                 *reinterpret_cast<float4 *>(&GRP(G_POS)) = make_float4(ex, ey, ez, E);
                 *reinterpret_cast<float4 *>(&GRP(G_DIR)) = make_float4(dx, dy, dz, 0.f);
@@ -606,6 +620,7 @@ struct monte_mc_scene {
     void *d_clear = nullptr, *d_invlo = nullptr;
     size_t cap_clear = 0;
     int heavy = -1, cshift = 0, cg[3] = {0, 0, 0};
+    unsigned coct = 0;                                                 // DIRECTIONAL: cells per octant grid
     float cunit = 0.f;
     monte_mc_volume vol;                                               // kept for scene_update_labels
     int n_mat_host = 0;
@@ -626,10 +641,10 @@ static int check_mc(const monte_mc_geom *g, const monte_mc_volume *vol, const mo
               "mc: unknown detector_mode %d", g->detector_mode);
     MONTE_ARG(vol->nx > 0 && vol->ny > 0 && vol->nz > 0 && vol->pitch > 0, "mc: bad volume");
     MONTE_ARG((uint64_t)vol->nx * vol->ny * vol->nz < (1ull << 32), "mc: label volume has 2^32 voxels or more");
-    MONTE_ARG(vol->tracking_mode == MONTE_MC_TRACK_GLOBAL || vol->tracking_mode == MONTE_MC_TRACK_CLEARANCE ||
-              vol->tracking_mode == MONTE_MC_TRACK_AUTO || vol->tracking_mode == MONTE_MC_TRACK_ADAPTIVE,
+    MONTE_ARG(vol->tracking_mode >= MONTE_MC_TRACK_GLOBAL && vol->tracking_mode <= MONTE_MC_TRACK_DIRECTIONAL,
               "mc: unknown tracking_mode %d", vol->tracking_mode);
-    MONTE_ARG((vol->tracking_mode != MONTE_MC_TRACK_CLEARANCE && vol->tracking_mode != MONTE_MC_TRACK_ADAPTIVE) ||
+    MONTE_ARG((vol->tracking_mode != MONTE_MC_TRACK_CLEARANCE && vol->tracking_mode != MONTE_MC_TRACK_ADAPTIVE &&
+               vol->tracking_mode != MONTE_MC_TRACK_DIRECTIONAL) ||
               (vol->clearance_cell_log2 >= 0 && vol->clearance_cell_log2 <= 8),
               "mc: clearance_cell_log2 must be 0..8 (got %d)", vol->clearance_cell_log2);
     MONTE_ARG(xs->n_materials >= 1 && xs->n_materials <= MONTE_MC_MAX_MATERIALS, "mc: n_materials must be 1..%d", MONTE_MC_MAX_MATERIALS);
@@ -693,14 +708,18 @@ static uint64_t hash_labels(const uint8_t *p, size_t n) {
 static int upload_clearance(monte_mc_scene *s, const uint8_t *labels, cudaStream_t st) {
     const monte_mc_volume &v = s->vol;
     const uint64_t hsh = hash_labels(labels, (size_t)v.nx * v.ny * v.nz);
-    const int key[6] = {v.nx, v.ny, v.nz, v.clearance_cell_log2, s->heavy, s->n_mat_host};
+    const bool oct = v.tracking_mode == MONTE_MC_TRACK_DIRECTIONAL;
+    const int key[6] = {v.nx, v.ny, v.nz, v.clearance_cell_log2 + (oct ? 100 : 0), s->heavy, s->n_mat_host};
     int32_t d[3];
     if (int rc = monte_mc_clearance_dims(&v, v.clearance_cell_log2, d)) return rc;
     s->cshift = v.clearance_cell_log2;
     s->cunit = (float)(0.5 * (double)(1 << v.clearance_cell_log2) * v.pitch);
     if (s->d_clear && hsh == s->clear_hash && memcmp(key, s->clear_key, sizeof(key)) == 0) return MONTE_OK;
-    std::vector<uint8_t> grid((size_t)d[0] * d[1] * d[2]);
-    if (int rc = monte_mc_clearance_grid(&v, labels, s->n_mat_host, s->heavy, v.clearance_cell_log2, grid.data())) return rc;
+    const size_t ncell = (size_t)d[0] * d[1] * d[2];
+    s->coct = oct ? (unsigned)ncell : 0u;
+    std::vector<uint8_t> grid(ncell * (oct ? 8 : 1));
+    if (int rc = oct ? monte_mc_clearance_grid_octants(&v, labels, s->n_mat_host, s->heavy, v.clearance_cell_log2, grid.data())
+                     : monte_mc_clearance_grid(&v, labels, s->n_mat_host, s->heavy, v.clearance_cell_log2, grid.data())) return rc;
     if (int rc = grow(&s->d_clear, &s->cap_clear, grid.size())) return rc;
     MONTE_CUDA(cudaMemcpyAsync(s->d_clear, grid.data(), grid.size(), cudaMemcpyHostToDevice, st));
     MONTE_CUDA(cudaStreamSynchronize(st));                             // `grid` is pageable and goes out of scope
@@ -730,7 +749,8 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
     monte_mc_volume vres = *vol;                                   // AUTO resolved (same rule on every rank: inputs only)
     if (vol->tracking_mode == MONTE_MC_TRACK_AUTO)
         vres.tracking_mode = monte_mc_resolve_tracking(xs, spec, &vres.clearance_cell_log2, nullptr);
-    const bool adaptive = vres.tracking_mode == MONTE_MC_TRACK_ADAPTIVE;
+    const bool directional = vres.tracking_mode == MONTE_MC_TRACK_DIRECTIONAL;
+    const bool adaptive = vres.tracking_mode == MONTE_MC_TRACK_ADAPTIVE || directional;
     s->heavy = vres.tracking_mode == MONTE_MC_TRACK_CLEARANCE || adaptive ? monte_xs_heavy_material(xs) : -1;
     for (int k = 0; k < TAB_ROWS; k++) {
         double mumax = 0, mulo = 0;
@@ -863,6 +883,7 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     L.clear = (const uint8_t *)s->d_clear; L.inv_mulo = (const float *)s->d_invlo;
     L.cgx = s->cg[0]; L.cgy = s->cg[1]; L.cshift = s->cshift; L.cunit = s->cunit;
     L.clear_thr = L.inv_mulo ? L.inv_mulo + TAB_ROWS : nullptr;
+    L.coct = s->coct;
     { static int sm = -1; if (sm < 0) { const char *e = getenv("MONTE_MC_SECOND"); sm = e ? atoi(e) : 16; } L.second_min = (uint32_t)sm; }
     if (L.total == 0) return MONTE_OK;
     MONTE_CUDA(cudaMemsetAsync(s->d_work, 0, sizeof(unsigned long long), st));

@@ -229,9 +229,9 @@ def mc_run(g, vol, labels, tables, spec, opts, per, views=None, n_range=None, pi
 def with_clearance(opts, grid, heavy):
     """attach the clearance grid of monte_mc_clearance_grid (uint8 [gz][gy][gx]) to oracle options; the volume's
     tracking_mode switches the two-level majorant on.  Returns (opts, array to keep alive)."""
-    grid = np.ascontiguousarray(grid, np.uint8)
+    grid = np.ascontiguousarray(grid, np.uint8)                   # [gz][gy][gx], or [8][gz][gy][gx] for DIRECTIONAL
     opts.clear_grid = grid.ctypes.data
-    opts.clear_dims[0], opts.clear_dims[1], opts.clear_dims[2] = grid.shape[2], grid.shape[1], grid.shape[0]
+    opts.clear_dims[0], opts.clear_dims[1], opts.clear_dims[2] = grid.shape[-1], grid.shape[-2], grid.shape[-3]
     opts.heavy = heavy
     return opts, grid
 

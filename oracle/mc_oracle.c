@@ -211,15 +211,18 @@ static double mu_lo_at(const scene_t *S, int k) {
     }
     return m;
 }
-/* clearance (cm) of the cell holding (x,y,z): no voxel of the heavy material within this distance */
-static double clearance_at(const scene_t *S, double x, double y, double z) {
+/* clearance (cm) of the cell holding (x,y,z): no voxel of the heavy material within this distance -- for
+ * tracking_mode DIRECTIONAL, none that a ray with direction (dx,dy,dz) can still reach (eight grids, one per octant) */
+static double clearance_at(const scene_t *S, double x, double y, double z, double dx, double dy, double dz) {
     const monte_mc_volume *v = S->vol;
     const double inv = 1.0 / v->pitch;
     int ix = (int)floor((x - v->origin[0]) * inv), iy = (int)floor((y - v->origin[1]) * inv), iz = (int)floor((z - v->origin[2]) * inv);
     if (ix < 0) ix = 0; if (iy < 0) iy = 0; if (iz < 0) iz = 0;
     if (ix > v->nx - 1) ix = v->nx - 1; if (iy > v->ny - 1) iy = v->ny - 1; if (iz > v->nz - 1) iz = v->nz - 1;
     const int s = v->clearance_cell_log2;
-    const int q = S->o->clear_grid[((size_t)(iz >> s) * S->o->clear_dims[1] + (iy >> s)) * S->o->clear_dims[0] + (ix >> s)];
+    const size_t ncell = (size_t)S->o->clear_dims[0] * S->o->clear_dims[1] * S->o->clear_dims[2];
+    const size_t oct = v->tracking_mode == MONTE_MC_TRACK_DIRECTIONAL ? (size_t)((dx > 0) | ((dy > 0) << 1) | ((dz > 0) << 2)) : 0;
+    const int q = S->o->clear_grid[oct * ncell + ((size_t)(iz >> s) * S->o->clear_dims[1] + (iy >> s)) * S->o->clear_dims[0] + (ix >> s)];
     return q * (0.5 * (double)(1 << s) * v->pitch);
 }
 
@@ -258,7 +261,8 @@ static int delta_sampling(const scene_t *S, rng_t *R, photon_t *p, double E, dou
     const int q = S->o->quirks;
     const monte_mc_volume *v = S->vol;
     int collided = 0;
-    const int clearance = (v->tracking_mode == MONTE_MC_TRACK_CLEARANCE || v->tracking_mode == MONTE_MC_TRACK_ADAPTIVE) && S->o->clear_grid && !q;
+    const int clearance = (v->tracking_mode == MONTE_MC_TRACK_CLEARANCE || v->tracking_mode == MONTE_MC_TRACK_ADAPTIVE ||
+                           v->tracking_mode == MONTE_MC_TRACK_DIRECTIONAL) && S->o->clear_grid && !q;
     const double mu_lo = clearance ? mu_lo_at(S, k) : 0;
     for (;;) {
         double beta, nu;
@@ -270,10 +274,11 @@ static int delta_sampling(const scene_t *S, rng_t *R, photon_t *p, double E, dou
             /* on the entry face the cell is taken 1e-3 of a voxel side further along the ray (as in the kernel) */
             const double nud = p->at_entry ? 1e-3 * v->pitch : 0.0;
             p->at_entry = 0;
-            const double D = clearance_at(S, x + nud * sin_theta_a * cos_phi_a, y + nud * sin_theta_a * sin_phi_a, z + nud * cos_theta_a);
+            const double ux = sin_theta_a * cos_phi_a, uy = sin_theta_a * sin_phi_a, uz = cos_theta_a;
+            const double D = clearance_at(S, x + nud * ux, y + nud * uy, z + nud * uz, (float)ux, (float)uy, (float)uz);
             /* ADAPTIVE: only where stopping at D is less likely than a virtual collision would be */
             double thr = 0;
-            if (v->tracking_mode == MONTE_MC_TRACK_ADAPTIVE) thr = mu_lo < mu_max ? (double)(float)(-log(1.0 - mu_lo / mu_max) / mu_lo) : 1e30;
+            if (v->tracking_mode == MONTE_MC_TRACK_ADAPTIVE || v->tracking_mode == MONTE_MC_TRACK_DIRECTIONAL) thr = mu_lo < mu_max ? (double)(float)(-log(1.0 - mu_lo / mu_max) / mu_lo) : 1e30;
             if (D > thr) {
                 double r = -log(beta) / mu_lo;
                 const int cut = r > D;

@@ -74,7 +74,7 @@ def _mc_case(rng):
         g.coherent_mode = _abi.COHERENT_FORMFACTOR
         scenes.add_formfactors(xs, mats)
     vol = scenes.volume_for(lab, pitch, tight=bool(rng.integers(0, 2)))
-    vol.tracking_mode = int(rng.integers(0, 4))
+    vol.tracking_mode = int(rng.integers(0, 5))
     vol.clearance_cell_log2 = int(rng.integers(0, 4))
     if rng.integers(0, 2):
         spec, keep = scenes.kramers_spectrum(kvp=float(rng.choice([80.0, 120.0])))
@@ -97,7 +97,7 @@ def test_emu_fuzz_mc_fates_against_oracle(monte_emu, oracle, seed):
     ovol = _abi.McVolume.from_buffer_copy(vol)
     ovol.tracking_mode, ovol.clearance_cell_log2 = mode, cl
     opts = oracle.mc_opts(oracle.RNG_PHILOX, seed=sd)
-    if mode in (_abi.TRACK_CLEARANCE, _abi.TRACK_ADAPTIVE) and xs.n_materials > 1:
+    if mode in (_abi.TRACK_CLEARANCE, _abi.TRACK_ADAPTIVE, _abi.TRACK_DIRECTIONAL) and xs.n_materials > 1:
         grid, heavy = m.clearance_grid(ovol, lab, xs)
         opts, keepg = oracle.with_clearance(opts, grid, heavy)
     sc = m.Scene(g, vol, lab, xs, spec)

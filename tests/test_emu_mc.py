@@ -283,3 +283,8 @@ def test_emu_cbct_mc_driver_end_to_end(monte_emu, tmp_path):
             vol.tracking_mode, vol.clearance_cell_log2 = _abi.TRACK_CLEARANCE, 1
         r0, r5, _ = monte_emu.simulate(g, vol, lab, xs, scenes.mono_spectrum(140.0), 40, 3)
         assert np.array_equal(r0, p0) and np.array_equal(r5, p5), tag
+
+
+@pytest.mark.parametrize("cell_log2,poly,rayleigh", [(0, True, False), (1, False, False), (1, True, True)])
+def test_emu_directional_history_coupled_fates_match_oracle(monte_emu, oracle, cell_log2, poly, rayleigh):
+    CL.test_directional_history_coupled_fates_match_oracle(monte_emu, oracle, cell_log2, poly, rayleigh)

@@ -51,18 +51,25 @@ def test_adaptive_history_coupled_fates_match_oracle(monte, oracle, cell_log2, p
     test_clearance_history_coupled_fates_match_oracle(monte, oracle, cell_log2, poly, False, mode=_abi.TRACK_ADAPTIVE)
 
 
+@pytest.mark.parametrize("cell_log2,poly,rayleigh", [(0, True, False), (1, False, False), (1, True, True)])
+def test_directional_history_coupled_fates_match_oracle(monte, oracle, cell_log2, poly, rayleigh):
+    """tracking_mode DIRECTIONAL: one clearance per octant of the flight direction, re-read after every deflection"""
+    test_clearance_history_coupled_fates_match_oracle(monte, oracle, cell_log2, poly, rayleigh, mode=_abi.TRACK_DIRECTIONAL)
+
+
 def test_adaptive_never_needs_more_steps_than_the_reference_loop(monte):
     g, vol, lab = G.scene(n=41, pitch=0.5, det=17, views=2)
     xs = scenes.make_xs()
     kr, keep = scenes.kramers_spectrum()
     for spec in (scenes.mono_spectrum(140.0), scenes.mono_spectrum(60.0), kr):
         steps = {}
-        for mode in (_abi.TRACK_GLOBAL, _abi.TRACK_CLEARANCE, _abi.TRACK_ADAPTIVE):
+        for mode in (_abi.TRACK_GLOBAL, _abi.TRACK_CLEARANCE, _abi.TRACK_ADAPTIVE, _abi.TRACK_DIRECTIONAL):
             vol.tracking_mode, vol.clearance_cell_log2 = mode, 0
             _, _, st = monte.simulate(g, vol, lab, xs, spec, 300, 17)
             steps[mode] = st["woodcock_steps"] / st["histories"]
         assert steps[_abi.TRACK_ADAPTIVE] <= 1.03 * steps[_abi.TRACK_GLOBAL], steps
         assert steps[_abi.TRACK_ADAPTIVE] <= 1.03 * steps[_abi.TRACK_CLEARANCE], steps
+        assert steps[_abi.TRACK_DIRECTIONAL] <= 0.93 * steps[_abi.TRACK_ADAPTIVE], steps      # the directional grids pay everywhere
 
 
 def test_clearance_counters_and_fewer_steps_than_the_reference_loop(monte, oracle):
