@@ -9,6 +9,7 @@ mkdir -p gpurun_out
 timeout 60 python -m pytest tests/test_tracking_gpu.py tests/test_rayleigh_gpu.py -m gpu -x -q > gpurun_out/r02_tests.log 2>&1
 echo "rc=$?" >> gpurun_out/r02_tests.log
 # 2. transport modes at C2: reference loop / CLEARANCE cells 4,8,16 / Rayleigh (scripts/mc_modes_perf.py), then ADAPTIVE
+#    and DIRECTIONAL (the candidate for the C2 headline: 21 % fewer tentative collisions at 140 keV under emulation)
 timeout 60 python scripts/mc_modes_perf.py > gpurun_out/r02_mc_modes.log 2>&1
 timeout 60 python - > gpurun_out/r02_mc_adaptive.log 2>&1 <<'PY'
 import json, sys
@@ -19,7 +20,8 @@ g, vol, lab = scenes.config_c2()
 xs = scenes.make_xs()
 poly, keep = scenes.kramers_spectrum()
 for name, spec in (("mono140", scenes.mono_spectrum(140.0)), ("mono60", scenes.mono_spectrum(60.0)), ("kramers120", poly)):
-    for mode, cl in ((_abi.TRACK_GLOBAL, 0), (_abi.TRACK_CLEARANCE, 2), (_abi.TRACK_ADAPTIVE, 2), (_abi.TRACK_ADAPTIVE, 3)):
+    for mode, cl in ((_abi.TRACK_GLOBAL, 0), (_abi.TRACK_CLEARANCE, 2), (_abi.TRACK_ADAPTIVE, 2), (_abi.TRACK_ADAPTIVE, 3),
+                     (_abi.TRACK_DIRECTIONAL, 2), (_abi.TRACK_DIRECTIONAL, 3)):
         vol.tracking_mode, vol.clearance_cell_log2 = mode, cl
         best = 1e30
         for it in range(3):
