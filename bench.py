@@ -222,6 +222,10 @@ def main():
                     help="which hot path provides the top-level keys (default: MC, BASELINE configs[1]); the other is nested")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-c4", action="store_true", help="skip the nested polyenergetic MC block (BASELINE configs[3])")
+    ap.add_argument("--mc-tracking", type=int, default=0,
+                    help="monte_mc_volume.tracking_mode of the headline scene: 0 = the reference's single-majorant loop (default), "
+                         "1 CLEARANCE, 3 ADAPTIVE, 4 DIRECTIONAL (same physics, fewer tentative collisions; see DESIGN.md section 3)")
+    ap.add_argument("--mc-cell-log2", type=int, default=3, help="clearance cells of 2^n voxels for --mc-tracking != 0")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -253,6 +257,8 @@ def main():
 
     # ------------------------------------------------------------------ MC, config 2
     g, vol, lab = scenes.config_c2()
+    if args.mc_tracking:
+        vol.tracking_mode, vol.clearance_cell_log2 = args.mc_tracking, args.mc_cell_log2
     xs = scenes.make_xs()
     spec = scenes.mono_spectrum(140.0)
     scene = api.Scene(g, vol, lab, xs, spec)
@@ -382,6 +388,7 @@ def main():
                                    "mono 140 keV, pencil-per-pixel source, <=5 scatters, image0+image5 tallies",
                        "histories_per_step": npix * PER * ws, "parallelism": "photon-range x%d + 1 NCCL reduce/view" % ws if ws > 1 else "single GPU",
                        "l2": "256 MiB fill between steps (outside the per-step CUDA events); the 34 MB label volume is re-read from HBM each step",
+                       "tracking_mode": int(args.mc_tracking),
                        "steps_per_history": steps_per_hist, "interactions_per_history": int_per_hist,
                        "primary_fraction": st["primaries"] / hist_rank, "scatter_detected_fraction": st["scatter_detected"] / hist_rank},
             "e2e": mc_e2e, "gpu_launches": K,

@@ -31,6 +31,8 @@ for name, spec in (("mono140", scenes.mono_spectrum(140.0)), ("mono60", scenes.m
         print(json.dumps({"spectrum": name, "tracking_mode": mode, "cell_log2": cl, "ms_kernel": best,
                           "steps_per_hist": st["woodcock_steps"] / st["histories"]}), flush=True)
 PY
+# 2b. the headline through bench.py with the directional majorant (same physics; compare ms_per_step with the default run)
+timeout 60 python bench.py --skip-cpu --skip-fdk --skip-c4 --steps 8 --mc-tracking 4 --mc-cell-log2 3 > gpurun_out/r02_bench_tracking4.log 2>&1
 # 3. deterministic projector at C3, host-buffer call: voxel walk vs macro-cells / leaping (one process per setting)
 for m in 0 2 3 4; do
   MONTE_PROJ_MACRO=$m timeout 90 python scripts/c3_pipeline.py > gpurun_out/r02_c3_macro$m.log 2>&1
