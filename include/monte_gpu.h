@@ -26,9 +26,12 @@
 extern "C" {
 #endif
 
-#define MONTE_GPU_ABI_VERSION 3   /* 2: monte_mc_geom.detector_mode; 3: monte_mc_geom.coherent_mode (was
+#define MONTE_GPU_ABI_VERSION 4   /* 2: monte_mc_geom.detector_mode; 3: monte_mc_geom.coherent_mode (was
                                      `reserved`, 0 = unchanged behaviour), form-factor tables appended to monte_mc_xs,
-                                     tracking_mode / clearance_cell_log2 appended to monte_mc_volume (0 = unchanged) */
+                                     tracking_mode / clearance_cell_log2 appended to monte_mc_volume (0 = unchanged);
+                                     4: monte_gpu_init binds 1..8 devices and the host-buffer calls monte_gpu_simulate* /
+                                     monte_gpu_fdk shard over them; monte_gpu_simulate_maps; "all views" is spelled
+                                     view_end < 0 (the range [0, 0) is now empty, as in the device forms)        */
 
 /* ---- status codes ------------------------------------------------------ */
 #define MONTE_OK            0
@@ -40,9 +43,17 @@ extern "C" {
 #define MONTE_E_IO         -6   /* table / raw file problems (host helpers)      */
 
 /* ---- library lifetime --------------------------------------------------- */
-/* Selects the device of this process (one process per GPU).  ndev must be 1 in
- * this ABI version; ids[0] is the CUDA ordinal (ids == NULL -> device 0).      */
+/* Binds ndev (1..8) devices of one NVSwitch box to this process; ids[] are CUDA ordinals
+ * (ids == NULL -> 0..ndev-1).  With ndev == 1 every call runs on that device (one process
+ * per GPU, the form the torch.distributed plumbing uses).  With ndev > 1 (one
+ * stream per device, peer access over NVLink, an in-library NCCL communicator created on
+ * first use) the host-buffer calls monte_gpu_simulate / _range / _maps split the photon
+ * range over the devices and sum the tallies onto ids[0], and monte_gpu_fdk shards the
+ * filter by views and the backprojection by z-slabs of equal work; results are bit-identical
+ * to ndev == 1.  All other calls (device-pointer forms, scenes, projector, fbp2) run on ids[0]. */
 int  monte_gpu_init(int ndev, const int *ids);
+int  monte_gpu_device_count(void);     /* devices bound by the last monte_gpu_init (0 before)     */
+int  monte_gpu_peer_access(void);      /* 1: every bound device can address every other (NVLink P2P) */
 void monte_gpu_shutdown(void);
 const char *monte_gpu_last_error(void);
 int  monte_gpu_abi_version(void);
@@ -108,7 +119,10 @@ typedef struct monte_fdk_stats {
 void monte_fdk_geom_bp3d20(monte_fdk_geom *g);      /* recon/bp3d20.cpp        */
 void monte_fdk_geom_bp3d20_325(monte_fdk_geom *g);  /* recon/bp3d20_325.cpp    */
 
-/* Whole pipeline on host buffers (the drop-in for bp3d20.cpp:29-171).
+/* Whole pipeline on host buffers (the drop-in for bp3d20.cpp:29-171).  With several bound devices (monte_gpu_init):
+ * device i uploads and filters views [n_views i/N, n_views (i+1)/N), then backprojects all views into z-slab i of
+ * monte_gpu_fdk_partition, loading the detector rows that slab reads straight out of its peers' memory over NVLink
+ * (the exchange is fused into the backprojector's row-pair conversion), and copies the slab into vol_xy in place.
  * map      [n_views][nu][nv]  float32, in
  * filtered [n_views][nv][nu]  float32, out, nullable   ("map_out", bp3d20.cpp:187)
  * vol_xy   [nz][ny][nx]       float32, out             ("image_xy")
@@ -139,6 +153,11 @@ int monte_gpu_fdk_pad_dev(const monte_fdk_geom *g, float *d_filtered_padded, voi
  * owns a z-slab needs only these rows of the other ranks' filtered views (multi-GPU exchange).
  * row_lo == row_hi: no view sees the slab.                                                               */
 int monte_gpu_fdk_slab_rows(const monte_fdk_geom *g, int z_lo, int z_hi, int *row_lo, int *row_hi);
+/* z-slab cuts of equal modelled work, z_cuts[0] = 0 <= ... <= z_cuts[n_parts] = nz (on multiples of 16 slices where
+ * possible): at wide cone angles the end slices see the detector in few views or none (bp3d20.cpp:116 skips them), so
+ * slabs of equal thickness would leave the end devices idle.  This is the partition monte_gpu_fdk uses with n_parts =
+ * bound devices; any partition gives the same voxels bit for bit.  Host only.                                       */
+int monte_gpu_fdk_partition(const monte_fdk_geom *g, int n_parts, int *z_cuts);
 /* Backproject all views into z-slices [z_lo, z_hi) of the volume;
  * d_vol_slab points at slice z_lo, layout [z_hi-z_lo][ny][nx].  Overwrites.        */
 int monte_gpu_fdk_backproject_dev(const monte_fdk_geom *g, const float *d_filtered_padded,
@@ -300,8 +319,9 @@ typedef struct monte_mc_stats {
 /* Whole simulation on host buffers.  photons_per_pixel is the reference's `per`
  * (CBCT_real325im.cu:182): histories per view = per*ny*nx.  History id
  * h = (view*ny*nx + pixel)*per + n keys a Philox2x32-10 counter (seed, h), so the
- * result is independent of how histories are partitioned.  view_begin == view_end == 0 means
- * all views; only the requested views of image0/image5 are written.
+ * result is independent of how histories are partitioned (lanes, CTAs, devices).  view_end < 0
+ * (with view_begin == 0) means all views; [v, v) is empty; only the requested views of
+ * image0/image5 are written.
  * image0 [n_views][ny][nx] int32: unscattered;  image5: unscattered + scattered
  * (CBCT_real325im.cu:584-585,692,841).  labels: uint8 [nz][ny][nx].                    */
 int monte_gpu_simulate(const monte_mc_geom *g, const monte_mc_volume *vol,
@@ -319,6 +339,21 @@ int monte_gpu_simulate_range(const monte_mc_geom *g, const monte_mc_volume *vol,
                              uint64_t seed, int view_begin, int view_end,
                              int32_t *image0, int32_t *image5, monte_mc_stats *stats);
 
+/* The whole seam of the reference's main() in one call (CBCT_real325im.cu:232-288: launch, D2H of both count
+ * images, clamp + -log maps): as monte_gpu_simulate_range, and additionally map0 / map5 (nullable, float32
+ * [n_views][ny][nx]) = -ln(clamp(image, 1, I0)) + ln(I0), I0 = n_end - n_begin, computed on the device in the same
+ * pass that sums the per-device tallies (fused reduce + epilogue).  With several bound
+ * devices: MONTE_MC_REDUCE=p2p (default; the root kernel loads the peers' tallies over NVLink) or =nccl (one
+ * ncclReduce to ids[0], then the epilogue kernel).  The label volume is re-uploaded only when its content changed
+ * (64-bit hash of the host buffer; MONTE_MC_LABEL_CACHE=0 uploads it on every call).                           */
+int monte_gpu_simulate_maps(const monte_mc_geom *g, const monte_mc_volume *vol,
+                            const uint8_t *labels, const monte_mc_xs *xs,
+                            const monte_mc_spectrum *spec, uint32_t photons_per_pixel,
+                            uint32_t n_begin, uint32_t n_end,
+                            uint64_t seed, int view_begin, int view_end,
+                            int32_t *image0, int32_t *image5, float *map0, float *map5,
+                            monte_mc_stats *stats);
+
 /* Device-resident form: the scene is uploaded once, tallies accumulate into device
  * int32 images [view_end-view_begin... indexed by absolute view][ny][nx].             */
 typedef struct monte_mc_scene monte_mc_scene;   /* opaque */
@@ -331,6 +366,8 @@ int monte_gpu_scene_update_labels(monte_mc_scene *s, const uint8_t *labels, void
 /* Run photons n in [n_begin, n_end) of every pixel of views [view_begin, view_end)
  * and add into d_image0/d_image5 (device, [n_views][ny][nx], caller zeroes).
  * d_stats: device uint64[16] accumulators (nullable), see monte_gpu_mc_stats_unpack. */
+/* Launches of ONE scene may overlap on different streams (each takes its own work counter out of a ring of 16);
+ * more than 16 launches of one scene in flight at once are not supported.                                  */
 int monte_gpu_simulate_dev(const monte_mc_scene *s, uint64_t seed,
                            int view_begin, int view_end,
                            uint32_t n_begin, uint32_t n_end, uint32_t photons_per_pixel,

@@ -45,6 +45,12 @@ def _bind(path):
         "monte_gpu_last_error": (C.c_char_p, []),
         "monte_gpu_abi_version": (C.c_int, []),
         "monte_gpu_sm_count": (C.c_int, []),
+        "monte_gpu_device_count": (C.c_int, []),
+        "monte_gpu_peer_access": (C.c_int, []),
+        "monte_gpu_fdk_partition": (C.c_int, [G, C.c_int, C.POINTER(C.c_int)]),
+        "monte_gpu_simulate_maps": (C.c_int, [C.POINTER(McGeom), C.POINTER(McVolume), vp, C.POINTER(McXs),
+                                              C.POINTER(McSpectrum), u32, u32, u32, u64, C.c_int, C.c_int, vp, vp, vp, vp,
+                                              C.POINTER(McStats)]),
         "monte_fdk_geom_bp3d20": (None, [G]),
         "monte_fdk_geom_bp3d20_325": (None, [G]),
         "monte_fdk_geom_fbp2": (None, [G]),
@@ -115,13 +121,22 @@ _inited_dev = None
 
 
 def init(device=0):
-    """Bind this process to one B200 (one process per GPU)."""
+    """Bind this process to one B200 (one process per GPU), or -- device = a list of CUDA ordinals -- to several
+    GPUs of one box: the host-buffer calls simulate() / fdk() then shard over them inside the library."""
     global _inited_dev
     lib = load()
-    ids = (C.c_int * 1)(device)
-    _check(lib.monte_gpu_init(1, ids))
-    _inited_dev = device
+    devs = list(device) if isinstance(device, (list, tuple)) else [device]
+    ids = (C.c_int * len(devs))(*devs)
+    _check(lib.monte_gpu_init(len(devs), ids))
+    _inited_dev = devs[0]
     return lib
+
+
+def fdk_partition(g, n_parts):
+    """z-slab cuts [0, ..., nz] of equal modelled work that the multi-device monte_gpu_fdk uses"""
+    cuts = (C.c_int * (n_parts + 1))()
+    _check(load().monte_gpu_fdk_partition(C.byref(g), n_parts, cuts))
+    return list(cuts)
 
 
 def shutdown():
@@ -223,9 +238,11 @@ def fdk_transpose_dev(g, d_xy, d_zy, stream=None):
 
 
 # ------------------------------------------------------------------ Monte Carlo
-def simulate(g, vol, labels, xs, spec, per, seed=1, views=None, n_range=None, out=None):
+def simulate(g, vol, labels, xs, spec, per, seed=1, views=None, n_range=None, out=None, maps=None):
     """monte_gpu_simulate(_range) on host buffers.  Returns (image0, image5 [n_views][ny][nx] int32,
-    stats dict).  out=(image0, image5) reuses caller (e.g. pinned) buffers; only `views` are written."""
+    stats dict).  out=(image0, image5) reuses caller (e.g. pinned) buffers; only `views` are written.
+    maps=(map0, map5) float32 arrays (or True to allocate them): monte_gpu_simulate_maps, the -log maps come
+    back too, as 4th and 5th element."""
     lib = load()
     labels = np.ascontiguousarray(labels, np.uint8)
     vb, ve = views if views else (0, g.n_views)
@@ -236,6 +253,12 @@ def simulate(g, vol, labels, xs, spec, per, seed=1, views=None, n_range=None, ou
     else:
         im0, im5 = out
     st = McStats()
+    if maps is not None:
+        m0, m5 = (np.zeros(im0.shape, np.float32), np.zeros(im0.shape, np.float32)) if maps is True else maps
+        _check(lib.monte_gpu_simulate_maps(C.byref(g), C.byref(vol), _ptr(labels), C.byref(xs),
+                                           C.byref(spec) if spec is not None else None, per, nb, ne, seed, vb, ve,
+                                           _ptr(im0), _ptr(im5), _ptr(m0), _ptr(m5), C.byref(st)))
+        return im0, im5, _abi.stats_dict(st), m0, m5
     _check(lib.monte_gpu_simulate_range(C.byref(g), C.byref(vol), _ptr(labels), C.byref(xs),
                                         C.byref(spec) if spec is not None else None, per, nb, ne, seed, vb, ve,
                                         _ptr(im0), _ptr(im5), C.byref(st)))

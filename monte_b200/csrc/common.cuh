@@ -24,18 +24,35 @@
 
 namespace monte {
 
+constexpr int MAX_DEV = 8;         // devices one process may bind (monte_gpu_init(ndev, ids)): one NVSwitch box
+constexpr int N_SCRATCH = 16;
+
+// One Context per bound device.  Every entry point works on the *current* device (index cur_dev(), 0 after
+// monte_gpu_init); the multi-device orchestration (multi.cu) walks the devices with use_dev(i), issues the same
+// single-device code on each of them, and returns to device 0.
 struct Context {
     bool      inited = false;
-    int       device = 0;
+    int       device = 0;              // CUDA ordinal
     int       sm_count = 0;
     cudaStream_t stream = nullptr;     // library-owned stream for the host-buffer entry points
     cudaStream_t copy_stream = nullptr; // second stream: D2H of finished slabs overlaps compute
     // grow-only device scratch shared by the host-buffer entry points
-    void  *scratch[12] = {nullptr};
-    size_t scratch_bytes[12] = {0};
+    void  *scratch[N_SCRATCH] = {nullptr};
+    size_t scratch_bytes[N_SCRATCH] = {0};
 };
 
-Context &ctx();
+Context &ctx();                    // of the current device
+Context &ctx_of(int i);
+int  n_dev();                      // devices bound by monte_gpu_init (0 before)
+int  cur_dev();                    // index of the current device in the bound list
+int  use_dev(int i);               // cudaSetDevice + make it current; MONTE_OK or an error code
+bool peers_ok();                   // every bound device can load/store every other one's memory (NVLink P2P enabled)
+// per-device module state (function attributes already raised, cached tables, events ...): one copy per bound device
+template <class T> struct PerDev {
+    T v[MAX_DEV];
+    T &get() { return v[cur_dev()]; }
+    T &of(int i) { return v[i]; }
+};
 // modules register a function that frees their cached device buffers (called by monte_gpu_shutdown)
 void at_shutdown(void (*fn)());
 void set_error(const char *fmt, ...);

@@ -15,6 +15,8 @@
 // per-row taps, the backprojector a gather.  Bound: FP32 pipe + L1 gather.
 #include "common.cuh"
 #include "fft_core.cuh"
+#include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 
@@ -246,6 +248,35 @@ __global__ void fdk_pair_kernel(const float *__restrict__ f, float2 *__restrict_
     pairs[(size_t)r * pitch + c] = make_float2(a, b - a);
 }
 
+// The same pairs built straight from the devices that filtered the views (multi-device reconstruction): the
+// exchange of filtered projections IS this kernel -- every device loads the detector-row band its z-slab reads out of
+// its peers' memory (NVLink P2P, coalesced rows) while converting it to the pair layout, so no filtered view is ever
+// copied, packed or stored twice.  src.base[o] is the (virtual) base of owner o's padded-row layout: row R of the
+// global layout lives at base[o] + R * pitch for the views [v_end[o-1], v_end[o]) owner o filtered.  The pad rules of
+// fdk_pad_kernel (element [r][nu] = [r+1][0], columns beyond and rows past the last view = 0) are applied on the fly.
+struct PairSrc {
+    const float *base[MAX_DEV];
+    int v_end[MAX_DEV];
+    int n;
+};
+__device__ __forceinline__ float pair_fetch(const PairSrc &src, int R, int c, int rows, int nv, int nu, int pitch) {
+    if (c > nu || R >= rows) return 0.f;
+    if (c == nu) { R += 1; c = 0; if (R >= rows) return 0.f; }
+    const int v = R / nv;
+    int o = 0;
+    while (o < src.n - 1 && v >= src.v_end[o]) o++;
+    return src.base[o][(size_t)R * pitch + c];
+}
+__global__ void fdk_pair_gather_kernel(const PairSrc src, float2 *__restrict__ pairs, int view_lo, int nv, int nu, int b_lo, int b_hi,
+                                       int rows, int pitch) {
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    const int R = (view_lo + (int)blockIdx.z) * nv + b_lo + (int)blockIdx.x;
+    if (c >= pitch || (int)blockIdx.x >= b_hi - b_lo || R >= rows + 2) return;
+    const float a = pair_fetch(src, R, c, rows, nv, nu, pitch);
+    const float b = pair_fetch(src, R + 1, c, rows, nv, nu, pitch);
+    pairs[(size_t)R * pitch + c] = make_float2(a, b - a);
+}
+
 __global__ void fdk_unpad_kernel(const float *f, float *dense, size_t rows, int nu, int pitch) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * nu) return;
@@ -260,8 +291,7 @@ __global__ void fdk_unpad_kernel(const float *f, float *dense, size_t rows, int 
 constexpr int BP_TX = 32, BP_TY = 8;   // threads: 32 along s (x-fastest, coalesced), 8 along t
 
 struct BpParams {
-    const float *filt;          // padded rows [n_views*nv + 2][pitch]
-    const float2 *pairs;        // same rows as vertical pairs (fdk_pair_kernel)
+    const float2 *pairs;        // padded rows [n_views*nv + 2][pitch] as vertical pairs (fdk_pair_kernel / fdk_pair_gather_kernel)
     const ViewConst *vc;
     float *vol;                 // slab base: slice z_lo
     int n_views, nu, nv, pitch;
@@ -319,11 +349,13 @@ __device__ __noinline__ bool bp_exact_ts_negative(const BpParams &p, const ViewC
     return __dsub_rn(__dmul_rn(X, c.cbd), __dmul_rn(Y, c.sbd)) < 0;
 }
 
-__device__ __forceinline__ float bp_bilinear(const float *__restrict__ f, int pitch, float x, float y) {
+// the same four texels out of the pair layout: pairs[r][c].x IS f[r][c], so rows xi and xi + 1 give the bits
+// bp_bilinear reads from the plain rows (the band a slab pairs always holds row xi + 1 of an on-detector xi)
+__device__ __forceinline__ float bp_bilinear_pairs(const float2 *__restrict__ f, int pitch, float x, float y) {
     const int xi = (int)x, yi = (int)y;
     const float fx = x - (float)xi, fy = y - (float)yi;
-    const float *q = f + (size_t)xi * pitch + yi;
-    const float a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + pitch), d = __ldg(q + pitch + 1);
+    const float2 *q = f + (size_t)xi * pitch + yi;
+    const float a = __ldg(&q->x), b = __ldg(&(q + 1)->x), c = __ldg(&(q + pitch)->x), d = __ldg(&(q + pitch + 1)->x);
     const float lo = fmaf(fx, c - a, a);      // (1-fx)*a + fx*c
     const float hi = fmaf(fx, d - b, b);
     return fmaf(fy, hi - lo, lo);
@@ -331,12 +363,12 @@ __device__ __forceinline__ float bp_bilinear(const float *__restrict__ f, int pi
 
 // exact contribution of one band voxel (rare path, kept out of line and out of the hot loop)
 __device__ __noinline__ float bp_fix_one(const BpParams &p, const ViewConst &c, int s, int t, int z,
-                                         const float *__restrict__ fv, float wgt) {
+                                         const float2 *__restrict__ fpv, float wgt) {
     float xe, ye;
     if (!bp_exact(p, c, s, t, z, xe, ye) || xe < 0.f) return 0.f;
     xe = fminf(fmaxf(xe, 0.f), (float)p.nv);
     ye = fminf(fmaxf(ye, 0.f), (float)p.nu);
-    return wgt * bp_bilinear(fv, p.pitch, xe, ye);
+    return wgt * bp_bilinear_pairs(fpv, p.pitch, xe, ye);
 }
 
 // Hot loop structure per view: (1) everything that depends on (s,t,view) only; (2) for a batch of
@@ -408,7 +440,6 @@ fdk_backproject_kernel(const __grid_constant__ BpParams p) {
         const float fy = y - (float)yi;
         // warp-uniform row pointers + one 32-bit element offset per voxel: one IMAD and two
         // IMAD.WIDE per update instead of 64-bit add/shift chains on the ALU pipe
-        const float *__restrict__ fv = p.filt + (size_t)v * p.nv * p.pitch;
         const float2 *__restrict__ fp = p.pairs + (size_t)v * p.nv * p.pitch;
         // column yi of this view's rows as one opaque 64-bit value: otherwise the compiler keeps the
         // warp-uniform view base apart and re-adds it for every slice (IADD3 + IADD3.X per update)
@@ -478,7 +509,7 @@ fdk_backproject_kernel(const __grid_constant__ BpParams p) {
         if (band) {                                             // rare: exact double evaluation
 #pragma unroll
             for (int i = 0; i < ZT; i++)
-                if (band & (1u << i)) acc[i] += bp_fix_one(p, p.vc[v], s, t, zb + i, fv, wgt);
+                if (band & (1u << i)) acc[i] += bp_fix_one(p, p.vc[v], s, t, zb + i, p.pairs + (size_t)v * p.nv * p.pitch, wgt);
         }
     }
 #pragma unroll
@@ -525,28 +556,53 @@ struct FdkCache {           // per-geometry device constants, rebuilt only when 
     int noff = 0, tap_len = 0, nu_pad = 0, in_pitch = 0;
     size_t vc_cap = 0, wtab_cap = 0, taps_cap = 0, fft_cap = 0;
 };
-static FdkCache g_fdk;
+// one cache (and one set of events / raised function attributes) per bound device
+static PerDev<FdkCache> g_fdk_pd;
+#define g_fdk (g_fdk_pd.get())
 // per-context state that must not survive monte_gpu_shutdown (a later monte_gpu_init may bind another device):
 // function attributes already raised, and the events of the host-buffer pipeline
-static bool g_fft_attr_set = false;
-static size_t g_filter_smem_set = 0;
 constexpr int FDK_MAXC = 16;
-static cudaEvent_t g_ev_up[FDK_MAXC] = {nullptr}, g_ev_slab[FDK_MAXC] = {nullptr}, g_ev_t[6] = {nullptr};
-static void fdk_cleanup() {
+struct FdkDevState {
+    bool fft_attr_set = false;
+    size_t filter_smem_set = 0;
+    cudaEvent_t ev_up[FDK_MAXC] = {nullptr}, ev_slab[FDK_MAXC] = {nullptr}, ev_t[6] = {nullptr};
+};
+static PerDev<FdkDevState> g_fdk_state;
+#define g_fft_attr_set (g_fdk_state.get().fft_attr_set)
+#define g_filter_smem_set (g_fdk_state.get().filter_smem_set)
+#define g_ev_up (g_fdk_state.get().ev_up)
+#define g_ev_slab (g_fdk_state.get().ev_slab)
+#define g_ev_t (g_fdk_state.get().ev_t)
+static void fdk_cleanup() {                       // called once per bound device, with that device current
     cudaFree(g_fdk.d_vc); cudaFree(g_fdk.d_wtab); cudaFree(g_fdk.d_taps); cudaFree(g_fdk.d_tw); cudaFree(g_fdk.d_spec);
     g_fdk = FdkCache();
-    g_fft_attr_set = false;
-    g_filter_smem_set = 0;
     for (int i = 0; i < FDK_MAXC; i++) {
         if (g_ev_up[i]) cudaEventDestroy(g_ev_up[i]);
         if (g_ev_slab[i]) cudaEventDestroy(g_ev_slab[i]);
-        g_ev_up[i] = g_ev_slab[i] = nullptr;
     }
-    for (int i = 0; i < 6; i++) { if (g_ev_t[i]) cudaEventDestroy(g_ev_t[i]); g_ev_t[i] = nullptr; }
+    for (int i = 0; i < 6; i++) if (g_ev_t[i]) cudaEventDestroy(g_ev_t[i]);
+    g_fdk_state.get() = FdkDevState();
+}
+
+// the geometry as a cache key: copied field by field into a zeroed struct, so that the padding bytes of a
+// caller's hand-filled monte_fdk_geom (after nv, after nz, before mask_r2) cannot make equal geometries differ
+static monte_fdk_geom canon_geom(const monte_fdk_geom *g) {
+    monte_fdk_geom c;
+    memset(&c, 0, sizeof(c));
+    c.n_views = g->n_views; c.nu = g->nu; c.nv = g->nv; c.du = g->du; c.dv = g->dv;
+    c.half_u = g->half_u; c.half_v = g->half_v; c.dso = g->dso; c.dsd = g->dsd;
+    c.weight_dist = g->weight_dist; c.filter_scale = g->filter_scale; c.out_scale = g->out_scale; c.out_scale2 = g->out_scale2;
+    c.angle0_deg = g->angle0_deg; c.angle_step_deg = g->angle_step_deg;
+    c.nx = g->nx; c.ny = g->ny; c.nz = g->nz; c.vox = g->vox; c.x0 = g->x0; c.y0 = g->y0; c.z0 = g->z0;
+    c.s_begin = g->s_begin; c.s_end = g->s_end; c.t_begin = g->t_begin; c.t_end = g->t_end; c.z_begin = g->z_begin; c.z_end = g->z_end;
+    c.mask_cs = g->mask_cs; c.mask_ct = g->mask_ct; c.mask_cz = g->mask_cz; c.mask_r2 = g->mask_r2;
+    c.weight_mode = g->weight_mode; c.coord_mode = g->coord_mode;
+    return c;
 }
 
 static int fdk_prepare(const monte_fdk_geom *g, cudaStream_t st) {
-    if (g_fdk.valid && memcmp(&g_fdk.g, g, sizeof(*g)) == 0) return MONTE_OK;
+    const monte_fdk_geom key = canon_geom(g);
+    if (g_fdk.valid && memcmp(&g_fdk.g, &key, sizeof(key)) == 0) return MONTE_OK;
     at_shutdown(fdk_cleanup);
     g_fdk.valid = false;
     std::vector<ViewConst> vc;
@@ -616,7 +672,7 @@ static int fdk_prepare(const monte_fdk_geom *g, cudaStream_t st) {
         MONTE_CUDA(cudaMemcpyAsync(g_fdk.d_spec, spec.data(), fft_len * sizeof(float), cudaMemcpyHostToDevice, st));
     }
     MONTE_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope
-    g_fdk.g = *g;
+    g_fdk.g = key;
     g_fdk.noff = noff; g_fdk.tap_len = tap_len; g_fdk.nu_pad = nu_pad; g_fdk.in_pitch = in_pitch;
     g_fdk.fft_len = fft_len;
     g_fdk.valid = true;
@@ -739,8 +795,10 @@ static void slab_band(const monte_fdk_geom *g, int z_lo, int z_hi, int &b_lo, in
     if (b_hi > g->nv) b_hi = g->nv;       // rows nv, nv+1 of a view are rows 0, 1 of the next one
 }
 
+// src != nullptr: the filtered rows live on the devices that filtered them (d_filtered_padded is not read)
 static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_padded, int z_lo, int z_hi,
-                             float *d_vol_slab, cudaStream_t st, int view_lo, int view_hi, bool continue_sum) {
+                             float *d_vol_slab, cudaStream_t st, int view_lo, int view_hi, bool continue_sum,
+                             const PairSrc *src = nullptr) {
     if (int rc = fdk_prepare(g, st)) return rc;
     if (z_lo == z_hi) return MONTE_OK;
     // everything outside the ROI is zero (the reference callocs the volume, bp3d20.cpp:32)
@@ -748,7 +806,7 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
     if (g->s_begin == g->s_end || g->t_begin == g->t_end || view_lo >= view_hi) return MONTE_OK;
     const bool textbook = g->weight_mode == MONTE_FDK_TEXTBOOK;
     BpParams p;
-    p.filt = d_filtered_padded; p.vc = g_fdk.d_vc; p.vol = d_vol_slab;
+    p.vc = g_fdk.d_vc; p.vol = d_vol_slab;
     p.n_views = g->n_views; p.nu = g->nu; p.nv = g->nv; p.pitch = (int)filtered_pitch(g);
     p.nx = g->nx; p.ny = g->ny;
     p.s_begin = g->s_begin; p.s_end = g->s_end; p.t_begin = g->t_begin; p.t_end = g->t_end;
@@ -809,23 +867,27 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
         if (b_hi <= b_lo) return MONTE_OK;
         // rows 0..3 of every view are always paired too: they are what the previous view reaches past its end
         const int n_v = view_hi - view_lo + (view_hi < g->n_views ? 1 : 0);
+        // (one launch shape for both sources: the local padded rows, or the peers' rows over NVLink)
+        auto pair_rows = [&](int v_first, int r_lo, int r_hi, int n_views_z) {
+            const dim3 grid(r_hi - r_lo, ceil_div(p.pitch, 128), n_views_z);
+            if (src) fdk_pair_gather_kernel MONTE_CFG(grid, 128, 0, st)(*src, d_pairs, v_first, g->nv, g->nu, r_lo, r_hi, rows_total - 2, p.pitch);
+            else fdk_pair_kernel MONTE_CFG(grid, 128, 0, st)(d_filtered_padded, d_pairs, v_first, g->nv, r_lo, r_hi, rows_total, p.pitch);
+        };
         if (b_lo > 0) {
-            fdk_pair_kernel MONTE_CFG(dim3(b_lo < 4 ? b_lo : 4, ceil_div(p.pitch, 128), n_v), 128, 0, st)(d_filtered_padded, d_pairs, view_lo, g->nv, 0,
-                                                                                                   b_lo < 4 ? b_lo : 4, rows_total, p.pitch);
+            pair_rows(view_lo, 0, b_lo < 4 ? b_lo : 4, n_v);
             MONTE_CUDA(cudaGetLastError());
         }
-        fdk_pair_kernel MONTE_CFG(dim3(b_hi - b_lo, ceil_div(p.pitch, 128), n_v), 128, 0, st)(d_filtered_padded, d_pairs, view_lo, g->nv, b_lo, b_hi,
-                                                                                       rows_total, p.pitch);
+        pair_rows(view_lo, b_lo, b_hi, n_v);
         MONTE_CUDA(cudaGetLastError());
         if (view_hi == g->n_views) {          // the two zero rows after the last view
-            fdk_pair_kernel MONTE_CFG(dim3(2, ceil_div(p.pitch, 128), 1), 128, 0, st)(d_filtered_padded, d_pairs, g->n_views, g->nv, 0, 2, rows_total, p.pitch);
+            pair_rows(g->n_views, 0, 2, 1);
             MONTE_CUDA(cudaGetLastError());
         }
     }
     for (int vb = view_lo; vb < view_hi; vb += vchunk) {
     // a chunk is presented to the kernel as a shorter scan: shifted view constants and rows
     p.n_views = vb + vchunk < view_hi ? vchunk : view_hi - vb;
-    p.vc = g_fdk.d_vc + vb; p.filt = d_filtered_padded + (size_t)vb * g->nv * p.pitch;
+    p.vc = g_fdk.d_vc + vb;
     p.pairs = d_pairs + (size_t)vb * g->nv * p.pitch; p.accumulate = continue_sum || vb > view_lo;
     switch (variant) {
         case 1: BP_LAUNCH(32, 8, 2); break;     // 32 slices per thread, 2 CTAs/SM: 74.8 ms at C3 (before the 12-instruction update)
@@ -878,12 +940,249 @@ int monte_gpu_fdk_transpose_dev(const monte_fdk_geom *g, const float *d_vol_xy, 
     return MONTE_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// multi-device reconstruction: filter sharded by views, backprojection by z-slabs of equal work
+// ------------------------------------------------------------------------------------------
+// Relative backprojection cost of every z-slice: at wide cone angles the end slices see the detector in few views
+// or none.  cost = overhead + f (1 + penalty [f below its maximum]), f = fraction of the slice's (voxel, view) pairs
+// that project onto the detector (bp3d20.cpp:116 skips the others), sampled on a coarse (s, t, view) grid with the
+// reference's projection formulas (:99-113); `overhead` = per-column work done while any view sees the slice,
+// `penalty` = the slower general path of columns near the detector edge.  Calibrated on one B200 at C3
+// (scripts/fdk_slab_cost.py); the same model as monte_b200/dist.py:fdk_slice_cost.
+static void fdk_slice_cost(const monte_fdk_geom *g, std::vector<double> &cost) {
+    const double overhead = 0.32, penalty = 0.45;
+    const int stride = 8;
+    std::vector<float> ks;
+    size_t total = 0;
+    for (int t = 0; t < g->ny; t += stride)
+        for (int s = 0; s < g->nx; s += stride)
+            for (int v = 0; v < g->n_views; v += stride) {
+                const double X = g->x0 + g->vox * s, Y = g->y0 - g->vox * t;
+                const double beta = M_PI * (g->angle0_deg + g->angle_step_deg * v) / 180;
+                const double k = g->dsd / (X * cos(beta) + Y * sin(beta) + g->dso);
+                total++;
+                if (fabs(k * (-X * sin(beta) + Y * cos(beta))) <= g->half_u) ks.push_back((float)k);
+            }
+    std::sort(ks.begin(), ks.end());
+    cost.assign(g->nz, 0.0);
+    std::vector<double> frac(g->nz);
+    double fmaxv = 0;
+    for (int z = 0; z < g->nz; z++) {
+        const double Z = fmax(fabs(g->z0 - g->vox * z), 1e-12);
+        // |k Z| <= half_v  <=>  k <= half_v / |Z|
+        frac[z] = (double)(std::upper_bound(ks.begin(), ks.end(), (float)(g->half_v / Z)) - ks.begin()) / (double)(total ? total : 1);
+        fmaxv = fmax(fmaxv, frac[z]);
+    }
+    for (int z = 0; z < g->nz; z++) {
+        const bool partial = frac[z] > 0 && frac[z] < 0.97 * fmaxv;
+        cost[z] = (frac[z] > 0 ? overhead : 0.02) + frac[z] * (1.0 + (partial ? penalty : 0.0));
+    }
+}
+
+// contiguous cuts of range(n) into `world` pieces of nearly equal cost, moved to multiples of `align` (the
+// backprojector's z-block) where that keeps every piece non-empty; cuts[0] = 0 .. cuts[world] = n
+static void balanced_cuts(const std::vector<double> &cost, int world, int align, int *cuts) {
+    const int n = (int)cost.size();
+    std::vector<double> acc(n + 1, 0.0);
+    for (int i = 0; i < n; i++) acc[i + 1] = acc[i] + cost[i];
+    cuts[0] = 0;
+    for (int r = 1; r < world; r++) {
+        const double target = acc[n] * r / world;
+        const int lo = n >= world ? cuts[r - 1] + 1 : cuts[r - 1], hi = n >= world ? n - (world - r) : n;
+        int k = lo;
+        while (k < hi && acc[k] < target) k++;
+        if (k > lo && target - acc[k - 1] < acc[k] - target) k--;
+        k = k < lo ? lo : (k > hi ? hi : k);
+        if (align > 1) {
+            const int ka = (k + align / 2) / align * align;
+            if (lo <= ka && ka <= hi) k = ka;
+        }
+        cuts[r] = k;
+    }
+    cuts[world] = n;
+}
+
+struct FdkMultiDev {              // what one device holds during a multi-device reconstruction
+    int v_lo = 0, v_hi = 0, z_lo = 0, z_hi = 0;
+    float *d_map = nullptr, *d_filt = nullptr, *d_vol = nullptr;
+    cudaEvent_t filtered = nullptr;
+    EventTimer *t_f = nullptr, *t_b = nullptr;
+};
+
+int monte_gpu_fdk_partition(const monte_fdk_geom *g, int n_parts, int *z_cuts) {
+    if (int rc = check_geom(g)) return rc;
+    MONTE_ARG(n_parts >= 1 && z_cuts, "fdk_partition: bad argument");
+    std::vector<double> cost;
+    fdk_slice_cost(g, cost);
+    std::vector<int> cuts(n_parts + 1);
+    balanced_cuts(cost, n_parts, 16, cuts.data());
+    for (int i = 0; i <= n_parts; i++) z_cuts[i] = cuts[i];
+    return MONTE_OK;
+}
+
+// monte_gpu_fdk on all bound devices.  Device i uploads and filters views [v_lo_i, v_hi_i) (upload chunks overlap the
+// filter), then backprojects ALL views into its own z-slab, fetching the detector-row band that slab reads straight
+// out of the peers' filtered rows (fdk_pair_gather_kernel: the exchange is fused into the pair conversion, nothing is
+// packed, copied or stored twice), and sends the slab home in pieces that overlap the next piece's backprojection.
+// Views are consumed in ascending order on every device, so the volume has the bits of the one-device call.
+static int fdk_multi(const monte_fdk_geom *g, const float *map, float *filtered, float *vol_xy, float *vol_zy, monte_fdk_stats *stats) {
+    const int nd = n_dev();
+    if (!peers_ok()) {
+        set_error("fdk: the %d bound devices lack mutual peer access (NVLink P2P), which the multi-device reconstruction needs", nd);
+        return MONTE_E_NODEV;
+    }
+    const auto t_host0 = std::chrono::steady_clock::now();
+    const size_t per_view = (size_t)g->nu * g->nv, slice = (size_t)g->nx * g->ny;
+    const int pitch = (int)filtered_pitch(g);
+    int cuts[MAX_DEV + 1];
+    {
+        static monte_fdk_geom key;                                  // the partition depends on the geometry only
+        static int key_nd = 0, key_cuts[MAX_DEV + 1];
+        const monte_fdk_geom cg = canon_geom(g);
+        if (key_nd != nd || memcmp(&key, &cg, sizeof(cg)) != 0) {
+            std::vector<double> cost;
+            fdk_slice_cost(g, cost);
+            balanced_cuts(cost, nd, 16, key_cuts);
+            key = cg; key_nd = nd;
+        }
+        memcpy(cuts, key_cuts, sizeof(cuts));
+    }
+    FdkMultiDev dv[MAX_DEV];
+    PairSrc src;
+    src.n = nd;
+    int rc = MONTE_OK, launches = 0;
+    // ---- phase 1 on every device: upload | filter
+    for (int i = 0; i < nd && rc == MONTE_OK; i++) {
+        FdkMultiDev &d = dv[i];
+        d.v_lo = (int)((long long)g->n_views * i / nd); d.v_hi = (int)((long long)g->n_views * (i + 1) / nd);
+        d.z_lo = cuts[i]; d.z_hi = cuts[i + 1];
+        if ((rc = use_dev(i))) break;
+        Context &c = ctx();
+        cudaStream_t st = c.stream, cp = c.copy_stream;
+        const int nvw = d.v_hi - d.v_lo;
+        d.d_map = (float *)scratch(0, (size_t)(nvw ? nvw : 1) * per_view * sizeof(float));
+        d.d_filt = (float *)scratch(1, ((size_t)nvw * g->nv + 2) * pitch * sizeof(float));
+        d.d_vol = (float *)scratch(2, (size_t)(d.z_hi > d.z_lo ? d.z_hi - d.z_lo : 1) * slice * sizeof(float));
+        if (!d.d_map || !d.d_filt || !d.d_vol) { rc = MONTE_E_NOMEM; break; }
+        if ((rc = fdk_prepare(g, st))) break;
+        src.base[i] = d.d_filt - (size_t)d.v_lo * g->nv * pitch;    // virtual base: row R of the global layout at base + R * pitch
+        src.v_end[i] = d.v_hi;
+        FdkDevState &ds = g_fdk_state.get();
+        if (!ds.ev_up[0]) {
+            for (int k = 0; k < FDK_MAXC && rc == MONTE_OK; k++)
+                if (cudaEventCreateWithFlags(&ds.ev_up[k], cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&ds.ev_slab[k], cudaEventDisableTiming) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__);
+            for (int k = 0; k < 6 && rc == MONTE_OK; k++)
+                if (cudaEventCreate(&ds.ev_t[k]) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__);
+            if (rc) break;
+        }
+        d.t_f = new EventTimer(st); d.t_b = new EventTimer(st);
+        d.t_f->start();
+        if (cudaEventRecord(ds.ev_t[0], st) != cudaSuccess || cudaStreamWaitEvent(cp, ds.ev_t[0], 0) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__); break; }
+        const int n_up = nvw >= 16 ? 4 : 1;
+        for (int k = 0; k < n_up && rc == MONTE_OK && nvw > 0; k++) {
+            const int a = d.v_lo + (int)((long long)nvw * k / n_up), b = d.v_lo + (int)((long long)nvw * (k + 1) / n_up);
+            if (b <= a) continue;
+            if (cudaMemcpyAsync(d.d_map + (size_t)(a - d.v_lo) * per_view, map + (size_t)a * per_view, (size_t)(b - a) * per_view * sizeof(float),
+                                cudaMemcpyHostToDevice, cp) != cudaSuccess ||
+                cudaEventRecord(ds.ev_up[k], cp) != cudaSuccess || cudaStreamWaitEvent(st, ds.ev_up[k], 0) != cudaSuccess) {
+                rc = cuda_fail(cudaGetLastError(), "upload of a view chunk", __FILE__, __LINE__); break;
+            }
+            // the filter addresses maps and rows by absolute view: hand it the virtual bases
+            rc = monte_gpu_fdk_filter_dev(g, d.d_map - (size_t)d.v_lo * per_view, a, b, d.d_filt - (size_t)d.v_lo * g->nv * pitch, st);
+            launches++;
+        }
+        if (rc) break;
+        d.t_f->stop();
+        if (cudaEventCreateWithFlags(&d.filtered, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(d.filtered, st) != cudaSuccess)
+            rc = cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__);
+    }
+    // ---- phase 2 on every device: wait for everybody's filtered rows | gather band + backproject | download
+    for (int i = 0; i < nd && rc == MONTE_OK; i++) {
+        FdkMultiDev &d = dv[i];
+        if ((rc = use_dev(i))) break;
+        Context &c = ctx();
+        cudaStream_t st = c.stream, cp = c.copy_stream;
+        FdkDevState &ds = g_fdk_state.get();
+        for (int j = 0; j < nd && rc == MONTE_OK; j++)
+            if (j != i && cudaStreamWaitEvent(st, dv[j].filtered, 0) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaStreamWaitEvent", __FILE__, __LINE__);
+        if (rc) break;
+        d.t_b->start();
+        const int nz_i = d.z_hi - d.z_lo;
+        const int n_part = nz_i >= 64 ? 2 : 1;                      // two pieces: the first goes home while the second is computed
+        for (int q = 0; q < n_part && rc == MONTE_OK && nz_i > 0; q++) {
+            int z0 = d.z_lo + (int)((long long)nz_i * q / n_part), z1 = d.z_lo + (int)((long long)nz_i * (q + 1) / n_part);
+            if (q > 0) z0 = z0 / 16 * 16;
+            if (q < n_part - 1) z1 = z1 / 16 * 16;
+            if (z1 <= z0) continue;
+            float *dst = d.d_vol + (size_t)(z0 - d.z_lo) * slice;
+            if ((rc = backproject_views(g, nullptr, z0, z1, dst, st, 0, g->n_views, false, &src))) break;
+            launches += 2;
+            if (cudaEventRecord(ds.ev_slab[q], st) != cudaSuccess || cudaStreamWaitEvent(cp, ds.ev_slab[q], 0) != cudaSuccess ||
+                cudaMemcpyAsync(vol_xy + (size_t)z0 * slice, dst, (size_t)(z1 - z0) * slice * sizeof(float), cudaMemcpyDeviceToHost, cp) != cudaSuccess)
+                rc = cuda_fail(cudaGetLastError(), "download of a slab", __FILE__, __LINE__);
+        }
+        if (rc) break;
+        d.t_b->stop();
+        if (vol_zy && nz_i > 0) {                                   // image_zy[s][t][z] (bp3d20.cpp:161): this slab's z-columns
+            float *d_zy = (float *)scratch(3, (size_t)nz_i * slice * sizeof(float));
+            if (!d_zy) { rc = MONTE_E_NOMEM; break; }
+            dim3 grid(ceil_div(g->nx, 32), ceil_div(nz_i, 32), g->ny);
+            fdk_transpose_kernel MONTE_CFG(grid, dim3(32, 8), 0, st)(d.d_vol, d_zy, g->nx, g->ny, nz_i);
+            launches++;
+            if (cudaGetLastError() != cudaSuccess ||
+                cudaMemcpy2DAsync(vol_zy + d.z_lo, (size_t)g->nz * sizeof(float), d_zy, (size_t)nz_i * sizeof(float), (size_t)nz_i * sizeof(float),
+                                  slice, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "transposed slab", __FILE__, __LINE__);
+        }
+    }
+    // ---- the filtered maps, if wanted: every device sends its own views (after all peers have read them? they are only read)
+    for (int i = 0; i < nd && rc == MONTE_OK && filtered; i++) {
+        FdkMultiDev &d = dv[i];
+        if ((rc = use_dev(i))) break;
+        cudaStream_t st = ctx().stream;
+        const size_t rows = (size_t)(d.v_hi - d.v_lo) * g->nv, n = rows * g->nu;
+        if (!n) continue;
+        fdk_unpad_kernel MONTE_CFG((unsigned)((n + 255) / 256), 256, 0, st)(d.d_filt, d.d_map, rows, g->nu, pitch);   // d_map is free now
+        launches++;
+        if (cudaGetLastError() != cudaSuccess ||
+            cudaMemcpyAsync(filtered + (size_t)d.v_lo * per_view, d.d_map, n * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            rc = cuda_fail(cudaGetLastError(), "download of the filtered views", __FILE__, __LINE__);
+    }
+    for (int i = 0; i < nd; i++) {                                   // (also after an error: nothing may stay in flight)
+        if (use_dev(i) != MONTE_OK) continue;
+        cudaError_t e = cudaStreamSynchronize(ctx().stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().copy_stream);
+        if (e != cudaSuccess && rc == MONTE_OK) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    }
+    if (rc == MONTE_OK && stats) {
+        memset(stats, 0, sizeof(*stats));
+        for (int i = 0; i < nd; i++) {
+            use_dev(i);
+            if (dv[i].t_f) stats->ms_filter = fmax(stats->ms_filter, dv[i].t_f->ms());          // incl. the overlapped uploads
+            if (dv[i].t_b) stats->ms_backproject = fmax(stats->ms_backproject, dv[i].t_b->ms());
+        }
+        stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
+        stats->ms_d2h = fmax(0.0, stats->ms_total - stats->ms_filter - stats->ms_backproject);   // what compute did not hide (host clock)
+        stats->voxel_updates = (uint64_t)(g->s_end - g->s_begin) * (g->t_end - g->t_begin) * (g->z_end - g->z_begin) * g->n_views;
+        stats->filter_macs = (uint64_t)g->n_views * g->nv * g->nu * g->nu;
+        stats->launches = launches; stats->sm_count = ctx_of(0).sm_count;
+    }
+    for (int i = 0; i < nd; i++) {
+        if (use_dev(i) != MONTE_OK) continue;
+        delete dv[i].t_f; delete dv[i].t_b;
+        if (dv[i].filtered) cudaEventDestroy(dv[i].filtered);
+    }
+    use_dev(0);
+    return rc;
+}
+
 // Host-buffer pipeline: the drop-in for bp3d20.cpp:29-171.
 int monte_gpu_fdk(const monte_fdk_geom *g, const float *map, float *filtered, float *vol_xy, float *vol_zy,
                   monte_fdk_stats *stats) {
     MONTE_REQUIRE_INIT();
     if (int rc = check_geom(g)) return rc;
     MONTE_ARG(map && vol_xy, "fdk: map and vol_xy must not be NULL");
+    if (n_dev() > 1) return fdk_multi(g, map, filtered, vol_xy, vol_zy, stats);
     Context &c = ctx();
     cudaStream_t st = c.stream, cp = c.copy_stream;
     const size_t per_view = (size_t)g->nu * g->nv;
@@ -898,7 +1197,8 @@ int monte_gpu_fdk(const monte_fdk_geom *g, const float *map, float *filtered, fl
     // chunk, and downloads finished z-slabs while the next slab is backprojected.  With pinned host
     // buffers the copies are truly asynchronous; with pageable ones they still overlap the kernels.
     constexpr int MAXC = FDK_MAXC;
-    cudaEvent_t *ev_up = g_ev_up, *ev_slab = g_ev_slab, *ev_t = g_ev_t;     // destroyed by fdk_cleanup at shutdown
+    FdkDevState &ds = g_fdk_state.get();
+    cudaEvent_t *ev_up = ds.ev_up, *ev_slab = ds.ev_slab, *ev_t = ds.ev_t;   // destroyed by fdk_cleanup at shutdown
     if (!ev_up[0]) {
         for (int i = 0; i < MAXC; i++) {
             MONTE_CUDA(cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming));

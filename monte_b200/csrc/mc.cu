@@ -16,8 +16,11 @@
 // The oracle (oracle/mc_oracle.c, quirks=0, Philox mode) consumes the same variates in the same
 // order; tests compare the two history by history.
 #include "common.cuh"
+#include "nccl_dl.cuh"
 #include <cmath>
+#include <chrono>
 #include <cstdlib>
+#include <thread>
 
 namespace monte {
 
@@ -603,6 +606,46 @@ __global__ void counts_to_map_kernel(const int32_t *counts, size_t n, int32_t pe
     map[i] = (float)(-log((double)c) + (double)log_per);
 }
 
+// Multi-device tally reduction fused with the counts -> map epilogue (SURVEY 8e + row A12): ONE kernel on the root
+// device sums the int32 tallies of up to MAX_DEV - 1 peer devices straight out of their memory (NVLink P2P loads,
+// 128-bit, coalesced) into its own, and -- when maps are wanted -- applies CBCT_real325im.cu:267-285 to the sum in
+// the same pass.  n covers [image0 | image5] of the requested views, so there is one launch per call.
+struct TallyPeers {
+    const int32_t *p[MAX_DEV];
+    int n;
+};
+__global__ void tally_reduce_map_kernel(const TallyPeers peers, int32_t *counts, size_t n, int32_t per, float log_per, float *map) {
+    const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= n) return;
+    int c[4];
+    if (i4 + 4 <= n) {
+        const int4 v = *reinterpret_cast<const int4 *>(counts + i4);
+        c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+        for (int k = 0; k < peers.n; k++) {
+            const int4 w = *reinterpret_cast<const int4 *>(peers.p[k] + i4);
+            c[0] += w.x; c[1] += w.y; c[2] += w.z; c[3] += w.w;
+        }
+        if (peers.n) *reinterpret_cast<int4 *>(counts + i4) = make_int4(c[0], c[1], c[2], c[3]);
+    } else {
+        for (int j = 0; j < 4; j++) {
+            if (i4 + j >= n) { c[j] = 1; continue; }
+            c[j] = counts[i4 + j];
+            for (int k = 0; k < peers.n; k++) c[j] += peers.p[k][i4 + j];
+            if (peers.n) counts[i4 + j] = c[j];
+        }
+    }
+    if (!map) return;
+    float m[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int q = min(c[j], per);
+        if (q == 0) q = 1;
+        m[j] = (float)(-log((double)q) + (double)log_per);
+    }
+    if (i4 + 4 <= n) *reinterpret_cast<float4 *>(map + i4) = make_float4(m[0], m[1], m[2], m[3]);
+    else for (int j = 0; j < 4 && i4 + j < n; j++) map[i4 + j] = m[j];
+}
+
 }  // namespace monte
 
 using namespace monte;
@@ -610,6 +653,7 @@ using namespace monte;
 // ------------------------------------------------------------------------------------------------
 // scene
 // ------------------------------------------------------------------------------------------------
+constexpr unsigned MC_WORK_RING = 16;
 struct monte_mc_scene {
     McSceneDev dev;
     monte_mc_geom geom;
@@ -626,7 +670,13 @@ struct monte_mc_scene {
     int n_mat_host = 0;
     uint64_t clear_hash = 0;                                           // labels the resident grid was built from
     int clear_key[6] = {0, 0, 0, -1, -1, -1};                          // nx, ny, nz, cell_log2, heavy, n_materials
+    uint64_t labels_hash = 0;                                          // content hash of the resident labels (0: unknown)
+    size_t labels_n = 0;
+    // work-unit counters: one per launch out of a ring, so that launches of one scene that overlap on different
+    // streams do not share (and re-zero) a counter.  More than MC_WORK_RING launches of one scene in flight at
+    // once are not supported.
     unsigned long long *d_work = nullptr;
+    mutable unsigned work_next = 0;
     size_t smem = 0;
     size_t h2d_bytes = 0;
 };
@@ -671,6 +721,36 @@ static int check_mc(const monte_mc_geom *g, const monte_mc_volume *vol, const mo
     return MONTE_OK;
 }
 
+// energies must index the tables (1..200 keV) and the majorant must be positive wherever a photon can be: a zero
+// majorant makes every Woodcock step zero-length and the persistent kernel would never finish
+static int check_spectrum(const monte_mc_xs *xs, const monte_mc_spectrum *spec) {
+    double e_max = 140.0;                                              // spec == NULL: the shipped 140 keV
+    if (spec) {
+        MONTE_ARG(spec->n_bins >= 0 && spec->n_bins <= 4096, "mc: bad spectrum (n_bins = %d)", spec->n_bins);
+        if (spec->n_bins == 0) {
+            MONTE_ARG(spec->mono_keV > 0 && spec->mono_keV <= MONTE_MC_TABLE_ROWS - 1, "mc: mono_keV must be in (0, %d] (got %g)",
+                      MONTE_MC_TABLE_ROWS - 1, spec->mono_keV);
+            e_max = spec->mono_keV;
+        } else {
+            MONTE_ARG(spec->cdf != nullptr, "mc: spectrum has bins but no cdf");
+            MONTE_ARG(spec->bin_keV > 0 && spec->n_bins * spec->bin_keV <= MONTE_MC_TABLE_ROWS - 1,
+                      "mc: spectrum must end at or below %d keV (n_bins * bin_keV = %g)", MONTE_MC_TABLE_ROWS - 1, spec->n_bins * spec->bin_keV);
+            e_max = spec->n_bins * spec->bin_keV;
+            if (spec->mono_keV > e_max) e_max = spec->mono_keV;        // fallback energy of an incomplete cdf (:497)
+            MONTE_ARG(e_max <= MONTE_MC_TABLE_ROWS - 1, "mc: mono_keV (cdf fallback) above %d keV", MONTE_MC_TABLE_ROWS - 1);
+        }
+    }
+    // Compton scattering only lowers the energy: rows 1 .. round(e_max) are reachable (row 0 only below 0.5 keV,
+    // where the tables end; it is checked too because the kernel clamps to it)
+    const int k_hi = (int)(e_max + 0.5);
+    for (int k = 0; k <= k_hi && k < MONTE_MC_TABLE_ROWS; k++) {
+        double mumax = 0;
+        for (int m = 0; m < xs->n_materials; m++) mumax = fmax(mumax, (double)xs->total[m][k] * (double)xs->density[m]);
+        MONTE_ARG(mumax > 0 && mumax < 1e30, "mc: the Woodcock majorant is %g at %d keV (tables must be positive up to the highest source energy)", mumax, k);
+    }
+    return MONTE_OK;
+}
+
 extern "C" {
 
 static int grow(void **p, size_t *cap, size_t bytes) {
@@ -685,7 +765,7 @@ static int grow(void **p, size_t *cap, size_t bytes) {
 // 64-bit content hash of the label volume (four interleaved multiply-xorshift lanes, ~2 ms for 325^3): the
 // host-buffer entry point re-uploads the scene on every call, and rebuilding the clearance grid (25-110 ms) for
 // labels that have not changed would cost more than the transport itself
-static uint64_t hash_labels(const uint8_t *p, size_t n) {
+static uint64_t hash_labels_1(const uint8_t *p, size_t n) {
     uint64_t h[4] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0x27D4EB2F165667C5ull};
     size_t i = 0;
     for (; i + 32 <= n; i += 32) {
@@ -703,11 +783,28 @@ static uint64_t hash_labels(const uint8_t *p, size_t n) {
     return r;
 }
 
+// the same on four host threads for volumes of 8 MB and more (325^3: 2 ms -> 0.6 ms)
+static uint64_t hash_labels(const uint8_t *p, size_t n) {
+    constexpr int T = 4;
+    if (n < (8u << 20)) return hash_labels_1(p, n);
+    uint64_t h[T];
+    std::thread th[T];
+    const size_t part = (n / T) & ~(size_t)63;
+    for (int t = 0; t < T; t++) {
+        const uint8_t *q = p + part * t;
+        const size_t m = t == T - 1 ? n - part * t : part;
+        th[t] = std::thread([q, m, &h, t] { h[t] = hash_labels_1(q, m); });
+    }
+    uint64_t r = n;
+    for (int t = 0; t < T; t++) { th[t].join(); r = (r ^ h[t]) * 0xD6E8FEB86659FD93ull; r ^= r >> 29; }
+    return r ? r : 1;
+}
+
 // clearance grid of the current labels (host transform) -> device; skipped when the resident grid was built from
 // the same labels, geometry and tables
-static int upload_clearance(monte_mc_scene *s, const uint8_t *labels, cudaStream_t st) {
+static int upload_clearance(monte_mc_scene *s, const uint8_t *labels, cudaStream_t st, uint64_t known_hash = 0) {
     const monte_mc_volume &v = s->vol;
-    const uint64_t hsh = hash_labels(labels, (size_t)v.nx * v.ny * v.nz);
+    const uint64_t hsh = known_hash ? known_hash : hash_labels(labels, (size_t)v.nx * v.ny * v.nz);
     const bool oct = v.tracking_mode == MONTE_MC_TRACK_DIRECTIONAL;
     const int key[6] = {v.nx, v.ny, v.nz, v.clearance_cell_log2 + (oct ? 100 : 0), s->heavy, s->n_mat_host};
     int32_t d[3];
@@ -730,13 +827,17 @@ static int upload_clearance(monte_mc_scene *s, const uint8_t *labels, cudaStream
 }
 
 // (re)fill a scene: device buffers are reused when large enough; copies are issued on `st`
+// labels_hash != 0: the caller has hashed `labels`; if the scene already holds exactly these bytes the 34 MB copy
+// (and a clearance-grid rebuild) is skipped.  0: always copied.
 static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_mc_volume *vol, const uint8_t *labels,
-                        const monte_mc_xs *xs, const monte_mc_spectrum *spec, cudaStream_t st) {
+                        const monte_mc_xs *xs, const monte_mc_spectrum *spec, cudaStream_t st, uint64_t labels_hash = 0) {
     s->geom = *g;
     McSceneDev &d = s->dev;
     const size_t nvox = (size_t)vol->nx * vol->ny * vol->nz;
     if (int rc = grow(&s->d_labels, &s->cap_labels, nvox)) return rc;
-    MONTE_CUDA(cudaMemcpyAsync(s->d_labels, labels, nvox, cudaMemcpyHostToDevice, st));
+    const bool labels_resident = labels_hash != 0 && s->labels_hash == labels_hash && s->labels_n == nvox;
+    if (!labels_resident) MONTE_CUDA(cudaMemcpyAsync(s->d_labels, labels, nvox, cudaMemcpyHostToDevice, st));
+    s->labels_hash = labels_hash; s->labels_n = nvox;
     d.labels = (const uint8_t *)s->d_labels;
     d.nx = vol->nx; d.ny = vol->ny; d.nz = vol->nz;
     d.inv_pitch = (float)(1.0 / vol->pitch);
@@ -795,7 +896,7 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
     if (s->heavy >= 0) {
         if (!s->d_invlo) MONTE_CUDA(cudaMalloc(&s->d_invlo, 2 * TAB_ROWS * sizeof(float)));
         MONTE_CUDA(cudaMemcpyAsync(s->d_invlo, invlo.data(), 2 * TAB_ROWS * sizeof(float), cudaMemcpyHostToDevice, st));
-        if (int rc = upload_clearance(s, labels, st)) return rc;
+        if (int rc = upload_clearance(s, labels, st, labels_hash)) return rc;
         clear_bytes = (size_t)s->cg[0] * s->cg[1] * s->cg[2] + 2 * TAB_ROWS * sizeof(float);
         MONTE_CUDA(cudaStreamSynchronize(st));                         // `invlo` is pageable and goes out of scope
     }
@@ -825,9 +926,9 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
     d.dso = (float)g->dso; d.dod = (float)g->dod; d.dsd = (float)(g->dso + g->dod);
     d.source_mode = g->source_mode; d.max_scatter = g->max_scatter;
     d.eid = g->detector_mode == MONTE_MC_DETECTOR_ENERGY ? 1 : 0;
-    if (!s->d_work) MONTE_CUDA(cudaMalloc(&s->d_work, sizeof(unsigned long long)));
+    if (!s->d_work) MONTE_CUDA(cudaMalloc(&s->d_work, MC_WORK_RING * sizeof(unsigned long long)));
     s->smem = (size_t)nm * TAB_ROWS * sizeof(float4) + (TAB_ROWS + 3 + d.n_bins + 1) * sizeof(float);
-    s->h2d_bytes = nvox + tab_bytes + inv_bytes + cdf_bytes + ray_bytes + clear_bytes + vcs.size() * sizeof(float2);
+    s->h2d_bytes = (labels_resident ? 0 : nvox) + tab_bytes + inv_bytes + cdf_bytes + ray_bytes + clear_bytes + vcs.size() * sizeof(float2);
     // the host vectors above are pageable: the async copies have already staged them
     MONTE_CUDA(cudaStreamSynchronize(st));
     return MONTE_OK;
@@ -838,7 +939,7 @@ int monte_gpu_scene_create(const monte_mc_geom *g, const monte_mc_volume *vol, c
     MONTE_REQUIRE_INIT();
     if (int rc = check_mc(g, vol, xs)) return rc;
     MONTE_ARG(labels && out, "mc: NULL argument");
-    MONTE_ARG(!spec || spec->n_bins == 0 || (spec->cdf && spec->n_bins > 0 && spec->n_bins <= 4096), "mc: bad spectrum");
+    if (int rc = check_spectrum(xs, spec)) return rc;
     monte_mc_scene *s = new monte_mc_scene();
     if (int rc = scene_upload(s, g, vol, labels, xs, spec, ctx().stream)) { monte_gpu_scene_destroy(s); return rc; }
     *out = s;
@@ -850,6 +951,7 @@ int monte_gpu_scene_update_labels(monte_mc_scene *s, const uint8_t *labels, void
     MONTE_ARG(s && labels, "scene_update_labels: NULL argument");
     const size_t nvox = (size_t)s->dev.nx * s->dev.ny * s->dev.nz;
     MONTE_CUDA(cudaMemcpyAsync(s->d_labels, labels, nvox, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    s->labels_hash = 0;
     if (s->heavy >= 0) return upload_clearance(s, labels, (cudaStream_t)stream);   // the grid follows the labels
     return MONTE_OK;
 }
@@ -871,13 +973,18 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     MONTE_ARG((uint64_t)s->geom.n_views * npix * per < (1ull << 40), "mc: more than 2^40 history ids");
     MONTE_ARG(!s->dev.eid || (uint64_t)per * (MONTE_MC_TABLE_ROWS - 1) * MONTE_MC_EID_SCALE < (1ull << 31),
               "mc: %u photons per pixel overflow an int32 energy tally", per);
+    // counting mode: a pixel receives at most its own `per` unscattered photons plus scattered ones from anywhere;
+    // below 2^30 per pixel the int32 tallies (the reference's type, CBCT_real325im.cu:104-105) cannot wrap in
+    // practice -- larger runs are split into several calls whose images the caller sums in 64 bits
+    MONTE_ARG(s->dev.eid || per < (1u << 30), "mc: %u photons per pixel could overflow the int32 tallies; split the run", per);
     McLaunch L;
     L.sc = s->dev;
     L.key = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u);
     L.view_begin = view_begin; L.n_begin = n_begin; L.cnt = n_end - n_begin; L.per = per;
     L.total = (unsigned long long)(view_end - view_begin) * npix * L.cnt;
     L.n_units = (L.total + MC_UNIT - 1) / MC_UNIT;
-    L.image0 = d_image0; L.image5 = d_image5; L.stats = d_stats; L.work = s->d_work;
+    L.image0 = d_image0; L.image5 = d_image5; L.stats = d_stats;
+    L.work = s->d_work + (s->work_next++ % MC_WORK_RING);
     L.fates = d_fates; L.fate_e = d_fate_e;
     L.ray = (const float *)s->d_ray; L.ray_n = s->ray_n;
     L.clear = (const uint8_t *)s->d_clear; L.inv_mulo = (const float *)s->d_invlo;
@@ -886,7 +993,7 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     L.coct = s->coct;
     { static int sm = -1; if (sm < 0) { const char *e = getenv("MONTE_MC_SECOND"); sm = e ? atoi(e) : 16; } L.second_min = (uint32_t)sm; }
     if (L.total == 0) return MONTE_OK;
-    MONTE_CUDA(cudaMemsetAsync(s->d_work, 0, sizeof(unsigned long long), st));
+    MONTE_CUDA(cudaMemsetAsync(L.work, 0, sizeof(unsigned long long), st));
     const int sms = ctx().sm_count;
     const unsigned long long warps_needed = L.n_units;
     // K = 5 parked histories per lane is the default (measured: K=4 9.83 ms, K=5 9.45 ms, K=6 11.2 ms per
@@ -932,9 +1039,11 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     }
     // resident CTAs per SM (persistent grid = SMs x occupancy) and the shared-memory attribute already raised, per
     // kernel variant; per-context state: forgotten at monte_gpu_shutdown (a later init may bind another device)
-    static int occ[96] = {0};
-    static size_t smem_set[96] = {0}, smem_occ[96] = {0};
-    at_shutdown([] { memset(occ, 0, sizeof(occ)); memset(smem_set, 0, sizeof(smem_set)); memset(smem_occ, 0, sizeof(smem_occ)); });
+    struct Attr { int occ[96] = {0}; size_t smem_set[96] = {0}, smem_occ[96] = {0}; };
+    static PerDev<Attr> attr_pd;                                       // function attributes are per device
+    at_shutdown([] { attr_pd.get() = Attr(); });
+    int *occ = attr_pd.get().occ;
+    size_t *smem_set = attr_pd.get().smem_set, *smem_occ = attr_pd.get().smem_occ;
     // 94, 95 (Rayleigh), 0..3 (clearance, clearance + Rayleigh): no `which` maps there (31..46 -> 62..93)
     const int slot_id = clear ? rec + (rayleigh ? 2 : 0) : rayleigh ? 94 + rec : (which * 2 + rec) % 96;
     int &oc = occ[slot_id];
@@ -977,8 +1086,10 @@ void monte_gpu_mc_stats_unpack(const unsigned long long *w, monte_mc_stats *out)
     out->sum_e_scatter = (double)w[ST_ESCAT] / 1024.0;
 }
 
-// scene kept between monte_gpu_simulate calls: device buffers are reused, contents re-uploaded
-static monte_mc_scene *g_host_scene = nullptr;
+// scene kept between monte_gpu_simulate calls, one per bound device: device buffers are reused, the tables are
+// re-uploaded, the label volume only when its content hash changed
+static PerDev<monte_mc_scene *> g_host_scene_pd;
+#define g_host_scene (g_host_scene_pd.get())
 static void mc_cleanup() {
     if (g_host_scene) monte_gpu_scene_destroy(g_host_scene);
     g_host_scene = nullptr;
@@ -987,56 +1098,156 @@ static void mc_cleanup() {
 int monte_gpu_simulate(const monte_mc_geom *g, const monte_mc_volume *vol, const uint8_t *labels, const monte_mc_xs *xs,
                        const monte_mc_spectrum *spec, uint32_t photons_per_pixel, uint64_t seed, int view_begin,
                        int view_end, int32_t *image0, int32_t *image5, monte_mc_stats *stats) {
-    return monte_gpu_simulate_range(g, vol, labels, xs, spec, photons_per_pixel, 0, photons_per_pixel, seed,
-                                    view_begin, view_end, image0, image5, stats);
+    return monte_gpu_simulate_maps(g, vol, labels, xs, spec, photons_per_pixel, 0, photons_per_pixel, seed,
+                                   view_begin, view_end, image0, image5, nullptr, nullptr, stats);
 }
 
 int monte_gpu_simulate_range(const monte_mc_geom *g, const monte_mc_volume *vol, const uint8_t *labels,
                              const monte_mc_xs *xs, const monte_mc_spectrum *spec, uint32_t photons_per_pixel,
                              uint32_t n_begin, uint32_t n_end, uint64_t seed, int view_begin, int view_end,
                              int32_t *image0, int32_t *image5, monte_mc_stats *stats) {
+    return monte_gpu_simulate_maps(g, vol, labels, xs, spec, photons_per_pixel, n_begin, n_end, seed, view_begin, view_end,
+                                   image0, image5, nullptr, nullptr, stats);
+}
+
+// The whole seam of the reference's main() (CBCT_real325im.cu:232-288) in one call, on every device bound by
+// monte_gpu_init: scene upload | photon range [n_begin, n_end) split evenly over the devices, one transport launch
+// each | tallies of the peers summed onto device 0 and turned into -log maps in the same pass | download.
+//   MONTE_MC_REDUCE=p2p  (default when all devices have peer access): tally_reduce_map_kernel, one launch on the
+//                        root that loads the peers' tallies over NVLink and fuses the clamp + log epilogue
+//   MONTE_MC_REDUCE=nccl: ONE ncclReduce(sum, int32) of [image0 | image5] to rank 0, then the epilogue kernel
+// Both give the bits of a single-device run (integer sums; history ids are global).
+int monte_gpu_simulate_maps(const monte_mc_geom *g, const monte_mc_volume *vol, const uint8_t *labels,
+                            const monte_mc_xs *xs, const monte_mc_spectrum *spec, uint32_t photons_per_pixel,
+                            uint32_t n_begin, uint32_t n_end, uint64_t seed, int view_begin, int view_end,
+                            int32_t *image0, int32_t *image5, float *map0, float *map5, monte_mc_stats *stats) {
     MONTE_REQUIRE_INIT();
     if (int rc = check_mc(g, vol, xs)) return rc;
     MONTE_ARG(labels && image0 && image5, "mc: NULL buffer");
-    MONTE_ARG(!spec || spec->n_bins == 0 || (spec->cdf && spec->n_bins > 0 && spec->n_bins <= 4096), "mc: bad spectrum");
-    if (view_begin == 0 && view_end == 0) view_end = g->n_views;
+    if (int rc = check_spectrum(xs, spec)) return rc;
+    if (view_end < 0) { MONTE_ARG(view_begin == 0, "mc: view_end < 0 (all views) needs view_begin == 0"); view_end = g->n_views; }
     MONTE_ARG(0 <= view_begin && view_begin <= view_end && view_end <= g->n_views, "mc: bad view range");
-    Context &c = ctx();
-    cudaStream_t st = c.stream;
-    EventTimer t_all(st), t_h2d(st), t_k(st), t_d2h(st);
-    t_all.start();
-    t_h2d.start();
-    if (!g_host_scene) { g_host_scene = new monte_mc_scene(); at_shutdown(mc_cleanup); }
-    monte_mc_scene *s = g_host_scene;
-    if (int rc = scene_upload(s, g, vol, labels, xs, spec, st)) return rc;
-    t_h2d.stop();
-    // tallies of the requested views only; the kernel indexes by absolute view
+    MONTE_ARG(n_begin <= n_end && n_end <= photons_per_pixel, "mc: bad photon range [%u,%u) of %u", n_begin, n_end, photons_per_pixel);
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (view_begin == view_end) return MONTE_OK;                         // [v, v) is empty: nothing is written
+    const int nd = n_dev();
+    const char *e_red = getenv("MONTE_MC_REDUCE"), *e_cache = getenv("MONTE_MC_LABEL_CACHE");   // read per call: tests flip them
+    const bool use_nccl = nd > 1 && ((e_red && !strcmp(e_red, "nccl")) || !peers_ok());
+    const int label_cache = e_cache ? atoi(e_cache) : 1;
+    const size_t nvox = (size_t)vol->nx * vol->ny * vol->nz;
+    const uint64_t lhash = label_cache ? hash_labels(labels, nvox) : 0;
     const size_t npix = (size_t)g->ny * g->nx, n_img = (size_t)(view_end - view_begin) * npix;
-    const size_t bytes = 2 * n_img * sizeof(int32_t) + MONTE_MC_STATS_WORDS * sizeof(unsigned long long);
-    int32_t *d_im = (int32_t *)scratch(5, bytes + 16);
-    if (!d_im) return MONTE_E_NOMEM;
-    unsigned long long *d_stats = (unsigned long long *)(((uintptr_t)(d_im + 2 * n_img) + 7) & ~(uintptr_t)7);
-    MONTE_CUDA(cudaMemsetAsync(d_im, 0, bytes + 16, st));
-    t_k.start();
-    if (int rc = launch_mc(s, seed, view_begin, view_end, n_begin, n_end, photons_per_pixel,
-                           d_im - (size_t)view_begin * npix, d_im + n_img - (size_t)view_begin * npix, d_stats,
-                           nullptr, nullptr, st)) return rc;
-    t_k.stop();
-    t_d2h.start();
-    unsigned long long w[MONTE_MC_STATS_WORDS];
-    MONTE_CUDA(cudaMemcpyAsync(image0 + (size_t)view_begin * npix, d_im, n_img * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    MONTE_CUDA(cudaMemcpyAsync(image5 + (size_t)view_begin * npix, d_im + n_img, n_img * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    MONTE_CUDA(cudaMemcpyAsync(w, d_stats, sizeof(w), cudaMemcpyDeviceToHost, st));
-    t_d2h.stop();
-    t_all.stop();
-    MONTE_CUDA(cudaStreamSynchronize(st));
-    if (stats) {
-        memset(stats, 0, sizeof(*stats));
-        monte_gpu_mc_stats_unpack(w, stats);
-        stats->ms_h2d = t_h2d.ms(); stats->ms_kernel = t_k.ms(); stats->ms_d2h = t_d2h.ms(); stats->ms_total = t_all.ms();
-        stats->launches = 1; stats->sm_count = c.sm_count;
+    const size_t n_cnt = 2 * n_img;
+    const bool want_maps = map0 || map5;
+    // per device: [image0 | image5] int32, then the stats words; on the root also the two float maps
+    const size_t off_stats = (n_cnt * sizeof(int32_t) + 15) & ~(size_t)15;
+    const size_t off_map = off_stats + MONTE_MC_STATS_WORDS * sizeof(unsigned long long);
+    const uint32_t cnt = n_end - n_begin;
+    struct Dev { int32_t *d_im = nullptr; unsigned long long *d_stats = nullptr; cudaEvent_t done = nullptr; unsigned long long w[MONTE_MC_STATS_WORDS] = {0}; } dv[MAX_DEV];
+    const auto t_host0 = std::chrono::steady_clock::now();
+    EventTimer *t_k[MAX_DEV] = {nullptr};
+    int rc = MONTE_OK;
+    for (int i = 0; i < nd && rc == MONTE_OK; i++) {
+        if ((rc = use_dev(i))) break;
+        Context &c = ctx();
+        cudaStream_t st = c.stream;
+        if (!g_host_scene) { g_host_scene = new monte_mc_scene(); at_shutdown(mc_cleanup); }
+        if ((rc = scene_upload(g_host_scene, g, vol, labels, xs, spec, st, lhash))) break;
+        char *base = (char *)scratch(5, off_map + (i == 0 && want_maps ? n_cnt * sizeof(float) : 0));
+        if (!base) { rc = MONTE_E_NOMEM; break; }
+        dv[i].d_im = (int32_t *)base;
+        dv[i].d_stats = (unsigned long long *)(base + off_stats);
+        if (cudaMemsetAsync(base, 0, off_map, st) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "cudaMemsetAsync", __FILE__, __LINE__); break; }
+        // photons [nb, ne) of every pixel on this device (contiguous balanced split, earlier devices take the extra)
+        const uint32_t q = cnt / nd, r = cnt % nd;
+        const uint32_t nb = n_begin + i * q + ((uint32_t)i < r ? i : r), ne = nb + q + ((uint32_t)i < r ? 1 : 0);
+        t_k[i] = new EventTimer(st);
+        t_k[i]->start();
+        rc = launch_mc(g_host_scene, seed, view_begin, view_end, nb, ne, photons_per_pixel,
+                       dv[i].d_im - (size_t)view_begin * npix, dv[i].d_im + n_img - (size_t)view_begin * npix, dv[i].d_stats,
+                       nullptr, nullptr, st);
+        t_k[i]->stop();
     }
-    return MONTE_OK;
+    // ---- reduce onto device 0 + counts -> maps
+    float *d_map = nullptr;
+    if (rc == MONTE_OK && (rc = use_dev(0)) == MONTE_OK) {
+        cudaStream_t st0 = ctx().stream;
+        d_map = want_maps ? (float *)((char *)dv[0].d_im + off_map) : nullptr;
+        const float log_per = logf((float)cnt);
+        do {
+            if (use_nccl) {
+                ncclComm_t *comms = nullptr;
+                if ((rc = nccl_comms(&comms))) break;
+                const NcclApi *n = nccl_api();
+                int r2 = n->GroupStart();
+                for (int i = 0; i < nd && r2 == 0; i++)
+                    r2 = n->Reduce(dv[i].d_im, dv[i].d_im, n_cnt, NCCL_INT32, NCCL_SUM, 0, comms[i], ctx_of(i).stream);
+                const int r3 = n->GroupEnd();
+                if (r2 || r3) { set_error("ncclReduce of the tallies failed: %s", n->GetErrorString(r2 ? r2 : r3)); rc = MONTE_E_CUDA; break; }
+            } else if (nd > 1) {
+                // the root's stream waits for the peers' transport kernels (events work across devices)
+                for (int i = 1; i < nd; i++) {
+                    use_dev(i);
+                    if (cudaEventCreateWithFlags(&dv[i].done, cudaEventDisableTiming) != cudaSuccess ||
+                        cudaEventRecord(dv[i].done, ctx().stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__); break; }
+                }
+                use_dev(0);
+                for (int i = 1; i < nd && rc == MONTE_OK; i++)
+                    if (cudaStreamWaitEvent(st0, dv[i].done, 0) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaStreamWaitEvent", __FILE__, __LINE__);
+                if (rc) break;
+            }
+            if ((nd > 1 && !use_nccl) || want_maps) {
+                TallyPeers tp;
+                tp.n = use_nccl ? 0 : nd - 1;
+                for (int i = 0; i < tp.n; i++) tp.p[i] = dv[i + 1].d_im;
+                tally_reduce_map_kernel MONTE_CFG((unsigned)((n_cnt / 4 + 1 + 255) / 256), 256, 0, st0)(tp, dv[0].d_im, n_cnt, (int32_t)cnt, log_per, d_map);
+                if (cudaGetLastError() != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "tally_reduce_map_kernel", __FILE__, __LINE__); break; }
+            }
+        } while (0);
+    }
+    // ---- download (root: images and maps; every device: its counters)
+    EventTimer *t_d2h = nullptr;
+    if (rc == MONTE_OK) {
+        cudaStream_t st0 = ctx().stream;
+        t_d2h = new EventTimer(st0);
+        t_d2h->start();
+        cudaMemcpyAsync(image0 + (size_t)view_begin * npix, dv[0].d_im, n_img * sizeof(int32_t), cudaMemcpyDeviceToHost, st0);
+        cudaMemcpyAsync(image5 + (size_t)view_begin * npix, dv[0].d_im + n_img, n_img * sizeof(int32_t), cudaMemcpyDeviceToHost, st0);
+        if (map0) cudaMemcpyAsync(map0 + (size_t)view_begin * npix, d_map, n_img * sizeof(float), cudaMemcpyDeviceToHost, st0);
+        if (map5) cudaMemcpyAsync(map5 + (size_t)view_begin * npix, d_map + n_img, n_img * sizeof(float), cudaMemcpyDeviceToHost, st0);
+        t_d2h->stop();
+        for (int i = 0; i < nd; i++) {
+            use_dev(i);
+            cudaMemcpyAsync(dv[i].w, dv[i].d_stats, sizeof(dv[i].w), cudaMemcpyDeviceToHost, ctx().stream);
+        }
+        for (int i = 0; i < nd; i++) {
+            use_dev(i);
+            const cudaError_t e = cudaStreamSynchronize(ctx().stream);
+            if (e != cudaSuccess && rc == MONTE_OK) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+        }
+    } else {
+        for (int i = 0; i < nd; i++) { if (use_dev(i) == MONTE_OK) cudaStreamSynchronize(ctx().stream); }
+    }
+    const double ms_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
+    if (rc == MONTE_OK && stats) {
+        unsigned long long w[MONTE_MC_STATS_WORDS] = {0};
+        for (int i = 0; i < nd; i++) for (int k = 0; k < MONTE_MC_STATS_WORDS; k++) w[k] += dv[i].w[k];
+        monte_gpu_mc_stats_unpack(w, stats);
+        for (int i = 0; i < nd; i++) if (t_k[i]) { use_dev(i); stats->ms_kernel = fmax(stats->ms_kernel, t_k[i]->ms()); }
+        use_dev(0);
+        stats->ms_d2h = t_d2h ? t_d2h->ms() : 0;
+        stats->ms_total = ms_host;
+        stats->ms_h2d = fmax(0.0, ms_host - stats->ms_kernel - stats->ms_d2h);   // scene upload + hashing (host clock)
+        stats->launches = nd + ((nd > 1 && !use_nccl) || want_maps ? 1 : 0); stats->sm_count = ctx_of(0).sm_count;
+    }
+    for (int i = 0; i < nd; i++) {
+        if (use_dev(i) != MONTE_OK) continue;
+        delete t_k[i];
+        if (dv[i].done) cudaEventDestroy(dv[i].done);
+    }
+    use_dev(0);
+    delete t_d2h;
+    return rc;
 }
 
 int monte_gpu_simulate_fates(const monte_mc_scene *s, uint64_t seed, int view, uint32_t photons_per_pixel,

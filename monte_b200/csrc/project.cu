@@ -275,7 +275,7 @@ extern "C" int monte_gpu_project_primary(const monte_mc_geom *g, const monte_mc_
     MONTE_ARG(g->n_views > 0 && g->ny > 0 && g->nx > 0 && g->pixel > 0, "project_primary: bad detector");
     MONTE_ARG(vol->nx > 0 && vol->ny > 0 && vol->nz > 0 && vol->pitch > 0, "project_primary: bad volume");
     MONTE_ARG(xs->n_materials >= 1 && xs->n_materials <= MONTE_MC_MAX_MATERIALS, "project_primary: bad materials");
-    if (view_begin == 0 && view_end == 0) view_end = g->n_views;
+    if (view_end < 0) { MONTE_ARG(view_begin == 0, "project_primary: view_end < 0 (all views) needs view_begin == 0"); view_end = g->n_views; }
     MONTE_ARG(0 <= view_begin && view_begin <= view_end && view_end <= g->n_views, "project_primary: bad view range");
     if (view_begin == view_end) return MONTE_OK;
     cudaStream_t st = ctx().stream;

@@ -1,6 +1,8 @@
 // cbct_fdk — the role of the main() of recon/bp3d20.cpp / bp3d20_325.cpp / fbp2.cpp: read a float32
 // map [views][nu][nv], reconstruct, write xy / zy volumes and the filtered map (bp3d20.cpp:170-190).
-//   cbct_fdk bp3d20|bp3d20_325|fbp2 map.raw [tag=out] [--full]      (--full: whole volume, not s in [125,130))
+//   cbct_fdk bp3d20|bp3d20_325|fbp2 map.raw [tag=out] [--full] [--gpus G]   (--full: whole volume, not s in [125,130))
+// --gpus G (1..8): filter sharded by views, backprojection by z-slabs over G devices inside libmonte_gpu
+// (monte_gpu_init(G, NULL)); the output files are byte-identical to --gpus 1.  fbp2 (2-D) runs on one device.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,7 +21,11 @@ int main(int argc, char **argv) {
     if (argc < 3) { fprintf(stderr, "usage: cbct_fdk bp3d20|bp3d20_325|fbp2 map.raw [tag] [--full]\n"); return 2; }
     const std::string prog = argv[1], tag = argc > 3 && argv[3][0] != '-' ? argv[3] : "out";
     bool full = false;
-    for (int i = 3; i < argc; i++) if (!strcmp(argv[i], "--full")) full = true;
+    int gpus = 1;
+    for (int i = 3; i < argc; i++) {
+        if (!strcmp(argv[i], "--full")) full = true;
+        if (!strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = atoi(argv[i + 1]);
+    }
     monte_fdk_geom g;
     if (prog == "bp3d20") monte_fdk_geom_bp3d20(&g);
     else if (prog == "bp3d20_325") monte_fdk_geom_bp3d20_325(&g);
@@ -31,7 +37,7 @@ int main(int argc, char **argv) {
     FILE *f = fopen(argv[2], "rb");
     if (!f || fread(map.data(), sizeof(float), n_map, f) != n_map) { fprintf(stderr, "failed to read %s\n", argv[2]); return 1; }
     fclose(f);
-    if (monte_gpu_init(1, nullptr)) return fail();
+    if (monte_gpu_init(prog == "fbp2" ? 1 : gpus, nullptr)) return fail();
     monte_fdk_stats st;
     if (prog == "fbp2") {
         if (monte_gpu_fbp2(&g, 1, map.data(), filt.data(), xy.data(), &st)) return fail();

@@ -1,7 +1,9 @@
 // cbct_mc — the role of the main() of monte_cu/CBCT_real325im.cu (:83-297): read the label volume and
 // the cross-section tables, run the photon transport, write the count images and the -log maps in
 // the reference's headerless layouts (proj*_0 / proj*_5 int32, map*_0 / map*_5 float32, [view][y][x]).
-//   cbct_mc labels.raw N pitch_cm xcom2.csv Ca.csv [det=325] [pixel=0.1] [views=360] [per=10000] [seed=0] [tag=out] [rayleigh=0] [clearance=0]
+//   cbct_mc labels.raw N pitch_cm xcom2.csv Ca.csv [det=325] [pixel=0.1] [views=360] [per=10000] [seed=0] [tag=out] [rayleigh=0] [clearance=0] [--gpus G]
+// --gpus G (1..8): the photons of every pixel are split over G devices inside libmonte_gpu and the tallies summed on
+// device 0 (monte_gpu_init(G, NULL)); the output files are byte-identical to --gpus 1.
 // rayleigh=1 (not in the reference): coherent events are deflected by the analytic form factor of
 // monte_xs_formfactor_hydrogenic (x0 = 1.0 for water, 2.2 for calcium) instead of flying straight on.
 // clearance=n > 0 (not in the reference): two-level Woodcock majorant with clearance cells of 2^n voxels
@@ -9,6 +11,7 @@
 // All compute is in libmonte_gpu (no CPU fallback: the call fails without a B200).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <string>
 #include <vector>
@@ -22,7 +25,10 @@ static void write_raw(const std::string &fn, const void *p, size_t bytes) {
 }
 
 int main(int argc, char **argv) {
-    if (argc < 6) { fprintf(stderr, "usage: cbct_mc labels.raw N pitch xcom2.csv Ca.csv [det] [pixel] [views] [per] [seed] [tag] [rayleigh] [clearance]\n"); return 2; }
+    int gpus = 1;
+    for (int i = 1; i + 1 < argc; i++)
+        if (!strcmp(argv[i], "--gpus")) { gpus = atoi(argv[i + 1]); for (int j = i; j + 2 < argc; j++) argv[j] = argv[j + 2]; argc -= 2; break; }
+    if (argc < 6) { fprintf(stderr, "usage: cbct_mc labels.raw N pitch xcom2.csv Ca.csv [det] [pixel] [views] [per] [seed] [tag] [rayleigh] [clearance] [--gpus G]\n"); return 2; }
     const int n = atoi(argv[2]);
     const double pitch = atof(argv[3]);
     const int det = argc > 6 ? atoi(argv[6]) : 325;
@@ -52,21 +58,22 @@ int main(int argc, char **argv) {
     for (int a = 0; a < 3; a++) { v.origin[a] = -0.5 * n * pitch; v.clip_lo[a] = v.origin[a]; v.clip_hi[a] = -v.origin[a]; }
     if (clearance > 0) { v.tracking_mode = MONTE_MC_TRACK_CLEARANCE; v.clearance_cell_log2 = clearance; }
     monte_mc_spectrum sp = {0, 0.5, 140.0, nullptr};                                              // as shipped: 140 keV
-    if (monte_gpu_init(1, nullptr)) return fail();
+    if (monte_gpu_init(gpus, nullptr)) return fail();
     const size_t n_img = (size_t)views * det * det;
     std::vector<int32_t> im0(n_img), im5(n_img);
-    std::vector<float> map(n_img);
+    std::vector<float> map0(n_img), map5(n_img);
     monte_mc_stats st;
-    if (monte_gpu_simulate(&g, &v, lab.data(), xs.get(), &sp, per, seed, 0, views, im0.data(), im5.data(), &st)) return fail();
-    printf("count = %llu primaries + %llu scattered / %llu histories, %.1f ms on the GPU (%.3g histories/s)\n",
+    // launch .. D2H .. clamp + -log maps (CBCT_real325im.cu:232-288) in one call: the maps come out of the pass that
+    // sums the per-device tallies
+    if (monte_gpu_simulate_maps(&g, &v, lab.data(), xs.get(), &sp, per, 0, per, seed, 0, views, im0.data(), im5.data(),
+                                map0.data(), map5.data(), &st)) return fail();
+    printf("count = %llu primaries + %llu scattered / %llu histories, %.1f ms on %d GPU%s (%.3g histories/s)\n",
            (unsigned long long)st.primaries, (unsigned long long)st.scatter_detected, (unsigned long long)st.histories,
-           st.ms_kernel, st.histories / (st.ms_kernel * 1e-3));
+           st.ms_kernel, gpus, gpus > 1 ? "s" : "", st.histories / (st.ms_kernel * 1e-3));
     write_raw("proj_" + tag + "0.raw", im0.data(), n_img * 4);
     write_raw("proj_" + tag + "5.raw", im5.data(), n_img * 4);
-    if (monte_gpu_counts_to_map(im0.data(), n_img, (int32_t)per, map.data())) return fail();
-    write_raw("map_" + tag + "0.raw", map.data(), n_img * 4);
-    if (monte_gpu_counts_to_map(im5.data(), n_img, (int32_t)per, map.data())) return fail();
-    write_raw("map_" + tag + "5.raw", map.data(), n_img * 4);
+    write_raw("map_" + tag + "0.raw", map0.data(), n_img * 4);
+    write_raw("map_" + tag + "5.raw", map5.data(), n_img * 4);
     monte_gpu_shutdown();
     return 0;
 }

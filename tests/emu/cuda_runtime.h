@@ -189,7 +189,7 @@ static inline unsigned long max(unsigned long a, unsigned long b) { return a > b
 
 // ---- runtime API (the subset libmonte_gpu uses) -------------------------------------------------------
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1, cudaErrorPeerAccessAlreadyEnabled = 704 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
@@ -207,6 +207,8 @@ cudaError_t cudaGetLastError();
 cudaError_t cudaGetDeviceCount(int *n);
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int dev);
 cudaError_t cudaSetDevice(int dev);
+cudaError_t cudaDeviceCanAccessPeer(int *can, int dev, int peer);
+cudaError_t cudaDeviceEnablePeerAccess(int peer, unsigned flags);
 cudaError_t cudaDeviceSynchronize();
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned flags);
 cudaError_t cudaStreamDestroy(cudaStream_t s);
@@ -223,6 +225,7 @@ template <class T> static inline cudaError_t cudaMalloc(T **p, size_t bytes) { r
 cudaError_t cudaFree(void *p);
 cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, cudaMemcpyKind kind, cudaStream_t s);
 cudaError_t cudaMemsetAsync(void *dst, int value, size_t n, cudaStream_t s);
+cudaError_t cudaMemcpy2DAsync(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, cudaMemcpyKind kind, cudaStream_t s);
 template <class T> static inline cudaError_t cudaFuncSetAttribute(T, cudaFuncAttribute, int) { return cudaSuccess; }
 template <class T> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, T, int, size_t) {
     *n = 1;

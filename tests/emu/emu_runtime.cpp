@@ -188,7 +188,13 @@ static double now_ms() {
 }
 const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : e == cudaErrorMemoryAllocation ? "out of memory" : "error"; }
 cudaError_t cudaGetLastError() { return cudaSuccess; }
-cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+// MONTE_EMU_DEVICES=n: n "devices" that all are this host's memory -- enough to drive the multi-device orchestration
+// (per-device contexts, photon / view / z-slab partition, peer loads, NCCL call pattern) on the CPU
+static int emu_device_count() { const char *e = getenv("MONTE_EMU_DEVICES"); const int n = e ? atoi(e) : 1; return n < 1 ? 1 : (n > 8 ? 8 : n); }
+static int g_emu_dev = 0;
+cudaError_t cudaGetDeviceCount(int *n) { *n = emu_device_count(); return cudaSuccess; }
+cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { const char *e = getenv("MONTE_EMU_NO_PEER"); *can = e && atoi(e) ? 0 : 1; return cudaSuccess; }
+cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
     memset(p, 0, sizeof(*p));
     snprintf(p->name, sizeof(p->name), "monte_emu (CPU SIMT emulation, tests only)");
@@ -197,7 +203,7 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
     p->multiProcessorCount = e ? atoi(e) : 2;
     return cudaSuccess;
 }
-cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaSetDevice(int d) { if (d < 0 || d >= emu_device_count()) return cudaErrorInvalidValue; g_emu_dev = d; return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
@@ -220,3 +226,78 @@ cudaError_t monte_emu_malloc(void **p, size_t bytes) {
 cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(dst, src, n); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void *dst, int value, size_t n, cudaStream_t) { memset(dst, value, n); return cudaSuccess; }
+cudaError_t cudaMemcpy2DAsync(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t) {
+    for (size_t r = 0; r < height; r++) memmove((char *)dst + r * dpitch, (const char *)src + r * spitch, width);
+    return cudaSuccess;
+}
+
+// ---- in-process stand-in for the NCCL entry points of csrc/nccl_dl.cuh (tests only) ----------------------------
+// One host thread drives all "devices", exactly like the product's single-process multi-device mode: collective calls
+// are queued between GroupStart and GroupEnd and executed at GroupEnd.  Reduce: the root's recv buffer receives the
+// sum of all send buffers; Send/Recv: matched in issue order per (source, destination) pair.
+#include "../../monte_b200/csrc/nccl_dl.cuh"
+struct ncclComm { int rank, size; };
+namespace {
+struct EmuOp { int kind; const void *send; void *recv; size_t count; int dtype, root_or_peer, rank; };
+std::vector<EmuOp> g_ops;
+int g_group = 0;
+size_t emu_dtype_size(int t) { return t == monte::NCCL_UINT8 ? 1 : t == monte::NCCL_INT64 ? 8 : 4; }
+int emu_run_ops() {
+    // reduces (kind 0): group by root
+    std::vector<bool> done(g_ops.size(), false);
+    for (size_t i = 0; i < g_ops.size(); i++) {
+        if (done[i] || g_ops[i].kind != 0) continue;
+        const EmuOp &a = g_ops[i];
+        std::vector<const void *> sends;
+        void *root_recv = nullptr;
+        for (size_t j = i; j < g_ops.size(); j++) {
+            if (done[j] || g_ops[j].kind != 0 || g_ops[j].root_or_peer != a.root_or_peer || g_ops[j].count != a.count) continue;
+            sends.push_back(g_ops[j].send);
+            if (g_ops[j].rank == a.root_or_peer) root_recv = g_ops[j].recv;
+            done[j] = true;
+        }
+        if (!root_recv) return 3;
+        if (a.dtype == monte::NCCL_INT32) {
+            std::vector<int32_t> acc(a.count, 0);
+            for (const void *s : sends) for (size_t k = 0; k < a.count; k++) acc[k] += ((const int32_t *)s)[k];
+            memcpy(root_recv, acc.data(), a.count * 4);
+        } else if (a.dtype == monte::NCCL_FLOAT32) {
+            std::vector<float> acc(a.count, 0.f);
+            for (const void *s : sends) for (size_t k = 0; k < a.count; k++) acc[k] += ((const float *)s)[k];
+            memcpy(root_recv, acc.data(), a.count * 4);
+        } else return 4;
+    }
+    // sends (kind 1) matched with recvs (kind 2) in issue order
+    for (size_t i = 0; i < g_ops.size(); i++) {
+        if (done[i] || g_ops[i].kind != 1) continue;
+        bool found = false;
+        for (size_t j = 0; j < g_ops.size() && !found; j++) {
+            if (done[j] || g_ops[j].kind != 2) continue;
+            if (g_ops[j].rank == g_ops[i].root_or_peer && g_ops[j].root_or_peer == g_ops[i].rank) {
+                if (g_ops[j].count != g_ops[i].count) return 5;
+                memmove(g_ops[j].recv, g_ops[i].send, g_ops[i].count * emu_dtype_size(g_ops[i].dtype));
+                done[i] = done[j] = true; found = true;
+            }
+        }
+        if (!found) return 6;
+    }
+    for (size_t i = 0; i < g_ops.size(); i++) if (!done[i]) return 7;
+    g_ops.clear();
+    return 0;
+}
+int emu_push(EmuOp op) { g_ops.push_back(op); return g_group ? 0 : emu_run_ops(); }
+}  // namespace
+namespace monte {
+bool nccl_emu_fill(NcclApi &a) {
+    a.CommInitAll = [](ncclComm_t *c, int n, const int *) { for (int i = 0; i < n; i++) c[i] = new ncclComm{i, n}; return 0; };
+    a.CommDestroy = [](ncclComm_t c) { delete c; return 0; };
+    a.GetErrorString = [](int r) -> const char * { return r == 0 ? "no error" : "monte_emu nccl: unmatched or malformed collective"; };
+    a.GroupStart = []() { g_group++; return 0; };
+    a.GroupEnd = []() { return --g_group == 0 ? emu_run_ops() : 0; };
+    a.Reduce = [](const void *s, void *r, size_t n, int t, int, int root, ncclComm_t c, cudaStream_t) { return emu_push(EmuOp{0, s, r, n, t, root, c->rank}); };
+    a.Send = [](const void *s, size_t n, int t, int peer, ncclComm_t c, cudaStream_t) { return emu_push(EmuOp{1, s, nullptr, n, t, peer, c->rank}); };
+    a.Recv = [](void *r, size_t n, int t, int peer, ncclComm_t c, cudaStream_t) { return emu_push(EmuOp{2, nullptr, r, n, t, peer, c->rank}); };
+    a.GetVersion = [](int *v) { *v = 0; return 0; };
+    return true;
+}
+}  // namespace monte

@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported(lib):
         assert hasattr(lib, n), "libmonte_gpu.so does not export %s" % n
     assert lib._monte_missing == []
     assert set(lib._monte_symbols) == set(names), set(lib._monte_symbols) ^ set(names)
-    assert lib.monte_gpu_abi_version() == 3
+    assert lib.monte_gpu_abi_version() == 4
 
 
 def test_struct_layouts_match_the_header():
@@ -80,7 +80,10 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, fn), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), fn
                 assert not re.search(r'#\s*include\s*[<"][^>"]*oracle', text), fn      # comments may cite it
-                assert "liboracle" not in text and "dlopen" not in text, fn
+                assert "liboracle" not in text, fn
+                # the one dlopen of the product binds NCCL for the multi-device mode (csrc/common.cu); nothing else is loaded at run time
+                if "dlopen(" in text:
+                    assert fn == "common.cu" and set(re.findall(r'"(lib[^"]*\.so[^"]*)"', text)) == {"libnccl.so.2", "libnccl.so"}, fn
 
 
 def test_product_never_contains_or_loads_the_emulation():

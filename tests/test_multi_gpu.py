@@ -1,0 +1,206 @@
+"""Multi-device mode of the C ABI (monte_gpu_init(ndev > 1, ids)): the host-buffer calls shard over
+the bound devices inside libmonte_gpu and must return the bits of the one-device call.
+
+The test bodies take the binding as an argument: here they run on real B200s (skipped on a box with fewer GPUs
+than they need); tests/test_emu_multi.py runs the same bodies on the CPU emulation with MONTE_EMU_DEVICES."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from monte_b200 import _abi, scenes
+
+
+def _need(n):
+    import torch
+    if torch.cuda.device_count() < n:
+        pytest.skip("needs %d GPUs" % n)
+
+
+def rebind(api, devs):
+    api.init(devs if len(devs) > 1 else devs[0])
+    assert api.load().monte_gpu_device_count() == len(devs)
+
+
+FDK_CASES = [
+    # n_views, nu, nv, n, roi / mask tweak
+    (24, 40, 30, 48, None),
+    (31, 65, 33, 40, "roi"),          # ragged view split, partial ROI + sphere mask
+    (16, 300, 20, 32, None),          # FFT filter path (nu > 256)
+    (12, 33, 65, 24, "tall"),         # tall detector: every slice is visible, equal-cost slabs
+]
+
+
+def body_fdk_multi_equals_single(api, n_dev, case):
+    n_views, nu, nv, n, tweak = case
+    g = _abi.generic_fdk_geom(n_views, nu, nv, n)
+    if tweak == "roi":
+        g.s_begin, g.s_end, g.t_begin, g.t_end, g.z_begin, g.z_end = 3, n - 5, 2, n - 1, 4, n - 6
+        g.mask_cs = g.mask_ct = g.mask_cz = n // 2
+        g.mask_r2 = (n // 2 - 2) ** 2
+    proj = np.random.default_rng(n_views).random((n_views, nu, nv), dtype=np.float32)
+    rebind(api, [0])
+    f1, v1, z1, _ = api.fdk(g, proj, want_zy=True)
+    rebind(api, list(range(n_dev)))
+    try:
+        f2, v2, z2, st = api.fdk(g, proj, want_zy=True)
+        f3, v3, _, _ = api.fdk(g, proj, want_filtered=False)          # second call: cached partition, reused buffers
+    finally:
+        rebind(api, [0])
+    assert np.array_equal(f1, f2), "filtered views differ"
+    assert np.array_equal(v1, v2) and np.array_equal(v1, v3), "volume differs from the one-device call"
+    assert np.array_equal(z1, z2), "transposed volume differs"
+    assert f3 is None and st["voxel_updates"] == (g.s_end - g.s_begin) * (g.t_end - g.t_begin) * (g.z_end - g.z_begin) * n_views
+    cuts = api.fdk_partition(g, n_dev)
+    assert cuts[0] == 0 and cuts[-1] == g.nz and all(b >= a for a, b in zip(cuts, cuts[1:]))
+
+
+def body_mc_multi_equals_single(api, n_dev, reduce_mode, per=37):
+    lab = scenes.cylinder_phantom(33, 1.0)
+    mg = scenes.mc_geom(9, 32.5 / 9, n_views=3)
+    mvol = scenes.volume_for(lab, 1.0)
+    xs = scenes.make_xs()
+    sp = scenes.mono_spectrum(140.0)
+    rebind(api, [0])
+    a0, a5, sa, ma0, ma5 = api.simulate(mg, mvol, lab, xs, sp, per, 7, maps=True)
+    assert np.array_equal(ma0, api.counts_to_map(a0, per)) and np.array_equal(ma5, api.counts_to_map(a5, per))
+    old = os.environ.get("MONTE_MC_REDUCE")
+    os.environ["MONTE_MC_REDUCE"] = reduce_mode
+    rebind(api, list(range(n_dev)))
+    try:
+        b0, b5, sb, mb0, mb5 = api.simulate(mg, mvol, lab, xs, sp, per, 7, maps=True)
+        c0, c5, sc = api.simulate(mg, mvol, lab, xs, sp, per, 7, views=(1, 3), n_range=(5, per - 3))   # ragged sub-range, no maps
+    finally:
+        rebind(api, [0])
+        if old is None:
+            del os.environ["MONTE_MC_REDUCE"]
+        else:
+            os.environ["MONTE_MC_REDUCE"] = old
+    d0, d5, sd = api.simulate(mg, mvol, lab, xs, sp, per, 7, views=(1, 3), n_range=(5, per - 3))
+    assert np.array_equal(a0, b0) and np.array_equal(a5, b5), "tallies differ from the one-device run"
+    assert np.array_equal(ma0, mb0) and np.array_equal(ma5, mb5), "maps differ"
+    for k in ("histories", "primaries", "scatter_detected", "absorbed", "interactions", "woodcock_steps"):
+        assert sa[k] == sb[k], k
+    assert np.array_equal(c0, d0) and np.array_equal(c5, d5) and sc["histories"] == sd["histories"] == 2 * 81 * (per - 8)
+    assert not c0[0].any()                                            # views outside the request stay untouched
+
+
+def body_label_cache(api):
+    """the label volume is re-uploaded only when its bytes changed; a changed buffer (same address) must be seen"""
+    lab = scenes.cylinder_phantom(33, 1.0).copy()
+    mg = scenes.mc_geom(9, 32.5 / 9, n_views=1)
+    mvol = scenes.volume_for(lab, 1.0)
+    xs, sp = scenes.make_xs(), scenes.mono_spectrum(140.0)
+    a0, a5, _ = api.simulate(mg, mvol, lab, xs, sp, 60, 3)
+    b0, b5, _ = api.simulate(mg, mvol, lab, xs, sp, 60, 3)            # cached labels
+    assert np.array_equal(a0, b0) and np.array_equal(a5, b5)
+    lab[:] = 0                                                        # all air, in place
+    c0, _, st = api.simulate(mg, mvol, lab, xs, sp, 60, 3)
+    assert (c0 == 60).all() and st["primaries"] == st["histories"]
+    os.environ["MONTE_MC_LABEL_CACHE"] = "0"
+    try:
+        lab[:] = scenes.cylinder_phantom(33, 1.0)
+        d0, d5, _ = api.simulate(mg, mvol, lab, xs, sp, 60, 3)
+    finally:
+        del os.environ["MONTE_MC_LABEL_CACHE"]
+    assert np.array_equal(a0, d0) and np.array_equal(a5, d5)
+
+
+def body_argument_errors(api):
+    from monte_b200.api import MonteError
+    lab = scenes.cylinder_phantom(17, 2.0)
+    mg = scenes.mc_geom(5, 6.5, n_views=2)
+    mvol = scenes.volume_for(lab, 2.0)
+    xs = scenes.make_xs()
+    err = getattr(api, "MonteError", MonteError)
+    for bad in (scenes.mono_spectrum(0.0), scenes.mono_spectrum(-5.0), scenes.mono_spectrum(250.0)):
+        with pytest.raises(err, match="mono_keV"):
+            api.simulate(mg, mvol, lab, xs, bad, 4, 1)
+    xz = scenes.make_xs()
+    for m in range(xz.n_materials):
+        xz.total[m][60] = 0.0                                          # zero majorant at a reachable energy: must not spin
+    with pytest.raises(err, match="majorant"):
+        api.simulate(mg, mvol, lab, xz, scenes.mono_spectrum(140.0), 4, 1)
+    api.simulate(mg, mvol, lab, xz, scenes.mono_spectrum(50.0), 4, 1)  # ... but 60 keV is out of reach from 50 keV
+    # [v, v) is empty: nothing runs, nothing is written
+    im0 = np.full((2, 5, 5), -7, np.int32)
+    im5 = np.full((2, 5, 5), -7, np.int32)
+    _, _, st = api.simulate(mg, mvol, lab, xs, scenes.mono_spectrum(140.0), 4, 1, views=(0, 0), out=(im0, im5))
+    assert (im0 == -7).all() and (im5 == -7).all() and st["histories"] == 0
+    with pytest.raises(err, match="ndev"):
+        api.init(list(range(9)))
+    api.init(0)
+
+
+# ------------------------------------------------------------------------------------------ on real GPUs
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", FDK_CASES[:3])
+def test_fdk_two_devices_equal_one(monte, case):
+    _need(2)
+    body_fdk_multi_equals_single(monte, 2, case)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+def test_mc_two_devices_equal_one(monte, mode):
+    _need(2)
+    body_mc_multi_equals_single(monte, 2, mode)
+
+
+@pytest.mark.gpu
+def test_label_cache(monte):
+    body_label_cache(monte)
+
+
+@pytest.mark.gpu
+def test_argument_errors(monte):
+    body_argument_errors(monte)
+
+
+@pytest.mark.gpu
+def test_overlapping_launches_of_one_scene(monte):
+    """two launches of one scene on two streams take their own work counters: the sum equals the serial run"""
+    import torch
+    lab = scenes.cylinder_phantom(65, 0.5)
+    mg = scenes.mc_geom(65, 0.5, n_views=2)
+    mvol = scenes.volume_for(lab, 0.5)
+    sc = monte.Scene(mg, mvol, lab, scenes.make_xs(), scenes.mono_spectrum(140.0))
+    per = 400
+    ref0 = torch.zeros((2, 65, 65), dtype=torch.int32, device="cuda"); ref5 = torch.zeros_like(ref0)
+    sc.simulate_dev(ref0, ref5, per, seed=5)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        a0 = torch.zeros_like(ref0); a5 = torch.zeros_like(ref0)
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        torch.cuda.synchronize()
+        sc.simulate_dev(a0, a5, per, seed=5, views=(0, 1), stream=s1)
+        sc.simulate_dev(a0, a5, per, seed=5, views=(1, 2), stream=s2)
+        torch.cuda.synchronize()
+        assert torch.equal(a0, ref0) and torch.equal(a5, ref5)
+    sc.close()
+
+
+@pytest.mark.gpu
+def test_drivers_with_two_gpus_write_the_one_gpu_bytes(tmp_path):
+    """cbct_mc / cbct_fdk --gpus 2 (the C++ hosts, monte_gpu_init(2, NULL)) against --gpus 1, byte for byte"""
+    _need(2)
+    from monte_b200 import build
+    from test_drivers import _write_csv
+    build.build_lib()
+    bins = {os.path.basename(p): p for p in build.build_drivers()}
+    d = str(tmp_path)
+    h2o, ca = scenes.load_tables()
+    _write_csv(os.path.join(d, "xcom2.csv"), h2o)
+    _write_csv(os.path.join(d, "Ca.csv"), ca)
+    subprocess.check_call([bins["make_fantom"], "cylinder", "33", "1.0", os.path.join(d, "cyl.raw")])
+    for tag, gpus in (("a", "1"), ("b", "2")):
+        subprocess.run([bins["cbct_mc"], "cyl.raw", "33", "1.0", "xcom2.csv", "Ca.csv", "17", str(32.5 / 17), "4", "201", "3", tag,
+                        "--gpus", gpus], cwd=d, check=True, stdout=subprocess.PIPE)
+    for f in ("proj_%s0.raw", "proj_%s5.raw", "map_%s0.raw", "map_%s5.raw"):
+        assert open(os.path.join(d, f % "a"), "rb").read() == open(os.path.join(d, f % "b"), "rb").read(), f
+    np.random.default_rng(3).random((360, 65, 65), dtype=np.float32).tofile(os.path.join(d, "m.raw"))
+    for tag, gpus in (("a", "1"), ("b", "2")):
+        subprocess.run([bins["cbct_fdk"], "bp3d20", "m.raw", tag, "--gpus", gpus], cwd=d, check=True, stdout=subprocess.PIPE)
+    for f in ("xy_%s.raw", "zy_%s.raw", "map_%s.raw"):
+        assert open(os.path.join(d, f % "a"), "rb").read() == open(os.path.join(d, f % "b"), "rb").read(), f
