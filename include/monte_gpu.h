@@ -246,9 +246,9 @@ typedef struct monte_mc_xs {
                                        (monte_mc_clearance_grid_octants): only the heavy material a ray with that direction
                                        can still reach counts, so a photon flying away from the insert is never cut short.
                                        Oracle, steps per history: 3.6 at 140 keV (reference loop 4.5), 3.6 at 120 kVp (22.4) */
-#define MONTE_MC_TRACK_AUTO      2  /* the library picks one of the two from the tables and the spectrum
-                                       (monte_mc_resolve_tracking): CLEARANCE with 4-voxel cells if the global
-                                       majorant is on average more than 3x the majorant of the lighter materials  */
+#define MONTE_MC_TRACK_AUTO      2  /* the library picks from the tables and the spectrum (monte_mc_resolve_tracking):
+                                       DIRECTIONAL with 4-voxel cells if the global majorant is on average more than
+                                       3x the majorant of the lighter materials, else GLOBAL                        */
 
 typedef struct monte_mc_volume {
     int32_t nx, ny, nz;
@@ -442,9 +442,10 @@ int monte_mc_clearance_grid_octants(const monte_mc_volume *vol, const uint8_t *l
 int monte_xs_heavy_material(const monte_mc_xs *xs);
 /* What MONTE_MC_TRACK_AUTO resolves to (host only, deterministic in its inputs, so every rank of a sharded run
  * decides alike): the spectrum-weighted mean of mu_max(E) / mu_light(E) -- the factor by which the heavy material
- * inflates the number of tentative collisions in the bulk -- above 3 selects MONTE_MC_TRACK_CLEARANCE
- * (*cell_log2 = 2), else MONTE_MC_TRACK_GLOBAL.  Measured on a B200, water + calcium: 140 keV (1.8) 8.1 ms global vs
- * 10.6 ms clearance; 60 keV (5.0) 11.1 vs 9.8 ms; 120 kVp (6.1) 20.9 vs 9.4 ms.  ratio (nullable) receives the mean. */
+ * inflates the number of tentative collisions in the bulk -- above 3 selects MONTE_MC_TRACK_DIRECTIONAL
+ * (*cell_log2 = 2), else MONTE_MC_TRACK_GLOBAL.  Measured on a B200, water + calcium, ms per 1e8 histories (round 2,
+ * profiles/r02_mc_tracking_modes.jsonl): 140 keV (ratio 1.8) 8.13 global vs 9.37 directional; 60 keV (5.0) 11.1 vs 8.61;
+ * 120 kVp (6.1) 20.9 vs 8.64 (plain CLEARANCE: 9.95).  ratio (nullable) receives the mean.                          */
 int monte_mc_resolve_tracking(const monte_mc_xs *xs, const monte_mc_spectrum *spec, int32_t *cell_log2, double *ratio);
 /* per-keV Woodcock majorant (1/cm) over the materials that occur in `labels` (NULL: all materials):
  * the max of CBCT_real325im.cu:866 restricted to what the volume contains; mu_max[201].               */

@@ -327,7 +327,7 @@ int monte_mc_resolve_tracking(const monte_mc_xs *xs, const monte_mc_spectrum *sp
         if (wsum > 0) mean = acc / wsum;
     } else mean = r_at(spec ? spec->mono_keV : 140.0);
     if (ratio) *ratio = mean;
-    return mean > 3.0 ? MONTE_MC_TRACK_CLEARANCE : MONTE_MC_TRACK_GLOBAL;
+    return mean > 3.0 ? MONTE_MC_TRACK_DIRECTIONAL : MONTE_MC_TRACK_GLOBAL;
 }
 
 }  // extern "C"

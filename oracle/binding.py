@@ -38,6 +38,13 @@ def lib():
     return _lib
 
 
+def set_threads(n=0):
+    """OpenMP threads of the oracle's loops: n > 0 sets them (overriding OMP_NUM_THREADS); returns the number in force"""
+    l = lib()
+    l.oracle_set_threads.restype = C.c_int
+    return int(l.oracle_set_threads(C.c_int(int(n))))
+
+
 def have_ref(name):
     return os.path.exists(os.path.join(REF_DIR, name))
 

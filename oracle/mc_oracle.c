@@ -769,3 +769,11 @@ void oracle_counts_to_map(const int32_t *counts, size_t n, int32_t per, float *m
         map[i] = -log((double)c) + (double)logf((float)per);   /* C++ overloads: log(int)->double, log(float)->float */
     }
 }
+
+/* OpenMP team size of every oracle entry point (the FDK loops have no per-call thread count): n > 0 sets it, the
+ * return value is the size in force.  bench.py's CPU legs call it with the host's core count because a launcher may
+ * export OMP_NUM_THREADS=1 (torch.distributed.run does), and report the number returned. */
+int oracle_set_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}

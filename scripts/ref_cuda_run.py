@@ -2,7 +2,7 @@
 """Run the reference's own CUDA programs (oracle/_ref/CBCT_real325im[_s], CBCT_real325[_s], built from the sources
 under /root/reference by `make -C oracle ref_cuda`) on this box's GPU, next to libmonte_gpu on the equivalent scene.
 
-    python scripts/ref_cuda_run.py [--variant im_s|s|im|plain] [--ncu] [--out gpurun_out/ref_cuda.json]
+    python scripts/ref_cuda_run.py [--skip-im] [--out gpurun_out/ref_cuda.json]
 
 TEST / MEASUREMENT INFRASTRUCTURE ("faster than `projection` compiled for sm_100 on the same box").
 Inputs the reference reads by hard-coded name are synthesized in a scratch directory from the packed tables
@@ -12,12 +12,13 @@ Inputs the reference reads by hard-coded name are synthesized in a scratch direc
                                    (:492-498) -- which is also what the shipped program effectively does (survey Q3)
   cyu8_2.raw                      200^3 uint8 labels @0.1 cm: water cylinder r = 8.5 cm with the 8 calcium rods (the
                                    program only looks labels up inside r <= 9 cm, :904); spher01.raw zeros (unused)
-The `_s` binaries differ from the shipped source in two #define literals only (oracle/Makefile); their sample size is
-read back from the build (REF_CUDA_PHOTONS / REF_CUDA_VIEWS below must match the Makefile defaults).
-Outputs: histories/s of the whole program (wall clock, incl. file I/O: the reference has no timers), the `projection`
-kernel's own duration when --ncu is given, the same scene through monte_gpu_simulate, and two parity figures that pin
-the quirk-free primary physics to reference-produced output: chi^2 of image0 (ours vs theirs, independent RNGs) and
--ln(image0/per) of the reference against monte_gpu_project_primary.
+The `_p<N>` binaries differ from the shipped source in two #define literals only (oracle/Makefile: N photons per pixel,
+REF_CUDA_VIEWS views).  Outputs: histories/s of the whole program (wall clock, incl. file I/O: the reference has no timers)
+and of the `projection` kernel alone (difference of two sample sizes), the same phantom through monte_gpu_simulate, and
+parity figures that pin the quirk-free primary physics to reference-produced output: chi^2 of image0 (ours vs theirs,
+independent RNGs) and both against monte_gpu_project_primary's line integrals.  CBCT_real325im.cu (voxel labels) is run
+once: on a B200 its kernel dies of an illegal address (the interaction-site label lookup, :624, is unguarded; a
+back-scattered photon below z = -10 cm indexes megabytes before the buffer) -- recorded with compute-sanitizer's report.
 """
 import argparse
 import json
@@ -32,13 +33,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 REF = os.path.join(ROOT, "oracle", "_ref")
-REF_CUDA_PHOTONS, REF_CUDA_VIEWS = 200, 36          # oracle/Makefile defaults of the `_s` builds
-VARIANTS = {
-    "im_s": ("CBCT_real325im_s", REF_CUDA_PHOTONS, REF_CUDA_VIEWS, "teth%dpmma8etim2"),
-    "im": ("CBCT_real325im", 10000, 360, "teth%dpmma8etim2"),
-    "s": ("CBCT_real325_s", REF_CUDA_PHOTONS, REF_CUDA_VIEWS, "teth%dcyu8e"),
-    "plain": ("CBCT_real325", 10000, 360, "teth%dcyu8e"),
-}
+REF_CUDA_VIEWS = 36                                # oracle/Makefile default of the `_p<N>` builds
+NPIX = 325 * 325
 
 
 def write_inputs(d, lab):
@@ -55,96 +51,117 @@ def write_inputs(d, lab):
     np.zeros(185 * 185 * 325, np.uint8).tofile(os.path.join(d, "spher01.raw"))
 
 
+def run_ref(exe, d, tag, views, timeout, wrap=()):
+    """run one reference binary in directory d; returns (wall seconds, image0, image5, stdout tail, rc)"""
+    t = time.perf_counter()
+    p = subprocess.run(list(wrap) + [exe], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout)
+    wall = time.perf_counter() - t
+    f0 = os.path.join(d, "proj325_%s.raw" % (tag % 0))
+    f5 = os.path.join(d, "proj325_%s.raw" % (tag % 5))
+    r0 = np.fromfile(f0, np.int32).reshape(-1, 325, 325)[:views].copy() if os.path.exists(f0) else None
+    r5 = np.fromfile(f5, np.int32).reshape(-1, 325, 325)[:views].copy() if os.path.exists(f5) else None
+    return wall, r0, r5, p.stdout.decode(errors="replace")[-1500:], p.returncode
+
+
+def chi2_images(a, b, per):
+    """two independent samples of the same per-pixel binomial(per, p): sum (a - b)^2 / (2 per p (1 - p)), p pooled"""
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    pp = (a + b) / (2.0 * per)
+    var = 2.0 * per * pp * (1.0 - pp)
+    ok = var > 0
+    chi2 = float(((a - b)[ok] ** 2 / var[ok]).sum())
+    dof = int(ok.sum())
+    return chi2, dof, (chi2 - dof) / np.sqrt(2.0 * dof) if dof else None
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--variant", default="im_s", choices=sorted(VARIANTS))
-    ap.add_argument("--ncu", action="store_true", help="second run under ncu for the kernel's own duration")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "ref_cuda.json"))
-    ap.add_argument("--timeout", type=int, default=900)
+    ap.add_argument("--timeout", type=int, default=600)
+    ap.add_argument("--skip-im", action="store_true")
     args = ap.parse_args()
-    exe_name, per, views, tag = VARIANTS[args.variant]
-    exe = os.path.join(REF, exe_name)
-    if not os.path.exists(exe):
-        print(json.dumps({"unavailable": "%s not built (make -C oracle ref_cuda needs /root/reference)" % exe_name}))
+    from monte_b200 import api, scenes
+    views = REF_CUDA_VIEWS
+    res = {"views": views, "gpu": None}
+    try:
+        res["gpu"] = subprocess.run(["nvidia-smi", "--query-gpu=name", "--format=csv,noheader", "-i", "0"], stdout=subprocess.PIPE, text=True).stdout.strip()
+    except Exception:
+        pass
+    if not os.path.exists(os.path.join(REF, "CBCT_real325_p100")):
+        print(json.dumps({"unavailable": "oracle/_ref/CBCT_real325_p100 not built (make -C oracle ref_cuda needs /root/reference)"}))
         return
-    from monte_b200 import _abi, api, scenes
-    voxel = args.variant.startswith("im")
-    lab = scenes.cylinder_phantom(200, 0.1, radius=8.5)
-    npix = 325 * 325
-    res = {"variant": args.variant, "binary": exe_name, "photons_per_pixel": per, "views": views, "histories": npix * per * views,
-           "phantom": "200^3 labels @0.1 cm, water r=8.5 + 8 Ca rods" if voxel else "analytic cylinder r=10 along x + 8 Ca rods (in the kernel)"}
+    lab200 = scenes.cylinder_phantom(200, 0.1, radius=8.5)
     with tempfile.TemporaryDirectory() as d:
-        write_inputs(d, lab)
-        t = time.perf_counter()
-        p = subprocess.run([exe], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=args.timeout)
-        wall = time.perf_counter() - t
-        res.update(rc=p.returncode, wall_s=wall, whole_program_hist_per_s=res["histories"] / wall,
-                   stdout_tail=p.stdout.decode(errors="replace")[-300:])
-        f0 = os.path.join(d, "proj325_%s.raw" % (tag % 0))
-        f5 = os.path.join(d, "proj325_%s.raw" % (tag % 5))
-        r0 = np.fromfile(f0, np.int32).reshape(-1, 325, 325)[:views].copy() if os.path.exists(f0) else None
-        r5 = np.fromfile(f5, np.int32).reshape(-1, 325, 325)[:views].copy() if os.path.exists(f5) else None
-        if args.ncu:
-            log = os.path.join(d, "ncu.csv")
-            subprocess.run(["ncu", "--metrics", "gpu__time_duration.sum", "--clock-control", "none", "--csv", "--log-file", log, exe],
-                           cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=args.timeout)
-            try:
-                import csv
-                for row in csv.DictReader(l for l in open(log) if not l.startswith("==")):
-                    if "projection" in row.get("Kernel Name", ""):
-                        v = float(row["Metric Value"].replace(",", ""))
-                        unit = row.get("Metric Unit", "ns")
-                        sec = v * {"ns": 1e-9, "us": 1e-6, "usecond": 1e-6, "ms": 1e-3, "msecond": 1e-3, "s": 1.0, "second": 1.0, "nsecond": 1e-9}.get(unit, 1e-9)
-                        res.update(kernel_s=sec, kernel_hist_per_s=res["histories"] / sec)
-            except Exception as ex:
-                res["ncu_error"] = repr(ex)[:200]
-    if r0 is None:
-        res["error"] = "the reference wrote no projection file"
-        print(json.dumps(res))
-        return
-    res["ref_primary_fraction"] = float(r0.sum()) / res["histories"]
-    res["ref_image5_minus_image0_fraction"] = float(r5.sum() - r0.sum()) / res["histories"]
-    if voxel:
-        # the same scene through libmonte_gpu: 200^3 labels, corner-indexed at origin -10 (CBCT_real325im.cu:921)
-        api.init(0)
-        g = scenes.mc_geom(325, 0.1, n_views=views)
-        g.angle_step_deg = 1.0                         # num_p counts whole degrees (:508)
-        vol = scenes.volume_for(lab, 0.1)
-        xs = scenes.make_xs(("h2o", "ca", "pmma"))
-        sp = scenes.mono_spectrum(140.0)
-        api.simulate(g, vol, lab, xs, sp, per, seed=1, views=(0, 1))      # warm-up (scene upload, module load)
-        t = time.perf_counter()
-        o0, o5, st = api.simulate(g, vol, lab, xs, sp, per, seed=1)
-        ours_wall = time.perf_counter() - t
-        res.update(ours_kernel_ms=st["ms_kernel"], ours_hist_per_s_kernel=st["histories"] / (st["ms_kernel"] * 1e-3),
-                   ours_hist_per_s_call=st["histories"] / ours_wall, ours_primary_fraction=st["primaries"] / st["histories"],
-                   ours_scatter_detected_fraction=st["scatter_detected"] / st["histories"])
-        if "kernel_hist_per_s" in res:
-            res["speedup_kernel"] = res["ours_hist_per_s_kernel"] / res["kernel_hist_per_s"]
-        res["speedup_whole_program_vs_our_call"] = res["ours_hist_per_s_call"] / res["whole_program_hist_per_s"]
-        # chi^2 of the two primary images (independent samples of the same binomial per pixel)
-        a, b = r0.astype(np.float64), o0.astype(np.float64)
-        m = (a + b) > 0
-        # pixels that every photon reaches unattenuated (both == per) carry no variance: leave them out
-        m &= ~((a == per) & (b == per))
-        # pooled binomial variance: Var(a - b) = 2 per p (1 - p), p = (a + b) / (2 per)
-        pp = (a[m] + b[m]) / (2.0 * per)
-        var = 2.0 * per * pp * (1.0 - pp)
-        ok = var > 0
-        chi2 = float((((a[m] - b[m])[ok]) ** 2 / var[ok]).sum())
-        dof = int(ok.sum())
-        res.update(chi2_image0=chi2, chi2_dof=dof, chi2_z=(chi2 - dof) / np.sqrt(2.0 * dof) if dof else None)
-        # deterministic check: -ln(image0 / per) of the REFERENCE against our line integrals, per-pixel 3 sigma
-        line = api.project_primary(g, vol, lab, xs, 140.0)
-        pexp = np.exp(-line.astype(np.float64))
-        sig = np.sqrt(np.maximum(per * pexp * (1 - pexp), 1e-12))
-        z = (a - per * pexp) / np.maximum(sig, 0.5)
-        res.update(ref_vs_projector_frac_within_3sigma=float((np.abs(z) <= 3).mean()), ref_vs_projector_mean_z=float(z.mean()),
-                   ours_vs_projector_frac_within_3sigma=float((np.abs((b - per * pexp) / np.maximum(sig, 0.5)) <= 3).mean()))
-        api.shutdown()
+        write_inputs(d, lab200)
+        # ---- monte_cu/CBCT_real325.cu (analytic phantom in the kernel): two sample sizes
+        runs = {}
+        for per in (100, 300):
+            wall, r0, r5, out, rc = run_ref(os.path.join(REF, "CBCT_real325_p%d" % per), d, "teth%dcyu8e", views, args.timeout)
+            runs[per] = (wall, r0, r5)
+            res["plain_p%d" % per] = {"histories": NPIX * per * views, "wall_s": wall, "rc": rc,
+                                      "primary_fraction": float(r0.sum()) / (NPIX * per * views) if r0 is not None else None,
+                                      "scattered_tally_fraction": float(r5.sum() - r0.sum()) / (NPIX * per * views) if r0 is not None else None}
+        dh = NPIX * views * 200
+        dt = runs[300][0] - runs[100][0]
+        res["ref_cuda"] = {"program": "monte_cu/CBCT_real325.cu (`projection`, one thread per pixel, cuRAND MRG32k3a), nvcc -O3 -arch=sm_100",
+                           "whole_program_hist_per_s": NPIX * 300 * views / runs[300][0],
+                           "kernel_hist_per_s": dh / dt if dt > 0 else None,
+                           "how": "two builds that differ in num_photon only (100 and 300 per pixel, %d views): the difference of their wall "
+                                  "clocks is %.3g histories of pure kernel time, free of file I/O and start-up" % (views, dh)}
+        # ---- monte_cu/CBCT_real325im.cu (voxel labels): does it survive?
+        if not args.skip_im:
+            wall, r0, r5, out, rc = run_ref(os.path.join(REF, "CBCT_real325im_p100"), d, "teth%dpmma8etim2", views, args.timeout)
+            dead = r0 is None or int(r0.max()) <= 1
+            res["im_p100"] = {"wall_s": wall, "rc": rc, "image0_max": int(r0.max()) if r0 is not None else None,
+                              "kernel_died": dead}
+            if dead:
+                try:
+                    p = subprocess.run(["compute-sanitizer", "--tool", "memcheck", "--print-limit", "2", os.path.join(REF, "CBCT_real325im_p100")],
+                                       cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=150)
+                    txt = p.stdout.decode(errors="replace")
+                    k = txt.find("=========")
+                    res["im_p100"]["memcheck_first_report"] = txt[k:k + 1800] if k >= 0 else txt[-600:]
+                except Exception as ex:
+                    res["im_p100"]["memcheck_first_report"] = "compute-sanitizer: %r" % (ex,)
+    # ---- the analytic phantom of CBCT_real325.cu:916-921 voxelised at 0.05 cm (cylinder axis along x, rods in the y-z plane:
+    # the z-axis phantom of scenes.cylinder_phantom with x and z swapped), through libmonte_gpu
+    api.init(0)
+    per = 300
+    lab = np.ascontiguousarray(scenes.cylinder_phantom(400, 0.05).transpose(2, 1, 0))
+    g = scenes.mc_geom(325, 0.1, n_views=views)
+    g.angle_step_deg = 1.0                              # num_p counts whole degrees (:508)
+    vol = scenes.volume_for(lab, 0.05)
+    xs = scenes.make_xs()
+    sp = scenes.mono_spectrum(140.0)
+    api.simulate(g, vol, lab, xs, sp, per, seed=1, views=(0, 1))      # warm-up (scene upload, module load)
+    t = time.perf_counter()
+    o0, o5, st = api.simulate(g, vol, lab, xs, sp, per, seed=1)
+    ours_wall = time.perf_counter() - t
+    rc_ = res["ref_cuda"]
+    res["ours"] = {"histories": st["histories"], "kernel_ms": st["ms_kernel"], "hist_per_s_kernel": st["histories"] / (st["ms_kernel"] * 1e-3),
+                   "hist_per_s_call": st["histories"] / ours_wall, "primary_fraction": st["primaries"] / st["histories"],
+                   "scatter_detected_fraction": st["scatter_detected"] / st["histories"],
+                   "scene": "the same phantom voxelised to 400^3 labels @0.05 cm, %d views x %d photons/pixel, monte_gpu_simulate" % (views, per)}
+    if rc_["kernel_hist_per_s"]:
+        res["speedup_kernel"] = res["ours"]["hist_per_s_kernel"] / rc_["kernel_hist_per_s"]
+    res["speedup_whole_program_vs_our_call"] = res["ours"]["hist_per_s_call"] / rc_["whole_program_hist_per_s"]
+    # parity: the reference's image0 is quirk-free physics (unscattered photons per pixel).  chi^2 against ours (independent
+    # RNGs), and both against the deterministic line integrals
+    r0 = runs[300][1]
+    chi2, dof, z = chi2_images(r0, o0, per)
+    res["parity"] = {"chi2_image0": chi2, "chi2_dof": dof, "chi2_z": z,
+                     "note": "reference image0 (CBCT_real325_p300, cuRAND) vs ours (Philox), %d views x 325^2 pixels x %d photons" % (views, per)}
+    line = api.project_primary(g, vol, lab, xs, 140.0)
+    pexp = np.exp(-line.astype(np.float64))
+    sig = np.maximum(np.sqrt(per * pexp * (1 - pexp)), 0.5)
+    res["parity"].update(ref_vs_projector_frac_within_3sigma=float((np.abs(r0 - per * pexp) / sig <= 3).mean()),
+                         ours_vs_projector_frac_within_3sigma=float((np.abs(o0 - per * pexp) / sig <= 3).mean()),
+                         ref_total_primaries=int(r0.sum()), ours_total_primaries=int(o0.sum()),
+                         ref_scattered_tallies=int(runs[300][2].sum() - r0.sum()), ours_scattered_tallies=int(o5.sum() - o0.sum()))
+    api.shutdown()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
-        json.dump(res, f)
+        json.dump(res, f, indent=1)
     print(json.dumps(res))
 
 

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_json_line(oracle):
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--c1-views", "2"],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600, cwd=ROOT)
     assert p.returncode == 0, p.stderr.decode()[-2000:]
     lines = [l for l in p.stdout.decode().splitlines() if l.startswith("{")]
@@ -23,6 +23,21 @@ def test_reference_arm_json_line(oracle):
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "histories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["fdk"]["unit"] == "GUPS" and d["fdk"]["value"] > 1e-3
+    # the thread count the oracle really ran with is what `cores` states (a launcher may export OMP_NUM_THREADS=1)
+    assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1) == d["cpu_baseline"]["host_cores"]
+    assert d["c1"]["config"]["workload"].startswith("C1 ") and d["c1"]["mc"]["value"] > 1e5 and d["mc_c4"]["value"] > 1e4
+
+
+def test_reference_arm_uses_all_cores_under_a_launcher_that_sets_omp_num_threads(oracle):
+    """torch.distributed.run exports OMP_NUM_THREADS=1 (the N >= 2 reference numbers collapsed 25x)"""
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--c1-views", "0"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600, cwd=ROOT, env=env)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    d = json.loads([l for l in p.stdout.decode().splitlines() if l.startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    import bench
+    assert d["config"]["workload"] == bench.WORKLOAD_C2
 
 
 def test_reference_arm_other_ranks_are_silent():

@@ -186,7 +186,7 @@ def test_emu_auto_tracking_equals_the_mode_it_resolves_to(monte_emu):
         b0, b5, sb = m.simulate(g, vol, lab, xs, spec, 30, 4)
         assert np.array_equal(a0, b0) and np.array_equal(a5, b5) and sa["woodcock_steps"] == sb["woodcock_steps"]
     assert m.resolve_tracking(xs, scenes.mono_spectrum(140.0))[0] == _abi.TRACK_GLOBAL
-    assert m.resolve_tracking(xs, scenes.mono_spectrum(50.0))[0] == _abi.TRACK_CLEARANCE
+    assert m.resolve_tracking(xs, scenes.mono_spectrum(50.0))[0] == _abi.TRACK_DIRECTIONAL
 
 
 @pytest.mark.parametrize("sched", ["reverse", "random"])

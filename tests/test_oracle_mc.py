@@ -289,15 +289,15 @@ def test_clearance_tracking_is_the_same_physics(oracle):
 
 
 def test_auto_tracking_resolution_follows_the_measured_crossover():
-    """MONTE_MC_TRACK_AUTO (host helper, deterministic): single majorant at 140 keV, clearance at 60 keV and for the
-    120 kVp spectrum -- the side of the crossover each was measured on"""
+    """MONTE_MC_TRACK_AUTO (host helper, deterministic): single majorant at 140 keV, the directional two-level majorant at
+    60 keV and for the 120 kVp spectrum -- the side of the crossover each was measured on"""
     from monte_b200 import api
     xs = scenes.make_xs()
     mode, cl, r = api.resolve_tracking(xs, scenes.mono_spectrum(140.0))
     assert mode == _abi.TRACK_GLOBAL and 1.5 < r < 2.2
     mode, cl, r = api.resolve_tracking(xs, scenes.mono_spectrum(60.0))
-    assert mode == _abi.TRACK_CLEARANCE and cl == 2 and 4.0 < r < 6.0
+    assert mode == _abi.TRACK_DIRECTIONAL and cl == 2 and 4.0 < r < 6.0
     spec, keep = scenes.kramers_spectrum()
     mode, cl, r = api.resolve_tracking(xs, spec)
-    assert mode == _abi.TRACK_CLEARANCE and r > 4.0
+    assert mode == _abi.TRACK_DIRECTIONAL and r > 4.0
     assert api.resolve_tracking(scenes.make_xs(("h2o",)), spec)[0] == _abi.TRACK_GLOBAL      # nothing to exclude
