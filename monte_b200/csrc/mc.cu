@@ -657,11 +657,13 @@ constexpr unsigned MC_WORK_RING = 16;
 struct monte_mc_scene {
     McSceneDev dev;
     monte_mc_geom geom;
-    void *d_labels = nullptr, *d_tab = nullptr, *d_inv = nullptr, *d_cdf = nullptr, *d_view = nullptr, *d_ray = nullptr;
-    size_t cap_labels = 0, cap_tab = 0, cap_cdf = 0, cap_view = 0, cap_ray = 0;     // grow-only capacities (bytes)
+    void *d_labels = nullptr;
+    void *d_small = nullptr, *h_small = nullptr;                       // all small tables: one device block + its pinned staging copy
+    void *d_tab = nullptr, *d_inv = nullptr, *d_cdf = nullptr, *d_view = nullptr, *d_ray = nullptr;   // (inside d_small)
+    size_t cap_labels = 0, cap_small = 0;                              // grow-only capacities (bytes)
     int ray_n = 0;                                                     // > 0: form-factor tables uploaded (coherent_mode 1)
     // two-level majorant (tracking_mode CLEARANCE): clearance grid, light-majorant table, the material it excludes
-    void *d_clear = nullptr, *d_invlo = nullptr;
+    void *d_clear = nullptr, *d_invlo = nullptr;                        // (d_invlo inside d_small)
     size_t cap_clear = 0;
     int heavy = -1, cshift = 0, cg[3] = {0, 0, 0};
     unsigned coct = 0;                                                 // DIRECTIONAL: cells per octant grid
@@ -783,9 +785,9 @@ static uint64_t hash_labels_1(const uint8_t *p, size_t n) {
     return r;
 }
 
-// the same on four host threads for volumes of 8 MB and more (325^3: 2 ms -> 0.6 ms)
+// the same on eight host threads for volumes of 8 MB and more (325^3: 2 ms -> ~0.4 ms)
 static uint64_t hash_labels(const uint8_t *p, size_t n) {
-    constexpr int T = 4;
+    constexpr int T = 8;
     if (n < (8u << 20)) return hash_labels_1(p, n);
     uint64_t h[T];
     std::thread th[T];
@@ -842,10 +844,10 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
     d.nx = vol->nx; d.ny = vol->ny; d.nz = vol->nz;
     d.inv_pitch = (float)(1.0 / vol->pitch);
     for (int a = 0; a < 3; a++) { d.org[a] = (float)vol->origin[a]; d.clip_lo[a] = (float)vol->clip_lo[a]; d.clip_hi[a] = (float)vol->clip_hi[a]; }
-    // per-keV tables: majorant over materials (CBCT_real325im.cu:867-868) and branching ratios (:651,656)
+    // per-keV tables: majorant over materials (CBCT_real325im.cu:867-868) and branching ratios (:651,656).  All small
+    // tables are assembled in ONE pinned staging block of the scene and go to the device in one asynchronous copy: no
+    // implicit stream synchronisation of a pageable source, so the uploads of several devices overlap.
     const int nm = xs->n_materials;
-    std::vector<float4> tab((size_t)nm * TAB_ROWS);
-    std::vector<float> inv(TAB_ROWS), invlo(2 * TAB_ROWS, 0.f);        // invlo: 1/mu_light, then the clearance thresholds
     // tracking_mode CLEARANCE needs a material to exclude; with a single material it is the reference's loop
     monte_mc_volume vres = *vol;                                   // AUTO resolved (same rule on every rank: inputs only)
     if (vol->tracking_mode == MONTE_MC_TRACK_AUTO)
@@ -853,6 +855,26 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
     const bool directional = vres.tracking_mode == MONTE_MC_TRACK_DIRECTIONAL;
     const bool adaptive = vres.tracking_mode == MONTE_MC_TRACK_ADAPTIVE || directional;
     s->heavy = vres.tracking_mode == MONTE_MC_TRACK_CLEARANCE || adaptive ? monte_xs_heavy_material(xs) : -1;
+    const bool rayleigh = g->coherent_mode == MONTE_MC_COHERENT_FORMFACTOR;
+    const int rn = rayleigh ? xs->ff_points : 0;
+    const int n_bins = spec && spec->n_bins > 0 ? spec->n_bins : 0;
+    auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t tab_bytes = (size_t)nm * TAB_ROWS * sizeof(float4), inv_bytes = TAB_ROWS * sizeof(float);
+    const size_t cdf_bytes = n_bins ? (n_bins + 1) * sizeof(float) : 0, ray_bytes = (size_t)nm * 2 * rn * sizeof(float);
+    const size_t vcs_bytes = (size_t)g->n_views * sizeof(float2);
+    const size_t o_tab = 0, o_inv = al(o_tab + tab_bytes), o_invlo = al(o_inv + inv_bytes), o_vcs = al(o_invlo + 2 * inv_bytes),
+                 o_ray = al(o_vcs + vcs_bytes), o_cdf = al(o_ray + ray_bytes), small_bytes = al(o_cdf + cdf_bytes) + 16;
+    if (small_bytes > s->cap_small) {
+        if (s->d_small) cudaFree(s->d_small);
+        if (s->h_small) cudaFreeHost(s->h_small);
+        s->d_small = nullptr; s->h_small = nullptr; s->cap_small = 0;
+        MONTE_CUDA(cudaMalloc(&s->d_small, small_bytes));
+        MONTE_CUDA(cudaHostAlloc(&s->h_small, small_bytes, cudaHostAllocPortable));
+        s->cap_small = small_bytes;
+    }
+    char *hs = (char *)s->h_small, *ds = (char *)s->d_small;
+    float4 *tab = (float4 *)(hs + o_tab);
+    float *inv = (float *)(hs + o_inv), *invlo = (float *)(hs + o_invlo);      // invlo: 1/mu_light, then the clearance thresholds
     for (int k = 0; k < TAB_ROWS; k++) {
         double mumax = 0, mulo = 0;
         for (int m = 0; m < nm; m++) {
@@ -873,53 +895,30 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
             tab[(size_t)m * TAB_ROWS + k] = t;
         }
     }
-    const size_t tab_bytes = tab.size() * sizeof(float4), inv_bytes = inv.size() * sizeof(float);
-    if (int rc = grow(&s->d_tab, &s->cap_tab, tab_bytes + inv_bytes)) return rc;
-    s->d_inv = (char *)s->d_tab + tab_bytes;
-    MONTE_CUDA(cudaMemcpyAsync(s->d_tab, tab.data(), tab_bytes, cudaMemcpyHostToDevice, st));
-    MONTE_CUDA(cudaMemcpyAsync(s->d_inv, inv.data(), inv_bytes, cudaMemcpyHostToDevice, st));
-    d.tab = (const float4 *)s->d_tab; d.inv_mumax = (const float *)s->d_inv; d.n_mat = nm;
-    d.n_bins = 0; d.cdf = nullptr; d.bin_keV = 0.5f; d.mono_keV = 140.f;
-    size_t cdf_bytes = 0;
-    if (spec) {
-        d.mono_keV = (float)spec->mono_keV; d.bin_keV = (float)spec->bin_keV;
-        if (spec->n_bins > 0) {
-            d.n_bins = spec->n_bins;
-            cdf_bytes = (spec->n_bins + 1) * sizeof(float);
-            if (int rc = grow(&s->d_cdf, &s->cap_cdf, cdf_bytes)) return rc;
-            MONTE_CUDA(cudaMemcpyAsync(s->d_cdf, spec->cdf, cdf_bytes, cudaMemcpyHostToDevice, st));
-            d.cdf = (const float *)s->d_cdf;
-        }
-    }
-    size_t clear_bytes = 0;
-    s->vol = vres; s->n_mat_host = nm;
-    if (s->heavy >= 0) {
-        if (!s->d_invlo) MONTE_CUDA(cudaMalloc(&s->d_invlo, 2 * TAB_ROWS * sizeof(float)));
-        MONTE_CUDA(cudaMemcpyAsync(s->d_invlo, invlo.data(), 2 * TAB_ROWS * sizeof(float), cudaMemcpyHostToDevice, st));
-        if (int rc = upload_clearance(s, labels, st, labels_hash)) return rc;
-        clear_bytes = (size_t)s->cg[0] * s->cg[1] * s->cg[2] + 2 * TAB_ROWS * sizeof(float);
-        MONTE_CUDA(cudaStreamSynchronize(st));                         // `invlo` is pageable and goes out of scope
-    }
-    s->ray_n = 0;
-    size_t ray_bytes = 0;
-    if (g->coherent_mode == MONTE_MC_COHERENT_FORMFACTOR) {           // [material][x^2 grid | cumulative F^2][ff_points]
-        const int rn = xs->ff_points;
-        std::vector<float> ray((size_t)nm * 2 * rn);
-        for (int m = 0; m < nm; m++)
-            for (int i = 0; i < rn; i++) { ray[((size_t)m * 2) * rn + i] = xs->ff_x2[m][i]; ray[((size_t)m * 2 + 1) * rn + i] = xs->ff_cum[m][i]; }
-        ray_bytes = ray.size() * sizeof(float);
-        if (int rc = grow(&s->d_ray, &s->cap_ray, ray_bytes)) return rc;
-        MONTE_CUDA(cudaMemcpyAsync(s->d_ray, ray.data(), ray_bytes, cudaMemcpyHostToDevice, st));
-        MONTE_CUDA(cudaStreamSynchronize(st));                         // `ray` is pageable and goes out of scope
-        s->ray_n = rn;
-    }
-    std::vector<float2> vcs(g->n_views);
+    float2 *vcs = (float2 *)(hs + o_vcs);
     for (int v = 0; v < g->n_views; v++) {
         const double beta = M_PI * (g->angle0_deg + g->angle_step_deg * v) / 180;
         vcs[v] = make_float2((float)cos(beta), (float)sin(beta));
     }
-    if (int rc = grow(&s->d_view, &s->cap_view, vcs.size() * sizeof(float2))) return rc;
-    MONTE_CUDA(cudaMemcpyAsync(s->d_view, vcs.data(), vcs.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
+    if (rayleigh) {                                                   // [material][x^2 grid | cumulative F^2][ff_points]
+        float *ray = (float *)(hs + o_ray);
+        for (int m = 0; m < nm; m++)
+            for (int i = 0; i < rn; i++) { ray[((size_t)m * 2) * rn + i] = xs->ff_x2[m][i]; ray[((size_t)m * 2 + 1) * rn + i] = xs->ff_cum[m][i]; }
+    }
+    if (n_bins) memcpy(hs + o_cdf, spec->cdf, cdf_bytes);
+    MONTE_CUDA(cudaMemcpyAsync(ds, hs, small_bytes - 16, cudaMemcpyHostToDevice, st));
+    s->d_tab = ds + o_tab; s->d_inv = ds + o_inv; s->d_invlo = ds + o_invlo; s->d_view = ds + o_vcs;
+    s->d_ray = rayleigh ? ds + o_ray : nullptr; s->d_cdf = n_bins ? ds + o_cdf : nullptr;
+    d.tab = (const float4 *)s->d_tab; d.inv_mumax = (const float *)s->d_inv; d.n_mat = nm;
+    d.n_bins = n_bins; d.cdf = (const float *)s->d_cdf; d.bin_keV = 0.5f; d.mono_keV = 140.f;
+    if (spec) { d.mono_keV = (float)spec->mono_keV; d.bin_keV = (float)spec->bin_keV; }
+    size_t clear_bytes = 0;
+    s->vol = vres; s->n_mat_host = nm;
+    if (s->heavy >= 0) {
+        if (int rc = upload_clearance(s, labels, st, labels_hash)) return rc;
+        clear_bytes = (size_t)s->cg[0] * s->cg[1] * s->cg[2] + 2 * TAB_ROWS * sizeof(float);
+    }
+    s->ray_n = rn;
     d.view_cs = (const float2 *)s->d_view;
     d.n_views = g->n_views; d.det_ny = g->ny; d.det_nx = g->nx;
     d.pixel = (float)g->pixel; d.inv_pixel = (float)(1.0 / g->pixel); d.half = (float)g->half;
@@ -928,9 +927,9 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
     d.eid = g->detector_mode == MONTE_MC_DETECTOR_ENERGY ? 1 : 0;
     if (!s->d_work) MONTE_CUDA(cudaMalloc(&s->d_work, MC_WORK_RING * sizeof(unsigned long long)));
     s->smem = (size_t)nm * TAB_ROWS * sizeof(float4) + (TAB_ROWS + 3 + d.n_bins + 1) * sizeof(float);
-    s->h2d_bytes = (labels_resident ? 0 : nvox) + tab_bytes + inv_bytes + cdf_bytes + ray_bytes + clear_bytes + vcs.size() * sizeof(float2);
-    // the host vectors above are pageable: the async copies have already staged them
-    MONTE_CUDA(cudaStreamSynchronize(st));
+    s->h2d_bytes = (labels_resident ? 0 : nvox) + tab_bytes + inv_bytes + cdf_bytes + ray_bytes + clear_bytes + vcs_bytes;
+    // nothing is synchronised here: the staging block lives in the scene, and `labels` must stay valid until the
+    // caller's next synchronisation of `st` (the host-buffer entry points synchronise before they return)
     return MONTE_OK;
 }
 
@@ -942,6 +941,8 @@ int monte_gpu_scene_create(const monte_mc_geom *g, const monte_mc_volume *vol, c
     if (int rc = check_spectrum(xs, spec)) return rc;
     monte_mc_scene *s = new monte_mc_scene();
     if (int rc = scene_upload(s, g, vol, labels, xs, spec, ctx().stream)) { monte_gpu_scene_destroy(s); return rc; }
+    const cudaError_t e = cudaStreamSynchronize(ctx().stream);        // `labels` may be pageable and short-lived
+    if (e != cudaSuccess) { monte_gpu_scene_destroy(s); return cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__); }
     *out = s;
     return MONTE_OK;
 }
@@ -958,7 +959,8 @@ int monte_gpu_scene_update_labels(monte_mc_scene *s, const uint8_t *labels, void
 
 void monte_gpu_scene_destroy(monte_mc_scene *s) {
     if (!s) return;
-    cudaFree(s->d_labels); cudaFree(s->d_tab); cudaFree(s->d_cdf); cudaFree(s->d_view); cudaFree(s->d_work); cudaFree(s->d_ray); cudaFree(s->d_clear); cudaFree(s->d_invlo);
+    cudaFree(s->d_labels); cudaFree(s->d_small); cudaFree(s->d_work); cudaFree(s->d_clear);
+    if (s->h_small) cudaFreeHost(s->h_small);
     delete s;
 }
 

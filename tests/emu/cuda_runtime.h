@@ -223,6 +223,9 @@ cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
 cudaError_t monte_emu_malloc(void **p, size_t bytes);
 template <class T> static inline cudaError_t cudaMalloc(T **p, size_t bytes) { return monte_emu_malloc((void **)p, bytes); }
 cudaError_t cudaFree(void *p);
+enum { cudaHostAllocPortable = 1 };
+template <class T> static inline cudaError_t cudaHostAlloc(T **p, size_t bytes, unsigned) { return monte_emu_malloc((void **)p, bytes); }
+cudaError_t cudaFreeHost(void *p);
 cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, cudaMemcpyKind kind, cudaStream_t s);
 cudaError_t cudaMemsetAsync(void *dst, int value, size_t n, cudaStream_t s);
 cudaError_t cudaMemcpy2DAsync(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, cudaMemcpyKind kind, cudaStream_t s);

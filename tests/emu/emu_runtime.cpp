@@ -224,6 +224,7 @@ cudaError_t monte_emu_malloc(void **p, size_t bytes) {
     return cudaSuccess;
 }
 cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(dst, src, n); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void *dst, int value, size_t n, cudaStream_t) { memset(dst, value, n); return cudaSuccess; }
 cudaError_t cudaMemcpy2DAsync(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t) {
