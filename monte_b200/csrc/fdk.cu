@@ -15,6 +15,9 @@
 // per-row taps, the backprojector a gather.  Bound: FP32 pipe + L1 gather.
 #include "common.cuh"
 #include "fft_core.cuh"
+#ifndef MONTE_EMU
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#endif
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -289,6 +292,7 @@ __global__ void fdk_unpad_kernel(const float *f, float *dense, size_t rows, int 
 // backprojection
 // ------------------------------------------------------------------------------------------
 constexpr int BP_TX = 32, BP_TY = 8;   // threads: 32 along s (x-fastest, coalesced), 8 along t
+constexpr int BP_DEFAULT_VARIANT = 0;  // MONTE_BP_VARIANT overrides: 0 L1 gathers, 10 / 11 footprint staged in shared memory (4 / 3 CTAs per SM)
 
 struct BpParams {
     const float2 *pairs;        // padded rows [n_views*nv + 2][pitch] as vertical pairs (fdk_pair_kernel / fdk_pair_gather_kernel)
@@ -527,6 +531,304 @@ fdk_backproject_kernel(const __grid_constant__ BpParams p) {
     }
 }
 
+#ifndef MONTE_EMU
+// ------------------------------------------------------------------------------------------
+// Backprojection with the detector footprint of a CTA staged in shared memory by TMA.
+// A CTA owns a brick of 16 x 16 columns x ZT slices.  Per view its voxels project into a small rectangle of the
+// row-pair layout (C3: ~50 columns x ~42 rows = 17 KB) that the 4096 updates of the brick re-read ~5 times; the
+// kernel above takes those re-reads from L1 (LDG.64 x 2 per update: the L1 tag/data path was the busiest unit,
+// 83 %).  Here ONE thread issues ONE `cp.async.bulk.tensor.2d` per view (a 2-D tensor map over the pair rows; the
+// hardware clips the box at the buffer's edges), three stages deep, completion counted on `full` mbarriers; a stage
+// is handed back through an `empty` mbarrier on which every warp arrives when it has finished the view, so there
+// is no CTA-wide barrier in the loop and warps may drift a view apart.  The update reads its two texels with
+// LDS.64.  Same arithmetic on the same texels: the volume is bit-identical.  Columns whose footprint is not safely
+// inside the detector, or falls outside the staged box, take the global-memory path of the kernel above, view by
+// view.  (v1 of this kernel issued one non-tensor bulk copy per tile row from the lanes of warp 0: the compiler
+// serialises such copies lane by lane -- UBLKCP takes uniform registers -- and with a __syncthreads per view
+// the whole CTA waited for that warp: 85 ms against 56 ms; profiles/r02_fdk_smem_v1_ncu_full.txt.)
+// ------------------------------------------------------------------------------------------
+constexpr int BPS_T = 16;                        // columns per CTA along s and along t
+constexpr int BPS_STAGES = 3;
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+template <int ZT, int ZB, int MINB>
+__global__ void __launch_bounds__(BPS_T *BPS_T, MINB)
+fdk_backproject_smem_kernel(const __grid_constant__ BpParams p, const __grid_constant__ CUtensorMap tmap, const int C, const int R,
+                            const int stage_elems) {
+    extern __shared__ __align__(128) unsigned char bps_smem[];
+    float2 *tile = reinterpret_cast<float2 *>(bps_smem);                        // [BPS_STAGES][stage_elems >= R * C] row pairs
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(tile + BPS_STAGES * stage_elems);   // full[3], empty[3]
+    int2 *s_org = reinterpret_cast<int2 *>(bars + 2 * BPS_STAGES);              // [3] {c0, r0}
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // a warp covers an 8 (s) x 4 (t) patch of columns, the CTA 2 x 4 such patches
+    const int s_cta = p.s_begin + blockIdx.x * BPS_T, t_cta = p.t_begin + blockIdx.y * BPS_T;
+    const int s = s_cta + (wid & 1) * 8 + (lane & 7);
+    const int t = t_cta + (wid >> 1) * 4 + (lane >> 3);
+    const int zb = (p.z_lo / ZT) * ZT + blockIdx.z * ZT;
+    const bool valid = s < p.s_end && t < p.t_end;
+    {
+        const float Za = fmaf(-p.vox, (float)zb, p.z0), Zb = fmaf(-p.vox, (float)(zb + ZT - 1), p.z0);
+        if (Za * Zb > 0.f && fminf(fabsf(Za), fabsf(Zb)) * p.kmin > p.half_v + 2.f * p.eps_v) return;      // CTA-uniform
+    }
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8u * BPS_STAGES, tile0 = smem_u32(tile);
+    const uint32_t stage_bytes = (uint32_t)stage_elems * (uint32_t)sizeof(float2);
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < BPS_STAGES; i++) { mbar_init(bar_full + 8u * i, 1); mbar_init(bar_empty + 8u * i, BPS_T * BPS_T / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const float X = fmaf(p.vox, (float)s, p.x0);
+    const float Y = fmaf(-p.vox, (float)t, p.y0);
+    const float Z0 = fmaf(-p.vox, (float)zb, p.z0);
+    const float xoff = p.half_v * p.inv_dv;
+    // stage the footprint of view v (one thread): the box origin from the brick's corners -- the extremes of the
+    // magnification and of the transaxial coordinate over the brick are taken there
+    auto issue = [&](int v) {
+        const int b = v % BPS_STAGES;
+        const float Xa = fmaf(p.vox, (float)s_cta, p.x0), Xb = fmaf(p.vox, (float)min(s_cta + BPS_T - 1, p.s_end - 1), p.x0);
+        const float Ya = fmaf(-p.vox, (float)t_cta, p.y0), Yb = fmaf(-p.vox, (float)min(t_cta + BPS_T - 1, p.t_end - 1), p.y0);
+        const float Zl = fmaf(-p.vox, (float)(ZT - 1), Z0);
+        const float4 cv = __ldg(reinterpret_cast<const float4 *>(p.vc + v));
+        float kmn = 1e30f, kmx = -1e30f, ymn = 1e30f;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float Xc = (q & 1) ? Xb : Xa, Yc = (q & 2) ? Yb : Ya;
+            const float rx = fmaf(Xc, cv.x, fmaf(Yc, cv.y, p.dso)), ry = fmaf(Yc, cv.x, -Xc * cv.y);
+            const float k = __fdividef(p.dsd, rx);
+            kmn = fminf(kmn, k); kmx = fmaxf(kmx, k); ymn = fminf(ymn, (p.half_u - k * ry) * p.inv_du);
+        }
+        const float xa = fmaf(-kmn * p.inv_dv, Z0, xoff), xb = fmaf(-kmx * p.inv_dv, Z0, xoff);
+        const float xc = fmaf(-kmn * p.inv_dv, Zl, xoff), xd = fmaf(-kmx * p.inv_dv, Zl, xoff);
+        // one texel of slack against fp32 rounding differences with the per-thread coordinates; columns from an even
+        // index (16-byte aligned box rows).  Threads whose texels fall outside the box use the global path.
+        const int c0 = ((int)floorf(fmaxf(ymn, 0.f)) - 1) & ~1;
+        const int r0 = (int)floorf(fmaxf(fminf(fminf(xa, xb), fminf(xc, xd)), 0.f)) - 1;
+        s_org[b] = make_int2(c0, r0);
+        mbar_arrive_expect_tx(bar_full + 8u * b, (uint32_t)(R * C) * (uint32_t)sizeof(float2));
+        tma_load_2d(tile0 + (uint32_t)b * stage_bytes, &tmap, 2 * c0, v * p.nv + r0, bar_full + 8u * b);
+    };
+    if (tid == 0)
+        for (int v = 0; v < BPS_STAGES && v < p.n_views; v++) issue(v);
+
+    float acc[ZT];
+#pragma unroll
+    for (int i = 0; i < ZT; i++) acc[i] = 0.f;
+    if (p.accumulate && valid) {
+#pragma unroll
+        for (int i = 0; i < ZT; i++) {
+            const int z = zb + i;
+            if (z >= p.z_lo && z < p.z_hi) acc[i] = p.vol[((size_t)(z - p.z_lo) * p.ny + t) * p.nx + s];
+        }
+    }
+    const float hv_in = p.half_v - p.eps_v, hu_in = p.half_u - p.eps_u;
+    const float nvf = (float)p.nv, nuf = (float)p.nu;
+
+    for (int v = 0; v < p.n_views; v++) {
+        const int b = v % BPS_STAGES;
+        // the warps take turns as producer: at the start of view v, once every warp has handed back the stage of view
+        // v - 1, that stage is refilled with view v + 2 (two views of lead time)
+        if (v >= 1 && v + BPS_STAGES - 1 < p.n_views && wid == (v & 7) && lane == 0) {
+            const int u = v - 1, ub = u % BPS_STAGES;
+            const uint32_t par = (uint32_t)(u / BPS_STAGES) & 1u;
+            mbar_wait(bar_empty + 8u * ub, par);
+            mbar_wait(bar_full + 8u * ub, par);          // (its copy has landed even if no thread read it)
+            issue(v + BPS_STAGES - 1);
+        }
+        // EVERY thread passes through the full barrier of every view, also those that will not read the box: it bounds
+        // the run-ahead of a warp to the staged views (a stage is re-armed only after all warps handed it back), which
+        // keeps the arrivals on `empty` in their own phase and makes the parity waits unambiguous
+        mbar_wait(bar_full + 8u * b, (uint32_t)(v / BPS_STAGES) & 1u);
+        const int2 org = s_org[b];
+        do {
+            if (!valid) break;
+            const float4 cv = __ldg(reinterpret_cast<const float4 *>(p.vc + v));     // cb, sb, ca, sa
+            const float cb = cv.x, sb = cv.y;
+            const float rx = fmaf(X, cb, fmaf(Y, sb, p.dso));
+            const float ry = fmaf(Y, cb, -X * sb);
+            const float k = __fdividef(p.dsd, rx);
+            const float u = k * ry;
+            const float au = fabsf(u);
+            if (au > p.half_u + p.eps_u) break;                      // bp3d20.cpp:116
+            const bool u_ok = au <= hu_in;
+            float wgt;
+            if (!p.textbook) {
+                const float ts = fmaf(X, cb, -Y * sb);               // bp3d20.cpp:134-142
+                const float tt = fmaf(X, sb, Y * cb);
+                float d = fabsf(fmaf(ts, cv.z, -tt * cv.w));
+                bool neg = ts < 0.f;
+                if (fabsf(ts) < p.eps_ts) neg = bp_exact_ts_negative(p, p.vc[v], s, t);
+                d = neg ? -d : d;
+                const float e = p.wd - d;
+                wgt = __fdividef(p.wd2, e * e) * p.out_fac;
+            } else {
+                wgt = __fdividef(p.dso * p.dso, rx * rx) * p.out_fac;
+            }
+            const float y = fminf(fmaxf((p.half_u - u) * p.inv_du, 0.f), nuf);
+            const int yi = (int)y;
+            const float fy = y - (float)yi;
+            const float2 *__restrict__ fp = p.pairs + (size_t)v * p.nv * p.pitch;
+            const float kz = k * p.inv_dv;
+            const float kzv = kz * p.vox, kv = k * p.vox;
+            const float x0v = fmaf(-kz, Z0, xoff), w0v = k * Z0;
+            unsigned band = 0;
+            const float w_last = fmaf(-kv, (float)(ZT - 1), w0v);
+            if (w0v * w_last > 0.f && fminf(fabsf(w0v), fabsf(w_last)) > p.half_v + p.eps_v) break;
+            if (u_ok && fmaxf(fabsf(w0v), fabsf(w_last)) <= hv_in) {
+                const float x_last = fmaf(kzv, (float)(ZT - 1), x0v);
+                const int xlo = (int)fminf(x0v, x_last) - org.y, xhi = (int)fmaxf(x0v, x_last) - org.y, yc = yi - org.x;
+                if (yc >= 0 && yc + 1 < C && xlo >= 0 && xhi < R) {
+                    const uint32_t tb = tile0 + (uint32_t)b * stage_bytes + (uint32_t)(yc - org.y * C) * (uint32_t)sizeof(float2);
+#pragma unroll
+                    for (int h = 0; h < ZT; h += ZB) {
+                        float fx[ZB]; float2 p0[ZB], p1[ZB];
+#pragma unroll
+                        for (int i = 0; i < ZB; i++) {
+                            const float x = fmaf(kzv, (float)(h + i), x0v);
+                            const int xi = (int)x;
+                            fx[i] = x - (float)xi;
+                            const uint32_t a = tb + (uint32_t)(xi * C) * (uint32_t)sizeof(float2);
+                            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(p0[i].x), "=f"(p0[i].y) : "r"(a));
+                            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+8];" : "=f"(p1[i].x), "=f"(p1[i].y) : "r"(a));
+                        }
+#pragma unroll
+                        for (int i = 0; i < ZB; i++) {
+                            const float lo = fmaf(fx[i], p0[i].y, p0[i].x);
+                            const float hi = fmaf(fx[i], p1[i].y, p1[i].x);
+                            acc[h + i] = fmaf(wgt, fmaf(fy, hi - lo, lo), acc[h + i]);
+                        }
+                    }
+                    break;
+                }
+                // texels outside the staged box: the same updates from global memory
+                unsigned long long fcol = reinterpret_cast<unsigned long long>(fp + yi);
+                const unsigned pitch_bytes = (unsigned)p.pitch * (unsigned)sizeof(float2);
+#pragma unroll
+                for (int h = 0; h < ZT; h += ZB) {
+                    float fx[ZB], va[ZB], vb[ZB], vc2[ZB], vd[ZB];
+#pragma unroll
+                    for (int i = 0; i < ZB; i++) {
+                        const float x = fmaf(kzv, (float)(h + i), x0v);
+                        const int xi = (int)x;
+                        fx[i] = x - (float)xi;
+                        const float2 *__restrict__ q = reinterpret_cast<const float2 *>(fcol + (unsigned long long)(unsigned)xi * pitch_bytes);
+                        const float2 q0 = __ldg(q), q1 = __ldg(q + 1);
+                        va[i] = q0.x; vc2[i] = q0.y; vb[i] = q1.x; vd[i] = q1.y;
+                    }
+#pragma unroll
+                    for (int i = 0; i < ZB; i++) {
+                        const float lo = fmaf(fx[i], vc2[i], va[i]);
+                        const float hi = fmaf(fx[i], vd[i], vb[i]);
+                        acc[h + i] = fmaf(wgt, fmaf(fy, hi - lo, lo), acc[h + i]);
+                    }
+                }
+                break;
+            }
+            {
+                unsigned long long fcol = reinterpret_cast<unsigned long long>(fp + yi);
+                const unsigned pitch_bytes = (unsigned)p.pitch * (unsigned)sizeof(float2);
+#pragma unroll
+                for (int h = 0; h < ZT; h += ZB) {
+                    float fx[ZB], va[ZB], vb[ZB], vc2[ZB], vd[ZB];
+                    bool ok[ZB];
+#pragma unroll
+                    for (int i = 0; i < ZB; i++) {
+                        const float fi = (float)(h + i);
+                        const float w = fmaf(-kv, fi, w0v);
+                        const float aw = fabsf(w);
+                        float x = fmaf(kzv, fi, x0v);
+                        ok[i] = u_ok && aw <= hv_in;
+                        if (fabsf(aw - p.half_v) < p.eps_v || (!u_ok && aw < p.half_v + p.eps_v)) band |= 1u << (h + i);
+                        x = fminf(fmaxf(x, 0.f), nvf);
+                        const int xi = (int)x;
+                        fx[i] = x - (float)xi;
+                        const float2 *__restrict__ q = reinterpret_cast<const float2 *>(fcol + (unsigned long long)(unsigned)xi * pitch_bytes);
+                        const float2 q0 = __ldg(q), q1 = __ldg(q + 1);
+                        va[i] = q0.x; vc2[i] = q0.y; vb[i] = q1.x; vd[i] = q1.y;
+                    }
+#pragma unroll
+                    for (int i = 0; i < ZB; i++) {
+                        const float lo = fmaf(fx[i], vc2[i], va[i]);
+                        const float hi = fmaf(fx[i], vd[i], vb[i]);
+                        const float val = fmaf(fy, hi - lo, lo);
+                        acc[h + i] = fmaf(ok[i] ? wgt : 0.f, val, acc[h + i]);
+                    }
+                }
+                if (band) {
+#pragma unroll
+                    for (int i = 0; i < ZT; i++)
+                        if (band & (1u << i)) acc[i] += bp_fix_one(p, p.vc[v], s, t, zb + i, p.pairs + (size_t)v * p.nv * p.pitch, wgt);
+                }
+            }
+        } while (0);
+        // this warp is done with the stage of view v
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8u * b);
+    }
+    // the last staged boxes may still be in flight: a CTA must not exit under an outstanding bulk copy
+    if (tid == 0)
+        for (int v = max(p.n_views - BPS_STAGES, 0); v < p.n_views; v++) mbar_wait(bar_full + 8u * (v % BPS_STAGES), (uint32_t)(v / BPS_STAGES) & 1u);
+    if (!valid) return;
+#pragma unroll
+    for (int i = 0; i < ZT; i++) {
+        const int z = zb + i;
+        if (z >= p.z_lo && z < p.z_hi) {
+            float r = acc[i];
+            if (z < p.roi_z_begin || z >= p.roi_z_end) r = 0.f;
+            if (p.mask_r2 >= 0) {
+                const long long dz = z - p.mask_cz, dt = t - p.mask_ct, ds = s - p.mask_cs;
+                if (dz * dz + dt * dt + ds * ds > p.mask_r2) r = 0.f;
+            }
+            p.vol[((size_t)(z - p.z_lo) * p.ny + t) * p.nx + s] = r;
+        }
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libmonte_gpu does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_pairs_tensor_map(CUtensorMap *out, const float2 *pairs, size_t rows, int pitch, int C, int R) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        MONTE_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr));
+        if (!sym || qr != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return MONTE_E_CUDA; }
+        fn = (EncodeTiledFn)sym;
+    }
+    // the pair rows as a 2-D fp32 tensor [rows][2 * pitch]; box = 2C floats x R rows; reads outside it give zeros
+    const cuuint64_t dims[2] = {(cuuint64_t)2 * pitch, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float2)};
+    const cuuint32_t box[2] = {(cuuint32_t)(2 * C), (cuuint32_t)R}, estr[2] = {1, 1};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)pairs, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for %zu rows of pitch %d, box %d x %d", (int)r, rows, pitch, C, R); return MONTE_E_CUDA; }
+    return MONTE_OK;
+}
+#endif   // !MONTE_EMU
+
 // vol_zy[s][t][z] = vol_xy[z][t][s]  (32x32 tiles of the (z,s) plane for every t)
 __global__ void fdk_transpose_kernel(const float *__restrict__ in, float *__restrict__ out, int nx, int ny, int nz) {
     __shared__ float tile[32][33];
@@ -564,7 +866,7 @@ static PerDev<FdkCache> g_fdk_pd;
 constexpr int FDK_MAXC = 16;
 struct FdkDevState {
     bool fft_attr_set = false;
-    size_t filter_smem_set = 0;
+    size_t filter_smem_set = 0, bps_smem_set[2] = {0, 0};
     cudaEvent_t ev_up[FDK_MAXC] = {nullptr}, ev_slab[FDK_MAXC] = {nullptr}, ev_t[6] = {nullptr};
 };
 static PerDev<FdkDevState> g_fdk_state;
@@ -831,8 +1133,8 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
     p.nu_half = g->nu / 2.; p.nv_half = g->nv / 2.;
     dim3 block(BP_TX, BP_TY);
     // tuning knob (default = the fastest measured variant): MONTE_BP_VARIANT=0..3
-    static int variant = -1;
-    if (variant < 0) { const char *e = getenv("MONTE_BP_VARIANT"); variant = e ? atoi(e) : 0; }
+    int variant;                                                     // (read per call: tests and A/B scripts flip it)
+    { const char *e = getenv("MONTE_BP_VARIANT"); variant = e ? atoi(e) : BP_DEFAULT_VARIANT; }
 #define BP_LAUNCH(ZT, ZB, MINB)                                                                          \
     do {                                                                                                 \
         dim3 grid(ceil_div(g->s_end - g->s_begin, BP_TX), ceil_div(g->t_end - g->t_begin, BP_TY),        \
@@ -857,7 +1159,7 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
     }
     // vertical row pairs of the views of this call (+ the rows the last view reaches into)
     const int rows_total = g->n_views * g->nv + 2;
-    float2 *d_pairs = (float2 *)scratch(8, (size_t)rows_total * p.pitch * sizeof(float2));
+    float2 *d_pairs = (float2 *)scratch(8, (size_t)rows_total * p.pitch * sizeof(float2) + 65536);   // (+ slack: staged tile rows may end past the last row)
     if (!d_pairs) return MONTE_E_NOMEM;
     {
         int b_lo, b_hi;
@@ -890,11 +1192,42 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
     p.vc = g_fdk.d_vc + vb;
     p.pairs = d_pairs + (size_t)vb * g->nv * p.pitch; p.accumulate = continue_sum || vb > view_lo;
     switch (variant) {
+#ifndef MONTE_EMU
+        case 10: case 11: {
+            // footprint staged in shared memory by TMA (fdk_backproject_smem_kernel): box = the largest rectangle of row
+            // pairs a 16 x 16 x 16 brick can project onto, from the geometry
+            const double rf = 0.5 * g->vox * sqrt((double)g->nx * g->nx + (double)g->ny * g->ny) +
+                              fmax(fabs(g->x0 + 0.5 * g->vox * g->nx), fabs(g->y0 - 0.5 * g->vox * g->ny));
+            const double kmax = g->dsd / fmax(g->dso - rf, 0.1 * g->dso);
+            const double diag = (BPS_T - 1) * sqrt(2.0);
+            int C = (int)ceil(diag * g->vox * kmax / g->du + 5.0);
+            C = (C + 1) & ~1;
+            const double zmax = fmax(fabs(g->z0), fabs(g->z0 - g->vox * (g->nz - 1)));
+            const double dk = kmax * (diag * g->vox) / fmax(g->dso - rf, 0.1 * g->dso);
+            const int R = (int)ceil(15.0 * g->vox * kmax / g->dv + zmax / g->dv * dk + 4.0);
+            const int stage_elems = (R * C + 15) & ~15;                                   // stages start 128-byte aligned
+            const size_t smem = (size_t)BPS_STAGES * stage_elems * sizeof(float2) + 2 * BPS_STAGES * sizeof(unsigned long long) + BPS_STAGES * sizeof(int2);
+            if (C >= 8 && C <= 128 && R <= 256 && smem <= 100 * 1024) {
+                FdkDevState &ds = g_fdk_state.get();
+                auto fn = variant == 10 ? fdk_backproject_smem_kernel<16, 8, 4> : fdk_backproject_smem_kernel<16, 8, 3>;
+                if (smem > ds.bps_smem_set[variant - 10]) {
+                    MONTE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    ds.bps_smem_set[variant - 10] = smem;
+                }
+                CUtensorMap tmap;
+                if (int rc = make_pairs_tensor_map(&tmap, p.pairs, (size_t)rows_total - (size_t)vb * g->nv, p.pitch, C, R)) return rc;
+                dim3 grid(ceil_div(g->s_end - g->s_begin, BPS_T), ceil_div(g->t_end - g->t_begin, BPS_T), ceil_div(z_hi - (z_lo / 16) * 16, 16));
+                fn<<<grid, BPS_T * BPS_T, smem, st>>>(p, tmap, C, R, stage_elems);
+                break;
+            }
+        }   // (tile too large for shared memory: the L1 kernel)
+        // fallthrough
+#endif
+        case 0: default: BP_LAUNCH(16, 8, 4); break;    // 64 registers (4 bytes spilled), 4 CTAs/SM = 32 warps: 56.2 ms -- the gathers'
+                                                // latency (long scoreboard, the top stall) is hidden by more resident warps
         case 1: BP_LAUNCH(32, 8, 2); break;     // 32 slices per thread, 2 CTAs/SM: 74.8 ms at C3 (before the 12-instruction update)
         case 2: BP_LAUNCH(16, 8, 3); break;     // 80 registers, 3 CTAs/SM: 61.9 ms
         case 3: BP_LAUNCH(16, 16, 3); break;    // gather batches of 16: 58.6 ms
-        default: BP_LAUNCH(16, 8, 4); break;    // 64 registers (4 bytes spilled), 4 CTAs/SM = 32 warps: 56.2 ms -- the gathers'
-                                                // latency (long scoreboard, the top stall) is hidden by more resident warps
     }
     }
 #undef BP_LAUNCH

@@ -235,3 +235,38 @@ def test_bad_arguments_are_reported_not_fatal(monte):
             monte.fdk_filter_dev(gw, d, f)
     finally:
         del os.environ["MONTE_FDK_FILTER"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["10", "11"])
+def test_tma_staged_backprojector_gives_the_bits_of_the_default_kernel(monte, variant):
+    """MONTE_BP_VARIANT=10/11: the footprint of a 16x16x16 brick staged in shared memory by TMA (cp.async.bulk.tensor.2d,
+    3 stages, full/empty mbarriers) instead of gathered through L1 -- same arithmetic on the same texels, so the volume is
+    bit-identical, including ROI / mask handling, ragged sizes and the view-chunk continuation"""
+    import torch
+    for n_views, nu, nv, n, roi in ((31, 96, 40, 40, False), (48, 65, 65, 32, True), (90, 300, 200, 96, False)):
+        g = _abi.generic_fdk_geom(n_views, nu, nv, n)
+        if roi:
+            g.s_begin, g.s_end, g.t_begin, g.t_end, g.z_begin, g.z_end = 3, n - 5, 2, n - 1, 4, n - 6
+            g.mask_cs = g.mask_ct = g.mask_cz = n // 2
+            g.mask_r2 = (n // 2 - 2) ** 2
+        gen = torch.Generator(device="cuda").manual_seed(n_views)
+        proj = torch.rand((n_views, nu, nv), device="cuda", generator=gen)
+        filt = torch.zeros(monte.fdk_filtered_shape(g), device="cuda")
+        monte.fdk_filter_dev(g, proj, filt)
+        vols = {}
+        for var in ("0", variant):
+            os.environ["MONTE_BP_VARIANT"] = var
+            try:
+                v = torch.full((n, n, n), float("nan"), device="cuda")
+                monte.fdk_backproject_dev(g, filt, v)
+                # ... and in two view pieces that continue the stored partial sums
+                w = torch.full((n, n, n), float("nan"), device="cuda")
+                monte.fdk_backproject_views_dev(g, filt, w, 0, n, 0, n_views // 3, False)
+                monte.fdk_backproject_views_dev(g, filt, w, 0, n, n_views // 3, n_views, True)
+                torch.cuda.synchronize()
+            finally:
+                del os.environ["MONTE_BP_VARIANT"]
+            assert torch.equal(v, w)
+            vols[var] = v
+        assert bool(torch.isfinite(vols["0"]).all()) and torch.equal(vols["0"], vols[variant])
