@@ -49,9 +49,11 @@ struct McSceneDev {
     int eid;                    // energy-integrating detector: tally (int)(E*16+0.5) instead of 1
 };
 
+struct PhiloxKeys { uint32_t rk[10]; };   // key + r * 0x9E3779B9, r = 0..9 (see philox2x32_10)
+
 struct McLaunch {
     McSceneDev sc;
-    uint32_t key;
+    PhiloxKeys key;               // the ten Philox round keys of this launch's seed
     int view_begin;
     uint32_t n_begin, cnt, per;   // photons [n_begin, n_begin+cnt) of every pixel; per = id-space size
     unsigned long long total;     // histories of this launch
@@ -61,7 +63,7 @@ struct McLaunch {
     unsigned long long *work;     // unit counter (zeroed by the host)
     uint32_t *fates;              // RECORD only
     float *fate_e;
-    uint32_t second_min;          // run the runner-up phase on the same vote if >= this many lanes wait for it
+    uint32_t vote_bias;           // (128 - T) in every byte: a phase runs on a vote when >= T lanes wait for it (T = 16)
     // RAYLEIGH instantiations only (appended: the parameter offsets of everything above do not move)
     const float *ray;             // [n_mat][2][ray_n]: x^2 grid, then cumulative F^2 (monte_mc_xs.ff_x2 / ff_cum)
     int ray_n;
@@ -79,14 +81,16 @@ struct McLaunch {
 enum { ST_HIST = 0, ST_PRIM, ST_SCAT, ST_ABS, ST_INT, ST_COH, ST_COMP, ST_STEPS, ST_EPRIM, ST_ESCAT };
 
 // ---- Philox2x32-10 (Salmon, Moraes, Dror, Shaw, SC'11): counter (c0,c1), 32-bit key ---------
-__device__ __forceinline__ uint2 philox2x32_10(uint32_t c0, uint32_t c1, uint32_t key) {
+// rk[r] = key + r * 0x9E3779B9 (the key schedule) is the same for every history of a launch: the host computes the ten
+// round keys once and the kernel reads them from the parameter (constant) bank as an operand of the round's LOP3,
+// instead of every lane bumping its own copy every round (3.1 % of the kernel's instructions, ncu source page r02).
+__device__ __forceinline__ uint2 philox2x32_10(uint32_t c0, uint32_t c1, const PhiloxKeys &k) {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
         const uint32_t hi = __umulhi(0xD256D193u, c0);
         const uint32_t lo = 0xD256D193u * c0;
-        c0 = hi ^ key ^ c1;
+        c0 = hi ^ k.rk[r] ^ c1;
         c1 = lo;
-        key += 0x9E3779B9u;
     }
     return make_uint2(c0, c1);
 }
@@ -158,6 +162,8 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
     float *s_invlo = s_ray + sc.n_mat * 2 * ray_stride;                // CLEAR: [201 (+3)], then the thresholds [201 (+3)]
     float *s_thr = s_invlo + TAB_ROWS + 3;
     uint4 *s_slots = reinterpret_cast<uint4 *>(s_invlo + (CLEAR ? 2 * (TAB_ROWS + 3) : 0)) + (threadIdx.x >> 5) * (NG * GSTRIDE);
+    // per-warp cache of the last pixel's source ray (pencil source, one energy: the `per` photons of a pixel share it)
+    uint4 *s_src = s_slots + (MC_THREADS / 32 - (threadIdx.x >> 5)) * (NG * GSTRIDE) + (threadIdx.x >> 5) * 3;
     for (int i = threadIdx.x; i < sc.n_mat * TAB_ROWS; i += MC_THREADS) s_tab[i] = sc.tab[i];
     for (int i = threadIdx.x; i < TAB_ROWS; i += MC_THREADS) s_inv[i] = sc.inv_mumax[i];
     for (int i = threadIdx.x; i <= sc.n_bins && sc.n_bins > 0; i += MC_THREADS) s_cdf[i] = sc.cdf[i];
@@ -178,6 +184,9 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
 #define WORD(g, w) (reinterpret_cast<uint32_t *>(slot + (g) * GSTRIDE)[w])
 #define WORDF(g, w) (reinterpret_cast<float *>(slot + (g) * GSTRIDE)[w])
 
+    const bool src_cached = sc.source_mode != MONTE_MC_SOURCE_CONE && sc.n_bins == 0;
+    if ((threadIdx.x & 31) == 0) s_src[2] = make_uint4(0xffffffffu, 0u, 0u, 0u);   // tag: no pixel yet
+    __syncwarp();
     uint32_t st = ALL * P_REFILL;                                      // one-hot phase per slot
 #pragma unroll
     for (int j = 0; j < K; j++) s_slots[G_ID * GSTRIDE + j * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);   // no pending detection
@@ -198,16 +207,22 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
         if (st & (ALL * P_COMPTON)) onehot |= 1u << 24;
         const uint32_t cnts = __reduce_add_sync(0xffffffffu, onehot);
         if (cnts == 0u) break;                                          // every slot of every lane is done
-        // keys = count << 4 | phase bit; the two best phases are run on one vote (the second one's
-        // count can only have grown meanwhile), which halves the voting overhead per phase visit
-        const uint32_t k_ref = ((cnts & 0xFFu) << 4) | P_REFILL, k_step = (((cnts >> 8) & 0xFFu) << 4) | P_STEP;
-        const uint32_t k_col = (((cnts >> 16) & 0xFFu) << 4) | P_COLLIDE, k_kah = ((cnts >> 24) << 4) | P_COMPTON;
-        const uint32_t ka = max(k_ref, k_step), kb = max(k_col, k_kah), kc = min(k_ref, k_step), kd = min(k_col, k_kah);
-        const uint32_t key1 = max(ka, kb), key2 = max(min(ka, kb), ka > kb ? kc : kd);
-      for (int pass = 0; pass < 2; pass++) {
-        const uint32_t key = pass ? key2 : key1;
-        if (pass && (key >> 4) < P.second_min) break;                   // second phase only if it is well filled
-        const uint32_t phase = key & 0xFu;
+        // Every phase in which at least `second_min` (16) lanes wait is run on this one vote, in pipeline order STEP ->
+        // COLLIDE -> COMPTON -> REFILL (each feeds the next, so the stale counts of the later ones can only have grown).
+        // Bit 7 of byte p of `todo` = phase p qualifies: count + (128 - T) carries into bit 7 iff count >= T (counts <= 32,
+        // no carry between bytes).  Near the end of the grid no phase qualifies: then the fullest one runs alone.
+        uint32_t todo = (cnts + P.vote_bias) & 0x80808080u;
+        if (todo == 0u) {
+            const uint32_t c_r = cnts & 0xFFu, c_s = (cnts >> 8) & 0xFFu, c_c = (cnts >> 16) & 0xFFu, c_k = cnts >> 24;
+            const uint32_t mx = max(max(c_r, c_s), max(c_c, c_k));
+            todo = c_s == mx ? 0x8000u : c_c == mx ? 0x800000u : c_k == mx ? 0x80000000u : 0x80u;
+        }
+      while (todo) {
+        uint32_t phase;
+        if (todo & 0x8000u) { phase = P_STEP; todo &= ~0x8000u; }
+        else if (todo & 0x800000u) { phase = P_COLLIDE; todo &= ~0x800000u; }
+        else if (todo & 0x80000000u) { phase = P_COMPTON; todo &= ~0x80000000u; }
+        else { phase = P_REFILL; todo = 0u; }
         const uint32_t mine = st & (ALL * phase);
         const bool active = mine != 0u;
         const int j = active ? ((__ffs(mine) - 1) >> 2) : 0;            // my slot in that phase
@@ -299,14 +314,14 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                     st = (st & clrq) | (P_REFILL << (4 * jj[q]));
                     continue;
                 }
-                if (lab2[q] == 0) continue;                               // air: virtual collision
-                const int mat = min(lab2[q], sc.n_mat) - 1;
-                if (CLEAR) {                                              // acceptance against the majorant the step was sampled with
-                    const float ratio = lo2[q] ? s_tab[mat * TAB_ROWS + kE].w : s_tab[mat * TAB_ROWS + kE].x;
-                    if (u01(r2[q].y) > ratio) continue;
-                } else if (u01(r2[q].y) > s_tab[mat * TAB_ROWS + kE].x) continue;    // virtual collision, :941-961
-                WORD(G_ID, 1) = (meta & ~0x7000u) | ((uint32_t)mat << 12);
-                st = (st & clrq) | (P_COLLIDE << (4 * jj[q]));
+                // inside: air and rejected tentative collisions change nothing more; an accepted one records its material
+                // and moves the slot to COLLIDE.  Selects, not branches: the lanes of a warp take all three outcomes.
+                const int mat = max(min(lab2[q], sc.n_mat) - 1, 0);
+                const float4 tb = s_tab[mat * TAB_ROWS + kE];
+                const float ratio = CLEAR && lo2[q] ? tb.w : tb.x;    // acceptance against the majorant the step was sampled with
+                const bool accept = lab2[q] != 0 && !(u01(r2[q].y) > ratio);        // virtual collision otherwise, :941-961
+                if (accept) WORD(G_ID, 1) = (meta & ~0x7000u) | ((uint32_t)mat << 12);
+                st = accept ? ((st & clrq) | (P_COLLIDE << (4 * jj[q]))) : st;
             }
             continue;
         }
@@ -452,6 +467,11 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             }
         }
         const unsigned m_ref = __ballot_sync(0xffffffffu, active);
+        // the cached source ray of this warp: read by all lanes together, right after the ballot and before anything
+        // divergent, so that the one lane that may refresh it further down cannot overtake a reader
+        __syncwarp();
+        const uint4 sca = s_src[0], scb = s_src[1], scc = s_src[2];
+        const uint32_t first_off = next_off;
         const uint32_t my_off = next_off + __popc(m_ref & lt_mask);
         next_off = min(next_off + (uint32_t)__popc(m_ref), unit_cnt);
         if (!active) continue;
@@ -508,12 +528,21 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             if (RECORD) { rec_idx = pix * P.per + n; WORD(G_REC, 0) = rec_idx; }
             c_hist++;
             // ---- source, CBCT_real325im.cu:464-540 (exact aim at the pixel) ----
+            float E, dx, dy, dz, ex, ey, ez;
+            int kE;
+            uint32_t qe = 0u;
+            bool miss;
+            if (src_cached && scc.x == pva) {                 // same pixel as the cached ray: nothing to compute
+                ex = __uint_as_float(sca.x); ey = __uint_as_float(sca.y); ez = __uint_as_float(sca.z); E = __uint_as_float(sca.w);
+                dx = __uint_as_float(scb.x); dy = __uint_as_float(scb.y); dz = __uint_as_float(scb.z);
+                miss = scb.w != 0u; qe = scc.y; kE = (int)scc.z;
+            } else {
             float uy = 0.5f, uz = 0.5f;
             if (sc.source_mode == MONTE_MC_SOURCE_CONE) {
                 const uint2 r = philox2x32_10(c0, c1hi | (STREAM_SOURCE << 22), P.key);
                 uy = u01(r.x); uz = u01(r.y);
             }
-            float E = sc.mono_keV;
+            E = sc.mono_keV;
             if (sc.n_bins > 0) {                              // CBCT_real325im.cu:492-498
                 const uint2 r = philox2x32_10(c0, c1hi | (STREAM_SOURCE << 22) | 1u, P.key);
                 const float ue = u01(r.x);
@@ -521,15 +550,15 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (ue <= s_cdf[mid + 1]) hi = mid; else lo = mid + 1; }
                 if (lo < sc.n_bins) E = (float)(lo + 1) * sc.bin_keV;
             }
-            const int kE = min(max((int)(E + 0.5f), 0), TAB_ROWS - 1);
+            kE = min(max((int)(E + 0.5f), 0), TAB_ROWS - 1);
             const float yl = sc.half - sc.pixel * ((float)pi + uy);
             const float zl = sc.half - sc.pixel * ((float)pj + uz);
             const float rn = rsqrtf(sc.dsd * sc.dsd + yl * yl + zl * zl);
             const float2 cs = __ldg(sc.view_cs + view);
             const float dxr = sc.dsd * rn, dyr = yl * rn;
-            const float dx = dxr * cs.x - dyr * cs.y;
-            const float dy = dxr * cs.y + dyr * cs.x;
-            const float dz = zl * rn;
+            dx = dxr * cs.x - dyr * cs.y;
+            dy = dxr * cs.y + dyr * cs.x;
+            dz = zl * rn;
             const float sx = -sc.dso * cs.x, sy = -sc.dso * cs.y;
             // analytic flight to the clip box: branch-free slab method (a zero direction component gives
             // +-inf bounds, which fminf/fmaxf handle; CUDA's fminf/fmaxf drop a NaN operand)
@@ -543,7 +572,27 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                     t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
                 }
             }
-            if (t0 >= t1) {                                   // misses the phantom: unscattered
+            miss = t0 >= t1;
+            ex = fmaf(t0, dx, sx); ey = fmaf(t0, dy, sy); ez = t0 * dz;
+            if (CLEAR && !miss) {                             // clearance of the cell the photon enters through
+                // the entry point lies exactly on a voxel face of the clip box: take the voxel 1e-3 of a voxel
+                // side further along the ray, so that the choice does not hang on rounding (the oracle does the same)
+                int ix = __float_as_int(fmaf(ex, sc.inv_pitch, vox_off[0]) + 1e-3f * dx + 12582912.0f) - 0x4B400000;
+                int iy = __float_as_int(fmaf(ey, sc.inv_pitch, vox_off[1]) + 1e-3f * dy + 12582912.0f) - 0x4B400000;
+                int iz = __float_as_int(fmaf(ez, sc.inv_pitch, vox_off[2]) + 1e-3f * dz + 12582912.0f) - 0x4B400000;
+                ix = min(max(ix, 0), sc.nx - 1); iy = min(max(iy, 0), sc.ny - 1); iz = min(max(iz, 0), sc.nz - 1);
+                const unsigned oc = (dx > 0.f ? 1u : 0u) | (dy > 0.f ? 2u : 0u) | (dz > 0.f ? 4u : 0u);
+                qe = __ldg(P.clear + oc * P.coct + ((unsigned)((iz >> P.cshift) * P.cgy + (iy >> P.cshift)) * (unsigned)P.cgx + (unsigned)(ix >> P.cshift)));
+            }
+            // the first lane of the visit refreshes the cache (one writer: entries are never mixed; readers took their copy
+            // right after the ballot)
+            if (src_cached && my_off == first_off) {
+                s_src[0] = make_uint4(__float_as_uint(ex), __float_as_uint(ey), __float_as_uint(ez), __float_as_uint(E));
+                s_src[1] = make_uint4(__float_as_uint(dx), __float_as_uint(dy), __float_as_uint(dz), miss ? 1u : 0u);
+                s_src[2] = make_uint4(pva, qe, (uint32_t)kE, 0u);
+            }
+            }
+            if (miss) {                                       // misses the phantom: unscattered
                 if (pva != cur_pv) {
                     if (prim_cnt) { atomicAdd(P.image0 + cur_pv, (int)prim_cnt); atomicAdd(P.image5 + cur_pv, (int)prim_cnt); }
                     cur_pv = pva; prim_cnt = 0;
@@ -553,25 +602,13 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 if (RECORD) { P.fates[rec_idx] = 1u | (pix << 8); P.fate_e[rec_idx] = E; }
                 // the slot stays in REFILL and takes another history on the next visit
             } else {
-                const float ex = fmaf(t0, dx, sx), ey = fmaf(t0, dy, sy), ez = t0 * dz;
-                uint32_t qe = 0u;
-                if (CLEAR) {                                  // clearance of the cell the photon enters through
-                    // the entry point lies exactly on a voxel face of the clip box: take the voxel 1e-3 of a voxel
-                    // side further along the ray, so that the choice does not hang on rounding (the oracle does the same)
-                    int ix = __float_as_int(fmaf(ex, sc.inv_pitch, vox_off[0]) + 1e-3f * dx + 12582912.0f) - 0x4B400000;
-                    int iy = __float_as_int(fmaf(ey, sc.inv_pitch, vox_off[1]) + 1e-3f * dy + 12582912.0f) - 0x4B400000;
-                    int iz = __float_as_int(fmaf(ez, sc.inv_pitch, vox_off[2]) + 1e-3f * dz + 12582912.0f) - 0x4B400000;
-                    ix = min(max(ix, 0), sc.nx - 1); iy = min(max(iy, 0), sc.ny - 1); iz = min(max(iz, 0), sc.nz - 1);
-                    const unsigned oc = (dx > 0.f ? 1u : 0u) | (dy > 0.f ? 2u : 0u) | (dz > 0.f ? 4u : 0u);
-                    qe = __ldg(P.clear + oc * P.coct + ((unsigned)((iz >> P.cshift) * P.cgy + (iy >> P.cshift)) * (unsigned)P.cgx + (unsigned)(ix >> P.cshift)));
-                }
                 *reinterpret_cast<float4 *>(&GRP(G_POS)) = make_float4(ex, ey, ez, E);
                 *reinterpret_cast<float4 *>(&GRP(G_DIR)) = make_float4(dx, dy, dz, 0.f);
                 GRP(G_ID) = make_uint4(c0, c1hi | (qe << 17) | (uint32_t)kE, 0u, ((uint32_t)view << 20) | pix);
                 st = (st & clr) | (P_STEP << (4 * j));
             }
         }
-      }   // pass
+      }   // phases of this vote
     }
 #undef GRP
 #undef WORD
@@ -981,7 +1018,10 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     MONTE_ARG(s->dev.eid || per < (1u << 30), "mc: %u photons per pixel could overflow the int32 tallies; split the run", per);
     McLaunch L;
     L.sc = s->dev;
-    L.key = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u);
+    {
+        const uint32_t key = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u);
+        for (int r = 0; r < 10; r++) L.key.rk[r] = key + (uint32_t)r * 0x9E3779B9u;
+    }
     L.view_begin = view_begin; L.n_begin = n_begin; L.cnt = n_end - n_begin; L.per = per;
     L.total = (unsigned long long)(view_end - view_begin) * npix * L.cnt;
     L.n_units = (L.total + MC_UNIT - 1) / MC_UNIT;
@@ -993,7 +1033,11 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     L.cgx = s->cg[0]; L.cgy = s->cg[1]; L.cshift = s->cshift; L.cunit = s->cunit;
     L.clear_thr = L.inv_mulo ? L.inv_mulo + TAB_ROWS : nullptr;
     L.coct = s->coct;
-    { static int sm = -1; if (sm < 0) { const char *e = getenv("MONTE_MC_SECOND"); sm = e ? atoi(e) : 16; } L.second_min = (uint32_t)sm; }
+    {
+        static int thr = -1;                                           // MONTE_MC_SECOND=T: lanes a phase needs to run on a vote (1..32)
+        if (thr < 0) { const char *e = getenv("MONTE_MC_SECOND"); thr = e ? atoi(e) : 16; if (thr < 1) thr = 1; if (thr > 32) thr = 32; }
+        L.vote_bias = (uint32_t)(128 - thr) * 0x01010101u;
+    }
     if (L.total == 0) return MONTE_OK;
     MONTE_CUDA(cudaMemsetAsync(L.work, 0, sizeof(unsigned long long), st));
     const int sms = ctx().sm_count;
@@ -1008,7 +1052,8 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     const bool clear = s->heavy >= 0;        // two-level majorant: its own instantiations too
     const int which = rayleigh || clear ? 35 : which_env;
     const int K = which >= 31 && which <= 36 ? which - 30 : (which == 44 ? 4 : (which == 43 ? 3 : 5));
-    const size_t slot_bytes = (size_t)K * 32 * mc_slot_groups(rec != 0) * sizeof(uint4) * (MC_THREADS / 32);
+    const size_t slot_bytes = (size_t)K * 32 * mc_slot_groups(rec != 0) * sizeof(uint4) * (MC_THREADS / 32) +
+                              (MC_THREADS / 32) * 3 * sizeof(uint4);                      // + the per-warp source-ray cache
     const size_t smem = (size_t)s->dev.n_mat * TAB_ROWS * sizeof(float4) +
                         (TAB_ROWS + 3 + ((s->dev.n_bins + 1 + 3) & ~3)) * sizeof(float) + slot_bytes +
                         (rayleigh ? (size_t)s->dev.n_mat * 2 * ((s->ray_n + 3) & ~3) * sizeof(float) : 0) +
