@@ -579,7 +579,7 @@ def ref_cuda_record():
     try:
         with open(os.path.join(ROOT, "profiles", "r02_ref_cuda.json")) as f:
             r = json.load(f)
-        return {k: r[k] for k in ("binary", "histories", "wall_s", "whole_program_hist_per_s", "kernel_s", "kernel_hist_per_s",
+        return {k: r[k] for k in ("binary", "histories", "wall_s", "whole_program_hist_per_s", "kernel_hist_per_s", "chi2_z",
                                   "ours_hist_per_s_kernel", "speedup_kernel", "chi2_image0", "chi2_dof") if k in r} | \
                {"kind": "reference (CUDA, sm_100)", "source": "profiles/r02_ref_cuda.json (recorded, same GPU model)"}
     except Exception:

@@ -36,6 +36,7 @@ struct McSceneDev {
     int nx, ny, nz;
     float inv_pitch;
     float org[3], clip_lo[3], clip_hi[3];
+    float vox_off[3];           // -org * inv_pitch - 0.5 (one rounding): voxel index = round-to-nearest(pos * inv_pitch + vox_off)
     const float4 *tab;          // [n_mat][201]: {mu_m/mu_max, photo/total, (photo+coh)/total, 0}
     const float *inv_mumax;     // [201]
     int n_mat;
@@ -177,7 +178,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t npix = (uint32_t)(sc.det_ny * sc.det_nx);
-    const float vox_off[3] = {-sc.org[0] * sc.inv_pitch - 0.5f, -sc.org[1] * sc.inv_pitch - 0.5f, -sc.org[2] * sc.inv_pitch - 0.5f};
+    const float *vox_off = sc.vox_off;                                 // (parameter bank: an operand, not registers)
     constexpr uint32_t ALL = (K == 6) ? 0x111111u : (K == 5) ? 0x11111u : (K == 4) ? 0x1111u : (K == 3) ? 0x0111u : (K == 2) ? 0x0011u : 0x0001u;
 
 #define GRP(g) (slot[(g) * GSTRIDE])
@@ -217,20 +218,16 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             const uint32_t mx = max(max(c_r, c_s), max(c_c, c_k));
             todo = c_s == mx ? 0x8000u : c_c == mx ? 0x800000u : c_k == mx ? 0x80000000u : 0x80u;
         }
-      while (todo) {
-        uint32_t phase;
-        if (todo & 0x8000u) { phase = P_STEP; todo &= ~0x8000u; }
-        else if (todo & 0x800000u) { phase = P_COLLIDE; todo &= ~0x800000u; }
-        else if (todo & 0x80000000u) { phase = P_COMPTON; todo &= ~0x80000000u; }
-        else { phase = P_REFILL; todo = 0u; }
-        const uint32_t mine = st & (ALL * phase);
-        const bool active = mine != 0u;
-        const int j = active ? ((__ffs(mine) - 1) >> 2) : 0;            // my slot in that phase
-        uint4 *slot = s_slots + j * 32 + lane;
+        // the qualifying phases, straight-line (no phase variable, no compare chain)
+#define MC_PHASE_SLOT(PH)                                                                                   \
+        const uint32_t mine = st & (ALL * (PH));                                                              \
+        const bool active = mine != 0u;                                                                       \
+        const int j = active ? ((__ffs(mine) - 1) >> 2) : 0;            /* my slot in that phase */           \
+        uint4 *slot = s_slots + j * 32 + lane;                                                                \
         const uint32_t clr = ~(0xFu << (4 * j));
-
-        if (phase == P_STEP) {
-            if (!active) continue;
+        if (todo & 0x8000u) do {                                        // ======== STEP
+        MC_PHASE_SLOT(P_STEP)
+            if (!active) break;
             // ---------------- Woodcock steps, CBCT_real325im.cu:886-968 ---------------
             // Two slots of the lane are advanced per visit when it has two waiting (the second one is
             // predicated off otherwise): the two Philox chains and the two label fetches are independent,
@@ -323,11 +320,12 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 if (accept) WORD(G_ID, 1) = (meta & ~0x7000u) | ((uint32_t)mat << 12);
                 st = accept ? ((st & clrq) | (P_COLLIDE << (4 * jj[q]))) : st;
             }
-            continue;
-        }
 
-        if (phase == P_COLLIDE) {
-            if (!active) continue;
+        } while (0);
+
+        if (todo & 0x800000u) do {                                      // ======== COLLIDE
+        MC_PHASE_SLOT(P_COLLIDE)
+            if (!active) break;
             // ---------------- real collision, CBCT_real325im.cu:599-656 ----------------------
             uint4 id = GRP(G_ID);
             const float4 pos = *reinterpret_cast<float4 *>(&GRP(G_POS));
@@ -336,7 +334,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             if (nint >= sc.max_scatter) {                             // scatter budget used up
                 if (RECORD) { P.fates[WORD(G_REC, 0)] = 5u | ((uint32_t)nint << 28); P.fate_e[WORD(G_REC, 0)] = pos.w; }
                 st = (st & clr) | (P_REFILL << (4 * j));
-                continue;
+                break;
             }
             {
                 const float2 cs = __ldg(sc.view_cs + (id.w >> 20));
@@ -344,7 +342,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 if (xr >= sc.dod || fabsf(yr) >= sc.half || fabsf(pos.z) >= sc.half) {        // :613-619
                     if (RECORD) { P.fates[WORD(G_REC, 0)] = 4u | ((uint32_t)nint << 28); P.fate_e[WORD(G_REC, 0)] = pos.w; }
                     st = (st & clr) | (P_REFILL << (4 * j));
-                    continue;
+                    break;
                 }
             }
             meta += 0x100u;                                           // nint++
@@ -366,11 +364,12 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 } else st = (st & clr) | (P_STEP << (4 * j));
             }
             else { c_comp++; WORDF(G_DIR, 3) = u01(re.y); st = (st & clr) | (P_COMPTON << (4 * j)); }
-            continue;
-        }
 
-        if (phase == P_COMPTON) {
-            if (!active) continue;
+        } while (0);
+
+        if (todo & 0x80000000u) do {                                    // ======== COMPTON
+        MC_PHASE_SLOT(P_COMPTON)
+            if (!active) break;
             // ---------------- one round of Kahn's method, :701-736 -----------------------------
             uint4 id = GRP(G_ID);
             const float E0 = WORDF(G_POS, 3);
@@ -390,7 +389,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 const float amax = ray_interp(gx, gc, rn, x2max);
                 const float x2 = fminf(ray_interp(gc, gx, rn, r2 * amax), x2max);
                 cos_t = fmaxf(1.0f - 2.0f * __fdividef(x2, x2max), -1.0f);
-                if (!(r3 <= 0.5f * (1.0f + cos_t * cos_t))) { WORD(G_ID, 2) = id.z; continue; }
+                if (!(r3 <= 0.5f * (1.0f + cos_t * cos_t))) { WORD(G_ID, 2) = id.z; break; }
                 id.y &= ~0x10000u;
                 E = E0;
             } else {
@@ -402,7 +401,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             const float iro = __fdividef(1.0f, ro);
             const float t = lam - ro * lam + 1.0f;
             const float lim = br1 ? 4.0f * (iro - iro * iro) : 0.5f * (t * t + iro);
-            if (!(r3 <= lim)) { WORD(G_ID, 2) = id.z; continue; }     // rejected: next round next time
+            if (!(r3 <= lim)) { WORD(G_ID, 2) = id.z; break; }     // rejected: next round next time
             const float lam_d = ro * lam;
             cos_t = 1.0f - (lam_d - lam);
             cos_t = fmaxf(cos_t, -1.0f);                              // :746-747
@@ -446,9 +445,11 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 WORD(G_ID, 1) = (id.y & ~0xFE0000u) | (qd << 17);
             }
             st = (st & clr) | (P_STEP << (4 * j));
-            continue;
-        }
 
+        } while (0);
+
+        if (todo & 0x80u) do {                                          // ======== REFILL
+        MC_PHASE_SLOT(P_REFILL)
         // ---------------- phase == P_REFILL: finish the ended history, start the next one ----------
         // unit bookkeeping is warp-uniform: executed by every lane
         if (next_off >= unit_cnt && !grid_done) {
@@ -474,7 +475,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
         const uint32_t first_off = next_off;
         const uint32_t my_off = next_off + __popc(m_ref & lt_mask);
         next_off = min(next_off + (uint32_t)__popc(m_ref), unit_cnt);
-        if (!active) continue;
+        if (!active) break;
         {
             const uint4 id = GRP(G_ID);
             if (id.y & 0x8000u) {                        // scatter detection, CBCT_real325im.cu:823-843
@@ -506,7 +507,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
         }
         if (my_off >= unit_cnt) {                        // no history left in this unit for me
             if (grid_done) st &= clr;                    // ... nor anywhere: the slot is done
-            continue;                                    // else: stays REFILL, the next visit opens a new unit
+            break;                                    // else: stays REFILL, the next visit opens a new unit
         }
         {
             // history index -> (pixel, photon): divisions only in the rare general case
@@ -608,7 +609,8 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 st = (st & clr) | (P_STEP << (4 * j));
             }
         }
-      }   // phases of this vote
+        } while (0);
+#undef MC_PHASE_SLOT
     }
 #undef GRP
 #undef WORD
@@ -880,7 +882,10 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
     d.labels = (const uint8_t *)s->d_labels;
     d.nx = vol->nx; d.ny = vol->ny; d.nz = vol->nz;
     d.inv_pitch = (float)(1.0 / vol->pitch);
-    for (int a = 0; a < 3; a++) { d.org[a] = (float)vol->origin[a]; d.clip_lo[a] = (float)vol->clip_lo[a]; d.clip_hi[a] = (float)vol->clip_hi[a]; }
+    for (int a = 0; a < 3; a++) {
+        d.org[a] = (float)vol->origin[a]; d.clip_lo[a] = (float)vol->clip_lo[a]; d.clip_hi[a] = (float)vol->clip_hi[a];
+        d.vox_off[a] = (float)(-(double)d.org[a] * (double)d.inv_pitch - 0.5);
+    }
     // per-keV tables: majorant over materials (CBCT_real325im.cu:867-868) and branching ratios (:651,656).  All small
     // tables are assembled in ONE pinned staging block of the scene and go to the device in one asynchronous copy: no
     // implicit stream synchronisation of a pageable source, so the uploads of several devices overlap.

@@ -145,19 +145,31 @@ def main():
     if rc_["kernel_hist_per_s"]:
         res["speedup_kernel"] = res["ours"]["hist_per_s_kernel"] / rc_["kernel_hist_per_s"]
     res["speedup_whole_program_vs_our_call"] = res["ours"]["hist_per_s_call"] / rc_["whole_program_hist_per_s"]
-    # parity: the reference's image0 is quirk-free physics (unscattered photons per pixel).  chi^2 against ours (independent
-    # RNGs), and both against the deterministic line integrals
+    # parity: the reference's image0 is quirk-free physics (unscattered photons per pixel).  Two caveats, both visible in the
+    # first run of this script (profiles/r02_ref_cuda.json): (1) the program starts every photon 10.1 cm in front of the
+    # rotation axis (:520, `start_fantom`), inside this 20 cm long x-axis cylinder at every view but beta = 0, so only view 0
+    # sees the whole phantom; (2) its phantom is analytic, ours is voxelised: rays that graze the lateral surface of the
+    # cylinder or of a rod differ by centimetres of path.  So: view 0 only, and only the pixels whose line integral agrees
+    # between a 0.05 cm and a 0.1 cm voxelisation to 0.002 (away from grazing rays).  chi^2 against ours (independent RNGs),
+    # and both against the deterministic line integrals.
     r0 = runs[300][1]
-    chi2, dof, z = chi2_images(r0, o0, per)
-    res["parity"] = {"chi2_image0": chi2, "chi2_dof": dof, "chi2_z": z,
-                     "note": "reference image0 (CBCT_real325_p300, cuRAND) vs ours (Philox), %d views x 325^2 pixels x %d photons" % (views, per)}
-    line = api.project_primary(g, vol, lab, xs, 140.0)
-    pexp = np.exp(-line.astype(np.float64))
+    line = api.project_primary(g, vol, lab, xs, 140.0, views=(0, 1))[0].astype(np.float64)
+    lab10 = np.ascontiguousarray(scenes.cylinder_phantom(200, 0.1).transpose(2, 1, 0))
+    line10 = api.project_primary(g, scenes.volume_for(lab10, 0.1), lab10, xs, 140.0, views=(0, 1))[0].astype(np.float64)
+    keep = np.abs(line - line10) < 0.002
+    chi2, dof, z = chi2_images(r0[0][keep], o0[0][keep], per)
+    chi2_all, dof_all, z_all = chi2_images(r0, o0, per)
+    pexp = np.exp(-line)
     sig = np.maximum(np.sqrt(per * pexp * (1 - pexp)), 0.5)
-    res["parity"].update(ref_vs_projector_frac_within_3sigma=float((np.abs(r0 - per * pexp) / sig <= 3).mean()),
-                         ours_vs_projector_frac_within_3sigma=float((np.abs(o0 - per * pexp) / sig <= 3).mean()),
-                         ref_total_primaries=int(r0.sum()), ours_total_primaries=int(o0.sum()),
-                         ref_scattered_tallies=int(runs[300][2].sum() - r0.sum()), ours_scattered_tallies=int(o5.sum() - o0.sum()))
+    res["parity"] = {"chi2_image0": chi2, "chi2_dof": dof, "chi2_z": z, "pixels_kept": int(keep.sum()), "pixels": int(keep.size),
+                     "note": "reference image0 (CBCT_real325_p300, cuRAND MRG32k3a) vs ours (Philox), view 0, %d photons/pixel, pixels away "
+                             "from rays grazing the analytic surfaces" % per,
+                     "ref_vs_projector_frac_within_3sigma": float((np.abs(r0[0] - per * pexp) / sig <= 3)[keep].mean()),
+                     "ours_vs_projector_frac_within_3sigma": float((np.abs(o0[0] - per * pexp) / sig <= 3)[keep].mean()),
+                     "ref_primaries_view0": int(r0[0][keep].sum()), "ours_primaries_view0": int(o0[0][keep].sum()),
+                     "all_views_all_pixels": {"chi2_z": z_all, "ref_total_primaries": int(r0.sum()), "ours_total_primaries": int(o0.sum()),
+                                              "why_it_differs": "reference starts photons inside the phantom at beta != 0 (start_fantom = 10.1 cm) + grazing rays"},
+                     "ref_scattered_tallies": int(runs[300][2].sum() - r0.sum()), "ours_scattered_tallies": int(o5.sum() - o0.sum())}
     api.shutdown()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
