@@ -64,6 +64,7 @@ struct McLaunch {
     unsigned long long *work;     // unit counter (zeroed by the host)
     uint32_t *fates;              // RECORD only
     float *fate_e;
+    uint32_t off_inv, off_cdf, off_ray, off_invlo, off_slots;   // shared-memory layout, byte offsets (see the kernel)
     uint32_t vote_bias;           // (128 - T) in every byte: a phase runs on a vote when >= T lanes wait for it (T = 16)
     // RAYLEIGH instantiations only (appended: the parameter offsets of everything above do not move)
     const float *ray;             // [n_mat][2][ray_n]: x^2 grid, then cumulative F^2 (monte_mc_xs.ff_x2 / ff_cum)
@@ -153,18 +154,23 @@ __global__ void __launch_bounds__(MC_THREADS, MINB)
 mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
     MONTE_DYN_SMEM(float4, s_mem);
     const McSceneDev &sc = P.sc;
-    float4 *s_tab = s_mem;                                             // [n_mat*201]
-    float *s_inv = reinterpret_cast<float *>(s_tab + sc.n_mat * TAB_ROWS);   // [201]
-    float *s_cdf = s_inv + TAB_ROWS + 3;                               // [n_bins+1]
+    // layout (byte offsets computed once on the host, McLaunch::off_*: with a run-time material count the compiler
+    // re-derived these pointers inside the loop): tables [n_mat*201] float4 | 1/mu_max [201 (+3)] | spectrum CDF
+    // [n_bins+1, padded to 4] | RAYLEIGH: [n_mat][2][ray_n padded to 4] | CLEAR: 1/mu_light [201 (+3)], thresholds
+    // [201 (+3)] | slots | per-warp source-ray cache
     constexpr int NG = mc_slot_groups(RECORD);
     constexpr int GSTRIDE = K * 32;                                    // uint4 per group per warp
-    float *s_ray = s_cdf + ((sc.n_bins + 1 + 3) & ~3);                 // RAYLEIGH: [n_mat][2][ray_n], ray_n padded to 4
+    char *s_base = reinterpret_cast<char *>(s_mem);
+    float4 *s_tab = s_mem;
+    float *s_inv = reinterpret_cast<float *>(s_base + P.off_inv);
+    float *s_cdf = reinterpret_cast<float *>(s_base + P.off_cdf);
+    float *s_ray = reinterpret_cast<float *>(s_base + P.off_ray);
     const int ray_stride = RAYLEIGH ? ((P.ray_n + 3) & ~3) : 0;
-    float *s_invlo = s_ray + sc.n_mat * 2 * ray_stride;                // CLEAR: [201 (+3)], then the thresholds [201 (+3)]
+    float *s_invlo = reinterpret_cast<float *>(s_base + P.off_invlo);
     float *s_thr = s_invlo + TAB_ROWS + 3;
-    uint4 *s_slots = reinterpret_cast<uint4 *>(s_invlo + (CLEAR ? 2 * (TAB_ROWS + 3) : 0)) + (threadIdx.x >> 5) * (NG * GSTRIDE);
+    uint4 *s_slots = reinterpret_cast<uint4 *>(s_base + P.off_slots) + (threadIdx.x >> 5) * (NG * GSTRIDE);
     // per-warp cache of the last pixel's source ray (pencil source, one energy: the `per` photons of a pixel share it)
-    uint4 *s_src = s_slots + (MC_THREADS / 32 - (threadIdx.x >> 5)) * (NG * GSTRIDE) + (threadIdx.x >> 5) * 3;
+    uint4 *s_src = reinterpret_cast<uint4 *>(s_base + P.off_slots) + (MC_THREADS / 32) * (NG * GSTRIDE) + (threadIdx.x >> 5) * 3;
     for (int i = threadIdx.x; i < sc.n_mat * TAB_ROWS; i += MC_THREADS) s_tab[i] = sc.tab[i];
     for (int i = threadIdx.x; i < TAB_ROWS; i += MC_THREADS) s_inv[i] = sc.inv_mumax[i];
     for (int i = threadIdx.x; i <= sc.n_bins && sc.n_bins > 0; i += MC_THREADS) s_cdf[i] = sc.cdf[i];
@@ -296,29 +302,18 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 WORD(G_ID, 2) = (ctr & 0xFFF00000u) | ((ctr + 1u) & 0xFFFFFu);
                 *reinterpret_cast<float4 *>(&GRP(G_POS)) = pos2[q];
                 c_steps++;
-                if (!inside2[q]) {                   // left the volume: only air ahead
-                    if ((meta & 0xF00u) == 0u) {     // unscattered: lands in the pixel it was aimed at (:567-590)
-                        const uint32_t pvw = id2[q].w;
-                        const uint32_t pva = (pvw >> 20) * npix + (pvw & 0xFFFFFu);
-                        if (pva != cur_pv) {
-                            if (prim_cnt) { atomicAdd(P.image0 + cur_pv, (int)prim_cnt); atomicAdd(P.image5 + cur_pv, (int)prim_cnt); }
-                            cur_pv = pva; prim_cnt = 0;
-                        }
-                        prim_cnt += sc.eid ? (uint32_t)(pos2[q].w * (float)MONTE_MC_EID_SCALE + 0.5f) : 1u; c_prim++;
-                        e_prim += (unsigned long long)(pos2[q].w * 1024.f + 0.5f);
-                        if (RECORD) { P.fates[WORD(G_REC, 0)] = 1u | ((pvw & 0xFFFFFu) << 8); P.fate_e[WORD(G_REC, 0)] = pos2[q].w; }
-                    } else WORD(G_ID, 1) = meta | 0x8000u;     // scatter detection runs with the refill phase
-                    st = (st & clrq) | (P_REFILL << (4 * jj[q]));
-                    continue;
-                }
-                // inside: air and rejected tentative collisions change nothing more; an accepted one records its material
-                // and moves the slot to COLLIDE.  Selects, not branches: the lanes of a warp take all three outcomes.
+                // Three outcomes, selects instead of branches (the lanes of a warp take all of them on every visit):
+                //  left the volume -- only air ahead: the history is finished with the REFILL phase (primary tally or scatter
+                //    detection; there nearly every lane of a visit has one to finish, here it would be the 3-5 that leave);
+                //  accepted tentative collision -- records its material and moves to COLLIDE;
+                //  air or rejected (virtual) collision, :941-961 -- nothing more.
+                const bool out = !inside2[q];
                 const int mat = max(min(lab2[q], sc.n_mat) - 1, 0);
                 const float4 tb = s_tab[mat * TAB_ROWS + kE];
                 const float ratio = CLEAR && lo2[q] ? tb.w : tb.x;    // acceptance against the majorant the step was sampled with
-                const bool accept = lab2[q] != 0 && !(u01(r2[q].y) > ratio);        // virtual collision otherwise, :941-961
-                if (accept) WORD(G_ID, 1) = (meta & ~0x7000u) | ((uint32_t)mat << 12);
-                st = accept ? ((st & clrq) | (P_COLLIDE << (4 * jj[q]))) : st;
+                const bool accept = !out && lab2[q] != 0 && !(u01(r2[q].y) > ratio);
+                if (out | accept) WORD(G_ID, 1) = out ? (meta | 0x8000u) : ((meta & ~0x7000u) | ((uint32_t)mat << 12));
+                st = (out | accept) ? ((st & clrq) | ((out ? P_REFILL : P_COLLIDE) << (4 * jj[q]))) : st;
             }
 
         } while (0);
@@ -478,11 +473,22 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
         if (!active) break;
         {
             const uint4 id = GRP(G_ID);
-            if (id.y & 0x8000u) {                        // scatter detection, CBCT_real325im.cu:823-843
+            if (id.y & 0x8000u) {                        // the slot's history left the volume on its last step
                 WORD(G_ID, 1) = id.y & ~0x8000u;
                 const int nint = (id.y >> 8) & 0xF;
-                uint32_t fate = 4u | ((uint32_t)nint << 28);
                 const float4 pos = *reinterpret_cast<float4 *>(&GRP(G_POS));
+                if (nint == 0) {                         // unscattered: lands in the pixel it was aimed at (:567-590)
+                    const uint32_t pvw = id.w;
+                    const uint32_t pvq = (pvw >> 20) * npix + (pvw & 0xFFFFFu);
+                    if (pvq != cur_pv) {
+                        if (prim_cnt) { atomicAdd(P.image0 + cur_pv, (int)prim_cnt); atomicAdd(P.image5 + cur_pv, (int)prim_cnt); }
+                        cur_pv = pvq; prim_cnt = 0;
+                    }
+                    prim_cnt += sc.eid ? (uint32_t)(pos.w * (float)MONTE_MC_EID_SCALE + 0.5f) : 1u; c_prim++;
+                    e_prim += (unsigned long long)(pos.w * 1024.f + 0.5f);
+                    if (RECORD) { P.fates[WORD(G_REC, 0)] = 1u | ((pvw & 0xFFFFFu) << 8); P.fate_e[WORD(G_REC, 0)] = pos.w; }
+                } else {                                 // scatter detection, CBCT_real325im.cu:823-843
+                uint32_t fate = 4u | ((uint32_t)nint << 28);
                 const float4 dir = *reinterpret_cast<float4 *>(&GRP(G_DIR));
                 const int view = (int)(id.w >> 20);
                 const float2 cs = __ldg(sc.view_cs + view);
@@ -503,6 +509,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                     }
                 }
                 if (RECORD) { P.fates[WORD(G_REC, 0)] = fate; P.fate_e[WORD(G_REC, 0)] = pos.w; }
+                }
             }
         }
         if (my_off >= unit_cnt) {                        // no history left in this unit for me
@@ -1059,10 +1066,12 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     const int K = which >= 31 && which <= 36 ? which - 30 : (which == 44 ? 4 : (which == 43 ? 3 : 5));
     const size_t slot_bytes = (size_t)K * 32 * mc_slot_groups(rec != 0) * sizeof(uint4) * (MC_THREADS / 32) +
                               (MC_THREADS / 32) * 3 * sizeof(uint4);                      // + the per-warp source-ray cache
-    const size_t smem = (size_t)s->dev.n_mat * TAB_ROWS * sizeof(float4) +
-                        (TAB_ROWS + 3 + ((s->dev.n_bins + 1 + 3) & ~3)) * sizeof(float) + slot_bytes +
-                        (rayleigh ? (size_t)s->dev.n_mat * 2 * ((s->ray_n + 3) & ~3) * sizeof(float) : 0) +
-                        (clear ? 2 * (TAB_ROWS + 3) * sizeof(float) : 0);
+    L.off_inv = (uint32_t)((size_t)s->dev.n_mat * TAB_ROWS * sizeof(float4));
+    L.off_cdf = L.off_inv + (TAB_ROWS + 3) * (uint32_t)sizeof(float);
+    L.off_ray = L.off_cdf + (uint32_t)((s->dev.n_bins + 1 + 3) & ~3) * (uint32_t)sizeof(float);
+    L.off_invlo = L.off_ray + (rayleigh ? (uint32_t)s->dev.n_mat * 2u * (uint32_t)((s->ray_n + 3) & ~3) * (uint32_t)sizeof(float) : 0u);
+    L.off_slots = L.off_invlo + (clear ? 2u * (TAB_ROWS + 3) * (uint32_t)sizeof(float) : 0u);
+    const size_t smem = (size_t)L.off_slots + slot_bytes;
     const void *fn = nullptr;
     switch (rayleigh || clear ? 200 + rec + (clear ? 2 : 0) + (rayleigh && clear ? 2 : 0) : which * 2 + rec) {
         case 200: fn = (const void *)mc_transport_kernel_v3<false, 5, 3, 2, true>; break;
