@@ -26,12 +26,14 @@
 extern "C" {
 #endif
 
-#define MONTE_GPU_ABI_VERSION 4   /* 2: monte_mc_geom.detector_mode; 3: monte_mc_geom.coherent_mode (was
+#define MONTE_GPU_ABI_VERSION 5   /* 2: monte_mc_geom.detector_mode; 3: monte_mc_geom.coherent_mode (was
                                      `reserved`, 0 = unchanged behaviour), form-factor tables appended to monte_mc_xs,
                                      tracking_mode / clearance_cell_log2 appended to monte_mc_volume (0 = unchanged);
                                      4: monte_gpu_init binds 1..8 devices and the host-buffer calls monte_gpu_simulate* /
                                      monte_gpu_fdk shard over them; monte_gpu_simulate_maps; "all views" is spelled
-                                     view_end < 0 (the range [0, 0) is now empty, as in the device forms)        */
+                                     view_end < 0 (the range [0, 0) is now empty, as in the device forms);
+                                     5: majorant_mode appended to monte_mc_volume (0 = unchanged); monte_hu_class,
+                                     monte_hu_classes_default, monte_ctnum_segment (N-class HU segmentation)       */
 
 /* ---- status codes ------------------------------------------------------ */
 #define MONTE_OK            0
@@ -250,6 +252,13 @@ typedef struct monte_mc_xs {
                                        DIRECTIONAL with 4-voxel cells if the global majorant is on average more than
                                        3x the majorant of the lighter materials, else GLOBAL                        */
 
+/* majorant_mode: which materials the per-keV Woodcock majorant is taken over.  Exact either way (a majorant only has
+ * to bound the attenuation that occurs); a run is reproducible bit for bit only within one mode.               */
+#define MONTE_MC_MAJORANT_ALL     0  /* every table that was loaded (CBCT_real325im.cu:866-868)                    */
+#define MONTE_MC_MAJORANT_PRESENT 1  /* only the materials that occur in the label volume (monte_xs_majorant): a
+                                        segmented CT volume without dense bone is not tracked with bone's majorant.
+                                        The library scans the labels when they are uploaded (8 host threads)       */
+
 typedef struct monte_mc_volume {
     int32_t nx, ny, nz;
     double  pitch;
@@ -257,6 +266,8 @@ typedef struct monte_mc_volume {
     double  clip_lo[3], clip_hi[3];
     int32_t tracking_mode;        /* MONTE_MC_TRACK_*; 0 = the reference's single majorant                      */
     int32_t clearance_cell_log2;  /* CLEARANCE / ADAPTIVE: cells of 2^n voxels per side (0..8); 2 or 3         */
+    int32_t majorant_mode;        /* MONTE_MC_MAJORANT_*; 0 = the reference's maximum over all tables           */
+    int32_t reserved0;            /* 0                                                                          */
 } monte_mc_volume;
 
 #define MONTE_MC_SOURCE_PENCIL 0  /* one pencil per pixel centre, `per` photons each
@@ -421,6 +432,31 @@ void monte_make_sphere(uint8_t *g, int nx, int ny, int nz, int cx, int cy, int c
  * mu_water(E)*(1+HU/1000) and a label segmentation by HU thresholds.                   */
 int monte_ctnum_to_mu(const float *hu, size_t n, const monte_mc_xs *xs, double keV,
                       float hu_air_max, float hu_bone_min, float *mu, uint8_t *labels);
+/* The same role done so that the TRANSPORT consumes the result: an N-class segmentation of a CT volume.
+ * A class covers HU in [hu_min, hu_min of the next class) (the last one is open above); classes ascend in hu_min and
+ * everything below the first class is air.  A class with density <= 0 is air as well (label 0); every other class
+ * becomes one material of the transport: tables = the mass-fraction mixture (mixture rule: mu/rho = (1-f) (mu/rho)_a
+ * + f (mu/rho)_b, per interaction type) of two base materials, density = the class's own -- so one base table serves
+ * several density bins (lung / adipose / soft tissue as water at 0.3 / 0.93 / 1.03 g/cm^3) and bone is water + calcium. */
+typedef struct monte_hu_class {
+    float   hu_min;
+    int32_t material_a;      /* index into the base tables (0-based)                                  */
+    int32_t material_b;      /* second component, or < 0 for none                                     */
+    float   frac_b;          /* mass fraction of material_b, 0..1                                     */
+    float   density;         /* g/cm^3 of the class; <= 0: air                                        */
+} monte_hu_class;
+/* Default table for base tables {0: water (xcom2.csv), 1: calcium (Ca.csv)}: air < -900 | lung | adipose | soft
+ * tissue | muscle | spongy bone | bone | dense bone | cortical bone (ICRU-44-like densities and calcium mass
+ * fractions 0.05 .. 0.225).  have_calcium == 0: the bone classes are water at their density.  Writes at most
+ * MONTE_MC_MAX_MATERIALS + 1 classes; returns their number.                                                        */
+int monte_hu_classes_default(int have_calcium, monte_hu_class *classes);
+/* hu[n] -> labels[n] (0 = air, k = the k-th non-air class) and the material tables `out` those labels index
+ * (out->n_materials = number of non-air classes <= MONTE_MC_MAX_MATERIALS; form-factor tables of material_a are
+ * carried over).  mu (nullable): the linear attenuation the transport will see at keV, total[label-1][keV] * density
+ * -- the deterministic projector integrates exactly this.  present (nullable): bit m set iff material m occurs.   */
+int monte_ctnum_segment(const float *hu, size_t n, const monte_hu_class *classes, int n_classes,
+                        const monte_mc_xs *base, double keV, monte_mc_xs *out, uint8_t *labels, float *mu,
+                        uint32_t *present);
 /* Analytic stand-in for a measured form factor (the reference ships none): F(x)^2 ~ (1 + x^2/x0^2)^-4, the
  * hydrogen-like 1s charge cloud, x0 in 1/Angstrom (0.30 * Z_eff).  Fills ff_x2 / ff_cum of `material` on a
  * logarithmic grid of MONTE_MC_FF_POINTS points up to x^2 = 270 (200 keV back-scatter) and sets ff_points.  */

@@ -20,6 +20,12 @@ COORD_SCALE_AFTER, COORD_SCALE_BEFORE = 0, 1
 SOURCE_PENCIL, SOURCE_CONE = 0, 1
 COHERENT_FORWARD, COHERENT_FORMFACTOR = 0, 1
 TRACK_GLOBAL, TRACK_CLEARANCE, TRACK_AUTO, TRACK_ADAPTIVE, TRACK_DIRECTIONAL = 0, 1, 2, 3, 4
+MAJORANT_ALL, MAJORANT_PRESENT = 0, 1
+
+
+class HuClass(C.Structure):
+    _fields_ = [("hu_min", C.c_float), ("material_a", C.c_int32), ("material_b", C.c_int32),
+                ("frac_b", C.c_float), ("density", C.c_float)]
 
 
 class FdkGeom(C.Structure):
@@ -83,6 +89,7 @@ class McVolume(C.Structure):
         ("origin", C.c_double * 3),
         ("clip_lo", C.c_double * 3), ("clip_hi", C.c_double * 3),
         ("tracking_mode", C.c_int32), ("clearance_cell_log2", C.c_int32),
+        ("majorant_mode", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

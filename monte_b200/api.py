@@ -90,6 +90,9 @@ def _bind(path):
         "monte_make_sphere": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
         "monte_ctnum_to_mu": (C.c_int, [vp, sz, C.POINTER(McXs), C.c_double, C.c_float, C.c_float, vp, vp]),
         "monte_xs_majorant": (C.c_int, [C.POINTER(McXs), vp, sz, vp]),
+        "monte_hu_classes_default": (C.c_int, [C.c_int, vp]),
+        "monte_ctnum_segment": (C.c_int, [vp, sz, vp, C.c_int, C.POINTER(McXs), C.c_double, C.POINTER(McXs), vp, vp,
+                                          C.POINTER(C.c_uint32)]),
         "monte_xs_formfactor_hydrogenic": (C.c_int, [C.POINTER(McXs), C.c_int, C.c_double]),
         "monte_mc_clearance_dims": (C.c_int, [C.POINTER(McVolume), C.c_int, C.POINTER(C.c_int32)]),
         "monte_mc_clearance_grid": (C.c_int, [C.POINTER(McVolume), vp, C.c_int, C.c_int, C.c_int, vp]),
@@ -369,6 +372,30 @@ class Projector:
             self.close()
         except Exception:
             pass
+
+
+def hu_classes_default(have_calcium=True):
+    """the library's default HU class table (monte_hu_classes_default): a ctypes array of HuClass"""
+    from ._abi import HuClass
+    arr = (HuClass * (_abi.MAX_MATERIALS + 1))()
+    n = load().monte_hu_classes_default(1 if have_calcium else 0, C.cast(arr, C.c_void_p))
+    if n < 0:
+        _check(n)
+    return (HuClass * n)(*arr[:n])
+
+
+def ctnum_segment(hu, classes, base_xs, keV=140.0, want_mu=True):
+    """N-class segmentation of a CT volume (monte_ctnum_segment, host only): returns (labels uint8 like hu, the
+    McXs those labels index, mu float32 or None, present-material bit mask)"""
+    hu = np.ascontiguousarray(hu, np.float32)
+    labels = np.empty(hu.shape, np.uint8)
+    mu = np.empty(hu.shape, np.float32) if want_mu else None
+    out = McXs()
+    present = C.c_uint32(0)
+    _check(load().monte_ctnum_segment(_ptr(hu), hu.size, C.cast(classes, C.c_void_p), len(classes), C.byref(base_xs),
+                                      float(keV), C.byref(out), _ptr(labels), _ptr(mu) if want_mu else None,
+                                      C.byref(present)))
+    return labels, out, mu, present.value
 
 
 def resolve_tracking(xs, spec):

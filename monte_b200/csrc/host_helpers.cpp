@@ -135,6 +135,96 @@ int monte_ctnum_to_mu(const float *hu, size_t n, const monte_mc_xs *xs, double k
     return MONTE_OK;
 }
 
+/* ---- N-class segmentation of a CT volume ----------------------------------------------------
+ * The reference's ctnum_to_mu.cpp loads the water table, forms mu_H2O (:55) and stops; its transport
+ * (CBCT_real325im.cu:640-646) reads a LABEL volume and picks Ca / H2O / PMMA tables by label.  This is the missing
+ * link: HU -> labels the transport reads + the tables those labels index.                                      */
+int monte_hu_classes_default(int have_calcium, monte_hu_class *c) {
+    if (!c) { monte::set_error("monte_hu_classes_default: NULL argument"); return MONTE_E_ARG; }
+    // hu_min, a, b, calcium mass fraction, density.  Densities follow rho ~ 1 + HU/1000 for soft tissue (the bin's
+    // typical HU) and the ICRU-44 bone series above it (spongiosa 1.18 ... cortical 1.92 g/cm^3, Ca 22.5 % by mass).
+    const monte_hu_class t[9] = {
+        {-900.f, 0, -1, 0.f, 0.30f},      // lung
+        {-400.f, 0, -1, 0.f, 0.93f},      // adipose
+        {-40.f, 0, -1, 0.f, 1.01f},       // water / soft tissue
+        {60.f, 0, -1, 0.f, 1.07f},        // muscle, organs with contrast
+        {150.f, 0, 1, 0.050f, 1.18f},     // spongy bone
+        {400.f, 0, 1, 0.120f, 1.40f},     // bone
+        {800.f, 0, 1, 0.180f, 1.65f},     // dense bone
+        {1300.f, 0, 1, 0.225f, 1.92f},    // cortical bone
+        {0.f, 0, -1, 0.f, 0.f}};
+    for (int i = 0; i < 8; i++) {
+        c[i] = t[i];
+        if (!have_calcium) { c[i].material_b = -1; c[i].frac_b = 0.f; }
+    }
+    return 8;
+}
+
+int monte_ctnum_segment(const float *hu, size_t n, const monte_hu_class *classes, int n_classes,
+                        const monte_mc_xs *base, double keV, monte_mc_xs *out, uint8_t *labels, float *mu,
+                        uint32_t *present) {
+    if (!hu || !classes || !base || !out || !labels || n_classes < 1 || n_classes > 64 || base->n_materials < 1 ||
+        base->n_materials > MONTE_MC_MAX_MATERIALS) {
+        monte::set_error("monte_ctnum_segment: bad argument");
+        return MONTE_E_ARG;
+    }
+    // classes -> materials
+    int label_of[64];
+    memset(out, 0, sizeof(*out));
+    int nm = 0;
+    for (int c = 0; c < n_classes; c++) {
+        const monte_hu_class &k = classes[c];
+        if (c > 0 && !(k.hu_min > classes[c - 1].hu_min)) { monte::set_error("monte_ctnum_segment: classes must ascend in hu_min (class %d)", c); return MONTE_E_ARG; }
+        if (!(k.density > 0.f)) { label_of[c] = 0; continue; }
+        if (k.material_a < 0 || k.material_a >= base->n_materials || k.material_b >= base->n_materials ||
+            !(k.frac_b >= 0.f && k.frac_b <= 1.f)) { monte::set_error("monte_ctnum_segment: class %d names a material outside the base tables", c); return MONTE_E_ARG; }
+        if (nm == MONTE_MC_MAX_MATERIALS) { monte::set_error("monte_ctnum_segment: more than %d non-air classes", MONTE_MC_MAX_MATERIALS); return MONTE_E_ARG; }
+        const int a = k.material_a, b = k.material_b;
+        const double fb = b >= 0 ? (double)k.frac_b : 0.0, fa = 1.0 - fb;
+        for (int r = 0; r < MONTE_MC_TABLE_ROWS; r++) {       // mixture rule, per interaction type (mass coefficients)
+            out->coh[nm][r] = (float)(fa * base->coh[a][r] + (b >= 0 ? fb * base->coh[b][r] : 0.0));
+            out->compt[nm][r] = (float)(fa * base->compt[a][r] + (b >= 0 ? fb * base->compt[b][r] : 0.0));
+            out->photo[nm][r] = (float)(fa * base->photo[a][r] + (b >= 0 ? fb * base->photo[b][r] : 0.0));
+            out->total[nm][r] = (float)(fa * base->total[a][r] + (b >= 0 ? fb * base->total[b][r] : 0.0));
+        }
+        out->density[nm] = k.density;
+        if (base->ff_points > 0) {                              // form factor of the main component (a stand-in anyway)
+            memcpy(out->ff_x2[nm], base->ff_x2[a], sizeof(out->ff_x2[nm]));
+            memcpy(out->ff_cum[nm], base->ff_cum[a], sizeof(out->ff_cum[nm]));
+        }
+        label_of[c] = ++nm;
+    }
+    if (nm == 0) { monte::set_error("monte_ctnum_segment: every class is air"); return MONTE_E_ARG; }
+    out->n_materials = nm;
+    out->ff_points = base->ff_points;
+    int kr = (int)(keV + 0.5);
+    kr = kr < 1 ? 1 : (kr > MONTE_MC_TABLE_ROWS - 1 ? MONTE_MC_TABLE_ROWS - 1 : kr);
+    float mu_of[MONTE_MC_MAX_MATERIALS + 1] = {0.f};
+    for (int m = 0; m < nm; m++) mu_of[m + 1] = out->total[m][kr] * out->density[m];
+    // voxels: binary search over the ascending class edges, eight host threads for big volumes
+    const int T = n >= (1u << 22) ? 8 : 1;
+    uint32_t seen[8] = {0};
+    auto work = [&](int t) {
+        const size_t lo = n * t / T, hi = n * (t + 1) / T;
+        uint32_t sm = 0;
+        for (size_t i = lo; i < hi; i++) {
+            const float h = hu[i];
+            int a = -1, b = n_classes - 1;                      // largest c with hu_min[c] <= h, or -1 (NaN: -1 = air)
+            if (!(h >= classes[0].hu_min)) b = -1;
+            else { a = 0; while (a < b) { const int mid = (a + b + 1) >> 1; if (classes[mid].hu_min <= h) a = mid; else b = mid - 1; } }
+            const int lab = b < 0 ? 0 : label_of[a];
+            labels[i] = (uint8_t)lab;
+            if (mu) mu[i] = mu_of[lab];
+            if (lab) sm |= 1u << (lab - 1);
+        }
+        seen[t] = sm;
+    };
+    if (T == 1) work(0);
+    else { std::thread th[8]; for (int t = 0; t < T; t++) th[t] = std::thread(work, t); for (int t = 0; t < T; t++) th[t].join(); }
+    if (present) { *present = 0; for (int t = 0; t < T; t++) *present |= seen[t]; }
+    return MONTE_OK;
+}
+
 /* Woodcock majorant per keV: max over the materials (labels 1..n_materials) that occur in `labels`
  * (all materials if labels is NULL) of total[m][k]*density[m] -- CBCT_real325im.cu:866 takes the max over
  * every table it loaded; restricting it to the materials present is what makes a calcium-free volume

@@ -66,6 +66,9 @@ struct McLaunch {
     float *fate_e;
     uint32_t off_inv, off_cdf, off_ray, off_invlo, off_slots;   // shared-memory layout, byte offsets (see the kernel)
     uint32_t vote_bias;           // (128 - T) in every byte: a phase runs on a vote when >= T lanes wait for it (T = 16)
+    uint32_t collide_check;       // 0: the clip box lies inside the detector-side bounds of :613-619 for every view, so no
+                                  // collision site can fail that test and COLLIDE skips it (host: launch_mc)
+    uint32_t n_vox_m1;            // voxels of the label volume - 1: the one clamp of a label address
     // RAYLEIGH instantiations only (appended: the parameter offsets of everything above do not move)
     const float *ray;             // [n_mat][2][ray_n]: x^2 grid, then cumulative F^2 (monte_mc_xs.ff_x2 / ff_cum)
     int ray_n;
@@ -282,9 +285,14 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 int ix = __float_as_int(fmaf(pos2[q].x, sc.inv_pitch, vox_off[0]) + 12582912.0f) - 0x4B400000;
                 int iy = __float_as_int(fmaf(pos2[q].y, sc.inv_pitch, vox_off[1]) + 12582912.0f) - 0x4B400000;
                 int iz = __float_as_int(fmaf(pos2[q].z, sc.inv_pitch, vox_off[2]) + 12582912.0f) - 0x4B400000;
-                ix = (int)min((unsigned)ix, (unsigned)(sc.nx - 1)); iy = (int)min((unsigned)iy, (unsigned)(sc.ny - 1));
-                iz = (int)min((unsigned)iz, (unsigned)(sc.nz - 1));     // safety only: the clip box lies inside the volume
-                lab2[q] = (en2[q] && inside2[q] && !cut) ? __ldg(sc.labels + ((unsigned)(iz * sc.ny + iy) * (unsigned)sc.nx + (unsigned)ix)) : 0;
+                // the clip box lies inside the volume (scene_upload checks it), so a position that passed the clip test
+                // indexes a voxel; a coordinate exactly on an outer face may round one voxel out: safety only, one clamp
+                // of the linear address (CLEAR kernels: per axis, the cell address below needs the three indices)
+                if (CLEAR) {
+                    ix = (int)min((unsigned)ix, (unsigned)(sc.nx - 1)); iy = (int)min((unsigned)iy, (unsigned)(sc.ny - 1));
+                    iz = (int)min((unsigned)iz, (unsigned)(sc.nz - 1));
+                }
+                lab2[q] = (en2[q] && inside2[q] && !cut) ? __ldg(sc.labels + min((unsigned)(iz * sc.ny + iy) * (unsigned)sc.nx + (unsigned)ix, P.n_vox_m1)) : 0;
                 if (CLEAR && en2[q] && inside2[q]) {
                     const unsigned oc = (dir.x > 0.f ? 1u : 0u) | (dir.y > 0.f ? 2u : 0u) | (dir.z > 0.f ? 4u : 0u);   // coct == 0: one grid
                     qn2[q] = __ldg(P.clear + oc * P.coct + ((unsigned)((iz >> P.cshift) * P.cgy + (iy >> P.cshift)) * (unsigned)P.cgx + (unsigned)(ix >> P.cshift)));
@@ -299,7 +307,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 if (CLEAR) { meta = (meta & ~0xFE0000u) | (qn2[q] << 17); WORD(G_ID, 1) = meta; }
                 const uint32_t clrq = ~(0xFu << (4 * jj[q]));
                 const int kE = meta & 0xFF;
-                WORD(G_ID, 2) = (ctr & 0xFFF00000u) | ((ctr + 1u) & 0xFFFFFu);
+                WORD(G_ID, 2) = ctr + 1u;     // flight-stream index, bits 0-19: a history does not take 2^20 Woodcock steps (mu_max > 0 is checked)
                 *reinterpret_cast<float4 *>(&GRP(G_POS)) = pos2[q];
                 c_steps++;
                 // Three outcomes, selects instead of branches (the lanes of a warp take all of them on every visit):
@@ -331,7 +339,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 st = (st & clr) | (P_REFILL << (4 * j));
                 break;
             }
-            {
+            if (P.collide_check) {
                 const float2 cs = __ldg(sc.view_cs + (id.w >> 20));
                 const float xr = pos.x * cs.x + pos.y * cs.y, yr = -pos.x * cs.y + pos.y * cs.x;
                 if (xr >= sc.dod || fabsf(yr) >= sc.half || fabsf(pos.z) >= sc.half) {        // :613-619
@@ -720,6 +728,13 @@ struct monte_mc_scene {
     int clear_key[6] = {0, 0, 0, -1, -1, -1};                          // nx, ny, nz, cell_log2, heavy, n_materials
     uint64_t labels_hash = 0;                                          // content hash of the resident labels (0: unknown)
     size_t labels_n = 0;
+    // majorant_mode PRESENT: materials that occur in the resident labels (bit m = material m); what scene_update_labels
+    // needs to rebuild the tables when that set changes
+    uint32_t present_mask = 0xffffffffu;
+    bool present_valid = false;
+    monte_mc_xs *xs_host = nullptr;
+    bool adaptive_host = false;
+    size_t o_tab = 0, o_inv = 0, o_invlo = 0, tables_bytes = 0;          // table region inside d_small / h_small
     // work-unit counters: one per launch out of a ring, so that launches of one scene that overlap on different
     // streams do not share (and re-zero) a counter.  More than MC_WORK_RING launches of one scene in flight at
     // once are not supported.
@@ -745,6 +760,8 @@ static int check_mc(const monte_mc_geom *g, const monte_mc_volume *vol, const mo
                vol->tracking_mode != MONTE_MC_TRACK_DIRECTIONAL) ||
               (vol->clearance_cell_log2 >= 0 && vol->clearance_cell_log2 <= 8),
               "mc: clearance_cell_log2 must be 0..8 (got %d)", vol->clearance_cell_log2);
+    MONTE_ARG(vol->majorant_mode == MONTE_MC_MAJORANT_ALL || vol->majorant_mode == MONTE_MC_MAJORANT_PRESENT,
+              "mc: unknown majorant_mode %d", vol->majorant_mode);
     MONTE_ARG(xs->n_materials >= 1 && xs->n_materials <= MONTE_MC_MAX_MATERIALS, "mc: n_materials must be 1..%d", MONTE_MC_MAX_MATERIALS);
     MONTE_ARG(g->coherent_mode == MONTE_MC_COHERENT_FORWARD || g->coherent_mode == MONTE_MC_COHERENT_FORMFACTOR,
               "mc: unknown coherent_mode %d", g->coherent_mode);
@@ -848,6 +865,68 @@ static uint64_t hash_labels(const uint8_t *p, size_t n) {
     return r ? r : 1;
 }
 
+// majorant_mode PRESENT: which materials occur in the labels (bit m = material m = label m + 1; labels above n_mat use
+// the last material, as in the transport).  One pass over the volume on eight host threads (325^3: ~2 ms), done when
+// labels are uploaded, not per launch.
+static uint32_t label_presence_1(const uint8_t *p, size_t n, int n_mat) {
+    uint32_t seen[4] = {0, 0, 0, 0};                   // four independent accumulators (the shifts do not serialise)
+    size_t i = 0;
+    for (; i + 4 <= n; i += 4)
+        for (int l = 0; l < 4; l++) seen[l] |= 1u << (p[i + l] < 31 ? p[i + l] : 31);
+    for (; i < n; i++) seen[0] |= 1u << (p[i] < 31 ? p[i] : 31);
+    const uint32_t raw = seen[0] | seen[1] | seen[2] | seen[3];       // bit L = label L occurs (31 = any label >= 31)
+    uint32_t mask = 0;
+    for (int L = 1; L < 32; L++) if (raw >> L & 1u) mask |= 1u << ((L <= n_mat ? L : n_mat) - 1);
+    return mask;
+}
+static uint32_t label_presence(const uint8_t *p, size_t n, int n_mat) {
+    constexpr int T = 8;
+    if (n < (4u << 20)) return label_presence_1(p, n, n_mat);
+    uint32_t m[T];
+    std::thread th[T];
+    const size_t part = n / T;
+    for (int t = 0; t < T; t++) {
+        const uint8_t *q = p + part * t;
+        const size_t cnt = t == T - 1 ? n - part * t : part;
+        th[t] = std::thread([q, cnt, &m, t, n_mat] { m[t] = label_presence_1(q, cnt, n_mat); });
+    }
+    uint32_t r = 0;
+    for (int t = 0; t < T; t++) { th[t].join(); r |= m[t]; }
+    return r;
+}
+
+// per-keV tables of a scene into its pinned staging block: Woodcock majorant over the materials in `mask`
+// (CBCT_real325im.cu:867-868 takes every table it loaded: mask = all) and the branching ratios (:651,656)
+static void fill_tables(monte_mc_scene *s, const monte_mc_xs *xs, uint32_t mask, bool adaptive) {
+    const int nm = xs->n_materials;
+    char *hs = (char *)s->h_small;
+    float4 *tab = (float4 *)(hs + s->o_tab);
+    float *inv = (float *)(hs + s->o_inv), *invlo = (float *)(hs + s->o_invlo);   // invlo: 1/mu_light, then the clearance thresholds
+    for (int k = 0; k < TAB_ROWS; k++) {
+        double mumax = 0, mulo = 0;
+        for (int m = 0; m < nm; m++) {
+            if (!(mask >> m & 1u)) continue;
+            mumax = fmax(mumax, (double)xs->total[m][k] * (double)xs->density[m]);
+            if (m != s->heavy) mulo = fmax(mulo, (double)xs->total[m][k] * (double)xs->density[m]);
+        }
+        // nothing that attenuates at this energy (an all-air volume under MAJORANT_PRESENT): the medium is transparent,
+        // one step of 1e30 cm leaves the clip box (a zero step length would keep the persistent kernel spinning)
+        inv[k] = mumax > 0 ? (float)(1.0 / mumax) : 1e30f;
+        invlo[k] = mulo > 0 ? (float)(1.0 / mulo) : inv[k];
+        // ADAPTIVE: light majorant only where a cut at D is less likely than a virtual collision, exp(-mu_light D) < 1 - mu_light/mu_max
+        invlo[TAB_ROWS + k] = !adaptive ? 0.f : (mulo > 0 && mulo < mumax ? (float)(-log(1.0 - mulo / mumax) / mulo) : 1e30f);
+        for (int m = 0; m < nm; m++) {
+            const double mu = (double)xs->total[m][k];
+            float4 t;
+            t.x = mumax > 0 ? (float)fmin(1.0, (mu * (double)xs->density[m]) / mumax) : 0.f;   // (an absent material is never looked up)
+            t.y = mu > 0 ? (float)((double)xs->photo[m][k] / mu) : 1.f;
+            t.z = mu > 0 ? (float)(((double)xs->photo[m][k] + (double)xs->coh[m][k]) / mu) : 1.f;
+            t.w = mulo > 0 ? (float)fmin(1.0, (mu * (double)xs->density[m]) / mulo) : t.x;   // acceptance against the light majorant
+            tab[(size_t)m * TAB_ROWS + k] = t;
+        }
+    }
+}
+
 // clearance grid of the current labels (host transform) -> device; skipped when the resident grid was built from
 // the same labels, geometry and tables
 static int upload_clearance(monte_mc_scene *s, const uint8_t *labels, cudaStream_t st, uint64_t known_hash = 0) {
@@ -877,8 +956,10 @@ static int upload_clearance(monte_mc_scene *s, const uint8_t *labels, cudaStream
 // (re)fill a scene: device buffers are reused when large enough; copies are issued on `st`
 // labels_hash != 0: the caller has hashed `labels`; if the scene already holds exactly these bytes the 34 MB copy
 // (and a clearance-grid rebuild) is skipped.  0: always copied.
+// present_known: the caller's label_presence() of `labels` (one scan for all devices), or ~0u: scan here if needed
 static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_mc_volume *vol, const uint8_t *labels,
-                        const monte_mc_xs *xs, const monte_mc_spectrum *spec, cudaStream_t st, uint64_t labels_hash = 0) {
+                        const monte_mc_xs *xs, const monte_mc_spectrum *spec, cudaStream_t st, uint64_t labels_hash = 0,
+                        uint32_t present_known = 0xffffffffu) {
     s->geom = *g;
     McSceneDev &d = s->dev;
     const size_t nvox = (size_t)vol->nx * vol->ny * vol->nz;
@@ -922,28 +1003,16 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
         s->cap_small = small_bytes;
     }
     char *hs = (char *)s->h_small, *ds = (char *)s->d_small;
-    float4 *tab = (float4 *)(hs + o_tab);
-    float *inv = (float *)(hs + o_inv), *invlo = (float *)(hs + o_invlo);      // invlo: 1/mu_light, then the clearance thresholds
-    for (int k = 0; k < TAB_ROWS; k++) {
-        double mumax = 0, mulo = 0;
-        for (int m = 0; m < nm; m++) {
-            mumax = fmax(mumax, (double)xs->total[m][k] * (double)xs->density[m]);
-            if (m != s->heavy) mulo = fmax(mulo, (double)xs->total[m][k] * (double)xs->density[m]);
-        }
-        inv[k] = mumax > 0 ? (float)(1.0 / mumax) : 0.f;
-        invlo[k] = mulo > 0 ? (float)(1.0 / mulo) : inv[k];
-        // ADAPTIVE: light majorant only where a cut at D is less likely than a virtual collision, exp(-mu_light D) < 1 - mu_light/mu_max
-        invlo[TAB_ROWS + k] = !adaptive ? 0.f : (mulo > 0 && mulo < mumax ? (float)(-log(1.0 - mulo / mumax) / mulo) : 1e30f);
-        for (int m = 0; m < nm; m++) {
-            const double mu = (double)xs->total[m][k];
-            float4 t;
-            t.x = mumax > 0 ? (float)((mu * (double)xs->density[m]) / mumax) : 0.f;
-            t.y = mu > 0 ? (float)((double)xs->photo[m][k] / mu) : 1.f;
-            t.z = mu > 0 ? (float)(((double)xs->photo[m][k] + (double)xs->coh[m][k]) / mu) : 1.f;
-            t.w = mulo > 0 ? (float)fmin(1.0, (mu * (double)xs->density[m]) / mulo) : t.x;   // acceptance against the light majorant
-            tab[(size_t)m * TAB_ROWS + k] = t;
-        }
-    }
+    s->o_tab = o_tab; s->o_inv = o_inv; s->o_invlo = o_invlo; s->tables_bytes = o_vcs;
+    uint32_t mask = 0xffffffffu;                                       // MAJORANT_ALL: CBCT_real325im.cu:867-868
+    if (vol->majorant_mode == MONTE_MC_MAJORANT_PRESENT) {
+        mask = present_known != 0xffffffffu ? present_known
+             : (labels_resident && s->present_valid) ? s->present_mask : label_presence(labels, nvox, nm);
+        if (!s->xs_host) s->xs_host = new monte_mc_xs();
+        memcpy(s->xs_host, xs, sizeof(monte_mc_xs));
+        s->present_mask = mask; s->present_valid = true; s->adaptive_host = adaptive;
+    } else s->present_valid = false;
+    fill_tables(s, xs, mask, adaptive);
     float2 *vcs = (float2 *)(hs + o_vcs);
     for (int v = 0; v < g->n_views; v++) {
         const double beta = M_PI * (g->angle0_deg + g->angle_step_deg * v) / 180;
@@ -1002,6 +1071,15 @@ int monte_gpu_scene_update_labels(monte_mc_scene *s, const uint8_t *labels, void
     const size_t nvox = (size_t)s->dev.nx * s->dev.ny * s->dev.nz;
     MONTE_CUDA(cudaMemcpyAsync(s->d_labels, labels, nvox, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     s->labels_hash = 0;
+    if (s->vol.majorant_mode == MONTE_MC_MAJORANT_PRESENT && s->xs_host) {            // the majorant follows the labels
+        const uint32_t mask = label_presence(labels, nvox, s->n_mat_host);
+        if (mask != s->present_mask) {
+            MONTE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));                 // the staging block may still be in flight
+            fill_tables(s, s->xs_host, mask, s->adaptive_host);
+            MONTE_CUDA(cudaMemcpyAsync(s->d_small, s->h_small, s->tables_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+            s->present_mask = mask;
+        }
+    }
     if (s->heavy >= 0) return upload_clearance(s, labels, (cudaStream_t)stream);   // the grid follows the labels
     return MONTE_OK;
 }
@@ -1010,6 +1088,7 @@ void monte_gpu_scene_destroy(monte_mc_scene *s) {
     if (!s) return;
     cudaFree(s->d_labels); cudaFree(s->d_small); cudaFree(s->d_work); cudaFree(s->d_clear);
     if (s->h_small) cudaFreeHost(s->h_small);
+    delete s->xs_host;
     delete s;
 }
 
@@ -1049,6 +1128,17 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
         static int thr = -1;                                           // MONTE_MC_SECOND=T: lanes a phase needs to run on a vote (1..32)
         if (thr < 0) { const char *e = getenv("MONTE_MC_SECOND"); thr = e ? atoi(e) : 16; if (thr < 1) thr = 1; if (thr > 32) thr = 32; }
         L.vote_bias = (uint32_t)(128 - thr) * 0x01010101u;
+    }
+    {
+        // CBCT_real325im.cu:613-619 ends a history whose collision site lies beyond the detector plane or outside the
+        // detector's extent (rotated frame).  Collision sites lie in the clip box; if the box (its circumscribed cylinder
+        // about the rotation axis) lies inside those bounds for every view angle the test cannot fire
+        const McSceneDev &d = s->dev;
+        const float rx = fmaxf(fabsf(d.clip_lo[0]), fabsf(d.clip_hi[0])), ry = fmaxf(fabsf(d.clip_lo[1]), fabsf(d.clip_hi[1]));
+        const float rz = fmaxf(fabsf(d.clip_lo[2]), fabsf(d.clip_hi[2]));
+        const float rxy = sqrtf(rx * rx + ry * ry) * 1.0001f;
+        L.collide_check = (rxy < d.dod && rxy < d.half && rz < d.half) ? 0u : 1u;
+        L.n_vox_m1 = (uint32_t)((size_t)d.nx * d.ny * d.nz - 1);
     }
     if (L.total == 0) return MONTE_OK;
     MONTE_CUDA(cudaMemsetAsync(L.work, 0, sizeof(unsigned long long), st));
@@ -1197,6 +1287,12 @@ int monte_gpu_simulate_maps(const monte_mc_geom *g, const monte_mc_volume *vol, 
     const int label_cache = e_cache ? atoi(e_cache) : 1;
     const size_t nvox = (size_t)vol->nx * vol->ny * vol->nz;
     const uint64_t lhash = label_cache ? hash_labels(labels, nvox) : 0;
+    uint32_t present = 0xffffffffu;                                      // majorant_mode PRESENT: one scan for all devices
+    if (vol->majorant_mode == MONTE_MC_MAJORANT_PRESENT) {
+        static uint64_t seen_hash = 0; static uint32_t seen_mask = 0; static int seen_nm = 0;   // (calls are not re-entrant)
+        if (lhash && lhash == seen_hash && seen_nm == xs->n_materials) present = seen_mask;
+        else { present = label_presence(labels, nvox, xs->n_materials); seen_hash = lhash; seen_mask = present; seen_nm = xs->n_materials; }
+    }
     const size_t npix = (size_t)g->ny * g->nx, n_img = (size_t)(view_end - view_begin) * npix;
     const size_t n_cnt = 2 * n_img;
     const bool want_maps = map0 || map5;
@@ -1213,7 +1309,7 @@ int monte_gpu_simulate_maps(const monte_mc_geom *g, const monte_mc_volume *vol, 
         Context &c = ctx();
         cudaStream_t st = c.stream;
         if (!g_host_scene) { g_host_scene = new monte_mc_scene(); at_shutdown(mc_cleanup); }
-        if ((rc = scene_upload(g_host_scene, g, vol, labels, xs, spec, st, lhash))) break;
+        if ((rc = scene_upload(g_host_scene, g, vol, labels, xs, spec, st, lhash, present))) break;
         char *base = (char *)scratch(5, off_map + (i == 0 && want_maps ? n_cnt * sizeof(float) : 0));
         if (!base) { rc = MONTE_E_NOMEM; break; }
         dv[i].d_im = (int32_t *)base;

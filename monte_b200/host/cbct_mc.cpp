@@ -1,7 +1,11 @@
 // cbct_mc — the role of the main() of monte_cu/CBCT_real325im.cu (:83-297): read the label volume and
 // the cross-section tables, run the photon transport, write the count images and the -log maps in
 // the reference's headerless layouts (proj*_0 / proj*_5 int32, map*_0 / map*_5 float32, [view][y][x]).
-//   cbct_mc labels.raw N pitch_cm xcom2.csv Ca.csv [det=325] [pixel=0.1] [views=360] [per=10000] [seed=0] [tag=out] [rayleigh=0] [clearance=0] [--gpus G]
+//   cbct_mc labels.raw N pitch_cm xcom2.csv Ca.csv [det=325] [pixel=0.1] [views=360] [per=10000] [seed=0] [tag=out] [rayleigh=0] [clearance=0] [--gpus G] [--hu] [--kev E]
+// --hu: the first file is a CT volume in Hounsfield units (float32) instead of labels: it is segmented into the classes
+// of monte_hu_classes_default (density bins of water, water + calcium for bone; the role ctnum_to_mu.cpp:55-82 hints at)
+// and tracked with the majorant of the classes that occur (monte_mc_volume.majorant_mode = MONTE_MC_MAJORANT_PRESENT).
+// --kev E: source energy (default 140, CBCT_real325im.cu as shipped).
 // --gpus G (1..8): the photons of every pixel are split over G devices inside libmonte_gpu and the tallies summed on
 // device 0 (monte_gpu_init(G, NULL)); the output files are byte-identical to --gpus 1.
 // rayleigh=1 (not in the reference): coherent events are deflected by the analytic form factor of
@@ -26,8 +30,19 @@ static void write_raw(const std::string &fn, const void *p, size_t bytes) {
 
 int main(int argc, char **argv) {
     int gpus = 1;
-    for (int i = 1; i + 1 < argc; i++)
-        if (!strcmp(argv[i], "--gpus")) { gpus = atoi(argv[i + 1]); for (int j = i; j + 2 < argc; j++) argv[j] = argv[j + 2]; argc -= 2; break; }
+    bool hu_input = false;
+    double kev = 140.0;
+    for (int i = 1; i < argc;) {
+        if (!strcmp(argv[i], "--hu")) { hu_input = true; for (int j = i; j + 1 < argc; j++) argv[j] = argv[j + 1]; argc -= 1; continue; }
+        const bool gp = !strcmp(argv[i], "--gpus"), ke = !strcmp(argv[i], "--kev");
+        if ((gp || ke) && i + 1 < argc) {
+            if (gp) gpus = atoi(argv[i + 1]); else kev = atof(argv[i + 1]);
+            for (int j = i; j + 2 < argc; j++) argv[j] = argv[j + 2];
+            argc -= 2;
+            continue;
+        }
+        i++;
+    }
     if (argc < 6) { fprintf(stderr, "usage: cbct_mc labels.raw N pitch xcom2.csv Ca.csv [det] [pixel] [views] [per] [seed] [tag] [rayleigh] [clearance] [--gpus G]\n"); return 2; }
     const int n = atoi(argv[2]);
     const double pitch = atof(argv[3]);
@@ -40,24 +55,36 @@ int main(int argc, char **argv) {
     const bool rayleigh = argc > 12 && atoi(argv[12]) != 0;
     const int clearance = argc > 13 ? atoi(argv[13]) : 0;
     std::vector<uint8_t> lab((size_t)n * n * n);
+    std::vector<float> hu(hu_input ? lab.size() : 0);
     FILE *f = fopen(argv[1], "rb");
-    if (!f || fread(lab.data(), 1, lab.size(), f) != lab.size()) { fprintf(stderr, "failed to read %s\n", argv[1]); return 1; }
+    if (!f || (hu_input ? fread(hu.data(), 4, hu.size(), f) != hu.size() : fread(lab.data(), 1, lab.size(), f) != lab.size())) { fprintf(stderr, "failed to read %s\n", argv[1]); return 1; }
     fclose(f);
     std::unique_ptr<monte_mc_xs> xs(new monte_mc_xs());
     if (monte_xs_load_csv(argv[4], 0, 1.0f, 1, xs.get()) || monte_xs_load_csv(argv[5], 1, 1.55f, 1, xs.get())) return fail();
+    if (hu_input) {                                             // CT numbers -> labels + the tables they index
+        monte_hu_class cls[MONTE_MC_MAX_MATERIALS + 1];
+        const int nc = monte_hu_classes_default(1, cls);
+        std::unique_ptr<monte_mc_xs> seg(new monte_mc_xs());
+        uint32_t present = 0;
+        if (nc < 0 || monte_ctnum_segment(hu.data(), hu.size(), cls, nc, xs.get(), kev, seg.get(), lab.data(), nullptr, &present)) return fail();
+        printf("segmented into %d classes, present mask 0x%x\n", seg->n_materials, present);
+        xs.swap(seg);
+    }
     monte_mc_geom g = {};
     g.n_views = views; g.angle0_deg = 0; g.angle_step_deg = 360.0 / views;
     g.ny = g.nx = det; g.pixel = pixel; g.half = 0.5 * det * pixel; g.dso = 160; g.dod = 60;   // :459
     g.source_mode = MONTE_MC_SOURCE_PENCIL; g.max_scatter = 5;                                    // :7
     if (rayleigh) {
-        if (monte_xs_formfactor_hydrogenic(xs.get(), 0, 1.0) || monte_xs_formfactor_hydrogenic(xs.get(), 1, 2.2)) return fail();
+        for (int m = 0; m < xs->n_materials; m++)               // (segmented volumes: water-like classes 1.0, calcium-loaded 1.3)
+            if (monte_xs_formfactor_hydrogenic(xs.get(), m, hu_input ? (m < 4 ? 1.0 : 1.3) : (m == 0 ? 1.0 : 2.2))) return fail();
         g.coherent_mode = MONTE_MC_COHERENT_FORMFACTOR;
     }
     monte_mc_volume v = {};
     v.nx = v.ny = v.nz = n; v.pitch = pitch;
     for (int a = 0; a < 3; a++) { v.origin[a] = -0.5 * n * pitch; v.clip_lo[a] = v.origin[a]; v.clip_hi[a] = -v.origin[a]; }
     if (clearance > 0) { v.tracking_mode = MONTE_MC_TRACK_CLEARANCE; v.clearance_cell_log2 = clearance; }
-    monte_mc_spectrum sp = {0, 0.5, 140.0, nullptr};                                              // as shipped: 140 keV
+    if (hu_input) v.majorant_mode = MONTE_MC_MAJORANT_PRESENT;
+    monte_mc_spectrum sp = {0, 0.5, kev, nullptr};                                                // as shipped: 140 keV
     if (monte_gpu_init(gpus, nullptr)) return fail();
     const size_t n_img = (size_t)views * det * det;
     std::vector<int32_t> im0(n_img), im5(n_img);

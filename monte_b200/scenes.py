@@ -75,6 +75,29 @@ def cylinder_phantom(n, pitch, radius=10.0, half_len=10.0, rods=True, rod_r=1.5,
     return lab
 
 
+def hu_head_phantom(n, pitch, cortical=False):
+    """A synthetic CT volume in HU, float32 [n][n][n] (z, y, x): an ellipsoidal head of soft tissue (40 HU) in air
+    (-1000) with a skull shell (900 HU; cortical=True: 1400-HU plates at the sides), a fat layer under the skin (-90), two air
+    sinuses, a water-filled ventricle (5) and a lung-like insert (-750).  Values sit well inside the default classes
+    of monte_hu_classes_default (air | lung | adipose | soft | muscle | spongy | bone | dense | cortical)."""
+    c = (n - 1) / 2.0
+    z, y, x = np.meshgrid(*(((np.arange(n) - c) * pitch,) * 3), indexing="ij")
+    R = 0.42 * n * pitch
+    r_out = np.sqrt((x / R) ** 2 + (y / (0.85 * R)) ** 2 + (z / (0.95 * R)) ** 2)
+    hu = np.full((n, n, n), -1000.0, np.float32)
+    hu[r_out <= 1.0] = -90.0                     # skin + fat
+    hu[r_out <= 0.93] = 900.0                    # skull
+    if cortical:
+        hu[(r_out <= 0.93) & (np.abs(x) > 0.7 * R)] = 1400.0
+    hu[r_out <= 0.82] = 40.0                     # brain
+    hu[(x / (0.25 * R)) ** 2 + (y / (0.12 * R)) ** 2 + (z / (0.2 * R)) ** 2 <= 1.0] = 5.0          # ventricle
+    for sx in (-1.0, 1.0):
+        hu[((x - sx * 0.3 * R) / (0.12 * R)) ** 2 + ((y - 0.45 * R) / (0.15 * R)) ** 2 + (z / (0.2 * R)) ** 2 <= 1.0] = -1000.0
+    hu[(x / (0.2 * R)) ** 2 + ((y + 0.4 * R) / (0.15 * R)) ** 2 + ((z - 0.3 * R) / (0.2 * R)) ** 2 <= 1.0] = -750.0
+    hu[((x / (0.2 * R)) ** 2 + ((y + 0.4 * R) / (0.15 * R)) ** 2 + ((z + 0.3 * R) / (0.2 * R)) ** 2 <= 1.0)] = 100.0   # muscle-like
+    return hu
+
+
 def volume_for(labels, pitch, tight=True):
     """monte_mc_volume centred on the origin; clip box = bounding box of the non-air voxels
     (outside it the photon flies straight, CBCT_real2.cpp:770)."""

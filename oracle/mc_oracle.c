@@ -173,6 +173,9 @@ typedef struct {
     const oracle_mc_tables *tb;
     const monte_mc_spectrum *spec;
     const oracle_mc_opts *o;
+    uint32_t present;            /* materials the majorant is taken over (bit m); all ones unless
+                                    monte_mc_volume.majorant_mode == MONTE_MC_MAJORANT_PRESENT (not in the reference,
+                                    which takes every table it loaded, CBCT_real325im.cu:866-868) */
 } scene_t;
 
 typedef struct {                 /* class photon, CBCT_real2.cpp:38-49 (fields that matter) */
@@ -195,6 +198,7 @@ static double mu_max_at(const scene_t *S, int k) {
     if (S->o->quirks & OQ_MUMAX_FIRST) return S->tb->total[0][k] * S->tb->density[0];
     double m = 0;
     for (int i = 0; i < S->tb->n_materials; i++) {
+        if (!(S->present >> i & 1u)) continue;
         double v = S->tb->total[i][k] * S->tb->density[i];
         if (v > m) m = v;
     }
@@ -205,7 +209,7 @@ static double mu_max_at(const scene_t *S, int k) {
 static double mu_lo_at(const scene_t *S, int k) {
     double m = 0;
     for (int i = 0; i < S->tb->n_materials; i++) {
-        if (i == S->o->heavy) continue;
+        if (i == S->o->heavy || !(S->present >> i & 1u)) continue;
         double v = S->tb->total[i][k] * S->tb->density[i];
         if (v > m) m = v;
     }
@@ -299,7 +303,9 @@ static int delta_sampling(const scene_t *S, rng_t *R, photon_t *p, double E, dou
                 continue;
             }
         }
-        double r = -log(beta) / mu_max;
+        /* mu_max == 0: nothing present attenuates at this energy (an all-air volume under MAJORANT_PRESENT) --
+           the medium is transparent, one step of 1e30 cm leaves the tracking region (as in the kernel) */
+        double r = mu_max > 0 ? -log(beta) / mu_max : 1e30;
         x += r * sin_theta_a * cos_phi_a;
         y += r * sin_theta_a * sin_phi_a;
         z += r * cos_theta_a;
@@ -653,7 +659,15 @@ int oracle_mc_run(const monte_mc_geom *g, const monte_mc_volume *vol, const uint
                   uint32_t per, uint32_t n_begin, uint32_t n_end, int view_begin, int view_end,
                   int i_begin, int i_end, int j_begin, int j_end,
                   int32_t *image0, int32_t *image5, oracle_mc_result *result, uint32_t *fates, float *fate_e) {
-    scene_t S = {g, vol, labels, tb, spec, o};
+    scene_t S = {g, vol, labels, tb, spec, o, 0xffffffffu};
+    if (vol->majorant_mode == MONTE_MC_MAJORANT_PRESENT) {
+        S.present = 0;
+        const size_t nvox = (size_t)vol->nx * vol->ny * vol->nz;
+        for (size_t i = 0; i < nvox; i++) {
+            const int m = label_material(&S, labels[i]);
+            if (m >= 0) S.present |= 1u << m;
+        }
+    }
     memset(result, 0, sizeof(*result));
     const size_t npix = (size_t)g->ny * g->nx;
     int nthreads = o->n_threads;

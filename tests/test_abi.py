@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported(lib):
         assert hasattr(lib, n), "libmonte_gpu.so does not export %s" % n
     assert lib._monte_missing == []
     assert set(lib._monte_symbols) == set(names), set(lib._monte_symbols) ^ set(names)
-    assert lib.monte_gpu_abi_version() == 4
+    assert lib.monte_gpu_abi_version() == 5
 
 
 def test_struct_layouts_match_the_header():
@@ -45,6 +45,7 @@ def test_struct_layouts_match_the_header():
 #include <stddef.h>
 #include "monte_gpu.h"
 int main(void){
+ printf("%zu %zu %zu ", sizeof(monte_hu_class), offsetof(monte_hu_class, density), offsetof(monte_mc_volume, majorant_mode));
  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(monte_fdk_geom), sizeof(monte_fdk_stats),
    sizeof(monte_mc_xs), sizeof(monte_mc_volume), sizeof(monte_mc_geom), sizeof(monte_mc_spectrum),
    sizeof(monte_mc_stats), offsetof(monte_fdk_geom, mask_r2), offsetof(monte_fdk_geom, coord_mode),
@@ -56,7 +57,8 @@ int main(void){
             f.write(probe)
         subprocess.check_call(["gcc", "-I" + os.path.join(ROOT, "include"), os.path.join(d, "p.c"), "-o", os.path.join(d, "p")])
         got = [int(x) for x in subprocess.check_output([os.path.join(d, "p")]).split()]
-    want = [C.sizeof(_abi.FdkGeom), C.sizeof(_abi.FdkStats), C.sizeof(_abi.McXs), C.sizeof(_abi.McVolume),
+    want = [C.sizeof(_abi.HuClass), _abi.HuClass.density.offset, _abi.McVolume.majorant_mode.offset,
+            C.sizeof(_abi.FdkGeom), C.sizeof(_abi.FdkStats), C.sizeof(_abi.McXs), C.sizeof(_abi.McVolume),
             C.sizeof(_abi.McGeom), C.sizeof(_abi.McSpectrum), C.sizeof(_abi.McStats),
             _abi.FdkGeom.mask_r2.offset, _abi.FdkGeom.coord_mode.offset, _abi.McGeom.max_scatter.offset,
             _abi.McStats.sum_e_primary.offset]

@@ -80,6 +80,11 @@ def _mc_case(rng):
         spec, keep = scenes.kramers_spectrum(kvp=float(rng.choice([80.0, 120.0])))
     else:
         spec, keep = scenes.mono_spectrum(float(rng.uniform(25, 150))), None
+    # majorant over the materials present only (monte_mc_volume.majorant_mode); half of those cases lose their calcium,
+    # so the majorant really drops and the clearance modes meet a heavy material that does not occur
+    vol.majorant_mode = int(rng.integers(0, 2))
+    if vol.majorant_mode and len(mats) > 1 and rng.integers(0, 2):
+        lab[lab == 2] = 1
     return g, vol, lab, xs, spec, keep
 
 

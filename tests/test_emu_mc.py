@@ -32,6 +32,18 @@ def test_emu_three_materials_im_variant_coupled(monte_emu, oracle):
     G.test_three_materials_im_variant_coupled(monte_emu, oracle)
 
 
+def test_emu_hu_volume_transport_with_present_material_majorant(monte_emu, oracle):
+    G.test_hu_volume_transport_with_present_material_majorant(monte_emu, oracle)
+
+
+def test_emu_scene_update_labels_follows_the_present_materials(monte_emu):
+    G.test_scene_update_labels_follows_the_present_materials(monte_emu)
+
+
+def test_emu_all_air_volume_under_present_majorant(monte_emu):
+    G.test_all_air_volume_under_present_majorant(monte_emu)
+
+
 def test_emu_edge_cases(monte_emu):
     G.test_edge_cases(monte_emu)
 
@@ -283,6 +295,22 @@ def test_emu_cbct_mc_driver_end_to_end(monte_emu, tmp_path):
             vol.tracking_mode, vol.clearance_cell_log2 = _abi.TRACK_CLEARANCE, 1
         r0, r5, _ = monte_emu.simulate(g, vol, lab, xs, scenes.mono_spectrum(140.0), 40, 3)
         assert np.array_equal(r0, p0) and np.array_equal(r5, p5), tag
+    # --hu: a CT volume in Hounsfield units goes in; the driver segments it (monte_ctnum_segment, default classes) and
+    # tracks with the majorant of the classes present -- equal to the same chain through the Python binding
+    hu = scenes.hu_head_phantom(33, 0.6)
+    hu.tofile(os.path.join(d, "head_hu.raw"))
+    out = subprocess.run([exe, "head_hu.raw", "33", "0.6", "xcom2.csv", "Ca.csv", "9", str(32.5 / 9), "2", "40", "3", "h", "--hu", "--kev", "60"],
+                         cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout.decode()
+    assert "segmented into 8 classes, present mask 0x4f" in out
+    p0 = np.fromfile(os.path.join(d, "proj_h0.raw"), np.int32).reshape(2, 9, 9)
+    p5 = np.fromfile(os.path.join(d, "proj_h5.raw"), np.int32).reshape(2, 9, 9)
+    lab_h, xs_h, _, present = monte_emu.ctnum_segment(hu, monte_emu.hu_classes_default(True), scenes.make_xs(quirk_bom=True), 60.0)
+    g = scenes.mc_geom(9, 32.5 / 9, n_views=2)
+    g.angle_step_deg = 180.0
+    vol = scenes.volume_for(lab_h, 0.6, tight=False)
+    vol.majorant_mode = _abi.MAJORANT_PRESENT
+    r0, r5, _ = monte_emu.simulate(g, vol, lab_h, xs_h, scenes.mono_spectrum(60.0), 40, 3)
+    assert np.array_equal(r0, p0) and np.array_equal(r5, p5) and 0 < p0.sum() < 2 * 81 * 40
 
 
 @pytest.mark.parametrize("cell_log2,poly,rayleigh", [(0, True, False), (1, False, False), (1, True, True)])

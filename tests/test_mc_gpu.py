@@ -304,3 +304,97 @@ def test_three_materials_im_variant_coupled(monte, oracle):
                                       oracle.mc_opts(oracle.RNG_PHILOX, seed=seed), per)
     assert np.abs(im5.astype(int) - o5).sum() <= 0.004 * st["histories"]
     assert abs(st["compton"] - res["compton"]) <= 0.004 * res["compton"] + 5
+
+
+def hu_scene(monte, keV=60.0, n=33, pitch=0.6, det=17, views=2, cortical=False):
+    """a CT volume in HU -> labels + tables through monte_ctnum_segment"""
+    hu = scenes.hu_head_phantom(n, pitch, cortical=cortical)
+    classes = monte.hu_classes_default(True)
+    lab, xs, mu, present = monte.ctnum_segment(hu, classes, scenes.make_xs(), keV)
+    g = scenes.mc_geom(det, 32.5 / det, n_views=views)
+    g.angle_step_deg = 360.0 / views
+    return hu, classes, g, scenes.volume_for(lab, pitch), lab, xs, mu, present
+
+
+def test_hu_volume_transport_with_present_material_majorant(monte, oracle):
+    """a HU volume segmented into 8 classes (density bins of water, water + calcium mixtures) is what
+    the transport consumes; with majorant_mode PRESENT the Woodcock majorant covers only the classes that occur.
+    History by history against the oracle (same variates), fewer tentative collisions than with the majorant of all
+    tables, same physics."""
+    keV = 60.0
+    hu, classes, g, vol, lab, xs, mu, present = hu_scene(monte, keV)
+    assert xs.n_materials == 8 and present == 0b01001111            # lung, adipose, soft, muscle, dense bone: no cortical bone in this head
+    per, seed, view = 24, 11, 1
+    spec = scenes.mono_spectrum(keV)
+    vol.majorant_mode = _abi.MAJORANT_PRESENT
+    sc = monte.Scene(g, vol, lab, xs, spec)
+    f_gpu, e_gpu = sc.fates(view, per, seed)
+    sc.close()
+    _, _, res, f_cpu, e_cpu = oracle.mc_run(g, vol, lab, oracle.tables_from_xs(xs), spec,
+                                            oracle.mc_opts(oracle.RNG_PHILOX, seed=seed), per,
+                                            views=(view, view + 1), want_fates=True)
+    same = f_gpu == f_cpu
+    assert same.mean() > 0.995, "only %.4f of %d histories end identically" % (same.mean(), same.size)
+    assert np.allclose(e_gpu[same], e_cpu[same], rtol=2e-5)
+    for k in (1, 3, 4):
+        assert ((f_cpu & 0xFF) == k).any(), k
+    # tallies and counters of the host-buffer call, PRESENT against the oracle and against the majorant of all tables
+    p0, p5, st_p = monte.simulate(g, vol, lab, xs, spec, 60, seed)
+    o0, o5, res, _, _ = oracle.mc_run(g, vol, lab, oracle.tables_from_xs(xs), spec, oracle.mc_opts(oracle.RNG_PHILOX, seed=seed), 60)
+    n = st_p["histories"]
+    assert np.abs(p0.astype(int) - o0).sum() <= 0.005 * n and np.abs(p5.astype(int) - o5).sum() <= 0.005 * n
+    assert abs(st_p["woodcock_steps"] - res["woodcock_steps"]) <= 0.005 * res["woodcock_steps"] + 5
+    vol.majorant_mode = _abi.MAJORANT_ALL
+    a0, a5, st_a = monte.simulate(g, vol, lab, xs, spec, 60, seed)
+    assert st_p["woodcock_steps"] < 0.9 * st_a["woodcock_steps"], (st_p["woodcock_steps"], st_a["woodcock_steps"])
+    # same physics: primaries are binomial with the same p per pixel in both runs
+    for k in ("primaries", "absorbed", "interactions"):
+        assert abs(st_p[k] - st_a[k]) <= 6.0 * math.sqrt(st_p[k] + st_a[k] + 1), (k, st_p[k], st_a[k])
+    c2, nb, _ = chi2_images(p0, a0, binomial_per=60)
+    assert c2 < nb + 6.0 * math.sqrt(2.0 * nb), (c2, nb)
+    # the deterministic projector integrates exactly the mu the segmentation reports
+    pm = monte.project_primary(g, vol, lab, xs, keV, views=(0, 1))
+    po = oracle.project_primary(g, vol, lab, oracle.tables_from_xs(xs), keV)
+    assert np.abs(pm[0] - po[0]).max() <= 1e-4 * np.abs(po[0]).max()
+    for m in range(xs.n_materials):
+        sel = lab == m + 1
+        if sel.any():
+            assert np.all(mu[sel] == np.float32(xs.total[m][60]) * np.float32(xs.density[m]))
+    assert np.all(mu[lab == 0] == 0)
+
+
+def test_scene_update_labels_follows_the_present_materials(monte):
+    """majorant_mode PRESENT on a resident scene: new labels with another set of materials rebuild the tables"""
+    keV = 60.0
+    hu, classes, g, vol, lab, xs, mu, present = hu_scene(monte, keV)
+    hu2 = scenes.hu_head_phantom(33, 0.6, cortical=True)
+    lab2, xs2, _, present2 = monte.ctnum_segment(hu2, classes, scenes.make_xs(), keV)
+    assert present2 == 0b11001111 and np.array_equal(np.ctypeslib.as_array(xs2.total), np.ctypeslib.as_array(xs.total))
+    vol.majorant_mode = _abi.MAJORANT_PRESENT
+    spec = scenes.mono_spectrum(keV)
+    per, seed = 30, 3
+    sc2 = monte.Scene(g, vol, lab2, xs, spec)                                        # built from lab2 directly
+    want, want_e = sc2.fates(1, per, seed)
+    sc2.close()
+    sc = monte.Scene(g, vol, lab, xs, spec)                                          # built from lab, then updated
+    before, _ = sc.fates(1, per, seed)
+    sc.update_labels(lab2)
+    got, got_e = sc.fates(1, per, seed)
+    sc.close()
+    assert np.array_equal(got, want) and np.array_equal(got_e, want_e)
+    assert not np.array_equal(before, want)
+
+
+def test_all_air_volume_under_present_majorant(monte):
+    """majorant_mode PRESENT with nothing present: the medium is transparent, the kernel returns (one step of 1e30 cm
+    leaves the clip box) and every photon is a primary"""
+    lab = np.zeros((9, 9, 9), np.uint8)
+    g = scenes.mc_geom(5, 32.5 / 5, n_views=2)
+    vol = scenes.volume_for(lab, 2.0)
+    vol.majorant_mode = _abi.MAJORANT_PRESENT
+    im0, im5, st = monte.simulate(g, vol, lab, scenes.make_xs(), scenes.mono_spectrum(140.0), 7, 1)
+    assert st["histories"] == st["primaries"] == 2 * 25 * 7 and st["interactions"] == 0
+    assert (im0 == 7).all() and np.array_equal(im0, im5)
+    vol.majorant_mode = 9
+    with pytest.raises(Exception, match="majorant_mode"):
+        monte.simulate(g, vol, lab, scenes.make_xs(), scenes.mono_spectrum(140.0), 7, 1)
