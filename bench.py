@@ -529,10 +529,10 @@ def bench_mc_c2(c):
         if ws > 1:
             c.rebind_own()
         mc_e2e = {"value": hist_total / res["strict"], "unit": "histories/s",
-                  "h2d_bytes_per_step": int(ws * (lab.size + 2 * 201 * 16 + 201 * 4 + g.n_views * 8)),
+                  "h2d_bytes_per_step": int(lab.size + ws * (2 * 201 * 16 + 201 * 4 + g.n_views * 8)),
                   "d2h_bytes_per_step": int(2 * npix * 4 + ws * 128), "ms_per_step": 1e3 * res["strict"] / K,
                   "call": "monte_gpu_simulate (C ABI, pinned host buffers)" + (" with the library bound to %d devices on rank 0" % ws if ws > 1 else ""),
-                  "note": "the label volume is uploaded on every call (MONTE_MC_LABEL_CACHE=0), to every device",
+                  "note": "the label volume is uploaded on every call (MONTE_MC_LABEL_CACHE=0)" + (": every device takes 1/%d of it from the host and the rest from its peers over NVLink" % ws if ws > 1 else ""),
                   "cached_labels": {"value": hist_total / res["cached_labels"], "ms_per_step": 1e3 * res["cached_labels"] / K,
                                     "h2d_bytes_per_step": int(ws * (2 * 201 * 16 + 201 * 4 + g.n_views * 8)),
                                     "note": "default behaviour: the host buffer is hashed (4 threads) and re-uploaded only when its content changed"}}
@@ -676,7 +676,7 @@ def bench_mc_c4(c):
         te = time.perf_counter() - t0
         del os.environ["MONTE_MC_LABEL_CACHE"]
         out["e2e"] = {"value": hist_step * Ke / te, "unit": "histories/s", "ms_per_step": 1e3 * te / Ke, "steps": Ke,
-                      "h2d_bytes_per_step": int(ws * (lab.size + 2 * 201 * 16 + 481 * 4)), "d2h_bytes_per_step": int(2 * npix * 4 + ws * 128),
+                      "h2d_bytes_per_step": int(lab.size + ws * (2 * 201 * 16 + 481 * 4)), "d2h_bytes_per_step": int(2 * npix * 4 + ws * 128),
                       "note": "labels uploaded on every call; the clearance grids are rebuilt only when the labels change (content hash)"}
         if ws > 1:
             c.rebind_own()

@@ -700,6 +700,23 @@ __global__ void tally_reduce_map_kernel(const TallyPeers peers, int32_t *counts,
     else for (int j = 0; j < 4 && i4 + j < n; j++) map[i4 + j] = m[j];
 }
 
+// Label volume of a multi-device call: every device uploads 1/N of the labels over its own PCIe link, then completes
+// its copy by loading the other parts out of the peers' memory over NVLink (N x 34 MB through the host's memory system
+// took 1.5 ms of an 8 ms C2 step on 8 B200s; 34 MB once + NVLink is ~0.25 ms).  Parts are cut on 16-byte words.
+struct LabelPeers {
+    const uint4 *p[8];          // the peers' label buffers (index = device)
+    unsigned long long w_end[8];   // part j = words [w_end[j-1], w_end[j])
+    int n, self;
+};
+__global__ void label_gather_kernel(const LabelPeers L, uint4 *mine, unsigned long long n_words) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+        int j = 0;
+        while (j < L.n - 1 && w >= L.w_end[j]) j++;
+        if (j != L.self) mine[w] = L.p[j][w];
+    }
+}
+
 }  // namespace monte
 
 using namespace monte;
@@ -959,13 +976,19 @@ static int upload_clearance(monte_mc_scene *s, const uint8_t *labels, cudaStream
 // present_known: the caller's label_presence() of `labels` (one scan for all devices), or ~0u: scan here if needed
 static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_mc_volume *vol, const uint8_t *labels,
                         const monte_mc_xs *xs, const monte_mc_spectrum *spec, cudaStream_t st, uint64_t labels_hash = 0,
-                        uint32_t present_known = 0xffffffffu) {
+                        uint32_t present_known = 0xffffffffu, size_t part_lo = 0, size_t part_hi = ~(size_t)0,
+                        bool *labels_were_resident = nullptr) {
     s->geom = *g;
     McSceneDev &d = s->dev;
     const size_t nvox = (size_t)vol->nx * vol->ny * vol->nz;
-    if (int rc = grow(&s->d_labels, &s->cap_labels, nvox)) return rc;
+    if (int rc = grow(&s->d_labels, &s->cap_labels, (nvox + 15) & ~(size_t)15)) return rc;
     const bool labels_resident = labels_hash != 0 && s->labels_hash == labels_hash && s->labels_n == nvox;
-    if (!labels_resident) MONTE_CUDA(cudaMemcpyAsync(s->d_labels, labels, nvox, cudaMemcpyHostToDevice, st));
+    if (labels_were_resident) *labels_were_resident = labels_resident;
+    // [part_lo, part_hi): the bytes this device takes from the host (a multi-device caller completes the volume from the
+    // peers afterwards, label_gather_kernel); default: everything
+    if (part_hi > nvox) part_hi = nvox;
+    if (!labels_resident && part_hi > part_lo)
+        MONTE_CUDA(cudaMemcpyAsync((char *)s->d_labels + part_lo, labels + part_lo, part_hi - part_lo, cudaMemcpyHostToDevice, st));
     s->labels_hash = labels_hash; s->labels_n = nvox;
     d.labels = (const uint8_t *)s->d_labels;
     d.nx = vol->nx; d.ny = vol->ny; d.nz = vol->nz;
@@ -1045,7 +1068,7 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
     d.eid = g->detector_mode == MONTE_MC_DETECTOR_ENERGY ? 1 : 0;
     if (!s->d_work) MONTE_CUDA(cudaMalloc(&s->d_work, MC_WORK_RING * sizeof(unsigned long long)));
     s->smem = (size_t)nm * TAB_ROWS * sizeof(float4) + (TAB_ROWS + 3 + d.n_bins + 1) * sizeof(float);
-    s->h2d_bytes = (labels_resident ? 0 : nvox) + tab_bytes + inv_bytes + cdf_bytes + ray_bytes + clear_bytes + vcs_bytes;
+    s->h2d_bytes = (labels_resident || part_hi <= part_lo ? 0 : part_hi - part_lo) + tab_bytes + inv_bytes + cdf_bytes + ray_bytes + clear_bytes + vcs_bytes;
     // nothing is synchronised here: the staging block lives in the scene, and `labels` must stay valid until the
     // caller's next synchronisation of `st` (the host-buffer entry points synchronise before they return)
     return MONTE_OK;
@@ -1304,12 +1327,46 @@ int monte_gpu_simulate_maps(const monte_mc_geom *g, const monte_mc_volume *vol, 
     const auto t_host0 = std::chrono::steady_clock::now();
     EventTimer *t_k[MAX_DEV] = {nullptr};
     int rc = MONTE_OK;
+    // ---- scene upload.  Several devices with peer access: every device takes 1/nd of the label volume from the host and
+    // the rest from its peers (MONTE_MC_LABEL_SCATTER=0: every device uploads the whole volume itself)
+    const char *e_sc = getenv("MONTE_MC_LABEL_SCATTER");
+    const bool scatter = nd > 1 && peers_ok() && !(e_sc && atoi(e_sc) == 0) && nvox >= (size_t)nd * 4096;
+    LabelPeers lp;
+    lp.n = nd;
+    const unsigned long long n_words = (nvox + 15) / 16;
+    for (int j = 0; j < nd; j++) lp.w_end[j] = j == nd - 1 ? n_words : n_words * (j + 1) / nd;
+    cudaEvent_t lab_up[MAX_DEV] = {nullptr};
+    bool need_gather = false;
+    for (int i = 0; i < nd && rc == MONTE_OK; i++) {
+        if ((rc = use_dev(i))) break;
+        cudaStream_t st = ctx().stream;
+        if (!g_host_scene) { g_host_scene = new monte_mc_scene(); at_shutdown(mc_cleanup); }
+        const size_t lo = scatter ? (size_t)(i ? lp.w_end[i - 1] : 0) * 16 : 0, hi = scatter ? (size_t)lp.w_end[i] * 16 : ~(size_t)0;
+        bool resident = false;
+        if ((rc = scene_upload(g_host_scene, g, vol, labels, xs, spec, st, lhash, present, lo, hi, &resident))) break;
+        lp.p[i] = (const uint4 *)g_host_scene->d_labels;
+        if (scatter && !resident) {
+            need_gather = true;
+            if (cudaEventCreateWithFlags(&lab_up[i], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(lab_up[i], st) != cudaSuccess)
+                rc = cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__);
+        }
+    }
+    for (int i = 0; i < nd && rc == MONTE_OK && need_gather; i++) {
+        if ((rc = use_dev(i))) break;
+        cudaStream_t st = ctx().stream;
+        // (a device whose labels were resident has them complete, and nobody overwrites them: residency is decided by
+        // the same hash on every device, so either all gather or none -- the events of the others are simply absent)
+        for (int j = 0; j < nd && rc == MONTE_OK; j++)
+            if (j != i && lab_up[j] && cudaStreamWaitEvent(st, lab_up[j], 0) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaStreamWaitEvent", __FILE__, __LINE__);
+        if (rc || !lab_up[i]) continue;
+        lp.self = i;
+        label_gather_kernel MONTE_CFG((unsigned)(ctx().sm_count * 4), 256, 0, st)(lp, (uint4 *)g_host_scene->d_labels, n_words);
+        if (cudaGetLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "label_gather_kernel", __FILE__, __LINE__);
+    }
     for (int i = 0; i < nd && rc == MONTE_OK; i++) {
         if ((rc = use_dev(i))) break;
         Context &c = ctx();
         cudaStream_t st = c.stream;
-        if (!g_host_scene) { g_host_scene = new monte_mc_scene(); at_shutdown(mc_cleanup); }
-        if ((rc = scene_upload(g_host_scene, g, vol, labels, xs, spec, st, lhash, present))) break;
         char *base = (char *)scratch(5, off_map + (i == 0 && want_maps ? n_cnt * sizeof(float) : 0));
         if (!base) { rc = MONTE_E_NOMEM; break; }
         dv[i].d_im = (int32_t *)base;
@@ -1401,6 +1458,8 @@ int monte_gpu_simulate_maps(const monte_mc_geom *g, const monte_mc_volume *vol, 
         if (use_dev(i) != MONTE_OK) continue;
         delete t_k[i];
         if (dv[i].done) cudaEventDestroy(dv[i].done);
+        if (lab_up[i]) cudaEventDestroy(lab_up[i]);
+        if (rc != MONTE_OK && g_host_scene) g_host_scene->labels_hash = 0;    // (a scattered upload may be incomplete)
     }
     use_dev(0);
     delete t_d2h;

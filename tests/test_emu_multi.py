@@ -63,5 +63,10 @@ def test_emu_label_cache(monte_emu):
     M.body_label_cache(monte_emu)
 
 
+@pytest.mark.parametrize("n_dev", [2, 3, 8])
+def test_emu_scattered_label_upload(emu8, n_dev):
+    M.body_scattered_label_upload(emu8, n_dev)
+
+
 def test_emu_argument_errors(emu8):
     M.body_argument_errors(emu8)

@@ -107,6 +107,51 @@ def body_label_cache(api):
     assert np.array_equal(a0, d0) and np.array_equal(a5, d5)
 
 
+def body_scattered_label_upload(api, n_dev):
+    """several devices: every device takes 1/N of the label volume from the host and the rest from its peers over
+    NVLink (label_gather_kernel).  Same tallies with the scatter on or off, with the label cache on or off, when the
+    buffer changes in place, and when only some devices already hold the labels (a one-device call came first)."""
+    lab = scenes.cylinder_phantom(33, 1.0).copy()
+    lab[::3, 1::2, ::5] = 2                                            # make every part of the volume matter
+    mg = scenes.mc_geom(9, 32.5 / 9, n_views=2)
+    mvol = scenes.volume_for(lab, 1.0, tight=False)
+    xs, sp = scenes.make_xs(), scenes.mono_spectrum(60.0)
+    per = 40
+    env = os.environ
+    keep = {k: env.get(k) for k in ("MONTE_MC_LABEL_CACHE", "MONTE_MC_LABEL_SCATTER")}
+    try:
+        rebind(api, [0])
+        env["MONTE_MC_LABEL_CACHE"] = "0"
+        want = api.simulate(mg, mvol, lab, xs, sp, per, 11)[:2]
+        rebind(api, list(range(n_dev)))
+        for cache in ("0", "1"):
+            for scatter in ("1", "0"):
+                env["MONTE_MC_LABEL_CACHE"], env["MONTE_MC_LABEL_SCATTER"] = cache, scatter
+                for rep in range(2):                                  # second call: cached (cache = 1) or re-scattered
+                    got = api.simulate(mg, mvol, lab, xs, sp, per, 11)[:2]
+                    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (cache, scatter, rep)
+        # the buffer changes in place: a scattered re-upload must reach every device
+        env["MONTE_MC_LABEL_CACHE"], env["MONTE_MC_LABEL_SCATTER"] = "1", "1"
+        lab2 = lab.copy()
+        lab2[lab2 == 2] = 1
+        rebind(api, [0])
+        want2 = api.simulate(mg, mvol, lab2, xs, sp, per, 11)[:2]      # device 0 now holds lab2 (hash known)
+        assert not np.array_equal(want2[1], want[1])
+        rebind(api, list(range(n_dev)))                                # rebinding resets the per-device scenes ...
+        got2 = api.simulate(mg, mvol, lab2, xs, sp, per, 11)[:2]
+        assert np.array_equal(got2[0], want2[0]) and np.array_equal(got2[1], want2[1])
+        lab2[:] = lab                                                  # ... and now in place, same address
+        got3 = api.simulate(mg, mvol, lab2, xs, sp, per, 11)[:2]
+        assert np.array_equal(got3[0], want[0]) and np.array_equal(got3[1], want[1])
+    finally:
+        for k, v in keep.items():
+            if v is None:
+                env.pop(k, None)
+            else:
+                env[k] = v
+        rebind(api, [0])
+
+
 def body_argument_errors(api):
     from monte_b200.api import MonteError
     lab = scenes.cylinder_phantom(17, 2.0)
@@ -151,6 +196,12 @@ def test_mc_two_devices_equal_one(monte, mode):
 @pytest.mark.gpu
 def test_label_cache(monte):
     body_label_cache(monte)
+
+
+@pytest.mark.gpu
+def test_scattered_label_upload_two_devices(monte):
+    _need(2)
+    body_scattered_label_upload(monte, 2)
 
 
 @pytest.mark.gpu
