@@ -852,8 +852,14 @@ def bench_fdk_c3(c):
         e2e = {"value": updates * Kf / t_e2e / 1e9, "unit": "GUPS", "ms_per_step": 1e3 * t_e2e / Kf,
                "h2d_bytes_per_step": int(4 * g.n_views * g.nu * g.nv), "d2h_bytes_per_step": int(4 * g.nx * g.ny * g.nz),
                "call": "monte_gpu_fdk (C ABI, pinned host buffers)" + (" with the library bound to %d devices on rank 0" % ws if ws > 1 else ""),
-               "breakdown_ms": {"upload+filter": stf["ms_filter"], "gather+backproject": stf["ms_backproject"],
-                                "not_hidden_d2h_and_sync": stf["ms_d2h"], "total": stf["ms_total"]}}
+               "breakdown_ms": {"upload+filter": stf["ms_filter"],
+                                ("backproject_after_the_last_filter" if ws > 1 else "gather+backproject"): stf["ms_backproject"],
+                                "not_hidden_d2h_and_sync": stf["ms_d2h"], "total": stf["ms_total"]},
+               "limiter": ("host links: %.2f GB in + %.2f GB out in %.1f ms = %.0f GB/s through one host's PCIe / memory system; the backprojection "
+                           "runs underneath the uploads (views are dealt to the devices in interleaved chunks)" %
+                           (4e-9 * g.n_views * g.nu * g.nv, 4e-9 * g.nx * g.ny * g.nz, 1e3 * t_e2e / Kf,
+                            (4e-9 * g.n_views * g.nu * g.nv + 4e-9 * g.nx * g.ny * g.nz) / (t_e2e / Kf))) if ws > 1 else
+                          "backprojection (the uploads run underneath it)"}
         if not args.skip_parity and ws > 1:             # the N-device call against the one-device call on the same host buffers
             got = host_vol.numpy().copy()
             c.rebind_own()

@@ -166,6 +166,7 @@ int monte_gpu_init(int ndev, const int *ids) {
         MONTE_CUDA(cudaSetDevice(dev[i]));
         MONTE_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
         MONTE_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        MONTE_CUDA(cudaStreamCreateWithFlags(&c.aux_stream, cudaStreamNonBlocking));
         c.device = dev[i];
         c.sm_count = prop.multiProcessorCount;
         c.inited = true;
@@ -210,7 +211,8 @@ void monte_gpu_shutdown(void) {
         }
         if (c.stream) cudaStreamDestroy(c.stream);
         if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
-        c.stream = c.copy_stream = nullptr;
+        if (c.aux_stream) cudaStreamDestroy(c.aux_stream);
+        c.stream = c.copy_stream = c.aux_stream = nullptr;
         c.inited = false;
     }
     g_ndev = 0; g_cur = 0; g_peers = false;

@@ -36,6 +36,7 @@ struct Context {
     int       sm_count = 0;
     cudaStream_t stream = nullptr;     // library-owned stream for the host-buffer entry points
     cudaStream_t copy_stream = nullptr; // second stream: D2H of finished slabs overlaps compute
+    cudaStream_t aux_stream = nullptr;  // third stream: multi-device FDK backprojects on it while `stream` still filters
     // grow-only device scratch shared by the host-buffer entry points
     void  *scratch[N_SCRATCH] = {nullptr};
     size_t scratch_bytes[N_SCRATCH] = {0};

@@ -257,26 +257,29 @@ __global__ void fdk_pair_kernel(const float *__restrict__ f, float2 *__restrict_
 // copied, packed or stored twice.  src.base[o] is the (virtual) base of owner o's padded-row layout: row R of the
 // global layout lives at base[o] + R * pitch for the views [v_end[o-1], v_end[o]) owner o filtered.  The pad rules of
 // fdk_pad_kernel (element [r][nu] = [r+1][0], columns beyond and rows past the last view = 0) are applied on the fly.
+// (A device filters several chunks of views, interleaved with the other devices' chunks so that the reconstruction can
+// start while later chunks are still being uploaded: the layout is described per chunk = segment.)
+constexpr int PAIR_MAX_SEG = MAX_DEV * 4;
 struct PairSrc {
-    const float *base[MAX_DEV];
-    int v_end[MAX_DEV];
+    const float *base[PAIR_MAX_SEG];   // segment o holds views [v_end[o-1], v_end[o]) (segments may be empty)
+    int v_end[PAIR_MAX_SEG];
     int n;
 };
-__device__ __forceinline__ float pair_fetch(const PairSrc &src, int R, int c, int rows, int nv, int nu, int pitch) {
+__device__ __forceinline__ float pair_fetch(const PairSrc &src, int R, int c, int rows, int nv, int nu, int pitch, int seg0) {
     if (c > nu || R >= rows) return 0.f;
     if (c == nu) { R += 1; c = 0; if (R >= rows) return 0.f; }
     const int v = R / nv;
-    int o = 0;
+    int o = seg0;                                   // the segment of the launch's first view: the search starts there
     while (o < src.n - 1 && v >= src.v_end[o]) o++;
     return src.base[o][(size_t)R * pitch + c];
 }
 __global__ void fdk_pair_gather_kernel(const PairSrc src, float2 *__restrict__ pairs, int view_lo, int nv, int nu, int b_lo, int b_hi,
-                                       int rows, int pitch) {
+                                       int rows, int pitch, int seg0) {
     const int c = blockIdx.y * blockDim.x + threadIdx.x;
     const int R = (view_lo + (int)blockIdx.z) * nv + b_lo + (int)blockIdx.x;
     if (c >= pitch || (int)blockIdx.x >= b_hi - b_lo || R >= rows + 2) return;
-    const float a = pair_fetch(src, R, c, rows, nv, nu, pitch);
-    const float b = pair_fetch(src, R + 1, c, rows, nv, nu, pitch);
+    const float a = pair_fetch(src, R, c, rows, nv, nu, pitch, seg0);
+    const float b = pair_fetch(src, R + 1, c, rows, nv, nu, pitch, seg0);
     pairs[(size_t)R * pitch + c] = make_float2(a, b - a);
 }
 
@@ -1167,14 +1170,22 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
         // the whole slab projects above or below the detector in every view (bp3d20.cpp:116 skips every
         // voxel of it): its voxels keep the zeros / partial sums they have
         if (b_hi <= b_lo) return MONTE_OK;
-        // rows 0..3 of every view are always paired too: they are what the previous view reaches past its end
-        const int n_v = view_hi - view_lo + (view_hi < g->n_views ? 1 : 0);
+        // rows 0..3 of every view are always paired too: they are what the previous view reaches past its end -- also
+        // those of the view after the last one of this call (and only those of it: the rest of that view may not be
+        // filtered yet when a multi-device caller feeds the views chunk by chunk)
+        const int n_v = view_hi - view_lo;
         // (one launch shape for both sources: the local padded rows, or the peers' rows over NVLink)
         auto pair_rows = [&](int v_first, int r_lo, int r_hi, int n_views_z) {
             const dim3 grid(r_hi - r_lo, ceil_div(p.pitch, 128), n_views_z);
-            if (src) fdk_pair_gather_kernel MONTE_CFG(grid, 128, 0, st)(*src, d_pairs, v_first, g->nv, g->nu, r_lo, r_hi, rows_total - 2, p.pitch);
+            int seg0 = 0;
+            if (src) while (seg0 < src->n - 1 && v_first >= src->v_end[seg0]) seg0++;
+            if (src) fdk_pair_gather_kernel MONTE_CFG(grid, 128, 0, st)(*src, d_pairs, v_first, g->nv, g->nu, r_lo, r_hi, rows_total - 2, p.pitch, seg0);
             else fdk_pair_kernel MONTE_CFG(grid, 128, 0, st)(d_filtered_padded, d_pairs, v_first, g->nv, r_lo, r_hi, rows_total, p.pitch);
         };
+        if (view_hi < g->n_views) {
+            pair_rows(view_hi, 0, 4, 1);
+            MONTE_CUDA(cudaGetLastError());
+        }
         if (b_lo > 0) {
             pair_rows(view_lo, 0, b_lo < 4 ? b_lo : 4, n_v);
             MONTE_CUDA(cudaGetLastError());
@@ -1336,10 +1347,10 @@ static void balanced_cuts(const std::vector<double> &cost, int world, int align,
 }
 
 struct FdkMultiDev {              // what one device holds during a multi-device reconstruction
-    int v_lo = 0, v_hi = 0, z_lo = 0, z_hi = 0;
+    int n_views = 0, z_lo = 0, z_hi = 0;                 // views it filters (all its chunks), its z-slab
+    int off[8] = {0, 0, 0, 0, 0, 0, 0, 0};               // first local view of its k-th chunk
     float *d_map = nullptr, *d_filt = nullptr, *d_vol = nullptr;
-    cudaEvent_t filtered = nullptr;
-    EventTimer *t_f = nullptr, *t_b = nullptr;
+    cudaEvent_t start = nullptr, filter_end = nullptr, bp_end = nullptr;   // timing events on this device
 };
 
 int monte_gpu_fdk_partition(const monte_fdk_geom *g, int n_parts, int *z_cuts) {
@@ -1353,10 +1364,16 @@ int monte_gpu_fdk_partition(const monte_fdk_geom *g, int n_parts, int *z_cuts) {
     return MONTE_OK;
 }
 
-// monte_gpu_fdk on all bound devices.  Device i uploads and filters views [v_lo_i, v_hi_i) (upload chunks overlap the
-// filter), then backprojects ALL views into its own z-slab, fetching the detector-row band that slab reads straight
-// out of the peers' filtered rows (fdk_pair_gather_kernel: the exchange is fused into the pair conversion, nothing is
-// packed, copied or stored twice), and sends the slab home in pieces that overlap the next piece's backprojection.
+// monte_gpu_fdk on all bound devices.  The views are cut into C = N x n_up chunks in ascending order; chunk c
+// belongs to device c mod N, which uploads it over its own PCIe link and filters it.  Every device backprojects ALL
+// views into its own z-slab, chunk by chunk in ascending order, as soon as a chunk (and the one after it, whose first
+// rows the last view of a chunk reaches into) has been filtered wherever it lives: the detector-row band the slab reads
+// is loaded straight out of the owner's filtered rows (fdk_pair_gather_kernel: the exchange is fused into the pair
+// conversion over NVLink peer loads, nothing is packed, copied or stored twice) and the fp32 partial sums of the slab
+// are continued exactly.  Interleaving the chunks over the devices is what lets the reconstruction run while the
+// later chunks are still on their way: all PCIe links are busy from the start AND the first views are complete after
+// 1/n_up of the upload time (with contiguous view ranges nothing could start before device 0 had all of its views).
+// Three streams per device: copy (H2D chunks, D2H slab), stream (filter), aux (pair gather + backprojection).
 // Views are consumed in ascending order on every device, so the volume has the bits of the one-device call.
 static int fdk_multi(const monte_fdk_geom *g, const float *map, float *filtered, float *vol_xy, float *vol_zy, monte_fdk_stats *stats) {
     const int nd = n_dev();
@@ -1380,26 +1397,36 @@ static int fdk_multi(const monte_fdk_geom *g, const float *map, float *filtered,
         }
         memcpy(cuts, key_cuts, sizeof(cuts));
     }
+    // chunks of views: c = k * nd + i is the k-th chunk of device i
+    // (as many chunks as the segment table holds, at most 8 per device, at least 4 views each: finer chunks start the
+    // backprojection earlier and shorten what is left of it after the last upload; each costs ~4 launches per device)
+    int n_up = PAIR_MAX_SEG / nd < 8 ? PAIR_MAX_SEG / nd : 8;
+    while (n_up > 1 && g->n_views < 4 * nd * n_up) n_up--;
+    { const char *e = getenv("MONTE_FDK_MULTI_CHUNKS"); if (e && atoi(e) >= 1 && atoi(e) <= 8 && atoi(e) * nd <= PAIR_MAX_SEG) n_up = atoi(e); }
+    const int C = nd * n_up;
+    int V[PAIR_MAX_SEG + 1];
+    for (int c = 0; c <= C; c++) V[c] = (int)((long long)g->n_views * c / C);
     FdkMultiDev dv[MAX_DEV];
     PairSrc src;
-    src.n = nd;
+    src.n = C;
+    cudaEvent_t ev_f[PAIR_MAX_SEG] = {nullptr};                      // chunk c is filtered (recorded on its owner's stream)
     int rc = MONTE_OK, launches = 0;
-    // ---- phase 1 on every device: upload | filter
+    for (int i = 0; i < nd; i++) {
+        int n = 0;
+        for (int k = 0; k < n_up; k++) { dv[i].off[k] = n; n += V[k * nd + i + 1] - V[k * nd + i]; }
+        dv[i].n_views = n; dv[i].z_lo = cuts[i]; dv[i].z_hi = cuts[i + 1];
+    }
+    // ---- on every device: upload | filter, chunk by chunk
     for (int i = 0; i < nd && rc == MONTE_OK; i++) {
         FdkMultiDev &d = dv[i];
-        d.v_lo = (int)((long long)g->n_views * i / nd); d.v_hi = (int)((long long)g->n_views * (i + 1) / nd);
-        d.z_lo = cuts[i]; d.z_hi = cuts[i + 1];
         if ((rc = use_dev(i))) break;
         Context &c = ctx();
         cudaStream_t st = c.stream, cp = c.copy_stream;
-        const int nvw = d.v_hi - d.v_lo;
-        d.d_map = (float *)scratch(0, (size_t)(nvw ? nvw : 1) * per_view * sizeof(float));
-        d.d_filt = (float *)scratch(1, ((size_t)nvw * g->nv + 2) * pitch * sizeof(float));
+        d.d_map = (float *)scratch(0, (size_t)(d.n_views ? d.n_views : 1) * per_view * sizeof(float));
+        d.d_filt = (float *)scratch(1, ((size_t)d.n_views * g->nv + 2) * pitch * sizeof(float));
         d.d_vol = (float *)scratch(2, (size_t)(d.z_hi > d.z_lo ? d.z_hi - d.z_lo : 1) * slice * sizeof(float));
         if (!d.d_map || !d.d_filt || !d.d_vol) { rc = MONTE_E_NOMEM; break; }
-        if ((rc = fdk_prepare(g, st))) break;
-        src.base[i] = d.d_filt - (size_t)d.v_lo * g->nv * pitch;    // virtual base: row R of the global layout at base + R * pitch
-        src.v_end[i] = d.v_hi;
+        if ((rc = fdk_prepare(g, st))) break;                       // (synchronises on a miss: the tables are complete for every stream)
         FdkDevState &ds = g_fdk_state.get();
         if (!ds.ev_up[0]) {
             for (int k = 0; k < FDK_MAXC && rc == MONTE_OK; k++)
@@ -1409,81 +1436,97 @@ static int fdk_multi(const monte_fdk_geom *g, const float *map, float *filtered,
                 if (cudaEventCreate(&ds.ev_t[k]) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__);
             if (rc) break;
         }
-        d.t_f = new EventTimer(st); d.t_b = new EventTimer(st);
-        d.t_f->start();
-        if (cudaEventRecord(ds.ev_t[0], st) != cudaSuccess || cudaStreamWaitEvent(cp, ds.ev_t[0], 0) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__); break; }
-        const int n_up = nvw >= 16 ? 4 : 1;
-        for (int k = 0; k < n_up && rc == MONTE_OK && nvw > 0; k++) {
-            const int a = d.v_lo + (int)((long long)nvw * k / n_up), b = d.v_lo + (int)((long long)nvw * (k + 1) / n_up);
-            if (b <= a) continue;
-            if (cudaMemcpyAsync(d.d_map + (size_t)(a - d.v_lo) * per_view, map + (size_t)a * per_view, (size_t)(b - a) * per_view * sizeof(float),
-                                cudaMemcpyHostToDevice, cp) != cudaSuccess ||
-                cudaEventRecord(ds.ev_up[k], cp) != cudaSuccess || cudaStreamWaitEvent(st, ds.ev_up[k], 0) != cudaSuccess) {
-                rc = cuda_fail(cudaGetLastError(), "upload of a view chunk", __FILE__, __LINE__); break;
+        d.start = ds.ev_t[0]; d.filter_end = ds.ev_t[1]; d.bp_end = ds.ev_t[2];
+        if (cudaEventRecord(d.start, st) != cudaSuccess || cudaStreamWaitEvent(cp, d.start, 0) != cudaSuccess ||
+            cudaStreamWaitEvent(c.aux_stream, d.start, 0) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__); break; }
+        for (int k = 0; k < n_up && rc == MONTE_OK; k++) {
+            const int ch = k * nd + i, a = V[ch], b = V[ch + 1];
+            // row R of the global padded-row layout, R in chunk ch, lives at base + R * pitch on its owner
+            src.base[ch] = d.d_filt + ((long long)d.off[k] - a) * g->nv * pitch;
+            src.v_end[ch] = b;
+            if (b > a) {
+                float *dm = d.d_map + (size_t)d.off[k] * per_view;
+                if (cudaMemcpyAsync(dm, map + (size_t)a * per_view, (size_t)(b - a) * per_view * sizeof(float), cudaMemcpyHostToDevice, cp) != cudaSuccess ||
+                    cudaEventRecord(ds.ev_up[k], cp) != cudaSuccess || cudaStreamWaitEvent(st, ds.ev_up[k], 0) != cudaSuccess) {
+                    rc = cuda_fail(cudaGetLastError(), "upload of a view chunk", __FILE__, __LINE__); break;
+                }
+                // the filter addresses maps and rows by absolute view: hand it the virtual bases
+                if ((rc = monte_gpu_fdk_filter_dev(g, dm - (size_t)a * per_view, a, b, const_cast<float *>(src.base[ch]), st))) break;
+                launches++;
+                if (filtered) {                                     // the filtered views, if wanted: dense rows through the (now free) map chunk
+                    const size_t rows = (size_t)(b - a) * g->nv, n = rows * g->nu;
+                    fdk_unpad_kernel MONTE_CFG((unsigned)((n + 255) / 256), 256, 0, st)(d.d_filt + (size_t)d.off[k] * g->nv * pitch, dm, rows, g->nu, pitch);
+                    launches++;
+                }
             }
-            // the filter addresses maps and rows by absolute view: hand it the virtual bases
-            rc = monte_gpu_fdk_filter_dev(g, d.d_map - (size_t)d.v_lo * per_view, a, b, d.d_filt - (size_t)d.v_lo * g->nv * pitch, st);
-            launches++;
+            if (cudaEventCreateWithFlags(&ev_f[ch], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(ev_f[ch], st) != cudaSuccess)
+                rc = cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__);
         }
         if (rc) break;
-        d.t_f->stop();
-        if (cudaEventCreateWithFlags(&d.filtered, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(d.filtered, st) != cudaSuccess)
-            rc = cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__);
+        if (cudaEventRecord(d.filter_end, st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__);
     }
-    // ---- phase 2 on every device: wait for everybody's filtered rows | gather band + backproject | download
+    // ---- on every device: chunk by chunk, gather the band from the chunk's owner + backproject into the own slab
     for (int i = 0; i < nd && rc == MONTE_OK; i++) {
         FdkMultiDev &d = dv[i];
         if ((rc = use_dev(i))) break;
         Context &c = ctx();
-        cudaStream_t st = c.stream, cp = c.copy_stream;
+        cudaStream_t bp = c.aux_stream, cp = c.copy_stream;
         FdkDevState &ds = g_fdk_state.get();
-        for (int j = 0; j < nd && rc == MONTE_OK; j++)
-            if (j != i && cudaStreamWaitEvent(st, dv[j].filtered, 0) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaStreamWaitEvent", __FILE__, __LINE__);
-        if (rc) break;
-        d.t_b->start();
         const int nz_i = d.z_hi - d.z_lo;
-        const int n_part = nz_i >= 64 ? 2 : 1;                      // two pieces: the first goes home while the second is computed
-        for (int q = 0; q < n_part && rc == MONTE_OK && nz_i > 0; q++) {
-            int z0 = d.z_lo + (int)((long long)nz_i * q / n_part), z1 = d.z_lo + (int)((long long)nz_i * (q + 1) / n_part);
-            if (q > 0) z0 = z0 / 16 * 16;
-            if (q < n_part - 1) z1 = z1 / 16 * 16;
-            if (z1 <= z0) continue;
-            float *dst = d.d_vol + (size_t)(z0 - d.z_lo) * slice;
-            if ((rc = backproject_views(g, nullptr, z0, z1, dst, st, 0, g->n_views, false, &src))) break;
+        bool first = true;
+        int waited = -1;                                            // chunks [0, waited] are known to this stream
+        for (int ch = 0; ch < C && rc == MONTE_OK && nz_i > 0; ch++) {
+            if (V[ch + 1] <= V[ch]) continue;
+            int need = ch + 1;                                      // ... up to the next chunk that holds a view
+            while (need < C - 1 && V[need + 1] <= V[need]) need++;
+            if (need > C - 1) need = C - 1;
+            if (g->nv < 8) need = C - 1;                            // (rows 0..3 of "the next view" then span several views)
+            for (int w = waited + 1; w <= need && rc == MONTE_OK; w++)   // (own chunks too: they are filtered on another stream)
+                if (cudaStreamWaitEvent(bp, ev_f[w], 0) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaStreamWaitEvent", __FILE__, __LINE__);
+            if (rc) break;
+            if (need > waited) waited = need;
+            if ((rc = backproject_views(g, nullptr, d.z_lo, d.z_hi, d.d_vol, bp, V[ch], V[ch + 1], !first, &src))) break;
+            first = false;
             launches += 2;
-            if (cudaEventRecord(ds.ev_slab[q], st) != cudaSuccess || cudaStreamWaitEvent(cp, ds.ev_slab[q], 0) != cudaSuccess ||
-                cudaMemcpyAsync(vol_xy + (size_t)z0 * slice, dst, (size_t)(z1 - z0) * slice * sizeof(float), cudaMemcpyDeviceToHost, cp) != cudaSuccess)
-                rc = cuda_fail(cudaGetLastError(), "download of a slab", __FILE__, __LINE__);
         }
         if (rc) break;
-        d.t_b->stop();
+        if (nz_i > 0 && first) {                                    // no view at all: the slab is zero
+            if (cudaMemsetAsync(d.d_vol, 0, (size_t)nz_i * slice * sizeof(float), bp) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "cudaMemsetAsync", __FILE__, __LINE__); break; }
+        }
+        if (cudaEventRecord(d.bp_end, bp) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__); break; }
+        if (nz_i > 0) {                                             // the slab goes home
+            if (cudaStreamWaitEvent(cp, d.bp_end, 0) != cudaSuccess ||
+                cudaMemcpyAsync(vol_xy + (size_t)d.z_lo * slice, d.d_vol, (size_t)nz_i * slice * sizeof(float), cudaMemcpyDeviceToHost, cp) != cudaSuccess)
+                { rc = cuda_fail(cudaGetLastError(), "download of a slab", __FILE__, __LINE__); break; }
+        }
         if (vol_zy && nz_i > 0) {                                   // image_zy[s][t][z] (bp3d20.cpp:161): this slab's z-columns
             float *d_zy = (float *)scratch(3, (size_t)nz_i * slice * sizeof(float));
             if (!d_zy) { rc = MONTE_E_NOMEM; break; }
             dim3 grid(ceil_div(g->nx, 32), ceil_div(nz_i, 32), g->ny);
-            fdk_transpose_kernel MONTE_CFG(grid, dim3(32, 8), 0, st)(d.d_vol, d_zy, g->nx, g->ny, nz_i);
+            fdk_transpose_kernel MONTE_CFG(grid, dim3(32, 8), 0, bp)(d.d_vol, d_zy, g->nx, g->ny, nz_i);
             launches++;
             if (cudaGetLastError() != cudaSuccess ||
                 cudaMemcpy2DAsync(vol_zy + d.z_lo, (size_t)g->nz * sizeof(float), d_zy, (size_t)nz_i * sizeof(float), (size_t)nz_i * sizeof(float),
-                                  slice, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "transposed slab", __FILE__, __LINE__);
+                                  slice, cudaMemcpyDeviceToHost, bp) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "transposed slab", __FILE__, __LINE__);
         }
+        (void)ds;
     }
-    // ---- the filtered maps, if wanted: every device sends its own views (after all peers have read them? they are only read)
+    // ---- the filtered maps, if wanted: every device sends its own chunks (dense copies made right after the filter)
     for (int i = 0; i < nd && rc == MONTE_OK && filtered; i++) {
         FdkMultiDev &d = dv[i];
         if ((rc = use_dev(i))) break;
         cudaStream_t st = ctx().stream;
-        const size_t rows = (size_t)(d.v_hi - d.v_lo) * g->nv, n = rows * g->nu;
-        if (!n) continue;
-        fdk_unpad_kernel MONTE_CFG((unsigned)((n + 255) / 256), 256, 0, st)(d.d_filt, d.d_map, rows, g->nu, pitch);   // d_map is free now
-        launches++;
-        if (cudaGetLastError() != cudaSuccess ||
-            cudaMemcpyAsync(filtered + (size_t)d.v_lo * per_view, d.d_map, n * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess)
-            rc = cuda_fail(cudaGetLastError(), "download of the filtered views", __FILE__, __LINE__);
+        for (int k = 0; k < n_up && rc == MONTE_OK; k++) {
+            const int ch = k * nd + i, a = V[ch], b = V[ch + 1];
+            if (b <= a) continue;
+            if (cudaMemcpyAsync(filtered + (size_t)a * per_view, d.d_map + (size_t)d.off[k] * per_view, (size_t)(b - a) * per_view * sizeof(float),
+                                cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "download of the filtered views", __FILE__, __LINE__);
+        }
     }
     for (int i = 0; i < nd; i++) {                                   // (also after an error: nothing may stay in flight)
         if (use_dev(i) != MONTE_OK) continue;
         cudaError_t e = cudaStreamSynchronize(ctx().stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().aux_stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().copy_stream);
         if (e != cudaSuccess && rc == MONTE_OK) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
     }
@@ -1491,20 +1534,21 @@ static int fdk_multi(const monte_fdk_geom *g, const float *map, float *filtered,
         memset(stats, 0, sizeof(*stats));
         for (int i = 0; i < nd; i++) {
             use_dev(i);
-            if (dv[i].t_f) stats->ms_filter = fmax(stats->ms_filter, dv[i].t_f->ms());          // incl. the overlapped uploads
-            if (dv[i].t_b) stats->ms_backproject = fmax(stats->ms_backproject, dv[i].t_b->ms());
+            float tf = 0.f, tb = 0.f;
+            // ms_filter: upload + filter of the device's chunks; ms_backproject: what the backprojection still needed after
+            // that (the rest ran underneath the uploads); both as the maximum over the devices
+            if (dv[i].start && cudaEventElapsedTime(&tf, dv[i].start, dv[i].filter_end) == cudaSuccess) stats->ms_filter = fmax(stats->ms_filter, (double)tf);
+            if (dv[i].start && cudaEventElapsedTime(&tb, dv[i].start, dv[i].bp_end) == cudaSuccess) stats->ms_backproject = fmax(stats->ms_backproject, (double)tb);
         }
+        cudaGetLastError();
+        stats->ms_backproject = fmax(0.0, stats->ms_backproject - stats->ms_filter);
         stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
         stats->ms_d2h = fmax(0.0, stats->ms_total - stats->ms_filter - stats->ms_backproject);   // what compute did not hide (host clock)
         stats->voxel_updates = (uint64_t)(g->s_end - g->s_begin) * (g->t_end - g->t_begin) * (g->z_end - g->z_begin) * g->n_views;
         stats->filter_macs = (uint64_t)g->n_views * g->nv * g->nu * g->nu;
         stats->launches = launches; stats->sm_count = ctx_of(0).sm_count;
     }
-    for (int i = 0; i < nd; i++) {
-        if (use_dev(i) != MONTE_OK) continue;
-        delete dv[i].t_f; delete dv[i].t_b;
-        if (dv[i].filtered) cudaEventDestroy(dv[i].filtered);
-    }
+    for (int ch = 0; ch < C; ch++) if (ev_f[ch]) cudaEventDestroy(ev_f[ch]);
     use_dev(0);
     return rc;
 }

@@ -26,6 +26,14 @@ def test_emu_fdk_multi_equals_single(emu8, n_dev, case):
     M.body_fdk_multi_equals_single(emu8, n_dev, case)
 
 
+@pytest.mark.parametrize("n_dev,chunks,case", [(2, 4, (37, 40, 30, 48, None)), (3, 4, (37, 40, 30, 48, "roi")), (8, 3, (5, 24, 16, 16, None)),
+                                               (8, 4, (130, 24, 20, 24, None)), (2, 4, (64, 300, 12, 16, None)), (5, 2, (12, 33, 65, 24, "tall")),
+                                               (4, 4, (9, 16, 5, 16, None)), (2, 8, (37, 40, 30, 48, None)), (4, 8, (130, 24, 20, 24, "roi")),
+                                               (3, 7, (20, 24, 20, 24, None))])
+def test_emu_fdk_multi_chunked_pipeline(emu8, n_dev, chunks, case):
+    M.body_fdk_multi_chunked(emu8, n_dev, chunks, case)
+
+
 @pytest.mark.parametrize("n_dev,mode", [(2, "p2p"), (3, "nccl"), (8, "p2p"), (5, "nccl")])
 def test_emu_mc_multi_equals_single(emu8, n_dev, mode):
     M.body_mc_multi_equals_single(emu8, n_dev, mode)

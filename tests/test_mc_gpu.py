@@ -3,7 +3,11 @@
 Three levels, from strongest to the one BASELINE.json's north_star states:
  1. history-coupled: the oracle (intended physics, Philox mode) and the CUDA kernel draw the same
     Philox2x32-10 variates per history, so every history must end the same way (same fate, same
-    detector bin); the only allowed differences are fp32-vs-fp64 threshold flips (< 0.3 %).
+    detector bin); the only allowed differences are fp32-vs-fp64 threshold flips.  Census on a B200
+    (scripts/mc_flip_census.py, profiles/r02_mc_flip_census.jsonl): 26 of 3.04e6 histories over six scenes
+    (8.5e-6; 6 scatter hits within rounding of a pixel edge, 20 histories whose path diverged at an upstream
+    threshold -- Woodcock acceptance, voxel face, interaction selection, Kahn acceptance), worst scene 1.4e-5.
+    The bars below are 1e-3: two orders of magnitude above what is observed, ten times below round 1's.
  2. deterministic: the primary projection agrees with the oracle within 1e-4 relative (fp32),
     counts->map exactly, results are independent of how histories are partitioned.
  3. statistical (north_star): against the oracle driven by the reference's own generator
@@ -53,7 +57,7 @@ def test_history_coupled_fates_match_oracle(monte, oracle, mode, poly):
     kind_g, kind_c = f_gpu & 0xFF, f_cpu & 0xFF
     assert (kind_g != 0).all() and (kind_c != 0).all()      # every history was run and ended
     same = f_gpu == f_cpu
-    assert same.mean() > 0.997, "only %.4f of %d histories end identically" % (same.mean(), same.size)
+    assert same.mean() > 0.999, "only %.4f of %d histories end identically" % (same.mean(), same.size)
     # where the fate matches the photon energy must too
     assert np.allclose(e_gpu[same], e_cpu[same], rtol=2e-5)
     # every kind of ending is exercised
@@ -71,11 +75,11 @@ def test_images_and_counters_match_coupled_oracle(monte, oracle):
                                       oracle.mc_opts(oracle.RNG_PHILOX, seed=seed), per)
     n = st["histories"]
     assert n == res["histories"] == 2 * 17 * 17 * per
-    assert np.abs(im0.astype(int) - o0).sum() <= 0.003 * n
-    assert np.abs(im5.astype(int) - o5).sum() <= 0.003 * n
+    assert np.abs(im0.astype(int) - o0).sum() <= 0.001 * n
+    assert np.abs(im5.astype(int) - o5).sum() <= 0.001 * n
     for k in ("primaries", "scatter_detected", "absorbed", "interactions", "coherent", "compton", "woodcock_steps"):
-        assert abs(st[k] - res[k]) <= 0.003 * max(res[k], 1) + 5, (k, st[k], res[k])
-    assert abs(st["sum_e_scatter"] - res["sum_e_scatter"]) <= 0.003 * res["sum_e_scatter"] + 200
+        assert abs(st[k] - res[k]) <= 0.001 * max(res[k], 1) + 5, (k, st[k], res[k])
+    assert abs(st["sum_e_scatter"] - res["sum_e_scatter"]) <= 0.001 * res["sum_e_scatter"] + 200
     assert im0.sum() == st["primaries"] and im5.sum() == st["primaries"] + st["scatter_detected"]
 
 
@@ -95,8 +99,8 @@ def test_energy_integrating_detector_matches_coupled_oracle(monte, oracle):
     o0, o5, res, _, _ = oracle.mc_run(g, vol, lab, oracle.tables_from_xs(xs), scenes.mono_spectrum(140.0),
                                       oracle.mc_opts(oracle.RNG_PHILOX, seed=seed), per)
     n = ste["histories"]
-    assert np.abs(e0.astype(np.int64) - o0).sum() <= 0.003 * n * 16 * 140
-    assert np.abs(e5.astype(np.int64) - o5).sum() <= 0.003 * n * 16 * 140
+    assert np.abs(e0.astype(np.int64) - o0).sum() <= 0.001 * n * 16 * 140
+    assert np.abs(e5.astype(np.int64) - o5).sum() <= 0.001 * n * 16 * 140
     g.detector_mode = 7
     with pytest.raises(Exception, match="detector_mode"):
         monte.simulate(g, vol, lab, xs, scenes.mono_spectrum(140.0), per, seed)
@@ -298,7 +302,7 @@ def test_three_materials_im_variant_coupled(monte, oracle):
     sc.close()
     _, _, res, f_cpu, _ = oracle.mc_run(g, vol, lab, oracle.tables_from_xs(xs), scenes.mono_spectrum(140.0),
                                         oracle.mc_opts(oracle.RNG_PHILOX, seed=seed), per, views=(0, 1), want_fates=True)
-    assert (f_gpu == f_cpu).mean() > 0.997
+    assert (f_gpu == f_cpu).mean() > 0.999
     im0, im5, st = monte.simulate(g, vol, lab, xs, scenes.mono_spectrum(140.0), per, seed)
     o0, o5, res, _, _ = oracle.mc_run(g, vol, lab, oracle.tables_from_xs(xs), scenes.mono_spectrum(140.0),
                                       oracle.mc_opts(oracle.RNG_PHILOX, seed=seed), per)
@@ -334,7 +338,7 @@ def test_hu_volume_transport_with_present_material_majorant(monte, oracle):
                                             oracle.mc_opts(oracle.RNG_PHILOX, seed=seed), per,
                                             views=(view, view + 1), want_fates=True)
     same = f_gpu == f_cpu
-    assert same.mean() > 0.995, "only %.4f of %d histories end identically" % (same.mean(), same.size)
+    assert same.mean() > 0.999, "only %.4f of %d histories end identically" % (same.mean(), same.size)
     assert np.allclose(e_gpu[same], e_cpu[same], rtol=2e-5)
     for k in (1, 3, 4):
         assert ((f_cpu & 0xFF) == k).any(), k
@@ -342,8 +346,8 @@ def test_hu_volume_transport_with_present_material_majorant(monte, oracle):
     p0, p5, st_p = monte.simulate(g, vol, lab, xs, spec, 60, seed)
     o0, o5, res, _, _ = oracle.mc_run(g, vol, lab, oracle.tables_from_xs(xs), spec, oracle.mc_opts(oracle.RNG_PHILOX, seed=seed), 60)
     n = st_p["histories"]
-    assert np.abs(p0.astype(int) - o0).sum() <= 0.005 * n and np.abs(p5.astype(int) - o5).sum() <= 0.005 * n
-    assert abs(st_p["woodcock_steps"] - res["woodcock_steps"]) <= 0.005 * res["woodcock_steps"] + 5
+    assert np.abs(p0.astype(int) - o0).sum() <= 0.001 * n and np.abs(p5.astype(int) - o5).sum() <= 0.001 * n
+    assert abs(st_p["woodcock_steps"] - res["woodcock_steps"]) <= 0.001 * res["woodcock_steps"] + 5
     vol.majorant_mode = _abi.MAJORANT_ALL
     a0, a5, st_a = monte.simulate(g, vol, lab, xs, spec, 60, seed)
     assert st_p["woodcock_steps"] < 0.9 * st_a["woodcock_steps"], (st_p["woodcock_steps"], st_a["woodcock_steps"])

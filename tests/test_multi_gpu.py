@@ -56,6 +56,21 @@ def body_fdk_multi_equals_single(api, n_dev, case):
     assert cuts[0] == 0 and cuts[-1] == g.nz and all(b >= a for a, b in zip(cuts, cuts[1:]))
 
 
+def body_fdk_multi_chunked(api, n_dev, chunks, case=(37, 40, 30, 48, None)):
+    """the chunk-interleaved pipeline of the multi-device reconstruction: `chunks` chunks of views per device (the
+    library takes 4 when there are >= 16 views per device; forced here, so that ragged and empty chunks occur),
+    every chunk gathered from its owner and backprojected as soon as it and its successor are filtered"""
+    old = os.environ.get("MONTE_FDK_MULTI_CHUNKS")
+    os.environ["MONTE_FDK_MULTI_CHUNKS"] = str(chunks)
+    try:
+        body_fdk_multi_equals_single(api, n_dev, case)
+    finally:
+        if old is None:
+            del os.environ["MONTE_FDK_MULTI_CHUNKS"]
+        else:
+            os.environ["MONTE_FDK_MULTI_CHUNKS"] = old
+
+
 def body_mc_multi_equals_single(api, n_dev, reduce_mode, per=37):
     lab = scenes.cylinder_phantom(33, 1.0)
     mg = scenes.mc_geom(9, 32.5 / 9, n_views=3)
@@ -184,6 +199,13 @@ def body_argument_errors(api):
 def test_fdk_two_devices_equal_one(monte, case):
     _need(2)
     body_fdk_multi_equals_single(monte, 2, case)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunks,case", [(8, (70, 40, 30, 48, None)), (4, (37, 40, 30, 48, None)), (3, (5, 24, 16, 16, None)), (4, (64, 300, 24, 32, None)), (2, (31, 65, 33, 40, "roi"))])
+def test_fdk_two_devices_chunked_pipeline(monte, chunks, case):
+    _need(2)
+    body_fdk_multi_chunked(monte, 2, chunks, case)
 
 
 @pytest.mark.gpu
