@@ -871,6 +871,9 @@ struct FdkDevState {
     bool fft_attr_set = false;
     size_t filter_smem_set = 0, bps_smem_set[2] = {0, 0};
     cudaEvent_t ev_up[FDK_MAXC] = {nullptr}, ev_slab[FDK_MAXC] = {nullptr}, ev_t[6] = {nullptr};
+    // z-block streams of the backprojector (thin multi-GPU slabs, see backproject_views)
+    cudaStream_t zs[8] = {nullptr};
+    cudaEvent_t ev_zfork = nullptr, ev_zjoin[8] = {nullptr};
 };
 static PerDev<FdkDevState> g_fdk_state;
 #define g_fft_attr_set (g_fdk_state.get().fft_attr_set)
@@ -886,6 +889,11 @@ static void fdk_cleanup() {                       // called once per bound devic
         if (g_ev_slab[i]) cudaEventDestroy(g_ev_slab[i]);
     }
     for (int i = 0; i < 6; i++) if (g_ev_t[i]) cudaEventDestroy(g_ev_t[i]);
+    {
+        FdkDevState &ds = g_fdk_state.get();
+        for (int i = 0; i < 8; i++) { if (ds.zs[i]) cudaStreamDestroy(ds.zs[i]); if (ds.ev_zjoin[i]) cudaEventDestroy(ds.ev_zjoin[i]); }
+        if (ds.ev_zfork) cudaEventDestroy(ds.ev_zfork);
+    }
     g_fdk_state.get() = FdkDevState();
 }
 
@@ -1197,11 +1205,44 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
             MONTE_CUDA(cudaGetLastError());
         }
     }
+    // A thin slab (one of N multi-GPU slabs: 3..7 z-blocks of 16 slices) makes every view-chunk launch a handful of
+    // waves (C3 on 8 GPUs: 3072 CTAs on 592 resident slots = 5.2), and the launches of one stream do not overlap: each
+    // ends in a partly filled wave, ~10 % of the slab's time.  The z-blocks are independent, so each gets its own
+    // stream: its view chunks stay in order, and the tail of one z-block's launch is filled with CTAs of the next
+    // one's.  Launches are issued chunk-major, so the z-blocks walk through the views together (L2-sized chunks).
+    const int zb_first = z_lo / 16, zb_end = ceil_div(z_hi, 16);
+    bool zsplit = variant == 0 && zb_end - zb_first >= 2 && zb_end - zb_first <= 8 && view_hi - view_lo > vchunk;
+#ifdef MONTE_EMU
+    zsplit = false;
+#endif
+    { const char *e = getenv("MONTE_BP_ZSTREAMS"); if (e && atoi(e) == 0) zsplit = false; }   // (read per call: the test flips it)
+    FdkDevState &zds = g_fdk_state.get();
+    if (zsplit) {
+        if (!zds.ev_zfork) {
+            MONTE_CUDA(cudaEventCreateWithFlags(&zds.ev_zfork, cudaEventDisableTiming));
+            for (int i = 0; i < 8; i++) {
+                MONTE_CUDA(cudaStreamCreateWithFlags(&zds.zs[i], cudaStreamNonBlocking));
+                MONTE_CUDA(cudaEventCreateWithFlags(&zds.ev_zjoin[i], cudaEventDisableTiming));
+            }
+        }
+        MONTE_CUDA(cudaEventRecord(zds.ev_zfork, st));
+        for (int i = 0; i < zb_end - zb_first; i++) MONTE_CUDA(cudaStreamWaitEvent(zds.zs[i], zds.ev_zfork, 0));
+    }
     for (int vb = view_lo; vb < view_hi; vb += vchunk) {
     // a chunk is presented to the kernel as a shorter scan: shifted view constants and rows
     p.n_views = vb + vchunk < view_hi ? vchunk : view_hi - vb;
     p.vc = g_fdk.d_vc + vb;
     p.pairs = d_pairs + (size_t)vb * g->nv * p.pitch; p.accumulate = continue_sum || vb > view_lo;
+    if (zsplit) {
+        for (int zb = zb_first; zb < zb_end; zb++) {
+            BpParams q = p;
+            q.z_lo = zb * 16 > z_lo ? zb * 16 : z_lo; q.z_hi = (zb + 1) * 16 < z_hi ? (zb + 1) * 16 : z_hi;
+            q.vol = d_vol_slab + (size_t)(q.z_lo - z_lo) * g->ny * g->nx;
+            dim3 grid(ceil_div(g->s_end - g->s_begin, BP_TX), ceil_div(g->t_end - g->t_begin, BP_TY), 1);
+            fdk_backproject_kernel<16, 8, 4> MONTE_CFG(grid, block, 0, zds.zs[zb - zb_first])(q);
+        }
+        continue;
+    }
     switch (variant) {
 #ifndef MONTE_EMU
         case 10: case 11: {
@@ -1243,6 +1284,11 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
     }
 #undef BP_LAUNCH
     MONTE_CUDA(cudaGetLastError());
+    if (zsplit)
+        for (int i = 0; i < zb_end - zb_first; i++) {
+            MONTE_CUDA(cudaEventRecord(zds.ev_zjoin[i], zds.zs[i]));
+            MONTE_CUDA(cudaStreamWaitEvent(st, zds.ev_zjoin[i], 0));
+        }
     return MONTE_OK;
 }
 

@@ -270,3 +270,36 @@ def test_tma_staged_backprojector_gives_the_bits_of_the_default_kernel(monte, va
             assert torch.equal(v, w)
             vols[var] = v
         assert bool(torch.isfinite(vols["0"]).all()) and torch.equal(vols["0"], vols[variant])
+
+
+def test_thin_slab_z_block_streams_are_bit_identical(tmp_path):
+    """a thin z-slab (2..8 z-blocks) backprojected in several view chunks runs every z-block on its own stream so that
+    the tail of one launch is filled by the next z-block's CTAs (multi-GPU slabs): same bits as the single-stream
+    launches and as the whole-volume call.  Own process: the view-chunk size is read once per process."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import os, sys, numpy as np, torch
+sys.path.insert(0, %r)
+from monte_b200 import _abi, api
+api.init(0)
+g = _abi.generic_fdk_geom(26, 72, 56, 64)
+proj = torch.rand((26, 72, 56), device="cuda")
+filt = torch.zeros(api.fdk_filtered_shape(g), device="cuda")
+api.fdk_filter_dev(g, proj, filt)
+whole = torch.zeros((64, 64, 64), device="cuda")
+api.fdk_backproject_dev(g, filt, whole)
+outs = []
+for zs in ("1", "0"):
+    os.environ["MONTE_BP_ZSTREAMS"] = zs
+    slab = torch.full((43, 64, 64), float("nan"), device="cuda")
+    api.fdk_backproject_dev(g, filt, slab, 9, 52)          # 4 z-blocks (one ragged at each end), 26 views in chunks of 4
+    torch.cuda.synchronize()
+    outs.append(slab)
+assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], whole[9:52]) and bool(torch.isfinite(outs[0]).all())
+print("ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MONTE_BP_VCHUNK="4")
+    out = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
