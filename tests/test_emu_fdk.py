@@ -194,9 +194,16 @@ def test_emu_shutdown_and_reinit_rebuild_every_cache(monte_emu, oracle):
 def test_emu_smoke_path(monte_emu):
     """__graft_entry__.smoke()'s own checks (FDK, FFT filter, MC coupled with the oracle, projector, the optional
     transport modes), run on the emulated library; leaves the binding initialised for the tests that follow"""
+    import os
     import __graft_entry__ as ge
     ge._smoke(monte_emu)
     monte_emu.init(0)
+    os.environ["MONTE_EMU_DEVICES"] = "2"                # ... and once more with two "devices": the 2-device check of smoke()
+    try:
+        ge._smoke(monte_emu)
+    finally:
+        del os.environ["MONTE_EMU_DEVICES"]
+        monte_emu.init(0)
 
 
 @pytest.mark.slow
