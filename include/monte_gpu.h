@@ -26,14 +26,15 @@
 extern "C" {
 #endif
 
-#define MONTE_GPU_ABI_VERSION 5   /* 2: monte_mc_geom.detector_mode; 3: monte_mc_geom.coherent_mode (was
+#define MONTE_GPU_ABI_VERSION 6   /* 2: monte_mc_geom.detector_mode; 3: monte_mc_geom.coherent_mode (was
                                      `reserved`, 0 = unchanged behaviour), form-factor tables appended to monte_mc_xs,
                                      tracking_mode / clearance_cell_log2 appended to monte_mc_volume (0 = unchanged);
                                      4: monte_gpu_init binds 1..8 devices and the host-buffer calls monte_gpu_simulate* /
                                      monte_gpu_fdk shard over them; monte_gpu_simulate_maps; "all views" is spelled
                                      view_end < 0 (the range [0, 0) is now empty, as in the device forms);
                                      5: majorant_mode appended to monte_mc_volume (0 = unchanged); monte_hu_class,
-                                     monte_hu_classes_default, monte_ctnum_segment (N-class HU segmentation)       */
+                                     monte_hu_classes_default, monte_ctnum_segment (N-class HU segmentation);
+                                     6: detector_shape / ring_radius appended to monte_mc_geom (0 = the flat panel)   */
 
 /* ---- status codes ------------------------------------------------------ */
 #define MONTE_OK            0
@@ -287,6 +288,16 @@ typedef struct monte_mc_volume {
                                            probability (1+cos^2 theta)/2, cos theta = 1 - 2 x^2/x^2_max; phi
                                            uniform; energy unchanged                                             */
 
+/* detector shape.  RING is the geometry of the reference's 2-D programs (monte_cpp/circle3_2.cpp:
+ * a source at the centre of a water disc, a ring of 180 angular bins at radius 10 cm, :162,:252), generalised to a
+ * cylinder: the source sits on the rotation axis at the origin, bin (i, j) of the [ny][nx] images covers the angle
+ * [2 pi i / ny, 2 pi (i + 1) / ny) about the z axis (rotated by the view angle) and the height
+ * [half - pixel (j + 1), half - pixel j] at radius ring_radius; nx = 1 with max_scatter as wanted is the 2-D case.
+ * `per` photons are aimed at the centre of every bin (SOURCE_PENCIL) or uniformly inside it (SOURCE_CONE); dso / dod
+ * are not used.  The clip box must lie inside the ring.                                                          */
+#define MONTE_MC_DETECTOR_FLAT 0      /* the flat panel at x = dod (CBCT_real325im.cu:459-466, :567-590)          */
+#define MONTE_MC_DETECTOR_RING 1
+
 typedef struct monte_mc_geom {
     int32_t n_views;
     double  angle0_deg, angle_step_deg;  /* view v at angle0 + v*step (1 deg, :462,508) */
@@ -300,6 +311,9 @@ typedef struct monte_mc_geom {
     int32_t max_scatter;     /* ScatterNUM = 5 (CBCT_real325im.cu:7)                     */
     int32_t detector_mode;   /* MONTE_MC_DETECTOR_*; 0 = the reference's photon counting  */
     int32_t coherent_mode;   /* MONTE_MC_COHERENT_*; 0 = the reference's undeflected coherent event */
+    int32_t detector_shape;  /* MONTE_MC_DETECTOR_FLAT / _RING; 0 = the reference's flat panel               */
+    int32_t reserved1;       /* 0                                                                         */
+    double  ring_radius;     /* RING only: radius of the detector cylinder, cm                            */
 } monte_mc_geom;
 
 /* spectrum: n_bins == 0 -> mono-energetic at mono_keV (as shipped: 140, survey Q3);

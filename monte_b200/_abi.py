@@ -21,6 +21,7 @@ SOURCE_PENCIL, SOURCE_CONE = 0, 1
 COHERENT_FORWARD, COHERENT_FORMFACTOR = 0, 1
 TRACK_GLOBAL, TRACK_CLEARANCE, TRACK_AUTO, TRACK_ADAPTIVE, TRACK_DIRECTIONAL = 0, 1, 2, 3, 4
 MAJORANT_ALL, MAJORANT_PRESENT = 0, 1
+DETECTOR_FLAT, DETECTOR_RING = 0, 1
 
 
 class HuClass(C.Structure):
@@ -102,6 +103,7 @@ class McGeom(C.Structure):
         ("dso", C.c_double), ("dod", C.c_double),
         ("source_mode", C.c_int32), ("max_scatter", C.c_int32),
         ("detector_mode", C.c_int32), ("coherent_mode", C.c_int32),
+        ("detector_shape", C.c_int32), ("reserved1", C.c_int32), ("ring_radius", C.c_double),
     ]
 
 
@@ -196,4 +198,18 @@ def generic_fdk_geom(n_views, nu, nv, n, *, full_circle=True, textbook=False):
     g.full_roi()
     g.weight_mode = FDK_TEXTBOOK if textbook else FDK_REFERENCE
     g.coord_mode = COORD_SCALE_AFTER
+    return g
+
+
+def fan_beam_2d_geom(n_views, nu, n, *, textbook=True):
+    """2-D fan-beam reconstruction as the degenerate nv = 1 case of the cone-beam kernels: one detector row
+    in the central plane, one slice at Z = 0.  half_v = 0 puts every voxel's axial detector coordinate exactly on row 0
+    (x = (half_v - w) / dv = 0 with w = k Z = 0), so the bilinear fetch reduces to linear interpolation along u, and the
+    cone-beam weights reduce to the fan-beam ones.  (recon/fbp2.cpp itself -- nearest-neighbour lookup, double
+    arithmetic -- is reproduced by monte_gpu_fbp2.)"""
+    g = generic_fdk_geom(n_views, nu, 1, n, textbook=textbook)
+    g.nz = 1
+    g.z_begin, g.z_end = 0, 1
+    g.z0 = 0.0
+    g.half_v = 0.0
     return g

@@ -48,6 +48,8 @@ struct McSceneDev {
     float pixel, inv_pixel, half, dso, dod, dsd;
     int source_mode, max_scatter;
     int eid;                    // energy-integrating detector: tally (int)(E*16+0.5) instead of 1
+    int ring;                   // detector_shape RING: source at the origin, cylinder of radius ring_r about the z axis
+    float ring_r, ring_r2, ring_dphi, ring_kphi;   // radius, its square, 2 pi / ny, ny / 2 pi
 };
 
 struct PhiloxKeys { uint32_t rk[10]; };   // key + r * 0x9E3779B9, r = 0..9 (see philox2x32_10)
@@ -152,7 +154,9 @@ __device__ __forceinline__ float ray_interp(const float *xs, const float *ys, in
 // step); a step that starts with clearance > 0 is sampled with the majorant of the lighter materials and cut
 // at the clearance radius.  Same collision-site distribution as the reference's loop, far fewer virtual
 // collisions when a dense insert sets the global majorant (C4: 23 -> ~5 steps per history).
-template <bool RECORD, int K, int MINB = 3, int NSTEP = 2, bool RAYLEIGH = false, bool CLEAR = false>
+// RING = true: monte_mc_geom.detector_shape == MONTE_MC_DETECTOR_RING: source at the origin, detector bins on a
+// cylinder about the z axis.  Its own instantiation: the flat-panel kernels carry none of it.
+template <bool RECORD, int K, int MINB = 3, int NSTEP = 2, bool RAYLEIGH = false, bool CLEAR = false, bool RING = false>
 __global__ void __launch_bounds__(MC_THREADS, MINB)
 mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
     MONTE_DYN_SMEM(float4, s_mem);
@@ -342,7 +346,8 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             if (P.collide_check) {
                 const float2 cs = __ldg(sc.view_cs + (id.w >> 20));
                 const float xr = pos.x * cs.x + pos.y * cs.y, yr = -pos.x * cs.y + pos.y * cs.x;
-                if (xr >= sc.dod || fabsf(yr) >= sc.half || fabsf(pos.z) >= sc.half) {        // :613-619
+                if (RING ? (xr * xr + yr * yr >= sc.ring_r2 || fabsf(pos.z) >= sc.half)
+                            : (xr >= sc.dod || fabsf(yr) >= sc.half || fabsf(pos.z) >= sc.half)) {        // :613-619
                     if (RECORD) { P.fates[WORD(G_REC, 0)] = 4u | ((uint32_t)nint << 28); P.fate_e[WORD(G_REC, 0)] = pos.w; }
                     st = (st & clr) | (P_REFILL << (4 * j));
                     break;
@@ -502,6 +507,30 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 const float2 cs = __ldg(sc.view_cs + view);
                 const float xr = pos.x * cs.x + pos.y * cs.y, yr = -pos.x * cs.y + pos.y * cs.x;      // rotate by -beta
                 const float dxr = dir.x * cs.x + dir.y * cs.y, dyr = -dir.x * cs.y + dir.y * cs.x;
+                if (RING) {
+                    // the flight leaves through the cylinder x^2 + y^2 = R^2 (circle3_2.cpp:243-252, a ring of angular bins)
+                    const float qa = dxr * dxr + dyr * dyr, qb = xr * dxr + yr * dyr, qc = xr * xr + yr * yr - sc.ring_r2;
+                    const float disc = qb * qb - qa * qc;
+                    const float xf = fmaf(1000.f, dxr, xr), yf = fmaf(1000.f, dyr, yr);
+                    if (qa > 0.f && disc >= 0.f && xf * xf + yf * yf >= sc.ring_r2) {
+                        // the root where the line LEAVES the cylinder; negative when the last Woodcock step ended beyond the
+                        // ring (the history came from inside: that crossing is the hit either way)
+                        const float t = __fdividef(sqrtf(disc) - qb, qa);
+                        const float zd = fmaf(t, dir.z, pos.z);
+                        if (fabsf(zd) <= sc.half) {
+                            float phi = atan2f(fmaf(t, dyr, yr), fmaf(t, dxr, xr));
+                            if (phi < 0.f) phi += 6.2831853071795865f;
+                            const int by = min((int)(phi * sc.ring_kphi), sc.det_ny - 1), bx = (int)((sc.half - zd) * sc.inv_pixel);
+                            if (by >= 0 && bx >= 0 && bx < sc.det_nx) {
+                                const uint32_t bin = (uint32_t)(by * sc.det_nx + bx);
+                                atomicAdd(P.image5 + (size_t)view * npix + bin, sc.eid ? (int)(pos.w * (float)MONTE_MC_EID_SCALE + 0.5f) : 1);
+                                c_scat++;
+                                e_scat += (unsigned long long)(pos.w * 1024.f + 0.5f);
+                                fate = 2u | (bin << 8) | ((uint32_t)nint << 28);
+                            }
+                        }
+                    }
+                } else
                 if (dxr > 0.f) {
                     const float t = __fdividef(sc.dod - xr, dxr);
                     const float yd = fmaf(t, dyr, yr), zd = fmaf(t, dir.z, pos.z);
@@ -567,15 +596,24 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 if (lo < sc.n_bins) E = (float)(lo + 1) * sc.bin_keV;
             }
             kE = min(max((int)(E + 0.5f), 0), TAB_ROWS - 1);
-            const float yl = sc.half - sc.pixel * ((float)pi + uy);
             const float zl = sc.half - sc.pixel * ((float)pj + uz);
-            const float rn = rsqrtf(sc.dsd * sc.dsd + yl * yl + zl * zl);
             const float2 cs = __ldg(sc.view_cs + view);
-            const float dxr = sc.dsd * rn, dyr = yl * rn;
+            float dxr, dyr, rn, sx, sy;
+            if (RING) {                                       // aim from the origin at bin (pi, pj) of the ring
+                float sph, cph;
+                sincosf(sc.ring_dphi * ((float)pi + uy), &sph, &cph);
+                rn = rsqrtf(sc.ring_r2 + zl * zl);
+                dxr = sc.ring_r * cph * rn; dyr = sc.ring_r * sph * rn;
+                sx = 0.f; sy = 0.f;
+            } else {
+                const float yl = sc.half - sc.pixel * ((float)pi + uy);
+                rn = rsqrtf(sc.dsd * sc.dsd + yl * yl + zl * zl);
+                dxr = sc.dsd * rn; dyr = yl * rn;
+                sx = -sc.dso * cs.x; sy = -sc.dso * cs.y;
+            }
             dx = dxr * cs.x - dyr * cs.y;
             dy = dxr * cs.y + dyr * cs.x;
             dz = zl * rn;
-            const float sx = -sc.dso * cs.x, sy = -sc.dso * cs.y;
             // analytic flight to the clip box: branch-free slab method (a zero direction component gives
             // +-inf bounds, which fminf/fmaxf handle; CUDA's fminf/fmaxf drop a NaN operand)
             float t0 = 0.f, t1 = 1e30f;
@@ -769,6 +807,14 @@ static int check_mc(const monte_mc_geom *g, const monte_mc_volume *vol, const mo
     MONTE_ARG(g->max_scatter >= 0 && g->max_scatter <= 15, "mc: max_scatter must be 0..15");
     MONTE_ARG(g->detector_mode == MONTE_MC_DETECTOR_COUNTING || g->detector_mode == MONTE_MC_DETECTOR_ENERGY,
               "mc: unknown detector_mode %d", g->detector_mode);
+    MONTE_ARG(g->detector_shape == MONTE_MC_DETECTOR_FLAT || g->detector_shape == MONTE_MC_DETECTOR_RING,
+              "mc: unknown detector_shape %d", g->detector_shape);
+    if (g->detector_shape == MONTE_MC_DETECTOR_RING) {
+        MONTE_ARG(g->ring_radius > 0, "mc: detector_shape RING needs ring_radius > 0 (got %g)", g->ring_radius);
+        const double rx = fmax(fabs(vol->clip_lo[0]), fabs(vol->clip_hi[0])), ry = fmax(fabs(vol->clip_lo[1]), fabs(vol->clip_hi[1]));
+        MONTE_ARG(sqrt(rx * rx + ry * ry) < g->ring_radius, "mc: the clip box must lie inside the detector ring (corner at %g cm, ring_radius %g)",
+                  sqrt(rx * rx + ry * ry), g->ring_radius);
+    }
     MONTE_ARG(vol->nx > 0 && vol->ny > 0 && vol->nz > 0 && vol->pitch > 0, "mc: bad volume");
     MONTE_ARG((uint64_t)vol->nx * vol->ny * vol->nz < (1ull << 32), "mc: label volume has 2^32 voxels or more");
     MONTE_ARG(vol->tracking_mode >= MONTE_MC_TRACK_GLOBAL && vol->tracking_mode <= MONTE_MC_TRACK_DIRECTIONAL,
@@ -1066,6 +1112,9 @@ static int scene_upload(monte_mc_scene *s, const monte_mc_geom *g, const monte_m
     d.dso = (float)g->dso; d.dod = (float)g->dod; d.dsd = (float)(g->dso + g->dod);
     d.source_mode = g->source_mode; d.max_scatter = g->max_scatter;
     d.eid = g->detector_mode == MONTE_MC_DETECTOR_ENERGY ? 1 : 0;
+    d.ring = g->detector_shape == MONTE_MC_DETECTOR_RING ? 1 : 0;
+    d.ring_r = (float)g->ring_radius; d.ring_r2 = d.ring_r * d.ring_r;
+    d.ring_dphi = (float)(2.0 * M_PI / g->ny); d.ring_kphi = (float)(g->ny / (2.0 * M_PI));
     if (!s->d_work) MONTE_CUDA(cudaMalloc(&s->d_work, MC_WORK_RING * sizeof(unsigned long long)));
     s->smem = (size_t)nm * TAB_ROWS * sizeof(float4) + (TAB_ROWS + 3 + d.n_bins + 1) * sizeof(float);
     s->h2d_bytes = (labels_resident || part_hi <= part_lo ? 0 : part_hi - part_lo) + tab_bytes + inv_bytes + cdf_bytes + ray_bytes + clear_bytes + vcs_bytes;
@@ -1160,7 +1209,7 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
         const float rx = fmaxf(fabsf(d.clip_lo[0]), fabsf(d.clip_hi[0])), ry = fmaxf(fabsf(d.clip_lo[1]), fabsf(d.clip_hi[1]));
         const float rz = fmaxf(fabsf(d.clip_lo[2]), fabsf(d.clip_hi[2]));
         const float rxy = sqrtf(rx * rx + ry * ry) * 1.0001f;
-        L.collide_check = (rxy < d.dod && rxy < d.half && rz < d.half) ? 0u : 1u;
+        L.collide_check = (d.ring ? (rxy < d.ring_r && rz < d.half) : (rxy < d.dod && rxy < d.half && rz < d.half)) ? 0u : 1u;
         L.n_vox_m1 = (uint32_t)((size_t)d.nx * d.ny * d.nz - 1);
     }
     if (L.total == 0) return MONTE_OK;
@@ -1175,7 +1224,9 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     const int rec = d_fates ? 1 : 0;
     const bool rayleigh = s->ray_n > 0;      // form-factor deflection of coherent events: its own instantiation (K = 5)
     const bool clear = s->heavy >= 0;        // two-level majorant: its own instantiations too
-    const int which = rayleigh || clear ? 35 : which_env;
+    const bool ring = s->dev.ring != 0;      // ring detector: its own instantiations (reference tracking loop and coherent event only)
+    MONTE_ARG(!ring || (!rayleigh && !clear), "mc: detector_shape RING is not available together with coherent_mode FORMFACTOR or a clearance tracking mode");
+    const int which = rayleigh || clear || ring ? 35 : which_env;
     const int K = which >= 31 && which <= 36 ? which - 30 : (which == 44 ? 4 : (which == 43 ? 3 : 5));
     const size_t slot_bytes = (size_t)K * 32 * mc_slot_groups(rec != 0) * sizeof(uint4) * (MC_THREADS / 32) +
                               (MC_THREADS / 32) * 3 * sizeof(uint4);                      // + the per-warp source-ray cache
@@ -1186,7 +1237,9 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     L.off_slots = L.off_invlo + (clear ? 2u * (TAB_ROWS + 3) * (uint32_t)sizeof(float) : 0u);
     const size_t smem = (size_t)L.off_slots + slot_bytes;
     const void *fn = nullptr;
-    switch (rayleigh || clear ? 200 + rec + (clear ? 2 : 0) + (rayleigh && clear ? 2 : 0) : which * 2 + rec) {
+    switch (ring ? 210 + rec : rayleigh || clear ? 200 + rec + (clear ? 2 : 0) + (rayleigh && clear ? 2 : 0) : which * 2 + rec) {
+        case 210: fn = (const void *)mc_transport_kernel_v3<false, 5, 3, 2, false, false, true>; break;
+        case 211: fn = (const void *)mc_transport_kernel_v3<true, 5, 3, 2, false, false, true>; break;
         case 200: fn = (const void *)mc_transport_kernel_v3<false, 5, 3, 2, true>; break;
         case 201: fn = (const void *)mc_transport_kernel_v3<true, 5, 3, 2, true>; break;
         case 202: fn = (const void *)mc_transport_kernel_v3<false, 5, 3, 2, false, true>; break;
@@ -1218,8 +1271,8 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     at_shutdown([] { attr_pd.get() = Attr(); });
     int *occ = attr_pd.get().occ;
     size_t *smem_set = attr_pd.get().smem_set, *smem_occ = attr_pd.get().smem_occ;
-    // 94, 95 (Rayleigh), 0..3 (clearance, clearance + Rayleigh): no `which` maps there (31..46 -> 62..93)
-    const int slot_id = clear ? rec + (rayleigh ? 2 : 0) : rayleigh ? 94 + rec : (which * 2 + rec) % 96;
+    // 94, 95 (Rayleigh), 0..3 (clearance, clearance + Rayleigh), 4, 5 (ring detector): no `which` maps there (31..46 -> 62..93)
+    const int slot_id = ring ? 4 + rec : clear ? rec + (rayleigh ? 2 : 0) : rayleigh ? 94 + rec : (which * 2 + rec) % 96;
     int &oc = occ[slot_id];
     MONTE_ARG(smem <= 227 * 1024, "mc: %zu bytes of shared memory needed (> 227 KB)", smem);
     if (smem > smem_set[slot_id]) {

@@ -133,6 +133,16 @@ def mc_geom(n_det, pixel, n_views=360, source_mode=_abi.SOURCE_PENCIL, max_scatt
     return g
 
 
+def ring_geom(n_phi, n_axial, pixel, radius, n_views=1, source_mode=_abi.SOURCE_PENCIL, max_scatter=5):
+    """monte_mc_geom with a ring detector (monte_cpp/circle3_2.cpp): source at the origin, n_phi angular bins
+    around the z axis at `radius`, n_axial bins of height `pixel` centred on the central plane"""
+    g = mc_geom(0, pixel, n_views=n_views, source_mode=source_mode, max_scatter=max_scatter, ny=n_phi, nx=n_axial)
+    g.half = 0.5 * n_axial * pixel
+    g.detector_shape = _abi.DETECTOR_RING
+    g.ring_radius = radius
+    return g
+
+
 def mono_spectrum(keV=140.0):
     s = McSpectrum()
     s.n_bins, s.bin_keV, s.mono_keV = 0, 0.5, keV

@@ -379,6 +379,29 @@ static double sample_energy(const scene_t *S, double u) {
 
 /* one history.  image0/image5 are [ny][nx] of the current view.  fate (nullable) receives the
  * record described in include/monte_gpu.h (monte_gpu_simulate_fates).                           */
+/* Ring detector (monte_gpu.h MONTE_MC_DETECTOR_RING; the geometry of monte_cpp/circle3_2.cpp:162,243-252 generalised to a
+ * cylinder about the z axis): where the flight from (xp,yp,zp) through the far point (x,y,z) -- both rotated by -beta --
+ * leaves the cylinder of radius ring_radius.  1 and the bin (angle, height) if it does within |z| <= half. */
+static int det_bin(double d, double inv_pixel, int n);
+static int ring_hit(const monte_mc_geom *g, double xp, double yp, double zp, double x, double y, double z, int *ry, int *rx) {
+    const double dx = x - xp, dy = y - yp, dz = z - zp;
+    const double R2 = g->ring_radius * g->ring_radius;
+    const double a = dx * dx + dy * dy, b = xp * dx + yp * dy, c = xp * xp + yp * yp - R2;
+    if (!(a > 0) || x * x + y * y < R2) return 0;
+    const double disc = b * b - a * c;
+    if (disc < 0) return 0;
+    const double t = (sqrt(disc) - b) / a;
+    if (!(t > 0)) return 0;
+    const double zd = zp + t * dz;
+    if (fabs(zd) > g->half) return 0;
+    double phi = atan2(yp + t * dy, xp + t * dx);
+    if (phi < 0) phi += 2 * M_PI;
+    int by = (int)(phi * g->ny / (2 * M_PI));
+    if (by > g->ny - 1) by = g->ny - 1;
+    *ry = by; *rx = det_bin(zd, 1.0 / g->pixel, g->nx);
+    return 1;
+}
+
 static void history(const scene_t *S, rng_t *R, int view, int i, int j, uint64_t hid, int32_t *image0,
                     int32_t *image5, oracle_mc_result *res, uint32_t *fate, float *fate_e) {
     const monte_mc_geom *g = S->g;
@@ -420,6 +443,13 @@ static void history(const scene_t *S, rng_t *R, int view, int i, int j, uint64_t
     } else {                                   /* exact aim at (Dsd, yl, zl) */
         double n = sqrt(Dsd * Dsd + yl * yl + zl * zl);
         cos_theta_a = zl / n; sin_theta_a = sqrt(Dsd * Dsd + yl * yl) / n;
+    }
+    const int ring = g->detector_shape == MONTE_MC_DETECTOR_RING;
+    if (ring) {                                /* from the origin at bin (i, j) of the ring */
+        P.x = 0;
+        phia = 2 * M_PI * (i + u_jy) / g->ny + M_PI * num_p / 180.;
+        double n = sqrt(g->ring_radius * g->ring_radius + zl * zl);
+        cos_theta_a = zl / n; sin_theta_a = g->ring_radius / n;
     }
     sin_phi_a = sin(phia); cos_phi_a = cos(phia);
     const double sin_theta_a0 = sin_theta_a, cos_theta_a0 = cos_theta_a, sin_phi_a0 = sin_phi_a, cos_phi_a0 = cos_phi_a;
@@ -475,6 +505,10 @@ static void history(const scene_t *S, rng_t *R, int view, int i, int j, uint64_t
         double d_z = ((P.z - 0) / (x_r - (-g->dso))) * g->dod + g->dso * P.z / (x_r + g->dso);   /* .cu:571-572 */
         double d_y = ((y_r - 0) / (x_r - (-g->dso))) * g->dod + g->dso * y_r / (x_r + g->dso);
         int ry = det_bin(d_y, inv_pixel, g->ny), rx = det_bin(d_z, inv_pixel, g->nx);
+        if (ring) {                                /* the bin it was aimed at, by the same cylinder intersection as a scattered hit */
+            ry = i; rx = j;
+            if (!missed && !ring_hit(g, 0, 0, 0, x_r, y_r, P.z, &ry, &rx)) { ry = i; rx = j; }
+        }
         if (!(q & OQ_NO_PRIMARY_TALLY) && ry >= 0 && ry < g->ny && rx >= 0 && rx < g->nx) {
             TALLY(image0[ry * g->nx + rx]);
             TALLY(image5[ry * g->nx + rx]);
@@ -494,6 +528,8 @@ static void history(const scene_t *S, rng_t *R, int view, int i, int j, uint64_t
                 if (x_rotate_c >= g->dod || fabs(y_rotate_c) >= g->half || fabs(P.z) > g->half) break;
             } else {
                 double x_rotate_c = P.x * cr - P.y * sr, y_rotate_c = P.x * sr + P.y * cr;
+                if (ring) { if (P.x * P.x + P.y * P.y >= g->ring_radius * g->ring_radius || fabs(P.z) >= g->half) break; }
+                else
                 if (x_rotate_c >= g->dod || fabs(y_rotate_c) >= g->half || fabs(P.z) >= g->half) break;
             }
             /* ---- material at the site, CBCT_real325im.cu:624-646 ---- */
@@ -552,8 +588,11 @@ static void history(const scene_t *S, rng_t *R, int view, int i, int j, uint64_t
                     double xp_rot = P.x_p * cr - P.y_p * sr, yp_rot = P.x_p * sr + P.y_p * cr;
                     double d_z = ((P.z - P.z_p) / (x_rot - xp_rot)) * g->dod + (x_rot * P.z_p - xp_rot * P.z) / (x_rot - xp_rot);
                     double d_y = ((y_rot - yp_rot) / (x_rot - xp_rot)) * g->dod + (x_rot * yp_rot - xp_rot * y_rot) / (x_rot - xp_rot);
-                    if (x_rot >= g->dod && fabs(d_z) <= g->half && fabs(d_y) <= g->half) {
+                    int ring_ry = 0, ring_rx = 0;
+                    if (ring ? ring_hit(g, xp_rot, yp_rot, P.z_p, x_rot, y_rot, P.z, &ring_ry, &ring_rx)
+                             : (x_rot >= g->dod && fabs(d_z) <= g->half && fabs(d_y) <= g->half)) {
                         int ry = det_bin(d_y, inv_pixel, g->ny), rx = det_bin(d_z, inv_pixel, g->nx);
+                        if (ring) { ry = ring_ry; rx = ring_rx; }
                         if (ry >= 0 && ry < g->ny && rx >= 0 && rx < g->nx) {
                             TALLY(image5[ry * g->nx + rx]);
                             res->scatter_detected++;
@@ -626,8 +665,11 @@ static void history(const scene_t *S, rng_t *R, int view, int i, int j, uint64_t
                     double x_p_rotate = P.x_p * cr - P.y_p * sr, y_p_rotate = P.x_p * sr + P.y_p * cr;
                     double d_z = ((P.z - P.z_p) / (x_rotate - x_p_rotate)) * g->dod + (x_rotate * P.z_p - x_p_rotate * P.z) / (x_rotate - x_p_rotate);
                     double d_y = ((y_rotate - y_p_rotate) / (x_rotate - x_p_rotate)) * g->dod + (x_rotate * y_p_rotate - x_p_rotate * y_rotate) / (x_rotate - x_p_rotate);
-                    if (x_rotate >= g->dod && fabs(d_z) <= g->half && fabs(d_y) <= g->half) {
+                    int ring_ry = 0, ring_rx = 0;
+                    if (ring ? ring_hit(g, x_p_rotate, y_p_rotate, P.z_p, x_rotate, y_rotate, P.z, &ring_ry, &ring_rx)
+                             : (x_rotate >= g->dod && fabs(d_z) <= g->half && fabs(d_y) <= g->half)) {
                         int ry = det_bin(d_y, inv_pixel, g->ny), rx = det_bin(d_z, inv_pixel, g->nx);
+                        if (ring) { ry = ring_ry; rx = ring_rx; }
                         if (ry >= 0 && ry < g->ny && rx >= 0 && rx < g->nx) {
                             TALLY(image5[ry * g->nx + rx]);
                             res->scatter_detected++;

@@ -62,7 +62,7 @@ def main():
         src = open(os.path.join(ROOT, "monte_b200", "csrc", "mc.cu")).read().splitlines()
         lo = [i + 1 for i, t in enumerate(src) if "// ======== STEP" in t][0]
         hi = [i + 1 for i, t in enumerate(src) if "// ======== COLLIDE" in t][0] - 1
-        seq = kernel_sass(os.path.join(d, "mc.sm_100a.cubin"), "mc_transport_kernel_v3ILb0ELi5ELi3ELi2ELb0ELb0E")
+        seq = kernel_sass(os.path.join(d, "mc.sm_100a.cubin"), "mc_transport_kernel_v3ILb0ELi5ELi3ELi2ELb0ELb0ELb0E")
         # the Philox rounds and u01() are inlined from lines above the kernel: take the contiguous address range
         n, ops = excerpt(seq, lo, hi, "mc_transport_kernel_v3<false,5,3,2>: the STEP phase, mc.cu:%d-%d -- one Woodcock step of TWO parked histories of the lane" % (lo, hi),
                          "slot select, 3 x LDS.128 per slot, Philox2x32-10 (IMAD.WIDE.U32 + LOP3 per round, round keys from the constant bank), lg2, "

@@ -191,6 +191,11 @@ def test_emu_shutdown_and_reinit_rebuild_every_cache(monte_emu, oracle):
     assert np.array_equal(f1, f2) and np.array_equal(v1, v2) and np.array_equal(a0, b0) and np.array_equal(a5, b5)
 
 
+@pytest.mark.parametrize("textbook", [False, True])
+def test_emu_two_d_fan_beam_is_the_nv1_case_of_the_same_kernels(monte_emu, oracle, textbook):
+    G.test_two_d_fan_beam_is_the_nv1_case_of_the_same_kernels(monte_emu, oracle, textbook)
+
+
 def test_emu_smoke_path(monte_emu):
     """__graft_entry__.smoke()'s own checks (FDK, FFT filter, MC coupled with the oracle, projector, the optional
     transport modes), run on the emulated library; leaves the binding initialised for the tests that follow"""

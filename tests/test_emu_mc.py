@@ -44,6 +44,14 @@ def test_emu_all_air_volume_under_present_majorant(monte_emu):
     G.test_all_air_volume_under_present_majorant(monte_emu)
 
 
+def test_emu_ring_detector_primary_transmission_kat(monte_emu, oracle):
+    G.test_ring_detector_primary_transmission_kat(monte_emu, oracle)
+
+
+def test_emu_ring_detector_coupled_with_oracle(monte_emu, oracle):
+    G.test_ring_detector_coupled_with_oracle(monte_emu, oracle)
+
+
 def test_emu_edge_cases(monte_emu):
     G.test_edge_cases(monte_emu)
 

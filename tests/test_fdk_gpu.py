@@ -303,3 +303,28 @@ print("ok")
     env = dict(os.environ, MONTE_BP_VCHUNK="4")
     out = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("textbook", [False, True])
+def test_two_d_fan_beam_is_the_nv1_case_of_the_same_kernels(monte, oracle, textbook):
+    """a 2-D fan-beam reconstruction through the cone-beam filter and backprojector (nv = 1, one slice in
+    the central plane): against the oracle on random data, and -- Feldkamp weights -- a disc's attenuation coefficient
+    recovered from its analytic fan-beam line integrals"""
+    g = _abi.fan_beam_2d_geom(90, 96, 48, textbook=textbook)
+    proj = rand(5, (90, 96, 1))
+    f, vol, _, st = monte.fdk(g, proj)
+    fo, vo, _ = oracle.fdk(g, proj)
+    assert vol.shape == (1, 48, 48) and np.abs(vo).max() > 0
+    assert np.abs(f - fo).max() <= REL * np.abs(fo).max() and np.abs(vol - vo).max() <= REL * np.abs(vo).max()
+    if not textbook:
+        return
+    g = _abi.fan_beam_2d_geom(360, 192, 64)
+    r, mu = 8.0, 0.2
+    u = g.half_u - g.du * (np.arange(g.nu) + 0.0)              # detector coordinate of column iu (bp3d20.cpp:40: 16.25 - pitch * zeta)
+    t = g.dso * u / np.sqrt(u * u + g.dsd * g.dsd)             # distance of the ray from the rotation centre
+    chord = 2.0 * mu * np.sqrt(np.maximum(r * r - t * t, 0.0))
+    proj = np.broadcast_to(chord.astype(np.float32)[None, :, None], (360, g.nu, 1)).copy()
+    _, vol, _, _ = monte.fdk(g, proj, want_filtered=False)
+    c = vol[0, 24:40, 24:40]
+    assert abs(c.mean() - mu) < 0.02 * mu, c.mean()
+    assert abs(vol[0, 32, 7]) < 0.05 * mu                       # 10 cm from the centre: outside the disc, inside the field of view

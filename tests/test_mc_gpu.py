@@ -402,3 +402,65 @@ def test_all_air_volume_under_present_majorant(monte):
     vol.majorant_mode = 9
     with pytest.raises(Exception, match="majorant_mode"):
         monte.simulate(g, vol, lab, scenes.make_xs(), scenes.mono_spectrum(140.0), 7, 1)
+
+
+def test_ring_detector_primary_transmission_kat(monte, oracle):
+    """SURVEY 8f-4 / 8c KAT: the reference's 2-D geometry (monte_cpp/circle3_2.cpp: source at the centre of an r = 10 cm
+    water disc, ring of angular bins).  Every primary crosses 10 cm of water: transmission exp(-0.1538092 * 10) =
+    0.214791 at 140 keV in every bin; history by history against the oracle."""
+    lab = scenes.cylinder_phantom(41, 0.5, radius=10.0, half_len=10.0, rods=False)
+    vol = scenes.volume_for(lab, 0.5)
+    g = scenes.ring_geom(36, 1, 1.0, 15.0)
+    xs = scenes.make_xs(("h2o",))
+    per, seed = 3000, 3
+    im0, im5, st = monte.simulate(g, vol, lab, xs, scenes.mono_spectrum(140.0), per, seed)
+    assert im0.shape == (1, 36, 1) and st["histories"] == 36 * per
+    p = math.exp(-0.1538092 * 10.0)
+    # the voxelised disc is 10 cm +- half a voxel along a ray: compare with the deterministic path length through the labels
+    sig = math.sqrt(per * p * (1 - p))
+    assert np.abs(im0[0, :, 0] - per * p).max() < 5.0 * sig + 0.1538 * 0.5 * per * p, im0[0, :, 0]
+    assert abs(im0.sum() / (36.0 * per) - p) < 0.01
+    assert (im5 >= im0).all() and st["scatter_detected"] > 0 and im5.sum() == st["primaries"] + st["scatter_detected"]
+    sc = monte.Scene(g, vol, lab, xs, scenes.mono_spectrum(140.0))
+    f_gpu, e_gpu = sc.fates(0, 200, seed)
+    sc.close()
+    _, _, res, f_cpu, e_cpu = oracle.mc_run(g, vol, lab, oracle.tables_from_xs(xs), scenes.mono_spectrum(140.0),
+                                            oracle.mc_opts(oracle.RNG_PHILOX, seed=seed), 200, want_fates=True)
+    same = f_gpu == f_cpu
+    assert same.mean() > 0.999, same.mean()
+    assert np.allclose(e_gpu[same], e_cpu[same], rtol=2e-5)
+
+
+def test_ring_detector_coupled_with_oracle(monte, oracle):
+    """ring detector with axial bins, calcium rods, jittered aim inside the bins, two view angles (the bins rotate with the
+    view): fates, tallies and counters against the oracle on the same variates; argument errors"""
+    lab = scenes.cylinder_phantom(33, 1.0)
+    vol = scenes.volume_for(lab, 1.0)
+    g = scenes.ring_geom(24, 5, 4.0, 20.0, n_views=2, source_mode=_abi.SOURCE_CONE)
+    g.angle0_deg, g.angle_step_deg = 10.0, 37.0
+    xs = scenes.make_xs()
+    spec = scenes.mono_spectrum(60.0)
+    per, seed = 60, 9
+    for view in (0, 1):
+        sc = monte.Scene(g, vol, lab, xs, spec)
+        f_gpu, e_gpu = sc.fates(view, per, seed)
+        sc.close()
+        _, _, res, f_cpu, e_cpu = oracle.mc_run(g, vol, lab, oracle.tables_from_xs(xs), spec, oracle.mc_opts(oracle.RNG_PHILOX, seed=seed), per,
+                                                views=(view, view + 1), want_fates=True)
+        same = f_gpu == f_cpu
+        assert same.mean() > 0.999, (view, same.mean())
+        for k in (1, 2, 3, 4):
+            assert ((f_cpu & 0xFF) == k).any(), k
+    im0, im5, st = monte.simulate(g, vol, lab, xs, spec, per, seed)
+    o0, o5, res, _, _ = oracle.mc_run(g, vol, lab, oracle.tables_from_xs(xs), spec, oracle.mc_opts(oracle.RNG_PHILOX, seed=seed), per)
+    n = st["histories"]
+    assert np.abs(im0.astype(int) - o0).sum() <= 0.001 * n + 2 and np.abs(im5.astype(int) - o5).sum() <= 0.001 * n + 2
+    for k in ("primaries", "scatter_detected", "absorbed", "interactions", "woodcock_steps"):
+        assert abs(st[k] - res[k]) <= 0.001 * max(res[k], 1) + 5, (k, st[k], res[k])
+    g.ring_radius = 12.0                                              # the clip box (corner at 14.1 cm) pokes through the ring
+    with pytest.raises(Exception, match="inside the detector ring"):
+        monte.simulate(g, vol, lab, xs, spec, per, seed)
+    g.ring_radius = 20.0
+    vol.tracking_mode, vol.clearance_cell_log2 = _abi.TRACK_CLEARANCE, 1
+    with pytest.raises(Exception, match="RING is not available"):
+        monte.simulate(g, vol, lab, xs, spec, per, seed)
