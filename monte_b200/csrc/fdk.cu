@@ -1635,7 +1635,8 @@ int monte_gpu_fdk(const monte_fdk_geom *g, const float *map, float *filtered, fl
     // Views travel in chunks: upload k | filter k | (pad k-1, which needs the first row of chunk k) |
     // backproject k-1 into the whole volume, continuing the stored partial sums.  The last chunk is
     // backprojected slab by slab so that finished slabs go home while the next one is computed.
-    const int n_up = g->n_views >= 64 ? 8 : 1;
+    int n_up = g->n_views >= 64 ? 8 : 1;
+    { const char *e = getenv("MONTE_FDK_CHUNKS"); if (e && atoi(e) >= 1 && atoi(e) <= MAXC && atoi(e) <= g->n_views) n_up = atoi(e); }   // (A/B knob)
     const int rows = g->n_views * g->nv, pitch = (int)filtered_pitch(g);
     const int n_slab = g->nz >= 128 ? 4 : 1;
     int prev0 = 0, prev1 = 0;
