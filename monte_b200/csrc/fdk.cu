@@ -1633,50 +1633,55 @@ int monte_gpu_fdk(const monte_fdk_geom *g, const float *map, float *filtered, fl
     MONTE_CUDA(cudaEventRecord(ev_t[0], st));                       // start of everything
     MONTE_CUDA(cudaStreamWaitEvent(cp, ev_t[0], 0));
     // Views travel in chunks: upload k | filter k | (pad k-1, which needs the first row of chunk k) |
-    // backproject k-1 into the whole volume, continuing the stored partial sums.  The last chunk is
-    // backprojected slab by slab so that finished slabs go home while the next one is computed.
-    int n_up = g->n_views >= 64 ? 8 : 1;
+    // backproject k-1 into the whole volume, continuing the stored partial sums.  The last `m_tail` chunks are
+    // backprojected slab by slab (slab-major: all of those chunks into slab 0, then slab 1, ...) so that a finished slab
+    // goes home while the next one is computed: the tail chunks together must outlast the download of the volume.
+    int n_up = g->n_views >= 128 ? 16 : (g->n_views >= 64 ? 8 : 1);
     { const char *e = getenv("MONTE_FDK_CHUNKS"); if (e && atoi(e) >= 1 && atoi(e) <= MAXC && atoi(e) <= g->n_views) n_up = atoi(e); }   // (A/B knob)
     const int rows = g->n_views * g->nv, pitch = (int)filtered_pitch(g);
     const int n_slab = g->nz >= 128 ? 4 : 1;
-    int prev0 = 0, prev1 = 0;
-    for (int k = 0; k <= n_up; k++) {
-        int v0 = 0, v1 = 0;
-        if (k < n_up) {
-            v0 = (int)((long long)g->n_views * k / n_up); v1 = (int)((long long)g->n_views * (k + 1) / n_up);
-            MONTE_CUDA(cudaMemcpyAsync(d_map + v0 * per_view, map + v0 * per_view, (size_t)(v1 - v0) * per_view * sizeof(float),
-                                       cudaMemcpyHostToDevice, cp));
-            MONTE_CUDA(cudaEventRecord(ev_up[k], cp));
-            MONTE_CUDA(cudaStreamWaitEvent(st, ev_up[k], 0));
-            if (int rc = monte_gpu_fdk_filter_dev(g, d_map, v0, v1, d_filt, st)) return rc;
+    int m_tail = n_slab > 1 ? (n_up + 4) / 5 : 1;                  // ~20 % of the views
+    { const char *e = getenv("MONTE_FDK_TAIL"); if (e && atoi(e) >= 1) m_tail = atoi(e); }
+    if (m_tail > n_up) m_tail = n_up;
+    auto chunk_lo = [&](int k) { return (int)((long long)g->n_views * k / n_up); };
+    auto pad_chunk = [&](int k) -> int {                           // chunk k = views [chunk_lo(k), chunk_lo(k + 1)); needs chunk k + 1 filtered
+        // the last view of the chunk reads up to two rows into the next chunk (already filtered):
+        // their duplicated column must be valid too
+        const int r0 = chunk_lo(k) * g->nv, r1 = k == n_up - 1 ? rows + 2 : min(chunk_lo(k + 1) * g->nv + 2, rows + 2);
+        fdk_pad_kernel MONTE_CFG(ceil_div(r1 - r0, 256), 256, 0, st)(d_filt, rows, g->nu, pitch, r0, r1);
+        MONTE_CUDA(cudaGetLastError());
+        launches++;
+        return MONTE_OK;
+    };
+    for (int k = 0; k < n_up; k++) {
+        const int v0 = chunk_lo(k), v1 = chunk_lo(k + 1);
+        MONTE_CUDA(cudaMemcpyAsync(d_map + v0 * per_view, map + v0 * per_view, (size_t)(v1 - v0) * per_view * sizeof(float),
+                                   cudaMemcpyHostToDevice, cp));
+        MONTE_CUDA(cudaEventRecord(ev_up[k], cp));
+        MONTE_CUDA(cudaStreamWaitEvent(st, ev_up[k], 0));
+        if (int rc = monte_gpu_fdk_filter_dev(g, d_map, v0, v1, d_filt, st)) return rc;
+        launches++;
+        if (k > 0 && k - 1 < n_up - m_tail) {                       // chunk k-1 into the whole volume
+            if (int rc = pad_chunk(k - 1)) return rc;
+            if (int rc = backproject_views(g, d_filt, 0, g->nz, d_vol, st, chunk_lo(k - 1), chunk_lo(k), k - 1 > 0)) return rc;
             launches++;
         }
-        if (k > 0) {                                                // chunk k-1 = views [prev0, prev1)
-            const bool last = k == n_up;
-            // the last view of the chunk reads up to two rows into the next chunk (already filtered):
-            // their duplicated column must be valid too
-            const int r0 = prev0 * g->nv, r1 = last ? rows + 2 : min(prev1 * g->nv + 2, rows + 2);
-            fdk_pad_kernel MONTE_CFG(ceil_div(r1 - r0, 256), 256, 0, st)(d_filt, rows, g->nu, pitch, r0, r1);
-            MONTE_CUDA(cudaGetLastError());
+    }
+    for (int k = n_up - m_tail; k < n_up; k++) if (int rc = pad_chunk(k)) return rc;
+    MONTE_CUDA(cudaEventRecord(ev_t[1], st));                       // everything filtered
+    for (int q = 0; q < n_slab; q++) {
+        int z0 = (int)((long long)g->nz * q / n_slab), z1 = (int)((long long)g->nz * (q + 1) / n_slab);
+        z0 = q == 0 ? 0 : (z0 / 32) * 32;                           // slabs on z-block boundaries
+        z1 = q == n_slab - 1 ? g->nz : (z1 / 32) * 32;
+        if (z1 <= z0) continue;
+        for (int k = n_up - m_tail; k < n_up; k++) {
+            if (int rc = backproject_views(g, d_filt, z0, z1, d_vol + z0 * slice, st, chunk_lo(k), chunk_lo(k + 1), k > 0)) return rc;
             launches++;
-            if (last) MONTE_CUDA(cudaEventRecord(ev_t[1], st));     // everything filtered
-            const int ns = last ? n_slab : 1;
-            for (int q = 0; q < ns; q++) {
-                int z0 = (int)((long long)g->nz * q / ns), z1 = (int)((long long)g->nz * (q + 1) / ns);
-                z0 = q == 0 ? 0 : (z0 / 32) * 32;                   // slabs on z-block boundaries
-                z1 = q == ns - 1 ? g->nz : (z1 / 32) * 32;
-                if (z1 <= z0) continue;
-                if (int rc = backproject_views(g, d_filt, z0, z1, d_vol + z0 * slice, st, prev0, prev1, prev0 > 0)) return rc;
-                launches++;
-                if (last) {
-                    MONTE_CUDA(cudaEventRecord(ev_slab[q], st));
-                    MONTE_CUDA(cudaStreamWaitEvent(cp, ev_slab[q], 0));
-                    MONTE_CUDA(cudaMemcpyAsync(vol_xy + z0 * slice, d_vol + z0 * slice, (size_t)(z1 - z0) * slice * sizeof(float),
-                                               cudaMemcpyDeviceToHost, cp));
-                }
-            }
         }
-        prev0 = v0; prev1 = v1;
+        MONTE_CUDA(cudaEventRecord(ev_slab[q], st));
+        MONTE_CUDA(cudaStreamWaitEvent(cp, ev_slab[q], 0));
+        MONTE_CUDA(cudaMemcpyAsync(vol_xy + z0 * slice, d_vol + z0 * slice, (size_t)(z1 - z0) * slice * sizeof(float),
+                                   cudaMemcpyDeviceToHost, cp));
     }
     MONTE_CUDA(cudaEventRecord(ev_t[2], st));                       // backprojected
     if (filtered) {   // d_map is free now: reuse it for the dense copy of the filtered projections

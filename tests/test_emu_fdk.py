@@ -196,6 +196,11 @@ def test_emu_two_d_fan_beam_is_the_nv1_case_of_the_same_kernels(monte_emu, oracl
     G.test_two_d_fan_beam_is_the_nv1_case_of_the_same_kernels(monte_emu, oracle, textbook)
 
 
+@pytest.mark.parametrize("chunks,tail", [(16, 3), (8, 8), (5, 1)])
+def test_emu_host_pipeline_chunking_is_bit_identical(monte_emu, chunks, tail):
+    G.test_host_pipeline_chunking_is_bit_identical(monte_emu, chunks, tail)
+
+
 def test_emu_smoke_path(monte_emu):
     """__graft_entry__.smoke()'s own checks (FDK, FFT filter, MC coupled with the oracle, projector, the optional
     transport modes), run on the emulated library; leaves the binding initialised for the tests that follow"""

@@ -328,3 +328,27 @@ def test_two_d_fan_beam_is_the_nv1_case_of_the_same_kernels(monte, oracle, textb
     c = vol[0, 24:40, 24:40]
     assert abs(c.mean() - mu) < 0.02 * mu, c.mean()
     assert abs(vol[0, 32, 7]) < 0.05 * mu                       # 10 cm from the centre: outside the disc, inside the field of view
+
+
+@pytest.mark.parametrize("chunks,tail", [(16, 3), (8, 8), (5, 1), (1, 1)])
+def test_host_pipeline_chunking_is_bit_identical(monte, chunks, tail):
+    """monte_gpu_fdk uploads, filters and backprojects the views in chunks and finishes the last `tail` chunks slab by slab
+    while finished slabs go home: any chunking gives the bits of the device-resident stages"""
+    import os
+    g = _abi.generic_fdk_geom(41, 40, 36, 128)
+    g.s_begin, g.s_end, g.t_begin, g.t_end = 58, 70, 60, 66          # a thin column of the 128^3 volume (four z-slabs)
+    proj = rand(9, (41, 40, 36))
+    keep = {k: os.environ.get(k) for k in ("MONTE_FDK_CHUNKS", "MONTE_FDK_TAIL")}
+    try:
+        os.environ["MONTE_FDK_CHUNKS"], os.environ["MONTE_FDK_TAIL"] = "1", "1"
+        f0, v0, z0, _ = monte.fdk(g, proj, want_zy=True)
+        os.environ["MONTE_FDK_CHUNKS"], os.environ["MONTE_FDK_TAIL"] = str(chunks), str(tail)
+        f1, v1, z1, st = monte.fdk(g, proj, want_zy=True)
+    finally:
+        for k, v in keep.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert np.array_equal(f0, f1) and np.array_equal(v0, v1) and np.array_equal(z0, z1)
+    assert np.abs(v0).max() > 0 and not v0[:, :, :58].any()
