@@ -1511,32 +1511,39 @@ static int fdk_multi(const monte_fdk_geom *g, const float *map, float *filtered,
         if (rc) break;
         if (cudaEventRecord(d.filter_end, st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__);
     }
-    // ---- on every device: chunk by chunk, gather the band from the chunk's owner + backproject into the own slab
+    // ---- on every device: chunk by chunk, gather the band from the chunk's owner + backproject into the own slab.
+    // The launches are issued chunk-major (chunk 0 on every device, then chunk 1, ...): one host thread feeds all the
+    // devices, and device-major order would hand the last device its first launch only after ~5 ms of enqueueing.
+    bool first_bp[MAX_DEV];
+    int waited[MAX_DEV];                                            // chunks [0, waited] are known to the device's aux stream
+    for (int i = 0; i < nd; i++) { first_bp[i] = true; waited[i] = -1; }
+    for (int ch = 0; ch < C && rc == MONTE_OK; ch++) {
+        if (V[ch + 1] <= V[ch]) continue;
+        int need = ch + 1;                                          // ... up to the next chunk that holds a view
+        while (need < C - 1 && V[need + 1] <= V[need]) need++;
+        if (need > C - 1) need = C - 1;
+        if (g->nv < 8) need = C - 1;                                // (rows 0..3 of "the next view" then span several views)
+        for (int i = 0; i < nd && rc == MONTE_OK; i++) {
+            FdkMultiDev &d = dv[i];
+            if (d.z_hi <= d.z_lo) continue;
+            if ((rc = use_dev(i))) break;
+            cudaStream_t bp = ctx().aux_stream;
+            for (int w = waited[i] + 1; w <= need && rc == MONTE_OK; w++)   // (own chunks too: they are filtered on another stream)
+                if (cudaStreamWaitEvent(bp, ev_f[w], 0) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaStreamWaitEvent", __FILE__, __LINE__);
+            if (rc) break;
+            if (need > waited[i]) waited[i] = need;
+            if ((rc = backproject_views(g, nullptr, d.z_lo, d.z_hi, d.d_vol, bp, V[ch], V[ch + 1], !first_bp[i], &src))) break;
+            first_bp[i] = false;
+            launches += 2;
+        }
+    }
     for (int i = 0; i < nd && rc == MONTE_OK; i++) {
         FdkMultiDev &d = dv[i];
         if ((rc = use_dev(i))) break;
         Context &c = ctx();
         cudaStream_t bp = c.aux_stream, cp = c.copy_stream;
-        FdkDevState &ds = g_fdk_state.get();
         const int nz_i = d.z_hi - d.z_lo;
-        bool first = true;
-        int waited = -1;                                            // chunks [0, waited] are known to this stream
-        for (int ch = 0; ch < C && rc == MONTE_OK && nz_i > 0; ch++) {
-            if (V[ch + 1] <= V[ch]) continue;
-            int need = ch + 1;                                      // ... up to the next chunk that holds a view
-            while (need < C - 1 && V[need + 1] <= V[need]) need++;
-            if (need > C - 1) need = C - 1;
-            if (g->nv < 8) need = C - 1;                            // (rows 0..3 of "the next view" then span several views)
-            for (int w = waited + 1; w <= need && rc == MONTE_OK; w++)   // (own chunks too: they are filtered on another stream)
-                if (cudaStreamWaitEvent(bp, ev_f[w], 0) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaStreamWaitEvent", __FILE__, __LINE__);
-            if (rc) break;
-            if (need > waited) waited = need;
-            if ((rc = backproject_views(g, nullptr, d.z_lo, d.z_hi, d.d_vol, bp, V[ch], V[ch + 1], !first, &src))) break;
-            first = false;
-            launches += 2;
-        }
-        if (rc) break;
-        if (nz_i > 0 && first) {                                    // no view at all: the slab is zero
+        if (nz_i > 0 && first_bp[i]) {                              // no view at all: the slab is zero
             if (cudaMemsetAsync(d.d_vol, 0, (size_t)nz_i * slice * sizeof(float), bp) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "cudaMemsetAsync", __FILE__, __LINE__); break; }
         }
         if (cudaEventRecord(d.bp_end, bp) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__); break; }
@@ -1555,7 +1562,6 @@ static int fdk_multi(const monte_fdk_geom *g, const float *map, float *filtered,
                 cudaMemcpy2DAsync(vol_zy + d.z_lo, (size_t)g->nz * sizeof(float), d_zy, (size_t)nz_i * sizeof(float), (size_t)nz_i * sizeof(float),
                                   slice, cudaMemcpyDeviceToHost, bp) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "transposed slab", __FILE__, __LINE__);
         }
-        (void)ds;
     }
     // ---- the filtered maps, if wanted: every device sends its own chunks (dense copies made right after the filter)
     for (int i = 0; i < nd && rc == MONTE_OK && filtered; i++) {
