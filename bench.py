@@ -709,10 +709,35 @@ def fdk_sharded_setup(c, g, proj):
     for a, b in my_z:
         z_off[a] = o
         o += b - a
-    exchange = os.environ.get("MONTE_BENCH_FDK_EXCHANGE", "band")
+    exchange = os.environ.get("MONTE_BENCH_FDK_EXCHANGE", "peers" if ws > 1 else "band")
+    peers = None
+    for old in getattr(c, "peer_rows", []):                      # (an earlier set-up of this run: unmap before mapping anew)
+        c.barrier()
+        old.close()
+    c.peer_rows = []
+    if exchange == "peers":
+        try:
+            peers = mdist.PeerRows(api, filt, g.n_views)
+        except Exception as ex:                                   # (no CUDA IPC between these processes: the all_to_all form)
+            sys.stderr.write("bench: CUDA IPC set-up failed (%s); using the band all_to_all\n" % ex)
+            exchange = "band"
+        ok = torch.tensor([1 if exchange == "peers" else 0], device=dev)
+        c.dist.all_reduce(ok, op=c.dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            exchange = "band"
+            if peers is not None:
+                peers.close()
+                peers = None
+        if peers is not None:
+            c.peer_rows.append(peers)
 
     def sharded(src):
-        if exchange == "pipelined":
+        if exchange == "peers":
+            mdist.fdk_sharded_peers(lambda a, b: api.fdk_filter_dev(g, src, filt, a, b, pad=False),
+                                    lambda z0, z1, ptrs, ends: api.fdk_backproject_peers_dev(
+                                        g, ptrs, ends, slab[z_off[z0]:z_off[z0] + z1 - z0], z0, z1),
+                                    peers, g.n_views, z_ranges)
+        elif exchange == "pipelined":
             mdist.fdk_sharded_pipelined(lambda a, b: api.fdk_filter_dev(g, src, filt, a, b, pad=False),
                                         lambda a, b: api.fdk_pad_views_dev(g, filt, a, b),
                                         lambda z0, z1, a, b, cont: api.fdk_backproject_views_dev(
@@ -723,6 +748,7 @@ def fdk_sharded_setup(c, g, proj):
                                    lambda: api.fdk_pad_dev(g, filt),
                                    lambda z0, z1: api.fdk_backproject_dev(g, filt, slab[z_off[z0]:z_off[z0] + z1 - z0], z0, z1),
                                    lambda z0, z1: api.fdk_slab_rows(g, z0, z1), filt, g.n_views, g.nv, z_ranges)
+    sharded.peers = peers
     return sharded, filt, slab, my_z, z_off, z_ranges, n_my, exchange
 
 
@@ -759,7 +785,10 @@ def bench_fdk_c3(c):
     sharded(proj)                                   # (restores every row this rank's slabs read)
     e[1].record()
     for a, b in my_z:
-        api.fdk_backproject_dev(g, filt, slab[z_off[a]:z_off[a] + b - a], a, b)
+        if sharded.peers is not None:               # (the gather from the peers' rows is part of this rank's backprojection)
+            api.fdk_backproject_peers_dev(g, sharded.peers.ptrs, sharded.peers.v_end, slab[z_off[a]:z_off[a] + b - a], a, b)
+        else:
+            api.fdk_backproject_dev(g, filt, slab[z_off[a]:z_off[a] + b - a], a, b)
     e[2].record()
     torch.cuda.synchronize()
     t_bp = e[1].elapsed_time(e[2])
@@ -889,6 +918,8 @@ def bench_fdk_c3(c):
                        "parallelism": "z-ranges of equal work x%d %s, filter by views, %s" % (
                            ws, [[list(z) for z in zr] for zr in z_ranges],
                            "view pieces broadcast in order and overlapped with the backprojection" if exchange == "pipelined"
+                           else "no collective: the backprojector's pair conversion loads the detector-row band each slab reads out of the "
+                                "peers' filtered rows (CUDA IPC, NVLink peer loads), two one-element all-reduces order the ranks" if exchange == "peers"
                            else "one all_to_all of the detector-row bands each slab reads") if ws > 1 else "single GPU",
                        "l2": "256 MiB fill between steps; projections (2.26 GB) exceed L2"},
             "breakdown_ms": {"filter_max_over_ranks": t_filter_max, "backproject_max_over_ranks": t_bp_max,

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MONTE_GPU_ABI_VERSION 6   /* 2: monte_mc_geom.detector_mode; 3: monte_mc_geom.coherent_mode (was
+#define MONTE_GPU_ABI_VERSION 7   /* 2: monte_mc_geom.detector_mode; 3: monte_mc_geom.coherent_mode (was
                                      `reserved`, 0 = unchanged behaviour), form-factor tables appended to monte_mc_xs,
                                      tracking_mode / clearance_cell_log2 appended to monte_mc_volume (0 = unchanged);
                                      4: monte_gpu_init binds 1..8 devices and the host-buffer calls monte_gpu_simulate* /
@@ -34,7 +34,8 @@ extern "C" {
                                      view_end < 0 (the range [0, 0) is now empty, as in the device forms);
                                      5: majorant_mode appended to monte_mc_volume (0 = unchanged); monte_hu_class,
                                      monte_hu_classes_default, monte_ctnum_segment (N-class HU segmentation);
-                                     6: detector_shape / ring_radius appended to monte_mc_geom (0 = the flat panel)   */
+                                     6: detector_shape / ring_radius appended to monte_mc_geom (0 = the flat panel);
+                                     7: monte_gpu_ipc_export / _open / _close, monte_gpu_fdk_backproject_peers_dev       */
 
 /* ---- status codes ------------------------------------------------------ */
 #define MONTE_OK            0
@@ -175,6 +176,23 @@ int monte_gpu_fdk_backproject_views_dev(const monte_fdk_geom *g, const float *d_
 /* pad fix-up restricted to the rows of views [view_lo, view_hi) (+ the two rows they reach into) */
 int monte_gpu_fdk_pad_views_dev(const monte_fdk_geom *g, float *d_filtered_padded,
                                 int view_lo, int view_hi, void *stream);
+/* One process per GPU: backproject all views into slices [z_lo, z_hi) with the filtered rows left where they
+ * were computed -- n_seg segments of views in ascending order, segment o = views [seg_v_end[o-1], seg_v_end[o]) whose
+ * padded-row layout (monte_gpu_fdk_filter_dev output, pad not needed) starts at seg_base[o] such that row R of the GLOBAL
+ * layout lives at seg_base[o] + R * pitch.  seg_base[o] may point into a peer process's memory opened with
+ * monte_gpu_ipc_open: the detector-row band the slab reads is loaded over NVLink while it is converted to the
+ * backprojector's pair layout (the kernel the in-library multi-device call uses), so the exchange needs no collective,
+ * no packing and no second copy.  The caller orders the processes (the peers' filters must have finished; nobody may
+ * overwrite its rows before every peer is done).  n_seg <= 32.                                                     */
+int monte_gpu_fdk_backproject_peers_dev(const monte_fdk_geom *g, int n_seg, const float *const *seg_base, const int *seg_v_end,
+                                        int z_lo, int z_hi, float *d_vol_slab, void *stream);
+/* CUDA IPC plumbing for such hosts.  export: a 64-byte handle of the device allocation that contains d_ptr and d_ptr's
+ * byte offset in it (send both to the peer process).  open: map that allocation into this process (peer access is
+ * enabled lazily) and return the address of the same byte.  close: unmap (pass the pointer open returned).          */
+#define MONTE_IPC_HANDLE_BYTES 64
+int monte_gpu_ipc_export(const void *d_ptr, unsigned char handle[MONTE_IPC_HANDLE_BYTES], uint64_t *offset);
+int monte_gpu_ipc_open(const unsigned char handle[MONTE_IPC_HANDLE_BYTES], uint64_t offset, void **d_ptr);
+int monte_gpu_ipc_close(void *d_ptr);
 /* vol_zy[s][t][z] = vol_xy[z][t][s] */
 int monte_gpu_fdk_transpose_dev(const monte_fdk_geom *g, const float *d_vol_xy,
                                 float *d_vol_zy, void *stream);

@@ -100,6 +100,10 @@ def _bind(path):
         "monte_mc_clearance_grid_octants": (C.c_int, [C.POINTER(McVolume), vp, C.c_int, C.c_int, C.c_int, vp]),
         "monte_mc_resolve_tracking": (C.c_int, [C.POINTER(McXs), C.POINTER(McSpectrum), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
         "monte_gpu_fdk_slab_rows": (C.c_int, [C.POINTER(FdkGeom), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "monte_gpu_fdk_backproject_peers_dev": (C.c_int, [G, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp]),
+        "monte_gpu_ipc_export": (C.c_int, [vp, vp, C.POINTER(C.c_uint64)]),
+        "monte_gpu_ipc_open": (C.c_int, [vp, C.c_uint64, C.POINTER(vp)]),
+        "monte_gpu_ipc_close": (C.c_int, [vp]),
     }
     missing = []
     for name, (res, args) in proto.items():
@@ -217,6 +221,36 @@ def fdk_backproject_views_dev(g, d_filt, d_slab, z_lo, z_hi, view_lo, view_hi, c
     _check(load().monte_gpu_fdk_backproject_views_dev(C.byref(g), C.c_void_p(d_filt.data_ptr()), z_lo, z_hi,
                                                       C.c_void_p(d_slab.data_ptr()), view_lo, view_hi,
                                                       1 if continue_sum else 0, _stream_ptr(stream)))
+
+
+def ipc_export(d_tensor):
+    """(64-byte handle, offset) of the device allocation holding a cuda tensor (or emulated device buffer), for a peer process"""
+    h = (C.c_ubyte * 64)()
+    off = C.c_uint64(0)
+    _check(load().monte_gpu_ipc_export(C.c_void_p(d_tensor.data_ptr()), C.cast(h, C.c_void_p), C.byref(off)))
+    return bytes(h), off.value
+
+
+def ipc_open(handle, offset):
+    """address (int) in this process of the byte a peer exported with ipc_export"""
+    h = (C.c_ubyte * 64).from_buffer_copy(handle)
+    p = C.c_void_p()
+    _check(load().monte_gpu_ipc_open(C.cast(h, C.c_void_p), offset, C.byref(p)))
+    return p.value
+
+
+def ipc_close(ptr):
+    _check(load().monte_gpu_ipc_close(C.c_void_p(ptr)))
+
+
+def fdk_backproject_peers_dev(g, seg_ptrs, seg_v_end, d_slab, z_lo, z_hi, stream=None):
+    """backproject all views into d_slab = slices [z_lo, z_hi), gathering the detector-row band out of the segments'
+    padded-row buffers (addresses: own tensors' data_ptr() or ipc_open() results); monte_gpu_fdk_backproject_peers_dev"""
+    n = len(seg_ptrs)
+    bases = (C.c_void_p * n)(*seg_ptrs)
+    ends = (C.c_int * n)(*seg_v_end)
+    _check(load().monte_gpu_fdk_backproject_peers_dev(C.byref(g), n, C.cast(bases, C.c_void_p), C.cast(ends, C.c_void_p), z_lo, z_hi,
+                                                      C.c_void_p(d_slab.data_ptr()), _stream_ptr(stream)))
 
 
 def fdk_slab_rows(g, z_lo, z_hi):

@@ -1321,6 +1321,86 @@ int monte_gpu_fdk_backproject_views_dev(const monte_fdk_geom *g, const float *d_
     return backproject_views(g, d_filtered_padded, z_lo, z_hi, d_vol_slab, (cudaStream_t)stream, view_lo, view_hi, continue_sum != 0);
 }
 
+int monte_gpu_fdk_backproject_peers_dev(const monte_fdk_geom *g, int n_seg, const float *const *seg_base, const int *seg_v_end,
+                                        int z_lo, int z_hi, float *d_vol_slab, void *stream) {
+    MONTE_REQUIRE_INIT();
+    if (int rc = check_geom(g)) return rc;
+    MONTE_ARG(seg_base && seg_v_end && d_vol_slab && n_seg >= 1 && n_seg <= PAIR_MAX_SEG, "fdk_backproject_peers: bad argument (n_seg = %d, at most %d)", n_seg, PAIR_MAX_SEG);
+    MONTE_ARG(0 <= z_lo && z_lo <= z_hi && z_hi <= g->nz, "fdk_backproject_peers: bad z range");
+    PairSrc src;
+    src.n = n_seg;
+    int prev = 0;
+    for (int o = 0; o < n_seg; o++) {
+        MONTE_ARG(seg_base[o] && seg_v_end[o] >= prev, "fdk_backproject_peers: segments must ascend in views and have a base");
+        src.base[o] = seg_base[o]; src.v_end[o] = seg_v_end[o];
+        prev = seg_v_end[o];
+    }
+    MONTE_ARG(prev == g->n_views, "fdk_backproject_peers: the segments cover %d of %d views", prev, g->n_views);
+    return backproject_views(g, nullptr, z_lo, z_hi, d_vol_slab, (cudaStream_t)stream, 0, g->n_views, false, &src);
+}
+
+// ---- CUDA IPC (one process per GPU): the containing allocation of a pointer is found through the driver entry point
+// cuMemGetAddressRange (libmonte_gpu does not link libcuda); opened mappings are remembered so that close() can unmap
+struct IpcMap { void *base; void *user; };
+static std::vector<IpcMap> g_ipc_maps;
+int monte_gpu_ipc_export(const void *d_ptr, unsigned char handle[MONTE_IPC_HANDLE_BYTES], uint64_t *offset) {
+    MONTE_REQUIRE_INIT();
+    MONTE_ARG(d_ptr && handle && offset, "ipc_export: NULL argument");
+#ifdef MONTE_EMU
+    memset(handle, 0, MONTE_IPC_HANDLE_BYTES);
+    memcpy(handle, &d_ptr, sizeof(d_ptr));                          // (one address space: the "handle" is the pointer)
+    *offset = 0;
+    return MONTE_OK;
+#else
+    static_assert(sizeof(cudaIpcMemHandle_t) == MONTE_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+    typedef CUresult (*range_fn)(CUdeviceptr *, size_t *, CUdeviceptr);
+    static range_fn get_range = nullptr;
+    if (!get_range) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        MONTE_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &sym, cudaEnableDefault, &qr));
+        if (!sym || qr != cudaDriverEntryPointSuccess) { set_error("cuMemGetAddressRange is not available in this driver"); return MONTE_E_CUDA; }
+        get_range = (range_fn)sym;
+    }
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    if (get_range(&base, &size, (CUdeviceptr)d_ptr) != CUDA_SUCCESS) { set_error("ipc_export: %p is not inside a device allocation", d_ptr); return MONTE_E_ARG; }
+    cudaIpcMemHandle_t h;
+    MONTE_CUDA(cudaIpcGetMemHandle(&h, (void *)base));
+    memcpy(handle, &h, sizeof(h));
+    *offset = (uint64_t)((CUdeviceptr)d_ptr - base);
+    return MONTE_OK;
+#endif
+}
+int monte_gpu_ipc_open(const unsigned char handle[MONTE_IPC_HANDLE_BYTES], uint64_t offset, void **d_ptr) {
+    MONTE_REQUIRE_INIT();
+    MONTE_ARG(handle && d_ptr, "ipc_open: NULL argument");
+    void *base = nullptr;
+#ifdef MONTE_EMU
+    memcpy(&base, handle, sizeof(base));
+#else
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    MONTE_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+#endif
+    *d_ptr = (char *)base + offset;
+    g_ipc_maps.push_back({base, *d_ptr});
+    return MONTE_OK;
+}
+int monte_gpu_ipc_close(void *d_ptr) {
+    for (size_t i = 0; i < g_ipc_maps.size(); i++)
+        if (g_ipc_maps[i].user == d_ptr) {
+#ifndef MONTE_EMU
+            const cudaError_t e = cudaIpcCloseMemHandle(g_ipc_maps[i].base);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaIpcCloseMemHandle", __FILE__, __LINE__);
+#endif
+            g_ipc_maps.erase(g_ipc_maps.begin() + i);
+            return MONTE_OK;
+        }
+    set_error("ipc_close: %p was not returned by monte_gpu_ipc_open", d_ptr);
+    return MONTE_E_ARG;
+}
+
 int monte_gpu_fdk_transpose_dev(const monte_fdk_geom *g, const float *d_vol_xy, float *d_vol_zy, void *stream) {
     MONTE_REQUIRE_INIT();
     if (int rc = check_geom(g)) return rc;

@@ -6,8 +6,10 @@ MC  : histories are independent.  Every rank runs photons n in its slice of [0, 
 FDK : the volume is cut into z-slabs of equal work (fdk_slice_cost, balanced_split), the filter into view
       ranges.  One exchange step, three forms with identical results: fdk_sharded (every rank gathers all
       filtered views), fdk_sharded_pipelined (view pieces broadcast in order, overlapped with the
-      backprojection) and fdk_sharded_band (one all_to_all of just the detector rows each slab reads --
-      the one bench.py uses).  After that each rank backprojects its own slab; nothing else is exchanged.
+      backprojection), fdk_sharded_band (one all_to_all of just the detector rows each slab reads) and
+      fdk_sharded_peers (no collective at all: the backprojector's pair conversion loads the band out of the
+      peers' buffers, opened through CUDA IPC -- the one bench.py uses).  After that each rank backprojects its
+      own slab; nothing else is exchanged.
 
 The compute callables are injected, so the same code is exercised on CPU with the gloo backend
 (tests/test_dist_cpu.py) and on B200s with NCCL (bench.py, tests/test_dist_gpu.py).
@@ -279,6 +281,66 @@ def fdk_sharded_band(filter_views, pad, backproject_slab, slab_rows, filt_rows, 
     for z_lo, z_hi in norm[rank]:
         if z_hi > z_lo:
             backproject_slab(z_lo, z_hi)
+    return (v_lo, v_hi), (norm[rank][0] if len(norm[rank]) == 1 else norm[rank])
+
+
+class PeerRows:
+    """The padded-row buffers of all ranks, visible to every rank: each rank exports its own buffer (CUDA IPC handle of
+    the allocation + offset, api.ipc_export) and opens the others' once (api.ipc_open).  ptrs[r] is the address, in THIS
+    process, of rank r's buffer; v_end[r] the end of the view range rank r filters.  Set-up is a collective."""
+
+    def __init__(self, api, filt_rows, n_views):
+        rank, ws = world()
+        self.api, self.rank, self.ws = api, rank, ws
+        self.v_end = [split_range(n_views, ws, r)[1] for r in range(ws)]
+        mine = api.ipc_export(filt_rows)
+        handles = [None] * ws
+        if ws > 1:
+            dist.all_gather_object(handles, mine)
+        else:
+            handles[0] = mine
+        self.opened = []
+        self.ptrs = []
+        for r in range(ws):
+            if r == rank:
+                self.ptrs.append(filt_rows.data_ptr())
+            else:
+                p = api.ipc_open(*handles[r])
+                self.opened.append(p)
+                self.ptrs.append(p)
+        self.token = torch.zeros(1, device=filt_rows.device) if filt_rows.is_cuda else None
+
+    def fence(self):
+        """every rank's work issued so far on the current stream is done before any rank's later work starts: a
+        one-element all-reduce ON THE STREAM (no host synchronisation)"""
+        if self.ws > 1:
+            if self.token is not None:
+                dist.all_reduce(self.token)
+            else:
+                dist.barrier()
+
+    def close(self):
+        for p in self.opened:
+            self.api.ipc_close(p)
+        self.opened = []
+
+
+def fdk_sharded_peers(filter_views, backproject_peers, peers, n_views, z_ranges):
+    """Same voxels as the other fdk_sharded_* forms, bit for bit, with NO collective on the data path: every rank filters
+    its own views into its own buffer; after a fence each rank backprojects its z ranges with
+    backproject_peers(z_lo, z_hi, ptrs, v_end) (monte_gpu_fdk_backproject_peers_dev), which loads the detector-row band
+    the slab reads straight out of the peers' buffers over NVLink while converting it to the backprojector's pair
+    layout -- no packing, no all_to_all, no unpacking, and only the rows a slab reads travel.  A second fence keeps
+    everybody's rows in place until all peers have read them."""
+    rank, ws = world()
+    norm = [[tuple(zr)] if len(zr) == 2 and not isinstance(zr[0], (tuple, list)) else [tuple(q) for q in zr] for zr in z_ranges]
+    v_lo, v_hi = split_range(n_views, ws, rank)
+    filter_views(v_lo, v_hi)
+    peers.fence()
+    for z_lo, z_hi in norm[rank]:
+        if z_hi > z_lo:
+            backproject_peers(z_lo, z_hi, peers.ptrs, peers.v_end)
+    peers.fence()
     return (v_lo, v_hi), (norm[rank][0] if len(norm[rank]) == 1 else norm[rank])
 
 

@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported(lib):
         assert hasattr(lib, n), "libmonte_gpu.so does not export %s" % n
     assert lib._monte_missing == []
     assert set(lib._monte_symbols) == set(names), set(lib._monte_symbols) ^ set(names)
-    assert lib.monte_gpu_abi_version() == 6
+    assert lib.monte_gpu_abi_version() == 7
 
 
 def test_struct_layouts_match_the_header():

@@ -65,6 +65,23 @@ mdist.fdk_sharded_band(lambda a, b: api.fdk_filter_dev(fg, proj, filt, a, b, pad
 torch.cuda.synchronize()
 assert torch.equal(slab, slab4), "band-limited exchange differs from gather-then-backproject"
 assert bool(torch.isnan(filt[: fg.n_views * fg.nv]).any()), "every row travelled: the band is not limiting anything"
+# >>> peers
+# no collective on the data path: the band is loaded out of the peers' buffers (CUDA IPC) by the backprojector's pair conversion
+filt.fill_(float("nan"))
+slab5 = torch.empty_like(slab)
+peers = mdist.PeerRows(api, filt, fg.n_views)
+for rep in range(2):                               # twice: the closing fence must keep the rows in place for slow peers
+    mdist.fdk_sharded_peers(lambda a, b: api.fdk_filter_dev(fg, proj, filt, a, b, pad=False),
+                            lambda z0, z1, ptrs, ends: api.fdk_backproject_peers_dev(fg, ptrs, ends, slab5, z0, z1),
+                            peers, fg.n_views, [mdist.split_range(fg.nz, ws, r) for r in range(ws)])
+torch.cuda.synchronize()
+assert torch.equal(slab, slab5), "peer-memory gather differs from gather-then-backproject"
+v_lo, v_hi = mdist.split_range(fg.n_views, ws, rank)
+own = filt[v_lo * fg.nv: v_hi * fg.nv]
+assert not bool(torch.isnan(own[:, :fg.nu]).any()) and bool(torch.isnan(filt[: fg.n_views * fg.nv]).any()), "only the own views are ever written"
+dist.barrier()
+peers.close()
+# <<< peers
 np.savez(os.path.join(out, "r%%d.npz" %% rank), im0=im0.cpu().numpy(), im5=im5.cpu().numpy(), slab=slab2.cpu().numpy(), z=np.array([z_lo, z_hi]))
 dist.barrier(); dist.destroy_process_group()
 '''

@@ -95,6 +95,37 @@ def test_emu_device_api_slabs_equal_whole(monte_emu):
     assert np.array_equal(whole, piece)
 
 
+def test_emu_backproject_from_segment_buffers_equals_one_buffer(monte_emu):
+    """monte_gpu_fdk_backproject_peers_dev: the views stay in the buffers of the "ranks" that filtered them (everything else
+    NaN), the backprojector's pair conversion gathers the band out of them -- the bits of the padded single buffer"""
+    m = monte_emu
+    g = _abi.generic_fdk_geom(37, 56, 40, 48)
+    proj = rand(11, (37, 56, 40))
+    filt = np.zeros(m.fdk_filtered_shape(g), np.float32)
+    m.fdk_filter_dev(g, _Dev(proj), _Dev(filt))
+    cuts = [0, 9, 9, 30, 37]
+    bufs = []
+    for a, b in zip(cuts, cuts[1:]):
+        f = np.full(m.fdk_filtered_shape(g), np.nan, np.float32)
+        if b > a:
+            m.fdk_filter_dev(g, _Dev(proj), _Dev(f), a, b, pad=False)
+        bufs.append(f)
+    for z_lo, z_hi in ((0, 48), (5, 29), (32, 48)):
+        want = np.zeros((z_hi - z_lo, 48, 48), np.float32)
+        m.fdk_backproject_dev(g, _Dev(filt), _Dev(want), z_lo, z_hi)
+        got = np.full_like(want, np.nan)
+        m.fdk_backproject_peers_dev(g, [f.ctypes.data for f in bufs], cuts[1:], _Dev(got), z_lo, z_hi)
+        assert np.array_equal(got, want), (z_lo, z_hi)
+    with pytest.raises(m.MonteError, match="cover"):
+        m.fdk_backproject_peers_dev(g, [bufs[0].ctypes.data], [9], _Dev(got), 32, 48)
+    h, off = m.ipc_export(_Dev(filt))
+    p = m.ipc_open(h, off)
+    assert p == filt.ctypes.data
+    m.ipc_close(p)
+    with pytest.raises(m.MonteError, match="ipc_close"):
+        m.ipc_close(p)
+
+
 def test_emu_band_limited_rows_are_all_a_slab_reads(monte_emu):
     """monte_gpu_fdk_slab_rows: with every row outside the reported band (and rows 0..3) set to NaN the slab
     still equals the full-data volume -- the contract the band-limited multi-GPU exchange relies on"""

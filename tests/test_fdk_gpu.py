@@ -352,3 +352,34 @@ def test_host_pipeline_chunking_is_bit_identical(monte, chunks, tail):
                 os.environ[k] = v
     assert np.array_equal(f0, f1) and np.array_equal(v0, v1) and np.array_equal(z0, z1)
     assert np.abs(v0).max() > 0 and not v0[:, :, :58].any()
+
+
+def test_backproject_from_segment_buffers_equals_one_buffer(monte):
+    """monte_gpu_fdk_backproject_peers_dev (the one-process-per-GPU exchange: every rank's filtered views stay in its own
+    buffer, the backprojector gathers the band out of them): three "ranks" as three buffers of one device, everything a
+    rank did not filter is NaN -- same bits as the padded single buffer"""
+    import torch
+    g = _abi.generic_fdk_geom(37, 56, 40, 48)
+    proj = torch.from_numpy(rand(11, (37, 56, 40))).cuda()
+    filt = torch.zeros(monte.fdk_filtered_shape(g), device="cuda")
+    monte.fdk_filter_dev(g, proj, filt)
+    cuts = [0, 9, 9, 30, 37]                                        # four segments, one of them empty
+    bufs = []
+    for a, b in zip(cuts, cuts[1:]):
+        f = torch.full(monte.fdk_filtered_shape(g), float("nan"), device="cuda")
+        if b > a:
+            monte.fdk_filter_dev(g, proj, f, a, b, pad=False)
+        bufs.append(f)
+    for z_lo, z_hi in ((0, 48), (5, 29), (32, 48)):
+        want = torch.empty((z_hi - z_lo, 48, 48), device="cuda")
+        monte.fdk_backproject_dev(g, filt, want, z_lo, z_hi)
+        got = torch.full_like(want, float("nan"))
+        monte.fdk_backproject_peers_dev(g, [f.data_ptr() for f in bufs], cuts[1:], got, z_lo, z_hi)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), (z_lo, z_hi)
+    with pytest.raises(Exception, match="cover"):
+        monte.fdk_backproject_peers_dev(g, [bufs[0].data_ptr()], [9], got, 32, 48)
+    # the IPC plumbing inside one process: export gives the allocation's handle and the offset of the pointer in it
+    h, off = monte.ipc_export(filt[3:])
+    h0, off0 = monte.ipc_export(filt)
+    assert len(h) == 64 and h == h0 and off - off0 == 3 * filt.shape[1] * 4
