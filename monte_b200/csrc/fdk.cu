@@ -273,14 +273,23 @@ __device__ __forceinline__ float pair_fetch(const PairSrc &src, int R, int c, in
     while (o < src.n - 1 && v >= src.v_end[o]) o++;
     return src.base[o][(size_t)R * pitch + c];
 }
+// A thread walks PAIR_RPT consecutive rows of one column: every texel is fetched once (+ one per strip) instead of
+// twice (as row R and as the partner of row R - 1) -- the fetches are NVLink peer loads here.
+constexpr int PAIR_RPT = 8;
 __global__ void fdk_pair_gather_kernel(const PairSrc src, float2 *__restrict__ pairs, int view_lo, int nv, int nu, int b_lo, int b_hi,
                                        int rows, int pitch, int seg0) {
     const int c = blockIdx.y * blockDim.x + threadIdx.x;
-    const int R = (view_lo + (int)blockIdx.z) * nv + b_lo + (int)blockIdx.x;
-    if (c >= pitch || (int)blockIdx.x >= b_hi - b_lo || R >= rows + 2) return;
-    const float a = pair_fetch(src, R, c, rows, nv, nu, pitch, seg0);
-    const float b = pair_fetch(src, R + 1, c, rows, nv, nu, pitch, seg0);
-    pairs[(size_t)R * pitch + c] = make_float2(a, b - a);
+    const int r_first = b_lo + (int)blockIdx.x * PAIR_RPT;
+    if (c >= pitch || r_first >= b_hi) return;
+    const int r_last = min(r_first + PAIR_RPT, b_hi);
+    int R = (view_lo + (int)blockIdx.z) * nv + r_first;
+    float a = pair_fetch(src, R, c, rows, nv, nu, pitch, seg0);
+    for (int r = r_first; r < r_last; r++, R++) {
+        if (R >= rows + 2) return;
+        const float b = pair_fetch(src, R + 1, c, rows, nv, nu, pitch, seg0);
+        pairs[(size_t)R * pitch + c] = make_float2(a, b - a);
+        a = b;
+    }
 }
 
 __global__ void fdk_unpad_kernel(const float *f, float *dense, size_t rows, int nu, int pitch) {
@@ -874,6 +883,10 @@ struct FdkDevState {
     // z-block streams of the backprojector (thin multi-GPU slabs, see backproject_views)
     cudaStream_t zs[8] = {nullptr};
     cudaEvent_t ev_zfork = nullptr, ev_zjoin[8] = {nullptr};
+    // pair-conversion stream of the backprojector: the conversion (and, between devices, the NVLink gather) of view chunk
+    // c + 1 runs underneath the backprojection of chunk c
+    cudaStream_t ps = nullptr;
+    cudaEvent_t ev_pfork = nullptr, ev_pair[32] = {nullptr};
 };
 static PerDev<FdkDevState> g_fdk_state;
 #define g_fft_attr_set (g_fdk_state.get().fft_attr_set)
@@ -893,6 +906,9 @@ static void fdk_cleanup() {                       // called once per bound devic
         FdkDevState &ds = g_fdk_state.get();
         for (int i = 0; i < 8; i++) { if (ds.zs[i]) cudaStreamDestroy(ds.zs[i]); if (ds.ev_zjoin[i]) cudaEventDestroy(ds.ev_zjoin[i]); }
         if (ds.ev_zfork) cudaEventDestroy(ds.ev_zfork);
+        if (ds.ps) cudaStreamDestroy(ds.ps);
+        if (ds.ev_pfork) cudaEventDestroy(ds.ev_pfork);
+        for (int i = 0; i < 32; i++) if (ds.ev_pair[i]) cudaEventDestroy(ds.ev_pair[i]);
     }
     g_fdk_state.get() = FdkDevState();
 }
@@ -1168,43 +1184,37 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
             vchunk = (int)fmax(30.0, 64.0 * 1024 * 1024 / per_view);
         }
     }
-    // vertical row pairs of the views of this call (+ the rows the last view reaches into)
+    // vertical row pairs of the views of this call (+ the rows the last view reaches into), converted view chunk by view
+    // chunk on a stream of their own (below): chunk c + 1 is converted -- between devices: fetched over NVLink -- while
+    // chunk c is backprojected
     const int rows_total = g->n_views * g->nv + 2;
     float2 *d_pairs = (float2 *)scratch(8, (size_t)rows_total * p.pitch * sizeof(float2) + 65536);   // (+ slack: staged tile rows may end past the last row)
     if (!d_pairs) return MONTE_E_NOMEM;
-    {
-        int b_lo, b_hi;
-        slab_band(g, z_lo, z_hi, b_lo, b_hi);
-        // the whole slab projects above or below the detector in every view (bp3d20.cpp:116 skips every
-        // voxel of it): its voxels keep the zeros / partial sums they have
-        if (b_hi <= b_lo) return MONTE_OK;
-        // rows 0..3 of every view are always paired too: they are what the previous view reaches past its end -- also
-        // those of the view after the last one of this call (and only those of it: the rest of that view may not be
-        // filtered yet when a multi-device caller feeds the views chunk by chunk)
-        const int n_v = view_hi - view_lo;
+    int b_lo, b_hi;
+    slab_band(g, z_lo, z_hi, b_lo, b_hi);
+    // the whole slab projects above or below the detector in every view (bp3d20.cpp:116 skips every
+    // voxel of it): its voxels keep the zeros / partial sums they have
+    if (b_hi <= b_lo) return MONTE_OK;
+    // rows 0..3 of every view are always paired too: they are what the previous view reaches past its end -- also
+    // those of the view after the last one of a chunk (and only those of it: the rest of that view may not be
+    // filtered yet when a multi-device caller feeds the views chunk by chunk)
+    auto pair_views = [&](int v_a, int v_b, cudaStream_t ss) -> int {
         // (one launch shape for both sources: the local padded rows, or the peers' rows over NVLink)
         auto pair_rows = [&](int v_first, int r_lo, int r_hi, int n_views_z) {
             const dim3 grid(r_hi - r_lo, ceil_div(p.pitch, 128), n_views_z);
+            const dim3 grid_g(ceil_div(r_hi - r_lo, PAIR_RPT), ceil_div(p.pitch, 128), n_views_z);
             int seg0 = 0;
             if (src) while (seg0 < src->n - 1 && v_first >= src->v_end[seg0]) seg0++;
-            if (src) fdk_pair_gather_kernel MONTE_CFG(grid, 128, 0, st)(*src, d_pairs, v_first, g->nv, g->nu, r_lo, r_hi, rows_total - 2, p.pitch, seg0);
-            else fdk_pair_kernel MONTE_CFG(grid, 128, 0, st)(d_filtered_padded, d_pairs, v_first, g->nv, r_lo, r_hi, rows_total, p.pitch);
+            if (src) fdk_pair_gather_kernel MONTE_CFG(grid_g, 128, 0, ss)(*src, d_pairs, v_first, g->nv, g->nu, r_lo, r_hi, rows_total - 2, p.pitch, seg0);
+            else fdk_pair_kernel MONTE_CFG(grid, 128, 0, ss)(d_filtered_padded, d_pairs, v_first, g->nv, r_lo, r_hi, rows_total, p.pitch);
         };
-        if (view_hi < g->n_views) {
-            pair_rows(view_hi, 0, 4, 1);
-            MONTE_CUDA(cudaGetLastError());
-        }
-        if (b_lo > 0) {
-            pair_rows(view_lo, 0, b_lo < 4 ? b_lo : 4, n_v);
-            MONTE_CUDA(cudaGetLastError());
-        }
-        pair_rows(view_lo, b_lo, b_hi, n_v);
+        if (v_b < g->n_views) pair_rows(v_b, 0, 4, 1);
+        if (b_lo > 0) pair_rows(v_a, 0, b_lo < 4 ? b_lo : 4, v_b - v_a);
+        pair_rows(v_a, b_lo, b_hi, v_b - v_a);
+        if (v_b == g->n_views) pair_rows(g->n_views, 0, 2, 1);       // the two zero rows after the last view
         MONTE_CUDA(cudaGetLastError());
-        if (view_hi == g->n_views) {          // the two zero rows after the last view
-            pair_rows(g->n_views, 0, 2, 1);
-            MONTE_CUDA(cudaGetLastError());
-        }
-    }
+        return MONTE_OK;
+    };
     // A thin slab (one of N multi-GPU slabs: 3..7 z-blocks of 16 slices) makes every view-chunk launch a handful of
     // waves (C3 on 8 GPUs: 3072 CTAs on 592 resident slots = 5.2), and the launches of one stream do not overlap: each
     // ends in a partly filled wave, ~10 % of the slab's time.  The z-blocks are independent, so each gets its own
@@ -1228,9 +1238,30 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
         MONTE_CUDA(cudaEventRecord(zds.ev_zfork, st));
         for (int i = 0; i < zb_end - zb_first; i++) MONTE_CUDA(cudaStreamWaitEvent(zds.zs[i], zds.ev_zfork, 0));
     }
-    for (int vb = view_lo; vb < view_hi; vb += vchunk) {
+    const int n_vchunks = ceil_div(view_hi - view_lo, vchunk);
+    bool psplit = n_vchunks >= 2 && n_vchunks <= 32;
+#ifdef MONTE_EMU
+    psplit = false;
+#endif
+    if (psplit) {
+        if (!zds.ps) {
+            MONTE_CUDA(cudaStreamCreateWithFlags(&zds.ps, cudaStreamNonBlocking));
+            MONTE_CUDA(cudaEventCreateWithFlags(&zds.ev_pfork, cudaEventDisableTiming));
+            for (int i = 0; i < 32; i++) MONTE_CUDA(cudaEventCreateWithFlags(&zds.ev_pair[i], cudaEventDisableTiming));
+        }
+        MONTE_CUDA(cudaEventRecord(zds.ev_pfork, st));
+        MONTE_CUDA(cudaStreamWaitEvent(zds.ps, zds.ev_pfork, 0));
+    }
+    int ci = 0;
+    for (int vb = view_lo; vb < view_hi; vb += vchunk, ci++) {
     // a chunk is presented to the kernel as a shorter scan: shifted view constants and rows
     p.n_views = vb + vchunk < view_hi ? vchunk : view_hi - vb;
+    if (int rc = pair_views(vb, vb + p.n_views, psplit ? zds.ps : st)) return rc;
+    if (psplit) {                                                  // the chunk's backprojection waits for its pairs only
+        MONTE_CUDA(cudaEventRecord(zds.ev_pair[ci], zds.ps));
+        if (zsplit) { for (int i = 0; i < zb_end - zb_first; i++) MONTE_CUDA(cudaStreamWaitEvent(zds.zs[i], zds.ev_pair[ci], 0)); }
+        else MONTE_CUDA(cudaStreamWaitEvent(st, zds.ev_pair[ci], 0));
+    }
     p.vc = g_fdk.d_vc + vb;
     p.pairs = d_pairs + (size_t)vb * g->nv * p.pitch; p.accumulate = continue_sum || vb > view_lo;
     if (zsplit) {
