@@ -275,7 +275,7 @@ def run_reference(args):
         c1 = cpu_c1(ob, threads, args.c1_views)
         c1.update(config={"workload": WORKLOAD_C1, "sample": c1.pop("sample")}, cores=threads, kind="port")
         line["c1"] = c1
-    shipped = as_shipped_reference(ob)
+    shipped = None if args.skip_shipped else as_shipped_reference(ob)
     if shipped:
         line["as_shipped"] = shipped
     print(json.dumps(line))
@@ -299,6 +299,7 @@ def main():
     ap.add_argument("--skip-c5", action="store_true", help="skip the nested FDK sweep (BASELINE configs[4])")
     ap.add_argument("--skip-c1", action="store_true", help="skip the nested C1 block (BASELINE configs[0] through the C ABI)")
     ap.add_argument("--skip-parity", action="store_true", help="skip the (untimed) parity checks")
+    ap.add_argument("--skip-shipped", action="store_true", help="reference arm: do not run the unmodified reference binaries (as_shipped block)")
     ap.add_argument("--c1-views", type=int, default=360, help="reference arm: views of the C1 run (360 = the stated size; 0 = skip)")
     ap.add_argument("--c4-histories", type=float, default=0.0, help="histories of the C4 run (default: 1e11 at 8 GPUs, else 1.25e10 per GPU... see mc_c4.config)")
     ap.add_argument("--mc-tracking", type=int, default=0,
