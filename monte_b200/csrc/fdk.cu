@@ -1127,7 +1127,10 @@ static void slab_band(const monte_fdk_geom *g, int z_lo, int z_hi, int &b_lo, in
 // src != nullptr: the filtered rows live on the devices that filtered them (d_filtered_padded is not read)
 static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_padded, int z_lo, int z_hi,
                              float *d_vol_slab, cudaStream_t st, int view_lo, int view_hi, bool continue_sum,
-                             const PairSrc *src = nullptr) {
+                             const PairSrc *src = nullptr, int *zs_pending = nullptr) {
+    // zs_pending (nullable): the caller feeds a thin slab chunk by chunk (fdk_multi) and joins the z-block streams itself
+    // at the end (bp_join_zstreams): this call then leaves its launches on them -- *zs_pending = streams in use -- so that
+    // the tail of one chunk's launches is filled by the next chunk's
     if (int rc = fdk_prepare(g, st)) return rc;
     if (z_lo == z_hi) return MONTE_OK;
     // everything outside the ROI is zero (the reference callocs the volume, bp3d20.cpp:32)
@@ -1221,7 +1224,7 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
     // stream: its view chunks stay in order, and the tail of one z-block's launch is filled with CTAs of the next
     // one's.  Launches are issued chunk-major, so the z-blocks walk through the views together (L2-sized chunks).
     const int zb_first = z_lo / 16, zb_end = ceil_div(z_hi, 16);
-    bool zsplit = variant == 0 && zb_end - zb_first >= 2 && zb_end - zb_first <= 8 && view_hi - view_lo > vchunk;
+    bool zsplit = variant == 0 && zb_end - zb_first >= 2 && zb_end - zb_first <= 8 && (view_hi - view_lo > vchunk || zs_pending != nullptr);
 #ifdef MONTE_EMU
     zsplit = false;
 #endif
@@ -1245,8 +1248,9 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
 #endif
     // With the conversion on its own stream only the FIRST chunk's conversion is exposed: it is made a quarter chunk
     // (between devices it is an NVLink gather: 0.65 ms of a 9 ms slab at C3 on 8 GPUs).
-    const int first_chunk = psplit ? (vchunk / 4 > 8 ? vchunk / 4 : 8) : vchunk;
-    if (psplit) n_vchunks = 1 + ceil_div(view_hi - view_lo - first_chunk > 0 ? view_hi - view_lo - first_chunk : 0, vchunk);
+    // (local rows: the conversion of a chunk is 0.25 ms and an extra launch costs more than that)
+    const int first_chunk = psplit && src ? (vchunk / 4 > 8 ? vchunk / 4 : 8) : vchunk;
+    if (first_chunk != vchunk) n_vchunks = 1 + ceil_div(view_hi - view_lo - first_chunk > 0 ? view_hi - view_lo - first_chunk : 0, vchunk);
     if (psplit) {
         if (!zds.ps) {
             MONTE_CUDA(cudaStreamCreateWithFlags(&zds.ps, cudaStreamNonBlocking));
@@ -1319,11 +1323,22 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
     }
 #undef BP_LAUNCH
     MONTE_CUDA(cudaGetLastError());
-    if (zsplit)
+    if (zsplit && zs_pending) *zs_pending = zb_end - zb_first;     // (joined by the caller)
+    else if (zsplit)
         for (int i = 0; i < zb_end - zb_first; i++) {
             MONTE_CUDA(cudaEventRecord(zds.ev_zjoin[i], zds.zs[i]));
             MONTE_CUDA(cudaStreamWaitEvent(st, zds.ev_zjoin[i], 0));
         }
+    return MONTE_OK;
+}
+
+// st waits for the first n z-block streams of the current device (the deferred join of backproject_views)
+static int bp_join_zstreams(cudaStream_t st, int n) {
+    FdkDevState &zds = g_fdk_state.get();
+    for (int i = 0; i < n; i++) {
+        MONTE_CUDA(cudaEventRecord(zds.ev_zjoin[i], zds.zs[i]));
+        MONTE_CUDA(cudaStreamWaitEvent(st, zds.ev_zjoin[i], 0));
+    }
     return MONTE_OK;
 }
 
@@ -1631,7 +1646,8 @@ static int fdk_multi(const monte_fdk_geom *g, const float *map, float *filtered,
     // devices, and device-major order would hand the last device its first launch only after ~5 ms of enqueueing.
     bool first_bp[MAX_DEV];
     int waited[MAX_DEV];                                            // chunks [0, waited] are known to the device's aux stream
-    for (int i = 0; i < nd; i++) { first_bp[i] = true; waited[i] = -1; }
+    int zs_pending[MAX_DEV];                                        // z-block streams a device's chunk launches were left on
+    for (int i = 0; i < nd; i++) { first_bp[i] = true; waited[i] = -1; zs_pending[i] = 0; }
     for (int ch = 0; ch < C && rc == MONTE_OK; ch++) {
         if (V[ch + 1] <= V[ch]) continue;
         int need = ch + 1;                                          // ... up to the next chunk that holds a view
@@ -1647,7 +1663,7 @@ static int fdk_multi(const monte_fdk_geom *g, const float *map, float *filtered,
                 if (cudaStreamWaitEvent(bp, ev_f[w], 0) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaStreamWaitEvent", __FILE__, __LINE__);
             if (rc) break;
             if (need > waited[i]) waited[i] = need;
-            if ((rc = backproject_views(g, nullptr, d.z_lo, d.z_hi, d.d_vol, bp, V[ch], V[ch + 1], !first_bp[i], &src))) break;
+            if ((rc = backproject_views(g, nullptr, d.z_lo, d.z_hi, d.d_vol, bp, V[ch], V[ch + 1], !first_bp[i], &src, &zs_pending[i]))) break;
             first_bp[i] = false;
             launches += 2;
         }
@@ -1658,6 +1674,7 @@ static int fdk_multi(const monte_fdk_geom *g, const float *map, float *filtered,
         Context &c = ctx();
         cudaStream_t bp = c.aux_stream, cp = c.copy_stream;
         const int nz_i = d.z_hi - d.z_lo;
+        if (zs_pending[i] && (rc = bp_join_zstreams(bp, zs_pending[i]))) break;
         if (nz_i > 0 && first_bp[i]) {                              // no view at all: the slab is zero
             if (cudaMemsetAsync(d.d_vol, 0, (size_t)nz_i * slice * sizeof(float), bp) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "cudaMemsetAsync", __FILE__, __LINE__); break; }
         }
@@ -1692,6 +1709,7 @@ static int fdk_multi(const monte_fdk_geom *g, const float *map, float *filtered,
     }
     for (int i = 0; i < nd; i++) {                                   // (also after an error: nothing may stay in flight)
         if (use_dev(i) != MONTE_OK) continue;
+        if (rc != MONTE_OK && zs_pending[i]) bp_join_zstreams(ctx().aux_stream, zs_pending[i]);
         cudaError_t e = cudaStreamSynchronize(ctx().stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().aux_stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().copy_stream);
