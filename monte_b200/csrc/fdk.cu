@@ -1269,6 +1269,9 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
         MONTE_CUDA(cudaEventRecord(zds.ev_pair[ci], zds.ps));
         if (zsplit) { for (int i = 0; i < zb_end - zb_first; i++) MONTE_CUDA(cudaStreamWaitEvent(zds.zs[i], zds.ev_pair[ci], 0)); }
         else MONTE_CUDA(cudaStreamWaitEvent(st, zds.ev_pair[ci], 0));
+    } else if (zsplit) {                                           // pairs converted on st: the z-block streams wait for them
+        MONTE_CUDA(cudaEventRecord(zds.ev_zfork, st));
+        for (int i = 0; i < zb_end - zb_first; i++) MONTE_CUDA(cudaStreamWaitEvent(zds.zs[i], zds.ev_zfork, 0));
     }
     p.vc = g_fdk.d_vc + vb;
     p.pairs = d_pairs + (size_t)vb * g->nv * p.pitch; p.accumulate = continue_sum || vb > view_lo;
