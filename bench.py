@@ -536,7 +536,7 @@ def bench_mc_c2(c):
                   "note": "the label volume is uploaded on every call (MONTE_MC_LABEL_CACHE=0)" + (": every device takes 1/%d of it from the host and the rest from its peers over NVLink" % ws if ws > 1 else ""),
                   "cached_labels": {"value": hist_total / res["cached_labels"], "ms_per_step": 1e3 * res["cached_labels"] / K,
                                     "h2d_bytes_per_step": int(ws * (2 * 201 * 16 + 201 * 4 + g.n_views * 8)),
-                                    "note": "default behaviour: the host buffer is hashed (4 threads) and re-uploaded only when its content changed"}}
+                                    "note": "MONTE_MC_LABEL_CACHE=1: the host buffer is hashed (8 threads) and re-uploaded only when its content changed (the default does that only where a clearance grid or a presence scan depends on the labels)"}}
     c.host_barrier()
 
     # cpu baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample

@@ -388,7 +388,8 @@ int monte_gpu_simulate_range(const monte_mc_geom *g, const monte_mc_volume *vol,
  * pass that sums the per-device tallies (fused reduce + epilogue).  With several bound
  * devices: MONTE_MC_REDUCE=p2p (default; the root kernel loads the peers' tallies over NVLink) or =nccl (one
  * ncclReduce to ids[0], then the epilogue kernel).  The label volume is re-uploaded only when its content changed
- * (64-bit hash of the host buffer; MONTE_MC_LABEL_CACHE=0 uploads it on every call).                           */
+ * (64-bit hash of the host buffer) wherever a clearance grid or a presence scan hangs on it; for the reference's tracking
+ * loop uploading is cheaper than hashing and is simply done (MONTE_MC_LABEL_CACHE=1 / 0 force either behaviour).        */
 int monte_gpu_simulate_maps(const monte_mc_geom *g, const monte_mc_volume *vol,
                             const uint8_t *labels, const monte_mc_xs *xs,
                             const monte_mc_spectrum *spec, uint32_t photons_per_pixel,

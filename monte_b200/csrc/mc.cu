@@ -1360,7 +1360,17 @@ int monte_gpu_simulate_maps(const monte_mc_geom *g, const monte_mc_volume *vol, 
     const int nd = n_dev();
     const char *e_red = getenv("MONTE_MC_REDUCE"), *e_cache = getenv("MONTE_MC_LABEL_CACHE");   // read per call: tests flip them
     const bool use_nccl = nd > 1 && ((e_red && !strcmp(e_red, "nccl")) || !peers_ok());
-    const int label_cache = e_cache ? atoi(e_cache) : 1;
+    // MONTE_MC_LABEL_CACHE unset: hash the labels only where a hit saves more than the hash costs -- a clearance grid
+    // (25-110 ms of host work per new volume) or a presence scan hangs on them; for the reference's tracking loop the
+    // upload itself (0.6 ms for 325^3 over PCIe, less when scattered over several devices) is cheaper than hashing
+    // 34 MB on the host (0.8 ms on 8 threads), so it is simply done.  1 / 0 force either behaviour.
+    int label_cache;
+    if (e_cache) label_cache = atoi(e_cache);
+    else {
+        int tm = vol->tracking_mode, cl = 0;
+        if (tm == MONTE_MC_TRACK_AUTO) tm = monte_mc_resolve_tracking(xs, spec, &cl, nullptr);
+        label_cache = (tm != MONTE_MC_TRACK_GLOBAL || vol->majorant_mode == MONTE_MC_MAJORANT_PRESENT) ? 1 : 0;
+    }
     const size_t nvox = (size_t)vol->nx * vol->ny * vol->nz;
     const uint64_t lhash = label_cache ? hash_labels(labels, nvox) : 0;
     uint32_t present = 0xffffffffu;                                      // majorant_mode PRESENT: one scan for all devices

@@ -107,12 +107,20 @@ def body_label_cache(api):
     mg = scenes.mc_geom(9, 32.5 / 9, n_views=1)
     mvol = scenes.volume_for(lab, 1.0)
     xs, sp = scenes.make_xs(), scenes.mono_spectrum(140.0)
-    a0, a5, _ = api.simulate(mg, mvol, lab, xs, sp, 60, 3)
-    b0, b5, _ = api.simulate(mg, mvol, lab, xs, sp, 60, 3)            # cached labels
-    assert np.array_equal(a0, b0) and np.array_equal(a5, b5)
-    lab[:] = 0                                                        # all air, in place
-    c0, _, st = api.simulate(mg, mvol, lab, xs, sp, 60, 3)
-    assert (c0 == 60).all() and st["primaries"] == st["histories"]
+    os.environ["MONTE_MC_LABEL_CACHE"] = "1"                          # (the default hashes only where a clearance grid or a presence scan needs it)
+    try:
+        a0, a5, sa = api.simulate(mg, mvol, lab, xs, sp, 60, 3)
+        b0, b5, sb = api.simulate(mg, mvol, lab, xs, sp, 60, 3)        # cached labels
+        assert np.array_equal(a0, b0) and np.array_equal(a5, b5)
+        lab[:] = 0                                                    # all air, in place
+        c0, _, st = api.simulate(mg, mvol, lab, xs, sp, 60, 3)
+        assert (c0 == 60).all() and st["primaries"] == st["histories"]
+    finally:
+        del os.environ["MONTE_MC_LABEL_CACHE"]
+    lab[:] = scenes.cylinder_phantom(33, 1.0)                         # default policy: the change in place is seen as well
+    e0, e5, _ = api.simulate(mg, mvol, lab, xs, sp, 60, 3)
+    assert np.array_equal(a0, e0) and np.array_equal(a5, e5)
+    lab[:] = 0
     os.environ["MONTE_MC_LABEL_CACHE"] = "0"
     try:
         lab[:] = scenes.cylinder_phantom(33, 1.0)
