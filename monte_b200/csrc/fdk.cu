@@ -241,17 +241,8 @@ __global__ void fdk_pad_kernel(float *f, int rows, int nu, int pitch, int r0, in
 // in the hot loop before) is taken once per texel here instead of once per voxel update there
 // Only rows [b_lo, b_hi) of every view are paired: the band a z-slab projects onto (all rows for a
 // whole-volume call, ~1/N of them for one of N multi-GPU slabs).
-__global__ void fdk_pair_kernel(const float *__restrict__ f, float2 *__restrict__ pairs, int view_lo, int nv, int b_lo, int b_hi,
-                                int rows_total, int pitch) {
-    const int c = blockIdx.y * blockDim.x + threadIdx.x;
-    const int r = (view_lo + (int)blockIdx.z) * nv + b_lo + (int)blockIdx.x;
-    if (c >= pitch || (int)blockIdx.x >= b_hi - b_lo || r >= rows_total) return;
-    const float a = f[(size_t)r * pitch + c];
-    const float b = r + 1 < rows_total ? f[(size_t)(r + 1) * pitch + c] : 0.f;
-    pairs[(size_t)r * pitch + c] = make_float2(a, b - a);
-}
-
-// The same pairs built straight from the devices that filtered the views (multi-device reconstruction): the
+// fdk_pair_gather_kernel builds them, from the local padded rows or straight from the devices that filtered the views
+// (multi-device reconstruction): there the
 // exchange of filtered projections IS this kernel -- every device loads the detector-row band its z-slab reads out of
 // its peers' memory (NVLink P2P, coalesced rows) while converting it to the pair layout, so no filtered view is ever
 // copied, packed or stored twice.  src.base[o] is the (virtual) base of owner o's padded-row layout: row R of the
@@ -274,14 +265,26 @@ __device__ __forceinline__ float pair_fetch(const PairSrc &src, int R, int c, in
     return src.base[o][(size_t)R * pitch + c];
 }
 // A thread walks PAIR_RPT consecutive rows of one column: every texel is fetched once (+ one per strip) instead of
-// twice (as row R and as the partner of row R - 1) -- the fetches are NVLink peer loads here.
+// twice (as row R and as the partner of row R - 1) -- the fetches are NVLink peer loads between devices.
+// ONE launch converts everything a view chunk needs (one host thread feeds up to eight devices: launches count):
+//   z <  n_v : view view_lo + z -- strip 0 = rows [0, a_hi) (what the previous view's last row reaches into; a_hi = 0:
+//              the band starts at row 0 and covers them), strips 1.. = the band [b_lo, b_hi)
+//   z == n_v : the view after the chunk -- rows [0, x_hi) only: 4 rows of the next view, or the two zero rows after the
+//              last view of all
 constexpr int PAIR_RPT = 8;
-__global__ void fdk_pair_gather_kernel(const PairSrc src, float2 *__restrict__ pairs, int view_lo, int nv, int nu, int b_lo, int b_hi,
-                                       int rows, int pitch, int seg0) {
+__global__ void fdk_pair_gather_kernel(const PairSrc src, float2 *__restrict__ pairs, int view_lo, int n_v, int nv, int nu,
+                                       int a_hi, int b_lo, int b_hi, int x_hi, int rows, int pitch, int seg0) {
     const int c = blockIdx.y * blockDim.x + threadIdx.x;
-    const int r_first = b_lo + (int)blockIdx.x * PAIR_RPT;
-    if (c >= pitch || r_first >= b_hi) return;
-    const int r_last = min(r_first + PAIR_RPT, b_hi);
+    if (c >= pitch) return;
+    const bool extra = (int)blockIdx.z == n_v;
+    int r_first, r_last;
+    if (blockIdx.x == 0) { r_first = 0; r_last = extra ? x_hi : a_hi; }
+    else {
+        if (extra) return;
+        r_first = b_lo + ((int)blockIdx.x - 1) * PAIR_RPT;
+        r_last = min(r_first + PAIR_RPT, b_hi);
+    }
+    if (r_first >= r_last) return;
     int R = (view_lo + (int)blockIdx.z) * nv + r_first;
     float a = pair_fetch(src, R, c, rows, nv, nu, pitch, seg0);
     for (int r = r_first; r < r_last; r++, R++) {
@@ -307,7 +310,7 @@ constexpr int BP_TX = 32, BP_TY = 8;   // threads: 32 along s (x-fastest, coales
 constexpr int BP_DEFAULT_VARIANT = 0;  // MONTE_BP_VARIANT overrides: 0 L1 gathers, 10 / 11 footprint staged in shared memory (4 / 3 CTAs per SM)
 
 struct BpParams {
-    const float2 *pairs;        // padded rows [n_views*nv + 2][pitch] as vertical pairs (fdk_pair_kernel / fdk_pair_gather_kernel)
+    const float2 *pairs;        // padded rows [n_views*nv + 2][pitch] as vertical pairs (fdk_pair_gather_kernel)
     const ViewConst *vc;
     float *vol;                 // slab base: slice z_lo
     int n_views, nu, nv, pitch;
@@ -1201,20 +1204,18 @@ static int backproject_views(const monte_fdk_geom *g, const float *d_filtered_pa
     // rows 0..3 of every view are always paired too: they are what the previous view reaches past its end -- also
     // those of the view after the last one of a chunk (and only those of it: the rest of that view may not be
     // filtered yet when a multi-device caller feeds the views chunk by chunk)
+    // (one kernel for both sources: the local padded rows as a single segment -- the pad rules it applies on the fly are
+    // the ones fdk_pad_kernel wrote into them -- or the peers' rows over NVLink)
+    PairSrc local_src;
+    if (!src) { local_src.n = 1; local_src.base[0] = d_filtered_padded; local_src.v_end[0] = g->n_views; }
+    const PairSrc &psrc = src ? *src : local_src;
     auto pair_views = [&](int v_a, int v_b, cudaStream_t ss) -> int {
-        // (one launch shape for both sources: the local padded rows, or the peers' rows over NVLink)
-        auto pair_rows = [&](int v_first, int r_lo, int r_hi, int n_views_z) {
-            const dim3 grid(r_hi - r_lo, ceil_div(p.pitch, 128), n_views_z);
-            const dim3 grid_g(ceil_div(r_hi - r_lo, PAIR_RPT), ceil_div(p.pitch, 128), n_views_z);
-            int seg0 = 0;
-            if (src) while (seg0 < src->n - 1 && v_first >= src->v_end[seg0]) seg0++;
-            if (src) fdk_pair_gather_kernel MONTE_CFG(grid_g, 128, 0, ss)(*src, d_pairs, v_first, g->nv, g->nu, r_lo, r_hi, rows_total - 2, p.pitch, seg0);
-            else fdk_pair_kernel MONTE_CFG(grid, 128, 0, ss)(d_filtered_padded, d_pairs, v_first, g->nv, r_lo, r_hi, rows_total, p.pitch);
-        };
-        if (v_b < g->n_views) pair_rows(v_b, 0, 4, 1);
-        if (b_lo > 0) pair_rows(v_a, 0, b_lo < 4 ? b_lo : 4, v_b - v_a);
-        pair_rows(v_a, b_lo, b_hi, v_b - v_a);
-        if (v_b == g->n_views) pair_rows(g->n_views, 0, 2, 1);       // the two zero rows after the last view
+        const int a_hi = b_lo > 0 ? (b_lo < 4 ? b_lo : 4) : 0;
+        const int x_hi = v_b < g->n_views ? 4 : 2;                  // rows of the next view / the two zero rows after the last view
+        const dim3 grid(1 + ceil_div(b_hi - b_lo, PAIR_RPT), ceil_div(p.pitch, 128), v_b - v_a + 1);
+        int seg0 = 0;
+        while (seg0 < psrc.n - 1 && v_a >= psrc.v_end[seg0]) seg0++;
+        fdk_pair_gather_kernel MONTE_CFG(grid, 128, 0, ss)(psrc, d_pairs, v_a, v_b - v_a, g->nv, g->nu, a_hi, b_lo, b_hi, x_hi, rows_total - 2, p.pitch, seg0);
         MONTE_CUDA(cudaGetLastError());
         return MONTE_OK;
     };
