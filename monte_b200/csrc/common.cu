@@ -8,7 +8,9 @@
 namespace monte {
 
 static Context g_ctxs[MAX_DEV];
-static int g_ndev = 0, g_cur = 0;
+static int g_ndev = 0;
+// (thread-local: a multi-device call may issue each device's launches from a thread of its own, see fdk_multi)
+static thread_local int g_cur = 0;
 static bool g_peers = false;
 static thread_local char g_err[1024] = "";
 

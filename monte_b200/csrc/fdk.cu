@@ -22,6 +22,8 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <string>
+#include <thread>
 
 namespace monte {
 
@@ -1646,30 +1648,52 @@ static int fdk_multi(const monte_fdk_geom *g, const float *map, float *filtered,
         if (cudaEventRecord(d.filter_end, st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "event", __FILE__, __LINE__);
     }
     // ---- on every device: chunk by chunk, gather the band from the chunk's owner + backproject into the own slab.
-    // The launches are issued chunk-major (chunk 0 on every device, then chunk 1, ...): one host thread feeds all the
-    // devices, and device-major order would hand the last device its first launch only after ~5 ms of enqueueing.
+    // Every device's launches are issued by a host thread of its own: ~250 launches per device (pair conversion + one
+    // backprojection launch per z-block, for each of up to 32 chunks) would otherwise queue behind each other in one
+    // thread for ~10 ms -- as long as the uploads they are meant to hide under.
     bool first_bp[MAX_DEV];
-    int waited[MAX_DEV];                                            // chunks [0, waited] are known to the device's aux stream
     int zs_pending[MAX_DEV];                                        // z-block streams a device's chunk launches were left on
-    for (int i = 0; i < nd; i++) { first_bp[i] = true; waited[i] = -1; zs_pending[i] = 0; }
-    for (int ch = 0; ch < C && rc == MONTE_OK; ch++) {
-        if (V[ch + 1] <= V[ch]) continue;
-        int need = ch + 1;                                          // ... up to the next chunk that holds a view
-        while (need < C - 1 && V[need + 1] <= V[need]) need++;
-        if (need > C - 1) need = C - 1;
-        if (g->nv < 8) need = C - 1;                                // (rows 0..3 of "the next view" then span several views)
-        for (int i = 0; i < nd && rc == MONTE_OK; i++) {
-            FdkMultiDev &d = dv[i];
-            if (d.z_hi <= d.z_lo) continue;
-            if ((rc = use_dev(i))) break;
+    int launches_dev[MAX_DEV], rc_dev[MAX_DEV];
+    std::string err_dev[MAX_DEV];
+    for (int i = 0; i < nd; i++) { first_bp[i] = true; zs_pending[i] = 0; launches_dev[i] = 0; rc_dev[i] = MONTE_OK; }
+    auto device_chunks = [&](int i) {
+        FdkMultiDev &d = dv[i];
+        int r = MONTE_OK;
+        do {
+            if (d.z_hi <= d.z_lo) break;
+            if ((r = use_dev(i))) break;
             cudaStream_t bp = ctx().aux_stream;
-            for (int w = waited[i] + 1; w <= need && rc == MONTE_OK; w++)   // (own chunks too: they are filtered on another stream)
-                if (cudaStreamWaitEvent(bp, ev_f[w], 0) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaStreamWaitEvent", __FILE__, __LINE__);
-            if (rc) break;
-            if (need > waited[i]) waited[i] = need;
-            if ((rc = backproject_views(g, nullptr, d.z_lo, d.z_hi, d.d_vol, bp, V[ch], V[ch + 1], !first_bp[i], &src, &zs_pending[i]))) break;
-            first_bp[i] = false;
-            launches += 2;
+            int waited = -1;                                        // chunks [0, waited] are known to this stream
+            for (int ch = 0; ch < C && r == MONTE_OK; ch++) {
+                if (V[ch + 1] <= V[ch]) continue;
+                int need = ch + 1;                                  // ... up to the next chunk that holds a view
+                while (need < C - 1 && V[need + 1] <= V[need]) need++;
+                if (need > C - 1) need = C - 1;
+                if (g->nv < 8) need = C - 1;                        // (rows 0..3 of "the next view" then span several views)
+                for (int w = waited + 1; w <= need && r == MONTE_OK; w++)   // (own chunks too: they are filtered on another stream)
+                    if (cudaStreamWaitEvent(bp, ev_f[w], 0) != cudaSuccess) r = cuda_fail(cudaGetLastError(), "cudaStreamWaitEvent", __FILE__, __LINE__);
+                if (r) break;
+                if (need > waited) waited = need;
+                if ((r = backproject_views(g, nullptr, d.z_lo, d.z_hi, d.d_vol, bp, V[ch], V[ch + 1], !first_bp[i], &src, &zs_pending[i]))) break;
+                first_bp[i] = false;
+                launches_dev[i] += 2;
+            }
+        } while (0);
+        rc_dev[i] = r;
+        if (r) err_dev[i] = monte_gpu_last_error();                 // (the error text is thread-local)
+    };
+    if (rc == MONTE_OK) {
+#ifdef MONTE_EMU
+        for (int i = 0; i < nd; i++) device_chunks(i);              // (the emulation runs kernels on the calling thread)
+#else
+        std::thread th[MAX_DEV];
+        for (int i = 1; i < nd; i++) th[i] = std::thread(device_chunks, i);
+        device_chunks(0);
+        for (int i = 1; i < nd; i++) th[i].join();
+#endif
+        for (int i = 0; i < nd; i++) {
+            launches += launches_dev[i];
+            if (rc_dev[i] && rc == MONTE_OK) { rc = rc_dev[i]; set_error("%s", err_dev[i].c_str()); }
         }
     }
     for (int i = 0; i < nd && rc == MONTE_OK; i++) {
