@@ -67,7 +67,7 @@ struct McLaunch {
     uint32_t *fates;              // RECORD only
     float *fate_e;
     uint32_t off_inv, off_cdf, off_ray, off_invlo, off_slots;   // shared-memory layout, byte offsets (see the kernel)
-    uint32_t vote_bias;           // (128 - T) in every byte: a phase runs on a vote when >= T lanes wait for it (T = 16)
+    uint32_t vote_bias;           // (128 - T) in every byte: a phase runs on a vote when >= T lanes wait for it (T = 14)
     uint32_t collide_check;       // 0: the clip box lies inside the detector-side bounds of :613-619 for every view, so no
                                   // collision site can fail that test and COLLIDE skips it (host: launch_mc)
     uint32_t n_vox_m1;            // voxels of the label volume - 1: the one clamp of a label address
@@ -221,7 +221,7 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
         if (st & (ALL * P_COMPTON)) onehot |= 1u << 24;
         const uint32_t cnts = __reduce_add_sync(0xffffffffu, onehot);
         if (cnts == 0u) break;                                          // every slot of every lane is done
-        // Every phase in which at least `second_min` (16) lanes wait is run on this one vote, in pipeline order STEP ->
+        // Every phase in which at least `second_min` (14) lanes wait is run on this one vote, in pipeline order STEP ->
         // COLLIDE -> COMPTON -> REFILL (each feeds the next, so the stale counts of the later ones can only have grown).
         // Bit 7 of byte p of `todo` = phase p qualifies: count + (128 - T) carries into bit 7 iff count >= T (counts <= 32,
         // no carry between bytes).  Near the end of the grid no phase qualifies: then the fullest one runs alone.
@@ -1198,7 +1198,7 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     L.coct = s->coct;
     {
         static int thr = -1;                                           // MONTE_MC_SECOND=T: lanes a phase needs to run on a vote (1..32)
-        if (thr < 0) { const char *e = getenv("MONTE_MC_SECOND"); thr = e ? atoi(e) : 16; if (thr < 1) thr = 1; if (thr > 32) thr = 32; }
+        if (thr < 0) { const char *e = getenv("MONTE_MC_SECOND"); thr = e ? atoi(e) : 14; if (thr < 1) thr = 1; if (thr > 32) thr = 32; }
         L.vote_bias = (uint32_t)(128 - thr) * 0x01010101u;
     }
     {

@@ -34,6 +34,13 @@ def build(force=False, asan=False, ubsan=False):
     san = "address" if asan else "undefined" if ubsan else None       # ubsan=True: same idea with -fsanitize=undefined
     flags = CXXFLAGS + (["-fsanitize=" + san, "-fno-omit-frame-pointer", "-O1"] if san else [])
     os.makedirs(out_dir, exist_ok=True)
+    import fcntl
+    with open(os.path.join(out_dir, ".lock"), "w") as lock:           # several pytest-xdist workers may get here at once
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        return _build_locked(force, out_dir, lib_path, san, flags)
+
+
+def _build_locked(force, out_dir, lib_path, san, flags):
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     hdrs += [os.path.join(ROOT, "include", "monte_gpu.h"), os.path.join(HERE, "cuda_runtime.h")]
     jobs, objs = [], []
