@@ -67,6 +67,11 @@ def test_emu_without_peer_access(emu8):
         emu8.init(0)
 
 
+@pytest.mark.parametrize("n_dev", [2, 5])
+def test_emu_hu_volume_and_ring_detector_multi(emu8, n_dev):
+    M.body_hu_volume_multi_equals_single(emu8, n_dev)
+
+
 def test_emu_label_cache(monte_emu):
     M.body_label_cache(monte_emu)
 

@@ -175,6 +175,28 @@ def body_scattered_label_upload(api, n_dev):
         rebind(api, [0])
 
 
+def body_hu_volume_multi_equals_single(api, n_dev):
+    """a segmented CT volume tracked with the majorant of the classes present (one presence scan for all devices, scattered
+    label upload) and the ring detector, sharded over the devices: the bits of the one-device runs"""
+    hu = scenes.hu_head_phantom(33, 0.6)
+    lab, xs, _, present = api.ctnum_segment(hu, api.hu_classes_default(True), scenes.make_xs(), 60.0)
+    vol = scenes.volume_for(lab, 0.6)
+    vol.majorant_mode = _abi.MAJORANT_PRESENT
+    sp = scenes.mono_spectrum(60.0)
+    flat = scenes.mc_geom(9, 32.5 / 9, n_views=2)
+    ring = scenes.ring_geom(12, 3, 4.0, 16.0, n_views=2)
+    rebind(api, [0])
+    want = [api.simulate(g, vol, lab, xs, sp, 23, 5)[:2] for g in (flat, ring)]
+    rebind(api, list(range(n_dev)))
+    try:
+        got = [api.simulate(g, vol, lab, xs, sp, 23, 5)[:2] for g in (flat, ring)]
+    finally:
+        rebind(api, [0])
+    for w, g_ in zip(want, got):
+        assert np.array_equal(w[0], g_[0]) and np.array_equal(w[1], g_[1])
+    assert want[1][1].sum() > want[1][0].sum() > 0
+
+
 def body_argument_errors(api):
     from monte_b200.api import MonteError
     lab = scenes.cylinder_phantom(17, 2.0)
@@ -226,6 +248,12 @@ def test_mc_two_devices_equal_one(monte, mode):
 @pytest.mark.gpu
 def test_label_cache(monte):
     body_label_cache(monte)
+
+
+@pytest.mark.gpu
+def test_hu_volume_and_ring_detector_two_devices(monte):
+    _need(2)
+    body_hu_volume_multi_equals_single(monte, 2)
 
 
 @pytest.mark.gpu
