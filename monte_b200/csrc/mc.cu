@@ -304,17 +304,16 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             }
 #pragma unroll
             for (int q = 0; q < NS; q++) {
-                if (!en2[q]) continue;
+                // Straight-line: everything is computed for both slots, only the stores hang on en2[q] (a lane with one waiting
+                // slot) -- the lanes of a warp take every outcome on every visit, so a branch saves nothing and costs its
+                // resolution (`branch_resolving` was a top-3 stall).  Bitwise &: no short-circuit branches around the table load.
                 uint4 *slot = sl[q];                               // GRP/WORD below refer to this slot
                 uint32_t meta = id2[q].y;
                 const uint32_t ctr = id2[q].z;
-                if (CLEAR) { meta = (meta & ~0xFE0000u) | (qn2[q] << 17); WORD(G_ID, 1) = meta; }
+                if (CLEAR) meta = (meta & ~0xFE0000u) | (qn2[q] << 17);
                 const uint32_t clrq = ~(0xFu << (4 * jj[q]));
                 const int kE = meta & 0xFF;
-                WORD(G_ID, 2) = ctr + 1u;     // flight-stream index, bits 0-19: a history does not take 2^20 Woodcock steps (mu_max > 0 is checked)
-                *reinterpret_cast<float4 *>(&GRP(G_POS)) = pos2[q];
-                c_steps++;
-                // Three outcomes, selects instead of branches (the lanes of a warp take all of them on every visit):
+                // Three outcomes:
                 //  left the volume -- only air ahead: the history is finished with the REFILL phase (primary tally or scatter
                 //    detection; there nearly every lane of a visit has one to finish, here it would be the 3-5 that leave);
                 //  accepted tentative collision -- records its material and moves to COLLIDE;
@@ -323,9 +322,16 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
                 const int mat = max(min(lab2[q], sc.n_mat) - 1, 0);
                 const float4 tb = s_tab[mat * TAB_ROWS + kE];
                 const float ratio = CLEAR && lo2[q] ? tb.w : tb.x;    // acceptance against the majorant the step was sampled with
-                const bool accept = !out && lab2[q] != 0 && !(u01(r2[q].y) > ratio);
-                if (out | accept) WORD(G_ID, 1) = out ? (meta | 0x8000u) : ((meta & ~0x7000u) | ((uint32_t)mat << 12));
-                st = (out | accept) ? ((st & clrq) | ((out ? P_REFILL : P_COLLIDE) << (4 * jj[q]))) : st;
+                const bool accept = (!out) & (lab2[q] != 0) & !(u01(r2[q].y) > ratio);
+                const bool moved = (out | accept) & en2[q];
+                const uint32_t new_meta = out ? (meta | 0x8000u) : (accept ? ((meta & ~0x7000u) | ((uint32_t)mat << 12)) : meta);
+                if (en2[q]) {
+                    WORD(G_ID, 1) = new_meta;
+                    WORD(G_ID, 2) = ctr + 1u;     // flight-stream index, bits 0-19: a history does not take 2^20 Woodcock steps (mu_max > 0 is checked)
+                    *reinterpret_cast<float4 *>(&GRP(G_POS)) = pos2[q];
+                }
+                c_steps += en2[q] ? 1u : 0u;
+                st = moved ? ((st & clrq) | ((out ? P_REFILL : P_COLLIDE) << (4 * jj[q]))) : st;
             }
 
         } while (0);
