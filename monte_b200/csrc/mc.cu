@@ -366,18 +366,15 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             GRP(G_ID) = id;
             const float u_sel = u01(re.x);
             const float4 tb = s_tab[mat * TAB_ROWS + kE];
-            if (u_sel <= tb.y) {                                      // photoelectric, :651-655
-                c_abs++;
-                if (RECORD) { P.fates[WORD(G_REC, 0)] = 3u | ((uint32_t)(nint + 1) << 28); P.fate_e[WORD(G_REC, 0)] = pos.w; }
-                st = (st & clr) | (P_REFILL << (4 * j));
-            } else if (u_sel <= tb.z) {                               // coherent: no deflection (:656-695) ...
-                c_coh++;
-                if (RAYLEIGH) {                                       // ... or an angle from the form factor
-                    WORD(G_ID, 1) = meta | 0x10000u; WORDF(G_DIR, 3) = u01(re.y);
-                    st = (st & clr) | (P_COMPTON << (4 * j));
-                } else st = (st & clr) | (P_STEP << (4 * j));
-            }
-            else { c_comp++; WORDF(G_DIR, 3) = u01(re.y); st = (st & clr) | (P_COMPTON << (4 * j)); }
+            // photoelectric (:651-655) | coherent: no deflection (:656-695), or an angle from the form factor | Compton --
+            // selects, not branches: the lanes of a visit take all three
+            const bool is_pe = u_sel <= tb.y, is_coh = !is_pe & (u_sel <= tb.z), is_com = !is_pe & !is_coh;
+            c_abs += is_pe ? 1u : 0u; c_coh += is_coh ? 1u : 0u; c_comp += is_com ? 1u : 0u;
+            if (RECORD && is_pe) { P.fates[WORD(G_REC, 0)] = 3u | ((uint32_t)(nint + 1) << 28); P.fate_e[WORD(G_REC, 0)] = pos.w; }
+            WORDF(G_DIR, 3) = u01(re.y);                              // the azimuthal variate of a deflection (read by COMPTON only)
+            if (RAYLEIGH && is_coh) WORD(G_ID, 1) = meta | 0x10000u;
+            const uint32_t next = is_pe ? P_REFILL : (is_com || (RAYLEIGH && is_coh)) ? P_COMPTON : P_STEP;
+            st = (st & clr) | (next << (4 * j));
 
         } while (0);
 
@@ -435,12 +432,11 @@ mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
             //   d' = cos_t d + sin_t (cos phi e1 + sin phi e2),
             //   e1 = (cos th_a cos ph_a, cos th_a sin ph_a, -sin th_a), e2 = (-sin ph_a, cos ph_a, 0).
             const float st2 = dx * dx + dy * dy;
-            float e1x, e1y, e1z, e2x, e2y;
-            if (st2 > 1e-12f) {
-                const float ist = rsqrtf(st2), sta = st2 * ist;
-                e1x = dx * dz * ist; e1y = dy * dz * ist; e1z = -sta;
-                e2x = -dy * ist; e2y = dx * ist;
-            } else { e1x = dz; e1y = 0.f; e1z = 0.f; e2x = 0.f; e2y = 1.f; }
+            // (selects: a flight along +-z takes e1 = (dz, 0, 0), e2 = (0, 1, 0))
+            const bool tilted = st2 > 1e-12f;
+            const float ist = rsqrtf(tilted ? st2 : 1.0f), sta = st2 * ist;
+            const float e1x = tilted ? dx * dz * ist : dz, e1y = tilted ? dy * dz * ist : 0.f, e1z = tilted ? -sta : 0.f;
+            const float e2x = tilted ? -dy * ist : 0.f, e2y = tilted ? dx * ist : 1.f;
             const float a = sin_t * cphi, b = sin_t * sphi;
             const float nxd = cos_t * dx + a * e1x + b * e2x;
             const float nyd = cos_t * dy + a * e1y + b * e2y;
