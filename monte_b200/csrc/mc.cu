@@ -155,7 +155,7 @@ __device__ __forceinline__ float ray_interp(const float *xs, const float *ys, in
 // at the clearance radius.  Same collision-site distribution as the reference's loop, far fewer virtual
 // collisions when a dense insert sets the global majorant (C4: 23 -> ~5 steps per history).
 // RING = true: monte_mc_geom.detector_shape == MONTE_MC_DETECTOR_RING: source at the origin, detector bins on a
-// cylinder about the z axis.  Its own instantiation: the flat-panel kernels carry none of it.
+// cylinder about the z axis.  Its own instantiations (with and without RAYLEIGH / CLEAR): the flat-panel kernels carry none of it.
 template <bool RECORD, int K, int MINB = 3, int NSTEP = 2, bool RAYLEIGH = false, bool CLEAR = false, bool RING = false>
 __global__ void __launch_bounds__(MC_THREADS, MINB)
 mc_transport_kernel_v3(const __grid_constant__ McLaunch P) {
@@ -1226,8 +1226,7 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     const int rec = d_fates ? 1 : 0;
     const bool rayleigh = s->ray_n > 0;      // form-factor deflection of coherent events: its own instantiation (K = 5)
     const bool clear = s->heavy >= 0;        // two-level majorant: its own instantiations too
-    const bool ring = s->dev.ring != 0;      // ring detector: its own instantiations (reference tracking loop and coherent event only)
-    MONTE_ARG(!ring || (!rayleigh && !clear), "mc: detector_shape RING is not available together with coherent_mode FORMFACTOR or a clearance tracking mode");
+    const bool ring = s->dev.ring != 0;      // ring detector: its own instantiations
     const int which = rayleigh || clear || ring ? 35 : which_env;
     const int K = which >= 31 && which <= 36 ? which - 30 : (which == 44 ? 4 : (which == 43 ? 3 : 5));
     const size_t slot_bytes = (size_t)K * 32 * mc_slot_groups(rec != 0) * sizeof(uint4) * (MC_THREADS / 32) +
@@ -1239,9 +1238,15 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     L.off_slots = L.off_invlo + (clear ? 2u * (TAB_ROWS + 3) * (uint32_t)sizeof(float) : 0u);
     const size_t smem = (size_t)L.off_slots + slot_bytes;
     const void *fn = nullptr;
-    switch (ring ? 210 + rec : rayleigh || clear ? 200 + rec + (clear ? 2 : 0) + (rayleigh && clear ? 2 : 0) : which * 2 + rec) {
+    switch (ring ? 210 + rec + (clear ? 2 : 0) + (rayleigh ? 4 : 0) : rayleigh || clear ? 200 + rec + (clear ? 2 : 0) + (rayleigh && clear ? 2 : 0) : which * 2 + rec) {
         case 210: fn = (const void *)mc_transport_kernel_v3<false, 5, 3, 2, false, false, true>; break;
         case 211: fn = (const void *)mc_transport_kernel_v3<true, 5, 3, 2, false, false, true>; break;
+        case 212: fn = (const void *)mc_transport_kernel_v3<false, 5, 3, 2, false, true, true>; break;
+        case 213: fn = (const void *)mc_transport_kernel_v3<true, 5, 3, 2, false, true, true>; break;
+        case 214: fn = (const void *)mc_transport_kernel_v3<false, 5, 3, 2, true, false, true>; break;
+        case 215: fn = (const void *)mc_transport_kernel_v3<true, 5, 3, 2, true, false, true>; break;
+        case 216: fn = (const void *)mc_transport_kernel_v3<false, 5, 3, 2, true, true, true>; break;
+        case 217: fn = (const void *)mc_transport_kernel_v3<true, 5, 3, 2, true, true, true>; break;
         case 200: fn = (const void *)mc_transport_kernel_v3<false, 5, 3, 2, true>; break;
         case 201: fn = (const void *)mc_transport_kernel_v3<true, 5, 3, 2, true>; break;
         case 202: fn = (const void *)mc_transport_kernel_v3<false, 5, 3, 2, false, true>; break;
@@ -1273,8 +1278,8 @@ static int launch_mc(const monte_mc_scene *s, uint64_t seed, int view_begin, int
     at_shutdown([] { attr_pd.get() = Attr(); });
     int *occ = attr_pd.get().occ;
     size_t *smem_set = attr_pd.get().smem_set, *smem_occ = attr_pd.get().smem_occ;
-    // 94, 95 (Rayleigh), 0..3 (clearance, clearance + Rayleigh), 4, 5 (ring detector): no `which` maps there (31..46 -> 62..93)
-    const int slot_id = ring ? 4 + rec : clear ? rec + (rayleigh ? 2 : 0) : rayleigh ? 94 + rec : (which * 2 + rec) % 96;
+    // 94, 95 (Rayleigh), 0..3 (clearance, clearance + Rayleigh), 4..11 (ring detector): no `which` maps there (31..46 -> 62..93)
+    const int slot_id = ring ? 4 + rec + (clear ? 2 : 0) + (rayleigh ? 4 : 0) : clear ? rec + (rayleigh ? 2 : 0) : rayleigh ? 94 + rec : (which * 2 + rec) % 96;
     int &oc = occ[slot_id];
     MONTE_ARG(smem <= 227 * 1024, "mc: %zu bytes of shared memory needed (> 227 KB)", smem);
     if (smem > smem_set[slot_id]) {

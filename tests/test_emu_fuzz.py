@@ -88,13 +88,11 @@ def _mc_case(rng):
     if vol.majorant_mode and len(mats) > 1 and rng.integers(0, 2):
         lab[lab == 2] = 1
     # a quarter of the cases on the ring detector (source at the origin, ny angular x nx axial bins on a
-    # cylinder around the clip box; its kernel instantiation has the reference's tracking loop and coherent event only)
+    # cylinder around the clip box), with whatever tracking and coherent mode the case drew
     if rng.integers(0, 4) == 0:
         g.detector_shape = _abi.DETECTOR_RING
         corner = math.hypot(max(abs(vol.clip_lo[0]), abs(vol.clip_hi[0])), max(abs(vol.clip_lo[1]), abs(vol.clip_hi[1])))
         g.ring_radius = corner * float(rng.uniform(1.05, 2.0))
-        g.coherent_mode = _abi.COHERENT_FORWARD
-        vol.tracking_mode = _abi.TRACK_GLOBAL
     return g, vol, lab, xs, spec, keep
 
 

@@ -461,6 +461,14 @@ def test_ring_detector_coupled_with_oracle(monte, oracle):
     with pytest.raises(Exception, match="inside the detector ring"):
         monte.simulate(g, vol, lab, xs, spec, per, seed)
     g.ring_radius = 20.0
-    vol.tracking_mode, vol.clearance_cell_log2 = _abi.TRACK_CLEARANCE, 1
-    with pytest.raises(Exception, match="RING is not available"):
-        monte.simulate(g, vol, lab, xs, spec, per, seed)
+    # the two-level majorant and the form-factor deflection on the ring detector (their own kernel instantiations)
+    vol.tracking_mode, vol.clearance_cell_log2 = _abi.TRACK_DIRECTIONAL, 1
+    g.coherent_mode = _abi.COHERENT_FORMFACTOR
+    xf = scenes.add_formfactors(scenes.make_xs())
+    sc = monte.Scene(g, vol, lab, xf, spec)
+    f_gpu, e_gpu = sc.fates(0, per, seed)
+    sc.close()
+    grid, heavy = monte.clearance_grid(vol, lab, xf)
+    opts, _keep = oracle.with_clearance(oracle.mc_opts(oracle.RNG_PHILOX, seed=seed), grid, heavy)
+    _, _, res, f_cpu, e_cpu = oracle.mc_run(g, vol, lab, oracle.tables_from_xs(xf), spec, opts, per, views=(0, 1), want_fates=True)
+    assert (f_gpu == f_cpu).mean() > 0.999
