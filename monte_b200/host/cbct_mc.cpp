@@ -6,6 +6,8 @@
 // of monte_hu_classes_default (density bins of water, water + calcium for bone; the role ctnum_to_mu.cpp:55-82 hints at)
 // and tracked with the majorant of the classes that occur (monte_mc_volume.majorant_mode = MONTE_MC_MAJORANT_PRESENT).
 // --kev E: source energy (default 140, CBCT_real325im.cu as shipped).
+// --ring R: the ring detector of the 2-D programs (monte_cpp/circle3_2.cpp) instead of the flat panel: source at the origin,
+// `det` angular bins around the z axis at radius R cm, one axial bin of height `pixel` (images are [views][det][1]).
 // --gpus G (1..8): the photons of every pixel are split over G devices inside libmonte_gpu and the tallies summed on
 // device 0 (monte_gpu_init(G, NULL)); the output files are byte-identical to --gpus 1.
 // rayleigh=1 (not in the reference): coherent events are deflected by the analytic form factor of
@@ -31,12 +33,12 @@ static void write_raw(const std::string &fn, const void *p, size_t bytes) {
 int main(int argc, char **argv) {
     int gpus = 1;
     bool hu_input = false;
-    double kev = 140.0;
+    double kev = 140.0, ring_r = 0.0;
     for (int i = 1; i < argc;) {
         if (!strcmp(argv[i], "--hu")) { hu_input = true; for (int j = i; j + 1 < argc; j++) argv[j] = argv[j + 1]; argc -= 1; continue; }
-        const bool gp = !strcmp(argv[i], "--gpus"), ke = !strcmp(argv[i], "--kev");
-        if ((gp || ke) && i + 1 < argc) {
-            if (gp) gpus = atoi(argv[i + 1]); else kev = atof(argv[i + 1]);
+        const bool gp = !strcmp(argv[i], "--gpus"), ke = !strcmp(argv[i], "--kev"), rg = !strcmp(argv[i], "--ring");
+        if ((gp || ke || rg) && i + 1 < argc) {
+            if (gp) gpus = atoi(argv[i + 1]); else if (ke) kev = atof(argv[i + 1]); else ring_r = atof(argv[i + 1]);
             for (int j = i; j + 2 < argc; j++) argv[j] = argv[j + 2];
             argc -= 2;
             continue;
@@ -74,6 +76,8 @@ int main(int argc, char **argv) {
     g.n_views = views; g.angle0_deg = 0; g.angle_step_deg = 360.0 / views;
     g.ny = g.nx = det; g.pixel = pixel; g.half = 0.5 * det * pixel; g.dso = 160; g.dod = 60;   // :459
     g.source_mode = MONTE_MC_SOURCE_PENCIL; g.max_scatter = 5;                                    // :7
+    const int det_x = ring_r > 0 ? 1 : det;                                                       // ring: one axial bin
+    if (ring_r > 0) { g.detector_shape = MONTE_MC_DETECTOR_RING; g.ring_radius = ring_r; g.nx = 1; g.half = 0.5 * pixel; }
     if (rayleigh) {
         for (int m = 0; m < xs->n_materials; m++)               // (segmented volumes: water-like classes 1.0, calcium-loaded 1.3)
             if (monte_xs_formfactor_hydrogenic(xs.get(), m, hu_input ? (m < 4 ? 1.0 : 1.3) : (m == 0 ? 1.0 : 2.2))) return fail();
@@ -86,7 +90,7 @@ int main(int argc, char **argv) {
     if (hu_input) v.majorant_mode = MONTE_MC_MAJORANT_PRESENT;
     monte_mc_spectrum sp = {0, 0.5, kev, nullptr};                                                // as shipped: 140 keV
     if (monte_gpu_init(gpus, nullptr)) return fail();
-    const size_t n_img = (size_t)views * det * det;
+    const size_t n_img = (size_t)views * det * det_x;
     std::vector<int32_t> im0(n_img), im5(n_img);
     std::vector<float> map0(n_img), map5(n_img);
     monte_mc_stats st;

@@ -319,6 +319,16 @@ def test_emu_cbct_mc_driver_end_to_end(monte_emu, tmp_path):
     vol.majorant_mode = _abi.MAJORANT_PRESENT
     r0, r5, _ = monte_emu.simulate(g, vol, lab_h, xs_h, scenes.mono_spectrum(60.0), 40, 3)
     assert np.array_equal(r0, p0) and np.array_equal(r5, p5) and 0 < p0.sum() < 2 * 81 * 40
+    # --ring R: the ring detector (source at the origin, 12 angular bins, one axial bin)
+    out = subprocess.run([exe, "cyl.raw", "33", "1.0", "xcom2.csv", "Ca.csv", "12", "2.0", "1", "50", "3", "r", "--ring", "25"],
+                         cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout.decode()
+    p0 = np.fromfile(os.path.join(d, "proj_r0.raw"), np.int32).reshape(1, 12, 1)
+    p5 = np.fromfile(os.path.join(d, "proj_r5.raw"), np.int32).reshape(1, 12, 1)
+    g = scenes.ring_geom(12, 1, 2.0, 25.0)
+    g.angle_step_deg = 360.0
+    vol = scenes.volume_for(lab, 1.0, tight=False)
+    r0, r5, _ = monte_emu.simulate(g, vol, lab, scenes.make_xs(quirk_bom=True), scenes.mono_spectrum(140.0), 50, 3)
+    assert np.array_equal(r0, p0) and np.array_equal(r5, p5) and 0 < p0.sum() < 12 * 50
 
 
 @pytest.mark.parametrize("cell_log2,poly,rayleigh", [(0, True, False), (1, False, False), (1, True, True)])
